@@ -1,0 +1,211 @@
+"""Generate the golden vectors under tests/golden/ from the SECOND SOURCE.
+
+The reference (perazz/fitpack) is Fortran and cannot be compiled in the build
+container (no Fortran compiler), so its own binary cannot produce fixtures.
+scipy.interpolate._fitpack is a C translation of the same Dierckx/netlib
+algorithms; on inputs where the reference does not deliberately deviate from
+netlib (fpknot seeding on all-zero/NaN residuals, zero-pivot
+skip, subnormal pivots, main-loop trip count) the two must agree bit for bit.
+This script records scipy's answers; tests/test_oracle_golden.py checks the
+oracle against them, and the GPU tests check the CUDA path against both.
+
+Run here (needs scipy):  python tests/golden/make_golden.py
+Outputs: curfit_golden.npz, splev_golden.npz, mncurf_golden.npz
+"""
+import os
+
+import numpy as np
+from scipy.interpolate import _fitpack
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+MNCURF_Y = np.array([1.0, 1.0, 1.4, 1.1, 1.0, 1.0, 4.0, 9.0, 13.0, 13.4, 12.8, 13.1, 13.0, 14.0,
+                     13.0, 13.5, 10.0, 2.0, 3.0, 2.5, 2.5, 2.5, 3.0, 4.0, 3.5])
+
+
+def lwrk_min(m, k, nest):
+    return m * (k + 1) + nest * (7 + 3 * k)
+
+
+def scipy_curfit(iopt, x, y, w, xb, xe, k, s, nest, t_in=None):
+    m = x.size
+    t = np.zeros(nest) if t_in is None else t_in.copy()
+    n, t, c, fp, ier = _fitpack.curfit(iopt, x, y, w, xb, xe, k, s, t,
+                                       np.zeros(lwrk_min(m, k, t.size)),
+                                       np.zeros(t.size, np.int32))
+    return int(n), np.asarray(t), np.asarray(c), float(fp), int(ier)
+
+
+def synth_curves(rng, B, m, sigma=0.1):
+    """C2-style synthetic batch: jittered abscissae, noisy sinusoid."""
+    u = rng.uniform(-1, 1, (B, m))
+    x = (np.arange(m)[None, :] + 0.3 * u) / (m - 1)
+    x[:, 0] = 0.0
+    x[:, -1] = 1.0
+    A = rng.uniform(0.5, 2, (B, 1))
+    f = rng.uniform(1, 4, (B, 1))
+    ph = rng.uniform(0, 2 * np.pi, (B, 1))
+    y = A * np.sin(2 * np.pi * f * x + ph) + sigma * rng.standard_normal((B, m))
+    return x, y
+
+
+def make_mncurf():
+    """reference test mncurf (test/fitpack_tests.f90:1138-1269), the steps scipy can replay:
+    iopt=0 and iopt=-1 calls, plus iopt=1 continuations that add no knots."""
+    x = np.arange(25.0)
+    w = np.ones(25)
+    out = {}
+    for k in (3, 5):
+        for s in (1000.0, 60.0, 10.0, 30.0, 0.0):
+            n, t, c, fp, ier = scipy_curfit(0, x, MNCURF_Y, w, 0.0, 24.0, k, s, 35)
+            key = f"k{k}_s{int(s)}"
+            out[key + "_n"] = n
+            out[key + "_t"] = t[:n]
+            out[key + "_c"] = c[:n]
+            out[key + "_fp"] = fp
+            out[key + "_ier"] = ier
+            y, ier2 = _fitpack.splev(t[:n], c[:n], k, x, 0)
+            out[key + "_sp"] = np.asarray(y)
+        tin = np.zeros(9 + 2 * k)
+        tin[k + 1:k + 8] = 3.0 * np.arange(1, 8)
+        n, t, c, fp, ier = scipy_curfit(-1, x, MNCURF_Y, w, 0.0, 24.0, k, 0.0, tin.size, tin)
+        key = f"k{k}_lsq"
+        out[key + "_n"] = n
+        out[key + "_t"] = t[:n]
+        out[key + "_c"] = c[:n]
+        out[key + "_fp"] = fp
+        out[key + "_ier"] = ier
+        # iopt=1 continuation without knot growth: s=10 fresh, then s=30 on the same knots
+        t0 = np.zeros(35)
+        wrk = np.zeros(lwrk_min(25, k, 35))
+        iwrk = np.zeros(35, np.int32)
+        n, t, c, fp, ier = _fitpack.curfit(0, x, MNCURF_Y, w, 0.0, 24.0, k, 10.0, t0, wrk, iwrk)
+        tt = np.asarray(t)[:n].copy()
+        n3, t3, c3, fp3, ier3 = _fitpack.curfit(1, x, MNCURF_Y, w, 0.0, 24.0, k, 30.0, tt, wrk, iwrk)
+        key = f"k{k}_cont30"
+        out[key + "_n"] = int(n3)
+        out[key + "_t"] = np.asarray(t3)[:n3]
+        out[key + "_c"] = np.asarray(c3)[:n3]
+        out[key + "_fp"] = float(fp3)
+        out[key + "_ier"] = int(ier3)
+    out["x"] = x
+    out["y"] = MNCURF_Y
+    np.savez_compressed(os.path.join(HERE, "mncurf_golden.npz"), **out)
+
+
+def make_curfit():
+    rng = np.random.default_rng(20261019)
+    cases = []
+    # (a) random mixed cases, all degrees, several s regimes, weights, wider [xb,xe]
+    for trial in range(160):
+        k = int(rng.integers(1, 6))
+        m = int(rng.integers(k + 2, 200))
+        x = np.sort(rng.uniform(0, 1, m))
+        if rng.random() < 0.3:
+            x = np.linspace(0, 1, m)
+        x = np.unique(x)
+        m = x.size
+        if m < k + 2:
+            continue
+        f = rng.uniform(1, 4)
+        y = rng.uniform(.5, 2) * np.sin(2 * np.pi * f * x + rng.uniform(0, 6)) \
+            + 0.1 * rng.standard_normal(m)
+        w = np.ones(m) if rng.random() < 0.5 else rng.uniform(0.5, 2, m)
+        s = float(rng.choice([0.0, m * 0.01, m * 0.001, m * 0.1, 1e-6, 1e-12, 1000.0]))
+        nest = int(rng.choice([m + k + 1, max(2 * k + 2, m // 4), max(2 * k + 3, m // 2)]))
+        xb, xe = x[0], x[-1]
+        if rng.random() < 0.2:
+            xb -= 0.1
+            xe += 0.05
+        cases.append((k, x, y, w, xb, xe, s, nest))
+    # (b) C2-shaped: m=256, k=3, s=m*sigma^2, nest=359
+    xs, ys = synth_curves(rng, 48, 256)
+    for b in range(48):
+        cases.append((3, xs[b], ys[b], np.ones(256), 0.0, 1.0, 2.56, 359))
+    # (c) C5-shaped source fits: k=5
+    xs, ys = synth_curves(rng, 16, 256)
+    for b in range(16):
+        cases.append((5, xs[b], ys[b], np.ones(256), 0.0, 1.0, 2.56, 359))
+
+    rec = dict(k=[], m=[], s=[], nest=[], xb=[], xe=[], n=[], fp=[], ier=[], off=[], toff=[])
+    xcat, ycat, wcat, tcat, ccat = [], [], [], [], []
+    off = toff = 0
+    for (k, x, y, w, xb, xe, s, nest) in cases:
+        n, t, c, fp, ier = scipy_curfit(0, x, y, w, xb, xe, k, s, nest)
+        if not np.isfinite(fp):
+            continue
+        if ier == 10:
+            n = 0
+        rec["k"].append(k); rec["m"].append(x.size); rec["s"].append(s); rec["nest"].append(nest)
+        rec["xb"].append(xb); rec["xe"].append(xe); rec["n"].append(n); rec["fp"].append(fp)
+        rec["ier"].append(ier); rec["off"].append(off); rec["toff"].append(toff)
+        xcat.append(x); ycat.append(y); wcat.append(w)
+        tcat.append(t[:n]); ccat.append(c[:n])
+        off += x.size
+        toff += n
+    np.savez_compressed(
+        os.path.join(HERE, "curfit_golden.npz"),
+        k=np.array(rec["k"], np.int32), m=np.array(rec["m"], np.int32), s=np.array(rec["s"]),
+        nest=np.array(rec["nest"], np.int32), xb=np.array(rec["xb"]), xe=np.array(rec["xe"]),
+        n=np.array(rec["n"], np.int32), fp=np.array(rec["fp"]), ier=np.array(rec["ier"], np.int32),
+        off=np.array(rec["off"], np.int64), toff=np.array(rec["toff"], np.int64),
+        x=np.concatenate(xcat), y=np.concatenate(ycat), w=np.concatenate(wcat),
+        t=np.concatenate(tcat), c=np.concatenate(ccat))
+    print("curfit cases:", len(rec["k"]), "ier histogram:",
+          {int(v): int((np.array(rec["ier"]) == v).sum()) for v in np.unique(rec["ier"])})
+
+
+def make_splev():
+    rng = np.random.default_rng(777)
+    out = {}
+    # mnspev (test/fitpack_tests.f90:3592-3667) with the netlib knot placement
+    # (interior knots at t(k+2..k+5)); every entry of t defined.
+    xs = 0.05 * np.arange(21)
+    for k in range(1, 6):
+        k1 = k + 1
+        n = 2 * k1 + 4
+        t = np.zeros(n)
+        t[n - k1:] = 1.0
+        t[k1:k1 + 4] = [0.1, 0.3, 0.4, 0.8]
+        nk1 = n - k1
+        c = np.zeros(n)
+        c[:nk1] = [0.01 * i * (i - 5) for i in range(1, nk1 + 1)]
+        y, ier = _fitpack.splev(t, c, k, xs, 0)
+        out[f"mnspev_k{k}_t"] = t
+        out[f"mnspev_k{k}_c"] = c
+        out[f"mnspev_k{k}_y"] = np.asarray(y)
+    out["mnspev_x"] = xs
+    # random splines, all degrees, all out-of-support policies, unsorted x incl. outside points
+    idx = 0
+    for k in range(1, 6):
+        for trial in range(6):
+            nint = int(rng.integers(0, 30))
+            interior = np.sort(rng.uniform(0, 1, nint))
+            if trial == 5 and nint > 3:
+                interior[2] = interior[1]  # a double interior knot
+            t = np.concatenate([np.zeros(k + 1), interior, np.ones(k + 1)])
+            n = t.size
+            c = np.zeros(n)
+            c[:n - k - 1] = rng.standard_normal(n - k - 1)
+            x = rng.uniform(-0.2, 1.2, 257)
+            x[:4] = [0.0, 1.0, -0.2, 1.2]
+            if nint:
+                x[4] = interior[0]
+            for e in (0, 1, 3):
+                y, ier = _fitpack.splev(t, c, k, x, e)
+                out[f"r{idx}_y_e{e}"] = np.asarray(y)
+            out[f"r{idx}_t"] = t
+            out[f"r{idx}_c"] = c
+            out[f"r{idx}_x"] = x
+            out[f"r{idx}_k"] = k
+            idx += 1
+    out["nrandom"] = idx
+    np.savez_compressed(os.path.join(HERE, "splev_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    make_mncurf()
+    make_curfit()
+    make_splev()
+    for f in ("mncurf_golden.npz", "curfit_golden.npz", "splev_golden.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

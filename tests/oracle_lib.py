@@ -1,0 +1,192 @@
+"""ctypes binding of the CPU oracle (oracle/libfitpack_oracle.so).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(fitpack_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB_PATH = os.path.join(ORACLE_DIR, "libfitpack_oracle.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class OrcStats(C.Structure):
+    _fields_ = [("lsq_passes", C.c_int32), ("p_iters", C.c_int32), ("rotations", C.c_int64)]
+
+
+STATS_DTYPE = np.dtype([("lsq_passes", np.int32), ("p_iters", np.int32), ("rotations", np.int64)])
+
+
+def build_oracle(force=False):
+    src = os.path.join(ORACLE_DIR, "fitpack_oracle.c")
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-B", "libfitpack_oracle.so"],
+                          stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_curfit_stats.restype = None
+        _lib.orc_splev_idx.restype = None
+        _lib.orc_fpchec.restype = C.c_int32
+        _lib.orc_equal.restype = C.c_int32
+        _lib.orc_equal.argtypes = [C.c_double, C.c_double]
+        _lib.orc_knot_interval.restype = C.c_int32
+        _lib.orc_message.restype = C.c_char_p
+        _lib.orc_max_threads.restype = C.c_int32
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def lwrk_min(m, k, nest):
+    return m * (k + 1) + nest * (7 + 3 * k)
+
+
+def curfit(iopt, x, y, w, xb, xe, k, s, nest, n=0, t=None, wrk=None, iwrk=None, lwrk=None,
+           c=None, fp=0.0):
+    """orc_curfit with the reference's argument list (core:1240).
+
+    Returns dict(n,t,c,fp,ier,wrk,iwrk,stats); t/c/wrk/iwrk are the (updated)
+    arrays so that an iopt=1 continuation can pass them back in.
+    """
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    m = x.size
+    w = np.ones(m) if w is None else np.ascontiguousarray(w, dtype=np.float64)
+    if lwrk is None:
+        lwrk = max(lwrk_min(m, k, nest), 1) if wrk is None else wrk.size
+    t = np.zeros(max(nest, 1)) if t is None else np.ascontiguousarray(t, dtype=np.float64)
+    c = np.zeros(max(nest, 1)) if c is None else np.ascontiguousarray(c, dtype=np.float64)
+    wrk = np.zeros(max(lwrk, 1)) if wrk is None else wrk
+    iwrk = np.zeros(max(nest, 1), dtype=np.int32) if iwrk is None else iwrk
+    n_ = C.c_int32(int(n))
+    fp_ = C.c_double(float(fp))
+    ier_ = C.c_int32(0)
+    st = OrcStats()
+    lib().orc_curfit_stats(C.c_int32(iopt), C.c_int32(m), _d(x), _d(y), _d(w), C.c_double(xb),
+                           C.c_double(xe), C.c_int32(k), C.c_double(s), C.c_int32(nest),
+                           C.byref(n_), _d(t), _d(c), C.byref(fp_), _d(wrk), C.c_int32(lwrk),
+                           _i(iwrk), C.byref(ier_), C.byref(st))
+    return dict(n=n_.value, t=t, c=c, fp=fp_.value, ier=ier_.value, wrk=wrk, iwrk=iwrk,
+                stats=(st.lsq_passes, st.p_iters, st.rotations))
+
+
+def splev(t, n, c, k, x, e=0, want_idx=False):
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    m = x.size
+    y = np.zeros(max(m, 1))
+    idx = np.zeros(max(m, 1), dtype=np.int32)
+    ier = C.c_int32(0)
+    lib().orc_splev_idx(_d(t), C.c_int32(n), _d(c), C.c_int32(k), _d(x), _d(y), _i(idx),
+                        C.c_int32(m), C.c_int32(e), C.byref(ier))
+    if want_idx:
+        return y[:m], ier.value, idx[:m]
+    return y[:m], ier.value
+
+
+def fpchec(x, t, n, k):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    return lib().orc_fpchec(_d(x), C.c_int32(x.size), _d(t), C.c_int32(n), C.c_int32(k))
+
+
+def fpbspl(t, n, k, x, l):
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    h = np.zeros(20)
+    lib().orc_fpbspl(_d(t), C.c_int32(n), C.c_int32(k), C.c_double(x), C.c_int32(l), _d(h))
+    return h[:k + 1]
+
+
+def knot_interval(t, x, l_start, l_max):
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    return lib().orc_knot_interval(_d(t), C.c_double(x), C.c_int32(l_start), C.c_int32(l_max))
+
+
+def equal(a, b):
+    return bool(lib().orc_equal(a, b))
+
+
+def argsort(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    il = np.zeros(max(x.size, 1), dtype=np.int32)
+    lib().orc_argsort(_d(x), C.c_int32(x.size), _i(il))
+    return il[:x.size]
+
+
+def message(ier):
+    return lib().orc_message(C.c_int32(ier)).decode()
+
+
+def max_threads():
+    return lib().orc_max_threads()
+
+
+def curfit_batch(iopt, x, y, w, k, s, nest, xb=None, xe=None, shared_x=False, n=None, t=None,
+                 nthreads=0, want_stats=False):
+    """OpenMP-over-curves driver.  y is [B][m]; x,w are [B][m] or [m] if shared_x."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    B, m = y.shape
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    wp = None
+    if w is not None:
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        wp = _d(w)
+    n_arr = np.zeros(B, dtype=np.int32) if n is None else np.ascontiguousarray(n, dtype=np.int32)
+    t_arr = np.zeros((B, nest)) if t is None else np.ascontiguousarray(t, dtype=np.float64)
+    c_arr = np.zeros((B, nest))
+    fp = np.zeros(B)
+    ier = np.zeros(B, dtype=np.int32)
+    stats = np.zeros(B, dtype=STATS_DTYPE) if want_stats else None
+    use_range = xb is None
+    lib().orc_curfit_batch(C.c_int32(B), C.c_int32(iopt), C.c_int32(m), _d(x), _d(y), wp,
+                           C.c_int32(1 if shared_x else 0),
+                           C.c_double(0.0 if xb is None else xb),
+                           C.c_double(0.0 if xe is None else xe), C.c_int32(1 if use_range else 0),
+                           C.c_int32(k), C.c_double(s), C.c_int32(nest), _i(n_arr), _d(t_arr),
+                           _d(c_arr), _d(fp), _i(ier),
+                           stats.ctypes.data_as(C.c_void_p) if want_stats else None,
+                           C.c_int32(nthreads))
+    out = dict(n=n_arr, t=t_arr, c=c_arr, fp=fp, ier=ier)
+    if want_stats:
+        out["stats"] = stats
+    return out
+
+
+def splev_batch(t, n, c, k, x, e=0, nthreads=0):
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    nspl, ldt = t.shape
+    m = x.shape[1]
+    y = np.zeros_like(x)
+    ier = np.zeros(nspl, dtype=np.int32)
+    lib().orc_splev_batch(C.c_int32(nspl), _d(t), _i(n), _d(c), C.c_int32(ldt), C.c_int32(k),
+                          _d(x), _d(y), C.c_int32(m), C.c_int32(e), _i(ier), C.c_int32(nthreads))
+    return y, ier

@@ -1,0 +1,247 @@
+"""CPU: the oracle against the committed golden vectors (second source: scipy's C
+translation of netlib FITPACK, tests/golden/make_golden.py) and against every
+assertion the reference's own tests make for this path."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from refdata import FPKNOT_X, FPKNOT_Y, MNCURF_STEPS, MNCURF_X, MNCURF_Y
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_equal_semantics():
+    # core:18644-18647 : exact equality for normal numbers, |x|<tiny against zero
+    tiny = np.finfo(float).tiny
+    assert O.equal(1.0, 1.0)
+    assert not O.equal(1.0, np.nextafter(1.0, 2.0))
+    assert not O.equal(1.0, np.nextafter(1.0, 0.0))
+    assert O.equal(0.0, 0.0)
+    assert O.equal(tiny / 2, 0.0)
+    assert not O.equal(tiny, 0.0)
+    assert O.equal(-tiny / 4, 0.0)
+    rng = np.random.default_rng(1)
+    for _ in range(2000):
+        a = rng.standard_normal() * 10.0 ** rng.integers(-300, 300)
+        b = np.nextafter(a, np.inf) if rng.random() < 0.5 else a
+        assert O.equal(a, b) == (abs(a - b) < tiny)
+
+
+def test_knot_interval_equals_linear_walk():
+    # core:2432-2473 : hybrid search == plain linear walk for non-decreasing knots
+    rng = np.random.default_rng(2)
+    for _ in range(300):
+        n = int(rng.integers(8, 60))
+        t = np.sort(rng.uniform(0, 1, n))
+        if rng.random() < 0.3:
+            t[3] = t[4]
+        l0 = int(rng.integers(1, n // 2))
+        lmax = int(rng.integers(l0, n))
+        x = rng.uniform(-0.1, 1.1)
+        l = l0
+        while l < lmax and x >= t[l]:
+            l += 1
+        assert O.knot_interval(t, x, l0, lmax) == l
+
+
+def test_curfit_golden_bit_exact():
+    g = np.load(os.path.join(G, "curfit_golden.npz"))
+    ncase = g["k"].size
+    assert ncase > 200
+    for i in range(ncase):
+        k, m, nest = int(g["k"][i]), int(g["m"][i]), int(g["nest"][i])
+        o = int(g["off"][i])
+        x, y, w = g["x"][o:o + m], g["y"][o:o + m], g["w"][o:o + m]
+        r = O.curfit(0, x, y, w, float(g["xb"][i]), float(g["xe"][i]), k, float(g["s"][i]), nest)
+        assert r["ier"] == int(g["ier"][i]), i
+        if r["ier"] == 10:
+            continue
+        n = int(g["n"][i])
+        assert r["n"] == n, i
+        to = int(g["toff"][i])
+        assert np.array_equal(r["t"][:n], g["t"][to:to + n]), i
+        assert np.array_equal(r["c"][:n - k - 1], g["c"][to:to + n - k - 1]), i
+        assert r["fp"] == float(g["fp"][i]), i
+
+
+def test_mncurf_golden_and_reference_assertions():
+    g = np.load(os.path.join(G, "mncurf_golden.npz"))
+    x, y, w = MNCURF_X, MNCURF_Y, np.ones(25)
+    for k in (3, 5):
+        # (a) the reference's own sequence (test/fitpack_tests.f90:1173-1251): all ier<=0,
+        #     state carried through wrk/iwrk for iopt=1
+        nest, lwrk = 35, 1000
+        t = np.zeros(nest); c = np.zeros(nest); wrk = np.zeros(lwrk); iwrk = np.zeros(nest, np.int32)
+        n = 0
+        seq = {}
+        for step, (iopt, s) in enumerate(MNCURF_STEPS, 1):
+            if iopt == -1:
+                t[k + 1:k + 8] = 3.0 * np.arange(1, 8)
+                n = 9 + 2 * k
+            r = O.curfit(iopt, x, y, w, 0.0, 24.0, k, s, nest, n=n, t=t, c=c, wrk=wrk, iwrk=iwrk,
+                         lwrk=lwrk)
+            n = r["n"]
+            assert O.lib().orc_success(r["ier"]), (k, step)
+            sp, ier = O.splev(t, n, c, k, x, e=0)
+            assert ier == 0
+            seq[step] = (n, t[:n].copy(), c[:n].copy(), r["fp"], r["ier"], sp.copy())
+        # (b) steps scipy can replay exactly
+        for step, key in ((1, "s1000"), (5, "s30"), (6, "s0"), (7, "lsq")):
+            n, tt, cc, fp, ier, sp = seq[step]
+            assert n == int(g[f"k{k}_{key}_n"]) and ier == int(g[f"k{k}_{key}_ier"])
+            assert np.array_equal(tt, g[f"k{k}_{key}_t"])
+            assert np.array_equal(cc[:n - k - 1], g[f"k{k}_{key}_c"][:n - k - 1])
+            assert fp == float(g[f"k{k}_{key}_fp"])
+            if key != "lsq":
+                assert np.array_equal(sp, g[f"k{k}_{key}_sp"])
+        # step 2 (iopt=1 right after the polynomial) equals a fresh s=60 fit
+        n, tt, cc, fp, ier, sp = seq[2]
+        assert n == int(g[f"k{k}_s60_n"]) and fp == float(g[f"k{k}_s60_fp"])
+        # (c) iopt=1 continuation on unchanged knots
+        r = O.curfit(0, x, y, w, 0.0, 24.0, k, 10.0, nest)
+        assert r["n"] == int(g[f"k{k}_s10_n"]) and r["fp"] == float(g[f"k{k}_s10_fp"])
+        r2 = O.curfit(1, x, y, w, 0.0, 24.0, k, 30.0, nest, n=r["n"], t=r["t"], wrk=r["wrk"],
+                      iwrk=r["iwrk"])
+        n = r2["n"]
+        assert n == int(g[f"k{k}_cont30_n"]) and r2["ier"] == int(g[f"k{k}_cont30_ier"])
+        assert r2["fp"] == float(g[f"k{k}_cont30_fp"])
+        assert np.array_equal(r2["c"][:n - k - 1], g[f"k{k}_cont30_c"][:n - k - 1])
+        # interpolating spline reproduces the data (ier=-1, fp=0)
+        n, tt, cc, fp, ier, sp = seq[6]
+        assert ier == -1 and fp == 0.0 and n == 25 + k + 1
+        assert np.allclose(sp, y, rtol=0, atol=1e-10)
+
+
+def test_splev_golden_bit_exact():
+    g = np.load(os.path.join(G, "splev_golden.npz"))
+    xs = g["mnspev_x"]
+    for k in range(1, 6):
+        t, c = g[f"mnspev_k{k}_t"], g[f"mnspev_k{k}_c"]
+        y, ier = O.splev(t, t.size, c, k, xs, e=0)
+        assert ier == 0
+        assert np.array_equal(y, g[f"mnspev_k{k}_y"])
+    for i in range(int(g["nrandom"])):
+        t, c, x, k = g[f"r{i}_t"], g[f"r{i}_c"], g[f"r{i}_x"], int(g[f"r{i}_k"])
+        for e in (0, 1, 3):
+            y, ier = O.splev(t, t.size, c, k, x, e=e)
+            assert ier == 0
+            assert np.array_equal(y, g[f"r{i}_y_e{e}"]), (i, e)
+        # e=2: reference returns FITPACK_INVALID_RANGE (6), core:17872 (netlib returns 1)
+        y, ier = O.splev(t, t.size, c, k, x, e=2)
+        assert ier == 6
+        y, ier = O.splev(t, t.size, c, k, np.clip(x, 0, 1), e=2)
+        assert ier == 0
+
+
+def test_splev_interval_is_history_independent():
+    # core:17880-17887: result == rightmost l in [k1,nk1] with t(l)<=arg
+    rng = np.random.default_rng(5)
+    for k in (1, 3, 5):
+        t = np.concatenate([np.zeros(k + 1), np.sort(rng.uniform(0, 1, 17)), np.ones(k + 1)])
+        n = t.size
+        c = rng.standard_normal(n)
+        x = rng.uniform(-0.1, 1.1, 400)
+        y1, _, l1 = O.splev(t, n, c, k, x, want_idx=True)
+        p = rng.permutation(400)
+        y2, _, l2 = O.splev(t, n, c, k, x[p], want_idx=True)
+        assert np.array_equal(y1[p], y2) and np.array_equal(l1[p], l2)
+        k1, nk1 = k + 1, n - k - 1
+        for xi, li in zip(x, l1):
+            cand = [l for l in range(k1, nk1 + 1) if t[l - 1] <= xi]
+            assert li == (max(cand) if cand else k1)
+
+
+def test_m_lt_1_and_input_errors():
+    t = np.array([0., 0, 0, 0, 1, 1, 1, 1]); c = np.zeros(8)
+    _, ier = O.splev(t, 8, c, 3, np.zeros(0))
+    assert ier == 10
+    x = np.linspace(0, 1, 10); y = x ** 2
+    assert O.curfit(0, x, y, None, 0, 1, 0, 1.0, 20)["ier"] == 10      # k out of range
+    assert O.curfit(0, x, y, None, 0, 1, 6, 1.0, 20)["ier"] == 10
+    assert O.curfit(2, x, y, None, 0, 1, 3, 1.0, 20)["ier"] == 10      # iopt
+    assert O.curfit(0, x[:3], y[:3], None, 0, 1, 3, 1.0, 20)["ier"] == 10  # m<k1
+    assert O.curfit(0, x, y, None, 0, 1, 3, 1.0, 7)["ier"] == 10       # nest<2k+2
+    assert O.curfit(0, x, y, None, 0.1, 1, 3, 1.0, 20)["ier"] == 10    # xb>x(1)
+    assert O.curfit(0, x, y, None, 0, 0.9, 3, 1.0, 20)["ier"] == 10    # xe<x(m)
+    assert O.curfit(0, x[::-1], y, None, 0, 1, 3, 1.0, 20)["ier"] == 10  # decreasing x
+    assert O.curfit(0, x, y, None, 0, 1, 3, -1.0, 20)["ier"] == 10     # s<0
+    assert O.curfit(0, x, y, None, 0, 1, 3, 0.0, 13)["ier"] == 10      # s=0 needs nest>=m+k1
+    assert O.curfit(0, x, y, None, 0, 1, 3, 1.0, 20, lwrk=10)["ier"] == 10  # lwrk too small
+    r = O.curfit(0, x, y, None, 0, 1, 3, 0.0, 14)
+    assert r["ier"] == -1 and r["n"] == 14
+
+
+def test_fpknot_crash_regression():
+    # test/fitpack_curve_tests.f90:61-85: new_fit(x,y,order=1) with the default smoothing
+    # trajectory 1000 -> 60 -> 30 (core:351-370), iopt 0 -> 1 -> 1, nest = max(102, ceil(1.4 m))
+    m, k = 109, 1
+    nest = max(102, int(np.ceil(np.float32(1.4) * m)))
+    lwrk = m * 6 + nest * 33
+    t = np.zeros(nest); c = np.zeros(nest); wrk = np.zeros(lwrk); iwrk = np.zeros(nest, np.int32)
+    n, iopt = 0, 0
+    for s in (1000.0, 60.0, 30.0):
+        r = O.curfit(iopt, FPKNOT_X, FPKNOT_Y, None, 0.0, 108.0, k, s, nest, n=n, t=t, c=c,
+                     wrk=wrk, iwrk=iwrk, lwrk=lwrk)
+        n = r["n"]
+        assert r["ier"] <= 0
+        iopt = 1
+    assert abs(r["fp"] - 30.0) < 30.0 * 1e-3
+
+
+def test_sine_interpolation_analytic():
+    # test/fitpack_curve_tests.f90:418-505 (value part) and test/test_curve.cpp:31-93
+    N = 201
+    x = np.linspace(0, 2 * np.pi, N)
+    y = np.sin(x)
+    nest = max(102, int(np.ceil(np.float32(1.4) * N)))
+    r = O.curfit(0, x, y, None, x[0], x[-1], 3, 0.0, nest)
+    assert r["ier"] == -1 and r["n"] == N + 4
+    xm = 0.5 * (x[:-1] + x[1:])
+    sp, ier = O.splev(r["t"], r["n"], r["c"], 3, xm, e=3)
+    assert ier == 0
+    assert np.max(np.abs(sp - np.sin(xm))) < 1e-7
+
+
+def test_self_consistency_properties():
+    # style of test/fitpack_grid_nd_tests.f90 gates: fp == recomputed SSR, knots valid,
+    # ier=0 => |fp-s| < 1e-3 s
+    from refdata import synth_curves
+    rng = np.random.default_rng(11)
+    x, y = synth_curves(rng, 40, 256)
+    for b in range(40):
+        k = 3 if b % 2 == 0 else 5
+        r = O.curfit(0, x[b], y[b], None, 0.0, 1.0, k, 2.56, 359)
+        n = r["n"]
+        assert r["ier"] in (0, -2)
+        if r["ier"] == 0:
+            assert abs(r["fp"] - 2.56) < 1e-3 * 2.56
+        else:
+            assert n == 2 * k + 2 and r["fp"] < 2.56 * (1 + 1e-3)
+        sp, _ = O.splev(r["t"], n, r["c"], k, x[b])
+        ssr = float(np.sum((y[b] - sp) ** 2))
+        assert abs(ssr - r["fp"]) <= 1e-11 * max(1.0, ssr)
+        assert O.fpchec(x[b], r["t"][:n], n, k) == 0
+
+
+def test_argsort_matches_numpy_on_distinct_values():
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 5, 8, 9, 33, 257):
+        v = rng.permutation(n).astype(float) * 0.37
+        assert np.array_equal(O.argsort(v) - 1, np.argsort(v))
+    v = np.arange(50.0)
+    assert np.array_equal(O.argsort(v), np.arange(1, 51))
+
+
+def test_batch_driver_equals_single_calls():
+    from refdata import synth_curves
+    rng = np.random.default_rng(12)
+    x, y = synth_curves(rng, 64, 128)
+    out = O.curfit_batch(0, x, y, None, 3, 1.28, 190, want_stats=True, nthreads=4)
+    for b in range(64):
+        r = O.curfit(0, x[b], y[b], None, 0.0, 1.0, 3, 1.28, 190)
+        assert out["n"][b] == r["n"] and out["ier"][b] == r["ier"] and out["fp"][b] == r["fp"]
+        assert np.array_equal(out["t"][b, :r["n"]], r["t"][:r["n"]])
+        assert np.array_equal(out["c"][b, :r["n"] - 4], r["c"][:r["n"] - 4])
+        assert tuple(out["stats"][b]) == r["stats"]
