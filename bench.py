@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric):
+curve fits/sec (256-pt, k=3) and splev GB/s, on N B200s vs the host CPU.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
+
+A "step" is one pass of the batched fit over one batch of synthetic curves
+(BASELINE config 2: 2^20 curves x 256 points per GPU, k=3, s=m*sigma^2=2.56, nest=359,
+point-major SoA resident in HBM).  N>1: one process per GPU (torchrun), every rank fits its
+own batch -- independent curves, no collective in the data path ("scaling": "weak").
+`value`   : whole-job fits/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`     : the same metric through the C-ABI host-pointer call fp_curfit_batch_c: pinned host
+            buffers, H2D + tile transpose + fit + D2H all inside the timed region.
+`splev`   : second half of the metric (BASELINE config 5 shape: 2^20 k=5 splines x 954 points per
+            GPU): GB/s at 16.5 algorithmic bytes/point, exact and fast modes, own roofline.
+`roofline`: fit kernel against measured HBM peak (it is FP64 issue/latency bound, so this
+            fraction is tiny by nature) -- the meaningful bound is in `fp64`.
+The reference arm times the CPU restatement of the reference algorithm (oracle/, OpenMP over
+curves, all host threads): the reference itself is Fortran and cannot be built in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+M, K, SIGMA, NEST = 256, 3, 0.1, 359
+S = M * SIGMA * SIGMA  # 2.56
+B_PER_GPU = 1 << 20
+SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--curves", type=int, default=B_PER_GPU, help="curves per GPU per step")
+    ap.add_argument("--no-splev", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.samples:
+            parts = [q.strip() for q in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_device(torch, dev, B, m, seed):
+    """C2 synthetic batch generated in HBM, point-major [m][B]."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    f64 = torch.float64
+    x = torch.rand((m, B), generator=g, device=dev, dtype=f64)
+    x.mul_(2).sub_(1).mul_(0.3)
+    x.add_(torch.arange(m, device=dev, dtype=f64)[:, None]).div_(m - 1)
+    x[0] = 0.0
+    x[-1] = 1.0
+    A = torch.rand((1, B), generator=g, device=dev, dtype=f64) * 1.5 + 0.5
+    f = torch.rand((1, B), generator=g, device=dev, dtype=f64) * 3 + 1
+    ph = torch.rand((1, B), generator=g, device=dev, dtype=f64) * (2 * 3.141592653589793)
+    y = torch.sin(x * (2 * 3.141592653589793) * f + ph).mul_(A)
+    y.add_(torch.randn((m, B), generator=g, device=dev, dtype=f64), alpha=SIGMA)
+    return x, y
+
+
+def fit_flops(n, passes, piters, m=M, k=K):
+    """algorithmic flop count of SURVEY.md 8(d) (div and sqrt = 1 flop), from the kernel's own
+    per-curve counters P (LSQ passes) and I (p-iterations) and the final knot count n."""
+    k1 = k + 1
+    nk1 = n - k1
+    n8 = n - 2 * k1
+    per_pass = m * (3.5 * k * (k + 1) + k1 + 1 + 13 * k1 + 3 * k1 * (k1 - 1) + 2) \
+        + nk1 * (2 * k + 1) + m * (2 * k1 + 3)
+    per_it = (13 + 6 * k1) * (n8 * nk1 - n8 * (n8 - 1) / 2) + nk1 * (2 * k1 + 1) + m * (2 * k1 + 3)
+    return passes * per_pass + piters * per_it
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the reference algorithm (oracle port; the Fortran cannot be built here) with all
+    host threads, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle_lib as O
+    from refdata import synth_curves
+    threads = O.max_threads()
+    rng = np.random.default_rng(1234)
+    x, y = synth_curves(rng, 2048, M, SIGMA)
+    t0 = time.perf_counter()
+    O.curfit_batch(0, x[:256], y[:256], None, K, S, NEST)
+    rate = 256 / (time.perf_counter() - t0)
+    budget = 120.0 / max(1, args.steps + args.warmup)       # seconds per step
+    sample = int(min(2048, max(64, rate * min(budget, 8.0))))
+    xs, ys = x[:sample], y[:sample]
+    for _ in range(args.warmup):
+        O.curfit_batch(0, xs, ys, None, K, S, NEST)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = O.curfit_batch(0, xs, ys, None, K, S, NEST)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    assert (out["ier"] <= 0).all()
+    desc = "first %d curves of the config-2 generator per step (bounded CPU sample)" % sample
+    print(json.dumps({
+        "impl": "reference", "metric": "curve fits/sec (256-pt, k=3)", "value": value,
+        "unit": "fits/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batched smoothing fit: %d-pt curves, k=3, s=2.56, nest=359, "
+                               "per-curve knot insertion (config 2)" % M,
+                   "curves_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": threads, "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fitpack_b200
+    from fitpack_b200.batch import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: fitpack_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    eng = Engine(dev)
+    B = args.curves
+    hbm_peak, peak_src = measured_peaks()
+    x, y = synth_device(torch, dev, B, M, 1234 + rank)
+    out = {}
+    # ---------------------------------------------------------------- fit: device-resident
+    for _ in range(args.warmup):
+        res = eng.curfit_batch(x, y, None, k=K, s=S, nest=NEST, want_stats=True, out=out)
+        out = {kk: res[kk] for kk in ("n", "t", "c", "fp", "ier", "stats")}
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        res = eng.curfit_batch(x, y, None, k=K, s=S, nest=NEST, want_stats=True, out=out)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    step_ms = ev0.elapsed_time(ev1) / args.steps
+    kernel_ms.append(eng.last_kernel_ms())  # CUDA events around the last fit-kernel launch
+    launches = eng.launches - launches0
+    step_ms_max = max_over_ranks(step_ms)
+    value = world * B / (step_ms_max * 1e-3)
+
+    n = res["n"]
+    ier = res["ier"]
+    stats = res["stats"].to(torch.float64)
+    n_f = n.to(torch.float64)
+    flops = float(fit_flops(n_f, stats[:, 0], stats[:, 1]).sum().item())
+    mean_n = float(n_f.mean().item())
+    ok_frac = float((ier <= 0).to(torch.float64).mean().item())
+    alg_bytes = B * (2 * 8 * M + 16 * mean_n + 16)
+    fit_ms = kernel_ms[-1]
+    roof = {"bound": "hbm", "kernel": "curfit_kernel<3>",
+            "achieved": alg_bytes / (fit_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_fit": alg_bytes / B,
+            "note": "fit kernel is FP64 issue/latency bound (~%.0f kflop per 4.4 KB): HBM "
+                    "fraction is tiny by construction; see fp64" % (flops / B / 1e3)}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    dmul_dadd = eng.probe_fp64_gops(False)
+    dfma = eng.probe_fp64_gops(True)
+    fp64 = {"achieved_gflops": flops / (fit_ms * 1e-3) / 1e9,
+            "peak_gops_dmul_dadd": dmul_dadd, "peak_gops_dfma": dfma,
+            "frac_of_unfused_peak": flops / (fit_ms * 1e-3) / 1e9 / dmul_dadd if dmul_dadd > 0 else None,
+            "flops_per_fit": flops / B, "mean_lsq_passes": float(stats[:, 0].mean().item()),
+            "mean_p_iters": float(stats[:, 1].mean().item()), "mean_n": mean_n,
+            "max_n": int(n.max().item())}
+
+    # ---------------------------------------------------------------- fit: end to end (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        L = fitpack_b200.lib()
+        Be = B
+        xh = torch.empty((Be, M), dtype=torch.float64, pin_memory=True)
+        yh = torch.empty((Be, M), dtype=torch.float64, pin_memory=True)
+        xh.copy_(eng.transpose(x))   # curve-major, as a caller of curfit holds the data
+        yh.copy_(eng.transpose(y))
+        nh = torch.zeros(Be, dtype=torch.int32, pin_memory=True)
+        th = torch.zeros((Be, NEST), dtype=torch.float64, pin_memory=True)
+        ch = torch.zeros((Be, NEST), dtype=torch.float64, pin_memory=True)
+        fph = torch.zeros(Be, dtype=torch.float64, pin_memory=True)
+        ierh = torch.zeros(Be, dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            rc = L.fp_curfit_batch_c(Be, 0, M, xh.data_ptr(), yh.data_ptr(), None, 0, None, None,
+                                     K, S, NEST, nh.data_ptr(), th.data_ptr(), ch.data_ptr(),
+                                     fph.data_ptr(), ierh.data_ptr(), 1)
+            if rc != 0:
+                raise RuntimeError("fp_curfit_batch_c failed: " + L.fpb_last_error().decode())
+
+        e2e_step()  # warm-up (allocates the staging buffers)
+        esteps = max(1, min(args.steps, 2))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        nmax_used = int(nh.max().item())
+        assert bool((nh == n.cpu()).all()) and bool((ierh == ier.cpu()).all()), "e2e != device path"
+        e2e = {"value": world * Be * esteps / dt, "unit": "fits/s",
+               "h2d_bytes_per_step": int(Be * M * 8 * 2 + Be * 8 + 24),
+               "d2h_bytes_per_step": int(Be * 16 + 2 * Be * nmax_used * 8),
+               "steps": esteps, "ms_per_step": 1e3 * dt / esteps,
+               "api": "fp_curfit_batch_c (host pointers, pinned)"}
+        del xh, yh, th, ch
+
+    # ---------------------------------------------------------------- splev (config 5 shape)
+    splev = None
+    if not args.no_splev:
+        del x, y, out, res
+        torch.cuda.empty_cache()
+        g = torch.Generator(device=dev)
+        g.manual_seed(99 + rank)
+        f64 = torch.float64
+        ns, ms, ks, nn = SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N
+        t = torch.zeros((ns, nn), device=dev, dtype=f64)
+        nint = nn - 2 * (ks + 1)
+        t[:, ks + 1:ks + 1 + nint] = torch.linspace(0, 1, nint + 2, device=dev, dtype=f64)[1:-1]
+        t[:, ks + 1 + nint:] = 1.0
+        c = torch.randn((ns, nn), generator=g, device=dev, dtype=f64)
+        nvec = torch.full((ns,), nn, device=dev, dtype=torch.int32)
+        xe = torch.rand((ns, ms), generator=g, device=dev, dtype=f64)
+        xe = torch.sort(xe, dim=1).values
+        so = {}
+        splev = {"config": {"workload": "splev bulk evaluation: %d k=%d splines (n=%d) x %d sorted "
+                                        "points per GPU (config 5 shape)" % (ns, ks, nn, ms)},
+                 "algorithmic_bytes_per_point": 16.0 + 8.0 * (nn + nn - ks - 1) / ms}
+        for mode, name in ((1, "fast"), (0, "exact")):
+            for _ in range(max(1, args.warmup)):
+                r = eng.splev_batch(t, nvec, c, ks, xe, e=0, mode=mode, out=so)
+                so = {"y": r["y"], "ier": r["ier"]}
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                r = eng.splev_batch(t, nvec, c, ks, xe, e=0, mode=mode, out=so)
+            ev1.record()
+            barrier()
+            ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+            kms = eng.last_kernel_ms()
+            bytes_alg = ns * ms * splev["algorithmic_bytes_per_point"]
+            splev[name] = {
+                "value": world * bytes_alg / (ms_step * 1e-3) / 1e9, "unit": "GB/s",
+                "gpts_per_s": world * ns * ms / (ms_step * 1e-3) / 1e9, "ms_per_step": ms_step,
+                "roofline": {"bound": "hbm", "kernel": "splev_kernel<5> mode=%s" % name,
+                             "achieved": bytes_alg / (kms * 1e-3) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": bytes_alg / (kms * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": None, "peak_source": peak_src}}
+        splev["gpu_launches"] = 2 * args.steps
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_lib as O
+        from refdata import synth_curves
+        rng = np.random.default_rng(1234)
+        xs, ys = synth_curves(rng, 4096, M, SIGMA)
+        t0 = time.perf_counter()
+        O.curfit_batch(0, xs[:256], ys[:256], None, K, S, NEST)
+        rate = 256 / (time.perf_counter() - t0)
+        sample = int(min(4096, max(256, rate * 15)))
+        t0 = time.perf_counter()
+        O.curfit_batch(0, xs[:sample], ys[:sample], None, K, S, NEST)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample / dt, "unit": "fits/s", "cores": O.max_threads(), "kind": "port",
+               "sample": "%d config-2 curves, oracle port of the reference algorithm, OpenMP over "
+                         "curves (reference is Fortran: no compiler in this image)" % sample}
+
+    if rank == 0:
+        line = {
+            "metric": "curve fits/sec (256-pt, k=3)", "value": value, "unit": "fits/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "batched smoothing fit: %d independent curves x %d points per "
+                                   "GPU, k=3, fixed s=2.56, nest=359, per-curve knot insertion "
+                                   "(config 2)" % (B, M),
+                       "curves_per_gpu": B, "layout": "point-major SoA in HBM",
+                       "l2": "inputs (%.1f GB/step) exceed the 126 MB L2; no flush needed"
+                             % (2 * B * M * 8 / 1e9),
+                       "success_fraction": ok_frac},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "fp64": fp64, "splev": splev, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

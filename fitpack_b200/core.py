@@ -1,0 +1,128 @@
+"""Flat entry points with the reference's argument conventions (fitpack_core curfit/splev:
+iopt, k, s, nest, n, t, c, fp, wrk, iwrk, ier) on host numpy arrays.  Each call goes through
+the C-ABI (fp_curfit_c / fp_splev_c / fp_*_batch_c) and therefore through the CUDA kernels;
+without a GPU the calls report an error -- there is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import FitpackB200Error, check, lib
+
+OUTSIDE_EXTRAPOLATE, OUTSIDE_ZERO, OUTSIDE_NOT_ALLOWED, OUTSIDE_NEAREST_BND = 0, 1, 2, 3
+IOPT_NEW_LEASTSQUARES, IOPT_NEW_SMOOTHING, IOPT_OLD_FIT = -1, 0, 1
+FPB_ERR_CUDA = -100
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def FITPACK_SUCCESS(ier):
+    """reference core:393-396"""
+    return bool(lib().FITPACK_SUCCESS_c(int(ier)))
+
+
+def FITPACK_MESSAGE(ier):
+    """reference core:315-339 via fitpack_message_c"""
+    buf = C.create_string_buffer(128)
+    lib().fitpack_message_c(int(ier), buf)
+    return buf.value.decode()
+
+
+def lwrk_min(m, k, nest):
+    return m * (k + 1) + nest * (7 + 3 * k)
+
+
+def curfit(iopt, x, y, w, xb, xe, k, s, nest, n=0, t=None, c=None, fp=0.0, wrk=None, iwrk=None,
+           lwrk=None):
+    """curfit (reference core:1240-1299) through fp_curfit_c.
+
+    t, c, wrk, iwrk are updated IN PLACE when given (pass them back for iopt=1);
+    returns dict(n, t, c, fp, ier, wrk, iwrk).
+    """
+    x = _f64(x)
+    y = _f64(y)
+    m = x.size
+    w = np.ones(m) if w is None else _f64(w)
+    if wrk is None:
+        wrk = np.zeros(max(lwrk_min(m, max(k, 0), max(nest, 0)) if lwrk is None else lwrk, 1))
+    if lwrk is None:
+        lwrk = wrk.size
+    t = np.zeros(max(nest, 1)) if t is None else t
+    c = np.zeros(max(nest, 1)) if c is None else c
+    iwrk = np.zeros(max(nest, 1), dtype=np.int32) if iwrk is None else iwrk
+    for name, arr, dt in (("t", t, np.float64), ("c", c, np.float64), ("wrk", wrk, np.float64),
+                          ("iwrk", iwrk, np.int32)):
+        if arr.dtype != dt or not arr.flags.c_contiguous:
+            raise TypeError("%s must be a contiguous %s array" % (name, dt.__name__))
+    n_ = C.c_int32(int(n))
+    fp_ = C.c_double(float(fp))
+    ier_ = C.c_int32(0)
+    lib().fp_curfit_c(int(iopt), m, _p(x), _p(y), _p(w), float(xb), float(xe), int(k), float(s),
+                      int(nest), C.addressof(n_), _p(t), _p(c), C.addressof(fp_), _p(wrk),
+                      int(lwrk), _p(iwrk), C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_curfit_c: %s" % lib().fpb_last_error().decode())
+    return dict(n=n_.value, t=t, c=c, fp=fp_.value, ier=ier_.value, wrk=wrk, iwrk=iwrk)
+
+
+def splev(t, n, c, k, x, e=OUTSIDE_EXTRAPOLATE, y=None):
+    """splev (reference core:17826-17896) through fp_splev_c; returns (y, ier)."""
+    t = _f64(t)
+    c = _f64(c)
+    x = _f64(x)
+    m = x.size
+    if y is None:
+        y = np.zeros(max(m, 1))
+    ier_ = C.c_int32(0)
+    lib().fp_splev_c(_p(t), int(n), _p(c), int(k), _p(x), _p(y), m, int(e), C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_splev_c: %s" % lib().fpb_last_error().decode())
+    return y[:m], ier_.value
+
+
+def curfit_batch(iopt, x, y, w, k, s, nest, xb=None, xe=None, shared_x=False, n=None, t=None,
+                 ngpus=1):
+    """Many independent curfit problems, host arrays, curve-major (fp_curfit_batch_c).
+
+    y: [B][m]; x, w: [B][m] or [m] when shared_x.  Returns dict(n, t, c, fp, ier).
+    """
+    y = _f64(y)
+    B, m = y.shape
+    x = _f64(x)
+    w = None if w is None else _f64(w)
+    n_arr = np.zeros(B, dtype=np.int32) if n is None else np.ascontiguousarray(n, dtype=np.int32)
+    t_arr = np.zeros((B, nest)) if t is None else _f64(t)
+    c_arr = np.zeros((B, nest))
+    fp = np.zeros(B)
+    ier = np.zeros(B, dtype=np.int32)
+    xb_ = None if xb is None else C.c_double(float(xb))
+    xe_ = None if xe is None else C.c_double(float(xe))
+    rc = lib().fp_curfit_batch_c(B, int(iopt), m, _p(x), _p(y), _p(w), 1 if shared_x else 0,
+                                 None if xb_ is None else C.addressof(xb_),
+                                 None if xe_ is None else C.addressof(xe_), int(k), float(s),
+                                 int(nest), _p(n_arr), _p(t_arr), _p(c_arr), _p(fp), _p(ier),
+                                 int(ngpus))
+    check(rc, "fp_curfit_batch_c")
+    return dict(n=n_arr, t=t_arr, c=c_arr, fp=fp, ier=ier)
+
+
+def splev_batch(t, n, c, k, x, e=OUTSIDE_EXTRAPOLATE, mode=0, ngpus=1):
+    """Many splines, m points each, host arrays (fp_splev_batch_c).  Returns (y, ier)."""
+    t = _f64(t)
+    c = _f64(c)
+    x = _f64(x)
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    nspl, ldt = t.shape
+    m = x.shape[1]
+    y = np.zeros_like(x)
+    ier = np.zeros(nspl, dtype=np.int32)
+    rc = lib().fp_splev_batch_c(nspl, _p(t), _p(n), _p(c), ldt, int(k), _p(x), _p(y), m, int(e),
+                                int(mode), _p(ier), int(ngpus))
+    check(rc, "fp_splev_batch_c")
+    return y, ier

@@ -1,0 +1,758 @@
+// fpb_curfit.cu -- batched smoothing-spline fit (curfit/fpcurf) for sm_100a.
+//
+// One thread per curve, 32 curves per warp, persistent warps pulling 32-curve
+// tiles from an atomic queue.  Follows, per curve, exactly the control flow
+// and IEEE operation order of the reference:
+//   curfit  src/fitpack_core.F90:1240-1299   (argument checks, fpchec)
+//   fpcurf  src/fitpack_core.F90:4737-5087   (knot loop, LSQ, p-iteration)
+//   fpbspl 2387-2413, fp_knot_interval 2432-2473, fp_rotate_row 5691-5717,
+//   fp_rotate_shifted 5800-5820, fpgivs 5638-5658, fprota 12385-12401,
+//   fpback 1808-1838, fpdisc 5453-5495, fpknot 8199-8275,
+//   root_finding_iterate 11641-11691, fprati 11996-12025, fpchec 2507-2570.
+//
+// B200 mapping (DESIGN.md "fit kernel"):
+//  * inputs are read point-major (SoA): lane b of a warp reads x[i*ld+b], so
+//    every pass over the m points is a stream of fully coalesced 256 B loads;
+//  * the band matrix R is never materialised per point: a point in knot
+//    interval l only touches R rows l-k..l, and x is sorted, so the k+1 active
+//    rows (+ their right-hand sides and the 2k knots fpbspl needs) live in
+//    REGISTERS as a sliding window; a row is written out exactly once per pass,
+//    when the window moves past it;
+//  * all per-knot state (t, c, z, R, fpint, nrdata, G, B) lives in a per-warp
+//    workspace interleaved by lane ([element][lane]), so loops whose index is
+//    uniform across the warp (back-substitution, p-iteration, fpknot, fpdisc)
+//    are coalesced too; trip counts are made warp-uniform with a max-reduce and
+//    per-lane predicates;
+//  * no host round trips: knot insertion, the rational p-search and all exits
+//    run inside the kernel; per-curve ier is an output, a bad curve never
+//    aborts the batch.
+#include "fpb_common.cuh"
+#include "fpb_kernels.h"
+
+namespace fpb {
+
+namespace {
+
+enum : int { ST_LOOP = 0, ST_PART2 = 1, ST_DONE = 2 };
+
+constexpr unsigned FULL = 0xffffffffu;
+
+#define WS(off, i) wsd[(size_t)((off) + (i)) * 32]
+// 1-based accessors in the reference's notation
+#define T_(i) WS(p.off_t, (i) - 1)
+#define C_(i) WS(p.off_c, (i) - 1)
+#define Z_(i) WS(p.off_z, (i) - 1)
+#define FPI_(i) WS(p.off_fpint, (i) - 1)
+#define A_(i, j) WS(p.off_a, ((i) - 1) * K1 + ((j) - 1))
+#define G_(i, j) WS(p.off_g, ((i) - 1) * K2 + ((j) - 1))
+#define B_(i, j) WS(p.off_b, ((i) - 1) * K2 + ((j) - 1))
+#define Q_(it, j) WS(p.off_q, (it) * K1 + (j))  /* it 0-based, j 0-based */
+#define NRD_(i) wsi[(size_t)((i) - 1) * 32]
+
+// interpolation knots, core:4806-4816 / 4975-4985
+template <int K>
+__device__ __forceinline__ void interp_knots(const FitParams &p, double *wsd, const double *xp, int m)
+{
+    constexpr int K1 = K + 1, K2 = K + 2;
+    const int mk1 = m - K1, k3 = K / 2;
+    int i = K2, j = k3 + 2;
+    for (int l = 1; l <= mk1; ++l) {
+        const double xj = xp[(size_t)(j - 1) * p.x_si];
+        double v;
+        if (k3 * 2 != K) v = xj;
+        else v = mul(add(xj, xp[(size_t)(j - 2) * p.x_si]), 0.5);
+        T_(i) = v;
+        ++i;
+        ++j;
+    }
+}
+
+// fpback, core:1808-1838.  Band matrix rows come from `offm` (row stride BAND),
+// right-hand side from `offz`, result into the c array.  The row loop runs over
+// a warp-uniform range so that the loads coalesce; `on` masks the lane.
+template <int BAND>
+__device__ __forceinline__ void back_subst(const FitParams &p, double *wsd, int offm, int offz,
+                                           int nk1, bool on)
+{
+    const int hi = __reduce_max_sync(FULL, on ? nk1 : 0);
+    double cw[BAND - 1];
+#pragma unroll
+    for (int q = 0; q < BAND - 1; ++q) cw[q] = 0.0;
+    for (int i = hi; i >= 1; --i) {
+        if (on && i <= nk1) {
+            double store = WS(offz, i - 1);
+            const int cnt = min(nk1 - i, BAND - 1);
+#pragma unroll
+            for (int q = 1; q <= BAND - 1; ++q)
+                if (q <= cnt) store = sub(store, mul(cw[q - 1], WS(offm, (i - 1) * BAND + q)));
+            const double ci = store / WS(offm, (i - 1) * BAND);
+            C_(i) = ci;
+#pragma unroll
+            for (int q = BAND - 2; q >= 1; --q) cw[q] = cw[q - 1];
+            cw[0] = ci;
+        }
+    }
+}
+
+// sum of squared residuals of the current c over all points using the stored
+// basis values q (get_fp loop, core:5061-5069); when FPINT is set also the
+// per-interval split of core:4942-4966.
+template <int K, bool FPINT>
+__device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd, const double *xp,
+                                                const double *yp, const double *wp, int m, int nk1,
+                                                int nrint, bool on)
+{
+    constexpr int K1 = K + 1, K2 = K + 2;
+    double cw[K1];
+    double fpart = 0.0, tl = 0.0;
+    int l = K2, i = 1;
+    if (on) {
+#pragma unroll
+        for (int j = 0; j < K1; ++j) cw[j] = C_(j + 1);
+        tl = T_(l);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K1; ++j) cw[j] = 0.0;
+    }
+    for (int it = 0; it < m; ++it) {
+        const double xi = xp[(size_t)it * p.x_si];
+        const double yi = yp[(size_t)it * p.y_si];
+        const double wi = wp ? wp[(size_t)it * p.w_si] : 1.0;
+        if (on) {
+            bool newk = false;
+            if (xi >= tl && l <= nk1) {
+                newk = true;
+                ++l;
+#pragma unroll
+                for (int j = 0; j < K; ++j) cw[j] = cw[j + 1];
+                cw[K] = C_(l - 1);
+                tl = T_(l);
+            }
+            double term = 0.0;
+#pragma unroll
+            for (int j = 0; j < K1; ++j) term = add(term, mul(cw[j], Q_(it, j)));
+            term = mul(wi, sub(term, yi));
+            term = mul(term, term);
+            fpart = add(fpart, term);
+            if (FPINT && newk) {
+                const double store = mul(term, 0.5);
+                FPI_(i) = sub(fpart, store);
+                ++i;
+                fpart = store;
+            }
+        }
+    }
+    if (FPINT && on) FPI_(nrint) = fpart;
+    return fpart;
+}
+
+// one least-squares pass (coefs loop core:4873-4896) with the active band rows
+// held in registers; returns fp = sum of squared transformed right-hand sides.
+template <int K>
+__device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, const double *xp,
+                                           const double *yp, const double *wp, int m, int nk1,
+                                           bool on)
+{
+    constexpr int K1 = K + 1;
+    double R[K1][K1], Zw[K1], tw[2 * K], h[K1];
+#pragma unroll
+    for (int r = 0; r < K1; ++r) {
+        Zw[r] = 0.0;
+#pragma unroll
+        for (int q = 0; q < K1; ++q) R[r][q] = 0.0;
+    }
+    int l = K1;
+    if (on) {
+#pragma unroll
+        for (int j = 0; j < 2 * K; ++j) tw[j] = T_(l - K + 1 + j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2 * K; ++j) tw[j] = 0.0;
+    }
+    double fp = 0.0;
+    for (int it = 0; it < m; ++it) {
+        const double xi = xp[(size_t)it * p.x_si];
+        const double wi = wp ? wp[(size_t)it * p.w_si] : 1.0;
+        double yi = mul(yp[(size_t)it * p.y_si], wi);
+        if (on) {
+            // fp_knot_interval (core:2432-2473) == linear walk from the previous interval
+            while (l < nk1 && xi >= tw[K]) {
+                // window leaves row l-K1+1 (1-based): it is final for this pass
+                const int row = l - K1 + 1;
+#pragma unroll
+                for (int q = 0; q < K1; ++q) A_(row, q + 1) = R[0][q];
+                Z_(row) = Zw[0];
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    Zw[r] = Zw[r + 1];
+#pragma unroll
+                    for (int q = 0; q < K1; ++q) R[r][q] = R[r + 1][q];
+                }
+                Zw[K] = 0.0;
+#pragma unroll
+                for (int q = 0; q < K1; ++q) R[K][q] = 0.0;
+#pragma unroll
+                for (int j = 0; j < 2 * K - 1; ++j) tw[j] = tw[j + 1];
+                ++l;
+                tw[2 * K - 1] = T_(l + K);
+            }
+            bspl<K>(tw, xi, h);
+#pragma unroll
+            for (int j = 0; j < K1; ++j) {
+                Q_(it, j) = h[j];
+                h[j] = mul(wi, h[j]);
+            }
+            // fp_rotate_row (core:5691-5717): window row i <-> R row l-K1+1+i
+#pragma unroll
+            for (int i = 0; i < K1; ++i) {
+                const double piv = h[i];
+                if (!fp_is_zero(piv)) {
+                    double cs, sn;
+                    givens(piv, R[i][0], cs, sn);
+                    rota(cs, sn, yi, Zw[i]);
+#pragma unroll
+                    for (int q = 1; q <= K - i; ++q) rota(cs, sn, h[i + q], R[i][q]);
+                }
+            }
+            fp = add(fp, mul(yi, yi));
+        }
+    }
+    if (on) {
+        // rows never reached by the data stay zero, exactly as in the reference
+        while (l < nk1) {
+            const int row = l - K1 + 1;
+#pragma unroll
+            for (int q = 0; q < K1; ++q) A_(row, q + 1) = R[0][q];
+            Z_(row) = Zw[0];
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                Zw[r] = Zw[r + 1];
+#pragma unroll
+                for (int q = 0; q < K1; ++q) R[r][q] = R[r + 1][q];
+            }
+            Zw[K] = 0.0;
+#pragma unroll
+            for (int q = 0; q < K1; ++q) R[K][q] = 0.0;
+            ++l;
+        }
+#pragma unroll
+        for (int r = 0; r < K1; ++r) {
+            const int row = l - K1 + 1 + r;
+#pragma unroll
+            for (int q = 0; q < K1; ++q) A_(row, q + 1) = R[r][q];
+            Z_(row) = Zw[r];
+        }
+    }
+    return fp;
+}
+
+// fpchec, core:2507-2570 (per lane, iopt=-1 only)
+template <int K>
+__device__ int check_knots(const FitParams &p, double *wsd, const double *xp, int m, int n)
+{
+    constexpr int K1 = K + 1, K2 = K + 2;
+    const int nk1 = n - K1, nk2 = nk1 + 1;
+    auto X = [&](int i) { return xp[(size_t)(i - 1) * p.x_si]; };
+    if (nk1 < K1 || nk1 > m) return IER_INPUT;
+    int j = n;
+    for (int i = 1; i <= K; ++i) {
+        if (T_(i) > T_(i + 1)) return IER_INPUT;
+        if (T_(j) < T_(j - 1)) return IER_INPUT;
+        --j;
+    }
+    for (int i = K2; i <= nk2; ++i)
+        if (T_(i) <= T_(i - 1)) return IER_INPUT;
+    if (X(1) < T_(K1) || X(m) > T_(nk2)) return IER_INPUT;
+    if (X(1) >= T_(K2) || X(m) <= T_(nk1)) return IER_INPUT;
+    int i = 1, l = K2;
+    const int nk3 = nk1 - 1;
+    for (j = 2; j <= nk3; ++j) {
+        const double tj = T_(j);
+        ++l;
+        const double tl = T_(l);
+        while (i < m && X(i) <= tj) {
+            ++i;
+            if (i >= m) return IER_INPUT;
+        }
+        if (X(i) >= tl) return IER_INPUT;
+    }
+    return IER_OK;
+}
+
+template <int K>
+__device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restrict__ wsd,
+                         int *__restrict__ wsi)
+{
+    constexpr int K1 = K + 1, K2 = K + 2;
+    const int m = p.m, nest = p.nest, iopt = p.iopt;
+    const int nmax = m + K1, nmin = 2 * K1;
+    const int bb = valid ? b : 0;
+    const double *xp = p.x + (size_t)bb * p.x_sb;
+    const double *yp = p.y + (size_t)bb * p.y_sb;
+    const double *wp = p.w ? p.w + (size_t)bb * p.w_sb : nullptr;
+
+    int state = valid ? ST_LOOP : ST_DONE;
+    int ier = IER_OK, n = 0;
+    double fp = 0.0;
+    bool write_fit = false;  // outputs beyond ier are only written once fpcurf ran
+
+    const double s = p.s[(size_t)bb * p.s_stride];
+    double xb, xe;
+    if (p.xb) {
+        xb = p.xb[(size_t)bb * p.xbe_stride];
+        xe = p.xe[(size_t)bb * p.xbe_stride];
+    } else {
+        xb = xp[0];
+        xe = xp[(size_t)(m - 1) * p.x_si];
+    }
+
+    // ---- curfit argument checks, core:1265-1285 (k, iopt, m, nest are call-level
+    //      and were checked on the host) ----
+    {
+        bool bad = false;
+        double prev = xp[0];
+        if (xb > prev) bad = true;
+        for (int it = 1; it < m; ++it) {  // any(x(1:m-1) > x(2:m))
+            const double cur = xp[(size_t)it * p.x_si];
+            if (prev > cur) bad = true;
+            prev = cur;
+        }
+        if (xe < prev) bad = true;
+        if (state == ST_LOOP) {
+            if (iopt >= 0) {
+                if (s < 0.0 || (fp_is_zero(s) && nest < (m + K1))) bad = true;
+            } else {
+                n = p.n[bb];
+                if (n < nmin || n > nest) bad = true;
+            }
+            if (bad) {
+                ier = IER_INPUT;
+                state = ST_DONE;
+            }
+        }
+    }
+    // knots / continuation state from the caller
+    if (state == ST_LOOP && iopt != 0) {
+        if (iopt > 0) n = p.n[bb];
+        const bool have = (iopt < 0) || (n >= nmin && n <= nest && n <= nmax);
+        if (iopt > 0 && !have) n = nmin;  // garbage n on a continuation: treat as a fresh start
+        if (have) {
+            for (int i = 1; i <= n; ++i) T_(i) = p.t[(size_t)bb * nest + (i - 1)];
+            if (iopt > 0 && p.fpint && p.nrdata) {
+                for (int i = 1; i <= n; ++i) {
+                    FPI_(i) = p.fpint[(size_t)bb * nest + (i - 1)];
+                    NRD_(i) = p.nrdata[(size_t)bb * nest + (i - 1)];
+                }
+            }
+        }
+        if (iopt < 0) {
+            int j = n;
+            for (int i = 1; i <= K1; ++i) {
+                T_(i) = xb;
+                T_(j) = xe;
+                --j;
+            }
+            // the clamped end knots are visible to the caller even if fpchec fails (core:1278-1284)
+            j = n;
+            for (int i = 1; i <= K1; ++i) {
+                p.t[(size_t)bb * nest + (i - 1)] = xb;
+                p.t[(size_t)bb * nest + (j - 1)] = xe;
+                --j;
+            }
+            const int chk = check_knots<K>(p, wsd, xp, m, n);
+            if (chk != 0) {
+                ier = chk;
+                state = ST_DONE;
+            }
+        }
+    }
+
+    // ---- fpcurf prologue, core:4761-4843 ----
+    double fpold = 0.0, fp0 = 0.0, fpms = DBL_MAX;
+    int nplus = 0;
+    const double acc = mul(kTol, s);
+    int lsq_passes = 0, p_iters = 0;
+    if (state == ST_LOOP) {
+        write_fit = true;
+        if (iopt >= 0) {
+            if (s <= 0.0) {
+                n = nmax;
+                if (nmax > nest) {
+                    ier = IER_STORAGE;
+                    state = ST_DONE;
+                } else {
+                    interp_knots<K>(p, wsd, xp, m);
+                }
+            } else if (iopt != 0 && n != nmin) {
+                fp0 = FPI_(n);
+                fpold = FPI_(n - 1);
+                nplus = NRD_(n);
+                if (fp0 <= s) {
+                    n = nmin;
+                    fpold = 0.0;
+                    nplus = 0;
+                    NRD_(1) = m - 2;
+                }
+            } else {
+                n = nmin;
+                fpold = 0.0;
+                nplus = 0;
+                NRD_(1) = m - 2;
+            }
+        }
+    }
+
+    // ---- part 1: knot loop, core:4847-4998 ----
+    int iter = 0, nk1 = n - K1, nrint = 0;
+    while (__any_sync(FULL, state == ST_LOOP)) {
+        bool on = (state == ST_LOOP);
+        if (on && !(iter <= m)) {
+            state = ST_PART2;
+            on = false;
+        }
+        if (on) {
+            ++iter;
+            if (n == nmin) ier = IER_LSQ;
+            nrint = n - nmin + 1;
+            nk1 = n - K1;
+            for (int i = 1; i <= K1; ++i) T_(i) = xb;
+            for (int i = nk1 + 1; i <= n; ++i) T_(i) = xe;
+            ++lsq_passes;
+        }
+        const double fp_pass = lsq_pass<K>(p, wsd, xp, yp, wp, m, nk1, on);
+        if (on) {
+            fp = fp_pass;
+            if (ier == IER_LSQ) fp0 = fp;
+            FPI_(n - 1) = fpold;
+            FPI_(n) = fp0;
+            NRD_(n) = nplus;
+        }
+        back_subst<K1>(p, wsd, p.off_a, p.off_z, nk1, on);
+        if (on) {
+            if (iopt < 0) {
+                state = ST_DONE;
+            } else {
+                fpms = sub(fp, s);
+                if (fabs(fpms) < acc) state = ST_DONE;
+                else if (fpms < 0.0) state = ST_PART2;
+                else if (n == nmax) { ier = IER_INTERP; state = ST_DONE; }
+                else if (n == nest) { ier = IER_STORAGE; state = ST_DONE; }
+            }
+        }
+        on = on && (state == ST_LOOP);
+        if (on) {  // number of knots to add, core:4927-4935
+            if (ier == IER_OK) {
+                int npl1 = nplus * 2;
+                const double rn = (double)nplus;
+                if (sub(fpold, fp) > acc) npl1 = x86_int(mul(rn, fpms) / sub(fpold, fp));
+                nplus = min(nplus * 2, max(max(npl1, nplus / 2), 1));
+            } else {
+                nplus = 1;
+                ier = IER_OK;
+            }
+            fpold = fp;
+        }
+        (void)residual_pass<K, true>(p, wsd, xp, yp, wp, m, nk1, nrint, on);
+        // add_new_knots, core:4968-4996 with fpknot core:8199-8275 inlined
+        {
+            const int maxplus = __reduce_max_sync(FULL, on ? nplus : 0);
+            bool adding = on;
+            for (int lp = 1; lp <= maxplus; ++lp) {
+                if (!__any_sync(FULL, adding && lp <= nplus)) break;
+                const bool act = adding && lp <= nplus;
+                const int hi = __reduce_max_sync(FULL, act ? nrint : 0);
+                double fpmax = 0.0;
+                int number = 0, maxpt = 0, maxbeg = 0, jbegin = 1;
+                for (int j = 1; j <= hi; ++j) {
+                    if (act && j <= nrint) {
+                        const int jpoint = NRD_(j);
+                        const double fj = FPI_(j);
+                        if (jpoint != 0 && (number == 0 || fj > fpmax)) {
+                            fpmax = fj;
+                            number = j;
+                            maxpt = jpoint;
+                            maxbeg = jbegin;
+                        }
+                        jbegin = jbegin + jpoint + 1;
+                    }
+                }
+                const bool ins = act && number != 0;
+                if (act && number == 0) adding = false;  // nothing left to refine: later calls are no-ops too
+                const int ihalf = maxpt / 2 + 1;
+                const int nrx = maxbeg + ihalf;
+                const int next = number + 1;
+                for (int jj = hi; jj >= 1; --jj) {
+                    if (ins && jj >= next && jj <= nrint) {
+                        FPI_(jj + 1) = FPI_(jj);
+                        NRD_(jj + 1) = NRD_(jj);
+                        T_(jj + K + 1) = T_(jj + K);
+                    }
+                }
+                if (ins) {
+                    NRD_(number) = ihalf - 1;
+                    NRD_(next) = maxpt - ihalf;
+                    const double am = (double)maxpt;
+                    double an = (double)(ihalf - 1);
+                    FPI_(number) = mul(fpmax, an) / am;
+                    an = (double)(maxpt - ihalf);
+                    FPI_(next) = mul(fpmax, an) / am;
+                    T_(next + K) = xp[(size_t)(nrx - 1) * p.x_si];
+                    ++n;
+                    ++nrint;
+                    if (n == nmax) {
+                        interp_knots<K>(p, wsd, xp, m);
+                        iter = 0;
+                        adding = false;
+                    } else if (n == nest) {
+                        adding = false;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- part 2: smoothing spline, core:5002-5084 ----
+    if (state == ST_PART2 && ier == IER_LSQ) state = ST_DONE;
+    {
+        const bool on2 = (state == ST_PART2);
+        nk1 = n - K1;
+        const int n8 = n - nmin;
+        // fpdisc, core:5453-5495
+        {
+            const int hi = __reduce_max_sync(FULL, on2 ? nk1 : 0);
+            double fac = 0.0;
+            if (on2) fac = (double)(nk1 - K) / sub(T_(nk1 + 1), T_(K1));
+            for (int l = K2; l <= hi; ++l) {
+                if (on2 && l <= nk1) {
+                    double hd[2 * K1];
+                    const double tl = T_(l);
+#pragma unroll
+                    for (int j = 1; j <= K1; ++j) {
+                        hd[j - 1] = sub(tl, T_(l + j - K2));
+                        hd[j + K1 - 1] = sub(tl, T_(l + j));
+                    }
+                    const int lmk = l - K1;
+#pragma unroll
+                    for (int j = 1; j <= K2; ++j) {
+                        double prod = hd[j - 1];
+#pragma unroll
+                        for (int i = 1; i <= K; ++i) prod = mul(mul(prod, hd[j - 1 + i]), fac);
+                        const int lp = lmk + j - 1;
+                        B_(lmk, j) = sub(T_(lp + K1), T_(lp)) / prod;
+                    }
+                }
+            }
+        }
+        double p1 = 0.0, f1 = sub(fp0, s), p3 = -1.0, f3 = fpms, p2 = 0.0, f2 = 0.0, pp = 0.0;
+        bool check1 = false, check3 = false;
+        {
+            const int hi = __reduce_max_sync(FULL, on2 ? nk1 : 0);
+            for (int i = 1; i <= hi; ++i)
+                if (on2 && i <= nk1) pp = add(pp, A_(i, 1));
+            if (on2) pp = (double)nk1 / pp;
+        }
+        int it2 = 0;
+        while (__any_sync(FULL, state == ST_PART2)) {
+            bool on = (state == ST_PART2);
+            if (on && !(it2 < kMaxIt)) {
+                ier = IER_MAXIT;
+                state = ST_DONE;
+                on = false;
+            }
+            double pinv = 0.0;
+            if (on) {
+                ++it2;
+                ++p_iters;
+                pinv = 1.0 / pp;
+            }
+            const int hi = __reduce_max_sync(FULL, on ? nk1 : 0);
+            const int hi8 = __reduce_max_sync(FULL, on ? n8 : 0);
+            for (int i = 1; i <= hi; ++i) {
+                if (on && i <= nk1) {
+                    C_(i) = Z_(i);
+#pragma unroll
+                    for (int q = 1; q <= K1; ++q) G_(i, q) = A_(i, q);
+                    G_(i, K2) = 0.0;
+                }
+            }
+            for (int it = 1; it <= hi8; ++it) {
+                const bool row_on = on && it <= n8;
+                double h[K2];
+#pragma unroll
+                for (int q = 0; q < K2; ++q) h[q] = row_on ? mul(B_(it, q + 1), pinv) : 0.0;
+                double yi = 0.0;
+                // fp_rotate_shifted, core:5800-5820
+                for (int j = it; j <= hi; ++j) {
+                    if (row_on && j <= nk1) {
+                        const double piv = h[0];
+                        const int noff = min(nk1 - j, K1);
+                        if (!fp_is_zero(piv)) {
+                            double gd = G_(j, 1), cj = C_(j), cs, sn;
+                            givens(piv, gd, cs, sn);
+                            G_(j, 1) = gd;
+                            rota(cs, sn, yi, cj);
+                            C_(j) = cj;
+#pragma unroll
+                            for (int q = 1; q <= K1; ++q) {
+                                if (q <= noff) {
+                                    double gq = G_(j, q + 1);
+                                    rota(cs, sn, h[q], gq);
+                                    G_(j, q + 1) = gq;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < K1; ++q) h[q] = h[q + 1];
+                        h[K1] = 0.0;
+                    }
+                }
+            }
+            back_subst<K2>(p, wsd, p.off_g, p.off_c, nk1, on);
+            const double fpn = residual_pass<K, false>(p, wsd, xp, yp, wp, m, nk1, 0, on);
+            if (on) {
+                fp = fpn;
+                fpms = sub(fp, s);
+                if (fabs(fpms) < acc) {
+                    state = ST_DONE;
+                } else {
+                    // root_finding_iterate core:11641-11691 + fprati core:11996-12025
+                    const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
+                    bool ret = false, ok = true;
+                    p2 = pp;
+                    f2 = fpms;
+                    if (!check3) {
+                        if (sub(f2, f3) > acc) {
+                            check3 = f2 < 0.0;
+                        } else {
+                            p3 = p2;
+                            f3 = f2;
+                            pp = mul(pp, con4);
+                            if (pp <= p1) pp = add(mul(p1, con9), mul(p2, con1));
+                            ret = true;
+                        }
+                    }
+                    if (!ret && !check1) {
+                        if (sub(f1, f2) > acc) {
+                            check1 = f2 > 0.0;
+                        } else {
+                            p1 = p2;
+                            f1 = f2;
+                            pp = pp / con4;
+                            if (p3 >= 0.0 && pp >= p3) pp = add(mul(p2, con1), mul(p3, con9));
+                            ret = true;
+                        }
+                    }
+                    if (!ret) {
+                        if (f2 >= f1 || f2 <= f3) {
+                            ok = false;
+                        } else {
+                            if (p3 > 0.0) {
+                                const double h1 = mul(f1, sub(f2, f3));
+                                const double h2 = mul(f2, sub(f3, f1));
+                                const double h3 = mul(f3, sub(f1, f2));
+                                const double num = add(add(mul(mul(p1, p2), h3), mul(mul(p2, p3), h1)),
+                                                       mul(mul(p3, p1), h2));
+                                const double den = add(add(mul(p1, h1), mul(p2, h2)), mul(p3, h3));
+                                pp = -num / den;
+                            } else {
+                                const double num = sub(mul(mul(p1, sub(f1, f3)), f2),
+                                                       mul(mul(p2, sub(f2, f3)), f1));
+                                pp = num / mul(sub(f1, f2), f3);
+                            }
+                            if (f2 >= 0.0) { p1 = p2; f1 = f2; } else { p3 = p2; f3 = f2; }
+                        }
+                    }
+                    if (!ok) {
+                        ier = IER_S_SMALL;
+                        state = ST_DONE;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- results (curve-major, as the caller of curfit holds them) ----
+    if (valid) {
+        p.ier[b] = ier;
+        if (write_fit) {
+            p.n[b] = n;
+            if (!(ier == IER_STORAGE && iopt >= 0 && s <= 0.0)) p.fp[b] = fp;
+            const int nk = n - K1;
+            for (int i = 1; i <= n; ++i) p.t[(size_t)b * nest + (i - 1)] = T_(i);
+            for (int i = 1; i <= nk; ++i) p.c[(size_t)b * nest + (i - 1)] = C_(i);
+            if (p.fpint && p.nrdata && iopt >= 0) {
+                for (int i = 1; i <= n; ++i) {
+                    p.fpint[(size_t)b * nest + (i - 1)] = FPI_(i);
+                    p.nrdata[(size_t)b * nest + (i - 1)] = NRD_(i);
+                }
+            }
+            if (p.stats) {
+                p.stats[2 * (size_t)b] = lsq_passes;
+                p.stats[2 * (size_t)b + 1] = p_iters;
+            }
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2) curfit_kernel(FitParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double *wsd = p.ws + (size_t)warp_slot * p.ws_per_lane * 32 + lane;
+    int *wsi = p.wsi + (size_t)warp_slot * p.nestp * 32 + lane;
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(p.counter, 1u);
+        tile = __shfl_sync(FULL, tile, 0);
+        const long long first = (long long)tile * 32;
+        if (first >= p.nbatch) break;
+        const int b = (int)first + lane;
+        fit_tile<K>(p, b, b < p.nbatch, wsd, wsi);
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+FitLayout fit_layout(int m, int k, int nest)
+{
+    const int k1 = k + 1, k2 = k + 2;
+    FitLayout L;
+    int nestp = nest < m + k1 ? nest : m + k1;
+    if (nestp < 2 * k1) nestp = 2 * k1;
+    L.nestp = nestp;
+    int off = 0;
+    L.off_t = off; off += nestp;
+    L.off_c = off; off += nestp;
+    L.off_z = off; off += nestp;
+    L.off_fpint = off; off += nestp;
+    L.off_a = off; off += nestp * k1;
+    L.off_g = off; off += nestp * k2;
+    L.off_b = off; off += nestp * k2;
+    L.off_q = off; off += m * k1;
+    L.ws_per_lane = off;
+    return L;
+}
+
+int fit_max_resident_warps(int k, int nsm)
+{
+    // matches __launch_bounds__ above: K<=3 -> 4 blocks of kFitThreads per SM, else 2
+    const int blocks_per_sm = (k <= 3) ? 4 : 2;
+    return nsm * blocks_per_sm * (kFitThreads / 32);
+}
+
+cudaError_t launch_curfit(const FitParams &p, int grid_blocks, cudaStream_t stream)
+{
+    switch (p.k) {
+    case 1: curfit_kernel<1><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
+    case 2: curfit_kernel<2><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
+    case 3: curfit_kernel<3><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
+    case 4: curfit_kernel<4><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
+    case 5: curfit_kernel<5><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace fpb

@@ -1,0 +1,829 @@
+// fpb_engine.cu -- host side of the C-ABI: engine lifetime, argument checks that
+// curfit/splev make before any arithmetic (core:1259-1270, 17844-17845), workspace
+// sizing, kernel launches, host<->device staging for the host-pointer entry points
+// and per-GPU sharding of a batch.  There is no CPU compute path in this file: every
+// entry point either runs the CUDA kernels or reports FPB_ERR_CUDA.
+#include "fpb_engine.h"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/fitpack_b200.h"
+
+namespace fpb {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+bool cuda_ok(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return true;
+    set_last_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+
+bool DevBuf::reserve(size_t want)
+{
+    if (want <= bytes) return true;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    // round up so that slowly growing batches do not reallocate every call
+    size_t cap = (want + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    if (!cuda_ok(cudaMalloc(&ptr, cap), "cudaMalloc")) {
+        ptr = nullptr;
+        return false;
+    }
+    bytes = cap;
+    return true;
+}
+
+void DevBuf::release()
+{
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+}
+
+static std::mutex g_engines_mu;
+static fpb_engine *g_engines[64] = {nullptr};
+
+fpb_engine *default_engine(int device)
+{
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) {
+            set_last_error("no CUDA device");
+            return nullptr;
+        }
+    }
+    if (device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_engines_mu);
+    if (!g_engines[device]) {
+        fpb_engine *e = nullptr;
+        if (fpb_engine_create(device, &e) != FPB_STATUS_OK) return nullptr;
+        g_engines[device] = e;
+    }
+    return g_engines[device];
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cuda_ok(cudaSetDevice(dev), "cudaSetDevice");
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static void begin_timing(fpb_engine *eng)
+{
+    cudaEventRecord(eng->ev0, eng->stream);
+}
+static void end_timing(fpb_engine *eng)
+{
+    cudaEventRecord(eng->ev1, eng->stream);
+    eng->timed = true;
+}
+
+}  // namespace fpb
+
+using namespace fpb;
+
+extern "C" {
+
+const char *fpb_last_error(void) { return g_last_error.c_str(); }
+const char *fpb_version(void) { return "fitpack_b200 0.1 (sm_100a)"; }
+
+int32_t fpb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int32_t fpb_engine_create(int32_t device, fpb_engine **out)
+{
+    if (!out) return FPB_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_last_error("no CUDA device visible: fitpack_b200 has no CPU fallback");
+        return FPB_ERR_CUDA;
+    }
+    if (device < 0 && !cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return FPB_ERR_CUDA;
+    if (device >= ndev) {
+        set_last_error("device index out of range");
+        return FPB_ERR_ARG;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    fpb_engine *e = new fpb_engine();
+    e->device = device;
+    cudaDeviceProp prop;
+    if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) {
+        delete e;
+        return FPB_ERR_CUDA;
+    }
+    e->nsm = prop.multiProcessorCount;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking), "stream") ||
+        !cuda_ok(cudaEventCreate(&e->ev0), "event") || !cuda_ok(cudaEventCreate(&e->ev1), "event")) {
+        delete e;
+        return FPB_ERR_CUDA;
+    }
+    e->stream = e->own_stream;
+    *out = e;
+    return FPB_STATUS_OK;
+}
+
+void fpb_engine_destroy(fpb_engine *eng)
+{
+    if (!eng) return;
+    DeviceGuard g(eng->device);
+    cudaStreamSynchronize(eng->stream);
+    eng->ws.release();
+    eng->wsi.release();
+    eng->counter.release();
+    eng->plan_cs.release();
+    eng->plan_w.release();
+    eng->plan_row.release();
+    eng->plan_skip.release();
+    eng->plan_R.release();
+    eng->plan_ier.release();
+    for (auto &b : eng->scratch) b.release();
+    if (eng->ev0) cudaEventDestroy(eng->ev0);
+    if (eng->ev1) cudaEventDestroy(eng->ev1);
+    if (eng->own_stream) cudaStreamDestroy(eng->own_stream);
+    delete eng;
+}
+
+int32_t fpb_engine_set_stream(fpb_engine *eng, void *cuda_stream)
+{
+    if (!eng) return FPB_ERR_ARG;
+    // taken literally: NULL is CUDA's default (legacy) stream, which is what torch uses
+    eng->stream = static_cast<cudaStream_t>(cuda_stream);
+    return FPB_STATUS_OK;
+}
+
+int32_t fpb_engine_reset_stream(fpb_engine *eng)
+{
+    if (!eng) return FPB_ERR_ARG;
+    eng->stream = eng->own_stream;
+    return FPB_STATUS_OK;
+}
+
+int32_t fpb_engine_synchronize(fpb_engine *eng)
+{
+    if (!eng) return FPB_ERR_ARG;
+    DeviceGuard g(eng->device);
+    return cuda_ok(cudaStreamSynchronize(eng->stream), "cudaStreamSynchronize") ? FPB_STATUS_OK
+                                                                                : FPB_ERR_CUDA;
+}
+
+int64_t fpb_engine_launch_count(const fpb_engine *eng) { return eng ? eng->launches : 0; }
+
+double fpb_engine_last_kernel_ms(fpb_engine *eng)
+{
+    if (!eng || !eng->timed) return -1.0;
+    DeviceGuard g(eng->device);
+    float ms = -1.0f;
+    if (cudaEventSynchronize(eng->ev1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+FP_BOOL FITPACK_SUCCESS_c(FP_FLAG ierr) { return ierr <= 0; }
+
+void fitpack_message_c(FP_FLAG ierr, char *msg)
+{
+    // strings of FITPACK_MESSAGE, reference core:315-339
+    const char *s;
+    switch (ierr) {
+    case 0: s = "Success!"; break;
+    case -1: s = "Success! (interpolation)"; break;
+    case -2: s = "Success! (least-squares)"; break;
+    case 1: s = "Insufficient Storage"; break;
+    case 2: s = "Smoothing parameter is too small"; break;
+    case 3: s = "Infinite loop detected"; break;
+    case 4: s = "More knots than data points"; break;
+    case 5: s = "Overlapping knots found"; break;
+    case 6: s = "Invalid variable range"; break;
+    case 10: s = "Invalid input"; break;
+    case 11: s = "Test(s) failed"; break;
+    case 12: s = "Invalid constraint(s) provided"; break;
+    case 13: s = "Not enough knots (n>=10)"; break;
+    case 14: s = "concon: maxbin too small"; break;
+    case 15: s = "concon: maxtr too small"; break;
+    case 16: s = "concon: QP solver failed"; break;
+    default: s = "UNKNOWN ERROR"; break;
+    }
+    if (msg) std::strcpy(msg, s);
+}
+
+// ------------------------------------------------------------------ device API
+
+int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m,
+                              const FP_REAL *x, int64_t x_sb, int64_t x_si, const FP_REAL *y,
+                              int64_t y_sb, int64_t y_si, const FP_REAL *w, int64_t w_sb,
+                              int64_t w_si, const FP_REAL *xb, const FP_REAL *xe, FP_SIZE xbe_stride,
+                              FP_SIZE k, const FP_REAL *s, FP_SIZE s_stride, FP_SIZE nest,
+                              FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
+                              FP_REAL *fpint, FP_SIZE *nrdata, FP_SIZE *stats)
+{
+    if (!eng) {
+        set_last_error("null engine");
+        return FPB_ERR_ARG;
+    }
+    if (nbatch <= 0) return FPB_STATUS_OK;
+    if (!x || !y || !s || !n || !t || !c || !fp || !ier || (xb && !xe) || (!xb && xe)) {
+        set_last_error("fp_curfit_batch_dev_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    if (iopt == 1 && (!fpint || !nrdata)) {
+        set_last_error("fp_curfit_batch_dev_c: iopt=1 needs the fpint/nrdata state arrays");
+        return FPB_ERR_ARG;
+    }
+    DeviceGuard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    // call-level part of the curfit data check (core:1265-1268): every curve gets ier=10
+    if (k <= 0 || k > 5 || iopt < -1 || iopt > 1 || m < k + 1 || nest < 2 * (k + 1)) {
+        if (!cuda_ok(launch_fill_i32(ier, FPB_INPUT_ERROR, nbatch, eng->stream), "fill ier"))
+            return FPB_ERR_CUDA;
+        eng->launches++;
+        return FPB_STATUS_OK;
+    }
+    const FitLayout L = fit_layout(m, k, nest);
+    long long blocks_needed = ((long long)nbatch + kFitThreads - 1) / kFitThreads;
+    const int max_warps = fit_max_resident_warps(k, eng->nsm);
+    long long grid = std::min<long long>(blocks_needed, max_warps / (kFitThreads / 32));
+    const size_t warps = (size_t)grid * (kFitThreads / 32);
+    if (!eng->ws.reserve(warps * (size_t)L.ws_per_lane * 32 * sizeof(double)) ||
+        !eng->wsi.reserve(warps * (size_t)L.nestp * 32 * sizeof(int)) ||
+        !eng->counter.reserve(256))
+        return FPB_ERR_ALLOC;
+    if (!cuda_ok(cudaMemsetAsync(eng->counter.ptr, 0, sizeof(unsigned), eng->stream), "memset"))
+        return FPB_ERR_CUDA;
+    FitParams p;
+    p.nbatch = nbatch; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest; p.nestp = L.nestp;
+    p.x = x; p.y = y; p.w = w;
+    p.x_sb = x_sb; p.x_si = x_si; p.y_sb = y_sb; p.y_si = y_si; p.w_sb = w_sb; p.w_si = w_si;
+    p.xb = xb; p.xe = xe; p.xbe_stride = xbe_stride;
+    p.s = s; p.s_stride = s_stride;
+    p.n = n; p.t = t; p.c = c; p.fp = fp; p.ier = ier;
+    p.fpint = fpint; p.nrdata = nrdata; p.stats = stats;
+    p.ws = eng->ws.as<double>(); p.wsi = eng->wsi.as<int>();
+    p.counter = eng->counter.as<unsigned>();
+    p.off_t = L.off_t; p.off_c = L.off_c; p.off_z = L.off_z; p.off_fpint = L.off_fpint;
+    p.off_a = L.off_a; p.off_g = L.off_g; p.off_b = L.off_b; p.off_q = L.off_q;
+    p.ws_per_lane = L.ws_per_lane;
+    begin_timing(eng);
+    if (!cuda_ok(launch_curfit(p, (int)grid, eng->stream), "curfit kernel launch"))
+        return FPB_ERR_CUDA;
+    end_timing(eng);
+    eng->launches++;
+    return FPB_STATUS_OK;
+}
+
+int32_t fp_curfit_shared_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE m, const FP_REAL *x,
+                               const FP_REAL *w, const FP_REAL *y, int64_t y_sb, int64_t y_si,
+                               FP_REAL xb, FP_REAL xe, FP_SIZE k, FP_SIZE n, FP_REAL *t, FP_REAL *c,
+                               int64_t ldc, FP_REAL *fp, FP_FLAG *ier)
+{
+    if (!eng || !x || !y || !t || !c || !fp || !ier) {
+        set_last_error("fp_curfit_shared_dev_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    DeviceGuard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    if (k <= 0 || k > 5 || m < k + 1 || n < 2 * (k + 1) || ldc < n - k - 1) {
+        if (!cuda_ok(launch_fill_i32(ier, FPB_INPUT_ERROR, 1, eng->stream), "fill ier"))
+            return FPB_ERR_CUDA;
+        eng->launches++;
+        return FPB_STATUS_OK;
+    }
+    const int k1 = k + 1, nk1 = n - k1;
+    if (!eng->plan_cs.reserve((size_t)m * k1 * 2 * sizeof(double)) ||
+        !eng->plan_w.reserve((size_t)m * sizeof(double)) ||
+        !eng->plan_row.reserve((size_t)m * sizeof(int)) ||
+        !eng->plan_skip.reserve((size_t)m * sizeof(int)) ||
+        !eng->plan_R.reserve((size_t)std::max(nk1, 1) * k1 * sizeof(double)) ||
+        !eng->plan_ier.reserve(256))
+        return FPB_ERR_ALLOC;
+    SharedPlan plan;
+    plan.cs_sn = eng->plan_cs.as<double>();
+    plan.wgt = eng->plan_w.as<double>();
+    plan.lrow = eng->plan_row.as<int>();
+    plan.skip = eng->plan_skip.as<int>();
+    plan.R = eng->plan_R.as<double>();
+    plan.ier = ier;
+    if (!cuda_ok(launch_shared_plan(x, w, m, xb, xe, k, n, t, plan, eng->stream), "plan kernel"))
+        return FPB_ERR_CUDA;
+    eng->launches++;
+    begin_timing(eng);
+    if (nbatch > 0) {
+        if (!cuda_ok(launch_shared_apply(nbatch, m, k, n, y, y_sb, y_si, plan, c, ldc, fp, eng->nsm,
+                                         eng->stream),
+                     "shared apply kernel"))
+            return FPB_ERR_CUDA;
+        eng->launches++;
+    }
+    end_timing(eng);
+    return FPB_STATUS_OK;
+}
+
+int32_t fp_splev_batch_dev_c(fpb_engine *eng, FP_SIZE nspl, const FP_REAL *t, const FP_SIZE *n,
+                             const FP_REAL *c, FP_SIZE ldt, FP_SIZE k, const FP_REAL *x, FP_REAL *y,
+                             FP_SIZE m, FP_FLAG e, FP_SIZE mode, FP_SIZE nshared, FP_FLAG *ier,
+                             FP_SIZE *lidx)
+{
+    if (!eng || !t || !n || !c || !x || !y) {
+        set_last_error("fp_splev_batch_dev_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    if (nspl <= 0) return FPB_STATUS_OK;
+    DeviceGuard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    if (m < 1) {  // core:17844-17845
+        if (ier) {
+            if (!cuda_ok(launch_fill_i32(ier, FPB_INPUT_ERROR, nspl, eng->stream), "fill ier"))
+                return FPB_ERR_CUDA;
+            eng->launches++;
+        }
+        return FPB_STATUS_OK;
+    }
+    if (k < 1 || k > 5 || ldt < 2 * (k + 1) || (mode != 0 && mode != 1) || e < 0 || e > 3) {
+        set_last_error("fp_splev_batch_dev_c: k must be 1..5, ldt >= 2k+2, mode 0/1, e 0..3");
+        return FPB_ERR_ARG;
+    }
+    SplevParams p;
+    p.nspl = nspl; p.ldt = ldt; p.k = k; p.m = m; p.e = e; p.mode = mode; p.nshared = nshared;
+    p.t = t; p.c = c; p.x = x; p.n = n; p.y = y; p.ier = ier; p.lidx = lidx;
+    begin_timing(eng);
+    if (!cuda_ok(launch_splev(p, eng->nsm, eng->stream), "splev kernel launch")) return FPB_ERR_CUDA;
+    end_timing(eng);
+    eng->launches++;
+    return FPB_STATUS_OK;
+}
+
+int32_t fpb_transpose_dev(fpb_engine *eng, const FP_REAL *src, int64_t ld_src, FP_REAL *dst,
+                          int64_t ld_dst, int64_t rows, int64_t cols)
+{
+    if (!eng || !src || !dst) return FPB_ERR_ARG;
+    DeviceGuard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    if (!cuda_ok(launch_transpose(src, ld_src, dst, ld_dst, rows, cols, eng->stream), "transpose"))
+        return FPB_ERR_CUDA;
+    eng->launches++;
+    return FPB_STATUS_OK;
+}
+
+double fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused)
+{
+    if (!eng) return -1.0;
+    DeviceGuard g(eng->device);
+    if (!g.ok || !eng->counter.reserve(256)) return -1.0;
+    const int blocks = eng->nsm * 8, iters = 1 << 14;
+    double best = -1.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(eng->ev0, eng->stream);
+        if (!cuda_ok(launch_fp64_probe(eng->counter.as<double>() + 8, blocks, iters, fused,
+                                       eng->stream), "fp64 probe"))
+            return -1.0;
+        cudaEventRecord(eng->ev1, eng->stream);
+        eng->launches++;
+        float ms = 0.f;
+        if (cudaEventSynchronize(eng->ev1) != cudaSuccess ||
+            cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) != cudaSuccess)
+            return -1.0;
+        // one FMA counts as one instruction here; mul+add as two
+        const double ops = (double)blocks * 256.0 * iters * 8.0 * (fused ? 1.0 : 2.0);
+        best = std::max(best, ops / (ms * 1e-3) * 1e-9);
+    }
+    eng->timed = false;
+    return best;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ host API
+
+namespace {
+
+// one GPU's share of a host-pointer batch fit, processed in chunks that bound
+// the device footprint
+int32_t fit_slice_host(fpb_engine *eng, long long b0, long long b1, FP_SIZE iopt, FP_SIZE m,
+                       const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
+                       const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
+                       FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
+                       FP_REAL *fpint, FP_SIZE *nrdata)
+{
+    DeviceGuard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    cudaStream_t st = eng->stream;
+    // bytes per curve on the device: x,y,w curve-major + point-major, outputs t,c (+state)
+    const size_t per_curve = (size_t)m * 8 * 6 + (size_t)nest * 8 * 2 + (size_t)nest * 12 + 64;
+    long long chunk = (long long)(((size_t)6 << 30) / per_curve);
+    chunk = std::max<long long>(chunk - chunk % 128, 128);
+    const bool state = (fpint && nrdata);
+    enum { XC, YC, WC, XP, YP, WP, TT, CC, NN, FP_, IER, AUX };
+    for (long long c0 = b0; c0 < b1; c0 += chunk) {
+        const long long nb = std::min(chunk, b1 - c0);
+        const size_t pts = (size_t)nb * m * sizeof(double);
+        DevBuf *B = eng->scratch;
+        const size_t aux_bytes = 64 + (state ? (size_t)nb * nest * 12 : 0);
+        if (!B[YC].reserve(pts) || !B[YP].reserve(pts) ||
+            !B[XC].reserve(shared_x ? (size_t)m * 8 : pts) ||
+            !B[XP].reserve(shared_x ? 8 : pts) ||
+            !B[WC].reserve(w ? (shared_x ? (size_t)m * 8 : pts) : 8) ||
+            !B[WP].reserve((w && !shared_x) ? pts : 8) ||
+            !B[TT].reserve((size_t)nb * nest * 8) || !B[CC].reserve((size_t)nb * nest * 8) ||
+            !B[NN].reserve((size_t)nb * 4) || !B[FP_].reserve((size_t)nb * 8) ||
+            !B[IER].reserve((size_t)nb * 4) || !B[AUX].reserve(aux_bytes))
+            return FPB_ERR_ALLOC;
+        double *aux = B[AUX].as<double>();  // [0]=s [1]=xb [2]=xe, then optional state
+        double hs[3] = {s, xb ? *xb : 0.0, xe ? *xe : 0.0};
+        bool ok = cuda_ok(cudaMemcpyAsync(aux, hs, sizeof hs, cudaMemcpyHostToDevice, st), "H2D s");
+        ok = ok && cuda_ok(cudaMemcpyAsync(B[YC].ptr, y + (size_t)c0 * m, pts,
+                                           cudaMemcpyHostToDevice, st), "H2D y");
+        const double *dx, *dw = nullptr;
+        long long x_sb, x_si, w_sb = 0, w_si = 0;
+        if (shared_x) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[XC].ptr, x, (size_t)m * 8, cudaMemcpyHostToDevice,
+                                               st), "H2D x");
+            dx = B[XC].as<double>(); x_sb = 0; x_si = 1;
+            if (w) {
+                ok = ok && cuda_ok(cudaMemcpyAsync(B[WC].ptr, w, (size_t)m * 8,
+                                                   cudaMemcpyHostToDevice, st), "H2D w");
+                dw = B[WC].as<double>(); w_sb = 0; w_si = 1;
+            }
+        } else {
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[XC].ptr, x + (size_t)c0 * m, pts,
+                                               cudaMemcpyHostToDevice, st), "H2D x");
+            ok = ok && cuda_ok(launch_transpose(B[XC].as<double>(), m, B[XP].as<double>(), nb, nb,
+                                                m, st), "transpose x");
+            eng->launches++;
+            dx = B[XP].as<double>(); x_sb = 1; x_si = nb;
+            if (w) {
+                ok = ok && cuda_ok(cudaMemcpyAsync(B[WC].ptr, w + (size_t)c0 * m, pts,
+                                                   cudaMemcpyHostToDevice, st), "H2D w");
+                ok = ok && cuda_ok(launch_transpose(B[WC].as<double>(), m, B[WP].as<double>(), nb,
+                                                    nb, m, st), "transpose w");
+                eng->launches++;
+                dw = B[WP].as<double>(); w_sb = 1; w_si = nb;
+            }
+        }
+        ok = ok && cuda_ok(launch_transpose(B[YC].as<double>(), m, B[YP].as<double>(), nb, nb, m,
+                                            st), "transpose y");
+        eng->launches++;
+        if (!ok) return FPB_ERR_CUDA;
+        double *dfpint = nullptr;
+        int *dnrd = nullptr;
+        if (state) {
+            dfpint = aux + 8;
+            dnrd = reinterpret_cast<int *>(dfpint + (size_t)nb * nest);
+        }
+        if (iopt != 0) {  // n, t (and the continuation state) are inputs
+            ok = cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + c0, (size_t)nb * 4, cudaMemcpyHostToDevice,
+                                         st), "H2D n");
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[TT].ptr, t + (size_t)c0 * nest,
+                                               (size_t)nb * nest * 8, cudaMemcpyHostToDevice, st),
+                               "H2D t");
+            if (iopt == -1)  // a curve rejected by fpchec must get its caller's c back unchanged
+                ok = ok && cuda_ok(cudaMemcpyAsync(B[CC].ptr, c + (size_t)c0 * nest,
+                                                   (size_t)nb * nest * 8, cudaMemcpyHostToDevice,
+                                                   st), "H2D c");
+            if (iopt == 1 && state) {
+                ok = ok && cuda_ok(cudaMemcpyAsync(dfpint, fpint + (size_t)c0 * nest,
+                                                   (size_t)nb * nest * 8, cudaMemcpyHostToDevice,
+                                                   st), "H2D fpint");
+                ok = ok && cuda_ok(cudaMemcpyAsync(dnrd, nrdata + (size_t)c0 * nest,
+                                                   (size_t)nb * nest * 4, cudaMemcpyHostToDevice,
+                                                   st), "H2D nrdata");
+            }
+            if (!ok) return FPB_ERR_CUDA;
+        }
+        // outputs the kernel may leave untouched (ier=10) must round-trip unchanged
+        ok = cuda_ok(cudaMemcpyAsync(B[FP_].ptr, fp + c0, (size_t)nb * 8, cudaMemcpyHostToDevice, st),
+                     "H2D fp");
+        if (iopt == 0)
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + c0, (size_t)nb * 4,
+                                               cudaMemcpyHostToDevice, st), "H2D n");
+        if (!ok) return FPB_ERR_CUDA;
+        int32_t rc = fp_curfit_batch_dev_c(eng, (FP_SIZE)nb, iopt, m, dx, x_sb, x_si,
+                                           B[YP].as<double>(), 1, nb, dw, w_sb, w_si,
+                                           xb ? aux + 1 : nullptr, xe ? aux + 2 : nullptr, 0, k, aux,
+                                           0, nest, B[NN].as<int>(), B[TT].as<double>(),
+                                           B[CC].as<double>(), B[FP_].as<double>(),
+                                           B[IER].as<int>(), dfpint, dnrd, nullptr);
+        if (rc != FPB_STATUS_OK) return rc;
+        ok = cuda_ok(cudaMemcpyAsync(n + c0, B[NN].ptr, (size_t)nb * 4, cudaMemcpyDeviceToHost, st),
+                     "D2H n");
+        ok = ok && cuda_ok(cudaMemcpyAsync(fp + c0, B[FP_].ptr, (size_t)nb * 8,
+                                           cudaMemcpyDeviceToHost, st), "D2H fp");
+        ok = ok && cuda_ok(cudaMemcpyAsync(ier + c0, B[IER].ptr, (size_t)nb * 4,
+                                           cudaMemcpyDeviceToHost, st), "D2H ier");
+        if (!ok || !cuda_ok(cudaStreamSynchronize(st), "sync")) return FPB_ERR_CUDA;
+        // knots/coefficients: only the leading max(n) columns carry information
+        int nmax_used = 0;
+        bool any_fit = false;
+        for (long long b = 0; b < nb; ++b) {
+            if (ier[c0 + b] != FPB_INPUT_ERROR) {
+                nmax_used = std::max(nmax_used, (int)n[c0 + b]);
+                any_fit = true;
+            }
+        }
+        if (iopt == -1) nmax_used = nest;  // clamped end knots may have been written even on ier=10
+        nmax_used = std::min<int>(std::max(nmax_used, 0), nest);
+        if (nmax_used > 0 && (any_fit || iopt == -1)) {
+            // rows whose fit was rejected keep the caller's t/c: copy only accepted rows' columns.
+            // (2-D copy of the leading columns; rejected rows are restored from a host backup.)
+            std::vector<double> keep_t, keep_c;
+            std::vector<long long> bad;
+            for (long long b = 0; b < nb; ++b)
+                if (ier[c0 + b] == FPB_INPUT_ERROR && iopt != -1) bad.push_back(b);
+            keep_t.resize(bad.size() * (size_t)nmax_used);
+            keep_c.resize(bad.size() * (size_t)nmax_used);
+            for (size_t i = 0; i < bad.size(); ++i) {
+                std::memcpy(&keep_t[i * nmax_used], t + (size_t)(c0 + bad[i]) * nest,
+                            (size_t)nmax_used * 8);
+                std::memcpy(&keep_c[i * nmax_used], c + (size_t)(c0 + bad[i]) * nest,
+                            (size_t)nmax_used * 8);
+            }
+            ok = cuda_ok(cudaMemcpy2DAsync(t + (size_t)c0 * nest, (size_t)nest * 8, B[TT].ptr,
+                                           (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
+                                           cudaMemcpyDeviceToHost, st), "D2H t");
+            if (iopt != -1 || any_fit)
+                ok = ok && cuda_ok(cudaMemcpy2DAsync(c + (size_t)c0 * nest, (size_t)nest * 8,
+                                                     B[CC].ptr, (size_t)nest * 8,
+                                                     (size_t)nmax_used * 8, (size_t)nb,
+                                                     cudaMemcpyDeviceToHost, st), "D2H c");
+            if (state && iopt >= 0) {
+                ok = ok && cuda_ok(cudaMemcpyAsync(fpint + (size_t)c0 * nest, dfpint,
+                                                   (size_t)nb * nest * 8, cudaMemcpyDeviceToHost,
+                                                   st), "D2H fpint");
+                ok = ok && cuda_ok(cudaMemcpyAsync(nrdata + (size_t)c0 * nest, dnrd,
+                                                   (size_t)nb * nest * 4, cudaMemcpyDeviceToHost,
+                                                   st), "D2H nrdata");
+            }
+            if (!ok || !cuda_ok(cudaStreamSynchronize(st), "sync")) return FPB_ERR_CUDA;
+            for (size_t i = 0; i < bad.size(); ++i) {
+                std::memcpy(t + (size_t)(c0 + bad[i]) * nest, &keep_t[i * nmax_used],
+                            (size_t)nmax_used * 8);
+                std::memcpy(c + (size_t)(c0 + bad[i]) * nest, &keep_c[i * nmax_used],
+                            (size_t)nmax_used * 8);
+            }
+        }
+    }
+    return FPB_STATUS_OK;
+}
+
+int32_t splev_slice_host(fpb_engine *eng, long long j0, long long j1, const FP_REAL *t,
+                         const FP_SIZE *n, const FP_REAL *c, FP_SIZE ldt, FP_SIZE k,
+                         const FP_REAL *x, FP_REAL *y, FP_SIZE m, FP_FLAG e, FP_SIZE mode,
+                         FP_FLAG *ier)
+{
+    DeviceGuard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    cudaStream_t st = eng->stream;
+    const size_t per_spl = (size_t)m * 16 + (size_t)ldt * 16 + 8;
+    long long chunk = std::max<long long>((long long)(((size_t)8 << 30) / per_spl), 1);
+    enum { TT, CC, NN, XX, YY, IER };
+    for (long long c0 = j0; c0 < j1; c0 += chunk) {
+        const long long ns = std::min(chunk, j1 - c0);
+        DevBuf *B = eng->scratch;
+        if (!B[TT].reserve((size_t)ns * ldt * 8) || !B[CC].reserve((size_t)ns * ldt * 8) ||
+            !B[NN].reserve((size_t)ns * 4) || !B[XX].reserve((size_t)ns * m * 8) ||
+            !B[YY].reserve((size_t)ns * m * 8) || !B[IER].reserve((size_t)ns * 4))
+            return FPB_ERR_ALLOC;
+        bool ok = cuda_ok(cudaMemcpyAsync(B[TT].ptr, t + (size_t)c0 * ldt, (size_t)ns * ldt * 8,
+                                          cudaMemcpyHostToDevice, st), "H2D t");
+        ok = ok && cuda_ok(cudaMemcpyAsync(B[CC].ptr, c + (size_t)c0 * ldt, (size_t)ns * ldt * 8,
+                                           cudaMemcpyHostToDevice, st), "H2D c");
+        ok = ok && cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + c0, (size_t)ns * 4, cudaMemcpyHostToDevice,
+                                           st), "H2D n");
+        ok = ok && cuda_ok(cudaMemcpyAsync(B[XX].ptr, x + (size_t)c0 * m, (size_t)ns * m * 8,
+                                           cudaMemcpyHostToDevice, st), "H2D x");
+        // splev leaves y untouched where it does not evaluate (e=2 early return): round-trip it
+        if (e == FPB_OUTSIDE_NOT_ALLOWED)
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[YY].ptr, y + (size_t)c0 * m, (size_t)ns * m * 8,
+                                               cudaMemcpyHostToDevice, st), "H2D y");
+        if (!ok) return FPB_ERR_CUDA;
+        int32_t rc = fp_splev_batch_dev_c(eng, (FP_SIZE)ns, B[TT].as<double>(), B[NN].as<int>(),
+                                          B[CC].as<double>(), ldt, k, B[XX].as<double>(),
+                                          B[YY].as<double>(), m, e, mode, 0, B[IER].as<int>(),
+                                          nullptr);
+        if (rc != FPB_STATUS_OK) return rc;
+        ok = cuda_ok(cudaMemcpyAsync(y + (size_t)c0 * m, B[YY].ptr, (size_t)ns * m * 8,
+                                     cudaMemcpyDeviceToHost, st), "D2H y");
+        if (ier)
+            ok = ok && cuda_ok(cudaMemcpyAsync(ier + c0, B[IER].ptr, (size_t)ns * 4,
+                                               cudaMemcpyDeviceToHost, st), "D2H ier");
+        if (!ok || !cuda_ok(cudaStreamSynchronize(st), "sync")) return FPB_ERR_CUDA;
+    }
+    return FPB_STATUS_OK;
+}
+
+template <class F> int32_t shard_over_gpus(long long total, int ngpus, long long align, F &&fn)
+{
+    int ndev = fpb_device_count();
+    if (ndev == 0) {
+        set_last_error("no CUDA device visible: fitpack_b200 has no CPU fallback");
+        return FPB_ERR_CUDA;
+    }
+    if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
+    if (total < (long long)ngpus * align) ngpus = (int)std::max<long long>(1, total / std::max<long long>(align, 1));
+    if (ngpus <= 1) {
+        fpb_engine *e = default_engine(-1);
+        if (!e) return FPB_ERR_CUDA;
+        return fn(e, 0LL, total);
+    }
+    std::vector<int32_t> rc(ngpus, FPB_STATUS_OK);
+    std::vector<std::string> err(ngpus);
+    std::vector<std::thread> th;
+    long long per = (total + ngpus - 1) / ngpus;
+    per = (per + align - 1) / align * align;
+    for (int d = 0; d < ngpus; ++d) {
+        const long long b0 = std::min(total, per * d), b1 = std::min(total, per * (d + 1));
+        th.emplace_back([&, d, b0, b1]() {
+            if (b0 >= b1) return;
+            fpb_engine *e = default_engine(d);
+            if (!e) {
+                rc[d] = FPB_ERR_CUDA;
+                err[d] = fpb_last_error();
+                return;
+            }
+            rc[d] = fn(e, b0, b1);
+            if (rc[d] != FPB_STATUS_OK) err[d] = fpb_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < ngpus; ++d)
+        if (rc[d] != FPB_STATUS_OK) {
+            set_last_error(err[d]);
+            return rc[d];
+        }
+    return FPB_STATUS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t fp_curfit_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x,
+                          const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x, const FP_REAL *xb,
+                          const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest, FP_SIZE *n,
+                          FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier, FP_SIZE ngpus)
+{
+    if (nbatch <= 0) return FPB_STATUS_OK;
+    if (!x || !y || !n || !t || !c || !fp || !ier || (xb && !xe) || (!xb && xe)) {
+        set_last_error("fp_curfit_batch_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    if (iopt == 1) {
+        set_last_error("fp_curfit_batch_c: iopt=1 needs per-curve state; use fp_curfit_c or the "
+                       "device entry point with fpint/nrdata");
+        return FPB_ERR_ARG;
+    }
+    if (m < 1 || nest < 1) {  // nothing addressable: mirror curfit's ier=10
+        for (FP_SIZE b = 0; b < nbatch; ++b) ier[b] = FPB_INPUT_ERROR;
+        return FPB_STATUS_OK;
+    }
+    return shard_over_gpus(nbatch, ngpus, 128, [&](fpb_engine *e, long long b0, long long b1) {
+        return fit_slice_host(e, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest, n, t, c,
+                              fp, ier, nullptr, nullptr);
+    });
+}
+
+int32_t fp_splev_batch_c(FP_SIZE nspl, const FP_REAL *t, const FP_SIZE *n, const FP_REAL *c,
+                         FP_SIZE ldt, FP_SIZE k, const FP_REAL *x, FP_REAL *y, FP_SIZE m, FP_FLAG e,
+                         FP_SIZE mode, FP_FLAG *ier, FP_SIZE ngpus)
+{
+    if (nspl <= 0) return FPB_STATUS_OK;
+    if (!t || !n || !c || !x || !y) {
+        set_last_error("fp_splev_batch_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    if (m < 1) {
+        if (ier)
+            for (FP_SIZE j = 0; j < nspl; ++j) ier[j] = FPB_INPUT_ERROR;
+        return FPB_STATUS_OK;
+    }
+    return shard_over_gpus(nspl, ngpus, 8, [&](fpb_engine *eng, long long j0, long long j1) {
+        return splev_slice_host(eng, j0, j1, t, n, c, ldt, k, x, y, m, e, mode, ier);
+    });
+}
+
+// ---- the reference's own flat entry points: a batch of one curve ----
+
+void fp_curfit_c(FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y, const FP_REAL *w,
+                 FP_REAL xb, FP_REAL xe, FP_SIZE k, FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t,
+                 FP_REAL *c, FP_REAL *fp, FP_REAL *wrk, FP_SIZE lwrk, FP_SIZE *iwrk, FP_FLAG *ier)
+{
+    // data check that does not need the data, core:1259-1270
+    *ier = FPB_INPUT_ERROR;
+    if (k <= 0 || k > 5) return;
+    if (iopt < -1 || iopt > 1) return;
+    if (m < k + 1 || nest < 2 * (k + 1)) return;
+    if (lwrk < m * (k + 1) + nest * (7 + 3 * k)) return;
+    fpb_engine *e = default_engine(-1);
+    if (!e) {
+        *ier = FPB_ERR_CUDA;  // no device: fail loudly, there is no CPU path
+        return;
+    }
+    // wrk(1:nest) is fpint and iwrk(1:nest) is nrdata in the reference (core:1289-1297):
+    // that is the state an iopt=1 continuation reads back.
+    int32_t rc = fit_slice_host(e, 0, 1, iopt, m, x, y, w, 0, &xb, &xe, k, s, nest, n, t, c, fp,
+                                ier, wrk, iwrk);
+    if (rc != FPB_STATUS_OK) *ier = rc;
+}
+
+void fp_splev_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, const FP_REAL *x,
+                FP_REAL *y, FP_SIZE m, FP_FLAG e, FP_FLAG *ier)
+{
+    *ier = FPB_INPUT_ERROR;
+    if (m < 1) return;  // core:17844-17845
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    // one spline, its m points spread over the whole device (nshared mode)
+    DeviceGuard g(eng->device);
+    cudaStream_t st = eng->stream;
+    DevBuf *B = eng->scratch;
+    const int chunk = 4096;
+    const long long nchunks = ((long long)m + chunk - 1) / chunk;
+    const size_t padded = (size_t)nchunks * chunk;
+    const int ldt = std::max((n + 1) & ~1, 2 * (k + 1));
+    if (k < 1 || k > 5 || n < 2 * (k + 1)) return;  // not a valid spline: nothing safe to evaluate
+    if (!B[0].reserve((size_t)ldt * 8) || !B[1].reserve((size_t)ldt * 8) || !B[2].reserve(64) ||
+        !B[3].reserve(padded * 8) || !B[4].reserve(padded * 8) ||
+        !B[5].reserve((size_t)nchunks * 4)) {
+        *ier = FPB_ERR_ALLOC;
+        return;
+    }
+    bool ok = cuda_ok(cudaMemcpyAsync(B[0].ptr, t, (size_t)n * 8, cudaMemcpyHostToDevice, st), "H2D");
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[1].ptr, c, (size_t)n * 8, cudaMemcpyHostToDevice, st), "H2D");
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[2].ptr, &n, 4, cudaMemcpyHostToDevice, st), "H2D");
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[3].ptr, x, (size_t)m * 8, cudaMemcpyHostToDevice, st), "H2D");
+    if (e == FPB_OUTSIDE_NOT_ALLOWED)
+        ok = ok && cuda_ok(cudaMemcpyAsync(B[4].ptr, y, (size_t)m * 8, cudaMemcpyHostToDevice, st),
+                           "H2D");
+    // pad the tail chunk with an in-support abscissa so that it cannot raise ier=6
+    if (ok && padded > (size_t)m) {
+        std::vector<double> pad(padded - m, x[0]);
+        // x[0] itself may be outside the support; t(k+1) never is
+        std::fill(pad.begin(), pad.end(), t[k]);
+        ok = cuda_ok(cudaMemcpyAsync(B[3].as<double>() + m, pad.data(), pad.size() * 8,
+                                     cudaMemcpyHostToDevice, st), "H2D pad");
+        ok = ok && cuda_ok(cudaStreamSynchronize(st), "sync");
+    }
+    if (!ok) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    int32_t rc = fp_splev_batch_dev_c(eng, (FP_SIZE)nchunks, B[0].as<double>(), B[2].as<int>(),
+                                      B[1].as<double>(), ldt, k, B[3].as<double>(),
+                                      B[4].as<double>(), chunk, e, FPB_SPLEV_EXACT, 1,
+                                      B[5].as<int>(), nullptr);
+    if (rc != FPB_STATUS_OK) {
+        *ier = rc;
+        return;
+    }
+    std::vector<int> hier((size_t)nchunks);
+    ok = cuda_ok(cudaMemcpyAsync(hier.data(), B[5].ptr, (size_t)nchunks * 4, cudaMemcpyDeviceToHost,
+                                 st), "D2H");
+    ok = ok && cuda_ok(cudaStreamSynchronize(st), "sync");
+    if (!ok) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    int result = FPB_OK;
+    for (int v : hier)
+        if (v != FPB_OK) result = v;
+    if (result == FPB_INVALID_RANGE) {
+        // reference semantics (core:17871-17873): y is filled up to the first offender only
+        const double tb = t[k], te = t[n - k - 1];
+        long long first = m;
+        for (long long i = 0; i < m; ++i)
+            if (x[i] < tb || x[i] > te) {
+                first = i;
+                break;
+            }
+        if (first > 0)
+            ok = cuda_ok(cudaMemcpy(y, B[4].ptr, (size_t)first * 8, cudaMemcpyDeviceToHost), "D2H y");
+    } else {
+        ok = cuda_ok(cudaMemcpy(y, B[4].ptr, (size_t)m * 8, cudaMemcpyDeviceToHost), "D2H y");
+    }
+    *ier = ok ? result : FPB_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// fpb_engine.h -- per-GPU engine object behind the C-ABI (include/fitpack_b200.h).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+
+#include "fpb_kernels.h"
+
+namespace fpb {
+
+void set_last_error(const std::string &msg);
+bool cuda_ok(cudaError_t e, const char *what);
+
+// grow-only device buffer
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    bool reserve(size_t want);
+    void release();
+    template <class T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+}  // namespace fpb
+
+struct fpb_engine {
+    int device = 0;
+    int nsm = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int64_t launches = 0;
+    fpb::DevBuf ws, wsi, counter;     // fit kernel workspace
+    fpb::DevBuf plan_cs, plan_w, plan_row, plan_skip, plan_R, plan_ier;  // shared-x plan
+    fpb::DevBuf scratch[12];          // staging for the host-pointer entry points
+};
+
+namespace fpb {
+// default engine of a device (created on first use, lives until process exit)
+fpb_engine *default_engine(int device);
+}

@@ -1,0 +1,74 @@
+// fpb_kernels.h -- host-visible declarations of the CUDA kernels' launchers.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fpb {
+
+constexpr int kFitThreads = 128;  // threads per CTA of the fit kernel (4 warps = 128 curves)
+
+// per-lane workspace layout of the fit kernel, in elements of 8 bytes
+struct FitLayout {
+    int nestp;  // knots a curve can actually reach: min(nest, m+k+1)
+    int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q;
+    int ws_per_lane;
+};
+FitLayout fit_layout(int m, int k, int nest);
+int fit_max_resident_warps(int k, int nsm);
+
+struct FitParams {
+    int nbatch, iopt, m, k, nest, nestp;
+    const double *x, *y, *w;
+    long long x_sb, x_si, y_sb, y_si, w_sb, w_si;
+    const double *xb, *xe;
+    int xbe_stride;
+    const double *s;
+    int s_stride;
+    int *n;
+    double *t, *c, *fp;
+    int *ier;
+    double *fpint;
+    int *nrdata;
+    int *stats;
+    double *ws;             // [resident warps][ws_per_lane][32]
+    int *wsi;               // [resident warps][nestp][32]   (nrdata)
+    unsigned int *counter;  // tile queue head, zeroed before the launch
+    int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q, ws_per_lane;
+};
+cudaError_t launch_curfit(const FitParams &p, int grid_blocks, cudaStream_t stream);
+
+// ---- shared-abscissa least squares (iopt=-1, one x/w/t for the whole batch) ----
+struct SharedPlan {
+    // device buffers owned by the engine
+    double *cs_sn;   // [m][k1][2]  rotation parameters per (point, band column)
+    double *wgt;     // [m]         weights (1 when w==NULL)
+    int *lrow;       // [m]         first band row (0-based) the point touches = l-k1
+    int *skip;       // [m]         bit i set: pivot i was (sub)normal-zero -> rotation skipped
+    double *R;       // [nk1][k1]   final triangular band factor
+    int *ier;        // [1]
+};
+cudaError_t launch_shared_plan(const double *x, const double *w, int m, double xb, double xe, int k,
+                               int n, double *t, const SharedPlan &plan, cudaStream_t stream);
+cudaError_t launch_shared_apply(int nbatch, int m, int k, int n, const double *y, long long y_sb,
+                                long long y_si, const SharedPlan &plan, double *c, long long ldc,
+                                double *fp, int nsm, cudaStream_t stream);
+
+// ---- evaluation ----
+struct SplevParams {
+    int nspl, ldt, k, m, e, mode, nshared;
+    const double *t, *c, *x;
+    const int *n;
+    double *y;
+    int *ier;
+    int *lidx;
+};
+cudaError_t launch_splev(const SplevParams &p, int nsm, cudaStream_t stream);
+
+// ---- utilities ----
+cudaError_t launch_transpose(const double *src, long long ld_src, double *dst, long long ld_dst,
+                             long long rows, long long cols, cudaStream_t stream);
+cudaError_t launch_fill_i32(int *dst, int value, long long count, cudaStream_t stream);
+cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused, cudaStream_t stream);
+
+}  // namespace fpb

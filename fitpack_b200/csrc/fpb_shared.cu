@@ -1,0 +1,276 @@
+// fpb_shared.cu -- shared-abscissa least-squares fast path (curfit iopt=-1 with
+// one x / w / knot set for the whole batch; BASELINE config 3).
+//
+// Reference: curfit core:1240-1299 (iopt=-1 branch, fpchec 2507-2570) and the
+// LSQ pass of fpcurf core:4859-4906 (fpbspl, fp_rotate_row, fpgivs, fprota,
+// fpback).  In that pass the Givens parameters depend only on (x, w, t): every
+// curve of the batch would regenerate the SAME cos/sin.  So:
+//   1. `shared_plan_kernel` runs the matrix half of the pass ONCE (the reference's
+//      arithmetic, sequential over the m points) and records, per point, the band
+//      row it starts at, the k+1 (cos, sin) pairs and which pivots were skipped;
+//      it also leaves the final triangular band factor R.
+//   2. `shared_apply_kernel` (the hot kernel, one thread per curve) streams y
+//      point-major with coalesced loads and applies the recorded rotations to the
+//      curve's own right-hand side only: 4 mul + 2 add per rotation, no sqrt, no
+//      division.  The plan is staged tile by tile through shared memory and
+//      read by all lanes as a broadcast; the k+1 live right-hand-side entries sit
+//      in registers and retire to a shared-memory column as the band window
+//      advances (uniform control flow: the window schedule is shared).
+//   3. back-substitution with the shared R, then a transposed, coalesced store
+//      of c (curve-major, as the caller holds it).
+// Results are bit-identical to running curfit(iopt=-1) per curve: the same IEEE
+// operations in the same order, no FMA.
+#include "fpb_common.cuh"
+#include "fpb_kernels.h"
+
+namespace fpb {
+
+namespace {
+
+constexpr int kApplyThreads = 128;
+constexpr int kPlanChunk = 64;  // points per staged plan tile
+
+template <int K>
+__global__ void shared_plan_kernel(const double *x, const double *w, int m, double xb, double xe,
+                                   int n, double *t, SharedPlan plan)
+{
+    constexpr int K1 = K + 1, K2 = K + 2;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nmin = 2 * K1;
+    auto X = [&](int i) { return x[i - 1]; };
+    auto Tt = [&](int i) -> double & { return t[i - 1]; };
+    // ---- curfit checks, core:1265-1285 ----
+    int ier = IER_INPUT;
+    *plan.ier = ier;
+    if (m < K1) return;
+    if (xb > X(1) || xe < X(m)) return;
+    for (int i = 1; i < m; ++i)
+        if (X(i) > X(i + 1)) return;
+    if (n < nmin) return;
+    {
+        int j = n;
+        for (int i = 1; i <= K1; ++i) {
+            Tt(i) = xb;
+            Tt(j) = xe;
+            --j;
+        }
+    }
+    // ---- fpchec, core:2507-2570 ----
+    const int nk1 = n - K1, nk2 = nk1 + 1;
+    if (nk1 < K1 || nk1 > m) return;
+    {
+        int j = n;
+        for (int i = 1; i <= K; ++i) {
+            if (Tt(i) > Tt(i + 1)) return;
+            if (Tt(j) < Tt(j - 1)) return;
+            --j;
+        }
+        for (int i = K2; i <= nk2; ++i)
+            if (Tt(i) <= Tt(i - 1)) return;
+        if (X(1) < Tt(K1) || X(m) > Tt(nk2)) return;
+        if (X(1) >= Tt(K2) || X(m) <= Tt(nk1)) return;
+        int i = 1, l = K2;
+        const int nk3 = nk1 - 1;
+        for (j = 2; j <= nk3; ++j) {
+            const double tj = Tt(j);
+            ++l;
+            const double tl = Tt(l);
+            while (i < m && X(i) <= tj) {
+                ++i;
+                if (i >= m) return;
+            }
+            if (X(i) >= tl) return;
+        }
+    }
+    // ---- matrix half of the LSQ pass, core:4867-4896 ----
+    double *R = plan.R;
+    for (int i = 0; i < nk1 * K1; ++i) R[i] = 0.0;
+    int l = K1;
+    for (int it = 1; it <= m; ++it) {
+        const double xi = X(it);
+        const double wi = w ? w[it - 1] : 1.0;
+        while (l < nk1 && xi >= Tt(l + 1)) ++l;
+        double tw[2 * K], h[K1];
+#pragma unroll
+        for (int j = 0; j < 2 * K; ++j) tw[j] = Tt(l - K + 1 + j);
+        bspl<K>(tw, xi, h);
+#pragma unroll
+        for (int j = 0; j < K1; ++j) h[j] = mul(wi, h[j]);
+        int skip = 0;
+        const int row0 = l - K1;  // 0-based first band row
+#pragma unroll
+        for (int i = 0; i < K1; ++i) {
+            const double piv = h[i];
+            double cs = 1.0, sn = 0.0;
+            if (fp_is_zero(piv)) {
+                skip |= (1 << i);
+            } else {
+                double *Rrow = R + (size_t)(row0 + i) * K1;
+                givens(piv, Rrow[0], cs, sn);
+#pragma unroll
+                for (int q = 1; q <= K - i; ++q) rota(cs, sn, h[i + q], Rrow[q]);
+            }
+            plan.cs_sn[((size_t)(it - 1) * K1 + i) * 2] = cs;
+            plan.cs_sn[((size_t)(it - 1) * K1 + i) * 2 + 1] = sn;
+        }
+        plan.wgt[it - 1] = wi;
+        plan.lrow[it - 1] = row0;
+        plan.skip[it - 1] = skip;
+    }
+    *plan.ier = IER_OK;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kApplyThreads)
+    shared_apply_kernel(int nbatch, int m, int n, const double *__restrict__ y, long long y_sb,
+                        long long y_si, SharedPlan plan, double *__restrict__ c, long long ldc,
+                        double *__restrict__ fp_out)
+{
+    constexpr int K1 = K + 1;
+    constexpr int ZLD = kApplyThreads + 1;
+    extern __shared__ __align__(16) double sm[];
+    const int nk1 = n - K1;
+    double *zs = sm;                                        // [nk1][ZLD]
+    double *Rs = zs + (size_t)nk1 * ZLD;                    // [nk1][K1]
+    double *pcs = Rs + (size_t)nk1 * K1;                    // [kPlanChunk][2*K1]
+    double *pw = pcs + (size_t)kPlanChunk * 2 * K1;         // [kPlanChunk]
+    int *prow = reinterpret_cast<int *>(pw + kPlanChunk);   // [kPlanChunk]
+    int *pskip = prow + kPlanChunk;                         // [kPlanChunk]
+    const int tid = threadIdx.x;
+    if (*plan.ier != IER_OK) return;
+    for (int i = tid; i < nk1 * K1; i += kApplyThreads) Rs[i] = plan.R[i];
+
+    const long long ntiles = ((long long)nbatch + kApplyThreads - 1) / kApplyThreads;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long b = tile * kApplyThreads + tid;
+        const bool valid = b < nbatch;
+        const double *yp = y + (valid ? b : 0) * y_sb;
+        double Zw[K1];
+#pragma unroll
+        for (int r = 0; r < K1; ++r) Zw[r] = 0.0;
+        double fp = 0.0;
+        int cur = 0;  // band row held in Zw[0]
+        for (int base = 0; base < m; base += kPlanChunk) {
+            const int cnt = min(kPlanChunk, m - base);
+            __syncthreads();  // previous chunk fully consumed
+            for (int i = tid; i < cnt * 2 * K1; i += kApplyThreads)
+                pcs[i] = plan.cs_sn[(size_t)base * 2 * K1 + i];
+            for (int i = tid; i < cnt; i += kApplyThreads) {
+                pw[i] = plan.wgt[base + i];
+                prow[i] = plan.lrow[base + i];
+                pskip[i] = plan.skip[base + i];
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int q = 0; q < cnt; ++q) {
+                double yi = mul(yp[(long long)(base + q) * y_si], pw[q]);
+                const int row0 = prow[q];
+                while (cur < row0) {  // uniform across the block
+                    zs[(size_t)cur * ZLD + tid] = Zw[0];
+#pragma unroll
+                    for (int r = 0; r < K; ++r) Zw[r] = Zw[r + 1];
+                    Zw[K] = 0.0;
+                    ++cur;
+                }
+                const int skip = pskip[q];
+#pragma unroll
+                for (int i = 0; i < K1; ++i) {
+                    if (!((skip >> i) & 1))
+                        rota(pcs[(q * K1 + i) * 2], pcs[(q * K1 + i) * 2 + 1], yi, Zw[i]);
+                }
+                fp = add(fp, mul(yi, yi));
+            }
+        }
+        while (cur < nk1 - K1) {
+            zs[(size_t)cur * ZLD + tid] = Zw[0];
+#pragma unroll
+            for (int r = 0; r < K; ++r) Zw[r] = Zw[r + 1];
+            Zw[K] = 0.0;
+            ++cur;
+        }
+#pragma unroll
+        for (int r = 0; r < K1; ++r) zs[(size_t)(cur + r) * ZLD + tid] = Zw[r];
+        // fpback, core:1808-1838 (own column of zs only: no barrier needed)
+        double cw[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) cw[q] = 0.0;
+        for (int i = nk1 - 1; i >= 0; --i) {
+            double store = zs[(size_t)i * ZLD + tid];
+            const int cnt = min(nk1 - 1 - i, K);
+#pragma unroll
+            for (int q = 1; q <= K; ++q)
+                if (q <= cnt) store = sub(store, mul(cw[q - 1], Rs[i * K1 + q]));
+            const double ci = store / Rs[i * K1];
+            zs[(size_t)i * ZLD + tid] = ci;
+#pragma unroll
+            for (int q = K - 1; q >= 1; --q) cw[q] = cw[q - 1];
+            cw[0] = ci;
+        }
+        if (valid) fp_out[b] = fp;
+        __syncthreads();
+        // transposed store: each warp writes its 32 curves, one curve per step, lanes along i
+        {
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int cb = 0; cb < 32; ++cb) {
+                const long long bc = tile * kApplyThreads + warp * 32 + cb;
+                if (bc >= nbatch) break;
+                for (int i = lane; i < nk1; i += 32)
+                    c[bc * ldc + i] = zs[(size_t)i * ZLD + warp * 32 + cb];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_shared_plan(const double *x, const double *w, int m, double xb, double xe, int k,
+                               int n, double *t, const SharedPlan &plan, cudaStream_t stream)
+{
+    switch (k) {
+    case 1: shared_plan_kernel<1><<<1, 32, 0, stream>>>(x, w, m, xb, xe, n, t, plan); break;
+    case 2: shared_plan_kernel<2><<<1, 32, 0, stream>>>(x, w, m, xb, xe, n, t, plan); break;
+    case 3: shared_plan_kernel<3><<<1, 32, 0, stream>>>(x, w, m, xb, xe, n, t, plan); break;
+    case 4: shared_plan_kernel<4><<<1, 32, 0, stream>>>(x, w, m, xb, xe, n, t, plan); break;
+    case 5: shared_plan_kernel<5><<<1, 32, 0, stream>>>(x, w, m, xb, xe, n, t, plan); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shared_apply(int nbatch, int m, int k, int n, const double *y, long long y_sb,
+                                long long y_si, const SharedPlan &plan, double *c, long long ldc,
+                                double *fp, int nsm, cudaStream_t stream)
+{
+    if (nbatch <= 0) return cudaSuccess;
+    const int k1 = k + 1, nk1 = n - k1;
+    const size_t smem = sizeof(double) * ((size_t)nk1 * (kApplyThreads + 1) + (size_t)nk1 * k1 +
+                                          (size_t)kPlanChunk * 2 * k1 + kPlanChunk) +
+                        sizeof(int) * 2 * kPlanChunk;
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    long long tiles = ((long long)nbatch + kApplyThreads - 1) / kApplyThreads;
+    long long resident = (long long)(220 * 1024 / smem);
+    if (resident > 8) resident = 8;
+    if (resident < 1) resident = 1;
+    long long grid = tiles < nsm * resident ? tiles : nsm * resident;
+#define FPB_LAUNCH_APPLY(KK)                                                                       \
+    do {                                                                                           \
+        cudaError_t e_ = cudaFuncSetAttribute(shared_apply_kernel<KK>,                             \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                              (int)smem);                                          \
+        if (e_ != cudaSuccess) return e_;                                                          \
+        shared_apply_kernel<KK><<<(unsigned)grid, kApplyThreads, smem, stream>>>(                  \
+            nbatch, m, n, y, y_sb, y_si, plan, c, ldc, fp);                                        \
+    } while (0)
+    switch (k) {
+    case 1: FPB_LAUNCH_APPLY(1); break;
+    case 2: FPB_LAUNCH_APPLY(2); break;
+    case 3: FPB_LAUNCH_APPLY(3); break;
+    case 4: FPB_LAUNCH_APPLY(4); break;
+    case 5: FPB_LAUNCH_APPLY(5); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef FPB_LAUNCH_APPLY
+    return cudaGetLastError();
+}
+
+}  // namespace fpb

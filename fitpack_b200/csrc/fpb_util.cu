@@ -1,0 +1,101 @@
+// fpb_util.cu -- layout helpers: tile transpose between the caller's curve-major
+// arrays ([curve][point], what a Fortran/C caller of curfit holds) and the
+// point-major SoA layout ([point][curve]) the fit kernels stream with coalesced
+// loads.  HBM-bound, 16 B/element of traffic; 32x32 tiles staged in shared memory
+// (padded to 33 columns: conflict-free for 8-byte elements in both phases).
+#include "fpb_kernels.h"
+
+namespace fpb {
+
+namespace {
+
+__global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ src,
+                                                        long long ld_src, double *__restrict__ dst,
+                                                        long long ld_dst, long long rows,
+                                                        long long cols, long long tiles_c)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const long long ntiles = tiles_c * ((rows + 31) / 32);
+    for (long long tid = blockIdx.x; tid < ntiles; tid += gridDim.x) {
+        const long long tr = tid / tiles_c, tc = tid % tiles_c;
+        const long long r0 = tr * 32, c0 = tc * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const long long r = r0 + ty + j, c = c0 + tx;
+            if (r < rows && c < cols) tile[ty + j][tx] = src[r * ld_src + c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const long long c = c0 + ty + j, r = r0 + tx;
+            if (r < rows && c < cols) dst[c * ld_dst + r] = tile[tx][ty + j];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void fill_i32_kernel(int *dst, int value, long long count)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = value;
+}
+
+}  // namespace
+
+cudaError_t launch_transpose(const double *src, long long ld_src, double *dst, long long ld_dst,
+                             long long rows, long long cols, cudaStream_t stream)
+{
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    const long long tiles_c = (cols + 31) / 32;
+    long long ntiles = tiles_c * ((rows + 31) / 32);
+    const long long grid = ntiles < 148LL * 32 ? ntiles : 148LL * 32;
+    transpose_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, ld_src, dst, ld_dst, rows, cols,
+                                                         tiles_c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_i32(int *dst, int value, long long count, cudaStream_t stream)
+{
+    if (count <= 0) return cudaSuccess;
+    long long grid = (count + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    fill_i32_kernel<<<(unsigned)grid, 256, 0, stream>>>(dst, value, count);
+    return cudaGetLastError();
+}
+
+}  // namespace fpb
+
+// ---- FP64 pipe probe (roofline denominator for the fit kernel; MEASURED_PEAKS.json has no
+// FP64 figure).  8 independent dependent-chains per thread; fused=0 issues DMUL+DADD pairs
+// (what the parity-exact kernels are allowed to use), fused=1 issues DFMA.
+namespace fpb {
+namespace {
+template <bool FUSED>
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters, double a, double b)
+{
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 1.0 + 1e-9 * (threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (FUSED) v[j] = fma(v[j], a, b);
+            else v[j] = __dadd_rn(__dmul_rn(v[j], a), b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+}  // namespace
+
+cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused, cudaStream_t stream)
+{
+    if (fused) fp64_probe_kernel<true><<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999, 1e-7);
+    else fp64_probe_kernel<false><<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999, 1e-7);
+    return cudaGetLastError();
+}
+}  // namespace fpb

@@ -1,0 +1,230 @@
+/*
+ * fitpack_b200.h -- C-ABI of the B200-native batched spline engine.
+ *
+ * Drop-in boundary for the curfit/fpcurf + splev/fpbspl hot path of
+ * perazz/fitpack.  Three groups of entry points:
+ *
+ *  (A) the reference's own symbols for this path, same names, same argument
+ *      lists, same error behaviour -- a caller linked against the reference's
+ *      libfitpack can link against libfitpack_b200 instead:
+ *        fp_curfit_c, fp_splev_c, FITPACK_SUCCESS_c, fitpack_message_c
+ *          (reference: include/fitpack_core_c.h:69,84,98-101,131-132;
+ *           src/fitpack_core_c.f90:44-74,145-154)
+ *        fitpack_curve_c_* opaque-handle API
+ *          (reference: include/fitpack_curves_c.h:37-63;
+ *           src/fitpack_curves_c.f90:56-396)
+ *      These run the SAME CUDA kernels as a batch of one curve.
+ *
+ *  (B) NEW batch entry points (the reference has none): many independent
+ *      curves per call, host-pointer and device-pointer variants, optional
+ *      sharding over the GPUs of one node.
+ *
+ *  (C) engine lifetime / introspection.
+ *
+ * All reals are IEEE binary64, all integers int32 (FP_REAL/FP_SIZE/FP_FLAG of
+ * the reference, src/fitpack_core.F90:26-29).  There is NO CPU fallback: every
+ * compute entry point needs a CUDA device and reports FPB_ERR_CUDA otherwise.
+ */
+#ifndef FITPACK_B200_H_INCLUDED
+#define FITPACK_B200_H_INCLUDED
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef double  FP_REAL;
+typedef int32_t FP_SIZE;
+typedef int32_t FP_FLAG;
+typedef bool    FP_BOOL;
+
+/* out-of-support policy of splev (reference core:101-105) */
+#define FPB_OUTSIDE_EXTRAPOLATE 0
+#define FPB_OUTSIDE_ZERO        1
+#define FPB_OUTSIDE_NOT_ALLOWED 2
+#define FPB_OUTSIDE_NEAREST_BND 3
+
+/* iopt (reference core:107-111) */
+#define FPB_IOPT_NEW_LEASTSQUARES (-1)
+#define FPB_IOPT_NEW_SMOOTHING      0
+#define FPB_IOPT_OLD_FIT            1
+
+/* ier codes (reference core:129-144) */
+#define FPB_OK                     0
+#define FPB_INTERPOLATING_OK     (-1)
+#define FPB_LEASTSQUARES_OK      (-2)
+#define FPB_INSUFFICIENT_STORAGE   1
+#define FPB_S_TOO_SMALL            2
+#define FPB_MAXIT                  3
+#define FPB_INVALID_RANGE          6
+#define FPB_INPUT_ERROR           10
+
+/* status of the batch/engine calls themselves (not per-curve ier) */
+#define FPB_STATUS_OK      0
+#define FPB_ERR_CUDA     (-100)  /* no device / CUDA runtime error (see fpb_last_error) */
+#define FPB_ERR_ARG      (-101)  /* invalid call-level argument (k, m, nest, strides...) */
+#define FPB_ERR_ALLOC    (-102)  /* device or host allocation failed */
+
+/* splev evaluation mode for the batch entry points */
+#define FPB_SPLEV_EXACT 0  /* de Boor-Cox exactly as the reference: bit-identical values    */
+#define FPB_SPLEV_FAST  1  /* per-interval local polynomial + Horner/FMA: HBM-bound;
+                              identical interval indices, values within 1e-12*max|c|        */
+
+/* ------------------------------------------------------------------ (A) -- */
+/* reference: src/fitpack_core_c.f90:44-47 */
+FP_BOOL FITPACK_SUCCESS_c(FP_FLAG ierr);
+/* reference: src/fitpack_core_c.f90:50-61 (NUL-terminated into caller buffer) */
+void fitpack_message_c(FP_FLAG ierr, char *msg);
+
+/* reference: src/fitpack_core_c.f90:64-74 -> curfit core:1240-1299.
+   Host pointers.  wrk/iwrk keep the reference's meaning: on return
+   wrk[0..nest) holds fpint and iwrk[0..nest) holds nrdata, which is the state an
+   iopt=1 continuation reads back (core:4825-4834, 4898-4900). */
+void fp_curfit_c(FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y, const FP_REAL *w,
+                 FP_REAL xb, FP_REAL xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
+                 FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
+                 FP_REAL *wrk, FP_SIZE lwrk, FP_SIZE *iwrk, FP_FLAG *ier);
+
+/* reference: src/fitpack_core_c.f90:145-154 -> splev core:17826-17896 */
+void fp_splev_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, const FP_REAL *x,
+                FP_REAL *y, FP_SIZE m, FP_FLAG e, FP_FLAG *ier);
+
+/* Opaque-handle curve API, reference include/fitpack_curves_c.h:37-63.
+   Optional arguments are nullable pointers exactly as in the reference
+   (src/fitpack_curves_c.f90:159-163,176-182,195-199). */
+typedef struct fitpack_curve_c {
+    void *cptr;
+} fitpack_curve_c;
+
+void    fitpack_curve_c_allocate     (fitpack_curve_c *self);
+void    fitpack_curve_c_destroy      (fitpack_curve_c *self);
+void    fitpack_curve_c_copy         (fitpack_curve_c *self, const fitpack_curve_c *other);
+void    fitpack_curve_c_move_alloc   (fitpack_curve_c *to, fitpack_curve_c *from);
+void    fitpack_curve_c_new_points   (fitpack_curve_c *self, FP_SIZE npts, FP_REAL *x, FP_REAL *y, FP_REAL *w);
+FP_FLAG fitpack_curve_c_new_fit      (fitpack_curve_c *self, FP_SIZE npts, FP_REAL *x, FP_REAL *y, FP_REAL *w, FP_REAL *smoothing);
+FP_FLAG fitpack_curve_c_fit          (fitpack_curve_c *self, FP_REAL *smoothing, FP_SIZE *order);
+FP_FLAG fitpack_curve_c_interpolating(fitpack_curve_c *self, FP_SIZE *order);
+FP_REAL fitpack_curve_c_eval_one     (fitpack_curve_c *self, FP_REAL x, FP_FLAG *ierr);
+void    fitpack_curve_c_eval_many    (fitpack_curve_c *self, FP_SIZE npts, FP_REAL *x, FP_REAL *y, FP_FLAG *ierr);
+FP_REAL fitpack_curve_c_smoothing    (fitpack_curve_c *self);
+FP_REAL fitpack_curve_c_mse          (fitpack_curve_c *self);
+FP_SIZE fitpack_curve_c_degree       (fitpack_curve_c *self);
+void    fitpack_curve_c_set_bc       (fitpack_curve_c *self, FP_FLAG bc);
+FP_FLAG fitpack_curve_c_get_bc       (fitpack_curve_c *self);
+/* extras the Fortran type exposes as public components (src/fitpack_curves.f90:54-78);
+   needed by host code that reads knots/coefficients back */
+FP_FLAG fitpack_curve_c_least_squares(fitpack_curve_c *self, FP_REAL *smoothing, FP_BOOL *reset_knots);
+FP_SIZE fitpack_curve_c_knots        (fitpack_curve_c *self);
+FP_SIZE fitpack_curve_c_get_t        (fitpack_curve_c *self, FP_SIZE nmax, FP_REAL *t);
+FP_SIZE fitpack_curve_c_get_c        (fitpack_curve_c *self, FP_SIZE nmax, FP_REAL *c);
+FP_SIZE fitpack_curve_c_set_knots    (fitpack_curve_c *self, FP_SIZE n, const FP_REAL *t);
+FP_FLAG fitpack_curve_c_iopt         (fitpack_curve_c *self);
+
+/* ------------------------------------------------------------------ (C) -- */
+typedef struct fpb_engine fpb_engine;   /* one per GPU: stream + workspace   */
+
+/* create an engine on CUDA device `device` (-1: current device). */
+int32_t fpb_engine_create(int32_t device, fpb_engine **out);
+void    fpb_engine_destroy(fpb_engine *eng);
+/* make the engine launch on an externally owned stream (cudaStream_t, e.g. torch's current
+   stream).  The handle is taken literally: NULL is CUDA's default stream.
+   fpb_engine_reset_stream goes back to the engine's own non-blocking stream. */
+int32_t fpb_engine_set_stream(fpb_engine *eng, void *cuda_stream);
+int32_t fpb_engine_reset_stream(fpb_engine *eng);
+int32_t fpb_engine_synchronize(fpb_engine *eng);
+/* number of kernels this engine has launched since creation (bench bookkeeping) */
+int64_t fpb_engine_launch_count(const fpb_engine *eng);
+/* device time in ms of the last dominant kernel (fit or splev), measured with
+   CUDA events on the engine's stream; valid after fpb_engine_synchronize */
+double  fpb_engine_last_kernel_ms(fpb_engine *eng);
+/* FP64 pipe probe: achieved 1e9 FP64 instructions/s of a register-resident kernel issuing
+   DMUL+DADD pairs (fused=0; the only forms the parity-exact kernels may use) or DFMA
+   (fused=1).  Roofline denominator of the fit kernel. */
+double  fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused);
+int32_t fpb_device_count(void);
+const char *fpb_last_error(void);
+const char *fpb_version(void);
+
+/* ------------------------------------------------------------------ (B) -- */
+/*
+ * Batched curfit on DEVICE pointers (the hot path).  One thread per curve.
+ * Element i of curve b of array A is A[b*A_sb + i*A_si]:
+ *   point-major / SoA (fast, coalesced):  A_sb = 1, A_si = ld (>= nbatch)
+ *   curve-major:                          A_sb = ld (>= m), A_si = 1
+ *   shared by all curves:                 A_sb = 0
+ * w == NULL means unit weights.  xb/xe: per-curve arrays (xbe_stride=1), one
+ * shared value (xbe_stride=0) or NULL (use x(1), x(m) of each curve).
+ * s: per-curve (s_stride=1) or shared (s_stride=0).
+ * Outputs are curve-major: n[b], fp[b], ier[b], t[b*nest+i], c[b*nest+i].
+ * iopt=-1: n and t are inputs (interior knots in place, as for curfit).
+ * iopt= 1: n, t, fpint, nrdata are in/out state of the previous call
+ *          (fpint,nrdata: [nbatch][nest]); they may be NULL for iopt<=0.
+ * stats (optional, [nbatch][2]): LSQ passes and p-iterations per curve.
+ * Per-curve argument errors give ier[b]=10 exactly as curfit does; the return
+ * value only reports call-level problems (FPB_ERR_*).
+ */
+int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m,
+                              const FP_REAL *x, int64_t x_sb, int64_t x_si,
+                              const FP_REAL *y, int64_t y_sb, int64_t y_si,
+                              const FP_REAL *w, int64_t w_sb, int64_t w_si,
+                              const FP_REAL *xb, const FP_REAL *xe, FP_SIZE xbe_stride,
+                              FP_SIZE k, const FP_REAL *s, FP_SIZE s_stride, FP_SIZE nest,
+                              FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
+                              FP_REAL *fpint, FP_SIZE *nrdata, FP_SIZE *stats);
+
+/*
+ * Shared-abscissa least-squares fast path (iopt=-1, one x/w/knot set for the
+ * whole batch): the Givens rotations depend only on (x,w,t) and are generated
+ * once; every curve applies them to its own right-hand side.
+ * y is strided as above; outputs c[b*ldc + i] (i < n-k-1), fp[b], ier (scalar,
+ * from the argument/knot checks of curfit+fpchec).  x,w,t are DEVICE arrays of
+ * length m, m, n (w may be NULL).
+ */
+int32_t fp_curfit_shared_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE m,
+                               const FP_REAL *x, const FP_REAL *w,
+                               const FP_REAL *y, int64_t y_sb, int64_t y_si,
+                               FP_REAL xb, FP_REAL xe, FP_SIZE k, FP_SIZE n, FP_REAL *t,
+                               FP_REAL *c, int64_t ldc, FP_REAL *fp, FP_FLAG *ier);
+
+/*
+ * Batched splev on DEVICE pointers.  Spline j has knots t[j*ldt + 0..n[j]) and
+ * coefficients c[j*ldt + ...]; it is evaluated at x[j*m + 0..m) into y[j*m + ..].
+ * nshared != 0: a single spline (j=0) evaluated at all nspl*m points.
+ * lidx (optional, same shape as y): the 1-based knot interval index used.
+ * ier[j] as splev: 0, 10 (m<1), or 6 (e=2 and a point outside the support; y of
+ * that spline is then unspecified from the first offender on, as in the reference).
+ */
+int32_t fp_splev_batch_dev_c(fpb_engine *eng, FP_SIZE nspl, const FP_REAL *t, const FP_SIZE *n,
+                             const FP_REAL *c, FP_SIZE ldt, FP_SIZE k, const FP_REAL *x,
+                             FP_REAL *y, FP_SIZE m, FP_FLAG e, FP_SIZE mode, FP_SIZE nshared,
+                             FP_FLAG *ier, FP_SIZE *lidx);
+
+/*
+ * Host-pointer batch calls (curve-major arrays, as a Fortran/C caller holds
+ * them): copy in, tile-transpose on the device, run the kernels above, copy
+ * out.  ngpus>1 shards the batch in contiguous slices over the first `ngpus`
+ * devices (independent curves: no collective).  ngpus<=0: all visible devices.
+ *   x,y,w : [nbatch][m]  (w NULL => 1; shared_x!=0 => x,w are [m])
+ *   xb,xe : NULL => data range of each curve; else scalars by pointer
+ */
+int32_t fp_curfit_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x,
+                          const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
+                          const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
+                          FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
+                          FP_SIZE ngpus);
+
+int32_t fp_splev_batch_c(FP_SIZE nspl, const FP_REAL *t, const FP_SIZE *n, const FP_REAL *c,
+                         FP_SIZE ldt, FP_SIZE k, const FP_REAL *x, FP_REAL *y, FP_SIZE m,
+                         FP_FLAG e, FP_SIZE mode, FP_FLAG *ier, FP_SIZE ngpus);
+
+/* device tile transpose helper: dst[j*ld_dst + i] = src[i*ld_src + j], i<rows, j<cols */
+int32_t fpb_transpose_dev(fpb_engine *eng, const FP_REAL *src, int64_t ld_src, FP_REAL *dst,
+                          int64_t ld_dst, int64_t rows, int64_t cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FITPACK_B200_H_INCLUDED */
