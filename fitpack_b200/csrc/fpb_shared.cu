@@ -117,7 +117,8 @@ __global__ void shared_plan_kernel(const double *x, const double *w, int m, doub
         plan.lrow[it - 1] = row0;
         plan.skip[it - 1] = skip;
     }
-    *plan.ier = IER_OK;
+    // curfit reports the polynomial case (no interior knots) as ier=-2 (core:4852)
+    *plan.ier = (n == nmin) ? IER_LSQ : IER_OK;
 }
 
 template <int K>
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kApplyThreads)
     int *prow = reinterpret_cast<int *>(pw + kPlanChunk);   // [kPlanChunk]
     int *pskip = prow + kPlanChunk;                         // [kPlanChunk]
     const int tid = threadIdx.x;
-    if (*plan.ier != IER_OK) return;
+    if (*plan.ier > 0) return;  // ier<=0: success codes (0, or -2 for the polynomial)
     for (int i = tid; i < nk1 * K1; i += kApplyThreads) Rs[i] = plan.R[i];
 
     const long long ntiles = ((long long)nbatch + kApplyThreads - 1) / kApplyThreads;

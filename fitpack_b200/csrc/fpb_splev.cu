@@ -76,13 +76,15 @@ __host__ __device__ inline int splev_smem_doubles(int mode, int k, int ld)
     return (mode == 1) ? ld * (2 + k + (k + 1)) : ld * 2;
 }
 
-// interval search: l = k1 + #{ i in (k1, nk1] : t(i) <= arg }  (1-based), t non-decreasing
-__device__ __forceinline__ int find_interval(const double *ts, int k1, int nk1, double arg)
+// interval search: l = k1 + #{ i in (k1, nk1] : t(i) <= arg }  (1-based), t non-decreasing.
+// Fixed number of halving steps (`top` = largest power of two <= nk1-k1, uniform per spline),
+// so the 32 lanes never diverge.
+__device__ __forceinline__ int find_interval(const double *ts, int k1, int nk1, int top, double arg)
 {
-    int lo = k1, hi = nk1;  // invariant: t(lo) <= arg or lo==k1 ; t(hi+1) > arg or hi==nk1
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (ts[mid - 1] <= arg) lo = mid; else hi = mid - 1;
+    int lo = k1;
+    for (int step = top; step > 0; step >>= 1) {
+        const int cand = lo + step;
+        if (cand <= nk1 && ts[cand - 1] <= arg) lo = cand;
     }
     return lo;
 }
@@ -162,15 +164,18 @@ __device__ void build_local_polys(const double *ts, const double *cs, int n, int
     __syncwarp();
 }
 
-template <int K>
-__global__ void __launch_bounds__(kSplevWarps * 32) splev_kernel(SplevParams p, int smem_ld)
+constexpr int kUnroll = 4;  // independent points per lane per iteration (memory-level parallelism)
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
+    splev_kernel(SplevParams p, int smem_ld)
 {
     constexpr int K1 = K + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     // per-warp regions: [t: ld][c: ld] and in fast mode [dlev: K*ld][poly: K1*ld]
-    const int per_warp = splev_smem_doubles(p.mode, K, smem_ld);
+    const int per_warp = splev_smem_doubles(MODE, K, smem_ld);
     uint64_t *mbars = reinterpret_cast<uint64_t *>(smem_raw);
     double *base = reinterpret_cast<double *>(smem_raw + 16 * kSplevWarps) + (size_t)warp * per_warp;
     double *ts = base, *cs = base + smem_ld, *dlev = base + 2 * smem_ld,
@@ -212,40 +217,58 @@ __global__ void __launch_bounds__(kSplevWarps * 32) splev_kernel(SplevParams p, 
                 }
             }
             __syncwarp();
-            if (p.mode == 1) build_local_polys<K>(ts, cs, n, smem_ld, dlev, poly, lane);
+            if (MODE == 1) build_local_polys<K>(ts, cs, n, smem_ld, dlev, poly, lane);
             __syncwarp();
             cached = (int)tj;
         }
         const int nk1 = n - K1;
+        int top = 1;
+        while (top * 2 <= nk1 - K1) top *= 2;
+        if (nk1 - K1 < 1) top = 0;
         const double tb = ts[K1 - 1], te = ts[nk1];
         const double *xg = p.x + j * p.m;
         double *yg = p.y + j * p.m;
         int *lg = p.lidx ? p.lidx + j * p.m : nullptr;
         bool out_of_range = false;
-        for (int i = lane; i < p.m; i += 32) {
-            double arg = xg[i];
-            bool zero = false;
-            if (arg < tb || arg > te) {  // core:17864-17877
-                if (p.e == 1) zero = true;
-                else if (p.e == 2) out_of_range = true;
-                else if (p.e == 3) arg = fmax(fmin(arg, te), tb);
-            }
-            double sp = 0.0;
-            int l = 0;
-            if (!zero) {
-                l = find_interval(ts, K1, nk1, arg);
-                if (p.mode == 1) {
-                    const double *pl = poly + (l - K1) * K1;
-                    const double u = arg - ts[l - 1];
-                    sp = pl[K];
+        for (int i0 = lane; i0 < p.m; i0 += 32 * kUnroll) {
+            double arg[kUnroll];
+            bool live[kUnroll], zero[kUnroll];
 #pragma unroll
-                    for (int r = K - 1; r >= 0; --r) sp = fma(sp, u, pl[r]);
-                } else {
-                    sp = eval_exact<K>(ts, cs, l, arg);
+            for (int u = 0; u < kUnroll; ++u) {
+                const int i = i0 + 32 * u;
+                live[u] = i < p.m;
+                arg[u] = live[u] ? xg[i] : tb;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                zero[u] = false;
+                if (arg[u] < tb || arg[u] > te) {  // core:17864-17877
+                    if (p.e == 1) zero[u] = true;
+                    else if (p.e == 2) out_of_range = out_of_range || live[u];
+                    else if (p.e == 3) arg[u] = fmax(fmin(arg[u], te), tb);
                 }
             }
-            yg[i] = sp;
-            if (lg) lg[i] = l;
+            int l[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) l[u] = find_interval(ts, K1, nk1, top, arg[u]);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                double sp;
+                if (MODE == 1) {
+                    const double *pl = poly + (l[u] - K1) * K1;
+                    const double uu = arg[u] - ts[l[u] - 1];
+                    sp = pl[K];
+#pragma unroll
+                    for (int r = K - 1; r >= 0; --r) sp = fma(sp, uu, pl[r]);
+                } else {
+                    sp = eval_exact<K>(ts, cs, l[u], arg[u]);
+                }
+                const int i = i0 + 32 * u;
+                if (live[u]) {
+                    yg[i] = zero[u] ? 0.0 : sp;
+                    if (lg) lg[i] = zero[u] ? 0 : l[u];
+                }
+            }
         }
         if (p.ier) {
             const bool any_out = __any_sync(FULL, out_of_range);
@@ -271,11 +294,11 @@ cudaError_t launch_splev(const SplevParams &p, int nsm, cudaStream_t stream)
     if (blocks > max_blocks) blocks = max_blocks;
 #define FPB_LAUNCH_SPLEV(KK)                                                                       \
     do {                                                                                           \
-        cudaError_t e_ = cudaFuncSetAttribute(splev_kernel<KK>,                                    \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+        auto kern = (p.mode == 1) ? splev_kernel<KK, 1> : splev_kernel<KK, 0>;                     \
+        cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                               (int)smem);                                          \
         if (e_ != cudaSuccess) return e_;                                                          \
-        splev_kernel<KK><<<(unsigned)blocks, wpb * 32, smem, stream>>>(p, smem_ld);                \
+        kern<<<(unsigned)blocks, wpb * 32, smem, stream>>>(p, smem_ld);                            \
     } while (0)
     switch (p.k) {
     case 1: FPB_LAUNCH_SPLEV(1); break;

@@ -1,0 +1,166 @@
+! fitpack_b200.f90 -- iso_c_binding interface module for libfitpack_b200.so
+!
+! Host code stays Modern Fortran (BASELINE.json north_star): this module is the thin shim
+! through which it reaches the CUDA kernels.  It binds
+!   (A) the reference's own C symbols for the path (same names/arguments as
+!       src/fitpack_core_c.f90:64-74,145-154 of perazz/fitpack), and
+!   (B) the new batch entry points of include/fitpack_b200.h.
+! It contains no arithmetic.  NOTE: the build container has no Fortran compiler, so this file
+! is shipped as source only (not compiled or tested here); INTEGRATION.md shows how the
+! reference's fitpack_curve%fit / %eval call sites switch over to it.
+module fitpack_b200
+   use, intrinsic :: iso_c_binding
+   implicit none
+   private
+
+   integer, parameter, public :: FP_REAL = c_double
+   integer, parameter, public :: FP_SIZE = c_int32_t
+   integer, parameter, public :: FP_FLAG = c_int32_t
+   integer, parameter, public :: FP_BOOL = c_bool
+
+   integer(FP_FLAG), parameter, public :: FPB_SPLEV_EXACT = 0, FPB_SPLEV_FAST = 1
+   integer(c_int32_t), parameter, public :: FPB_STATUS_OK = 0, FPB_ERR_CUDA = -100, &
+                                            FPB_ERR_ARG = -101, FPB_ERR_ALLOC = -102
+
+   public :: fp_curfit_c, fp_splev_c, fp_curfit_batch_c, fp_splev_batch_c
+   public :: fp_curfit_batch_dev_c, fp_curfit_shared_dev_c, fp_splev_batch_dev_c
+   public :: fpb_engine_create, fpb_engine_destroy, fpb_engine_synchronize, fpb_device_count
+   public :: curfit_batch, splev_batch
+
+   interface
+
+      ! (A) drop-in: same interface as the reference's curfit_c / splev_c
+      subroutine fp_curfit_c(iopt,m,x,y,w,xb,xe,k,s,nest,n,t,c,fp,wrk,lwrk,iwrk,ier) bind(C,name="fp_curfit_c")
+         import
+         real   (FP_REAL), intent(in),    value :: xb,xe,s
+         real   (FP_REAL), intent(inout)        :: fp
+         integer(FP_SIZE), intent(in),    value :: iopt,m,k,nest,lwrk
+         integer(FP_FLAG), intent(out)          :: ier
+         integer(FP_SIZE), intent(inout)        :: n
+         real   (FP_REAL), intent(in)           :: x(m),y(m),w(m)
+         real   (FP_REAL), intent(inout)        :: t(nest),c(nest),wrk(lwrk)
+         integer(FP_SIZE), intent(inout)        :: iwrk(nest)
+      end subroutine fp_curfit_c
+
+      subroutine fp_splev_c(t,n,c,k,x,y,m,e,ier) bind(C,name="fp_splev_c")
+         import
+         integer(FP_SIZE), intent(in), value :: n,k,m
+         real   (FP_REAL), intent(in)        :: t(n),c(n),x(m)
+         real   (FP_REAL), intent(out)       :: y(m)
+         integer(FP_FLAG), intent(in), value :: e
+         integer(FP_FLAG), intent(out)       :: ier
+      end subroutine fp_splev_c
+
+      ! (B) batches of independent curves, host arrays.  Fortran arrays x(m,nbatch) are exactly
+      ! the "curve-major" [nbatch][m] C layout the library expects.
+      integer(c_int32_t) function fp_curfit_batch_c(nbatch,iopt,m,x,y,w,shared_x,xb,xe,k,s,nest, &
+                                                    n,t,c,fp,ier,ngpus) bind(C,name="fp_curfit_batch_c")
+         import
+         integer(FP_SIZE), intent(in), value :: nbatch,iopt,m,shared_x,k,nest,ngpus
+         real   (FP_REAL), intent(in)        :: x(*),y(m,nbatch)
+         type(c_ptr),      intent(in), value :: w          ! c_null_ptr => unit weights
+         type(c_ptr),      intent(in), value :: xb,xe      ! c_null_ptr => data range per curve
+         real   (FP_REAL), intent(in), value :: s
+         integer(FP_SIZE), intent(inout)     :: n(nbatch)
+         real   (FP_REAL), intent(inout)     :: t(nest,nbatch),c(nest,nbatch),fp(nbatch)
+         integer(FP_FLAG), intent(out)       :: ier(nbatch)
+      end function fp_curfit_batch_c
+
+      integer(c_int32_t) function fp_splev_batch_c(nspl,t,n,c,ldt,k,x,y,m,e,mode,ier,ngpus) &
+                                                   bind(C,name="fp_splev_batch_c")
+         import
+         integer(FP_SIZE), intent(in), value :: nspl,ldt,k,m,mode,ngpus
+         integer(FP_FLAG), intent(in), value :: e
+         real   (FP_REAL), intent(in)        :: t(ldt,nspl),c(ldt,nspl),x(m,nspl)
+         integer(FP_SIZE), intent(in)        :: n(nspl)
+         real   (FP_REAL), intent(out)       :: y(m,nspl)
+         integer(FP_FLAG), intent(out)       :: ier(nspl)
+      end function fp_splev_batch_c
+
+      ! device-pointer variants (type(c_ptr) = device addresses, e.g. from cudaMalloc / OpenACC
+      ! host_data / CUDA Fortran c_devloc); see include/fitpack_b200.h for the stride convention
+      integer(c_int32_t) function fp_curfit_batch_dev_c(eng,nbatch,iopt,m,x,x_sb,x_si,y,y_sb,y_si, &
+                              w,w_sb,w_si,xb,xe,xbe_stride,k,s,s_stride,nest,n,t,c,fp,ier,       &
+                              fpint,nrdata,stats) bind(C,name="fp_curfit_batch_dev_c")
+         import
+         type(c_ptr),        intent(in), value :: eng,x,y,w,xb,xe,s,n,t,c,fp,ier,fpint,nrdata,stats
+         integer(FP_SIZE),   intent(in), value :: nbatch,iopt,m,xbe_stride,k,s_stride,nest
+         integer(c_int64_t), intent(in), value :: x_sb,x_si,y_sb,y_si,w_sb,w_si
+      end function fp_curfit_batch_dev_c
+
+      integer(c_int32_t) function fp_curfit_shared_dev_c(eng,nbatch,m,x,w,y,y_sb,y_si,xb,xe,k,n,t, &
+                              c,ldc,fp,ier) bind(C,name="fp_curfit_shared_dev_c")
+         import
+         type(c_ptr),        intent(in), value :: eng,x,w,y,t,c,fp,ier
+         integer(FP_SIZE),   intent(in), value :: nbatch,m,k,n
+         integer(c_int64_t), intent(in), value :: y_sb,y_si,ldc
+         real(FP_REAL),      intent(in), value :: xb,xe
+      end function fp_curfit_shared_dev_c
+
+      integer(c_int32_t) function fp_splev_batch_dev_c(eng,nspl,t,n,c,ldt,k,x,y,m,e,mode,nshared, &
+                              ier,lidx) bind(C,name="fp_splev_batch_dev_c")
+         import
+         type(c_ptr),      intent(in), value :: eng,t,n,c,x,y,ier,lidx
+         integer(FP_SIZE), intent(in), value :: nspl,ldt,k,m,mode,nshared
+         integer(FP_FLAG), intent(in), value :: e
+      end function fp_splev_batch_dev_c
+
+      integer(c_int32_t) function fpb_engine_create(device,eng) bind(C,name="fpb_engine_create")
+         import
+         integer(c_int32_t), intent(in), value :: device
+         type(c_ptr), intent(out) :: eng
+      end function fpb_engine_create
+
+      subroutine fpb_engine_destroy(eng) bind(C,name="fpb_engine_destroy")
+         import
+         type(c_ptr), intent(in), value :: eng
+      end subroutine fpb_engine_destroy
+
+      integer(c_int32_t) function fpb_engine_synchronize(eng) bind(C,name="fpb_engine_synchronize")
+         import
+         type(c_ptr), intent(in), value :: eng
+      end function fpb_engine_synchronize
+
+      integer(c_int32_t) function fpb_device_count() bind(C,name="fpb_device_count")
+         import
+      end function fpb_device_count
+
+   end interface
+
+contains
+
+   !> Fit nbatch independent curves y(:,b) on abscissae x(:,b) (the batched analogue of
+   !> curve%new_fit): same argument vocabulary as curfit (iopt, k, s, nest, n, t, c, fp, ier).
+   integer(FP_FLAG) function curfit_batch(x,y,k,s,nest,n,t,c,fp,ier,w,ngpus) result(status)
+      real(FP_REAL), intent(in), target   :: x(:,:), y(:,:)
+      integer(FP_SIZE), intent(in)        :: k, nest
+      real(FP_REAL), intent(in)           :: s
+      integer(FP_SIZE), intent(inout)     :: n(:)
+      real(FP_REAL), intent(inout)        :: t(:,:), c(:,:), fp(:)
+      integer(FP_FLAG), intent(out)       :: ier(:)
+      real(FP_REAL), intent(in), optional, target :: w(:,:)
+      integer(FP_SIZE), intent(in), optional :: ngpus
+      type(c_ptr) :: wp
+      integer(FP_SIZE) :: ng
+      wp = c_null_ptr; if (present(w)) wp = c_loc(w)
+      ng = 0;          if (present(ngpus)) ng = ngpus
+      status = fp_curfit_batch_c(size(y,2,FP_SIZE), 0_FP_SIZE, size(y,1,FP_SIZE), x, y, wp, &
+                                 0_FP_SIZE, c_null_ptr, c_null_ptr, k, s, nest, n, t, c, fp, ier, ng)
+   end function curfit_batch
+
+   !> Evaluate nspl splines (t(:,j), n(j), c(:,j)) at x(:,j): batched analogue of curve%eval.
+   integer(FP_FLAG) function splev_batch(t,n,c,k,x,y,e,ier,mode,ngpus) result(status)
+      real(FP_REAL), intent(in)       :: t(:,:), c(:,:), x(:,:)
+      integer(FP_SIZE), intent(in)    :: n(:), k
+      real(FP_REAL), intent(out)      :: y(:,:)
+      integer(FP_FLAG), intent(in)    :: e
+      integer(FP_FLAG), intent(out)   :: ier(:)
+      integer(FP_SIZE), intent(in), optional :: mode, ngpus
+      integer(FP_SIZE) :: md, ng
+      md = FPB_SPLEV_EXACT; if (present(mode)) md = mode
+      ng = 0;               if (present(ngpus)) ng = ngpus
+      status = fp_splev_batch_c(size(t,2,FP_SIZE), t, n, c, size(t,1,FP_SIZE), k, x, y, &
+                                size(x,1,FP_SIZE), e, md, ier, ng)
+   end function splev_batch
+
+end module fitpack_b200
