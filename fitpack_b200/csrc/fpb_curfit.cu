@@ -96,13 +96,14 @@ __device__ __forceinline__ void back_subst(const FitParams &p, double *wsd, int 
 
 // sum of squared residuals of the current c over all points using the stored
 // basis values q (get_fp loop, core:5061-5069); when FPINT is set also the
-// per-interval split of core:4942-4966.
-template <int K, bool FPINT>
+// per-interval split of core:4942-4966.  Loads of 2 consecutive points are
+// issued together (they do not depend on the interval walk) to cover HBM latency.
+template <int K, bool FPINT, bool HAS_W>
 __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd, const double *xp,
                                                 const double *yp, const double *wp, int m, int nk1,
                                                 int nrint, bool on)
 {
-    constexpr int K1 = K + 1, K2 = K + 2;
+    constexpr int K1 = K + 1, K2 = K + 2, U = 2;
     double cw[K1];
     double fpart = 0.0, tl = 0.0;
     int l = K2, i = 1;
@@ -114,31 +115,46 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
 #pragma unroll
         for (int j = 0; j < K1; ++j) cw[j] = 0.0;
     }
-    for (int it = 0; it < m; ++it) {
-        const double xi = xp[(size_t)it * p.x_si];
-        const double yi = yp[(size_t)it * p.y_si];
-        const double wi = wp ? wp[(size_t)it * p.w_si] : 1.0;
-        if (on) {
-            bool newk = false;
-            if (xi >= tl && l <= nk1) {
-                newk = true;
-                ++l;
+    for (int it0 = 0; it0 < m; it0 += U) {
+        double xv[U], yv[U], wv[U], qv[U][K1];
 #pragma unroll
-                for (int j = 0; j < K; ++j) cw[j] = cw[j + 1];
-                cw[K] = C_(l - 1);
-                tl = T_(l);
+        for (int u = 0; u < U; ++u) {
+            const int it = min(it0 + u, m - 1);
+            xv[u] = xp[(size_t)it * p.x_si];
+            yv[u] = yp[(size_t)it * p.y_si];
+            wv[u] = HAS_W ? wp[(size_t)it * p.w_si] : 1.0;
+            if (on) {
+#pragma unroll
+                for (int j = 0; j < K1; ++j) qv[u][j] = Q_(it, j);
             }
-            double term = 0.0;
+        }
+        if (on) {
 #pragma unroll
-            for (int j = 0; j < K1; ++j) term = add(term, mul(cw[j], Q_(it, j)));
-            term = mul(wi, sub(term, yi));
-            term = mul(term, term);
-            fpart = add(fpart, term);
-            if (FPINT && newk) {
-                const double store = mul(term, 0.5);
-                FPI_(i) = sub(fpart, store);
-                ++i;
-                fpart = store;
+            for (int u = 0; u < U; ++u) {
+                if (it0 + u < m) {
+                    bool newk = false;
+                    if (xv[u] >= tl && l <= nk1) {
+                        newk = true;
+                        ++l;
+#pragma unroll
+                        for (int j = 0; j < K; ++j) cw[j] = cw[j + 1];
+                        cw[K] = C_(l - 1);
+                        tl = T_(l);
+                    }
+                    double term = 0.0;
+#pragma unroll
+                    for (int j = 0; j < K1; ++j) term = add(term, mul(cw[j], qv[u][j]));
+                    term = sub(term, yv[u]);
+                    if (HAS_W) term = mul(wv[u], term);
+                    term = mul(term, term);
+                    fpart = add(fpart, term);
+                    if (FPINT && newk) {
+                        const double store = mul(term, 0.5);
+                        FPI_(i) = sub(fpart, store);
+                        ++i;
+                        fpart = store;
+                    }
+                }
             }
         }
     }
@@ -148,7 +164,7 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
 
 // one least-squares pass (coefs loop core:4873-4896) with the active band rows
 // held in registers; returns fp = sum of squared transformed right-hand sides.
-template <int K>
+template <int K, bool HAS_W>
 __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, const double *xp,
                                            const double *yp, const double *wp, int m, int nk1,
                                            bool on)
@@ -170,10 +186,20 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, cons
         for (int j = 0; j < 2 * K; ++j) tw[j] = 0.0;
     }
     double fp = 0.0;
+    // the next point's data is requested one iteration ahead (a pass is ~600 FP64
+    // instructions per point: one point of lookahead covers the HBM latency)
+    double xn = xp[0], yn = yp[0], wn = HAS_W ? wp[0] : 1.0;
     for (int it = 0; it < m; ++it) {
-        const double xi = xp[(size_t)it * p.x_si];
-        const double wi = wp ? wp[(size_t)it * p.w_si] : 1.0;
-        double yi = mul(yp[(size_t)it * p.y_si], wi);
+        const double xi = xn;
+        const double wi = wn;
+        // w == NULL means unit weights: y*1 and h*1 are exact, so the products are skipped
+        double yi = HAS_W ? mul(yn, wi) : yn;
+        {
+            const int nx = min(it + 1, m - 1);
+            xn = xp[(size_t)nx * p.x_si];
+            yn = yp[(size_t)nx * p.y_si];
+            if (HAS_W) wn = wp[(size_t)nx * p.w_si];
+        }
         if (on) {
             // fp_knot_interval (core:2432-2473) == linear walk from the previous interval
             while (l < nk1 && xi >= tw[K]) {
@@ -200,7 +226,7 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, cons
 #pragma unroll
             for (int j = 0; j < K1; ++j) {
                 Q_(it, j) = h[j];
-                h[j] = mul(wi, h[j]);
+                if (HAS_W) h[j] = mul(wi, h[j]);
             }
             // fp_rotate_row (core:5691-5717): window row i <-> R row l-K1+1+i
 #pragma unroll
@@ -279,7 +305,7 @@ __device__ int check_knots(const FitParams &p, double *wsd, const double *xp, in
     return IER_OK;
 }
 
-template <int K>
+template <int K, bool HAS_W>
 __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restrict__ wsd,
                          int *__restrict__ wsi)
 {
@@ -289,7 +315,7 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
     const int bb = valid ? b : 0;
     const double *xp = p.x + (size_t)bb * p.x_sb;
     const double *yp = p.y + (size_t)bb * p.y_sb;
-    const double *wp = p.w ? p.w + (size_t)bb * p.w_sb : nullptr;
+    const double *wp = HAS_W ? p.w + (size_t)bb * p.w_sb : nullptr;
 
     int state = valid ? ST_LOOP : ST_DONE;
     int ier = IER_OK, n = 0;
@@ -419,7 +445,7 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
             for (int i = nk1 + 1; i <= n; ++i) T_(i) = xe;
             ++lsq_passes;
         }
-        const double fp_pass = lsq_pass<K>(p, wsd, xp, yp, wp, m, nk1, on);
+        const double fp_pass = lsq_pass<K, HAS_W>(p, wsd, xp, yp, wp, m, nk1, on);
         if (on) {
             fp = fp_pass;
             if (ier == IER_LSQ) fp0 = fp;
@@ -452,7 +478,7 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
             }
             fpold = fp;
         }
-        (void)residual_pass<K, true>(p, wsd, xp, yp, wp, m, nk1, nrint, on);
+        (void)residual_pass<K, true, HAS_W>(p, wsd, xp, yp, wp, m, nk1, nrint, on);
         // add_new_knots, core:4968-4996 with fpknot core:8199-8275 inlined
         {
             const int maxplus = __reduce_max_sync(FULL, on ? nplus : 0);
@@ -608,7 +634,7 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
                 }
             }
             back_subst<K2>(p, wsd, p.off_g, p.off_c, nk1, on);
-            const double fpn = residual_pass<K, false>(p, wsd, xp, yp, wp, m, nk1, 0, on);
+            const double fpn = residual_pass<K, false, HAS_W>(p, wsd, xp, yp, wp, m, nk1, 0, on);
             if (on) {
                 fp = fpn;
                 fpms = sub(fp, s);
@@ -694,7 +720,7 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
     }
 }
 
-template <int K>
+template <int K, bool HAS_W>
 __global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2) curfit_kernel(FitParams p)
 {
     const int lane = threadIdx.x & 31;
@@ -708,7 +734,7 @@ __global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2) curfit_kernel(F
         const long long first = (long long)tile * 32;
         if (first >= p.nbatch) break;
         const int b = (int)first + lane;
-        fit_tile<K>(p, b, b < p.nbatch, wsd, wsi);
+        fit_tile<K, HAS_W>(p, b, b < p.nbatch, wsd, wsi);
         __syncwarp();
     }
 }
@@ -742,14 +768,21 @@ int fit_max_resident_warps(int k, int nsm)
     return nsm * blocks_per_sm * (kFitThreads / 32);
 }
 
+template <int K>
+static void launch_k(const FitParams &p, int grid_blocks, cudaStream_t stream)
+{
+    if (p.w) curfit_kernel<K, true><<<grid_blocks, kFitThreads, 0, stream>>>(p);
+    else curfit_kernel<K, false><<<grid_blocks, kFitThreads, 0, stream>>>(p);
+}
+
 cudaError_t launch_curfit(const FitParams &p, int grid_blocks, cudaStream_t stream)
 {
     switch (p.k) {
-    case 1: curfit_kernel<1><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
-    case 2: curfit_kernel<2><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
-    case 3: curfit_kernel<3><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
-    case 4: curfit_kernel<4><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
-    case 5: curfit_kernel<5><<<grid_blocks, kFitThreads, 0, stream>>>(p); break;
+    case 1: launch_k<1>(p, grid_blocks, stream); break;
+    case 2: launch_k<2>(p, grid_blocks, stream); break;
+    case 3: launch_k<3>(p, grid_blocks, stream); break;
+    case 4: launch_k<4>(p, grid_blocks, stream); break;
+    case 5: launch_k<5>(p, grid_blocks, stream); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
