@@ -1,7 +1,14 @@
 // fpb_curfit.cu -- batched smoothing-spline fit (curfit/fpcurf) for sm_100a.
 //
 // One thread per curve, 32 curves per warp, persistent warps pulling 32-curve
-// tiles from an atomic queue.  Follows, per curve, exactly the control flow
+// tiles from an atomic queue.  The knot loop of fpcurf is cut at pass granularity:
+// `curfit_pass_kernel` runs ONE least-squares pass (+ acceptance tests, residual
+// split, knot insertion) for every curve in its input list and re-buckets the
+// curves into "needs another pass" / "knots accepted: part 2" / done, so every
+// lane of every warp always has a pass to do (the monolithic version lost half
+// of its issue slots to lanes whose curve needed fewer knot sets, profiles/r01);
+// `curfit_part2_kernel` then runs the smoothing-parameter iteration on the
+// part-2 list sorted by knot count.  Follows, per curve, exactly the control flow
 // and IEEE operation order of the reference:
 //   curfit  src/fitpack_core.F90:1240-1299   (argument checks, fpchec)
 //   fpcurf  src/fitpack_core.F90:4737-5087   (knot loop, LSQ, p-iteration)
@@ -23,9 +30,10 @@
 //    uniform across the warp (back-substitution, p-iteration, fpknot, fpdisc)
 //    are coalesced too; trip counts are made warp-uniform with a max-reduce and
 //    per-lane predicates;
-//  * no host round trips: knot insertion, the rational p-search and all exits
-//    run inside the kernel; per-curve ier is an output, a bad curve never
-//    aborts the batch.
+//  * all decisions (knot insertion, the rational p-search, every exit) are taken
+//    on the device; the host only reads one counter every other pass to know
+//    when the "needs another pass" list is empty.  Per-curve ier is an output, a
+//    bad curve never aborts the batch.
 #include "fpb_common.cuh"
 #include "fpb_kernels.h"
 
@@ -305,9 +313,29 @@ __device__ int check_knots(const FitParams &p, double *wsd, const double *xp, in
     return IER_OK;
 }
 
+// warp-aggregated append of curve id `b` to a device list
+__device__ __forceinline__ void list_append(int *list, int *count, bool cond, int b, int lane)
+{
+    const unsigned mask = __ballot_sync(FULL, cond);
+    if (mask == 0u) return;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(FULL, base, leader);
+    if (cond) list[base + __popc(mask & ((1u << lane) - 1u))] = b;
+}
+
+// ---------------------------------------------------------------------------------------
+// ONE iteration of fpcurf's knot loop (main_loop, core:4847-4998) for the 32 curves of a
+// tile.  first != 0: also curfit's argument checks (core:1265-1285) and fpcurf's prologue
+// (core:4761-4843).  Returns the curve's state after the pass: ST_LOOP (another knot set is
+// needed), ST_PART2 (knots accepted, smoothing iteration follows), ST_DONE (result written).
+// Between passes a curve lives in global memory only: n, t (in the caller's output arrays),
+// nrdata(1:nrint) and the scalars fpold, fp0, nplus, iter.
+// ---------------------------------------------------------------------------------------
 template <int K, bool HAS_W>
-__device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restrict__ wsd,
-                         int *__restrict__ wsi)
+__device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
+                         double *__restrict__ wsd, int *__restrict__ wsi)
 {
     constexpr int K1 = K + 1, K2 = K + 2;
     const int m = p.m, nest = p.nest, iopt = p.iopt;
@@ -318,11 +346,12 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
     const double *wp = HAS_W ? p.w + (size_t)bb * p.w_sb : nullptr;
 
     int state = valid ? ST_LOOP : ST_DONE;
-    int ier = IER_OK, n = 0;
-    double fp = 0.0;
+    int ier = IER_OK, n = 0, nplus = 0, iter = 0;
+    double fp = 0.0, fpold = 0.0, fp0 = 0.0, fpms = DBL_MAX;
     bool write_fit = false;  // outputs beyond ier are only written once fpcurf ran
 
     const double s = p.s[(size_t)bb * p.s_stride];
+    const double acc = mul(kTol, s);
     double xb, xe;
     if (p.xb) {
         xb = p.xb[(size_t)bb * p.xbe_stride];
@@ -332,9 +361,9 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
         xe = xp[(size_t)(m - 1) * p.x_si];
     }
 
-    // ---- curfit argument checks, core:1265-1285 (k, iopt, m, nest are call-level
-    //      and were checked on the host) ----
-    {
+    if (first) {
+        // ---- curfit argument checks, core:1265-1285 (k, iopt, m, nest are call-level and were
+        //      checked on the host) ----
         bool bad = false;
         double prev = xp[0];
         if (xb > prev) bad = true;
@@ -356,81 +385,89 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
                 state = ST_DONE;
             }
         }
-    }
-    // knots / continuation state from the caller
-    if (state == ST_LOOP && iopt != 0) {
-        if (iopt > 0) n = p.n[bb];
-        const bool have = (iopt < 0) || (n >= nmin && n <= nest && n <= nmax);
-        if (iopt > 0 && !have) n = nmin;  // garbage n on a continuation: treat as a fresh start
-        if (have) {
-            for (int i = 1; i <= n; ++i) T_(i) = p.t[(size_t)bb * nest + (i - 1)];
-            if (iopt > 0 && p.fpint && p.nrdata) {
-                for (int i = 1; i <= n; ++i) {
-                    FPI_(i) = p.fpint[(size_t)bb * nest + (i - 1)];
-                    NRD_(i) = p.nrdata[(size_t)bb * nest + (i - 1)];
+        // knots / continuation state from the caller
+        if (state == ST_LOOP && iopt != 0) {
+            if (iopt > 0) n = p.n[bb];
+            const bool have = (iopt < 0) || (n >= nmin && n <= nest && n <= nmax);
+            if (iopt > 0 && !have) n = nmin;  // garbage n on a continuation: treat as a fresh start
+            if (have) {
+                for (int i = 1; i <= n; ++i) T_(i) = p.t[(size_t)bb * nest + (i - 1)];
+                if (iopt > 0 && p.fpint && p.nrdata) {
+                    for (int i = 1; i <= n; ++i) {
+                        FPI_(i) = p.fpint[(size_t)bb * nest + (i - 1)];
+                        NRD_(i) = p.nrdata[(size_t)bb * nest + (i - 1)];
+                    }
                 }
             }
-        }
-        if (iopt < 0) {
-            int j = n;
-            for (int i = 1; i <= K1; ++i) {
-                T_(i) = xb;
-                T_(j) = xe;
-                --j;
-            }
-            // the clamped end knots are visible to the caller even if fpchec fails (core:1278-1284)
-            j = n;
-            for (int i = 1; i <= K1; ++i) {
-                p.t[(size_t)bb * nest + (i - 1)] = xb;
-                p.t[(size_t)bb * nest + (j - 1)] = xe;
-                --j;
-            }
-            const int chk = check_knots<K>(p, wsd, xp, m, n);
-            if (chk != 0) {
-                ier = chk;
-                state = ST_DONE;
-            }
-        }
-    }
-
-    // ---- fpcurf prologue, core:4761-4843 ----
-    double fpold = 0.0, fp0 = 0.0, fpms = DBL_MAX;
-    int nplus = 0;
-    const double acc = mul(kTol, s);
-    int lsq_passes = 0, p_iters = 0;
-    if (state == ST_LOOP) {
-        write_fit = true;
-        if (iopt >= 0) {
-            if (s <= 0.0) {
-                n = nmax;
-                if (nmax > nest) {
-                    ier = IER_STORAGE;
+            if (iopt < 0) {
+                int j = n;
+                for (int i = 1; i <= K1; ++i) {
+                    T_(i) = xb;
+                    T_(j) = xe;
+                    --j;
+                }
+                // the clamped end knots are visible to the caller even if fpchec fails (core:1278-1284)
+                j = n;
+                for (int i = 1; i <= K1; ++i) {
+                    p.t[(size_t)bb * nest + (i - 1)] = xb;
+                    p.t[(size_t)bb * nest + (j - 1)] = xe;
+                    --j;
+                }
+                const int chk = check_knots<K>(p, wsd, xp, m, n);
+                if (chk != 0) {
+                    ier = chk;
                     state = ST_DONE;
-                } else {
-                    interp_knots<K>(p, wsd, xp, m);
                 }
-            } else if (iopt != 0 && n != nmin) {
-                fp0 = FPI_(n);
-                fpold = FPI_(n - 1);
-                nplus = NRD_(n);
-                if (fp0 <= s) {
+            }
+        }
+        // ---- fpcurf prologue, core:4761-4843 ----
+        if (state == ST_LOOP) {
+            write_fit = true;
+            if (iopt >= 0) {
+                if (s <= 0.0) {
+                    n = nmax;
+                    if (nmax > nest) {
+                        ier = IER_STORAGE;
+                        state = ST_DONE;
+                    } else {
+                        interp_knots<K>(p, wsd, xp, m);
+                    }
+                } else if (iopt != 0 && n != nmin) {
+                    fp0 = FPI_(n);
+                    fpold = FPI_(n - 1);
+                    nplus = NRD_(n);
+                    if (fp0 <= s) {
+                        n = nmin;
+                        fpold = 0.0;
+                        nplus = 0;
+                        NRD_(1) = m - 2;
+                    }
+                } else {
                     n = nmin;
                     fpold = 0.0;
                     nplus = 0;
                     NRD_(1) = m - 2;
                 }
-            } else {
-                n = nmin;
-                fpold = 0.0;
-                nplus = 0;
-                NRD_(1) = m - 2;
             }
         }
+    } else if (valid) {
+        // ---- resume: reload the curve's state ----
+        write_fit = true;
+        n = p.n[b];
+        ier = p.ier[b];
+        nplus = p.st_nplus[b];
+        iter = p.st_iter[b];
+        fpold = p.st_fpold[b];
+        fp0 = p.st_fp0[b];
+        for (int i = 1; i <= n; ++i) T_(i) = p.t[(size_t)b * nest + (i - 1)];
+        const int nri = n - nmin + 1;
+        for (int i = 1; i <= nri; ++i) NRD_(i) = p.st_nrd[(size_t)b * p.nestp + (i - 1)];
     }
 
-    // ---- part 1: knot loop, core:4847-4998 ----
-    int iter = 0, nk1 = n - K1, nrint = 0;
-    while (__any_sync(FULL, state == ST_LOOP)) {
+    // ---- one iteration of main_loop, core:4847-4998 ----
+    int nk1 = n - K1, nrint = 0;
+    bool ran_pass = false;
+    {
         bool on = (state == ST_LOOP);
         if (on && !(iter <= m)) {
             state = ST_PART2;
@@ -443,7 +480,7 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
             nk1 = n - K1;
             for (int i = 1; i <= K1; ++i) T_(i) = xb;
             for (int i = nk1 + 1; i <= n; ++i) T_(i) = xe;
-            ++lsq_passes;
+            ran_pass = true;
         }
         const double fp_pass = lsq_pass<K, HAS_W>(p, wsd, xp, yp, wp, m, nk1, on);
         if (on) {
@@ -478,7 +515,8 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
             }
             fpold = fp;
         }
-        (void)residual_pass<K, true, HAS_W>(p, wsd, xp, yp, wp, m, nk1, nrint, on);
+        if (__any_sync(FULL, on))
+            (void)residual_pass<K, true, HAS_W>(p, wsd, xp, yp, wp, m, nk1, nrint, on);
         // add_new_knots, core:4968-4996 with fpknot core:8199-8275 inlined
         {
             const int maxplus = __reduce_max_sync(FULL, on ? nplus : 0);
@@ -536,207 +574,333 @@ __device__ void fit_tile(const FitParams &p, int b, bool valid, double *__restri
             }
         }
     }
+    if (state == ST_PART2 && ier == IER_LSQ) state = ST_DONE;  // core:5002
 
-    // ---- part 2: smoothing spline, core:5002-5084 ----
-    if (state == ST_PART2 && ier == IER_LSQ) state = ST_DONE;
-    {
-        const bool on2 = (state == ST_PART2);
-        nk1 = n - K1;
-        const int n8 = n - nmin;
-        // fpdisc, core:5453-5495
-        {
-            const int hi = __reduce_max_sync(FULL, on2 ? nk1 : 0);
-            double fac = 0.0;
-            if (on2) fac = (double)(nk1 - K) / sub(T_(nk1 + 1), T_(K1));
-            for (int l = K2; l <= hi; ++l) {
-                if (on2 && l <= nk1) {
-                    double hd[2 * K1];
-                    const double tl = T_(l);
-#pragma unroll
-                    for (int j = 1; j <= K1; ++j) {
-                        hd[j - 1] = sub(tl, T_(l + j - K2));
-                        hd[j + K1 - 1] = sub(tl, T_(l + j));
-                    }
-                    const int lmk = l - K1;
-#pragma unroll
-                    for (int j = 1; j <= K2; ++j) {
-                        double prod = hd[j - 1];
-#pragma unroll
-                        for (int i = 1; i <= K; ++i) prod = mul(mul(prod, hd[j - 1 + i]), fac);
-                        const int lp = lmk + j - 1;
-                        B_(lmk, j) = sub(T_(lp + K1), T_(lp)) / prod;
-                    }
-                }
-            }
-        }
-        double p1 = 0.0, f1 = sub(fp0, s), p3 = -1.0, f3 = fpms, p2 = 0.0, f2 = 0.0, pp = 0.0;
-        bool check1 = false, check3 = false;
-        {
-            const int hi = __reduce_max_sync(FULL, on2 ? nk1 : 0);
-            for (int i = 1; i <= hi; ++i)
-                if (on2 && i <= nk1) pp = add(pp, A_(i, 1));
-            if (on2) pp = (double)nk1 / pp;
-        }
-        int it2 = 0;
-        while (__any_sync(FULL, state == ST_PART2)) {
-            bool on = (state == ST_PART2);
-            if (on && !(it2 < kMaxIt)) {
-                ier = IER_MAXIT;
-                state = ST_DONE;
-                on = false;
-            }
-            double pinv = 0.0;
-            if (on) {
-                ++it2;
-                ++p_iters;
-                pinv = 1.0 / pp;
-            }
-            const int hi = __reduce_max_sync(FULL, on ? nk1 : 0);
-            const int hi8 = __reduce_max_sync(FULL, on ? n8 : 0);
-            for (int i = 1; i <= hi; ++i) {
-                if (on && i <= nk1) {
-                    C_(i) = Z_(i);
-#pragma unroll
-                    for (int q = 1; q <= K1; ++q) G_(i, q) = A_(i, q);
-                    G_(i, K2) = 0.0;
-                }
-            }
-            for (int it = 1; it <= hi8; ++it) {
-                const bool row_on = on && it <= n8;
-                double h[K2];
-#pragma unroll
-                for (int q = 0; q < K2; ++q) h[q] = row_on ? mul(B_(it, q + 1), pinv) : 0.0;
-                double yi = 0.0;
-                // fp_rotate_shifted, core:5800-5820
-                for (int j = it; j <= hi; ++j) {
-                    if (row_on && j <= nk1) {
-                        const double piv = h[0];
-                        const int noff = min(nk1 - j, K1);
-                        if (!fp_is_zero(piv)) {
-                            double gd = G_(j, 1), cj = C_(j), cs, sn;
-                            givens(piv, gd, cs, sn);
-                            G_(j, 1) = gd;
-                            rota(cs, sn, yi, cj);
-                            C_(j) = cj;
-#pragma unroll
-                            for (int q = 1; q <= K1; ++q) {
-                                if (q <= noff) {
-                                    double gq = G_(j, q + 1);
-                                    rota(cs, sn, h[q], gq);
-                                    G_(j, q + 1) = gq;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < K1; ++q) h[q] = h[q + 1];
-                        h[K1] = 0.0;
-                    }
-                }
-            }
-            back_subst<K2>(p, wsd, p.off_g, p.off_c, nk1, on);
-            const double fpn = residual_pass<K, false, HAS_W>(p, wsd, xp, yp, wp, m, nk1, 0, on);
-            if (on) {
-                fp = fpn;
-                fpms = sub(fp, s);
-                if (fabs(fpms) < acc) {
-                    state = ST_DONE;
-                } else {
-                    // root_finding_iterate core:11641-11691 + fprati core:11996-12025
-                    const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
-                    bool ret = false, ok = true;
-                    p2 = pp;
-                    f2 = fpms;
-                    if (!check3) {
-                        if (sub(f2, f3) > acc) {
-                            check3 = f2 < 0.0;
-                        } else {
-                            p3 = p2;
-                            f3 = f2;
-                            pp = mul(pp, con4);
-                            if (pp <= p1) pp = add(mul(p1, con9), mul(p2, con1));
-                            ret = true;
-                        }
-                    }
-                    if (!ret && !check1) {
-                        if (sub(f1, f2) > acc) {
-                            check1 = f2 > 0.0;
-                        } else {
-                            p1 = p2;
-                            f1 = f2;
-                            pp = pp / con4;
-                            if (p3 >= 0.0 && pp >= p3) pp = add(mul(p2, con1), mul(p3, con9));
-                            ret = true;
-                        }
-                    }
-                    if (!ret) {
-                        if (f2 >= f1 || f2 <= f3) {
-                            ok = false;
-                        } else {
-                            if (p3 > 0.0) {
-                                const double h1 = mul(f1, sub(f2, f3));
-                                const double h2 = mul(f2, sub(f3, f1));
-                                const double h3 = mul(f3, sub(f1, f2));
-                                const double num = add(add(mul(mul(p1, p2), h3), mul(mul(p2, p3), h1)),
-                                                       mul(mul(p3, p1), h2));
-                                const double den = add(add(mul(p1, h1), mul(p2, h2)), mul(p3, h3));
-                                pp = -num / den;
-                            } else {
-                                const double num = sub(mul(mul(p1, sub(f1, f3)), f2),
-                                                       mul(mul(p2, sub(f2, f3)), f1));
-                                pp = num / mul(sub(f1, f2), f3);
-                            }
-                            if (f2 >= 0.0) { p1 = p2; f1 = f2; } else { p3 = p2; f3 = f2; }
-                        }
-                    }
-                    if (!ok) {
-                        ier = IER_S_SMALL;
-                        state = ST_DONE;
-                    }
-                }
-            }
-        }
-    }
-
-    // ---- results (curve-major, as the caller of curfit holds them) ----
+    // ---- write back ----
     if (valid) {
+        int passes = 0;
+        if (p.stats && write_fit) {
+            passes = (first ? 0 : p.stats[2 * (size_t)b]) + (ran_pass ? 1 : 0);
+            p.stats[2 * (size_t)b] = passes;
+            if (first) p.stats[2 * (size_t)b + 1] = 0;
+        }
         p.ier[b] = ier;
         if (write_fit) {
             p.n[b] = n;
-            if (!(ier == IER_STORAGE && iopt >= 0 && s <= 0.0)) p.fp[b] = fp;
-            const int nk = n - K1;
             for (int i = 1; i <= n; ++i) p.t[(size_t)b * nest + (i - 1)] = T_(i);
-            for (int i = 1; i <= nk; ++i) p.c[(size_t)b * nest + (i - 1)] = C_(i);
-            if (p.fpint && p.nrdata && iopt >= 0) {
-                for (int i = 1; i <= n; ++i) {
-                    p.fpint[(size_t)b * nest + (i - 1)] = FPI_(i);
-                    p.nrdata[(size_t)b * nest + (i - 1)] = NRD_(i);
-                }
+            if (state == ST_DONE) {
+                if (!(ier == IER_STORAGE && iopt >= 0 && s <= 0.0)) p.fp[b] = fp;
+                const int nk = n - K1;
+                for (int i = 1; i <= nk; ++i) p.c[(size_t)b * nest + (i - 1)] = C_(i);
             }
-            if (p.stats) {
-                p.stats[2 * (size_t)b] = lsq_passes;
-                p.stats[2 * (size_t)b + 1] = p_iters;
+            if (state != ST_LOOP) {
+                // knots are final: the continuation state the caller may keep (iopt=1 next time)
+                if (p.fpint && p.nrdata && iopt >= 0) {
+                    for (int i = 1; i <= n; ++i) {
+                        p.fpint[(size_t)b * nest + (i - 1)] = FPI_(i);
+                        p.nrdata[(size_t)b * nest + (i - 1)] = NRD_(i);
+                    }
+                }
+                if (state == ST_PART2) p.st_fp0[b] = fp0;
+            } else {
+                p.st_nplus[b] = nplus;
+                p.st_iter[b] = iter;
+                p.st_fpold[b] = fpold;
+                p.st_fp0[b] = fp0;
+                const int nri = n - nmin + 1;
+                for (int i = 1; i <= nri; ++i) p.st_nrd[(size_t)b * p.nestp + (i - 1)] = NRD_(i);
             }
         }
     }
+    return valid ? state : ST_DONE;
 }
 
+// ---------------------------------------------------------------------------------------
+// Part 2 of fpcurf (core:5004-5084) for the 32 curves of a tile: the knots are final; find
+// the smoothing parameter p with f(p)=s.  The triangularised system (R, z) and the basis
+// values q of the accepted knot set are regenerated by one LSQ pass (bit-identical to the
+// last pass of part 1), which keeps no per-curve matrix state alive between kernels.
+// ---------------------------------------------------------------------------------------
 template <int K, bool HAS_W>
-__global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2) curfit_kernel(FitParams p)
+__device__ void part2_tile(const FitParams &p, int b, bool valid, double *__restrict__ wsd,
+                           int *__restrict__ wsi)
+{
+    constexpr int K1 = K + 1, K2 = K + 2;
+    (void)wsi;
+    const int m = p.m, nest = p.nest;
+    const int nmin = 2 * K1;
+    const int bb = valid ? b : 0;
+    const double *xp = p.x + (size_t)bb * p.x_sb;
+    const double *yp = p.y + (size_t)bb * p.y_sb;
+    const double *wp = HAS_W ? p.w + (size_t)bb * p.w_sb : nullptr;
+    const double s = p.s[(size_t)bb * p.s_stride];
+    const double acc = mul(kTol, s);
+    int state = valid ? ST_PART2 : ST_DONE;
+    int ier = IER_OK, n = nmin, p_iters = 0;
+    double fp0 = 0.0;
+    if (valid) {
+        n = p.n[b];
+        fp0 = p.st_fp0[b];
+        for (int i = 1; i <= n; ++i) T_(i) = p.t[(size_t)b * nest + (i - 1)];
+    }
+    const int nk1 = n - K1;
+    const int n8 = n - nmin;
+    const bool on2 = valid;
+    double fp = lsq_pass<K, HAS_W>(p, wsd, xp, yp, wp, m, nk1, on2);
+    double fpms = sub(fp, s);
+    // fpdisc, core:5453-5495
+    {
+        const int hi = __reduce_max_sync(FULL, on2 ? nk1 : 0);
+        double fac = 0.0;
+        if (on2) fac = (double)(nk1 - K) / sub(T_(nk1 + 1), T_(K1));
+        for (int l = K2; l <= hi; ++l) {
+            if (on2 && l <= nk1) {
+                double hd[2 * K1];
+                const double tl = T_(l);
+#pragma unroll
+                for (int j = 1; j <= K1; ++j) {
+                    hd[j - 1] = sub(tl, T_(l + j - K2));
+                    hd[j + K1 - 1] = sub(tl, T_(l + j));
+                }
+                const int lmk = l - K1;
+#pragma unroll
+                for (int j = 1; j <= K2; ++j) {
+                    double prod = hd[j - 1];
+#pragma unroll
+                    for (int i = 1; i <= K; ++i) prod = mul(mul(prod, hd[j - 1 + i]), fac);
+                    const int lp = lmk + j - 1;
+                    B_(lmk, j) = sub(T_(lp + K1), T_(lp)) / prod;
+                }
+            }
+        }
+    }
+    double p1 = 0.0, f1 = sub(fp0, s), p3 = -1.0, f3 = fpms, p2 = 0.0, f2 = 0.0, pp = 0.0;
+    bool check1 = false, check3 = false;
+    {
+        const int hi = __reduce_max_sync(FULL, on2 ? nk1 : 0);
+        for (int i = 1; i <= hi; ++i)
+            if (on2 && i <= nk1) pp = add(pp, A_(i, 1));
+        if (on2) pp = (double)nk1 / pp;
+    }
+    int it2 = 0;
+    while (__any_sync(FULL, state == ST_PART2)) {
+        bool on = (state == ST_PART2);
+        if (on && !(it2 < kMaxIt)) {
+            ier = IER_MAXIT;
+            state = ST_DONE;
+            on = false;
+        }
+        double pinv = 0.0;
+        if (on) {
+            ++it2;
+            ++p_iters;
+            pinv = 1.0 / pp;
+        }
+        const int hi = __reduce_max_sync(FULL, on ? nk1 : 0);
+        const int hi8 = __reduce_max_sync(FULL, on ? n8 : 0);
+        for (int i = 1; i <= hi; ++i) {
+            if (on && i <= nk1) {
+                C_(i) = Z_(i);
+#pragma unroll
+                for (int q = 1; q <= K1; ++q) G_(i, q) = A_(i, q);
+                G_(i, K2) = 0.0;
+            }
+        }
+        for (int it = 1; it <= hi8; ++it) {
+            const bool row_on = on && it <= n8;
+            double h[K2];
+#pragma unroll
+            for (int q = 0; q < K2; ++q) h[q] = row_on ? mul(B_(it, q + 1), pinv) : 0.0;
+            double yi = 0.0;
+            // fp_rotate_shifted, core:5800-5820
+            for (int j = it; j <= hi; ++j) {
+                if (row_on && j <= nk1) {
+                    const double piv = h[0];
+                    const int noff = min(nk1 - j, K1);
+                    if (!fp_is_zero(piv)) {
+                        double gd = G_(j, 1), cj = C_(j), cs, sn;
+                        givens(piv, gd, cs, sn);
+                        G_(j, 1) = gd;
+                        rota(cs, sn, yi, cj);
+                        C_(j) = cj;
+#pragma unroll
+                        for (int q = 1; q <= K1; ++q) {
+                            if (q <= noff) {
+                                double gq = G_(j, q + 1);
+                                rota(cs, sn, h[q], gq);
+                                G_(j, q + 1) = gq;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < K1; ++q) h[q] = h[q + 1];
+                    h[K1] = 0.0;
+                }
+            }
+        }
+        back_subst<K2>(p, wsd, p.off_g, p.off_c, nk1, on);
+        const double fpn = residual_pass<K, false, HAS_W>(p, wsd, xp, yp, wp, m, nk1, 0, on);
+        if (on) {
+            fp = fpn;
+            fpms = sub(fp, s);
+            if (fabs(fpms) < acc) {
+                state = ST_DONE;
+            } else {
+                // root_finding_iterate core:11641-11691 + fprati core:11996-12025
+                const double con1 = 0.1, con9 = 0.9, con4 = 0.04;
+                bool ret = false, ok = true;
+                p2 = pp;
+                f2 = fpms;
+                if (!check3) {
+                    if (sub(f2, f3) > acc) {
+                        check3 = f2 < 0.0;
+                    } else {
+                        p3 = p2;
+                        f3 = f2;
+                        pp = mul(pp, con4);
+                        if (pp <= p1) pp = add(mul(p1, con9), mul(p2, con1));
+                        ret = true;
+                    }
+                }
+                if (!ret && !check1) {
+                    if (sub(f1, f2) > acc) {
+                        check1 = f2 > 0.0;
+                    } else {
+                        p1 = p2;
+                        f1 = f2;
+                        pp = pp / con4;
+                        if (p3 >= 0.0 && pp >= p3) pp = add(mul(p2, con1), mul(p3, con9));
+                        ret = true;
+                    }
+                }
+                if (!ret) {
+                    if (f2 >= f1 || f2 <= f3) {
+                        ok = false;
+                    } else {
+                        if (p3 > 0.0) {
+                            const double h1 = mul(f1, sub(f2, f3));
+                            const double h2 = mul(f2, sub(f3, f1));
+                            const double h3 = mul(f3, sub(f1, f2));
+                            const double num = add(add(mul(mul(p1, p2), h3), mul(mul(p2, p3), h1)),
+                                                   mul(mul(p3, p1), h2));
+                            const double den = add(add(mul(p1, h1), mul(p2, h2)), mul(p3, h3));
+                            pp = -num / den;
+                        } else {
+                            const double num = sub(mul(mul(p1, sub(f1, f3)), f2),
+                                                   mul(mul(p2, sub(f2, f3)), f1));
+                            pp = num / mul(sub(f1, f2), f3);
+                        }
+                        if (f2 >= 0.0) { p1 = p2; f1 = f2; } else { p3 = p2; f3 = f2; }
+                    }
+                }
+                if (!ok) {
+                    ier = IER_S_SMALL;
+                    state = ST_DONE;
+                }
+            }
+        }
+    }
+    if (valid) {
+        p.ier[b] = ier;
+        p.fp[b] = fp;
+        for (int i = 1; i <= nk1; ++i) p.c[(size_t)b * nest + (i - 1)] = C_(i);
+        if (p.stats) p.stats[2 * (size_t)b + 1] = p_iters;
+    }
+}
+
+// persistent warps; tiles of 32 list entries are handed out through an atomic counter
+template <int K, bool HAS_W>
+__global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2)
+    curfit_pass_kernel(FitParams p, const int *__restrict__ in_list, const int *in_count,
+                       int *out_list, int *out_count, int *p2_list, int *p2_count, int first)
 {
     const int lane = threadIdx.x & 31;
     const int warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double *wsd = p.ws + (size_t)warp_slot * p.ws_per_lane * 32 + lane;
     int *wsi = p.wsi + (size_t)warp_slot * p.nestp * 32 + lane;
+    const int count = first ? p.nbatch : *in_count;
     for (;;) {
         unsigned tile = 0;
         if (lane == 0) tile = atomicAdd(p.counter, 1u);
         tile = __shfl_sync(FULL, tile, 0);
-        const long long first = (long long)tile * 32;
-        if (first >= p.nbatch) break;
-        const int b = (int)first + lane;
-        fit_tile<K, HAS_W>(p, b, b < p.nbatch, wsd, wsi);
+        const long long base = (long long)tile * 32;
+        if (base >= count) break;
+        const bool valid = base + lane < count;
+        int b = 0;
+        if (valid) b = first ? (int)(base + lane) : in_list[base + lane];
+        const int st = pass_tile<K, HAS_W>(p, b, valid, first != 0, wsd, wsi);
+        __syncwarp();
+        list_append(out_list, out_count, valid && st == ST_LOOP, b, lane);
+        const bool to2 = valid && st == ST_PART2;
+        list_append(p2_list, p2_count, to2, b, lane);
+        if (to2) atomicAdd(&p.hist[min(p.n[b], p.nestp)], 1);
+    }
+}
+
+template <int K, bool HAS_W>
+__global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2)
+    curfit_part2_kernel(FitParams p, const int *__restrict__ list, const int *count_ptr)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double *wsd = p.ws + (size_t)warp_slot * p.ws_per_lane * 32 + lane;
+    int *wsi = p.wsi + (size_t)warp_slot * p.nestp * 32 + lane;
+    const int count = *count_ptr;
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(p.counter, 1u);
+        tile = __shfl_sync(FULL, tile, 0);
+        const long long base = (long long)tile * 32;
+        if (base >= count) break;
+        const bool valid = base + lane < count;
+        const int b = valid ? list[base + lane] : 0;
+        part2_tile<K, HAS_W>(p, b, valid, wsd, wsi);
         __syncwarp();
     }
+}
+
+// counting sort of the part-2 list by knot count, largest first: curves of one warp then
+// do the same amount of work per p-iteration, and the longest curves start first.
+__global__ void p2_offsets_kernel(int *hist, int nbins)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int run = 0;
+    for (int n = nbins - 1; n >= 0; --n) {
+        const int c = hist[n];
+        hist[n] = run;
+        run += c;
+    }
+}
+
+__global__ void p2_scatter_kernel(const int *list, const int *count_ptr, const int *n_arr,
+                                  int *offsets, int nbins, int *sorted)
+{
+    const int count = *count_ptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int b = list[i];
+        const int pos = atomicAdd(&offsets[min(n_arr[b], nbins - 1)], 1);
+        sorted[pos] = b;
+    }
+}
+
+template <int K>
+void launch_pass_k(const FitParams &p, int grid, cudaStream_t st, const int *in_list,
+                   const int *in_count, int *out_list, int *out_count, int *p2_list, int *p2_count,
+                   int first)
+{
+    if (p.w)
+        curfit_pass_kernel<K, true><<<grid, kFitThreads, 0, st>>>(p, in_list, in_count, out_list,
+                                                                   out_count, p2_list, p2_count, first);
+    else
+        curfit_pass_kernel<K, false><<<grid, kFitThreads, 0, st>>>(p, in_list, in_count, out_list,
+                                                                    out_count, p2_list, p2_count, first);
+}
+
+template <int K>
+void launch_part2_k(const FitParams &p, int grid, cudaStream_t st, const int *list, const int *count)
+{
+    if (p.w) curfit_part2_kernel<K, true><<<grid, kFitThreads, 0, st>>>(p, list, count);
+    else curfit_part2_kernel<K, false><<<grid, kFitThreads, 0, st>>>(p, list, count);
 }
 
 }  // namespace
@@ -768,23 +932,40 @@ int fit_max_resident_warps(int k, int nsm)
     return nsm * blocks_per_sm * (kFitThreads / 32);
 }
 
-template <int K>
-static void launch_k(const FitParams &p, int grid_blocks, cudaStream_t stream)
-{
-    if (p.w) curfit_kernel<K, true><<<grid_blocks, kFitThreads, 0, stream>>>(p);
-    else curfit_kernel<K, false><<<grid_blocks, kFitThreads, 0, stream>>>(p);
-}
-
-cudaError_t launch_curfit(const FitParams &p, int grid_blocks, cudaStream_t stream)
+cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t stream,
+                               const int *in_list, const int *in_count, int *out_list,
+                               int *out_count, int *p2_list, int *p2_count, int first)
 {
     switch (p.k) {
-    case 1: launch_k<1>(p, grid_blocks, stream); break;
-    case 2: launch_k<2>(p, grid_blocks, stream); break;
-    case 3: launch_k<3>(p, grid_blocks, stream); break;
-    case 4: launch_k<4>(p, grid_blocks, stream); break;
-    case 5: launch_k<5>(p, grid_blocks, stream); break;
+    case 1: launch_pass_k<1>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
+    case 2: launch_pass_k<2>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
+    case 3: launch_pass_k<3>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
+    case 4: launch_pass_k<4>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
+    case 5: launch_pass_k<5>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
     default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_curfit_part2(const FitParams &p, int grid_blocks, cudaStream_t stream,
+                                const int *list, const int *count)
+{
+    switch (p.k) {
+    case 1: launch_part2_k<1>(p, grid_blocks, stream, list, count); break;
+    case 2: launch_part2_k<2>(p, grid_blocks, stream, list, count); break;
+    case 3: launch_part2_k<3>(p, grid_blocks, stream, list, count); break;
+    case 4: launch_part2_k<4>(p, grid_blocks, stream, list, count); break;
+    case 5: launch_part2_k<5>(p, grid_blocks, stream, list, count); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_p2_sort(const int *list, const int *count, const int *n_arr, int *hist,
+                           int nbins, int *sorted, int nsm, cudaStream_t stream)
+{
+    p2_offsets_kernel<<<1, 32, 0, stream>>>(hist, nbins);
+    p2_scatter_kernel<<<nsm * 4, 256, 0, stream>>>(list, count, n_arr, hist, nbins, sorted);
     return cudaGetLastError();
 }
 

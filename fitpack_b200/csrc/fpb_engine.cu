@@ -152,6 +152,11 @@ void fpb_engine_destroy(fpb_engine *eng)
     eng->ws.release();
     eng->wsi.release();
     eng->counter.release();
+    eng->lists.release();
+    eng->st_i.release();
+    eng->st_d.release();
+    eng->st_nrd.release();
+    if (eng->h_count) cudaFreeHost(eng->h_count);
     eng->plan_cs.release();
     eng->plan_w.release();
     eng->plan_row.release();
@@ -265,11 +270,23 @@ int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_
     const int max_warps = fit_max_resident_warps(k, eng->nsm);
     long long grid = std::min<long long>(blocks_needed, max_warps / (kFitThreads / 32));
     const size_t warps = (size_t)grid * (kFitThreads / 32);
+    const size_t nb = (size_t)nbatch;
+    // counters: [0] tile queue head, [4] list A count, [5] list B count, [6] part-2 count
+    const size_t hist_off = 64;  // ints
     if (!eng->ws.reserve(warps * (size_t)L.ws_per_lane * 32 * sizeof(double)) ||
         !eng->wsi.reserve(warps * (size_t)L.nestp * 32 * sizeof(int)) ||
-        !eng->counter.reserve(256))
+        !eng->counter.reserve((hist_off + (size_t)L.nestp + 8) * sizeof(int)) ||
+        !eng->lists.reserve(4 * nb * sizeof(int)) ||
+        !eng->st_i.reserve(2 * nb * sizeof(int)) || !eng->st_d.reserve(2 * nb * sizeof(double)) ||
+        !eng->st_nrd.reserve(nb * (size_t)L.nestp * sizeof(int)))
         return FPB_ERR_ALLOC;
-    if (!cuda_ok(cudaMemsetAsync(eng->counter.ptr, 0, sizeof(unsigned), eng->stream), "memset"))
+    if (!eng->h_count) {
+        if (!cuda_ok(cudaHostAlloc((void **)&eng->h_count, 64, cudaHostAllocDefault), "cudaHostAlloc"))
+            return FPB_ERR_ALLOC;
+    }
+    int *cnt = eng->counter.as<int>();
+    cudaStream_t st = eng->stream;
+    if (!cuda_ok(cudaMemsetAsync(cnt, 0, (hist_off + (size_t)L.nestp + 8) * sizeof(int), st), "memset"))
         return FPB_ERR_CUDA;
     FitParams p;
     p.nbatch = nbatch; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest; p.nestp = L.nestp;
@@ -280,15 +297,69 @@ int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_
     p.n = n; p.t = t; p.c = c; p.fp = fp; p.ier = ier;
     p.fpint = fpint; p.nrdata = nrdata; p.stats = stats;
     p.ws = eng->ws.as<double>(); p.wsi = eng->wsi.as<int>();
-    p.counter = eng->counter.as<unsigned>();
+    p.counter = reinterpret_cast<unsigned *>(cnt);
     p.off_t = L.off_t; p.off_c = L.off_c; p.off_z = L.off_z; p.off_fpint = L.off_fpint;
     p.off_a = L.off_a; p.off_g = L.off_g; p.off_b = L.off_b; p.off_q = L.off_q;
     p.ws_per_lane = L.ws_per_lane;
+    p.st_nplus = eng->st_i.as<int>(); p.st_iter = p.st_nplus + nb;
+    p.st_fpold = eng->st_d.as<double>(); p.st_fp0 = p.st_fpold + nb;
+    p.st_nrd = eng->st_nrd.as<int>();
+    p.hist = cnt + hist_off;
+    int *list[2] = {eng->lists.as<int>(), eng->lists.as<int>() + nb};
+    int *p2_list = eng->lists.as<int>() + 2 * nb, *p2_sorted = eng->lists.as<int>() + 3 * nb;
+    int *lcount[2] = {cnt + 4, cnt + 5};
+    int *p2_count = cnt + 6;
+
     begin_timing(eng);
-    if (!cuda_ok(launch_curfit(p, (int)grid, eng->stream), "curfit kernel launch"))
+    // pass 1 over the whole batch (identity list), then passes over the shrinking list of curves
+    // that still need a finer knot set.  The host reads the list length every other pass.
+    if (!cuda_ok(launch_curfit_pass(p, (int)grid, st, nullptr, nullptr, list[0], lcount[0], p2_list,
+                                    p2_count, 1), "curfit pass kernel"))
         return FPB_ERR_CUDA;
-    end_timing(eng);
     eng->launches++;
+    int cur = 0, remaining = (iopt < 0) ? 0 : nbatch;  // iopt=-1: a single pass settles every curve
+    const int max_rounds = 2 * (m + 4) + 8;  // fpcurf's own bound on knot sets, with one restart
+    for (int round = 1; round <= max_rounds && remaining > 0; ++round) {
+        if (round >= 3 && (round & 1)) {
+            if (!cuda_ok(cudaMemcpyAsync(eng->h_count, lcount[cur], sizeof(int),
+                                         cudaMemcpyDeviceToHost, st), "count D2H") ||
+                !cuda_ok(cudaStreamSynchronize(st), "sync"))
+                return FPB_ERR_CUDA;
+            remaining = eng->h_count[0];
+            if (remaining <= 0) break;
+        }
+        // reset the queue head and the output list length
+        if (!cuda_ok(cudaMemsetAsync(cnt, 0, sizeof(int), st), "memset") ||
+            !cuda_ok(cudaMemsetAsync(lcount[1 - cur], 0, sizeof(int), st), "memset"))
+            return FPB_ERR_CUDA;
+        long long g2 = std::min<long long>(grid, ((long long)remaining + kFitThreads - 1) / kFitThreads);
+        if (g2 < 1) g2 = 1;
+        if (!cuda_ok(launch_curfit_pass(p, (int)g2, st, list[cur], lcount[cur], list[1 - cur],
+                                        lcount[1 - cur], p2_list, p2_count, 0), "curfit pass kernel"))
+            return FPB_ERR_CUDA;
+        eng->launches++;
+        cur = 1 - cur;
+    }
+    // part 2 on the curves whose knots were accepted with fp < s
+    if (iopt >= 0) {
+        if (!cuda_ok(cudaMemcpyAsync(eng->h_count, p2_count, sizeof(int), cudaMemcpyDeviceToHost, st),
+                     "count D2H") ||
+            !cuda_ok(cudaStreamSynchronize(st), "sync"))
+            return FPB_ERR_CUDA;
+        const int n2 = eng->h_count[0];
+        if (n2 > 0) {
+            if (!cuda_ok(launch_p2_sort(p2_list, p2_count, n, p.hist, L.nestp + 1, p2_sorted, eng->nsm,
+                                        st), "part-2 sort") ||
+                !cuda_ok(cudaMemsetAsync(cnt, 0, sizeof(int), st), "memset"))
+                return FPB_ERR_CUDA;
+            eng->launches += 2;
+            long long g2 = std::min<long long>(grid, ((long long)n2 + kFitThreads - 1) / kFitThreads);
+            if (!cuda_ok(launch_curfit_part2(p, (int)g2, st, p2_sorted, p2_count), "curfit part-2 kernel"))
+                return FPB_ERR_CUDA;
+            eng->launches++;
+        }
+    }
+    end_timing(eng);
     return FPB_STATUS_OK;
 }
 

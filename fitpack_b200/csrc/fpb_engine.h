@@ -33,6 +33,8 @@ struct fpb_engine {
     bool timed = false;
     int64_t launches = 0;
     fpb::DevBuf ws, wsi, counter;     // fit kernel workspace
+    fpb::DevBuf lists, st_i, st_d, st_nrd;  // pass pipeline: curve lists and per-curve state
+    int *h_count = nullptr;           // pinned host word for list-length read-back
     fpb::DevBuf plan_cs, plan_w, plan_row, plan_skip, plan_R, plan_ier;  // shared-x plan
     fpb::DevBuf scratch[12];          // staging for the host-pointer entry points
 };

@@ -33,10 +33,21 @@ struct FitParams {
     int *stats;
     double *ws;             // [resident warps][ws_per_lane][32]
     int *wsi;               // [resident warps][nestp][32]   (nrdata)
-    unsigned int *counter;  // tile queue head, zeroed before the launch
+    unsigned int *counter;  // tile queue head, zeroed before every launch
     int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q, ws_per_lane;
+    // per-curve state carried between passes (engine-owned)
+    int *st_nplus, *st_iter;
+    double *st_fpold, *st_fp0;
+    int *st_nrd;            // [nbatch][nestp]  nrdata(1:nrint)
+    int *hist;              // [nestp+1] histogram of n over the part-2 list
 };
-cudaError_t launch_curfit(const FitParams &p, int grid_blocks, cudaStream_t stream);
+cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t stream,
+                               const int *in_list, const int *in_count, int *out_list,
+                               int *out_count, int *p2_list, int *p2_count, int first);
+cudaError_t launch_curfit_part2(const FitParams &p, int grid_blocks, cudaStream_t stream,
+                                const int *list, const int *count);
+cudaError_t launch_p2_sort(const int *list, const int *count, const int *n_arr, int *hist,
+                           int nbins, int *sorted, int nsm, cudaStream_t stream);
 
 // ---- shared-abscissa least squares (iopt=-1, one x/w/t for the whole batch) ----
 struct SharedPlan {
