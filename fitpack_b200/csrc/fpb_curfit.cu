@@ -104,14 +104,15 @@ __device__ __forceinline__ void back_subst(const FitParams &p, double *wsd, int 
 
 // sum of squared residuals of the current c over all points using the stored
 // basis values q (get_fp loop, core:5061-5069); when FPINT is set also the
-// per-interval split of core:4942-4966.  Loads of 2 consecutive points are
+// per-interval split of core:4942-4966.  Loads of 4 consecutive points are
 // issued together (they do not depend on the interval walk) to cover HBM latency.
 template <int K, bool FPINT, bool HAS_W>
 __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd, const double *xp,
-                                                const double *yp, const double *wp, int m, int nk1,
+                                                const double *yp, const double *wp, size_t x_si,
+                                                size_t y_si, size_t w_si, int m, int nk1,
                                                 int nrint, bool on)
 {
-    constexpr int K1 = K + 1, K2 = K + 2, U = 2;
+    constexpr int K1 = K + 1, K2 = K + 2, U = 4;
     double cw[K1];
     double fpart = 0.0, tl = 0.0;
     int l = K2, i = 1;
@@ -128,9 +129,9 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int it = min(it0 + u, m - 1);
-            xv[u] = xp[(size_t)it * p.x_si];
-            yv[u] = yp[(size_t)it * p.y_si];
-            wv[u] = HAS_W ? wp[(size_t)it * p.w_si] : 1.0;
+            xv[u] = xp[(size_t)it * x_si];
+            yv[u] = yp[(size_t)it * y_si];
+            wv[u] = HAS_W ? wp[(size_t)it * w_si] : 1.0;
             if (on) {
 #pragma unroll
                 for (int j = 0; j < K1; ++j) qv[u][j] = Q_(it, j);
@@ -174,8 +175,8 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
 // held in registers; returns fp = sum of squared transformed right-hand sides.
 template <int K, bool HAS_W>
 __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, const double *xp,
-                                           const double *yp, const double *wp, int m, int nk1,
-                                           bool on)
+                                           const double *yp, const double *wp, size_t x_si,
+                                           size_t y_si, size_t w_si, int m, int nk1, bool on)
 {
     constexpr int K1 = K + 1;
     double R[K1][K1], Zw[K1], tw[2 * K], h[K1];
@@ -204,9 +205,9 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, cons
         double yi = HAS_W ? mul(yn, wi) : yn;
         {
             const int nx = min(it + 1, m - 1);
-            xn = xp[(size_t)nx * p.x_si];
-            yn = yp[(size_t)nx * p.y_si];
-            if (HAS_W) wn = wp[(size_t)nx * p.w_si];
+            xn = xp[(size_t)nx * x_si];
+            yn = yp[(size_t)nx * y_si];
+            if (HAS_W) wn = wp[(size_t)nx * w_si];
         }
         if (on) {
             // fp_knot_interval (core:2432-2473) == linear walk from the previous interval
@@ -482,7 +483,8 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             for (int i = nk1 + 1; i <= n; ++i) T_(i) = xe;
             ran_pass = true;
         }
-        const double fp_pass = lsq_pass<K, HAS_W>(p, wsd, xp, yp, wp, m, nk1, on);
+        const double fp_pass = lsq_pass<K, HAS_W>(p, wsd, xp, yp, wp, (size_t)p.x_si, (size_t)p.y_si,
+                                                  (size_t)p.w_si, m, nk1, on);
         if (on) {
             fp = fp_pass;
             if (ier == IER_LSQ) fp0 = fp;
@@ -516,7 +518,8 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             fpold = fp;
         }
         if (__any_sync(FULL, on))
-            (void)residual_pass<K, true, HAS_W>(p, wsd, xp, yp, wp, m, nk1, nrint, on);
+            (void)residual_pass<K, true, HAS_W>(p, wsd, xp, yp, wp, (size_t)p.x_si, (size_t)p.y_si,
+                                                (size_t)p.w_si, m, nk1, nrint, on);
         // add_new_knots, core:4968-4996 with fpknot core:8199-8275 inlined
         {
             const int maxplus = __reduce_max_sync(FULL, on ? nplus : 0);
@@ -527,17 +530,28 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
                 const int hi = __reduce_max_sync(FULL, act ? nrint : 0);
                 double fpmax = 0.0;
                 int number = 0, maxpt = 0, maxbeg = 0, jbegin = 1;
-                for (int j = 1; j <= hi; ++j) {
-                    if (act && j <= nrint) {
-                        const int jpoint = NRD_(j);
-                        const double fj = FPI_(j);
-                        if (jpoint != 0 && (number == 0 || fj > fpmax)) {
-                            fpmax = fj;
-                            number = j;
-                            maxpt = jpoint;
-                            maxbeg = jbegin;
+                // loads of 4 intervals are issued together (independent of the running maximum)
+                for (int j0 = 1; j0 <= hi; j0 += 4) {
+                    int jp[4];
+                    double fv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool in = act && (j0 + u) <= nrint;
+                        jp[u] = in ? NRD_(j0 + u) : 0;
+                        fv[u] = in ? FPI_(j0 + u) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (act && (j0 + u) <= nrint) {
+                            const int jpoint = jp[u];
+                            if (jpoint != 0 && (number == 0 || fv[u] > fpmax)) {
+                                fpmax = fv[u];
+                                number = j0 + u;
+                                maxpt = jpoint;
+                                maxbeg = jbegin;
+                            }
+                            jbegin = jbegin + jpoint + 1;
                         }
-                        jbegin = jbegin + jpoint + 1;
                     }
                 }
                 const bool ins = act && number != 0;
@@ -545,11 +559,28 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
                 const int ihalf = maxpt / 2 + 1;
                 const int nrx = maxbeg + ihalf;
                 const int next = number + 1;
-                for (int jj = hi; jj >= 1; --jj) {
-                    if (ins && jj >= next && jj <= nrint) {
-                        FPI_(jj + 1) = FPI_(jj);
-                        NRD_(jj + 1) = NRD_(jj);
-                        T_(jj + K + 1) = T_(jj + K);
+                // shift right by one, descending in chunks of 4: all loads of a chunk precede its
+                // stores, and a chunk only overwrites slots that later (lower) chunks never read
+                for (int j0 = hi; j0 >= 1; j0 -= 4) {
+                    double fv[4], tv[4];
+                    int nv[4];
+                    bool mv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int jj = j0 - u;
+                        mv[u] = ins && jj >= next && jj <= nrint && jj >= 1;
+                        fv[u] = mv[u] ? FPI_(jj) : 0.0;
+                        nv[u] = mv[u] ? NRD_(jj) : 0;
+                        tv[u] = mv[u] ? T_(jj + K) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int jj = j0 - u;
+                        if (mv[u]) {
+                            FPI_(jj + 1) = fv[u];
+                            NRD_(jj + 1) = nv[u];
+                            T_(jj + K + 1) = tv[u];
+                        }
                     }
                 }
                 if (ins) {
@@ -646,7 +677,34 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
     const int nk1 = n - K1;
     const int n8 = n - nmin;
     const bool on2 = valid;
-    double fp = lsq_pass<K, HAS_W>(p, wsd, xp, yp, wp, m, nk1, on2);
+    // The part-2 list is sorted by knot count, so the lanes of a warp hold unrelated curves and
+    // their x/y reads are scattered (one 32 B sector per 8 B).  Gather the curve's data ONCE into
+    // the warp's interleaved workspace; the LSQ pass and every f(p) evaluation then stream it
+    // with fully coalesced loads.
+    {
+        constexpr int U = 8;
+        for (int it0 = 0; it0 < m; it0 += U) {
+            double xv[U], yv[U], wv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int it = min(it0 + u, m - 1);
+                xv[u] = xp[(size_t)it * p.x_si];
+                yv[u] = yp[(size_t)it * p.y_si];
+                wv[u] = HAS_W ? wp[(size_t)it * p.w_si] : 1.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (it0 + u < m) {
+                    WS(p.off_x, it0 + u) = xv[u];
+                    WS(p.off_y, it0 + u) = yv[u];
+                    if (HAS_W) WS(p.off_w, it0 + u) = wv[u];
+                }
+            }
+        }
+    }
+    const double *xg = &WS(p.off_x, 0), *yg = &WS(p.off_y, 0);
+    const double *wg = HAS_W ? &WS(p.off_w, 0) : nullptr;
+    double fp = lsq_pass<K, HAS_W>(p, wsd, xg, yg, wg, 32, 32, 32, m, nk1, on2);
     double fpms = sub(fp, s);
     // fpdisc, core:5453-5495
     {
@@ -712,23 +770,39 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
 #pragma unroll
             for (int q = 0; q < K2; ++q) h[q] = row_on ? mul(B_(it, q + 1), pinv) : 0.0;
             double yi = 0.0;
-            // fp_rotate_shifted, core:5800-5820
+            // fp_rotate_shifted, core:5800-5820.  Row j+1 of G (and c(j+1)) is requested before
+            // the div/sqrt chain of row j starts: the sweep is otherwise bound by L2 latency.
+            double gn[K2], cn = 0.0;
+            {
+                const bool pre = row_on && it <= nk1;
+#pragma unroll
+                for (int q = 0; q < K2; ++q) gn[q] = pre ? G_(it, q + 1) : 0.0;
+                cn = pre ? C_(it) : 0.0;
+            }
             for (int j = it; j <= hi; ++j) {
+                double gc[K2], cj = cn;
+#pragma unroll
+                for (int q = 0; q < K2; ++q) gc[q] = gn[q];
+                {
+                    const bool pre = row_on && (j + 1) <= nk1;
+#pragma unroll
+                    for (int q = 0; q < K2; ++q) gn[q] = pre ? G_(j + 1, q + 1) : 0.0;
+                    cn = pre ? C_(j + 1) : 0.0;
+                }
                 if (row_on && j <= nk1) {
                     const double piv = h[0];
                     const int noff = min(nk1 - j, K1);
                     if (!fp_is_zero(piv)) {
-                        double gd = G_(j, 1), cj = C_(j), cs, sn;
-                        givens(piv, gd, cs, sn);
-                        G_(j, 1) = gd;
+                        double cs, sn;
+                        givens(piv, gc[0], cs, sn);
+                        G_(j, 1) = gc[0];
                         rota(cs, sn, yi, cj);
                         C_(j) = cj;
 #pragma unroll
                         for (int q = 1; q <= K1; ++q) {
                             if (q <= noff) {
-                                double gq = G_(j, q + 1);
-                                rota(cs, sn, h[q], gq);
-                                G_(j, q + 1) = gq;
+                                rota(cs, sn, h[q], gc[q]);
+                                G_(j, q + 1) = gc[q];
                             }
                         }
                     }
@@ -739,7 +813,7 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
             }
         }
         back_subst<K2>(p, wsd, p.off_g, p.off_c, nk1, on);
-        const double fpn = residual_pass<K, false, HAS_W>(p, wsd, xp, yp, wp, m, nk1, 0, on);
+        const double fpn = residual_pass<K, false, HAS_W>(p, wsd, xg, yg, wg, 32, 32, 32, m, nk1, 0, on);
         if (on) {
             fp = fpn;
             fpms = sub(fp, s);
@@ -921,6 +995,9 @@ FitLayout fit_layout(int m, int k, int nest)
     L.off_g = off; off += nestp * k2;
     L.off_b = off; off += nestp * k2;
     L.off_q = off; off += m * k1;
+    L.off_x = off; off += m;   // part 2: the curve's own data, gathered once
+    L.off_y = off; off += m;
+    L.off_w = off; off += m;
     L.ws_per_lane = off;
     return L;
 }

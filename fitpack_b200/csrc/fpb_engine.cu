@@ -63,8 +63,9 @@ fpb_engine *default_engine(int device)
     if (device >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(g_engines_mu);
     if (!g_engines[device]) {
+        // slots 32..63 hold a second engine for devices 0..31 (copy/compute overlap workers)
         fpb_engine *e = nullptr;
-        if (fpb_engine_create(device, &e) != FPB_STATUS_OK) return nullptr;
+        if (fpb_engine_create(device & 31, &e) != FPB_STATUS_OK) return nullptr;
         g_engines[device] = e;
     }
     return g_engines[device];
@@ -157,6 +158,13 @@ void fpb_engine_destroy(fpb_engine *eng)
     eng->st_d.release();
     eng->st_nrd.release();
     if (eng->h_count) cudaFreeHost(eng->h_count);
+    for (auto &b : eng->scratch2) b.release();
+    if (eng->s_in) cudaStreamDestroy(eng->s_in);
+    if (eng->s_out) cudaStreamDestroy(eng->s_out);
+    for (int i = 0; i < 2; ++i) {
+        if (eng->ev_in[i]) cudaEventDestroy(eng->ev_in[i]);
+        if (eng->ev_fit[i]) cudaEventDestroy(eng->ev_fit[i]);
+    }
     eng->plan_cs.release();
     eng->plan_w.release();
     eng->plan_row.release();
@@ -300,6 +308,7 @@ int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_
     p.counter = reinterpret_cast<unsigned *>(cnt);
     p.off_t = L.off_t; p.off_c = L.off_c; p.off_z = L.off_z; p.off_fpint = L.off_fpint;
     p.off_a = L.off_a; p.off_g = L.off_g; p.off_b = L.off_b; p.off_q = L.off_q;
+    p.off_x = L.off_x; p.off_y = L.off_y; p.off_w = L.off_w;
     p.ws_per_lane = L.ws_per_lane;
     p.st_nplus = eng->st_i.as<int>(); p.st_iter = p.st_nplus + nb;
     p.st_fpold = eng->st_d.as<double>(); p.st_fp0 = p.st_fpold + nb;
@@ -488,24 +497,23 @@ double fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused)
 
 namespace {
 
-// one GPU's share of a host-pointer batch fit, processed in chunks that bound
-// the device footprint
-int32_t fit_slice_host(fpb_engine *eng, long long b0, long long b1, FP_SIZE iopt, FP_SIZE m,
-                       const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
-                       const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
-                       FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
-                       FP_REAL *fpint, FP_SIZE *nrdata)
+// Sequential worker: fits the chunks [c_first, c_first + stride, ...) of a slice on ONE engine
+// (its stream, workspace and staging buffers): H2D, tile transpose, fit pipeline, D2H.
+int32_t fit_chunks_worker(fpb_engine *eng, long long b0, long long b1, long long chunk,
+                          long long c_first, long long c_stride, FP_SIZE iopt, FP_SIZE m,
+                          const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
+                          const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
+                          FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
+                          FP_REAL *fpint, FP_SIZE *nrdata)
 {
     DeviceGuard g(eng->device);
     if (!g.ok) return FPB_ERR_CUDA;
     cudaStream_t st = eng->stream;
-    // bytes per curve on the device: x,y,w curve-major + point-major, outputs t,c (+state)
-    const size_t per_curve = (size_t)m * 8 * 6 + (size_t)nest * 8 * 2 + (size_t)nest * 12 + 64;
-    long long chunk = (long long)(((size_t)6 << 30) / per_curve);
-    chunk = std::max<long long>(chunk - chunk % 128, 128);
     const bool state = (fpint && nrdata);
     enum { XC, YC, WC, XP, YP, WP, TT, CC, NN, FP_, IER, AUX };
-    for (long long c0 = b0; c0 < b1; c0 += chunk) {
+    const long long nchunks = (b1 - b0 + chunk - 1) / chunk;
+    for (long long ci = c_first; ci < nchunks; ci += c_stride) {
+        const long long c0 = b0 + ci * chunk;
         const long long nb = std::min(chunk, b1 - c0);
         const size_t pts = (size_t)nb * m * sizeof(double);
         DevBuf *B = eng->scratch;
@@ -605,23 +613,21 @@ int32_t fit_slice_host(fpb_engine *eng, long long b0, long long b1, FP_SIZE iopt
         // knots/coefficients: only the leading max(n) columns carry information
         int nmax_used = 0;
         bool any_fit = false;
+        std::vector<long long> bad;
         for (long long b = 0; b < nb; ++b) {
             if (ier[c0 + b] != FPB_INPUT_ERROR) {
                 nmax_used = std::max(nmax_used, (int)n[c0 + b]);
                 any_fit = true;
+            } else if (iopt != -1) {
+                bad.push_back(b);
             }
         }
         if (iopt == -1) nmax_used = nest;  // clamped end knots may have been written even on ier=10
         nmax_used = std::min<int>(std::max(nmax_used, 0), nest);
         if (nmax_used > 0 && (any_fit || iopt == -1)) {
-            // rows whose fit was rejected keep the caller's t/c: copy only accepted rows' columns.
-            // (2-D copy of the leading columns; rejected rows are restored from a host backup.)
-            std::vector<double> keep_t, keep_c;
-            std::vector<long long> bad;
-            for (long long b = 0; b < nb; ++b)
-                if (ier[c0 + b] == FPB_INPUT_ERROR && iopt != -1) bad.push_back(b);
-            keep_t.resize(bad.size() * (size_t)nmax_used);
-            keep_c.resize(bad.size() * (size_t)nmax_used);
+            // rows whose fit was rejected keep the caller's t/c (2-D copy of the leading columns;
+            // rejected rows are restored from a host backup)
+            std::vector<double> keep_t(bad.size() * (size_t)nmax_used), keep_c(keep_t.size());
             for (size_t i = 0; i < bad.size(); ++i) {
                 std::memcpy(&keep_t[i * nmax_used], t + (size_t)(c0 + bad[i]) * nest,
                             (size_t)nmax_used * 8);
@@ -631,11 +637,9 @@ int32_t fit_slice_host(fpb_engine *eng, long long b0, long long b1, FP_SIZE iopt
             ok = cuda_ok(cudaMemcpy2DAsync(t + (size_t)c0 * nest, (size_t)nest * 8, B[TT].ptr,
                                            (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
                                            cudaMemcpyDeviceToHost, st), "D2H t");
-            if (iopt != -1 || any_fit)
-                ok = ok && cuda_ok(cudaMemcpy2DAsync(c + (size_t)c0 * nest, (size_t)nest * 8,
-                                                     B[CC].ptr, (size_t)nest * 8,
-                                                     (size_t)nmax_used * 8, (size_t)nb,
-                                                     cudaMemcpyDeviceToHost, st), "D2H c");
+            ok = ok && cuda_ok(cudaMemcpy2DAsync(c + (size_t)c0 * nest, (size_t)nest * 8, B[CC].ptr,
+                                                 (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
+                                                 cudaMemcpyDeviceToHost, st), "D2H c");
             if (state && iopt >= 0) {
                 ok = ok && cuda_ok(cudaMemcpyAsync(fpint + (size_t)c0 * nest, dfpint,
                                                    (size_t)nb * nest * 8, cudaMemcpyDeviceToHost,
@@ -653,6 +657,55 @@ int32_t fit_slice_host(fpb_engine *eng, long long b0, long long b1, FP_SIZE iopt
             }
         }
     }
+    return FPB_STATUS_OK;
+}
+
+// One GPU's share of a host-pointer batch fit.  Large slices are cut into chunks that two
+// host workers (each with its own engine = stream + workspace + staging) process alternately,
+// so that one chunk's copies and the sparsely populated tail of its fit pipeline overlap the
+// other chunk's compute.  Calls for one device are serialised by a per-device mutex.
+std::mutex g_host_api_mu[64];
+
+int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_SIZE m,
+                       const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
+                       const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
+                       FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
+                       FP_REAL *fpint, FP_SIZE *nrdata)
+{
+    if (device < 0 && !cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return FPB_ERR_CUDA;
+    if (device >= 32) return FPB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_host_api_mu[device]);
+    fpb_engine *e0 = default_engine(device);
+    if (!e0) return FPB_ERR_CUDA;
+    const long long total = b1 - b0;
+    const size_t per_curve = (size_t)m * 8 * 6 + (size_t)nest * 8 * 2 + (size_t)nest * 12 + 64;
+    long long chunk = (long long)(((size_t)4 << 30) / per_curve);  // <= 4 GB of staging per engine
+    const bool split = total >= 4 * 65536;
+    if (split) chunk = std::min(chunk, std::max<long long>((total + 7) / 8, 65536));
+    chunk = std::max<long long>(chunk - chunk % 128, 128);
+    if (!split) {
+        return fit_chunks_worker(e0, b0, b1, chunk, 0, 1, iopt, m, x, y, w, shared_x, xb, xe, k, s,
+                                 nest, n, t, c, fp, ier, fpint, nrdata);
+    }
+    fpb_engine *e1 = default_engine(device + 32);  // second engine of the same device
+    if (!e1) return FPB_ERR_CUDA;
+    int32_t rc[2] = {FPB_STATUS_OK, FPB_STATUS_OK};
+    std::string err[2];
+    std::thread th[2];
+    fpb_engine *eng2[2] = {e0, e1};
+    for (int wk = 0; wk < 2; ++wk) {
+        th[wk] = std::thread([&, wk]() {
+            rc[wk] = fit_chunks_worker(eng2[wk], b0, b1, chunk, wk, 2, iopt, m, x, y, w, shared_x, xb,
+                                       xe, k, s, nest, n, t, c, fp, ier, fpint, nrdata);
+            if (rc[wk] != FPB_STATUS_OK) err[wk] = fpb_last_error();
+        });
+    }
+    for (auto &tt : th) tt.join();
+    for (int wk = 0; wk < 2; ++wk)
+        if (rc[wk] != FPB_STATUS_OK) {
+            set_last_error(err[wk]);
+            return rc[wk];
+        }
     return FPB_STATUS_OK;
 }
 
@@ -768,8 +821,8 @@ int32_t fp_curfit_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL
         return FPB_STATUS_OK;
     }
     return shard_over_gpus(nbatch, ngpus, 128, [&](fpb_engine *e, long long b0, long long b1) {
-        return fit_slice_host(e, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest, n, t, c,
-                              fp, ier, nullptr, nullptr);
+        return fit_slice_host(e->device, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest, n,
+                              t, c, fp, ier, nullptr, nullptr);
     });
 }
 
@@ -811,8 +864,8 @@ void fp_curfit_c(FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y, co
     }
     // wrk(1:nest) is fpint and iwrk(1:nest) is nrdata in the reference (core:1289-1297):
     // that is the state an iopt=1 continuation reads back.
-    int32_t rc = fit_slice_host(e, 0, 1, iopt, m, x, y, w, 0, &xb, &xe, k, s, nest, n, t, c, fp,
-                                ier, wrk, iwrk);
+    int32_t rc = fit_slice_host(e->device, 0, 1, iopt, m, x, y, w, 0, &xb, &xe, k, s, nest, n, t, c,
+                                fp, ier, wrk, iwrk);
     if (rc != FPB_STATUS_OK) *ier = rc;
 }
 

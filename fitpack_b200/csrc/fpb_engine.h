@@ -37,6 +37,10 @@ struct fpb_engine {
     int *h_count = nullptr;           // pinned host word for list-length read-back
     fpb::DevBuf plan_cs, plan_w, plan_row, plan_skip, plan_R, plan_ier;  // shared-x plan
     fpb::DevBuf scratch[12];          // staging for the host-pointer entry points
+    fpb::DevBuf scratch2[12];         // second staging set (copy/compute overlap)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_fit[2] = {nullptr, nullptr};
+    double h_aux[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 };
 
 namespace fpb {

@@ -11,7 +11,7 @@ constexpr int kFitThreads = 128;  // threads per CTA of the fit kernel (4 warps 
 // per-lane workspace layout of the fit kernel, in elements of 8 bytes
 struct FitLayout {
     int nestp;  // knots a curve can actually reach: min(nest, m+k+1)
-    int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q;
+    int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q, off_x, off_y, off_w;
     int ws_per_lane;
 };
 FitLayout fit_layout(int m, int k, int nest);
@@ -34,7 +34,7 @@ struct FitParams {
     double *ws;             // [resident warps][ws_per_lane][32]
     int *wsi;               // [resident warps][nestp][32]   (nrdata)
     unsigned int *counter;  // tile queue head, zeroed before every launch
-    int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q, ws_per_lane;
+    int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q, off_x, off_y, off_w, ws_per_lane;
     // per-curve state carried between passes (engine-owned)
     int *st_nplus, *st_iter;
     double *st_fpold, *st_fp0;

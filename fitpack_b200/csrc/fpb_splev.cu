@@ -71,9 +71,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t phase)
     } while (!done);
 }
 
+// number of cells of the interval lookup grid for a spline with `nint` knot intervals
+__host__ __device__ inline int splev_grid_cells(int nint)
+{
+    int g = 32;
+    while (g < 2 * nint && g < 1024) g <<= 1;
+    return g;
+}
+
+// per-warp shared memory in doubles: [t: ld][c: ld] (+ fast mode [dlev: K*ld][poly: K1*ld])
+// followed by the lookup grid (ints, counted here in doubles)
 __host__ __device__ inline int splev_smem_doubles(int mode, int k, int ld)
 {
-    return (mode == 1) ? ld * (2 + k + (k + 1)) : ld * 2;
+    const int grid = splev_grid_cells(ld - 2 * k - 1) / 2;
+    return ((mode == 1) ? ld * (2 + k + (k + 1)) : ld * 2) + grid;
+}
+
+// 1/d to ~1 ulp without the IEEE division sequence (FAST mode only): hardware seed + two
+// Newton steps; falls back to a true division outside the safe exponent range.
+__device__ __forceinline__ double fast_rcp(double d)
+{
+    const double ad = fabs(d);
+    if (!(ad > 1e-290 && ad < 1e290)) return 1.0 / d;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
 }
 
 // interval search: l = k1 + #{ i in (k1, nk1] : t(i) <= arg }  (1-based), t non-decreasing.
@@ -87,6 +113,19 @@ __device__ __forceinline__ int find_interval(const double *ts, int k1, int nk1, 
         if (cand <= nk1 && ts[cand - 1] <= arg) lo = cand;
     }
     return lo;
+}
+
+// Interval of `arg` from the lookup grid + the reference's own bidirectional walk
+// (core:17880-17887), which makes the result independent of the quality of the guess.
+__device__ __forceinline__ int locate(const double *ts, const int *grid, int gcells, double tb,
+                                      double inv_h, int k1, int nk1, double arg)
+{
+    int g = __double2int_rz((arg - tb) * inv_h);
+    g = max(0, min(g, gcells - 1));
+    int l = grid[g];
+    while (l > k1 && arg < ts[l - 1]) --l;
+    while (l < nk1 && arg >= ts[l]) ++l;
+    return l;
 }
 
 template <int K>
@@ -123,7 +162,7 @@ __device__ void build_local_polys(const double *ts, const double *cs, int n, int
             double v = 0.0;
             if (i0 >= r) {
                 const double den = ts[i0 + K - r + 1] - ts[i0];
-                if (fabs(den) >= DBL_MIN) v = scale * (prev[i0] - prev[i0 - 1]) / den;
+                if (fabs(den) >= DBL_MIN) v = scale * (prev[i0] - prev[i0 - 1]) * fast_rcp(den);
             }
             cur[i0] = v;
         }
@@ -146,7 +185,7 @@ __device__ void build_local_polys(const double *ts, const double *cs, int n, int
                 const double tli = ts[l + i - 1], tlj = ts[l + i - j - 1];
                 const double d = tli - tlj;
                 if (fabs(d) >= DBL_MIN) {
-                    const double f = hh[i - 1] / d;
+                    const double f = hh[i - 1] * fast_rcp(d);
                     h[i - 1] = fma(f, tli - x, h[i - 1]);
                     h[i] = f * (x - tlj);
                 } else {
@@ -166,7 +205,8 @@ __device__ void build_local_polys(const double *ts, const double *cs, int n, int
 
 constexpr int kUnroll = 4;  // independent points per lane per iteration (memory-level parallelism)
 
-template <int K, int MODE>
+// PLAIN: e == OUTSIDE_EXTRAPOLATE and no interval-index output -- no per-point policy code.
+template <int K, int MODE, bool PLAIN>
 __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
     splev_kernel(SplevParams p, int smem_ld)
 {
@@ -174,12 +214,12 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    // per-warp regions: [t: ld][c: ld] and in fast mode [dlev: K*ld][poly: K1*ld]
     const int per_warp = splev_smem_doubles(MODE, K, smem_ld);
     uint64_t *mbars = reinterpret_cast<uint64_t *>(smem_raw);
     double *base = reinterpret_cast<double *>(smem_raw + 16 * kSplevWarps) + (size_t)warp * per_warp;
     double *ts = base, *cs = base + smem_ld, *dlev = base + 2 * smem_ld,
            *poly = base + (size_t)(2 + K) * smem_ld;
+    int *grid = reinterpret_cast<int *>(base + ((MODE == 1) ? smem_ld * (2 + K + K1) : smem_ld * 2));
     uint64_t *mbar = mbars + warp * 2;
     if (lane == 0) {
         mbar_init(mbar, 1);
@@ -191,7 +231,8 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
     const long long gwarp = (long long)blockIdx.x * wpb + warp;
     const long long nwarps = (long long)gridDim.x * wpb;
     int cached = -1;
-    int n = 0;
+    int n = 0, gcells = 32;
+    double inv_h = 0.0;
     for (long long j = gwarp; j < p.nspl; j += nwarps) {
         const long long tj = p.nshared ? 0 : j;
         if (tj != cached) {
@@ -217,14 +258,26 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
                 }
             }
             __syncwarp();
+            // lookup grid over [t(k+1), t(n-k)]: grid[g] = interval of the cell's left edge
+            {
+                const int nk1_ = n - K1;
+                const int nint = nk1_ - K1 + 1;
+                gcells = splev_grid_cells(nint);
+                const double tb_ = ts[K1 - 1], te_ = ts[nk1_];
+                const double span = te_ - tb_;
+                inv_h = (span > 0.0) ? (double)gcells / span : 0.0;
+                const double hcell = span / (double)gcells;
+                int top = 1;
+                while (top * 2 <= nk1_ - K1) top *= 2;
+                if (nk1_ - K1 < 1) top = 0;
+                for (int gI = lane; gI < gcells; gI += 32)
+                    grid[gI] = find_interval(ts, K1, nk1_, top, tb_ + (double)gI * hcell);
+            }
             if (MODE == 1) build_local_polys<K>(ts, cs, n, smem_ld, dlev, poly, lane);
             __syncwarp();
             cached = (int)tj;
         }
         const int nk1 = n - K1;
-        int top = 1;
-        while (top * 2 <= nk1 - K1) top *= 2;
-        if (nk1 - K1 < 1) top = 0;
         const double tb = ts[K1 - 1], te = ts[nk1];
         const double *xg = p.x + j * p.m;
         double *yg = p.y + j * p.m;
@@ -238,19 +291,22 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
                 const int i = i0 + 32 * u;
                 live[u] = i < p.m;
                 arg[u] = live[u] ? xg[i] : tb;
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
                 zero[u] = false;
-                if (arg[u] < tb || arg[u] > te) {  // core:17864-17877
-                    if (p.e == 1) zero[u] = true;
-                    else if (p.e == 2) out_of_range = out_of_range || live[u];
-                    else if (p.e == 3) arg[u] = fmax(fmin(arg[u], te), tb);
+            }
+            if (!PLAIN) {
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    if (arg[u] < tb || arg[u] > te) {  // core:17864-17877
+                        if (p.e == 1) zero[u] = true;
+                        else if (p.e == 2) out_of_range = out_of_range || live[u];
+                        else if (p.e == 3) arg[u] = fmax(fmin(arg[u], te), tb);
+                    }
                 }
             }
             int l[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) l[u] = find_interval(ts, K1, nk1, top, arg[u]);
+            for (int u = 0; u < kUnroll; ++u)
+                l[u] = locate(ts, grid, gcells, tb, inv_h, K1, nk1, arg[u]);
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 double sp;
@@ -265,8 +321,12 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
                 }
                 const int i = i0 + 32 * u;
                 if (live[u]) {
-                    yg[i] = zero[u] ? 0.0 : sp;
-                    if (lg) lg[i] = zero[u] ? 0 : l[u];
+                    if (PLAIN) {
+                        yg[i] = sp;
+                    } else {
+                        yg[i] = zero[u] ? 0.0 : sp;
+                        if (lg) lg[i] = zero[u] ? 0 : l[u];
+                    }
                 }
             }
         }
@@ -294,7 +354,9 @@ cudaError_t launch_splev(const SplevParams &p, int nsm, cudaStream_t stream)
     if (blocks > max_blocks) blocks = max_blocks;
 #define FPB_LAUNCH_SPLEV(KK)                                                                       \
     do {                                                                                           \
-        auto kern = (p.mode == 1) ? splev_kernel<KK, 1> : splev_kernel<KK, 0>;                     \
+        const bool plain = (p.e == 0 && p.lidx == nullptr);                                       \
+        auto kern = (p.mode == 1) ? (plain ? splev_kernel<KK, 1, true> : splev_kernel<KK, 1, false>)\
+                                  : (plain ? splev_kernel<KK, 0, true> : splev_kernel<KK, 0, false>);\
         cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                               (int)smem);                                          \
         if (e_ != cudaSuccess) return e_;                                                          \
