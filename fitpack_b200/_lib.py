@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfitpack_b200.so")
+LIB_PATH = os.environ.get("FITPACK_B200_LIB") or os.path.join(_HERE, "libfitpack_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int32)

@@ -38,6 +38,26 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > tm for d in deps)
 
 
+def build_variant(tag, defines):
+    """Experimental side build (tuning only): same sources with extra -D flags, written to
+    libfitpack_b200_<tag>.so; select it at run time with FITPACK_B200_LIB=<path>."""
+    nvcc = nvcc_path()
+    bdir = os.path.join(HERE, "_build", "var_" + tag)
+    os.makedirs(bdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        o = os.path.join(bdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-x", "cu", "-c",
+                                                                   os.path.join(CSRC, src), "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout + r.stderr)
+        objs.append(o)
+    out = os.path.join(HERE, "libfitpack_b200_%s.so" % tag)
+    subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-lcudart"])
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     nvcc = nvcc_path()

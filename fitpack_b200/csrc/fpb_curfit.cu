@@ -112,7 +112,7 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
                                                 size_t y_si, size_t w_si, int m, int nk1,
                                                 int nrint, bool on)
 {
-    constexpr int K1 = K + 1, K2 = K + 2, U = 4;
+    constexpr int K1 = K + 1, K2 = K + 2, U = 2;
     double cw[K1];
     double fpart = 0.0, tl = 0.0;
     int l = K2, i = 1;
@@ -171,22 +171,30 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
     return fpart;
 }
 
-// one least-squares pass (coefs loop core:4873-4896) with the active band rows
-// held in registers; returns fp = sum of squared transformed right-hand sides.
+// one least-squares pass (coefs loop core:4873-4896); returns fp = sum of squared transformed
+// right-hand sides.  A point in knot interval l only touches band rows l-k..l and x is sorted,
+// so only k+1 rows of R (+ right-hand sides) are live at any time.  They sit in a per-thread
+// circular window in SHARED memory (column `rs` of the CTA's buffer, conflict-free
+// [element][thread] layout): that keeps the kernel at <= 80 registers, i.e. 24 warps per SM
+// instead of 16 -- the pass is bound by dependent FP64 issue latency, so warps are throughput.
+// A row is written to the workspace exactly once per pass, when the window leaves it.
 template <int K, bool HAS_W>
-__device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, const double *xp,
-                                           const double *yp, const double *wp, size_t x_si,
-                                           size_t y_si, size_t w_si, int m, int nk1, bool on)
+__device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, double *rs,
+                                           const double *xp, const double *yp, const double *wp,
+                                           size_t x_si, size_t y_si, size_t w_si, int m, int nk1,
+                                           bool on)
 {
-    constexpr int K1 = K + 1;
-    double R[K1][K1], Zw[K1], tw[2 * K], h[K1];
+    constexpr int K1 = K + 1, NT = kFitThreads;
+#define RS_(slot, q) rs[((slot) * K1 + (q)) * NT]
+#define ZS_(slot) rs[(K1 * K1 + (slot)) * NT]
+    double tw[2 * K], h[K1];
 #pragma unroll
     for (int r = 0; r < K1; ++r) {
-        Zw[r] = 0.0;
+        ZS_(r) = 0.0;
 #pragma unroll
-        for (int q = 0; q < K1; ++q) R[r][q] = 0.0;
+        for (int q = 0; q < K1; ++q) RS_(r, q) = 0.0;
     }
-    int l = K1;
+    int l = K1, s0 = 0;  // s0: window slot holding band row l-K1+1
     if (on) {
 #pragma unroll
         for (int j = 0; j < 2 * K; ++j) tw[j] = T_(l - K + 1 + j);
@@ -195,8 +203,7 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, cons
         for (int j = 0; j < 2 * K; ++j) tw[j] = 0.0;
     }
     double fp = 0.0;
-    // the next point's data is requested one iteration ahead (a pass is ~600 FP64
-    // instructions per point: one point of lookahead covers the HBM latency)
+    // the next point's data is requested one iteration ahead
     double xn = xp[0], yn = yp[0], wn = HAS_W ? wp[0] : 1.0;
     for (int it = 0; it < m; ++it) {
         const double xi = xn;
@@ -212,20 +219,17 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, cons
         if (on) {
             // fp_knot_interval (core:2432-2473) == linear walk from the previous interval
             while (l < nk1 && xi >= tw[K]) {
-                // window leaves row l-K1+1 (1-based): it is final for this pass
+                // window leaves row l-K1+1 (1-based): it is final for this pass; its slot is
+                // recycled (zeroed) for the row that enters at the other end
                 const int row = l - K1 + 1;
 #pragma unroll
-                for (int q = 0; q < K1; ++q) A_(row, q + 1) = R[0][q];
-                Z_(row) = Zw[0];
-#pragma unroll
-                for (int r = 0; r < K; ++r) {
-                    Zw[r] = Zw[r + 1];
-#pragma unroll
-                    for (int q = 0; q < K1; ++q) R[r][q] = R[r + 1][q];
+                for (int q = 0; q < K1; ++q) {
+                    A_(row, q + 1) = RS_(s0, q);
+                    RS_(s0, q) = 0.0;
                 }
-                Zw[K] = 0.0;
-#pragma unroll
-                for (int q = 0; q < K1; ++q) R[K][q] = 0.0;
+                Z_(row) = ZS_(s0);
+                ZS_(s0) = 0.0;
+                s0 = (s0 + 1 == K1) ? 0 : s0 + 1;
 #pragma unroll
                 for (int j = 0; j < 2 * K - 1; ++j) tw[j] = tw[j + 1];
                 ++l;
@@ -237,17 +241,25 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, cons
                 Q_(it, j) = h[j];
                 if (HAS_W) h[j] = mul(wi, h[j]);
             }
-            // fp_rotate_row (core:5691-5717): window row i <-> R row l-K1+1+i
+            // fp_rotate_row (core:5691-5717): pivot i <-> band row l-K1+1+i
+            int sl = s0;
 #pragma unroll
             for (int i = 0; i < K1; ++i) {
                 const double piv = h[i];
                 if (!fp_is_zero(piv)) {
-                    double cs, sn;
-                    givens(piv, R[i][0], cs, sn);
-                    rota(cs, sn, yi, Zw[i]);
+                    double cs, sn, d = RS_(sl, 0), z = ZS_(sl);
+                    givens(piv, d, cs, sn);
+                    RS_(sl, 0) = d;
+                    rota(cs, sn, yi, z);
+                    ZS_(sl) = z;
 #pragma unroll
-                    for (int q = 1; q <= K - i; ++q) rota(cs, sn, h[i + q], R[i][q]);
+                    for (int q = 1; q <= K - i; ++q) {
+                        double r = RS_(sl, q);
+                        rota(cs, sn, h[i + q], r);
+                        RS_(sl, q) = r;
+                    }
                 }
+                sl = (sl + 1 == K1) ? 0 : sl + 1;
             }
             fp = add(fp, mul(yi, yi));
         }
@@ -257,27 +269,27 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, cons
         while (l < nk1) {
             const int row = l - K1 + 1;
 #pragma unroll
-            for (int q = 0; q < K1; ++q) A_(row, q + 1) = R[0][q];
-            Z_(row) = Zw[0];
-#pragma unroll
-            for (int r = 0; r < K; ++r) {
-                Zw[r] = Zw[r + 1];
-#pragma unroll
-                for (int q = 0; q < K1; ++q) R[r][q] = R[r + 1][q];
+            for (int q = 0; q < K1; ++q) {
+                A_(row, q + 1) = RS_(s0, q);
+                RS_(s0, q) = 0.0;
             }
-            Zw[K] = 0.0;
-#pragma unroll
-            for (int q = 0; q < K1; ++q) R[K][q] = 0.0;
+            Z_(row) = ZS_(s0);
+            ZS_(s0) = 0.0;
+            s0 = (s0 + 1 == K1) ? 0 : s0 + 1;
             ++l;
         }
+        int sl = s0;
 #pragma unroll
         for (int r = 0; r < K1; ++r) {
             const int row = l - K1 + 1 + r;
 #pragma unroll
-            for (int q = 0; q < K1; ++q) A_(row, q + 1) = R[r][q];
-            Z_(row) = Zw[r];
+            for (int q = 0; q < K1; ++q) A_(row, q + 1) = RS_(sl, q);
+            Z_(row) = ZS_(sl);
+            sl = (sl + 1 == K1) ? 0 : sl + 1;
         }
     }
+#undef RS_
+#undef ZS_
     return fp;
 }
 
@@ -336,7 +348,7 @@ __device__ __forceinline__ void list_append(int *list, int *count, bool cond, in
 // ---------------------------------------------------------------------------------------
 template <int K, bool HAS_W>
 __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
-                         double *__restrict__ wsd, int *__restrict__ wsi)
+                         double *__restrict__ wsd, int *__restrict__ wsi, double *rs)
 {
     constexpr int K1 = K + 1, K2 = K + 2;
     const int m = p.m, nest = p.nest, iopt = p.iopt;
@@ -483,7 +495,7 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             for (int i = nk1 + 1; i <= n; ++i) T_(i) = xe;
             ran_pass = true;
         }
-        const double fp_pass = lsq_pass<K, HAS_W>(p, wsd, xp, yp, wp, (size_t)p.x_si, (size_t)p.y_si,
+        const double fp_pass = lsq_pass<K, HAS_W>(p, wsd, rs, xp, yp, wp, (size_t)p.x_si, (size_t)p.y_si,
                                                   (size_t)p.w_si, m, nk1, on);
         if (on) {
             fp = fp_pass;
@@ -654,7 +666,7 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
 // ---------------------------------------------------------------------------------------
 template <int K, bool HAS_W>
 __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__restrict__ wsd,
-                           int *__restrict__ wsi)
+                           int *__restrict__ wsi, double *rs)
 {
     constexpr int K1 = K + 1, K2 = K + 2;
     (void)wsi;
@@ -682,7 +694,7 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
     // the warp's interleaved workspace; the LSQ pass and every f(p) evaluation then stream it
     // with fully coalesced loads.
     {
-        constexpr int U = 8;
+        constexpr int U = 4;
         for (int it0 = 0; it0 < m; it0 += U) {
             double xv[U], yv[U], wv[U];
 #pragma unroll
@@ -704,7 +716,7 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
     }
     const double *xg = &WS(p.off_x, 0), *yg = &WS(p.off_y, 0);
     const double *wg = HAS_W ? &WS(p.off_w, 0) : nullptr;
-    double fp = lsq_pass<K, HAS_W>(p, wsd, xg, yg, wg, 32, 32, 32, m, nk1, on2);
+    double fp = lsq_pass<K, HAS_W>(p, wsd, rs, xg, yg, wg, 32, 32, 32, m, nk1, on2);
     double fpms = sub(fp, s);
     // fpdisc, core:5453-5495
     {
@@ -884,10 +896,12 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
 
 // persistent warps; tiles of 32 list entries are handed out through an atomic counter
 template <int K, bool HAS_W>
-__global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2)
+__global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K))
     curfit_pass_kernel(FitParams p, const int *__restrict__ in_list, const int *in_count,
                        int *out_list, int *out_count, int *p2_list, int *p2_count, int first)
 {
+    extern __shared__ double fit_smem[];
+    double *rs = fit_smem + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double *wsd = p.ws + (size_t)warp_slot * p.ws_per_lane * 32 + lane;
@@ -902,7 +916,7 @@ __global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2)
         const bool valid = base + lane < count;
         int b = 0;
         if (valid) b = first ? (int)(base + lane) : in_list[base + lane];
-        const int st = pass_tile<K, HAS_W>(p, b, valid, first != 0, wsd, wsi);
+        const int st = pass_tile<K, HAS_W>(p, b, valid, first != 0, wsd, wsi, rs);
         __syncwarp();
         list_append(out_list, out_count, valid && st == ST_LOOP, b, lane);
         const bool to2 = valid && st == ST_PART2;
@@ -912,9 +926,11 @@ __global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2)
 }
 
 template <int K, bool HAS_W>
-__global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2)
+__global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K))
     curfit_part2_kernel(FitParams p, const int *__restrict__ list, const int *count_ptr)
 {
+    extern __shared__ double fit_smem[];
+    double *rs = fit_smem + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double *wsd = p.ws + (size_t)warp_slot * p.ws_per_lane * 32 + lane;
@@ -928,7 +944,7 @@ __global__ void __launch_bounds__(kFitThreads, (K <= 3) ? 4 : 2)
         if (base >= count) break;
         const bool valid = base + lane < count;
         const int b = valid ? list[base + lane] : 0;
-        part2_tile<K, HAS_W>(p, b, valid, wsd, wsi);
+        part2_tile<K, HAS_W>(p, b, valid, wsd, wsi, rs);
         __syncwarp();
     }
 }
@@ -963,18 +979,18 @@ void launch_pass_k(const FitParams &p, int grid, cudaStream_t st, const int *in_
                    int first)
 {
     if (p.w)
-        curfit_pass_kernel<K, true><<<grid, kFitThreads, 0, st>>>(p, in_list, in_count, out_list,
+        curfit_pass_kernel<K, true><<<grid, kFitThreads, fit_smem_bytes(K), st>>>(p, in_list, in_count, out_list,
                                                                    out_count, p2_list, p2_count, first);
     else
-        curfit_pass_kernel<K, false><<<grid, kFitThreads, 0, st>>>(p, in_list, in_count, out_list,
+        curfit_pass_kernel<K, false><<<grid, kFitThreads, fit_smem_bytes(K), st>>>(p, in_list, in_count, out_list,
                                                                     out_count, p2_list, p2_count, first);
 }
 
 template <int K>
 void launch_part2_k(const FitParams &p, int grid, cudaStream_t st, const int *list, const int *count)
 {
-    if (p.w) curfit_part2_kernel<K, true><<<grid, kFitThreads, 0, st>>>(p, list, count);
-    else curfit_part2_kernel<K, false><<<grid, kFitThreads, 0, st>>>(p, list, count);
+    if (p.w) curfit_part2_kernel<K, true><<<grid, kFitThreads, fit_smem_bytes(K), st>>>(p, list, count);
+    else curfit_part2_kernel<K, false><<<grid, kFitThreads, fit_smem_bytes(K), st>>>(p, list, count);
 }
 
 }  // namespace
@@ -1004,9 +1020,7 @@ FitLayout fit_layout(int m, int k, int nest)
 
 int fit_max_resident_warps(int k, int nsm)
 {
-    // matches __launch_bounds__ above: K<=3 -> 4 blocks of kFitThreads per SM, else 2
-    const int blocks_per_sm = (k <= 3) ? 4 : 2;
-    return nsm * blocks_per_sm * (kFitThreads / 32);
+    return nsm * fit_blocks_per_sm(k) * (kFitThreads / 32);
 }
 
 cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t stream,

@@ -470,7 +470,7 @@ double fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused)
     if (!eng) return -1.0;
     DeviceGuard g(eng->device);
     if (!g.ok || !eng->counter.reserve(256)) return -1.0;
-    const int blocks = eng->nsm * 8, iters = 1 << 14;
+    const int blocks = eng->nsm * 8, iters = (fused >= 2) ? (1 << 11) : (1 << 14);
     double best = -1.0;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(eng->ev0, eng->stream);
@@ -484,7 +484,9 @@ double fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused)
             cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) != cudaSuccess)
             return -1.0;
         // one FMA counts as one instruction here; mul+add as two
-        const double ops = (double)blocks * 256.0 * iters * 8.0 * (fused ? 1.0 : 2.0);
+        // one FMA counts as one instruction; mul+add as two; modes 2/3: one div / sqrt per op
+        const double ops = (fused >= 2) ? (double)blocks * 256.0 * iters * 4.0
+                                        : (double)blocks * 256.0 * iters * 8.0 * (fused ? 1.0 : 2.0);
         best = std::max(best, ops / (ms * 1e-3) * 1e-9);
     }
     eng->timed = false;

@@ -7,6 +7,13 @@
 namespace fpb {
 
 constexpr int kFitThreads = 128;  // threads per CTA of the fit kernel (4 warps = 128 curves)
+// CTAs per SM the fit kernels are compiled for (register budget 65536/(128*blocks))
+#ifndef FPB_FIT_BLOCKS_K3
+#define FPB_FIT_BLOCKS_K3 5
+#endif
+constexpr int fit_blocks_per_sm(int k) { return k <= 3 ? FPB_FIT_BLOCKS_K3 : (k == 4 ? 4 : 3); }
+// shared-memory band window: (k+1)^2 + (k+1) doubles per thread
+constexpr unsigned fit_smem_bytes(int k) { return (unsigned)(((k + 1) * (k + 1) + (k + 1)) * kFitThreads * sizeof(double)); }
 
 // per-lane workspace layout of the fit kernel, in elements of 8 bytes
 struct FitLayout {

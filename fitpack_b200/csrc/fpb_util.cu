@@ -92,8 +92,36 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters,
 }
 }  // namespace
 
+// mode 2: IEEE division, mode 3: IEEE sqrt (4 independent chains per thread)
+template <int MODE>
+__global__ void __launch_bounds__(256) fp64_divsqrt_probe_kernel(double *out, int iters, double a)
+{
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = 1.5 + 1e-3 * (threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (MODE == 2) v[j] = a / v[j];
+            else v[j] = sqrt(v[j]) + a;
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += v[j];
+    if (s == 123.456) out[0] = s;
+}
+
 cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused, cudaStream_t stream)
 {
+    if (fused == 2) {
+        fp64_divsqrt_probe_kernel<2><<<blocks, 256, 0, stream>>>(scratch, iters, 1.75);
+        return cudaGetLastError();
+    }
+    if (fused == 3) {
+        fp64_divsqrt_probe_kernel<3><<<blocks, 256, 0, stream>>>(scratch, iters, 0.75);
+        return cudaGetLastError();
+    }
     if (fused) fp64_probe_kernel<true><<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999, 1e-7);
     else fp64_probe_kernel<false><<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999, 1e-7);
     return cudaGetLastError();
