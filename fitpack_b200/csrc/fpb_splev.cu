@@ -75,16 +75,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t phase)
 __host__ __device__ inline int splev_grid_cells(int nint)
 {
     int g = 32;
-    while (g < 2 * nint && g < 1024) g <<= 1;
+    while (g < 4 * nint && g < 1024) g <<= 1;
     return g;
 }
 
-// per-warp shared memory in doubles: [t: ld][c: ld] (+ fast mode [dlev: K*ld][poly: K1*ld])
+// per-warp shared memory in doubles: [t: ld][c: ld] (+ fast mode [dlev: K*ld][rec: 8*ld])
 // followed by the lookup grid (ints, counted here in doubles)
 __host__ __device__ inline int splev_smem_doubles(int mode, int k, int ld)
 {
     const int grid = splev_grid_cells(ld - 2 * k - 1) / 2;
-    return ((mode == 1) ? ld * (2 + k + (k + 1)) : ld * 2) + grid;
+    return ((mode == 1) ? ld * (2 + k + 8) : ld * 2) + 2 * 256 /* x tiles */ + grid;
 }
 
 // 1/d to ~1 ulp without the IEEE division sequence (FAST mode only): hardware seed + two
@@ -122,7 +122,7 @@ __device__ __forceinline__ int locate(const double *ts, const int *grid, int gce
 {
     int g = __double2int_rz((arg - tb) * inv_h);
     g = max(0, min(g, gcells - 1));
-    int l = grid[g];
+    int l = grid[g] & 0x3fffffff;
     while (l > k1 && arg < ts[l - 1]) --l;
     while (l < nk1 && arg >= ts[l]) ++l;
     return l;
@@ -141,15 +141,16 @@ __device__ __forceinline__ double eval_exact(const double *ts, const double *cs,
     return sp;
 }
 
-// Build the per-interval Taylor coefficients of spline (ts,cs):
-//   s(x) = sum_r poly[(l-k1)*(K+1)+r] * (x - t(l))^r   on knot interval l.
+// Build one 64-byte record per knot interval l of spline (ts,cs):
+//   rec[(l-k1)*8 + 0..1] = t(l), t(l+1);  rec[(l-k1)*8 + 2 + r] = a_r  with
+//   s(x) = sum_r a_r * (x - t(l))^r   on interval l   (unused slots are zero).
 // dlev[r*ld + i] (r = 1..K) receives the derivative pyramid
 //   d^r_i = (K-r+1)/r * (d^{r-1}_i - d^{r-1}_{i-1}) / (t_{i+K-r+1} - t_i),   d^0 = c,
 // i.e. the B-spline coefficients (degree K-r) of s^(r)/r!.  One de Boor-Cox recurrence
 // per interval at x = t(l) then yields the basis of every degree 0..K on the way up.
 template <int K>
 __device__ void build_local_polys(const double *ts, const double *cs, int n, int ld, double *dlev,
-                                  double *poly, int lane)
+                                  double *rec, int lane)
 {
     constexpr int K1 = K + 1;
     const int nk1 = n - K1;
@@ -173,7 +174,12 @@ __device__ void build_local_polys(const double *ts, const double *cs, int n, int
         const double x = ts[l - 1];  // t(l)
         double h[K1];
         h[0] = 1.0;
-        poly[li * K1 + K] = (K >= 1) ? dlev[(size_t)(K - 1) * ld + (l - 1)] : cs[l - 1];
+        double *rl = rec + (size_t)li * 8;
+        rl[0] = x;
+        rl[1] = ts[l];
+#pragma unroll
+        for (int r = K + 1; r < 6; ++r) rl[2 + r] = 0.0;
+        rl[2 + K] = (K >= 1) ? dlev[(size_t)(K - 1) * ld + (l - 1)] : cs[l - 1];
 #pragma unroll
         for (int j = 1; j <= K; ++j) {
             double hh[K];
@@ -197,17 +203,105 @@ __device__ void build_local_polys(const double *ts, const double *cs, int n, int
             double acc = 0.0;
 #pragma unroll
             for (int q = 0; q <= j; ++q) acc = fma(lev[l - j - 1 + q], h[q], acc);
-            poly[li * K1 + r] = acc;
+            rl[2 + r] = acc;
         }
     }
     __syncwarp();
 }
 
-constexpr int kUnroll = 4;  // independent points per lane per iteration (memory-level parallelism)
+constexpr int kUnroll = 4;   // independent points per lane per group (instruction-level parallelism)
+constexpr int kXTile = 256;  // evaluation points per TMA tile (2 KB), double buffered per warp
+
+// Evaluate one group of kUnroll points per lane (indices ibase + 32*u) and store the results.
+template <int K, int MODE, bool PLAIN>
+__device__ __forceinline__ void eval_group(const SplevParams &p, const double *ts, const double *cs,
+                                           const double *rec, const int *grid, int gcells, double tb,
+                                           double te, double inv_h, int nk1, double (&arg)[kUnroll],
+                                           const bool (&live)[kUnroll], double *yg, int *lg,
+                                           int ibase, bool &out_of_range)
+{
+    constexpr int K1 = K + 1;
+    bool zero[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) zero[u] = false;
+    if (!PLAIN) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (arg[u] < tb || arg[u] > te) {  // core:17864-17877
+                if (p.e == 1) zero[u] = true;
+                else if (p.e == 2) out_of_range = out_of_range || live[u];
+                else if (p.e == 3) arg[u] = fmax(fmin(arg[u], te), tb);
+            }
+        }
+    }
+    int l[kUnroll];
+    double sp[kUnroll];
+    if (MODE == 1) {
+        // FAST: one 64-byte record per interval {t(l), t(l+1), a0..a5}; the lookup grid lands in
+        // the interval of the cell's left edge, a predicated single step covers one knot inside
+        // the cell, the reference's own walk handles flagged cells (several knots) and edge rounding
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            int g = __double2int_rz((arg[u] - tb) * inv_h);
+            g = max(0, min(g, gcells - 1));
+            l[u] = grid[g];
+        }
+        double tl[kUnroll];
+        bool slow = false;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const bool cplx = (l[u] >> 30) != 0;
+            const int l0 = l[u] & 0x3fffffff;
+            const double2 tt = reinterpret_cast<const double2 *>(rec + (size_t)(l0 - K1) * 8)[0];
+            const bool step = (arg[u] >= tt.y) && (l0 < nk1);
+            l[u] = l0 + (step ? 1 : 0);
+            tl[u] = step ? tt.y : tt.x;
+            slow = slow || cplx || (arg[u] < tt.x && l0 > K1);
+        }
+        if (__any_sync(FULL, slow)) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                int ll = l[u];
+                while (ll > K1 && arg[u] < ts[ll - 1]) --ll;
+                while (ll < nk1 && arg[u] >= ts[ll]) ++ll;
+                l[u] = ll;
+                tl[u] = ts[ll - 1];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const double uu = arg[u] - tl[u];
+            const double2 *rp = reinterpret_cast<const double2 *>(rec + (size_t)(l[u] - K1) * 8);
+            const double2 a01 = rp[1], a23 = rp[2], a45 = rp[3];
+            const double a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+            double v = a[K];
+#pragma unroll
+            for (int r = K - 1; r >= 0; --r) v = fma(v, uu, a[r]);
+            sp[u] = v;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) l[u] = locate(ts, grid, gcells, tb, inv_h, K1, nk1, arg[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) sp[u] = eval_exact<K>(ts, cs, l[u], arg[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const int i = ibase + 32 * u;
+        if (live[u]) {
+            if (PLAIN) {
+                yg[i] = sp[u];
+            } else {
+                yg[i] = zero[u] ? 0.0 : sp[u];
+                if (lg) lg[i] = zero[u] ? 0 : l[u];
+            }
+        }
+    }
+}
 
 // PLAIN: e == OUTSIDE_EXTRAPOLATE and no interval-index output -- no per-point policy code.
 template <int K, int MODE, bool PLAIN>
-__global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
+__global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
     splev_kernel(SplevParams p, int smem_ld)
 {
     constexpr int K1 = K + 1;
@@ -216,17 +310,21 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
     const int wpb = blockDim.x >> 5;
     const int per_warp = splev_smem_doubles(MODE, K, smem_ld);
     uint64_t *mbars = reinterpret_cast<uint64_t *>(smem_raw);
-    double *base = reinterpret_cast<double *>(smem_raw + 16 * kSplevWarps) + (size_t)warp * per_warp;
+    double *base = reinterpret_cast<double *>(smem_raw + 32 * kSplevWarps) + (size_t)warp * per_warp;
     double *ts = base, *cs = base + smem_ld, *dlev = base + 2 * smem_ld,
-           *poly = base + (size_t)(2 + K) * smem_ld;
-    int *grid = reinterpret_cast<int *>(base + ((MODE == 1) ? smem_ld * (2 + K + K1) : smem_ld * 2));
-    uint64_t *mbar = mbars + warp * 2;
+           *rec = base + (size_t)(2 + K) * smem_ld;
+    double *after = base + ((MODE == 1) ? smem_ld * (2 + K + 8) : smem_ld * 2);
+    double *xs = after;                                         // [2][kXTile] evaluation points
+    int *grid = reinterpret_cast<int *>(after + 2 * kXTile);   // lookup grid
+    uint64_t *mbar = mbars + warp * 4;                          // [0] tables, [1..2] x tiles
     if (lane == 0) {
         mbar_init(mbar, 1);
+        mbar_init(mbar + 1, 1);
+        mbar_init(mbar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncwarp();
-    uint32_t phase = 0;
+    uint32_t phase = 0, xphase0 = 0, xphase1 = 0;
 
     const long long gwarp = (long long)blockIdx.x * wpb + warp;
     const long long nwarps = (long long)gridDim.x * wpb;
@@ -235,6 +333,24 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
     double inv_h = 0.0;
     for (long long j = gwarp; j < p.nspl; j += nwarps) {
         const long long tj = p.nshared ? 0 : j;
+        const double *xg = p.x + j * p.m;
+        // TMA tiles need 16-byte aligned rows of even length; otherwise plain loads
+        // (EXACT mode is FP64-bound, not latency-bound: it keeps the register-pipelined loads)
+        const bool xt_ok = (MODE == 1) && ((((uintptr_t)xg) & 15) == 0) && ((p.m & 1) == 0);
+        const int ntile = (p.m + kXTile - 1) / kXTile;
+        auto issue_tile = [&](int t) {
+            if (lane == 0) {
+                const int cnt = min(kXTile, p.m - t * kXTile);
+                uint64_t *mb = mbar + 1 + (t & 1);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                mbar_expect_tx(mb, (uint32_t)cnt * 8u);
+                tma_load_1d(xs + (t & 1) * kXTile, xg + (size_t)t * kXTile, (uint32_t)cnt * 8u, mb);
+            }
+        };
+        if (xt_ok) {  // the points start streaming in while the spline's tables are built
+            issue_tile(0);
+            if (ntile > 1) issue_tile(1);
+        }
         if (tj != cached) {
             n = p.n[tj];
             const double *tg = p.t + tj * p.ldt, *cg = p.c + tj * p.ldt;
@@ -258,7 +374,10 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
                 }
             }
             __syncwarp();
-            // lookup grid over [t(k+1), t(n-k)]: grid[g] = interval of the cell's left edge
+            // lookup grid over [t(k+1), t(n-k)]: grid[g] = interval of the cell's left edge;
+            // bit 30 flags a cell that may hold two or more knots (the single predicated step of
+            // the evaluation loop cannot resolve it: the full walk is taken).  Edges are widened
+            // by 1e-6 of a cell so that rounding in the cell index can never un-flag a cell.
             {
                 const int nk1_ = n - K1;
                 const int nint = nk1_ - K1 + 1;
@@ -267,67 +386,82 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 4 : 2)
                 const double span = te_ - tb_;
                 inv_h = (span > 0.0) ? (double)gcells / span : 0.0;
                 const double hcell = span / (double)gcells;
-                int top = 1;
-                while (top * 2 <= nk1_ - K1) top *= 2;
-                if (nk1_ - K1 < 1) top = 0;
-                for (int gI = lane; gI < gcells; gI += 32)
-                    grid[gI] = find_interval(ts, K1, nk1_, top, tb_ + (double)gI * hcell);
+                // Each lane owns knot intervals l = k1+lane, k1+lane+32, ... and fills the cells whose
+                // (widened) left edge falls into [t(l), t(l+1)): cell boundaries come from one
+                // monotone function of the knot, so the ranges of neighbouring lanes tile the grid.
+                auto bnd = [&](int l) -> int {  // first cell whose left edge is >= t(l)
+                    if (l <= K1) return 0;
+                    if (l > nk1_) return gcells;
+                    const double v = (ts[l - 1] - tb_) * inv_h + 1e-6;
+                    int c = __double2int_ru(v);
+                    return max(0, min(c, gcells));
+                };
+                for (int li = lane; li < nint; li += 32) {
+                    const int l = K1 + li;
+                    const int g0 = bnd(l), g1 = bnd(l + 1);
+                    const double t2 = (l + 2 <= nk1_) ? ts[l + 1] : 1.79e308;  // t(l+2), if stepping twice is possible
+                    for (int gI = g0; gI < g1; ++gI) {
+                        const double right = tb_ + ((double)(gI + 1) + 1e-6) * hcell;
+                        grid[gI] = l | ((right >= t2) ? (1 << 30) : 0);
+                    }
+                }
             }
-            if (MODE == 1) build_local_polys<K>(ts, cs, n, smem_ld, dlev, poly, lane);
+            if (MODE == 1) build_local_polys<K>(ts, cs, n, smem_ld, dlev, rec, lane);
             __syncwarp();
             cached = (int)tj;
         }
         const int nk1 = n - K1;
         const double tb = ts[K1 - 1], te = ts[nk1];
-        const double *xg = p.x + j * p.m;
         double *yg = p.y + j * p.m;
         int *lg = p.lidx ? p.lidx + j * p.m : nullptr;
         bool out_of_range = false;
-        for (int i0 = lane; i0 < p.m; i0 += 32 * kUnroll) {
-            double arg[kUnroll];
-            bool live[kUnroll], zero[kUnroll];
+        if (xt_ok) {
+            for (int t = 0; t < ntile; ++t) {
+                const int buf = t & 1;
+                if (buf == 0) { mbar_wait(mbar + 1, xphase0); xphase0 ^= 1; }
+                else { mbar_wait(mbar + 2, xphase1); xphase1 ^= 1; }
+                const int cnt = min(kXTile, p.m - t * kXTile);
+                const double *xt = xs + buf * kXTile;
+#pragma unroll
+                for (int gq = 0; gq < kXTile / (32 * kUnroll); ++gq) {
+                    const int il = gq * 32 * kUnroll + lane;
+                    if (il - lane < cnt) {  // uniform across the warp
+                        double arg[kUnroll];
+                        bool live[kUnroll];
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u) {
+                            live[u] = il + 32 * u < cnt;
+                            arg[u] = live[u] ? xt[il + 32 * u] : tb;
+                        }
+                        eval_group<K, MODE, PLAIN>(p, ts, cs, rec, grid, gcells, tb, te, inv_h, nk1,
+                                                   arg, live, yg, lg, t * kXTile + il, out_of_range);
+                    }
+                }
+                __syncwarp();  // every lane is done with this buffer
+                if (t + 2 < ntile) issue_tile(t + 2);
+            }
+        } else {
+            // software pipeline in registers: the loads of the next group are in flight while
+            // the current group is evaluated
+            double nxt[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int i = i0 + 32 * u;
-                live[u] = i < p.m;
-                arg[u] = live[u] ? xg[i] : tb;
-                zero[u] = false;
+                const int i = lane + 32 * u;
+                nxt[u] = (i < p.m) ? xg[i] : tb;
             }
-            if (!PLAIN) {
+            for (int i0 = lane; i0 < p.m; i0 += 32 * kUnroll) {
+                double arg[kUnroll];
+                bool live[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    if (arg[u] < tb || arg[u] > te) {  // core:17864-17877
-                        if (p.e == 1) zero[u] = true;
-                        else if (p.e == 2) out_of_range = out_of_range || live[u];
-                        else if (p.e == 3) arg[u] = fmax(fmin(arg[u], te), tb);
-                    }
+                    const int i = i0 + 32 * u;
+                    live[u] = i < p.m;
+                    arg[u] = nxt[u];
+                    const int inx = i + 32 * kUnroll;
+                    nxt[u] = (inx < p.m) ? xg[inx] : tb;
                 }
-            }
-            int l[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-                l[u] = locate(ts, grid, gcells, tb, inv_h, K1, nk1, arg[u]);
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                double sp;
-                if (MODE == 1) {
-                    const double *pl = poly + (l[u] - K1) * K1;
-                    const double uu = arg[u] - ts[l[u] - 1];
-                    sp = pl[K];
-#pragma unroll
-                    for (int r = K - 1; r >= 0; --r) sp = fma(sp, uu, pl[r]);
-                } else {
-                    sp = eval_exact<K>(ts, cs, l[u], arg[u]);
-                }
-                const int i = i0 + 32 * u;
-                if (live[u]) {
-                    if (PLAIN) {
-                        yg[i] = sp;
-                    } else {
-                        yg[i] = zero[u] ? 0.0 : sp;
-                        if (lg) lg[i] = zero[u] ? 0 : l[u];
-                    }
-                }
+                eval_group<K, MODE, PLAIN>(p, ts, cs, rec, grid, gcells, tb, te, inv_h, nk1, arg,
+                                           live, yg, lg, i0, out_of_range);
             }
         }
         if (p.ier) {
@@ -345,8 +479,8 @@ cudaError_t launch_splev(const SplevParams &p, int nsm, cudaStream_t stream)
     const int smem_ld = (p.ldt + 1) & ~1;  // keep every per-warp region 16 B aligned
     const size_t per_warp = (size_t)splev_smem_doubles(p.mode, p.k, smem_ld) * sizeof(double);
     int wpb = kSplevWarps;
-    while (wpb > 1 && 16 * kSplevWarps + per_warp * wpb > 100 * 1024) wpb >>= 1;
-    const size_t smem = 16 * kSplevWarps + per_warp * wpb;
+    while (wpb > 1 && 32 * kSplevWarps + per_warp * wpb > 100 * 1024) wpb >>= 1;
+    const size_t smem = 32 * kSplevWarps + per_warp * wpb;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;  // knot vectors beyond ~4000 entries
     long long blocks = ((long long)p.nspl + wpb - 1) / wpb;
     const long long resident = (long long)(220 * 1024 / smem);
