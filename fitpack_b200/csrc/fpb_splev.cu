@@ -79,12 +79,14 @@ __host__ __device__ inline int splev_grid_cells(int nint)
     return g;
 }
 
-// per-warp shared memory in doubles: [t: ld][c: ld] (+ fast mode [dlev: K*ld][rec: 8*ld])
+// per-warp shared memory in doubles: two (t, c) buffers [2][2][ld] (the next spline's tables are
+// prefetched while the current one is evaluated), + fast mode [dlev: K*ld][rc: K*ld]
+// [rec: 8*(ld-2K-1)]
 // followed by the lookup grid (ints, counted here in doubles)
 __host__ __device__ inline int splev_smem_doubles(int mode, int k, int ld)
 {
-    const int grid = splev_grid_cells(ld - 2 * k - 1) / 2;
-    return ((mode == 1) ? ld * (2 + k + 8) : ld * 2) + 2 * 256 /* x tiles */ + grid;
+    const int grid = (splev_grid_cells(ld - 2 * k - 1) + 3) / 4;  // uint16 entries
+    return ((mode == 1) ? ld * (4 + k + 8 + k) - 8 * (2 * k + 1) : ld * 4) + 2 * 256 /* x tiles */ + grid;
 }
 
 // 1/d to ~1 ulp without the IEEE division sequence (FAST mode only): hardware seed + two
@@ -117,12 +119,12 @@ __device__ __forceinline__ int find_interval(const double *ts, int k1, int nk1, 
 
 // Interval of `arg` from the lookup grid + the reference's own bidirectional walk
 // (core:17880-17887), which makes the result independent of the quality of the guess.
-__device__ __forceinline__ int locate(const double *ts, const int *grid, int gcells, double tb,
+__device__ __forceinline__ int locate(const double *ts, const unsigned short *grid, int gcells, double tb,
                                       double inv_h, int k1, int nk1, double arg)
 {
     int g = __double2int_rz((arg - tb) * inv_h);
     g = max(0, min(g, gcells - 1));
-    int l = grid[g] & 0x3fffffff;
+    int l = grid[g] & 0x7fff;
     while (l > k1 && arg < ts[l - 1]) --l;
     while (l < nk1 && arg >= ts[l]) ++l;
     return l;
@@ -150,21 +152,30 @@ __device__ __forceinline__ double eval_exact(const double *ts, const double *cs,
 // per interval at x = t(l) then yields the basis of every degree 0..K on the way up.
 template <int K>
 __device__ void build_local_polys(const double *ts, const double *cs, int n, int ld, double *dlev,
-                                  double *rec, int lane)
+                                  double *rec, double *rc, int lane)
 {
     constexpr int K1 = K + 1;
     const int nk1 = n - K1;
     const int nint = nk1 - K1 + 1;
+    // reciprocal knot spans rc[(j-1)*ld + a] = 1 / (t[a+j] - t[a]) (0-based a), j = 1..K; every
+    // denominator of the derivative pyramid and of the basis recurrences is one of them.
+    // Coincident knots give 0, which reproduces fpbspl's "skip the term" branch.
+#pragma unroll
+    for (int j = 1; j <= K; ++j) {
+        for (int a = lane; a + j < n; a += 32) {
+            const double den = ts[a + j] - ts[a];
+            rc[(size_t)(j - 1) * ld + a] = (fabs(den) >= DBL_MIN) ? fast_rcp(den) : 0.0;
+        }
+    }
+    __syncwarp();
     for (int r = 1; r <= K; ++r) {
         const double *prev = (r == 1) ? cs : dlev + (size_t)(r - 2) * ld;
         double *cur = dlev + (size_t)(r - 1) * ld;
         const double scale = (double)(K - r + 1) / (double)r;
+        const double *rcj = rc + (size_t)(K - r) * ld;  // span K-r+1
         for (int i0 = lane; i0 < nk1; i0 += 32) {
             double v = 0.0;
-            if (i0 >= r) {
-                const double den = ts[i0 + K - r + 1] - ts[i0];
-                if (fabs(den) >= DBL_MIN) v = scale * (prev[i0] - prev[i0 - 1]) * fast_rcp(den);
-            }
+            if (i0 >= r) v = scale * (prev[i0] - prev[i0 - 1]) * rcj[i0];
             cur[i0] = v;
         }
         __syncwarp();
@@ -186,17 +197,13 @@ __device__ void build_local_polys(const double *ts, const double *cs, int n, int
 #pragma unroll
             for (int i = 0; i < j; ++i) hh[i] = h[i];
             h[0] = 0.0;
+            const double *rcj = rc + (size_t)(j - 1) * ld;
 #pragma unroll
             for (int i = 1; i <= j; ++i) {
                 const double tli = ts[l + i - 1], tlj = ts[l + i - j - 1];
-                const double d = tli - tlj;
-                if (fabs(d) >= DBL_MIN) {
-                    const double f = hh[i - 1] * fast_rcp(d);
-                    h[i - 1] = fma(f, tli - x, h[i - 1]);
-                    h[i] = f * (x - tlj);
-                } else {
-                    h[i] = 0.0;
-                }
+                const double f = hh[i - 1] * rcj[l + i - j - 1];
+                h[i - 1] = fma(f, tli - x, h[i - 1]);
+                h[i] = f * (x - tlj);
             }
             const int r = K - j;  // basis of degree j pairs with derivative level K-j
             const double *lev = (r == 0) ? cs : dlev + (size_t)(r - 1) * ld;
@@ -213,9 +220,9 @@ constexpr int kUnroll = 4;   // independent points per lane per group (instructi
 constexpr int kXTile = 256;  // evaluation points per TMA tile (2 KB), double buffered per warp
 
 // Evaluate one group of kUnroll points per lane (indices ibase + 32*u) and store the results.
-template <int K, int MODE, bool PLAIN>
+template <int K, int MODE, bool PLAIN, bool ALLLIVE>
 __device__ __forceinline__ void eval_group(const SplevParams &p, const double *ts, const double *cs,
-                                           const double *rec, const int *grid, int gcells, double tb,
+                                           const double *rec, const unsigned short *grid, int gcells, double tb,
                                            double te, double inv_h, int nk1, double (&arg)[kUnroll],
                                            const bool (&live)[kUnroll], double *yg, int *lg,
                                            int ibase, bool &out_of_range)
@@ -240,9 +247,10 @@ __device__ __forceinline__ void eval_group(const SplevParams &p, const double *t
         // FAST: one 64-byte record per interval {t(l), t(l+1), a0..a5}; the lookup grid lands in
         // the interval of the cell's left edge, a predicated single step covers one knot inside
         // the cell, the reference's own walk handles flagged cells (several knots) and edge rounding
+        const double goff = -tb * inv_h;
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            int g = __double2int_rz((arg[u] - tb) * inv_h);
+            int g = __double2int_rz(fma(arg[u], inv_h, goff));
             g = max(0, min(g, gcells - 1));
             l[u] = grid[g];
         }
@@ -250,8 +258,8 @@ __device__ __forceinline__ void eval_group(const SplevParams &p, const double *t
         bool slow = false;
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            const bool cplx = (l[u] >> 30) != 0;
-            const int l0 = l[u] & 0x3fffffff;
+            const bool cplx = (l[u] >> 15) != 0;
+            const int l0 = l[u] & 0x7fff;
             const double2 tt = reinterpret_cast<const double2 *>(rec + (size_t)(l0 - K1) * 8)[0];
             const bool step = (arg[u] >= tt.y) && (l0 < nk1);
             l[u] = l0 + (step ? 1 : 0);
@@ -288,7 +296,7 @@ __device__ __forceinline__ void eval_group(const SplevParams &p, const double *t
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
         const int i = ibase + 32 * u;
-        if (live[u]) {
+        if (ALLLIVE || live[u]) {
             if (PLAIN) {
                 yg[i] = sp[u];
             } else {
@@ -311,11 +319,17 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
     const int per_warp = splev_smem_doubles(MODE, K, smem_ld);
     uint64_t *mbars = reinterpret_cast<uint64_t *>(smem_raw);
     double *base = reinterpret_cast<double *>(smem_raw + 32 * kSplevWarps) + (size_t)warp * per_warp;
-    double *ts = base, *cs = base + smem_ld, *dlev = base + 2 * smem_ld,
-           *rec = base + (size_t)(2 + K) * smem_ld;
-    double *after = base + ((MODE == 1) ? smem_ld * (2 + K + 8) : smem_ld * 2);
+    auto tsb = [&](int b) { return base + (size_t)(2 * b) * smem_ld; };      // (t, c) buffer b
+    auto csb = [&](int b) { return base + (size_t)(2 * b + 1) * smem_ld; };
+    double *dlev = base + 4 * smem_ld;
+    double *rc = base + (size_t)(4 + K) * smem_ld;
+    double *rec = base + (size_t)(4 + 2 * K) * smem_ld;
+    double *after = base + ((MODE == 1) ? smem_ld * (4 + K + 8 + K) - 8 * (2 * K + 1) : smem_ld * 4);
+    double *ts = tsb(0), *cs = csb(0);
+    int tbuf = 0;           // table buffer holding the current spline
+    long long staged = -1;  // spline whose tables were prefetched into buffer 1-tbuf (TMA in flight)
     double *xs = after;                                         // [2][kXTile] evaluation points
-    int *grid = reinterpret_cast<int *>(after + 2 * kXTile);   // lookup grid
+    unsigned short *grid = reinterpret_cast<unsigned short *>(after + 2 * kXTile);  // lookup grid
     uint64_t *mbar = mbars + warp * 4;                          // [0] tables, [1..2] x tiles
     if (lane == 0) {
         mbar_init(mbar, 1);
@@ -353,29 +367,52 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
         }
         if (tj != cached) {
             n = p.n[tj];
-            const double *tg = p.t + tj * p.ldt, *cg = p.c + tj * p.ldt;
-            const uint32_t bytes = (uint32_t)(((n + 1) & ~1) * 8);
-            const bool tma_ok = ((((uintptr_t)tg) | ((uintptr_t)cg)) & 15) == 0 &&
-                                (((n + 1) & ~1) <= p.ldt);
-            __syncwarp();  // previous spline's readers are done with ts/cs
-            if (tma_ok) {
+            __syncwarp();  // previous spline's readers are done with their tables
+            auto tables_tma_ok = [&](long long q, int nq) -> bool {
+                const double *tg = p.t + q * p.ldt, *cg = p.c + q * p.ldt;
+                return ((((uintptr_t)tg) | ((uintptr_t)cg)) & 15) == 0 && (((nq + 1) & ~1) <= p.ldt);
+            };
+            auto issue_tables = [&](long long q, int nq, int buf) {
                 if (lane == 0) {
+                    const uint32_t bytes = (uint32_t)(((nq + 1) & ~1) * 8);
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                     mbar_expect_tx(mbar, 2 * bytes);
-                    tma_load_1d(ts, tg, bytes, mbar);
-                    tma_load_1d(cs, cg, bytes, mbar);
+                    tma_load_1d(tsb(buf), p.t + q * p.ldt, bytes, mbar);
+                    tma_load_1d(csb(buf), p.c + q * p.ldt, bytes, mbar);
                 }
+            };
+            if (staged == tj) {  // prefetched while the previous spline was evaluated
+                tbuf ^= 1;
+                mbar_wait(mbar, phase);
+                phase ^= 1;
+            } else if (tables_tma_ok(tj, n)) {
+                issue_tables(tj, n, tbuf);
                 mbar_wait(mbar, phase);
                 phase ^= 1;
             } else {
+                const double *tg = p.t + tj * p.ldt, *cg = p.c + tj * p.ldt;
                 for (int i = lane; i < n; i += 32) {
-                    ts[i] = tg[i];
-                    cs[i] = cg[i];
+                    tsb(tbuf)[i] = tg[i];
+                    csb(tbuf)[i] = cg[i];
+                }
+            }
+            ts = tsb(tbuf);
+            cs = csb(tbuf);
+            staged = -1;
+            // start fetching the next spline's tables into the other buffer
+            {
+                const long long jn = j + nwarps;
+                if (!p.nshared && jn < p.nspl) {
+                    const int nn = p.n[jn];
+                    if (tables_tma_ok(jn, nn)) {
+                        issue_tables(jn, nn, tbuf ^ 1);
+                        staged = jn;
+                    }
                 }
             }
             __syncwarp();
             // lookup grid over [t(k+1), t(n-k)]: grid[g] = interval of the cell's left edge;
-            // bit 30 flags a cell that may hold two or more knots (the single predicated step of
+            // bit 15 flags a cell that may hold two or more knots (the single predicated step of
             // the evaluation loop cannot resolve it: the full walk is taken).  Edges are widened
             // by 1e-6 of a cell so that rounding in the cell index can never un-flag a cell.
             {
@@ -402,11 +439,11 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
                     const double t2 = (l + 2 <= nk1_) ? ts[l + 1] : 1.79e308;  // t(l+2), if stepping twice is possible
                     for (int gI = g0; gI < g1; ++gI) {
                         const double right = tb_ + ((double)(gI + 1) + 1e-6) * hcell;
-                        grid[gI] = l | ((right >= t2) ? (1 << 30) : 0);
+                        grid[gI] = (unsigned short)(l | ((right >= t2) ? (1 << 15) : 0));
                     }
                 }
             }
-            if (MODE == 1) build_local_polys<K>(ts, cs, n, smem_ld, dlev, rec, lane);
+            if (MODE == 1) build_local_polys<K>(ts, cs, n, smem_ld, dlev, rec, rc, lane);
             __syncwarp();
             cached = (int)tj;
         }
@@ -422,19 +459,37 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
                 else { mbar_wait(mbar + 2, xphase1); xphase1 ^= 1; }
                 const int cnt = min(kXTile, p.m - t * kXTile);
                 const double *xt = xs + buf * kXTile;
+                if (cnt == kXTile) {  // full tile: no per-point bounds predicates
 #pragma unroll
-                for (int gq = 0; gq < kXTile / (32 * kUnroll); ++gq) {
-                    const int il = gq * 32 * kUnroll + lane;
-                    if (il - lane < cnt) {  // uniform across the warp
+                    for (int gq = 0; gq < kXTile / (32 * kUnroll); ++gq) {
+                        const int il = gq * 32 * kUnroll + lane;
                         double arg[kUnroll];
                         bool live[kUnroll];
 #pragma unroll
                         for (int u = 0; u < kUnroll; ++u) {
-                            live[u] = il + 32 * u < cnt;
-                            arg[u] = live[u] ? xt[il + 32 * u] : tb;
+                            live[u] = true;
+                            arg[u] = xt[il + 32 * u];
                         }
-                        eval_group<K, MODE, PLAIN>(p, ts, cs, rec, grid, gcells, tb, te, inv_h, nk1,
-                                                   arg, live, yg, lg, t * kXTile + il, out_of_range);
+                        eval_group<K, MODE, PLAIN, true>(p, ts, cs, rec, grid, gcells, tb, te, inv_h,
+                                                         nk1, arg, live, yg, lg, t * kXTile + il,
+                                                         out_of_range);
+                    }
+                } else {
+#pragma unroll
+                    for (int gq = 0; gq < kXTile / (32 * kUnroll); ++gq) {
+                        const int il = gq * 32 * kUnroll + lane;
+                        if (il - lane < cnt) {  // uniform across the warp
+                            double arg[kUnroll];
+                            bool live[kUnroll];
+#pragma unroll
+                            for (int u = 0; u < kUnroll; ++u) {
+                                live[u] = il + 32 * u < cnt;
+                                arg[u] = live[u] ? xt[il + 32 * u] : tb;
+                            }
+                            eval_group<K, MODE, PLAIN, false>(p, ts, cs, rec, grid, gcells, tb, te,
+                                                              inv_h, nk1, arg, live, yg, lg,
+                                                              t * kXTile + il, out_of_range);
+                        }
                     }
                 }
                 __syncwarp();  // every lane is done with this buffer
@@ -460,8 +515,8 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
                     const int inx = i + 32 * kUnroll;
                     nxt[u] = (inx < p.m) ? xg[inx] : tb;
                 }
-                eval_group<K, MODE, PLAIN>(p, ts, cs, rec, grid, gcells, tb, te, inv_h, nk1, arg,
-                                           live, yg, lg, i0, out_of_range);
+                eval_group<K, MODE, PLAIN, false>(p, ts, cs, rec, grid, gcells, tb, te, inv_h, nk1,
+                                                  arg, live, yg, lg, i0, out_of_range);
             }
         }
         if (p.ier) {
@@ -483,7 +538,7 @@ cudaError_t launch_splev(const SplevParams &p, int nsm, cudaStream_t stream)
     const size_t smem = 32 * kSplevWarps + per_warp * wpb;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;  // knot vectors beyond ~4000 entries
     long long blocks = ((long long)p.nspl + wpb - 1) / wpb;
-    const long long resident = (long long)(220 * 1024 / smem);
+    const long long resident = (long long)((228 * 1024) / (smem + 1024));  // 1 KB/CTA is reserved
     const long long max_blocks = (long long)nsm * (resident < 1 ? 1 : (resident > 8 ? 8 : resident));
     if (blocks > max_blocks) blocks = max_blocks;
 #define FPB_LAUNCH_SPLEV(KK)                                                                       \
