@@ -36,6 +36,7 @@ M, K, SIGMA, NEST = 256, 3, 0.1, 359
 S = M * SIGMA * SIGMA  # 2.56
 B_PER_GPU = 1 << 20
 SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
+SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 22, 512, 3, 28   # config 3 shape, 2^22 curves/GPU
 
 
 def parse():
@@ -46,6 +47,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--curves", type=int, default=B_PER_GPU, help="curves per GPU per step")
     ap.add_argument("--no-splev", action="store_true")
+    ap.add_argument("--no-shared", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -271,9 +273,17 @@ def main():
     flops = float(fit_flops(n_f, stats[:, 0], stats[:, 1]).sum().item())
     mean_n = float(n_f.mean().item())
     ok_frac = float((ier <= 0).to(torch.float64).mean().item())
+    gathered = None
+    if world > 1:
+        # optional final gather of the per-curve summary over NVLink (outside the timed region);
+        # the fit itself has no collective
+        from fitpack_b200.dist import gather_fit_summary
+        n_all, fp_all, ier_all = gather_fit_summary(n, res["fp"], ier)
+        ok_frac = float((ier_all <= 0).to(torch.float64).mean().item())
+        gathered = int(n_all.numel())
     alg_bytes = B * (2 * 8 * M + 16 * mean_n + 16)
     fit_ms = kernel_ms[-1]
-    roof = {"bound": "hbm", "kernel": "curfit_kernel<3>",
+    roof = {"bound": "hbm", "kernel": "fit pipeline: curfit_pass_kernel<3> x R + curfit_part2_kernel<3>",
             "achieved": alg_bytes / (fit_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_fit": alg_bytes / B,
@@ -372,6 +382,52 @@ def main():
                              "unit": "GB/s", "frac": bytes_alg / (kms * 1e-3) / 1e9 / hbm_peak,
                              "traffic": None, "peak_source": peak_src}}
         splev["gpu_launches"] = 2 * args.steps
+        del t, c, nvec, xe, so, r
+        torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- shared-abscissa LSQ (config 3 shape)
+    shared = None
+    if not args.no_shared:
+        torch.cuda.empty_cache()
+        f64 = torch.float64
+        Bs, ms, ks, nint = SHARED_B, SHARED_M, SHARED_K, SHARED_NINT
+        gsh = torch.Generator(device=dev)
+        gsh.manual_seed(7 + rank)
+        xs_ = torch.linspace(0, 1, ms, device=dev, dtype=f64)
+        nn = 2 * (ks + 1) + nint
+        tsh = torch.zeros(nn, device=dev, dtype=f64)
+        tsh[ks + 1:ks + 1 + nint] = torch.linspace(0, 1, nint + 2, device=dev, dtype=f64)[1:-1]
+        ysh = torch.randn((ms, Bs), generator=gsh, device=dev, dtype=f64)   # point-major
+        sho = {}
+        for _ in range(max(1, args.warmup)):
+            r = eng.curfit_shared(xs_, ysh, tsh, k=ks, out=sho)
+            sho = {"c": r["c"], "fp": r["fp"], "ier": r["ier"]}
+        barrier()
+        l0 = eng.launches
+        ev0.record()
+        for _ in range(args.steps):
+            r = eng.curfit_shared(xs_, ysh, tsh, k=ks, out=sho)
+        ev1.record()
+        barrier()
+        ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        kms = eng.last_kernel_ms()
+        nk1 = nn - ks - 1
+        bytes_curve = 8 * ms + 8 * nk1 + 12
+        flops_curve = ms * (1 + 6 * (ks + 1) + 2) + nk1 * (2 * ks + 1)
+        assert int(r["ier"].cpu()[0]) == 0
+        shared = {
+            "config": {"workload": "shared-abscissa least squares (iopt=-1): %d curves x %d points per "
+                                   "GPU, k=3, %d interior knots (config 3 shape)" % (Bs, ms, nint)},
+            "value": world * Bs / (ms_step * 1e-3), "unit": "fits/s", "ms_per_step": ms_step,
+            "gpu_launches": int(eng.launches - l0),
+            "roofline": {"bound": "hbm", "kernel": "shared_apply_kernel<3>",
+                         "achieved": Bs * bytes_curve / (kms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": Bs * bytes_curve / (kms * 1e-3) / 1e9 / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_curve": bytes_curve},
+            "fp64_gflops": Bs * flops_curve / (kms * 1e-3) / 1e9}
+        del ysh, sho, r
+        torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
@@ -404,9 +460,10 @@ def main():
                        "curves_per_gpu": B, "layout": "point-major SoA in HBM",
                        "l2": "inputs (%.1f GB/step) exceed the 126 MB L2; no flush needed"
                              % (2 * B * M * 8 / 1e9),
-                       "success_fraction": ok_frac},
+                       "success_fraction": ok_frac, "gathered_summary_curves": gathered},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "fp64": fp64, "splev": splev, "cpu_baseline": cpu,
+            "roofline": roof, "fp64": fp64, "splev": splev, "shared_lsq": shared,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:

@@ -170,6 +170,7 @@ void fpb_engine_destroy(fpb_engine *eng)
     eng->plan_row.release();
     eng->plan_skip.release();
     eng->plan_R.release();
+    eng->plan_meta.release();
     eng->plan_ier.release();
     for (auto &b : eng->scratch) b.release();
     if (eng->ev0) cudaEventDestroy(eng->ev0);
@@ -395,6 +396,7 @@ int32_t fp_curfit_shared_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE m, const
         !eng->plan_row.reserve((size_t)m * sizeof(int)) ||
         !eng->plan_skip.reserve((size_t)m * sizeof(int)) ||
         !eng->plan_R.reserve((size_t)std::max(nk1, 1) * k1 * sizeof(double)) ||
+        !eng->plan_meta.reserve((size_t)m * sizeof(int)) ||
         !eng->plan_ier.reserve(256))
         return FPB_ERR_ALLOC;
     SharedPlan plan;
@@ -409,11 +411,11 @@ int32_t fp_curfit_shared_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE m, const
     eng->launches++;
     begin_timing(eng);
     if (nbatch > 0) {
-        if (!cuda_ok(launch_shared_apply(nbatch, m, k, n, y, y_sb, y_si, plan, c, ldc, fp, eng->nsm,
-                                         eng->stream),
+        if (!cuda_ok(launch_shared_apply(nbatch, m, k, n, y, y_sb, y_si, plan, w,
+                                         eng->plan_meta.as<int>(), c, ldc, fp, eng->nsm, eng->stream),
                      "shared apply kernel"))
             return FPB_ERR_CUDA;
-        eng->launches++;
+        eng->launches += 2;
     }
     end_timing(eng);
     return FPB_STATUS_OK;

@@ -35,7 +35,7 @@ struct fpb_engine {
     fpb::DevBuf ws, wsi, counter;     // fit kernel workspace
     fpb::DevBuf lists, st_i, st_d, st_nrd;  // pass pipeline: curve lists and per-curve state
     int *h_count = nullptr;           // pinned host word for list-length read-back
-    fpb::DevBuf plan_cs, plan_w, plan_row, plan_skip, plan_R, plan_ier;  // shared-x plan
+    fpb::DevBuf plan_cs, plan_w, plan_row, plan_skip, plan_R, plan_ier, plan_meta;  // shared-x plan
     fpb::DevBuf scratch[12];          // staging for the host-pointer entry points
     fpb::DevBuf scratch2[12];         // second staging set (copy/compute overlap)
     cudaStream_t s_in = nullptr, s_out = nullptr;

@@ -121,25 +121,34 @@ __global__ void shared_plan_kernel(const double *x, const double *w, int m, doub
     *plan.ier = (n == nmin) ? IER_LSQ : IER_OK;
 }
 
-template <int K>
+// meta word of a point: (band rows to retire before it) << 8 | skipped-pivot bits
+__global__ void shared_meta_kernel(int m, const int *lrow, const int *skip, int *meta)
+{
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < m; it += gridDim.x * blockDim.x) {
+        const int adv = lrow[it] - (it > 0 ? lrow[it - 1] : 0);
+        meta[it] = (adv << 8) | (skip[it] & 0xff);
+    }
+}
+
+template <int K, bool HAS_W>
 __global__ void __launch_bounds__(kApplyThreads)
     shared_apply_kernel(int nbatch, int m, int n, const double *__restrict__ y, long long y_sb,
-                        long long y_si, SharedPlan plan, double *__restrict__ c, long long ldc,
-                        double *__restrict__ fp_out)
+                        long long y_si, SharedPlan plan, const int *__restrict__ meta_g,
+                        double *__restrict__ c, long long ldc, double *__restrict__ fp_out)
 {
     constexpr int K1 = K + 1;
     constexpr int ZLD = kApplyThreads + 1;
     extern __shared__ __align__(16) double sm[];
     const int nk1 = n - K1;
-    double *zs = sm;                                        // [nk1][ZLD]
-    double *Rs = zs + (size_t)nk1 * ZLD;                    // [nk1][K1]
-    double *pcs = Rs + (size_t)nk1 * K1;                    // [kPlanChunk][2*K1]
-    double *pw = pcs + (size_t)kPlanChunk * 2 * K1;         // [kPlanChunk]
-    int *prow = reinterpret_cast<int *>(pw + kPlanChunk);   // [kPlanChunk]
-    int *pskip = prow + kPlanChunk;                         // [kPlanChunk]
+    double *zs = sm;                                           // [nk1][ZLD]
+    double *Rs = zs + (((size_t)nk1 * ZLD + 1) & ~(size_t)1);  // [nk1][K1]   (16 B aligned)
+    double2 *pcs = reinterpret_cast<double2 *>(Rs + (((size_t)nk1 * K1 + 1) & ~(size_t)1));
+    double *pw = reinterpret_cast<double *>(pcs + (size_t)kPlanChunk * K1);  // [kPlanChunk]
+    int *pmeta = reinterpret_cast<int *>(pw + kPlanChunk);                   // [kPlanChunk]
     const int tid = threadIdx.x;
     if (*plan.ier > 0) return;  // ier<=0: success codes (0, or -2 for the polynomial)
     for (int i = tid; i < nk1 * K1; i += kApplyThreads) Rs[i] = plan.R[i];
+    const double2 *cs_g = reinterpret_cast<const double2 *>(plan.cs_sn);
 
     const long long ntiles = ((long long)nbatch + kApplyThreads - 1) / kApplyThreads;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -151,35 +160,67 @@ __global__ void __launch_bounds__(kApplyThreads)
         for (int r = 0; r < K1; ++r) Zw[r] = 0.0;
         double fp = 0.0;
         int cur = 0;  // band row held in Zw[0]
+        // y is streamed through a register double buffer: the 8 loads of the next group are in
+        // flight while the current group is rotated in (independent of the plan chunking)
+        double nxt[8];
+        const double *ynext = yp;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            nxt[u] = (u < m) ? *ynext : 0.0;
+            ynext += y_si;
+        }
         for (int base = 0; base < m; base += kPlanChunk) {
             const int cnt = min(kPlanChunk, m - base);
             __syncthreads();  // previous chunk fully consumed
-            for (int i = tid; i < cnt * 2 * K1; i += kApplyThreads)
-                pcs[i] = plan.cs_sn[(size_t)base * 2 * K1 + i];
+            for (int i = tid; i < cnt * K1; i += kApplyThreads) pcs[i] = cs_g[(size_t)base * K1 + i];
             for (int i = tid; i < cnt; i += kApplyThreads) {
-                pw[i] = plan.wgt[base + i];
-                prow[i] = plan.lrow[base + i];
-                pskip[i] = plan.skip[base + i];
+                if (HAS_W) pw[i] = plan.wgt[base + i];
+                pmeta[i] = meta_g[base + i];
             }
             __syncthreads();
-#pragma unroll 4
-            for (int q = 0; q < cnt; ++q) {
-                double yi = mul(yp[(long long)(base + q) * y_si], pw[q]);
-                const int row0 = prow[q];
-                while (cur < row0) {  // uniform across the block
-                    zs[(size_t)cur * ZLD + tid] = Zw[0];
+            for (int q0 = 0; q0 < cnt; q0 += 8) {
+                double yv[8];
+                const int itn = base + q0 + 8;  // first point of the next group
 #pragma unroll
-                    for (int r = 0; r < K; ++r) Zw[r] = Zw[r + 1];
-                    Zw[K] = 0.0;
-                    ++cur;
+                for (int u = 0; u < 8; ++u) {
+                    yv[u] = nxt[u];
+                    nxt[u] = (itn + u < m) ? *ynext : 0.0;
+                    ynext += y_si;
                 }
-                const int skip = pskip[q];
+                const double2 *pc = pcs + q0 * K1;
 #pragma unroll
-                for (int i = 0; i < K1; ++i) {
-                    if (!((skip >> i) & 1))
-                        rota(pcs[(q * K1 + i) * 2], pcs[(q * K1 + i) * 2 + 1], yi, Zw[i]);
+                for (int u = 0; u < 8; ++u) {
+                    const int q = q0 + u;
+                    if (q < cnt) {  // uniform
+                        const int meta = pmeta[q];
+                        if (meta >> 8) {  // the band window moves: retire finished rows (uniform)
+                            for (int a = meta >> 8; a > 0; --a) {
+                                zs[(size_t)cur * ZLD + tid] = Zw[0];
+#pragma unroll
+                                for (int r = 0; r < K; ++r) Zw[r] = Zw[r + 1];
+                                Zw[K] = 0.0;
+                                ++cur;
+                            }
+                        }
+                        double yi = HAS_W ? mul(yv[u], pw[q]) : yv[u];
+                        if ((meta & 0xff) == 0) {
+#pragma unroll
+                            for (int i = 0; i < K1; ++i) {
+                                const double2 r2 = pc[u * K1 + i];
+                                rota(r2.x, r2.y, yi, Zw[i]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < K1; ++i) {
+                                if (!((meta >> i) & 1)) {
+                                    const double2 r2 = pc[u * K1 + i];
+                                    rota(r2.x, r2.y, yi, Zw[i]);
+                                }
+                            }
+                        }
+                        fp = add(fp, mul(yi, yi));
+                    }
                 }
-                fp = add(fp, mul(yi, yi));
             }
         }
         while (cur < nk1 - K1) {
@@ -239,28 +280,30 @@ cudaError_t launch_shared_plan(const double *x, const double *w, int m, double x
 }
 
 cudaError_t launch_shared_apply(int nbatch, int m, int k, int n, const double *y, long long y_sb,
-                                long long y_si, const SharedPlan &plan, double *c, long long ldc,
-                                double *fp, int nsm, cudaStream_t stream)
+                                long long y_si, const SharedPlan &plan, const double *w, int *meta,
+                                double *c, long long ldc, double *fp, int nsm, cudaStream_t stream)
 {
     if (nbatch <= 0) return cudaSuccess;
     const int k1 = k + 1, nk1 = n - k1;
-    const size_t smem = sizeof(double) * ((size_t)nk1 * (kApplyThreads + 1) + (size_t)nk1 * k1 +
+    shared_meta_kernel<<<(m + 255) / 256, 256, 0, stream>>>(m, plan.lrow, plan.skip, meta);
+    const size_t smem = sizeof(double) * ((((size_t)nk1 * (kApplyThreads + 1) + 1) & ~(size_t)1) +
+                                          (((size_t)nk1 * k1 + 1) & ~(size_t)1) +
                                           (size_t)kPlanChunk * 2 * k1 + kPlanChunk) +
-                        sizeof(int) * 2 * kPlanChunk;
+                        sizeof(int) * kPlanChunk;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
     long long tiles = ((long long)nbatch + kApplyThreads - 1) / kApplyThreads;
-    long long resident = (long long)(220 * 1024 / smem);
+    long long resident = (long long)((228 * 1024) / (smem + 1024));
     if (resident > 8) resident = 8;
     if (resident < 1) resident = 1;
     long long grid = tiles < nsm * resident ? tiles : nsm * resident;
 #define FPB_LAUNCH_APPLY(KK)                                                                       \
     do {                                                                                           \
-        cudaError_t e_ = cudaFuncSetAttribute(shared_apply_kernel<KK>,                             \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+        auto kern = w ? shared_apply_kernel<KK, true> : shared_apply_kernel<KK, false>;            \
+        cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                               (int)smem);                                          \
         if (e_ != cudaSuccess) return e_;                                                          \
-        shared_apply_kernel<KK><<<(unsigned)grid, kApplyThreads, smem, stream>>>(                  \
-            nbatch, m, n, y, y_sb, y_si, plan, c, ldc, fp);                                        \
+        kern<<<(unsigned)grid, kApplyThreads, smem, stream>>>(nbatch, m, n, y, y_sb, y_si, plan,   \
+                                                              meta, c, ldc, fp);                   \
     } while (0)
     switch (k) {
     case 1: FPB_LAUNCH_APPLY(1); break;
