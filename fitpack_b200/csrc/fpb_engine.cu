@@ -6,6 +6,7 @@
 #include "fpb_engine.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -501,70 +502,166 @@ double fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused)
 
 namespace {
 
-// Sequential worker: fits the chunks [c_first, c_first + stride, ...) of a slice on ONE engine
-// (its stream, workspace and staging buffers): H2D, tile transpose, fit pipeline, D2H.
-int32_t fit_chunks_worker(fpb_engine *eng, long long b0, long long b1, long long chunk,
-                          long long c_first, long long c_stride, FP_SIZE iopt, FP_SIZE m,
-                          const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
-                          const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
-                          FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
-                          FP_REAL *fpint, FP_SIZE *nrdata)
+// One GPU's share of a host-pointer batch fit.  The slice is cut into a few large chunks that
+// are software-pipelined over three streams of one engine: while chunk i is fitted on the
+// engine's stream, chunk i+1 is copied in (s_in) and the knots/coefficients of chunk i-1 are
+// copied out (s_out).  Two staging sets alternate.  Pinned host memory is needed for the copies
+// to be asynchronous; with pageable memory the result is the same, only not overlapped.
+// Calls for one device are serialised by a per-device mutex.
+struct FitStage {
+    long long c0 = 0, nb = 0;
+    int nmax_used = 0;
+    bool pending = false;          // t/c copy-out in flight on s_out
+    std::vector<long long> bad;    // rows rejected with ier=10: the caller's t/c must survive
+    std::vector<double> keep_t, keep_c;
+};
+
+int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, long long b0, long long b1, FP_SIZE iopt,
+                            FP_SIZE m, const FP_REAL *x, const FP_REAL *y, const FP_REAL *w,
+                            FP_SIZE shared_x, const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k,
+                            FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
+                            FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata)
 {
     DeviceGuard g(eng->device);
     if (!g.ok) return FPB_ERR_CUDA;
-    cudaStream_t st = eng->stream;
+    if (!eng->s_in) {
+        if (!cuda_ok(cudaStreamCreateWithFlags(&eng->s_in, cudaStreamNonBlocking), "stream") ||
+            !cuda_ok(cudaStreamCreateWithFlags(&eng->s_out, cudaStreamNonBlocking), "stream"))
+            return FPB_ERR_CUDA;
+        for (int i = 0; i < 2; ++i)
+            if (!cuda_ok(cudaEventCreateWithFlags(&eng->ev_in[i], cudaEventDisableTiming), "event") ||
+                !cuda_ok(cudaEventCreateWithFlags(&eng->ev_fit[i], cudaEventDisableTiming), "event"))
+                return FPB_ERR_CUDA;
+    }
+    cudaStream_t st = eng->stream, s_in = eng->s_in, s_out = eng->s_out;
+    const long long total = b1 - b0;
+    // bytes per curve on the device: x,y,w curve-major + point-major, outputs t,c (+state)
+    const size_t per_curve = (size_t)m * 8 * 6 + (size_t)nest * 8 * 2 + (size_t)nest * 12 + 64;
+    long long chunk = (long long)(((size_t)6 << 30) / per_curve);  // <= 6 GB per staging set
+    if (nsplit > 1) chunk = std::min(chunk, std::max<long long>((total + nsplit - 1) / nsplit, 65536));
+    chunk = std::max<long long>(chunk - chunk % 128, 128);
     const bool state = (fpint && nrdata);
     enum { XC, YC, WC, XP, YP, WP, TT, CC, NN, FP_, IER, AUX };
-    const long long nchunks = (b1 - b0 + chunk - 1) / chunk;
-    for (long long ci = c_first; ci < nchunks; ci += c_stride) {
-        const long long c0 = b0 + ci * chunk;
-        const long long nb = std::min(chunk, b1 - c0);
+    FitStage stage[2];
+    const long long nchunks = (total + chunk - 1) / chunk;
+    auto bufs = [&](int set) { return set ? eng->scratch2 : eng->scratch; };
+
+    auto copy_in = [&](int set, long long c0, long long nb) -> int32_t {
+        DevBuf *B = bufs(set);
         const size_t pts = (size_t)nb * m * sizeof(double);
-        DevBuf *B = eng->scratch;
         const size_t aux_bytes = 64 + (state ? (size_t)nb * nest * 12 : 0);
         if (!B[YC].reserve(pts) || !B[YP].reserve(pts) ||
-            !B[XC].reserve(shared_x ? (size_t)m * 8 : pts) ||
-            !B[XP].reserve(shared_x ? 8 : pts) ||
+            !B[XC].reserve(shared_x ? (size_t)m * 8 : pts) || !B[XP].reserve(shared_x ? 8 : pts) ||
             !B[WC].reserve(w ? (shared_x ? (size_t)m * 8 : pts) : 8) ||
-            !B[WP].reserve((w && !shared_x) ? pts : 8) ||
-            !B[TT].reserve((size_t)nb * nest * 8) || !B[CC].reserve((size_t)nb * nest * 8) ||
-            !B[NN].reserve((size_t)nb * 4) || !B[FP_].reserve((size_t)nb * 8) ||
-            !B[IER].reserve((size_t)nb * 4) || !B[AUX].reserve(aux_bytes))
+            !B[WP].reserve((w && !shared_x) ? pts : 8) || !B[TT].reserve((size_t)nb * nest * 8) ||
+            !B[CC].reserve((size_t)nb * nest * 8) || !B[NN].reserve((size_t)nb * 4) ||
+            !B[FP_].reserve((size_t)nb * 8) || !B[IER].reserve((size_t)nb * 4) ||
+            !B[AUX].reserve(aux_bytes))
             return FPB_ERR_ALLOC;
         double *aux = B[AUX].as<double>();  // [0]=s [1]=xb [2]=xe, then optional state
-        double hs[3] = {s, xb ? *xb : 0.0, xe ? *xe : 0.0};
-        bool ok = cuda_ok(cudaMemcpyAsync(aux, hs, sizeof hs, cudaMemcpyHostToDevice, st), "H2D s");
-        ok = ok && cuda_ok(cudaMemcpyAsync(B[YC].ptr, y + (size_t)c0 * m, pts,
-                                           cudaMemcpyHostToDevice, st), "H2D y");
+        eng->h_aux[set][0] = s;
+        eng->h_aux[set][1] = xb ? *xb : 0.0;
+        eng->h_aux[set][2] = xe ? *xe : 0.0;
+        bool ok = cuda_ok(cudaMemcpyAsync(aux, eng->h_aux[set], 24, cudaMemcpyHostToDevice, s_in),
+                          "H2D s");
+        ok = ok && cuda_ok(cudaMemcpyAsync(B[YC].ptr, y + (size_t)c0 * m, pts, cudaMemcpyHostToDevice,
+                                           s_in), "H2D y");
+        if (shared_x) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[XC].ptr, x, (size_t)m * 8, cudaMemcpyHostToDevice,
+                                               s_in), "H2D x");
+            if (w)
+                ok = ok && cuda_ok(cudaMemcpyAsync(B[WC].ptr, w, (size_t)m * 8,
+                                                   cudaMemcpyHostToDevice, s_in), "H2D w");
+        } else {
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[XC].ptr, x + (size_t)c0 * m, pts,
+                                               cudaMemcpyHostToDevice, s_in), "H2D x");
+            if (w)
+                ok = ok && cuda_ok(cudaMemcpyAsync(B[WC].ptr, w + (size_t)c0 * m, pts,
+                                                   cudaMemcpyHostToDevice, s_in), "H2D w");
+        }
+        if (iopt != 0) {  // n, t (and the continuation state) are inputs
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + c0, (size_t)nb * 4,
+                                               cudaMemcpyHostToDevice, s_in), "H2D n");
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[TT].ptr, t + (size_t)c0 * nest,
+                                               (size_t)nb * nest * 8, cudaMemcpyHostToDevice, s_in),
+                               "H2D t");
+            if (iopt == -1)  // a curve rejected by fpchec must get its caller's c back unchanged
+                ok = ok && cuda_ok(cudaMemcpyAsync(B[CC].ptr, c + (size_t)c0 * nest,
+                                                   (size_t)nb * nest * 8, cudaMemcpyHostToDevice,
+                                                   s_in), "H2D c");
+            if (iopt == 1 && state) {
+                double *dfpint = aux + 8;
+                int *dnrd = reinterpret_cast<int *>(dfpint + (size_t)nb * nest);
+                ok = ok && cuda_ok(cudaMemcpyAsync(dfpint, fpint + (size_t)c0 * nest,
+                                                   (size_t)nb * nest * 8, cudaMemcpyHostToDevice,
+                                                   s_in), "H2D fpint");
+                ok = ok && cuda_ok(cudaMemcpyAsync(dnrd, nrdata + (size_t)c0 * nest,
+                                                   (size_t)nb * nest * 4, cudaMemcpyHostToDevice,
+                                                   s_in), "H2D nrdata");
+            }
+        }
+        // outputs the kernel may leave untouched (ier=10) must round-trip unchanged
+        ok = ok && cuda_ok(cudaMemcpyAsync(B[FP_].ptr, fp + c0, (size_t)nb * 8,
+                                           cudaMemcpyHostToDevice, s_in), "H2D fp");
+        if (iopt == 0)
+            ok = ok && cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + c0, (size_t)nb * 4,
+                                               cudaMemcpyHostToDevice, s_in), "H2D n");
+        ok = ok && cuda_ok(cudaEventRecord(eng->ev_in[set], s_in), "event");
+        return ok ? FPB_STATUS_OK : FPB_ERR_CUDA;
+    };
+
+    // finish the copy-out of a stage: wait for s_out, restore rejected rows
+    auto retire = [&](int set) -> bool {
+        FitStage &S = stage[set];
+        if (!S.pending) return true;
+        if (!cuda_ok(cudaStreamSynchronize(s_out), "sync")) return false;
+        for (size_t i = 0; i < S.bad.size(); ++i) {
+            std::memcpy(t + (size_t)(S.c0 + S.bad[i]) * nest, &S.keep_t[i * S.nmax_used],
+                        (size_t)S.nmax_used * 8);
+            std::memcpy(c + (size_t)(S.c0 + S.bad[i]) * nest, &S.keep_c[i * S.nmax_used],
+                        (size_t)S.nmax_used * 8);
+        }
+        S.pending = false;
+        return true;
+    };
+
+    if (nchunks > 0) {
+        const int32_t rc = copy_in(0, b0, std::min(chunk, total));
+        if (rc != FPB_STATUS_OK) return rc;
+    }
+    for (long long ci = 0; ci < nchunks; ++ci) {
+        const int set = (int)(ci & 1);
+        const long long c0 = b0 + ci * chunk;
+        const long long nb = std::min(chunk, b1 - c0);
+        DevBuf *B = bufs(set);
+        // prefetch the next chunk into the other staging set while this one is fitted
+        if (ci + 1 < nchunks) {
+            const long long c1 = c0 + chunk;
+            if (!retire(1 - set)) return FPB_ERR_CUDA;
+            const int32_t rc = copy_in(1 - set, c1, std::min(chunk, b1 - c1));
+            if (rc != FPB_STATUS_OK) return rc;
+        }
+        double *aux = B[AUX].as<double>();
+        bool ok = cuda_ok(cudaStreamWaitEvent(st, eng->ev_in[set], 0), "wait");
         const double *dx, *dw = nullptr;
         long long x_sb, x_si, w_sb = 0, w_si = 0;
         if (shared_x) {
-            ok = ok && cuda_ok(cudaMemcpyAsync(B[XC].ptr, x, (size_t)m * 8, cudaMemcpyHostToDevice,
-                                               st), "H2D x");
             dx = B[XC].as<double>(); x_sb = 0; x_si = 1;
-            if (w) {
-                ok = ok && cuda_ok(cudaMemcpyAsync(B[WC].ptr, w, (size_t)m * 8,
-                                                   cudaMemcpyHostToDevice, st), "H2D w");
-                dw = B[WC].as<double>(); w_sb = 0; w_si = 1;
-            }
+            if (w) { dw = B[WC].as<double>(); w_sb = 0; w_si = 1; }
         } else {
-            ok = ok && cuda_ok(cudaMemcpyAsync(B[XC].ptr, x + (size_t)c0 * m, pts,
-                                               cudaMemcpyHostToDevice, st), "H2D x");
-            ok = ok && cuda_ok(launch_transpose(B[XC].as<double>(), m, B[XP].as<double>(), nb, nb,
-                                                m, st), "transpose x");
+            ok = ok && cuda_ok(launch_transpose(B[XC].as<double>(), m, B[XP].as<double>(), nb, nb, m,
+                                                st), "transpose x");
             eng->launches++;
             dx = B[XP].as<double>(); x_sb = 1; x_si = nb;
             if (w) {
-                ok = ok && cuda_ok(cudaMemcpyAsync(B[WC].ptr, w + (size_t)c0 * m, pts,
-                                                   cudaMemcpyHostToDevice, st), "H2D w");
                 ok = ok && cuda_ok(launch_transpose(B[WC].as<double>(), m, B[WP].as<double>(), nb,
                                                     nb, m, st), "transpose w");
                 eng->launches++;
                 dw = B[WP].as<double>(); w_sb = 1; w_si = nb;
             }
         }
-        ok = ok && cuda_ok(launch_transpose(B[YC].as<double>(), m, B[YP].as<double>(), nb, nb, m,
-                                            st), "transpose y");
+        ok = ok && cuda_ok(launch_transpose(B[YC].as<double>(), m, B[YP].as<double>(), nb, nb, m, st),
+                           "transpose y");
         eng->launches++;
         if (!ok) return FPB_ERR_CUDA;
         double *dfpint = nullptr;
@@ -573,33 +670,6 @@ int32_t fit_chunks_worker(fpb_engine *eng, long long b0, long long b1, long long
             dfpint = aux + 8;
             dnrd = reinterpret_cast<int *>(dfpint + (size_t)nb * nest);
         }
-        if (iopt != 0) {  // n, t (and the continuation state) are inputs
-            ok = cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + c0, (size_t)nb * 4, cudaMemcpyHostToDevice,
-                                         st), "H2D n");
-            ok = ok && cuda_ok(cudaMemcpyAsync(B[TT].ptr, t + (size_t)c0 * nest,
-                                               (size_t)nb * nest * 8, cudaMemcpyHostToDevice, st),
-                               "H2D t");
-            if (iopt == -1)  // a curve rejected by fpchec must get its caller's c back unchanged
-                ok = ok && cuda_ok(cudaMemcpyAsync(B[CC].ptr, c + (size_t)c0 * nest,
-                                                   (size_t)nb * nest * 8, cudaMemcpyHostToDevice,
-                                                   st), "H2D c");
-            if (iopt == 1 && state) {
-                ok = ok && cuda_ok(cudaMemcpyAsync(dfpint, fpint + (size_t)c0 * nest,
-                                                   (size_t)nb * nest * 8, cudaMemcpyHostToDevice,
-                                                   st), "H2D fpint");
-                ok = ok && cuda_ok(cudaMemcpyAsync(dnrd, nrdata + (size_t)c0 * nest,
-                                                   (size_t)nb * nest * 4, cudaMemcpyHostToDevice,
-                                                   st), "H2D nrdata");
-            }
-            if (!ok) return FPB_ERR_CUDA;
-        }
-        // outputs the kernel may leave untouched (ier=10) must round-trip unchanged
-        ok = cuda_ok(cudaMemcpyAsync(B[FP_].ptr, fp + c0, (size_t)nb * 8, cudaMemcpyHostToDevice, st),
-                     "H2D fp");
-        if (iopt == 0)
-            ok = ok && cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + c0, (size_t)nb * 4,
-                                               cudaMemcpyHostToDevice, st), "H2D n");
-        if (!ok) return FPB_ERR_CUDA;
         int32_t rc = fp_curfit_batch_dev_c(eng, (FP_SIZE)nb, iopt, m, dx, x_sb, x_si,
                                            B[YP].as<double>(), 1, nb, dw, w_sb, w_si,
                                            xb ? aux + 1 : nullptr, xe ? aux + 2 : nullptr, 0, k, aux,
@@ -615,59 +685,61 @@ int32_t fit_chunks_worker(fpb_engine *eng, long long b0, long long b1, long long
                                            cudaMemcpyDeviceToHost, st), "D2H ier");
         if (!ok || !cuda_ok(cudaStreamSynchronize(st), "sync")) return FPB_ERR_CUDA;
         // knots/coefficients: only the leading max(n) columns carry information
+        FitStage &S = stage[set];
+        S.c0 = c0;
+        S.nb = nb;
+        S.bad.clear();
         int nmax_used = 0;
         bool any_fit = false;
-        std::vector<long long> bad;
         for (long long b = 0; b < nb; ++b) {
             if (ier[c0 + b] != FPB_INPUT_ERROR) {
                 nmax_used = std::max(nmax_used, (int)n[c0 + b]);
                 any_fit = true;
             } else if (iopt != -1) {
-                bad.push_back(b);
+                S.bad.push_back(b);
             }
         }
         if (iopt == -1) nmax_used = nest;  // clamped end knots may have been written even on ier=10
         nmax_used = std::min<int>(std::max(nmax_used, 0), nest);
+        S.nmax_used = nmax_used;
         if (nmax_used > 0 && (any_fit || iopt == -1)) {
             // rows whose fit was rejected keep the caller's t/c (2-D copy of the leading columns;
-            // rejected rows are restored from a host backup)
-            std::vector<double> keep_t(bad.size() * (size_t)nmax_used), keep_c(keep_t.size());
-            for (size_t i = 0; i < bad.size(); ++i) {
-                std::memcpy(&keep_t[i * nmax_used], t + (size_t)(c0 + bad[i]) * nest,
+            // rejected rows are restored from a host backup when the stage retires)
+            S.keep_t.resize(S.bad.size() * (size_t)nmax_used);
+            S.keep_c.resize(S.bad.size() * (size_t)nmax_used);
+            for (size_t i = 0; i < S.bad.size(); ++i) {
+                std::memcpy(&S.keep_t[i * nmax_used], t + (size_t)(c0 + S.bad[i]) * nest,
                             (size_t)nmax_used * 8);
-                std::memcpy(&keep_c[i * nmax_used], c + (size_t)(c0 + bad[i]) * nest,
+                std::memcpy(&S.keep_c[i * nmax_used], c + (size_t)(c0 + S.bad[i]) * nest,
                             (size_t)nmax_used * 8);
             }
             ok = cuda_ok(cudaMemcpy2DAsync(t + (size_t)c0 * nest, (size_t)nest * 8, B[TT].ptr,
                                            (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
-                                           cudaMemcpyDeviceToHost, st), "D2H t");
+                                           cudaMemcpyDeviceToHost, s_out), "D2H t");
             ok = ok && cuda_ok(cudaMemcpy2DAsync(c + (size_t)c0 * nest, (size_t)nest * 8, B[CC].ptr,
                                                  (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
-                                                 cudaMemcpyDeviceToHost, st), "D2H c");
+                                                 cudaMemcpyDeviceToHost, s_out), "D2H c");
             if (state && iopt >= 0) {
                 ok = ok && cuda_ok(cudaMemcpyAsync(fpint + (size_t)c0 * nest, dfpint,
                                                    (size_t)nb * nest * 8, cudaMemcpyDeviceToHost,
-                                                   st), "D2H fpint");
+                                                   s_out), "D2H fpint");
                 ok = ok && cuda_ok(cudaMemcpyAsync(nrdata + (size_t)c0 * nest, dnrd,
                                                    (size_t)nb * nest * 4, cudaMemcpyDeviceToHost,
-                                                   st), "D2H nrdata");
+                                                   s_out), "D2H nrdata");
             }
-            if (!ok || !cuda_ok(cudaStreamSynchronize(st), "sync")) return FPB_ERR_CUDA;
-            for (size_t i = 0; i < bad.size(); ++i) {
-                std::memcpy(t + (size_t)(c0 + bad[i]) * nest, &keep_t[i * nmax_used],
-                            (size_t)nmax_used * 8);
-                std::memcpy(c + (size_t)(c0 + bad[i]) * nest, &keep_c[i * nmax_used],
-                            (size_t)nmax_used * 8);
-            }
+            if (!ok) return FPB_ERR_CUDA;
+            S.pending = true;
         }
     }
+    if (!retire(0) || !retire(1)) return FPB_ERR_CUDA;
     return FPB_STATUS_OK;
 }
 
-// One GPU's share of a host-pointer batch fit.  Large slices are cut into chunks that two
-// host workers (each with its own engine = stream + workspace + staging) process alternately,
-// so that one chunk's copies and the sparsely populated tail of its fit pipeline overlap the
-// other chunk's compute.  Calls for one device are serialised by a per-device mutex.
+// Few, large chunks: the fit pipeline is most efficient on big batches (its tail -- the last
+// knot sets and the longest p-iterations -- has a fixed latency).  A large slice is halved
+// between two host workers, each with its own engine (stream, workspace, staging) running the
+// pipelined loop on two chunks: the copies of one chunk and the sparsely populated tail of its
+// fit overlap the other worker's compute.  Calls for one device are serialised by a mutex.
 std::mutex g_host_api_mu[64];
 
 int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_SIZE m,
@@ -682,25 +754,29 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     fpb_engine *e0 = default_engine(device);
     if (!e0) return FPB_ERR_CUDA;
     const long long total = b1 - b0;
-    const size_t per_curve = (size_t)m * 8 * 6 + (size_t)nest * 8 * 2 + (size_t)nest * 12 + 64;
-    long long chunk = (long long)(((size_t)4 << 30) / per_curve);  // <= 4 GB of staging per engine
-    const bool split = total >= 4 * 65536;
-    if (split) chunk = std::min(chunk, std::max<long long>((total + 7) / 8, 65536));
-    chunk = std::max<long long>(chunk - chunk % 128, 128);
-    if (!split) {
-        return fit_chunks_worker(e0, b0, b1, chunk, 0, 1, iopt, m, x, y, w, shared_x, xb, xe, k, s,
-                                 nest, n, t, c, fp, ier, fpint, nrdata);
+    int workers = 2, nsplit = 2;
+    if (const char *e = std::getenv("FPB_HOST_WORKERS")) workers = std::max(1, std::min(2, std::atoi(e)));
+    if (const char *e = std::getenv("FPB_HOST_CHUNKS")) nsplit = std::max(1, std::atoi(e));
+    if (total < 4 * 65536) {
+        return fit_slice_pipelined(e0, 1, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest, n, t,
+                                   c, fp, ier, fpint, nrdata);
+    }
+    if (workers == 1) {
+        return fit_slice_pipelined(e0, 2 * nsplit, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s,
+                                   nest, n, t, c, fp, ier, fpint, nrdata);
     }
     fpb_engine *e1 = default_engine(device + 32);  // second engine of the same device
     if (!e1) return FPB_ERR_CUDA;
+    long long half = (total / 2 + 127) / 128 * 128;
     int32_t rc[2] = {FPB_STATUS_OK, FPB_STATUS_OK};
     std::string err[2];
     std::thread th[2];
     fpb_engine *eng2[2] = {e0, e1};
+    const long long lo[2] = {b0, b0 + half}, hi[2] = {b0 + half, b1};
     for (int wk = 0; wk < 2; ++wk) {
         th[wk] = std::thread([&, wk]() {
-            rc[wk] = fit_chunks_worker(eng2[wk], b0, b1, chunk, wk, 2, iopt, m, x, y, w, shared_x, xb,
-                                       xe, k, s, nest, n, t, c, fp, ier, fpint, nrdata);
+            rc[wk] = fit_slice_pipelined(eng2[wk], nsplit, lo[wk], hi[wk], iopt, m, x, y, w, shared_x,
+                                         xb, xe, k, s, nest, n, t, c, fp, ier, fpint, nrdata);
             if (rc[wk] != FPB_STATUS_OK) err[wk] = fpb_last_error();
         });
     }

@@ -347,6 +347,15 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
     double inv_h = 0.0;
     for (long long j = gwarp; j < p.nspl; j += nwarps) {
         const long long tj = p.nshared ? 0 : j;
+        {
+            // a knot count the row cannot hold, or too small for degree K, is invalid input
+            // (splev itself would read out of bounds): flag the spline and skip it
+            const int nj = p.n[tj];
+            if (nj < 2 * K1 || nj > p.ldt) {
+                if (p.ier && lane == 0) p.ier[j] = IER_INPUT;
+                continue;
+            }
+        }
         const double *xg = p.x + j * p.m;
         // TMA tiles need 16-byte aligned rows of even length; otherwise plain loads
         // (EXACT mode is FP64-bound, not latency-bound: it keeps the register-pipelined loads)
@@ -404,7 +413,7 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
                 const long long jn = j + nwarps;
                 if (!p.nshared && jn < p.nspl) {
                     const int nn = p.n[jn];
-                    if (tables_tma_ok(jn, nn)) {
+                    if (nn >= 2 * K1 && tables_tma_ok(jn, nn)) {
                         issue_tables(jn, nn, tbuf ^ 1);
                         staged = jn;
                     }

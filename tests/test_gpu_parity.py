@@ -387,6 +387,22 @@ def test_splev_batch_fast_mode_tolerance(eng, k):
         assert err.max() < 1e-12, err.max()
 
 
+def test_splev_batch_rejects_bad_knot_counts(eng):
+    import torch
+    dev = eng.device
+    k, ldt = 3, 16
+    t = torch.zeros((5, ldt), device=dev, dtype=torch.float64)
+    t[:, 4:] = 1.0
+    c = torch.ones((5, ldt), device=dev, dtype=torch.float64)
+    n = torch.tensor([8, 7, 17, 8, 0], device=dev, dtype=torch.int32)   # 7 < 2k+2, 17 > ldt, 0
+    x = torch.rand((5, 64), device=dev, dtype=torch.float64)
+    for mode in (0, 1):
+        r = eng.splev_batch(t, n, c, k, x, mode=mode)
+        assert r["ier"].cpu().tolist() == [0, 10, 10, 0, 10]
+        assert torch.allclose(r["y"][0], torch.ones(64, device=dev, dtype=torch.float64))
+        assert torch.allclose(r["y"][3], torch.ones(64, device=dev, dtype=torch.float64))
+
+
 def test_splev_shared_spline_and_large_knot_vectors(eng, F):
     import torch
     rng = np.random.default_rng(40)
