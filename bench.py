@@ -37,6 +37,11 @@ S = M * SIGMA * SIGMA  # 2.56
 B_PER_GPU = 1 << 20
 SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
 SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 22, 512, 3, 28   # config 3 shape, 2^22 curves/GPU
+# DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum,
+# profiles/r01_final_kernels.md, profiles/r01_final_launches.md); the bench itself never runs under ncu.
+NCU_FIT_DRAM_BYTES_PER_FIT = 8.1 * (6.558e9 + 1.593e9) / 2.5e5 + (51.47e9 + 10.02e9) / (0.94 * 262144)
+NCU_SPLEV_DRAM_BYTES_PER_POINT = (8.546e9 + 7.964e9) / (1048576 * 954)
+NCU_SHARED_DRAM_BYTES_PER_CURVE = (17.18e9 + 1.104e9) / 4194304
 
 
 def parse():
@@ -285,7 +290,10 @@ def main():
     fit_ms = kernel_ms[-1]
     roof = {"bound": "hbm", "kernel": "fit pipeline: curfit_pass_kernel<3> x R + curfit_part2_kernel<3>",
             "achieved": alg_bytes / (fit_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "traffic": None, "peak_source": peak_src,
+            "traffic": NCU_FIT_DRAM_BYTES_PER_FIT * B, "traffic_source": "ncu dram bytes per fit "
+            "(pass + part-2 kernels, profiles/r01_final_kernels.md) x curves per launch sequence; "
+            "workspace traffic (stored basis values, G copies, per-pass state), not re-reads of the input",
+            "peak_source": peak_src,
             "algorithmic_bytes_per_fit": alg_bytes / B,
             "note": "fit kernel is FP64 issue/latency bound (~%.0f kflop per 4.4 KB): HBM "
                     "fraction is tiny by construction; see fp64" % (flops / B / 1e3)}
@@ -380,7 +388,8 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "splev_kernel<5> mode=%s" % name,
                              "achieved": bytes_alg / (kms * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": bytes_alg / (kms * 1e-3) / 1e9 / hbm_peak,
-                             "traffic": None, "peak_source": peak_src}}
+                             "traffic": (NCU_SPLEV_DRAM_BYTES_PER_POINT * ns * ms) if mode == 1 else None,
+                             "peak_source": peak_src}}
         splev["gpu_launches"] = 2 * args.steps
         del t, c, nvec, xe, so, r
         torch.cuda.empty_cache()
@@ -423,7 +432,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "shared_apply_kernel<3>",
                          "achieved": Bs * bytes_curve / (kms * 1e-3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": Bs * bytes_curve / (kms * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_SHARED_DRAM_BYTES_PER_CURVE * Bs, "peak_source": peak_src,
                          "algorithmic_bytes_per_curve": bytes_curve},
             "fp64_gflops": Bs * flops_curve / (kms * 1e-3) / 1e9}
         del ysh, sho, r
