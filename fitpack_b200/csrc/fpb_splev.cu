@@ -5,19 +5,21 @@
 // One warp per spline: the warp stages the spline's knots and coefficients in
 // shared memory once (TMA bulk copy when the rows are 16-byte aligned), then
 // streams the spline's m evaluation points through its 32 lanes with fully
-// coalesced 256 B loads/stores.  Each lane finds its knot interval with a
-// branch-free upper-bound binary search over the staged knots; the result is
-// the history-independent interval the reference's bidirectional walk ends in
-// (rightmost l in [k+1, n-k-1] with t(l) <= arg, core:17880-17887).
+// coalesced 256 B loads/stores.  Each lane finds its knot interval through a
+// per-spline lookup grid; the result is always the history-independent interval
+// the reference's bidirectional walk ends in (rightmost l in [k+1, n-k-1] with
+// t(l) <= arg, core:17880-17887).
 //
-// mode FPB_SPLEV_EXACT: de Boor-Cox recurrence + (k+1)-term dot product in the
-//   reference's operation order, no FMA: values bit-identical to the reference.
-// mode FPB_SPLEV_FAST: the warp first converts the spline to one local Taylor
-//   polynomial per knot interval (derivative pyramid + one basis evaluation per
-//   interval, all in shared memory), then evaluates with Horner/FMA -- ~12
-//   FP64 instructions per point instead of ~400, which is what makes the
-//   kernel HBM-bound (16 B/point).  Same interval indices; values agree with
-//   the exact mode to ~1e-15*max|c| (tests state 1e-12).
+// mode FPB_SPLEV_EXACT (splev_kernel): de Boor-Cox recurrence + (k+1)-term dot
+//   product in the reference's operation order, no FMA: values bit-identical to
+//   the reference.  FP64-pipe bound (~400 FP64 slots per point).
+// mode FPB_SPLEV_FAST (splev_fast_kernel): the warp first converts the spline to
+//   one local Taylor polynomial per knot interval (each lane builds the records
+//   of its intervals in registers), then evaluates with Horner/FMA.  The
+//   evaluation points of the warp's whole spline sequence flow through a ring of
+//   TMA tiles that runs ahead across spline boundaries, so neither the table
+//   build nor the DRAM latency of the point stream is exposed.  Same interval
+//   indices; values agree with the exact mode to ~1e-15*max|c| (tests: 1e-12).
 #include "fpb_common.cuh"
 #include "fpb_kernels.h"
 
@@ -26,7 +28,15 @@ namespace fpb {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int kSplevWarps = 8;
+constexpr int kSplevWarps = 8;  // EXACT mode: warps per CTA (2 CTAs/SM); also sizes the mbarrier header
+// FAST mode launch shape: warps per CTA x CTAs per SM (register budget 65536 / threads per SM)
+#ifndef FPB_SPLEV_FAST_WARPS
+#define FPB_SPLEV_FAST_WARPS 8
+#endif
+#ifndef FPB_SPLEV_FAST_BLOCKS
+#define FPB_SPLEV_FAST_BLOCKS 2
+#endif
+constexpr int kFastWarps = FPB_SPLEV_FAST_WARPS, kFastBlocks = FPB_SPLEV_FAST_BLOCKS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -79,22 +89,37 @@ __host__ __device__ inline int splev_grid_cells(int nint)
     return g;
 }
 
+// FAST mode tables.  One record per knot interval, kRecD doubles apart (80 B: the STS.128 of a
+// record written by 32 lanes are bank-conflict free per quarter warp; 64 B would be 16-way):
+//   rec[0] = t(l) (expansion centre), rec[1 + r] = a_r, s(x) = sum_r a_r (x - t(l))^r on interval l.
+// One 16-byte cell per lookup-grid cell: {t(l0+1) or +inf, byte offset of record l0, l0 | flag<<31}
+// where l0 is the interval of the cell's (widened) left edge.
+constexpr int kRecD = 10;
+constexpr int kUnroll = 4;              // independent points per lane per group (instruction-level parallelism)
+constexpr int kTilePts = 32 * kUnroll;  // FAST: evaluation points per TMA tile (1 KB) = one group
+#ifndef FPB_SPLEV_NBUF
+#define FPB_SPLEV_NBUF 4
+#endif
+constexpr int kNBuf = FPB_SPLEV_NBUF;   // FAST: tiles in flight per warp (ring, power of two)
+constexpr int kMbarPerWarp = 16;        // mbarrier slots per warp: [0] tables, [1..kNBuf] tiles
+static_assert(kNBuf + 1 <= kMbarPerWarp && (kNBuf & (kNBuf - 1)) == 0, "ring size");
+static_assert(kFastWarps <= kSplevWarps, "mbarrier header is sized for kSplevWarps warps");
+
 // per-warp shared memory in doubles: two (t, c) buffers [2][2][ld] (the next spline's tables are
-// prefetched while the current one is evaluated), + fast mode [dlev: K*ld][rc: K*ld]
-// [rec: 8*(ld-2K-1)]
-// followed by the lookup grid (ints, counted here in doubles)
+// prefetched while the current one is evaluated); EXACT: + uint16 lookup grid; FAST: + interval
+// records [kRecD*(ld-2K-1)], the 16-byte lookup cells and the ring of x tiles
 __host__ __device__ inline int splev_smem_doubles(int mode, int k, int ld)
 {
-    const int grid = (splev_grid_cells(ld - 2 * k - 1) + 3) / 4;  // uint16 entries
-    return ((mode == 1) ? ld * (4 + k + 8 + k) - 8 * (2 * k + 1) : ld * 4) + 2 * 256 /* x tiles */ + grid;
+    const int cells = splev_grid_cells(ld - 2 * k - 1);
+    const int nintmax = (ld - 2 * k - 1 > 1) ? ld - 2 * k - 1 : 1;
+    return ld * 4 + ((mode == 1) ? ((kRecD * nintmax + 1) & ~1) + 2 * cells + kNBuf * kTilePts
+                                 : (cells + 3) / 4);
 }
 
-// 1/d to ~1 ulp without the IEEE division sequence (FAST mode only): hardware seed + two
-// Newton steps; falls back to a true division outside the safe exponent range.
-__device__ __forceinline__ double fast_rcp(double d)
+// 1/d by hardware seed + two Newton steps (FAST mode only; d must be a normal number well inside
+// the exponent range -- the caller checks once per interval).
+__device__ __forceinline__ double rcp_newton(double d)
 {
-    const double ad = fabs(d);
-    if (!(ad > 1e-290 && ad < 1e290)) return 1.0 / d;
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
     double e = fma(-d, r, 1.0);
@@ -102,19 +127,6 @@ __device__ __forceinline__ double fast_rcp(double d)
     e = fma(-d, r, 1.0);
     r = fma(r, e, r);
     return r;
-}
-
-// interval search: l = k1 + #{ i in (k1, nk1] : t(i) <= arg }  (1-based), t non-decreasing.
-// Fixed number of halving steps (`top` = largest power of two <= nk1-k1, uniform per spline),
-// so the 32 lanes never diverge.
-__device__ __forceinline__ int find_interval(const double *ts, int k1, int nk1, int top, double arg)
-{
-    int lo = k1;
-    for (int step = top; step > 0; step >>= 1) {
-        const int cand = lo + step;
-        if (cand <= nk1 && ts[cand - 1] <= arg) lo = cand;
-    }
-    return lo;
 }
 
 // Interval of `arg` from the lookup grid + the reference's own bidirectional walk
@@ -143,202 +155,187 @@ __device__ __forceinline__ double eval_exact(const double *ts, const double *cs,
     return sp;
 }
 
-// Build one 64-byte record per knot interval l of spline (ts,cs):
-//   rec[(l-k1)*8 + 0..1] = t(l), t(l+1);  rec[(l-k1)*8 + 2 + r] = a_r  with
-//   s(x) = sum_r a_r * (x - t(l))^r   on interval l   (unused slots are zero).
-// dlev[r*ld + i] (r = 1..K) receives the derivative pyramid
-//   d^r_i = (K-r+1)/r * (d^{r-1}_i - d^{r-1}_{i-1}) / (t_{i+K-r+1} - t_i),   d^0 = c,
-// i.e. the B-spline coefficients (degree K-r) of s^(r)/r!.  One de Boor-Cox recurrence
-// per interval at x = t(l) then yields the basis of every degree 0..K on the way up.
+// FAST mode: convert the spline (ts, cs) into one local Taylor polynomial per knot interval.
+// Each lane owns the intervals l = k1+lane, k1+lane+32, ... and works entirely in registers on the
+// 2K knots / K+1 coefficients around its interval (no cross-lane traffic, no scratch tables):
+//   R[j][i]  = 1 / (t(l+i) - t(l+i-j)),  1 <= i <= j <= K -- the K(K+1)/2 spans that contain
+//              [t(l), t(l+1)]; they are the denominators of BOTH recurrences below
+//   D^r[e]   = (D^{r-1}[e] - D^{r-1}[e-1]) * R[K-r+1][e-r+1],  D^0[e] = c(l-K+e): the B-spline
+//              coefficients of s^(r) / (K!/(K-r)!) restricted to the interval
+//   h_j[0..j]= the degree-j basis at x = t(l) (de Boor-Cox, core:2387-2413)
+//   a_r      = binom(K,r) * sum_q D^r[r+q] * h_{K-r}[q]   (= s^(r)(t(l)) / r!)
+// Coincident knots give R = 0, which reproduces fpbspl's "skip the term" branch (core:2403).
 template <int K>
-__device__ void build_local_polys(const double *ts, const double *cs, int n, int ld, double *dlev,
-                                  double *rec, double *rc, int lane)
+__device__ void build_records(const double *ts, const double *cs, int n, double *rec, int lane)
 {
     constexpr int K1 = K + 1;
     const int nk1 = n - K1;
-    const int nint = nk1 - K1 + 1;
-    // reciprocal knot spans rc[(j-1)*ld + a] = 1 / (t[a+j] - t[a]) (0-based a), j = 1..K; every
-    // denominator of the derivative pyramid and of the basis recurrences is one of them.
-    // Coincident knots give 0, which reproduces fpbspl's "skip the term" branch.
-#pragma unroll
-    for (int j = 1; j <= K; ++j) {
-        for (int a = lane; a + j < n; a += 32) {
-            const double den = ts[a + j] - ts[a];
-            rc[(size_t)(j - 1) * ld + a] = (fabs(den) >= DBL_MIN) ? fast_rcp(den) : 0.0;
-        }
-    }
-    __syncwarp();
-    for (int r = 1; r <= K; ++r) {
-        const double *prev = (r == 1) ? cs : dlev + (size_t)(r - 2) * ld;
-        double *cur = dlev + (size_t)(r - 1) * ld;
-        const double scale = (double)(K - r + 1) / (double)r;
-        const double *rcj = rc + (size_t)(K - r) * ld;  // span K-r+1
-        for (int i0 = lane; i0 < nk1; i0 += 32) {
-            double v = 0.0;
-            if (i0 >= r) v = scale * (prev[i0] - prev[i0 - 1]) * rcj[i0];
-            cur[i0] = v;
-        }
-        __syncwarp();
-    }
+    const int nint = nk1 - K;
     for (int li = lane; li < nint; li += 32) {
-        const int l = K1 + li;       // 1-based interval index
-        const double x = ts[l - 1];  // t(l)
-        double h[K1];
-        h[0] = 1.0;
-        double *rl = rec + (size_t)li * 8;
-        rl[0] = x;
-        rl[1] = ts[l];
+        const int l = K1 + li;  // 1-based interval index
+        double tw[2 * K], D[K1];
 #pragma unroll
-        for (int r = K + 1; r < 6; ++r) rl[2 + r] = 0.0;
-        rl[2 + K] = (K >= 1) ? dlev[(size_t)(K - 1) * ld + (l - 1)] : cs[l - 1];
+        for (int q = 0; q < 2 * K; ++q) tw[q] = ts[l - K + q];  // tw[q] = t(l-K+1+q)
+#pragma unroll
+        for (int e = 0; e <= K; ++e) D[e] = cs[l - 1 - K + e];  // c(l-K+e)
+        double R[K][K];
+        // every span contains [t(l), t(l+1)] and lies inside [t(l-K+1), t(l+K)]
+        const double dmin = tw[K] - tw[K - 1], dmax = tw[2 * K - 1] - tw[0];
+        if (dmin > 1e-290 && dmax < 1e290) {
+#pragma unroll
+            for (int j = 1; j <= K; ++j)
+#pragma unroll
+                for (int i = 1; i <= j; ++i) R[j - 1][i - 1] = rcp_newton(tw[K - 1 + i] - tw[K - 1 + i - j]);
+        } else {
+#pragma unroll
+            for (int j = 1; j <= K; ++j)
+#pragma unroll
+                for (int i = 1; i <= j; ++i) {
+                    const double den = tw[K - 1 + i] - tw[K - 1 + i - j];
+                    R[j - 1][i - 1] = (fabs(den) >= DBL_MIN) ? 1.0 / den : 0.0;
+                }
+        }
+        const double x = tw[K - 1];
+        double a[K1];
+        // basis of degree j pairs with derivative level r = K-j: run the basis upwards and the
+        // difference table downwards, meeting in the dot products
+        double h[K1], lev[K1][K1];  // lev[r][e], e = r..K (fully unrolled: registers)
+#pragma unroll
+        for (int e = 0; e <= K; ++e) lev[0][e] = D[e];
+#pragma unroll
+        for (int r = 1; r <= K; ++r)
+#pragma unroll
+            for (int e = r; e <= K; ++e)
+                lev[r][e] = (lev[r - 1][e] - lev[r - 1][e - 1]) * R[K - r][e - r];
+        // x = t(l) is a knot: the last basis function of every degree >= 1 vanishes there, so
+        // degree j has only j non-zero values h[0..j-1] and the i = j term of the recurrence drops
+        h[0] = 1.0;
+        a[K] = lev[K][K];
+        double binom = 1.0;
 #pragma unroll
         for (int j = 1; j <= K; ++j) {
             double hh[K];
 #pragma unroll
             for (int i = 0; i < j; ++i) hh[i] = h[i];
             h[0] = 0.0;
-            const double *rcj = rc + (size_t)(j - 1) * ld;
 #pragma unroll
-            for (int i = 1; i <= j; ++i) {
-                const double tli = ts[l + i - 1], tlj = ts[l + i - j - 1];
-                const double f = hh[i - 1] * rcj[l + i - j - 1];
-                h[i - 1] = fma(f, tli - x, h[i - 1]);
-                h[i] = f * (x - tlj);
+            for (int i = 1; i <= ((j == 1) ? 1 : j - 1); ++i) {
+                const double f = hh[i - 1] * R[j - 1][i - 1];
+                h[i - 1] = fma(f, tw[K - 1 + i] - x, h[i - 1]);
+                if (i < j) h[i] = f * (x - tw[K - 1 + i - j]);
             }
-            const int r = K - j;  // basis of degree j pairs with derivative level K-j
-            const double *lev = (r == 0) ? cs : dlev + (size_t)(r - 1) * ld;
+            const int r = K - j;
             double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q <= j; ++q) acc = fma(lev[l - j - 1 + q], h[q], acc);
-            rl[2 + r] = acc;
+            for (int q = 0; q < j; ++q) acc = fma(lev[r][r + q], h[q], acc);
+            a[r] = acc;
         }
+        // binom(K,r) for r = K-1 .. 0
+#pragma unroll
+        for (int r = K - 1; r >= 1; --r) {
+            binom = binom * (double)(r + 1) / (double)(K - r);
+            a[r] *= binom;
+        }
+        double2 *rl = reinterpret_cast<double2 *>(rec + (size_t)li * kRecD);
+        double v[8];
+        v[0] = x;
+#pragma unroll
+        for (int r = 0; r <= K; ++r) v[1 + r] = a[r];
+#pragma unroll
+        for (int r = K + 2; r < 8; ++r) v[r] = 0.0;
+#pragma unroll
+        for (int q = 0; q < (K + 3) / 2; ++q) rl[q] = make_double2(v[2 * q], v[2 * q + 1]);
     }
     __syncwarp();
 }
 
-constexpr int kUnroll = 4;   // independent points per lane per group (instruction-level parallelism)
-constexpr int kXTile = 256;  // evaluation points per TMA tile (2 KB), double buffered per warp
 
-// Evaluate one group of kUnroll points per lane (indices ibase + 32*u) and store the results.
-template <int K, int MODE, bool PLAIN, bool ALLLIVE>
-__device__ __forceinline__ void eval_group(const SplevParams &p, const double *ts, const double *cs,
-                                           const double *rec, const unsigned short *grid, int gcells, double tb,
-                                           double te, double inv_h, int nk1, double (&arg)[kUnroll],
-                                           const bool (&live)[kUnroll], double *yg, int *lg,
-                                           int ibase, bool &out_of_range)
+// ---------------------------------------------------------------------------------------------
+// shared pieces of the two kernels
+// ---------------------------------------------------------------------------------------------
+
+// out-of-support policy (core:17864-17877): returns true when the point's value is forced to 0
+__device__ __forceinline__ bool apply_policy(int e, double tb, double te, double &arg, bool live,
+                                             bool &out_of_range)
+{
+    if (arg < tb || arg > te) {
+        if (e == 1) return true;
+        if (e == 2) out_of_range = out_of_range || live;
+        else if (e == 3) arg = fmax(fmin(arg, te), tb);
+    }
+    return false;
+}
+
+// Lookup-grid construction over [t(k+1), t(n-k)].  Each lane owns the knot intervals l = k1+lane,
+// k1+lane+32, ... and fills the cells whose (widened) left edge falls into [t(l), t(l+1)): cell
+// boundaries come from one monotone function of the knot, so the ranges of neighbouring lanes
+// tile the grid.  A cell that may hold two or more knots is flagged (the single predicated step
+// of the evaluation cannot resolve it: the reference's walk is taken).  Edges are widened by
+// 1e-6 of a cell so that rounding in the cell index can never un-flag a cell.
+template <int K, bool FASTCELLS>
+__device__ __forceinline__ void build_grid(const double *ts, int n, void *grid, int &gcells,
+                                           double &inv_h, int lane)
 {
     constexpr int K1 = K + 1;
-    bool zero[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) zero[u] = false;
-    if (!PLAIN) {
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (arg[u] < tb || arg[u] > te) {  // core:17864-17877
-                if (p.e == 1) zero[u] = true;
-                else if (p.e == 2) out_of_range = out_of_range || live[u];
-                else if (p.e == 3) arg[u] = fmax(fmin(arg[u], te), tb);
-            }
-        }
-    }
-    int l[kUnroll];
-    double sp[kUnroll];
-    if (MODE == 1) {
-        // FAST: one 64-byte record per interval {t(l), t(l+1), a0..a5}; the lookup grid lands in
-        // the interval of the cell's left edge, a predicated single step covers one knot inside
-        // the cell, the reference's own walk handles flagged cells (several knots) and edge rounding
-        const double goff = -tb * inv_h;
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            int g = __double2int_rz(fma(arg[u], inv_h, goff));
-            g = max(0, min(g, gcells - 1));
-            l[u] = grid[g];
-        }
-        double tl[kUnroll];
-        bool slow = false;
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const bool cplx = (l[u] >> 15) != 0;
-            const int l0 = l[u] & 0x7fff;
-            const double2 tt = reinterpret_cast<const double2 *>(rec + (size_t)(l0 - K1) * 8)[0];
-            const bool step = (arg[u] >= tt.y) && (l0 < nk1);
-            l[u] = l0 + (step ? 1 : 0);
-            tl[u] = step ? tt.y : tt.x;
-            slow = slow || cplx || (arg[u] < tt.x && l0 > K1);
-        }
-        if (__any_sync(FULL, slow)) {
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                int ll = l[u];
-                while (ll > K1 && arg[u] < ts[ll - 1]) --ll;
-                while (ll < nk1 && arg[u] >= ts[ll]) ++ll;
-                l[u] = ll;
-                tl[u] = ts[ll - 1];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const double uu = arg[u] - tl[u];
-            const double2 *rp = reinterpret_cast<const double2 *>(rec + (size_t)(l[u] - K1) * 8);
-            const double2 a01 = rp[1], a23 = rp[2], a45 = rp[3];
-            const double a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
-            double v = a[K];
-#pragma unroll
-            for (int r = K - 1; r >= 0; --r) v = fma(v, uu, a[r]);
-            sp[u] = v;
-        }
-    } else {
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) l[u] = locate(ts, grid, gcells, tb, inv_h, K1, nk1, arg[u]);
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) sp[u] = eval_exact<K>(ts, cs, l[u], arg[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-        const int i = ibase + 32 * u;
-        if (ALLLIVE || live[u]) {
-            if (PLAIN) {
-                yg[i] = sp[u];
+    const int nk1 = n - K1;
+    const int nint = nk1 - K1 + 1;
+    gcells = splev_grid_cells(nint);
+    const double tb = ts[K1 - 1], te = ts[nk1];
+    const double span = te - tb;
+    inv_h = (span > 0.0) ? (double)gcells / span : 0.0;
+    const double hcell = span / (double)gcells;
+    auto bnd = [&](int l) -> int {  // first cell whose left edge is >= t(l)
+        if (l <= K1) return 0;
+        if (l > nk1) return gcells;
+        const double v = (ts[l - 1] - tb) * inv_h + 1e-6;
+        const int c = __double2int_ru(v);
+        return max(0, min(c, gcells));
+    };
+    for (int li = lane; li < nint; li += 32) {
+        const int l = K1 + li;
+        const int g0 = bnd(l), g1 = bnd(l + 1);
+        const double t2 = (l + 2 <= nk1) ? ts[l + 1] : 1.79e308;  // t(l+2), if stepping twice is possible
+        const double t1 = (l < nk1) ? ts[l] : __longlong_as_double(0x7ff0000000000000LL);
+        for (int gI = g0; gI < g1; ++gI) {
+            const double right = tb + ((double)(gI + 1) + 1e-6) * hcell;
+            const bool flag = right >= t2;
+            if (FASTCELLS) {
+                reinterpret_cast<double2 *>(grid)[gI] = make_double2(
+                    t1, __hiloint2double(l | (flag ? (int)0x80000000 : 0), li * kRecD * 8));
             } else {
-                yg[i] = zero[u] ? 0.0 : sp[u];
-                if (lg) lg[i] = zero[u] ? 0 : l[u];
+                reinterpret_cast<unsigned short *>(grid)[gI] = (unsigned short)(l | (flag ? (1 << 15) : 0));
             }
         }
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// EXACT mode
+// ---------------------------------------------------------------------------------------------
 // PLAIN: e == OUTSIDE_EXTRAPOLATE and no interval-index output -- no per-point policy code.
-template <int K, int MODE, bool PLAIN>
-__global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
-    splev_kernel(SplevParams p, int smem_ld)
+template <int K, bool PLAIN>
+__global__ void __launch_bounds__(kSplevWarps * 32, 2) splev_kernel(SplevParams p, int smem_ld)
 {
     constexpr int K1 = K + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    const int per_warp = splev_smem_doubles(MODE, K, smem_ld);
+    const int per_warp = splev_smem_doubles(0, K, smem_ld);
     uint64_t *mbars = reinterpret_cast<uint64_t *>(smem_raw);
-    double *base = reinterpret_cast<double *>(smem_raw + 32 * kSplevWarps) + (size_t)warp * per_warp;
-    auto tsb = [&](int b) { return base + (size_t)(2 * b) * smem_ld; };      // (t, c) buffer b
+    double *base = reinterpret_cast<double *>(smem_raw + 8 * kMbarPerWarp * kSplevWarps) + (size_t)warp * per_warp;
+    auto tsb = [&](int b) { return base + (size_t)(2 * b) * smem_ld; };  // (t, c) buffer b
     auto csb = [&](int b) { return base + (size_t)(2 * b + 1) * smem_ld; };
-    double *dlev = base + 4 * smem_ld;
-    double *rc = base + (size_t)(4 + K) * smem_ld;
-    double *rec = base + (size_t)(4 + 2 * K) * smem_ld;
-    double *after = base + ((MODE == 1) ? smem_ld * (4 + K + 8 + K) - 8 * (2 * K + 1) : smem_ld * 4);
+    unsigned short *grid = reinterpret_cast<unsigned short *>(base + 4 * smem_ld);
     double *ts = tsb(0), *cs = csb(0);
     int tbuf = 0;           // table buffer holding the current spline
     long long staged = -1;  // spline whose tables were prefetched into buffer 1-tbuf (TMA in flight)
-    double *xs = after;                                         // [2][kXTile] evaluation points
-    unsigned short *grid = reinterpret_cast<unsigned short *>(after + 2 * kXTile);  // lookup grid
-    uint64_t *mbar = mbars + warp * 4;                          // [0] tables, [1..2] x tiles
+    uint64_t *mbar = mbars + warp * kMbarPerWarp;
     if (lane == 0) {
         mbar_init(mbar, 1);
-        mbar_init(mbar + 1, 1);
-        mbar_init(mbar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncwarp();
-    uint32_t phase = 0, xphase0 = 0, xphase1 = 0;
+    uint32_t phase = 0;
 
     const long long gwarp = (long long)blockIdx.x * wpb + warp;
     const long long nwarps = (long long)gridDim.x * wpb;
@@ -357,23 +354,6 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
             }
         }
         const double *xg = p.x + j * p.m;
-        // TMA tiles need 16-byte aligned rows of even length; otherwise plain loads
-        // (EXACT mode is FP64-bound, not latency-bound: it keeps the register-pipelined loads)
-        const bool xt_ok = (MODE == 1) && ((((uintptr_t)xg) & 15) == 0) && ((p.m & 1) == 0);
-        const int ntile = (p.m + kXTile - 1) / kXTile;
-        auto issue_tile = [&](int t) {
-            if (lane == 0) {
-                const int cnt = min(kXTile, p.m - t * kXTile);
-                uint64_t *mb = mbar + 1 + (t & 1);
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                mbar_expect_tx(mb, (uint32_t)cnt * 8u);
-                tma_load_1d(xs + (t & 1) * kXTile, xg + (size_t)t * kXTile, (uint32_t)cnt * 8u, mb);
-            }
-        };
-        if (xt_ok) {  // the points start streaming in while the spline's tables are built
-            issue_tile(0);
-            if (ntile > 1) issue_tile(1);
-        }
         if (tj != cached) {
             n = p.n[tj];
             __syncwarp();  // previous spline's readers are done with their tables
@@ -408,8 +388,7 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
             ts = tsb(tbuf);
             cs = csb(tbuf);
             staged = -1;
-            // start fetching the next spline's tables into the other buffer
-            {
+            {  // start fetching the next spline's tables into the other buffer
                 const long long jn = j + nwarps;
                 if (!p.nshared && jn < p.nspl) {
                     const int nn = p.n[jn];
@@ -420,39 +399,267 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
                 }
             }
             __syncwarp();
-            // lookup grid over [t(k+1), t(n-k)]: grid[g] = interval of the cell's left edge;
-            // bit 15 flags a cell that may hold two or more knots (the single predicated step of
-            // the evaluation loop cannot resolve it: the full walk is taken).  Edges are widened
-            // by 1e-6 of a cell so that rounding in the cell index can never un-flag a cell.
-            {
-                const int nk1_ = n - K1;
-                const int nint = nk1_ - K1 + 1;
-                gcells = splev_grid_cells(nint);
-                const double tb_ = ts[K1 - 1], te_ = ts[nk1_];
-                const double span = te_ - tb_;
-                inv_h = (span > 0.0) ? (double)gcells / span : 0.0;
-                const double hcell = span / (double)gcells;
-                // Each lane owns knot intervals l = k1+lane, k1+lane+32, ... and fills the cells whose
-                // (widened) left edge falls into [t(l), t(l+1)): cell boundaries come from one
-                // monotone function of the knot, so the ranges of neighbouring lanes tile the grid.
-                auto bnd = [&](int l) -> int {  // first cell whose left edge is >= t(l)
-                    if (l <= K1) return 0;
-                    if (l > nk1_) return gcells;
-                    const double v = (ts[l - 1] - tb_) * inv_h + 1e-6;
-                    int c = __double2int_ru(v);
-                    return max(0, min(c, gcells));
-                };
-                for (int li = lane; li < nint; li += 32) {
-                    const int l = K1 + li;
-                    const int g0 = bnd(l), g1 = bnd(l + 1);
-                    const double t2 = (l + 2 <= nk1_) ? ts[l + 1] : 1.79e308;  // t(l+2), if stepping twice is possible
-                    for (int gI = g0; gI < g1; ++gI) {
-                        const double right = tb_ + ((double)(gI + 1) + 1e-6) * hcell;
-                        grid[gI] = (unsigned short)(l | ((right >= t2) ? (1 << 15) : 0));
-                    }
+            build_grid<K, false>(ts, n, grid, gcells, inv_h, lane);
+            __syncwarp();
+            cached = (int)tj;
+        }
+        const int nk1 = n - K1;
+        const double tb = ts[K1 - 1], te = ts[nk1];
+        double *yg = p.y + j * p.m;
+        int *lg = p.lidx ? p.lidx + j * p.m : nullptr;
+        bool out_of_range = false;
+        // software pipeline in registers: the loads of the next group are in flight while the
+        // current group is evaluated (the kernel is FP64-bound, not latency-bound)
+        double nxt[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int i = lane + 32 * u;
+            nxt[u] = (i < p.m) ? xg[i] : tb;
+        }
+        for (int i0 = lane; i0 < p.m; i0 += 32 * kUnroll) {
+            double arg[kUnroll];
+            bool live[kUnroll], zero[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int i = i0 + 32 * u;
+                live[u] = i < p.m;
+                arg[u] = nxt[u];
+                const int inx = i + 32 * kUnroll;
+                nxt[u] = (inx < p.m) ? xg[inx] : tb;
+                zero[u] = PLAIN ? false : apply_policy(p.e, tb, te, arg[u], live[u], out_of_range);
+            }
+            int l[kUnroll];
+            double sp[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) l[u] = locate(ts, grid, gcells, tb, inv_h, K1, nk1, arg[u]);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) sp[u] = eval_exact<K>(ts, cs, l[u], arg[u]);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int i = i0 + 32 * u;
+                if (live[u]) {
+                    yg[i] = zero[u] ? 0.0 : sp[u];
+                    if (!PLAIN && lg) lg[i] = zero[u] ? 0 : l[u];
                 }
             }
-            if (MODE == 1) build_local_polys<K>(ts, cs, n, smem_ld, dlev, rec, rc, lane);
+        }
+        if (p.ier) {
+            const bool any_out = __any_sync(FULL, out_of_range);
+            if (lane == 0) p.ier[j] = any_out ? IER_RANGE : IER_OK;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FAST mode
+// ---------------------------------------------------------------------------------------------
+// Evaluate one group of kUnroll points per lane (indices ibase + 32*u) from the interval records
+// and store the results.  The lookup cell gives the interval l0 of the cell's left edge, the next
+// knot and the byte offset of l0's record; one compare steps over a knot inside the cell.  Cells
+// that may hold two or more knots are flagged and take the reference's own walk
+// (core:17880-17887).  (arg - tb) * inv_h is computed exactly as in the grid construction, with
+// a relative error ~1e-16 << the 1e-6 cell widening used there.
+template <int K, bool PLAIN, bool ALLLIVE>
+__device__ __forceinline__ void fast_group(const SplevParams &p, const double *ts, const double *rec,
+                                           const double2 *cells, int gcells, double tb, double te,
+                                           double inv_h, int nk1, double (&arg)[kUnroll],
+                                           const bool (&live)[kUnroll], double *yg, int *lg, int ibase,
+                                           bool &out_of_range)
+{
+    constexpr int K1 = K + 1;
+    bool zero[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+        zero[u] = PLAIN ? false : apply_policy(p.e, tb, te, arg[u], live[u], out_of_range);
+    int off[kUnroll], lf[kUnroll];
+    int anyflag = 0;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        int g = __double2int_rz((arg[u] - tb) * inv_h);
+        g = max(0, min(g, gcells - 1));
+        const double2 cv = cells[g];
+        const bool step = arg[u] >= cv.x;
+        off[u] = __double2loint(cv.y) + (step ? kRecD * 8 : 0);
+        lf[u] = __double2hiint(cv.y) + (step ? 1 : 0);
+        anyflag |= lf[u];
+    }
+    if (__any_sync(FULL, anyflag < 0)) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (lf[u] < 0) {
+                int ll = lf[u] & 0x7fffffff;
+                while (ll > K1 && arg[u] < ts[ll - 1]) --ll;
+                while (ll < nk1 && arg[u] >= ts[ll]) ++ll;
+                lf[u] = ll;
+                off[u] = (ll - K1) * (kRecD * 8);
+            }
+        }
+    }
+    double sp[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const double2 *rp = reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(rec) + off[u]);
+        double a[8];
+#pragma unroll
+        for (int q = 0; q < (K + 3) / 2; ++q) {
+            const double2 v = rp[q];
+            a[2 * q] = v.x;
+            a[2 * q + 1] = v.y;
+        }
+        const double uu = arg[u] - a[0];
+        double v = a[1 + K];
+#pragma unroll
+        for (int r = K - 1; r >= 0; --r) v = fma(v, uu, a[1 + r]);
+        sp[u] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const int i = ibase + 32 * u;
+        if (ALLLIVE || live[u]) {
+            if (PLAIN) {
+                yg[i] = sp[u];
+            } else {
+                yg[i] = zero[u] ? 0.0 : sp[u];
+                if (lg) lg[i] = zero[u] ? 0 : lf[u];
+            }
+        }
+    }
+}
+
+template <int K, bool PLAIN>
+__global__ void __launch_bounds__(kFastWarps * 32, kFastBlocks) splev_fast_kernel(SplevParams p, int smem_ld)
+{
+    constexpr int K1 = K + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int per_warp = splev_smem_doubles(1, K, smem_ld);
+    uint64_t *mbars = reinterpret_cast<uint64_t *>(smem_raw);
+    double *base = reinterpret_cast<double *>(smem_raw + 8 * kMbarPerWarp * kSplevWarps) + (size_t)warp * per_warp;
+    auto tsb = [&](int b) { return base + (size_t)(2 * b) * smem_ld; };  // (t, c) buffer b
+    auto csb = [&](int b) { return base + (size_t)(2 * b + 1) * smem_ld; };
+    double *rec = base + 4 * smem_ld;  // interval records
+    const int nintmax = (smem_ld - 2 * K - 1 > 1) ? smem_ld - 2 * K - 1 : 1;
+    double2 *cells = reinterpret_cast<double2 *>(rec + ((kRecD * nintmax + 1) & ~1));
+    double *xs = reinterpret_cast<double *>(cells + splev_grid_cells(smem_ld - 2 * K - 1));  // [kNBuf][kTilePts]
+    double *ts = tsb(0), *cs = csb(0);
+    int tbuf = 0;           // table buffer holding the current spline
+    long long staged = -1;  // spline whose tables were prefetched into buffer 1-tbuf (TMA in flight)
+    uint64_t *mbar = mbars + warp * kMbarPerWarp;  // [0] tables, [1 + slot] x tiles
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b <= kNBuf; ++b) mbar_init(mbar + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+
+    const long long gwarp = (long long)blockIdx.x * wpb + warp;
+    const long long nwarps = (long long)gridDim.x * wpb;
+
+    // ---- the point stream: tiles of kTilePts points, spline after spline, kNBuf tiles ahead.
+    // TMA needs 16-byte aligned rows of even length (uniform for the launch); otherwise the
+    // points are loaded straight into registers.
+    const bool xt_ok = ((((uintptr_t)p.x) & 15) == 0) && ((p.m & 1) == 0);
+    const int ntile = (p.m + kTilePts - 1) / kTilePts;
+    long long pj = gwarp;  // producer cursor: next (spline, tile) to request
+    int pt = 0;
+    int slot = 0;          // ring slot of the next tile to consume == next slot to refill
+    uint32_t xphase = 0;   // phase bit per slot
+    auto produce = [&]() { // request the next tile of the stream into `slot`, then advance the ring
+        if (pj < p.nspl) {
+            if (lane == 0) {
+                const int cnt = min(kTilePts, p.m - pt * kTilePts);
+                uint64_t *mb = mbar + 1 + slot;
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                mbar_expect_tx(mb, (uint32_t)cnt * 8u);
+                tma_load_1d(xs + slot * kTilePts, p.x + pj * p.m + (size_t)pt * kTilePts, (uint32_t)cnt * 8u, mb);
+            }
+            if (++pt == ntile) {
+                pt = 0;
+                pj += nwarps;
+            }
+        }
+        slot = (slot + 1) & (kNBuf - 1);
+    };
+    auto consume_wait = [&]() {
+        mbar_wait(mbar + 1 + slot, (xphase >> slot) & 1u);
+        xphase ^= 1u << slot;
+    };
+    if (xt_ok) {
+#pragma unroll
+        for (int b = 0; b < kNBuf; ++b) produce();
+    }
+
+    auto tables_tma_ok = [&](long long q, int nq) -> bool {
+        const double *tg = p.t + q * p.ldt, *cg = p.c + q * p.ldt;
+        return ((((uintptr_t)tg) | ((uintptr_t)cg)) & 15) == 0 && (((nq + 1) & ~1) <= p.ldt);
+    };
+    auto issue_tables = [&](long long q, int nq, int buf) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(((nq + 1) & ~1) * 8);
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_expect_tx(mbar, 2 * bytes);
+            tma_load_1d(tsb(buf), p.t + q * p.ldt, bytes, mbar);
+            tma_load_1d(csb(buf), p.c + q * p.ldt, bytes, mbar);
+        }
+    };
+
+    int cached = -1;
+    int n = 0, gcells = 32;
+    double inv_h = 0.0;
+    // knot counts are read one spline ahead so that their DRAM latency is never on the critical path
+    int n_cur = (gwarp < p.nspl) ? p.n[p.nshared ? 0 : gwarp] : 0;
+    int n_nxt = (!p.nshared && gwarp + nwarps < p.nspl) ? p.n[gwarp + nwarps] : 0;
+    for (long long j = gwarp; j < p.nspl; j += nwarps) {
+        const long long tj = p.nshared ? 0 : j;
+        const int nj = n_cur;
+        const int n_fut = (!p.nshared && j + 2 * nwarps < p.nspl) ? p.n[j + 2 * nwarps] : 0;
+        if (nj < 2 * K1 || nj > p.ldt) {
+            // a knot count the row cannot hold, or too small for degree K, is invalid input
+            // (splev itself would read out of bounds): flag the spline, drain its tiles, skip it
+            if (p.ier && lane == 0) p.ier[j] = IER_INPUT;
+            if (xt_ok) {
+                for (int t = 0; t < ntile; ++t) {
+                    consume_wait();
+                    __syncwarp();
+                    produce();
+                }
+            }
+            if (!p.nshared) { n_cur = n_nxt; n_nxt = n_fut; }
+            continue;
+        }
+        if (tj != cached) {
+            n = nj;
+            __syncwarp();  // previous spline's readers are done with their tables
+            if (staged == tj) {  // prefetched while the previous spline was evaluated
+                tbuf ^= 1;
+                mbar_wait(mbar, phase);
+                phase ^= 1;
+            } else if (tables_tma_ok(tj, n)) {
+                issue_tables(tj, n, tbuf);
+                mbar_wait(mbar, phase);
+                phase ^= 1;
+            } else {
+                const double *tg = p.t + tj * p.ldt, *cg = p.c + tj * p.ldt;
+                for (int i = lane; i < n; i += 32) {
+                    tsb(tbuf)[i] = tg[i];
+                    csb(tbuf)[i] = cg[i];
+                }
+            }
+            ts = tsb(tbuf);
+            cs = csb(tbuf);
+            staged = -1;
+            {  // start fetching the next spline's tables into the other buffer
+                const long long jn = j + nwarps;
+                if (!p.nshared && jn < p.nspl && n_nxt >= 2 * K1 && n_nxt <= p.ldt && tables_tma_ok(jn, n_nxt)) {
+                    issue_tables(jn, n_nxt, tbuf ^ 1);
+                    staged = jn;
+                }
+            }
+            __syncwarp();
+            build_grid<K, true>(ts, n, cells, gcells, inv_h, lane);
+            build_records<K>(ts, cs, n, rec, lane);
             __syncwarp();
             cached = (int)tj;
         }
@@ -463,50 +670,32 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
         bool out_of_range = false;
         if (xt_ok) {
             for (int t = 0; t < ntile; ++t) {
-                const int buf = t & 1;
-                if (buf == 0) { mbar_wait(mbar + 1, xphase0); xphase0 ^= 1; }
-                else { mbar_wait(mbar + 2, xphase1); xphase1 ^= 1; }
-                const int cnt = min(kXTile, p.m - t * kXTile);
-                const double *xt = xs + buf * kXTile;
-                if (cnt == kXTile) {  // full tile: no per-point bounds predicates
+                consume_wait();
+                const double *xt = xs + slot * kTilePts;
+                const int cnt = p.m - t * kTilePts;  // points left, this tile included
+                double arg[kUnroll];
+                bool live[kUnroll];
 #pragma unroll
-                    for (int gq = 0; gq < kXTile / (32 * kUnroll); ++gq) {
-                        const int il = gq * 32 * kUnroll + lane;
-                        double arg[kUnroll];
-                        bool live[kUnroll];
-#pragma unroll
-                        for (int u = 0; u < kUnroll; ++u) {
-                            live[u] = true;
-                            arg[u] = xt[il + 32 * u];
-                        }
-                        eval_group<K, MODE, PLAIN, true>(p, ts, cs, rec, grid, gcells, tb, te, inv_h,
-                                                         nk1, arg, live, yg, lg, t * kXTile + il,
-                                                         out_of_range);
-                    }
+                for (int u = 0; u < kUnroll; ++u) {
+                    live[u] = lane + 32 * u < cnt;
+                    arg[u] = xt[lane + 32 * u];  // stale data beyond cnt is replaced below
+                }
+                __syncwarp();  // every lane has read the tile: hand the slot back to the stream
+                produce();
+                if (cnt >= kTilePts) {
+                    fast_group<K, PLAIN, true>(p, ts, rec, cells, gcells, tb, te, inv_h, nk1, arg, live, yg,
+                                               lg, t * kTilePts + lane, out_of_range);
                 } else {
 #pragma unroll
-                    for (int gq = 0; gq < kXTile / (32 * kUnroll); ++gq) {
-                        const int il = gq * 32 * kUnroll + lane;
-                        if (il - lane < cnt) {  // uniform across the warp
-                            double arg[kUnroll];
-                            bool live[kUnroll];
-#pragma unroll
-                            for (int u = 0; u < kUnroll; ++u) {
-                                live[u] = il + 32 * u < cnt;
-                                arg[u] = live[u] ? xt[il + 32 * u] : tb;
-                            }
-                            eval_group<K, MODE, PLAIN, false>(p, ts, cs, rec, grid, gcells, tb, te,
-                                                              inv_h, nk1, arg, live, yg, lg,
-                                                              t * kXTile + il, out_of_range);
-                        }
-                    }
+                    for (int u = 0; u < kUnroll; ++u)
+                        if (!live[u]) arg[u] = tb;
+                    fast_group<K, PLAIN, false>(p, ts, rec, cells, gcells, tb, te, inv_h, nk1, arg, live, yg,
+                                                lg, t * kTilePts + lane, out_of_range);
                 }
-                __syncwarp();  // every lane is done with this buffer
-                if (t + 2 < ntile) issue_tile(t + 2);
             }
         } else {
-            // software pipeline in registers: the loads of the next group are in flight while
-            // the current group is evaluated
+            // unaligned rows: software pipeline in registers, one group ahead
+            const double *xg = p.x + j * p.m;
             double nxt[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
@@ -524,14 +713,15 @@ __global__ void __launch_bounds__(kSplevWarps * 32, (MODE == 1) ? 3 : 2)
                     const int inx = i + 32 * kUnroll;
                     nxt[u] = (inx < p.m) ? xg[inx] : tb;
                 }
-                eval_group<K, MODE, PLAIN, false>(p, ts, cs, rec, grid, gcells, tb, te, inv_h, nk1,
-                                                  arg, live, yg, lg, i0, out_of_range);
+                fast_group<K, PLAIN, false>(p, ts, rec, cells, gcells, tb, te, inv_h, nk1, arg, live, yg, lg,
+                                            i0, out_of_range);
             }
         }
         if (p.ier) {
             const bool any_out = __any_sync(FULL, out_of_range);
             if (lane == 0) p.ier[j] = any_out ? IER_RANGE : IER_OK;
         }
+        if (!p.nshared) { n_cur = n_nxt; n_nxt = n_fut; }
     }
 }
 
@@ -542,19 +732,23 @@ cudaError_t launch_splev(const SplevParams &p, int nsm, cudaStream_t stream)
     if (p.nspl <= 0) return cudaSuccess;
     const int smem_ld = (p.ldt + 1) & ~1;  // keep every per-warp region 16 B aligned
     const size_t per_warp = (size_t)splev_smem_doubles(p.mode, p.k, smem_ld) * sizeof(double);
-    int wpb = kSplevWarps;
-    while (wpb > 1 && 32 * kSplevWarps + per_warp * wpb > 100 * 1024) wpb >>= 1;
-    const size_t smem = 32 * kSplevWarps + per_warp * wpb;
+    const size_t header = 8 * kMbarPerWarp * kSplevWarps;
+    int wpb = (p.mode == 1) ? kFastWarps : kSplevWarps;
+    const int reg_blocks = (p.mode == 1) ? kFastBlocks : 2;  // CTAs/SM the register budget allows
+    // keep reg_blocks CTAs resident if the tables allow it (227 KB per SM, 1 KB reserved per CTA)
+    while (wpb > 1 && header + per_warp * wpb > (size_t)(227 * 1024) / reg_blocks - 1024) wpb >>= 1;
+    const size_t smem = header + per_warp * wpb;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;  // knot vectors beyond ~4000 entries
     long long blocks = ((long long)p.nspl + wpb - 1) / wpb;
-    const long long resident = (long long)((228 * 1024) / (smem + 1024));  // 1 KB/CTA is reserved
-    const long long max_blocks = (long long)nsm * (resident < 1 ? 1 : (resident > 8 ? 8 : resident));
+    const long long resident = (long long)((228 * 1024) / (smem + 1024));
+    const long long max_blocks =
+        (long long)nsm * (resident < 1 ? 1 : (resident > reg_blocks ? reg_blocks : resident));
     if (blocks > max_blocks) blocks = max_blocks;
 #define FPB_LAUNCH_SPLEV(KK)                                                                       \
     do {                                                                                           \
         const bool plain = (p.e == 0 && p.lidx == nullptr);                                       \
-        auto kern = (p.mode == 1) ? (plain ? splev_kernel<KK, 1, true> : splev_kernel<KK, 1, false>)\
-                                  : (plain ? splev_kernel<KK, 0, true> : splev_kernel<KK, 0, false>);\
+        auto kern = (p.mode == 1) ? (plain ? splev_fast_kernel<KK, true> : splev_fast_kernel<KK, false>) \
+                                  : (plain ? splev_kernel<KK, true> : splev_kernel<KK, false>);   \
         cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                               (int)smem);                                          \
         if (e_ != cudaSuccess) return e_;                                                          \
