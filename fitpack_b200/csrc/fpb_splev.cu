@@ -96,9 +96,14 @@ __host__ __device__ inline int splev_grid_cells(int nint)
 // where l0 is the interval of the cell's (widened) left edge.
 constexpr int kRecD = 10;
 constexpr int kUnroll = 4;              // independent points per lane per group (instruction-level parallelism)
-constexpr int kTilePts = 32 * kUnroll;  // FAST: evaluation points per TMA tile (1 KB) = one group
+constexpr int kGroupPts = 32 * kUnroll;  // points one warp evaluates per group
+#ifndef FPB_SPLEV_TILE_GROUPS
+#define FPB_SPLEV_TILE_GROUPS 2
+#endif
+constexpr int kTileGroups = FPB_SPLEV_TILE_GROUPS;
+constexpr int kTilePts = kGroupPts * kTileGroups;  // FAST: evaluation points per TMA tile (2 KB)
 #ifndef FPB_SPLEV_NBUF
-#define FPB_SPLEV_NBUF 4
+#define FPB_SPLEV_NBUF 2
 #endif
 constexpr int kNBuf = FPB_SPLEV_NBUF;   // FAST: tiles in flight per warp (ring, power of two)
 constexpr int kMbarPerWarp = 16;        // mbarrier slots per warp: [0] tables, [1..kNBuf] tiles
@@ -562,22 +567,29 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastBlocks) splev_fast_kerne
     // points are loaded straight into registers.
     const bool xt_ok = ((((uintptr_t)p.x) & 15) == 0) && ((p.m & 1) == 0);
     const int ntile = (p.m + kTilePts - 1) / kTilePts;
-    long long pj = gwarp;  // producer cursor: next (spline, tile) to request
-    int pt = 0;
+    // producer cursor: where the next tile starts, how many points of that spline are left, and
+    // how many splines of this warp's sequence have not been requested completely
+    const double *psrc = p.x + gwarp * p.m;
+    int prem = p.m;
+    long long pleft = (gwarp < p.nspl) ? (p.nspl - gwarp + nwarps - 1) / nwarps : 0;
+    const long long pjump = (nwarps - 1) * (long long)p.m;
     int slot = 0;          // ring slot of the next tile to consume == next slot to refill
     uint32_t xphase = 0;   // phase bit per slot
     auto produce = [&]() { // request the next tile of the stream into `slot`, then advance the ring
-        if (pj < p.nspl) {
+        if (pleft > 0) {
+            const int cnt = min(kTilePts, prem);
             if (lane == 0) {
-                const int cnt = min(kTilePts, p.m - pt * kTilePts);
                 uint64_t *mb = mbar + 1 + slot;
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                 mbar_expect_tx(mb, (uint32_t)cnt * 8u);
-                tma_load_1d(xs + slot * kTilePts, p.x + pj * p.m + (size_t)pt * kTilePts, (uint32_t)cnt * 8u, mb);
+                tma_load_1d(xs + slot * kTilePts, psrc, (uint32_t)cnt * 8u, mb);
             }
-            if (++pt == ntile) {
-                pt = 0;
-                pj += nwarps;
+            psrc += cnt;
+            prem -= cnt;
+            if (prem == 0) {
+                psrc += pjump;
+                prem = p.m;
+                --pleft;
             }
         }
         slot = (slot + 1) & (kNBuf - 1);
@@ -673,24 +685,31 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastBlocks) splev_fast_kerne
                 consume_wait();
                 const double *xt = xs + slot * kTilePts;
                 const int cnt = p.m - t * kTilePts;  // points left, this tile included
-                double arg[kUnroll];
-                bool live[kUnroll];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    live[u] = lane + 32 * u < cnt;
-                    arg[u] = xt[lane + 32 * u];  // stale data beyond cnt is replaced below
-                }
-                __syncwarp();  // every lane has read the tile: hand the slot back to the stream
-                produce();
-                if (cnt >= kTilePts) {
-                    fast_group<K, PLAIN, true>(p, ts, rec, cells, gcells, tb, te, inv_h, nk1, arg, live, yg,
-                                               lg, t * kTilePts + lane, out_of_range);
-                } else {
+                for (int gq = 0; gq < kTileGroups; ++gq) {
+                    const int gcnt = cnt - gq * kGroupPts;  // points left from this group on
+                    double arg[kUnroll];
+                    bool live[kUnroll];
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u)
-                        if (!live[u]) arg[u] = tb;
-                    fast_group<K, PLAIN, false>(p, ts, rec, cells, gcells, tb, te, inv_h, nk1, arg, live, yg,
-                                                lg, t * kTilePts + lane, out_of_range);
+                    for (int u = 0; u < kUnroll; ++u) {
+                        live[u] = lane + 32 * u < gcnt;
+                        arg[u] = xt[gq * kGroupPts + lane + 32 * u];  // stale beyond cnt: replaced below
+                    }
+                    if (gq == kTileGroups - 1) {
+                        __syncwarp();  // every lane has read the tile: hand the slot back to the stream
+                        produce();
+                    }
+                    const int ibase = t * kTilePts + gq * kGroupPts + lane;
+                    if (gcnt >= kGroupPts) {
+                        fast_group<K, PLAIN, true>(p, ts, rec, cells, gcells, tb, te, inv_h, nk1, arg, live,
+                                                   yg, lg, ibase, out_of_range);
+                    } else if (gcnt > 0) {
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u)
+                            if (!live[u]) arg[u] = tb;
+                        fast_group<K, PLAIN, false>(p, ts, rec, cells, gcells, tb, te, inv_h, nk1, arg, live,
+                                                    yg, lg, ibase, out_of_range);
+                    }
                 }
             }
         } else {
