@@ -65,6 +65,16 @@ SYMBOLS = {
     "fp_splev_batch_c": (_I32, [_I32, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _I32, _I32, _I32, _VP,
                                 _I32]),
     "fpb_transpose_dev": (_I32, [_VP, _VP, _I64, _VP, _I64, _I64, _I64]),
+    "fp_regrid_c": (None, [_I32, _I32, _VP, _I32, _VP, _VP, _F64, _F64, _F64, _F64, _I32, _I32, _F64,
+                           _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _I32, _VP]),
+    "fp_bispev_c": (_I32, [_VP, _I32, _VP, _I32, _VP, _I32, _I32, _VP, _I32, _VP, _I32, _VP, _VP,
+                           _I32, _VP, _I32]),
+    "fp_regrid_dev_c": (_I32, [_VP, _I32, _I32, _VP, _I32, _VP, _VP, _F64, _F64, _F64, _F64, _I32,
+                               _I32, _F64, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _VP,
+                               _I32, _VP]),
+    "fp_bispev_dev_c": (_I32, [_VP, _VP, _I32, _VP, _I32, _VP, _I32, _I32, _VP, _I32, _VP, _I32,
+                               _VP, _VP]),
+    "fpb_engine_grid_fpgrre_calls": (_I64, [_VP]),
 }
 
 _lib = None

@@ -51,6 +51,15 @@ class Engine:
         check(lib().fpb_engine_synchronize(self._h), "synchronize")
 
     @property
+    def handle(self):
+        """the fpb_engine* of the C-ABI (for the fitpack_b200.core calls that take engine=)"""
+        return self._h
+
+    @property
+    def grid_fpgrre_calls(self):
+        return lib().fpb_engine_grid_fpgrre_calls(self._h)
+
+    @property
     def launches(self):
         return lib().fpb_engine_launch_count(self._h)
 

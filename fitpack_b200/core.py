@@ -126,3 +126,75 @@ def splev_batch(t, n, c, k, x, e=OUTSIDE_EXTRAPOLATE, mode=0, ngpus=1):
                                 int(mode), _p(ier), int(ngpus))
     check(rc, "fp_splev_batch_c")
     return y, ier
+
+
+# ------------------------------------------------------------------ gridded surfaces (dims = 2)
+def regrid_lwrk(mx, my, kx, ky, nxest, nyest):
+    """minimum (lwrk, kwrk) of regrid at dims=2 (reference core:16789-16797)"""
+    maxm, maxnest, maxk1 = max(mx, my), max(nxest, nyest), max(kx, ky) + 1
+    maxk2 = maxk1 + 1
+    nkx, nky = nxest - kx - 1, nyest - ky - 1
+    mm = max(maxnest, maxm, my, nkx, nky)
+    lwrk = 4 + maxnest * 2 + maxm * maxk1 * 2 + 2 * maxnest * maxk2 * 2 + mm + 2 * nkx * my
+    kwrk = 3 + maxm * 2 + maxnest * 2
+    return lwrk, kwrk
+
+
+def regrid(iopt, x, y, z, xb, xe, yb, ye, kx, ky, s, nxest, nyest, nx=0, ny=0, tx=None, ty=None,
+           c=None, wrk=None, iwrk=None, engine=None):
+    """regrid (reference core:16732-16839, dims=2) through fp_regrid_c, or fp_regrid_dev_c when
+    `z` is a CUDA torch tensor (then `engine` is a fitpack_b200.batch.Engine).
+    tx, ty, c, wrk, iwrk are updated IN PLACE when given (pass them back for iopt=1).
+    Returns dict(nx, tx, ny, ty, c, fp, ier, wrk, iwrk)."""
+    x = _f64(x)
+    y = _f64(y)
+    mx, my = x.size, y.size
+    lw, kw = regrid_lwrk(mx, my, max(kx, 0), max(ky, 0), max(nxest, 0), max(nyest, 0))
+    tx = np.zeros(max(nxest, 1)) if tx is None else tx
+    ty = np.zeros(max(nyest, 1)) if ty is None else ty
+    c = np.zeros(max((nxest - kx - 1) * (nyest - ky - 1), 1)) if c is None else c
+    wrk = np.zeros(max(lw, 8)) if wrk is None else wrk
+    iwrk = np.zeros(max(kw, 8), dtype=np.int32) if iwrk is None else iwrk
+    nx_, ny_ = C.c_int32(int(nx)), C.c_int32(int(ny))
+    fp_, ier_ = C.c_double(0.0), C.c_int32(0)
+    tail = (float(xb), float(xe), float(yb), float(ye), int(kx), int(ky), float(s), int(nxest),
+            int(nyest), C.addressof(nx_), _p(tx), C.addressof(ny_), _p(ty), _p(c), C.addressof(fp_),
+            _p(wrk), int(wrk.size), _p(iwrk), int(iwrk.size), C.addressof(ier_))
+    if hasattr(z, "data_ptr"):  # torch tensor in HBM
+        if engine is None:
+            raise ValueError("regrid with a device tensor needs engine=")
+        assert z.is_cuda and z.is_contiguous() and z.numel() == mx * my
+        rc = lib().fp_regrid_dev_c(engine.handle, int(iopt), mx, _p(x), my, _p(y),
+                                   C.c_void_p(z.data_ptr()), *tail)
+        check(rc, "fp_regrid_dev_c")
+    else:
+        z = _f64(z).ravel()
+        assert z.size == mx * my
+        lib().fp_regrid_c(int(iopt), mx, _p(x), my, _p(y), _p(z), *tail)
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_regrid_c: %s" % lib().fpb_last_error().decode())
+    return dict(nx=nx_.value, tx=tx, ny=ny_.value, ty=ty, c=c, fp=fp_.value, ier=ier_.value, wrk=wrk,
+                iwrk=iwrk)
+
+
+def bispev(tx, nx, ty, ny, c, kx, ky, x, y, out=None, engine=None):
+    """bispev (reference core:424-458) through fp_bispev_c; `out`: optional CUDA torch tensor
+    [mx, my] to receive the values in HBM (fp_bispev_dev_c).  Returns (z, ier)."""
+    tx, ty, c, x, y = _f64(tx), _f64(ty), _f64(c), _f64(x), _f64(y)
+    mx, my = x.size, y.size
+    if out is not None:
+        ier_ = C.c_int32(0)
+        rc = lib().fp_bispev_dev_c(engine.handle, _p(tx), int(nx), _p(ty), int(ny), _p(c), int(kx),
+                                   int(ky), _p(x), mx, _p(y), my, C.c_void_p(out.data_ptr()),
+                                   C.addressof(ier_))
+        check(rc, "fp_bispev_dev_c")
+        return out, ier_.value
+    z = np.zeros(max(mx * my, 1))
+    lwrk = (kx + 1) * mx + (ky + 1) * my
+    wrk = np.zeros(max(lwrk, 1))
+    iwrk = np.zeros(max(mx + my, 1), dtype=np.int32)
+    ier = lib().fp_bispev_c(_p(tx), int(nx), _p(ty), int(ny), _p(c), int(kx), int(ky), _p(x), mx,
+                            _p(y), my, _p(z), _p(wrk), lwrk, _p(iwrk), mx + my)
+    if ier <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_bispev_c: %s" % lib().fpb_last_error().decode())
+    return z[:mx * my].reshape(mx, my), int(ier)

@@ -41,6 +41,11 @@ struct fpb_engine {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_fit[2] = {nullptr, nullptr};
     double h_aux[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    // gridded surfaces (fpb_regrid.cu): device tables, pinned read-back of the row/column sums
+    fpb::DevBuf grid[16];
+    double *grid_pinned = nullptr;
+    size_t grid_pinned_bytes = 0;
+    int64_t grid_fpgrre_calls = 0;
 };
 
 namespace fpb {

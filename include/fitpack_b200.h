@@ -224,6 +224,44 @@ int32_t fp_splev_batch_c(FP_SIZE nspl, const FP_REAL *t, const FP_SIZE *n, const
 int32_t fpb_transpose_dev(fpb_engine *eng, const FP_REAL *src, int64_t ld_src, FP_REAL *dst,
                           int64_t ld_dst, int64_t rows, int64_t cols);
 
+/* ---------------------------------------------------------- gridded surfaces -- */
+/*
+ * regrid / bispev, the dims = 2 case of the reference's gridded engine.
+ * Same names and argument lists as the reference's C binding:
+ *   fp_regrid_c  include/fitpack_core_c.h:165-171, src/fitpack_core_c.f90:253-290
+ *                -> regrid core:16732-16839, fpregr 12079-12303, fpgrre 7111-7360
+ *   fp_bispev_c  include/fitpack_core_c.h:209-211, src/fitpack_core_c.f90:404-415
+ *                -> bispev core:424-458, fpndsp 2160-2241
+ * z and c are flat row-major with x slowest: z[my*i + j], c[(ny-ky-1)*i + j].
+ * Workspace: lwrk/kwrk must satisfy the reference's minimum sizes (core:16789-16797), else
+ * ier=10; only wrk[0..3] (fp0, fpold, reduc) and iwrk[0..2] (lastdi, nplus) are used -- they
+ * are the state an iopt=1 continuation reads back, as in the reference.
+ * fp and the smoothing parameter are grid-wide sums: they agree with the reference to rounding
+ * (rel 1e-10 stated in the tests), n / knots / ier are the same discrete outputs.
+ */
+void fp_regrid_c(FP_SIZE iopt, FP_SIZE mx, const FP_REAL *x, FP_SIZE my, const FP_REAL *y,
+                 const FP_REAL *z, FP_REAL xb, FP_REAL xe, FP_REAL yb, FP_REAL ye,
+                 FP_SIZE kx, FP_SIZE ky, FP_REAL s, FP_SIZE nxest, FP_SIZE nyest,
+                 FP_SIZE *nx, FP_REAL *tx, FP_SIZE *ny, FP_REAL *ty, FP_REAL *c, FP_REAL *fp,
+                 FP_REAL *wrk, FP_SIZE lwrk, FP_SIZE *iwrk, FP_SIZE kwrk, FP_FLAG *ier);
+
+FP_FLAG fp_bispev_c(const FP_REAL *tx, FP_SIZE nx, const FP_REAL *ty, FP_SIZE ny, const FP_REAL *c,
+                    FP_SIZE kx, FP_SIZE ky, const FP_REAL *x, FP_SIZE mx, const FP_REAL *y, FP_SIZE my,
+                    FP_REAL *z, FP_REAL *wrk, FP_SIZE lwrk, FP_SIZE *iwrk, FP_SIZE kwrk);
+
+/* NEW: the same with the mx*my grid values resident in HBM (z_dev is a DEVICE pointer; every
+   other array is a small host array).  Returns FPB_STATUS_* ; ier as regrid / bispev. */
+int32_t fp_regrid_dev_c(fpb_engine *eng, FP_SIZE iopt, FP_SIZE mx, const FP_REAL *x, FP_SIZE my,
+                        const FP_REAL *y, const FP_REAL *z_dev, FP_REAL xb, FP_REAL xe, FP_REAL yb,
+                        FP_REAL ye, FP_SIZE kx, FP_SIZE ky, FP_REAL s, FP_SIZE nxest, FP_SIZE nyest,
+                        FP_SIZE *nx, FP_REAL *tx, FP_SIZE *ny, FP_REAL *ty, FP_REAL *c, FP_REAL *fp,
+                        FP_REAL *wrk, FP_SIZE lwrk, FP_SIZE *iwrk, FP_SIZE kwrk, FP_FLAG *ier);
+int32_t fp_bispev_dev_c(fpb_engine *eng, const FP_REAL *tx, FP_SIZE nx, const FP_REAL *ty, FP_SIZE ny,
+                        const FP_REAL *c, FP_SIZE kx, FP_SIZE ky, const FP_REAL *x, FP_SIZE mx,
+                        const FP_REAL *y, FP_SIZE my, FP_REAL *z_dev, FP_FLAG *ier);
+/* number of fpgrre solves (knot sets + smoothing-parameter iterations) of the last regrid call */
+int64_t fpb_engine_grid_fpgrre_calls(const fpb_engine *eng);
+
 #ifdef __cplusplus
 }
 #endif

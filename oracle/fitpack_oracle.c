@@ -816,3 +816,475 @@ void orc_splev_batch(int32_t nspl, const double *t, const int32_t *n, const doub
         orc_splev(t + (size_t)b * ldt, n[b], c + (size_t)b * ldt, k, x + (size_t)b * m,
                   y + (size_t)b * m, m, e, &ier[b]);
 }
+
+/* =====================================================================================
+ * Gridded surfaces: regrid / fpregr / fpgrre at dims = 2, and bispev / fpndsp at dims = 2.
+ * The reference implements these for any number of axes; the C binding fp_regrid_c /
+ * fp_bispev_c (src/fitpack_core_c.f90:253-290, 404-415) is the dims = 2 case restated here.
+ * Layouts: z, c flat row-major, x (axis 1) slowest: z[(i1)*my + i2], c[(ix)*nk1y + iy].
+ * ===================================================================================== */
+
+typedef struct grid_axis {
+    int m, k, k1, k2, nest, n, nk1;
+    const double *x;   /* grid coordinates            */
+    double *t;         /* knots (nest)                */
+    double *sp;        /* [m][k1] basis values        */
+    int32_t *nr;       /* [m] interval number (0-based count of knots passed) */
+    double *a;         /* band matrix, column-major, leading dim nest, k2 columns */
+    double *b;         /* discontinuity matrix, leading dim nest, k2 columns      */
+    double *fpint;     /* [nest] */
+    int32_t *nrdat;    /* [nest] */
+    int iband;
+} grid_axis;
+
+/* core:7176-7196 : basis values and interval numbers of the grid coordinates of one axis */
+static void grid_basis(grid_axis *ax)
+{
+    const double *T = ax->t - 1;
+    int l = ax->k1, l1 = ax->k2, number = 0, it, j;
+    double h[ORC_MAX_ORDER + 1];
+    for (it = 1; it <= ax->m; ++it) {
+        double arg = ax->x[it - 1];
+        while (arg >= T[l1] && l != ax->nk1) {
+            l = l1;
+            l1 = l + 1;
+            ++number;
+        }
+        orc_fpbspl(ax->t, ax->n, ax->k, arg, l, h);
+        for (j = 0; j < ax->k1; ++j) ax->sp[(size_t)(it - 1) * ax->k1 + j] = h[j];
+        ax->nr[it - 1] = number;
+    }
+}
+
+/* fp_rotate_row_block / fp_rotate_row_stride (core:6034-6092): rotate h(1:band) into the band
+   matrix rows irot_start+1.., applying each rotation to nrhs right-hand sides:
+   right[j] against rhs[row*rs_row + j*rs_col]. */
+static void grid_rotate(double *h, int band, double *a, int lda, double *right, double *rhs,
+                        size_t rs_row, size_t rs_col, int nrhs, int irot_start)
+{
+    double *H = h - 1;
+    int i, irot = irot_start, j, q;
+    for (i = 1; i <= band; ++i) {
+        double piv, cs, sn;
+        double *row;
+        ++irot;
+        piv = H[i];
+        if (g_netlib_compat ? (piv == 0.0) : orc_equal(piv, 0.0)) continue;
+        fpgivs(piv, &a[irot - 1], &cs, &sn);
+        row = rhs + (size_t)(irot - 1) * rs_row;
+        for (j = 0; j < nrhs; ++j) fprota(cs, sn, &right[j], &row[(size_t)j * rs_col]);
+        for (q = 1; q <= band - i; ++q) fprota(cs, sn, &H[i + q], &a[(size_t)q * lda + (irot - 1)]);
+    }
+}
+
+/* core:7111-7360 at dims = 2 */
+static void fpgrre2(grid_axis *X, grid_axis *Y, const double *z, double p, double *c, double *fp,
+                    double *right, double *q, int *ifs, int *ifb)
+{
+    grid_axis *ax[2] = {X, Y};
+    const int mx = X->m, my = Y->m, nk1x = X->nk1, nk1y = Y->nk1;
+    const double pinv = (p > 0.0) ? 1.0 / p : 1.0;
+    double h[ORC_MAX_ORDER + 2];
+    int d, it, i, j;
+
+    for (d = 0; d < 2; ++d)
+        if (ifs[d] == 0) {
+            grid_basis(ax[d]);
+            ifs[d] = 1;
+        }
+    if (p > 0.0)
+        for (d = 0; d < 2; ++d)
+            if (ifb[d] == 0 && ax[d]->n != 2 * ax[d]->k1) {
+                fpdisc(ax[d]->t, ax[d]->n, ax[d]->k2, ax[d]->b, ax[d]->nest);
+                ifb[d] = 1;
+            }
+
+    /* ---- pass 1: block reduction of axis x; q is [nk1x][my] ---- */
+    for (d = 0; d < 2; ++d) {
+        grid_axis *A = ax[d];
+        const int nrhs = (d == 0) ? my : nk1x;
+        int nrold = 0, number;
+        if (d == 0) memset(q, 0, sizeof(double) * (size_t)nk1x * my);
+        else memset(c, 0, sizeof(double) * (size_t)nk1x * nk1y);
+        for (j = 0; j < A->k2; ++j)
+            for (i = 0; i < A->nk1; ++i) A->a[(size_t)j * A->nest + i] = 0.0;
+        A->iband = A->k1;
+        for (it = 1; it <= A->m; ++it) {
+            number = A->nr[it - 1];
+            for (;;) {
+                int irot;
+                if (nrold == number) {
+                    h[A->iband - 1] = 0.0;
+                    for (j = 0; j < A->k1; ++j) h[j] = A->sp[(size_t)(it - 1) * A->k1 + j];
+                    if (d == 0) {
+                        memcpy(right, z + (size_t)(it - 1) * my, sizeof(double) * my);
+                    } else {
+                        for (j = 0; j < nk1x; ++j) right[j] = q[(size_t)j * my + (it - 1)];
+                    }
+                    irot = number;
+                } else if (p <= 0.0) {
+                    ++nrold;
+                    continue;
+                } else {
+                    int n1 = nrold + 1;
+                    A->iband = A->k2;
+                    for (j = 0; j < A->k2; ++j) h[j] = A->b[(size_t)j * A->nest + (n1 - 1)] * pinv;
+                    for (j = 0; j < nrhs; ++j) right[j] = 0.0;
+                    irot = nrold;
+                }
+                if (d == 0) grid_rotate(h, A->iband, A->a, A->nest, right, q, (size_t)my, 1, nrhs, irot);
+                else grid_rotate(h, A->iband, A->a, A->nest, right, c, 1, (size_t)nk1y, nrhs, irot);
+                if (nrold == number) break;
+                ++nrold;
+            }
+        }
+    }
+
+    /* ---- back-substitution: axis y (contiguous lines), then axis x (stride nk1y) ---- */
+    for (i = 0; i < nk1x; ++i)
+        fpback(Y->a, c + (size_t)i * nk1y, nk1y, Y->iband, c + (size_t)i * nk1y, Y->nest);
+    for (j = 0; j < nk1y; ++j) {
+        for (i = 0; i < nk1x; ++i) right[i] = c[(size_t)i * nk1y + j];
+        fpback(X->a, right, nk1x, X->iband, right, X->nest);
+        for (i = 0; i < nk1x; ++i) c[(size_t)i * nk1y + j] = right[i];
+    }
+
+    /* ---- residuals ---- */
+    *fp = 0.0;
+    for (i = 0; i < X->nest; ++i) X->fpint[i] = 0.0;
+    for (i = 0; i < Y->nest; ++i) Y->fpint[i] = 0.0;
+    {
+        int i1, i2, cx, cy;
+        for (i1 = 0; i1 < mx; ++i1) {
+            const int numx = X->nr[i1], nroldx = (i1 >= 1) ? X->nr[i1 - 1] : 0;
+            const double *spx = X->sp + (size_t)i1 * X->k1;
+            for (i2 = 0; i2 < my; ++i2) {
+                const int numy = Y->nr[i2], nroldy = (i2 >= 1) ? Y->nr[i2 - 1] : 0;
+                const double *spy = Y->sp + (size_t)i2 * Y->k1;
+                const double *cc = c + (size_t)numx * nk1y + numy;
+                double sp_val = 0.0, term, fac;
+                if (g_netlib_compat) { /* netlib fpgrre: term += (spx*spy)*c, flat */
+                    for (cx = 0; cx < X->k1; ++cx)
+                        for (cy = 0; cy < Y->k1; ++cy)
+                            sp_val = sp_val + spx[cx] * spy[cy] * cc[(size_t)cx * nk1y + cy];
+                } else {               /* core:7316-7335 */
+                    for (cx = 0; cx < X->k1; ++cx) {
+                        double pw = 1.0 * spx[cx], dot = 0.0;
+                        for (cy = 0; cy < Y->k1; ++cy) dot = dot + spy[cy] * cc[(size_t)cx * nk1y + cy];
+                        sp_val = sp_val + pw * dot;
+                    }
+                }
+                term = z[(size_t)i1 * my + i2] - sp_val;
+                term = term * term;
+                *fp = *fp + term;
+                fac = term * 0.5;
+                if (g_netlib_compat) { /* netlib order: y axis bookkeeping first */
+                    Y->fpint[numy] += term;
+                    X->fpint[numx] += term;
+                    if (numy != nroldy) { Y->fpint[numy] -= fac; Y->fpint[numy - 1] += fac; }
+                    if (numx != nroldx) { X->fpint[numx] -= fac; X->fpint[numx - 1] += fac; }
+                } else {
+                    X->fpint[numx] += term;
+                    if (numx != nroldx) { X->fpint[numx] -= fac; X->fpint[numx - 1] += fac; }
+                    Y->fpint[numy] += term;
+                    if (numy != nroldy) { Y->fpint[numy] -= fac; Y->fpint[numy - 1] += fac; }
+                }
+            }
+        }
+    }
+}
+
+/* new_knot_dimension_nd (core:12347-12362) at dims = 2; netlib's fpregr alternates on ties */
+static int grid_knot_axis(const int *n, const int *npl, const int *ne, int lastdi)
+{
+    if (g_netlib_compat) {
+        int pick_x;
+        if (npl[0] < npl[1]) pick_x = 1;
+        else if (npl[0] == npl[1]) pick_x = !(lastdi == 1);  /* tie: not the axis used last (x first) */
+        else pick_x = 0;
+        if (pick_x && n[0] == ne[0]) pick_x = 0;
+        else if (!pick_x && n[1] == ne[1]) pick_x = 1;
+        return pick_x ? 1 : 2;
+    } else {
+        int dir = 0, d;
+        for (d = 1; d <= 2; ++d) {
+            if (n[d - 1] >= ne[d - 1]) continue;
+            if (dir == 0) dir = d;
+            else if (npl[d - 1] <= npl[dir - 1]) dir = d;
+        }
+        return dir;
+    }
+}
+
+/* regrid (core:16732-16839) + fpregr (core:12079-12303), dims = 2; argument list of fp_regrid_c */
+void orc_regrid(int32_t iopt, int32_t mx, const double *x, int32_t my, const double *y,
+                const double *z, double xb, double xe, double yb, double ye, int32_t kx, int32_t ky,
+                double s, int32_t nxest, int32_t nyest, int32_t *nx, double *tx, int32_t *ny,
+                double *ty, double *c, double *fp_out, double *wrk, int32_t lwrk, int32_t *iwrk,
+                int32_t kwrk, int32_t *ier_out)
+{
+    const double tol = 1.0e-03;
+    const int maxit = 20;
+    grid_axis X, Y, *ax[2];
+    int m[2] = {mx, my}, k[2] = {kx, ky}, nest[2] = {nxest, nyest};
+    double lo[2] = {xb, yb}, hi[2] = {xe, ye};
+    const double *xg[2] = {x, y};
+    double *tt[2] = {tx, ty};
+    int n[2], d, i, j, l, ier, iter, mpm;
+    int k1[2], k2[2], nmin[2], nmax[2], ne[2], nrint[2], npl[2], ifs[2] = {0, 0}, ifb[2] = {0, 0};
+    double acc, fpms = 0.0, fp = 0.0, p, p1, p2, p3, f1, f2, f3;
+    int check1, check3;
+    double *fp0 = wrk, *fpold = wrk + 1, *reduc = wrk + 2;
+    int32_t *lastdi = iwrk, *nplus = iwrk + 1;
+    double *scratch = NULL, *right, *q;
+    long maxm, maxnest, maxk1, maxk2, mm, mynx, lwest, kwest, nk1maxx, nk1maxy;
+
+    *ier_out = IER_INPUT;
+    for (d = 0; d < 2; ++d) {
+        k1[d] = k[d] + 1;
+        k2[d] = k[d] + 2;
+        nmin[d] = 2 * k1[d];
+    }
+    for (d = 0; d < 2; ++d) if (k[d] <= 0 || k[d] > 5) return;
+    if (iopt < -1 || iopt > 1) return;
+    for (d = 0; d < 2; ++d) if (m[d] < k1[d] || nest[d] < nmin[d]) return;
+    maxm = mx > my ? mx : my;
+    maxnest = nxest > nyest ? nxest : nyest;
+    maxk1 = (kx > ky ? kx : ky) + 1;
+    maxk2 = maxk1 + 1;
+    nk1maxx = nxest - k1[0];
+    nk1maxy = nyest - k1[1];
+    mm = maxnest;
+    if (maxm > mm) mm = maxm;
+    if (my > mm) mm = my;
+    if (nk1maxx > mm) mm = nk1maxx;
+    if (nk1maxy > mm) mm = nk1maxy;
+    mynx = 2 * nk1maxx * (long)my;
+    lwest = 4 + maxnest * 2 + maxm * maxk1 * 2 + 2 * maxnest * maxk2 * 2 + mm + mynx;
+    kwest = 3 + maxm * 2 + maxnest * 2;
+    if (lwrk < lwest || kwrk < kwest) return;
+    for (d = 0; d < 2; ++d) {
+        if (lo[d] > xg[d][0] || hi[d] < xg[d][m[d] - 1]) return;
+        for (i = 0; i < m[d] - 1; ++i)
+            if (xg[d][i] >= xg[d][i + 1]) return;
+    }
+    n[0] = *nx;
+    n[1] = *ny;
+    if (iopt < 0) {
+        for (d = 0; d < 2; ++d) {
+            if (n[d] < nmin[d] || n[d] > nest[d]) return;
+            j = n[d];
+            for (i = 1; i <= k1[d]; ++i) {
+                tt[d][i - 1] = lo[d];
+                tt[d][j - 1] = hi[d];
+                --j;
+            }
+            ier = orc_fpchec(xg[d], m[d], tt[d], n[d], k[d]);
+            if (ier != IER_OK) { *ier_out = ier; return; }
+        }
+    } else {
+        if (s < 0.0) return;
+        if (orc_equal(s, 0.0) && (nest[0] < m[0] + k1[0] || nest[1] < m[1] + k1[1])) return;
+    }
+    ier = IER_OK;
+
+    /* scratch (the reference carves the same arrays out of wrk/iwrk, core:16820-16832) */
+    {
+        size_t need = 0, off = 0;
+        for (d = 0; d < 2; ++d)
+            need += (size_t)m[d] * k1[d] + 2 * (size_t)nest[d] * k2[d] + nest[d] + m[d] + nest[d];
+        need += (size_t)mm + (size_t)nk1maxx * my + 64;
+        scratch = (double *)calloc(need, sizeof(double));
+        if (!scratch) return;
+        ax[0] = &X;
+        ax[1] = &Y;
+        for (d = 0; d < 2; ++d) {
+            grid_axis *A = ax[d];
+            A->m = m[d]; A->k = k[d]; A->k1 = k1[d]; A->k2 = k2[d]; A->nest = nest[d];
+            A->x = xg[d]; A->t = tt[d];
+            A->sp = scratch + off; off += (size_t)m[d] * k1[d];
+            A->a = scratch + off; off += (size_t)nest[d] * k2[d];
+            A->b = scratch + off; off += (size_t)nest[d] * k2[d];
+            A->fpint = scratch + off; off += nest[d];
+            A->nr = (int32_t *)(scratch + off); off += (m[d] + 1) / 2 + 1;
+            A->nrdat = (int32_t *)(scratch + off); off += (nest[d] + 1) / 2 + 1;
+            A->iband = k1[d];
+        }
+        right = scratch + off; off += mm;
+        q = scratch + off;
+    }
+
+    /* ---------------- fpregr ---------------- */
+    acc = tol * s;
+    for (d = 0; d < 2; ++d) {
+        nmax[d] = m[d] + k1[d];
+        ne[d] = nmax[d] < nest[d] ? nmax[d] : nest[d];
+    }
+    if (iopt >= 0) {
+        if (s <= 0.0) {
+            for (d = 0; d < 2; ++d) n[d] = nmax[d];
+            if (n[0] > nest[0] || n[1] > nest[1]) { ier = IER_STORAGE; goto done; }
+            for (d = 0; d < 2; ++d) interp_knots(xg[d], m[d], k[d], tt[d]);
+        } else if (iopt != 0 && *fp0 > s) {
+            for (d = 0; d < 2; ++d) {   /* core:12147-12163 */
+                const double *T = tt[d] - 1;
+                int32_t *NR = ax[d]->nrdat - 1;
+                int mp = m[d] - 1;
+                l = k2[d];
+                j = 1;
+                NR[1] = 0;
+                for (i = 2; i <= mp; ++i) {
+                    NR[j] = NR[j] + 1;
+                    if (xg[d][i - 1] >= T[l]) {
+                        NR[j] = NR[j] - 1;
+                        ++l;
+                        ++j;
+                        NR[j] = 0;
+                    }
+                }
+            }
+        } else {
+            for (d = 0; d < 2; ++d) {
+                n[d] = nmin[d];
+                ax[d]->nrdat[0] = m[d] - 2;
+                nplus[d] = 0;
+                reduc[d] = 0.0;
+            }
+            *lastdi = 0;
+            *fp0 = 0.0;
+            *fpold = 0.0;
+        }
+    }
+    mpm = mx + my;
+    p = -1.0;
+    iter = 0;
+    for (;;) {
+        if (g_netlib_compat ? !(iter < mpm) : !(iter <= mpm)) break;
+        ++iter;
+        if (n[0] == nmin[0] && n[1] == nmin[1]) ier = IER_LSQ;
+        for (d = 0; d < 2; ++d) {
+            nrint[d] = n[d] - nmin[d] + 1;
+            ax[d]->n = n[d];
+            ax[d]->nk1 = n[d] - k1[d];
+            j = n[d];
+            for (i = 1; i <= k1[d]; ++i) {
+                tt[d][i - 1] = lo[d];
+                tt[d][j - 1] = hi[d];
+                --j;
+            }
+        }
+        fpgrre2(&X, &Y, z, p, c, &fp, right, q, ifs, ifb);
+        if (ier == IER_LSQ) *fp0 = fp;
+        fpms = fp - s;
+        if (iopt < 0 || fabs(fpms) < acc) goto done;
+        if (fpms < 0.0) break;
+        if (n[0] == nmax[0] && n[1] == nmax[1]) { ier = IER_INTERP; fp = 0.0; goto done; }
+        if (n[0] == ne[0] && n[1] == ne[1]) { ier = IER_STORAGE; goto done; }
+        ier = IER_OK;
+        if (*lastdi != 0) reduc[*lastdi - 1] = *fpold - fp;
+        *fpold = fp;
+        for (d = 0; d < 2; ++d) {
+            npl[d] = 1;
+            if (n[d] != nmin[d]) {
+                int npl1 = nplus[d] * 2, a2 = nplus[d] * 2, b2;
+                double rn = (double)nplus[d];
+                if (reduc[d] > acc) npl1 = f_int(rn * fpms / reduc[d]);
+                b2 = npl1;
+                if (nplus[d] / 2 > b2) b2 = nplus[d] / 2;
+                if (1 > b2) b2 = 1;
+                npl[d] = a2 < b2 ? a2 : b2;
+            }
+        }
+        *lastdi = grid_knot_axis(n, npl, ne, *lastdi);
+        d = *lastdi - 1;
+        nplus[d] = npl[d];
+        ifs[d] = 0;
+        for (l = 1; l <= nplus[d]; ++l) {
+            fpknot(xg[d], m[d], tt[d], &n[d], ax[d]->fpint, ax[d]->nrdat, &nrint[d], nest[d], 1);
+            if (n[d] == ne[d]) break;
+        }
+    }
+    if (ier == IER_LSQ) goto done;
+
+    /* part 2: smoothing parameter (core:12270-12300) */
+    p1 = 0.0; f1 = *fp0 - s; p3 = -1.0; f3 = fpms; p = 1.0; p2 = 0.0; f2 = 0.0;
+    check1 = 0; check3 = 0;
+    for (iter = 1; iter <= maxit; ++iter) {
+        fpgrre2(&X, &Y, z, p, c, &fp, right, q, ifs, ifb);
+        fpms = fp - s;
+        if (fabs(fpms) < acc) goto done;
+        if (!root_iterate(&p1, &f1, &p2, &f2, &p3, &f3, &p, fpms, acc, &check1, &check3)) {
+            ier = IER_S_SMALL;
+            goto done;
+        }
+    }
+    ier = IER_MAXIT;
+
+done:
+    *nx = n[0];
+    *ny = n[1];
+    for (d = 0; d < 2; ++d)   /* fp_regrid_c zero-fills the knot arrays beyond n (core_c:286-289) */
+        for (i = n[d]; i < nest[d]; ++i) tt[d][i] = 0.0;
+    *fp_out = fp;
+    *ier_out = ier;
+    free(scratch);
+}
+
+/* bispev (core:424-458) + fpndsp (core:2160-2241) at dims = 2; argument list of fp_bispev_c */
+int32_t orc_bispev(const double *tx, int32_t nx, const double *ty, int32_t ny, const double *c,
+                   int32_t kx, int32_t ky, const double *x, int32_t mx, const double *y, int32_t my,
+                   double *z, double *wrk, int32_t lwrk, int32_t *iwrk, int32_t kwrk)
+{
+    const double *t[2] = {tx, ty}, *xg[2] = {x, y};
+    int n[2] = {nx, ny}, k[2] = {kx, ky}, m[2] = {mx, my};
+    int lwest = (kx + 1) * mx + (ky + 1) * my, d, i, j, i1, i2, cx, cy;
+    double *w[2];
+    int32_t *lidx[2];
+    (void)iwrk;
+    if (lwrk < lwest || kwrk < (mx + my) || mx < 1 || my < 1) return IER_INPUT;
+    for (i = 1; i < mx; ++i) if (x[i] < x[i - 1]) return IER_INPUT;
+    for (i = 1; i < my; ++i) if (y[i] < y[i - 1]) return IER_INPUT;
+    w[0] = wrk;
+    w[1] = wrk + (size_t)(kx + 1) * mx;
+    lidx[0] = (int32_t *)malloc(sizeof(int32_t) * (size_t)(mx + my));
+    if (!lidx[0]) return IER_INPUT;
+    lidx[1] = lidx[0] + mx;
+    for (d = 0; d < 2; ++d) {
+        const int k1 = k[d] + 1, nkd = n[d] - k1;
+        const double tb = t[d][k1 - 1], te = t[d][nkd];
+        double h[ORC_MAX_ORDER + 1];
+        int l = k1;
+        for (i = 0; i < m[d]; ++i) {
+            double arg = xg[d][i];
+            if (arg < tb) arg = tb;
+            if (arg > te) arg = te;
+            l = orc_knot_interval(t[d], arg, l, nkd);
+            orc_fpbspl(t[d], n[d], k[d], arg, l, h);
+            lidx[d][i] = l - k1;
+            for (j = 0; j < k1; ++j) w[d][(size_t)i * k1 + j] = h[j];
+        }
+    }
+    {
+        const int k1x = kx + 1, k1y = ky + 1, nk1y = ny - k1y;
+        for (i1 = 0; i1 < mx; ++i1)
+            for (i2 = 0; i2 < my; ++i2) {
+                const double *cc = c + (size_t)lidx[0][i1] * nk1y + lidx[1][i2];
+                const double *wx = w[0] + (size_t)i1 * k1x, *wy = w[1] + (size_t)i2 * k1y;
+                double sp = 0.0;
+                if (g_netlib_compat) { /* netlib fpbisp: sp += c*wx*wy, flat */
+                    for (cx = 0; cx < k1x; ++cx)
+                        for (cy = 0; cy < k1y; ++cy)
+                            sp = sp + cc[(size_t)cx * nk1y + cy] * wx[cx] * wy[cy];
+                } else {               /* core:2219-2222 */
+                    for (cx = 0; cx < k1x; ++cx) {
+                        double pw = 1.0 * wx[cx], dot = 0.0;
+                        for (cy = 0; cy < k1y; ++cy) dot = dot + cc[(size_t)cx * nk1y + cy] * wy[cy];
+                        sp = sp + pw * dot;
+                    }
+                }
+                z[(size_t)i1 * my + i2] = sp;
+            }
+    }
+    free(lidx[0]);
+    return IER_OK;
+}

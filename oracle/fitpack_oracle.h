@@ -94,6 +94,20 @@ void orc_splev_batch(int32_t nspl, const double *t, const int32_t *n, const doub
                      int32_t k, const double *x, double *y, int32_t m, int32_t e, int32_t *ier,
                      int32_t nthreads);
 
+/* regrid (dims = 2), core:16732-16839 + fpregr 12079-12303 + fpgrre 7111-7360 (argument list of
+   fp_regrid_c, src/fitpack_core_c.f90:253-290).  z, c flat row-major with x slowest.
+   State for iopt=1: wrk[0]=fp0, wrk[1]=fpold, wrk[2..3]=reduc, iwrk[0]=lastdi, iwrk[1..2]=nplus. */
+void orc_regrid(int32_t iopt, int32_t mx, const double *x, int32_t my, const double *y,
+                const double *z, double xb, double xe, double yb, double ye, int32_t kx, int32_t ky,
+                double s, int32_t nxest, int32_t nyest, int32_t *nx, double *tx, int32_t *ny,
+                double *ty, double *c, double *fp, double *wrk, int32_t lwrk, int32_t *iwrk,
+                int32_t kwrk, int32_t *ier);
+
+/* bispev, core:424-458 + fpndsp 2160-2241 at dims = 2 (argument list of fp_bispev_c) */
+int32_t orc_bispev(const double *tx, int32_t nx, const double *ty, int32_t ny, const double *c,
+                   int32_t kx, int32_t ky, const double *x, int32_t mx, const double *y, int32_t my,
+                   double *z, double *wrk, int32_t lwrk, int32_t *iwrk, int32_t kwrk);
+
 int32_t orc_max_threads(void);
 
 /* tests only: switch the documented reference-vs-netlib deviations off (see .c) */

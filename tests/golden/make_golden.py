@@ -203,9 +203,91 @@ def make_splev():
     np.savez_compressed(os.path.join(HERE, "splev_golden.npz"), **out)
 
 
+def scipy_regrid(x, y, z, kx, ky, s, nxest=None, nyest=None):
+    """iopt=0 smoothing fit on a grid through scipy's C translation of netlib regrid."""
+    mx, my = x.size, y.size
+    nxest = mx + kx + 1 if nxest is None else nxest
+    nyest = my + ky + 1 if nyest is None else nyest
+    lwrk = (4 + mx + my + nxest * (my + 2 * kx + 5) + nyest * (2 * ky + 5) + mx * (kx + 1)
+            + my * (ky + 1) + max((nxest - kx - 1) * (nyest - ky - 1), my))
+    wrk = np.zeros(lwrk)
+    iwrk = np.zeros(3 + mx + my + nxest + nyest, np.int32)
+    nx, tx, ny, ty, c, fp, ier = _fitpack.regrid(0, x, y, np.ascontiguousarray(z).ravel(), x[0], x[-1],
+                                                 y[0], y[-1], kx, ky, s, nxest, nyest, 20, wrk, iwrk)
+    return int(nx), np.asarray(tx), int(ny), np.asarray(ty), np.asarray(c), float(fp), int(ier)
+
+
+def grid_surface(rng, mx, my, sigma=0.05, uniform=True):
+    """C4-style synthetic grid: smooth bivariate function + noise on [-1.5,1.5]^2"""
+    if uniform:
+        x = np.linspace(-1.5, 1.5, mx)
+        y = np.linspace(-1.5, 1.5, my)
+    else:
+        x = np.sort(rng.uniform(-1.5, 1.5, mx)); x[0], x[-1] = -1.5, 1.5
+        y = np.sort(rng.uniform(-1.5, 1.5, my)); y[0], y[-1] = -1.5, 1.5
+        x, y = np.unique(x), np.unique(y)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    z = np.exp(-(X ** 2 + Y ** 2)) + 0.3 * np.sin(2.0 * X) * np.cos(1.5 * Y)
+    return x, y, z + sigma * rng.standard_normal(z.shape)
+
+
+def make_regrid():
+    """regrid (iopt=0) and bispev vectors.  NOTE: the reference deliberately differs from netlib in
+    the knot-direction arbiter (new_knot_dimension_nd, core:12347-12362: ties and the first knot go
+    to the LAST axis; netlib alternates starting with x), in fpknot and in the association order of
+    the tensor-product sums (fpgrre residual, fpndsp).  These vectors therefore pin the oracle in
+    its netlib-compatibility mode (orc_set_netlib_compat), which shares every other line of code
+    with the default (reference) mode."""
+    from refdata import DAREGR_X, DAREGR_Y, DAREGR_Z  # noqa: F401 (tests/ on sys.path)
+    rng = np.random.default_rng(4096)
+    cases = []
+    for (kx, ky, s) in [(3, 3, 10.0), (3, 3, 0.22), (3, 3, 0.1), (3, 3, 0.0), (5, 5, 0.2), (1, 2, 0.3),
+                        (4, 3, 0.15), (2, 5, 0.5), (1, 1, 0.05)]:
+        cases.append((DAREGR_X, DAREGR_Y, DAREGR_Z.reshape(11, 11), kx, ky, s, None, None))
+    for trial in range(40):
+        kx, ky = int(rng.integers(1, 6)), int(rng.integers(1, 6))
+        mx, my = int(rng.integers(kx + 2, 48)), int(rng.integers(ky + 2, 48))
+        x, y, z = grid_surface(rng, mx, my, 0.05, uniform=rng.random() < 0.5)
+        mx, my = x.size, y.size
+        if mx < kx + 2 or my < ky + 2:
+            continue
+        s = float(rng.choice([mx * my * 0.0025, mx * my * 0.001, mx * my * 0.01, 0.0, 1e3, 1e-9]))
+        nxe = nye = None
+        if rng.random() < 0.25:  # storage-limited
+            nxe, nye = max(2 * kx + 2, mx // 2), max(2 * ky + 2, my // 2)
+        cases.append((x, y, z, kx, ky, s, nxe, nye))
+    out = {"ncase": 0}
+    i = 0
+    for (x, y, z, kx, ky, s, nxe, nye) in cases:
+        nx, tx, ny, ty, c, fp, ier = scipy_regrid(x, y, z, kx, ky, s, nxe, nye)
+        if not np.isfinite(fp):
+            continue
+        pre = f"g{i}_"
+        out[pre + "x"], out[pre + "y"], out[pre + "z"] = x, y, np.ascontiguousarray(z).ravel()
+        out[pre + "par"] = np.array([kx, ky, nxe if nxe else x.size + kx + 1,
+                                     nye if nye else y.size + ky + 1, nx, ny, ier], np.int64)
+        out[pre + "s"], out[pre + "fp"] = s, fp
+        out[pre + "tx"], out[pre + "ty"] = tx[:nx], ty[:ny]
+        ncof = (nx - kx - 1) * (ny - ky - 1)
+        out[pre + "c"] = c[:ncof]
+        if ier <= 0 or ier in (1, 2, 3):
+            xe = np.sort(rng.uniform(x[0] - 0.1, x[-1] + 0.1, 37))
+            ye = np.sort(rng.uniform(y[0] - 0.1, y[-1] + 0.1, 29))
+            zz, ie = _fitpack.bispev(tx[:nx], ty[:ny], c[:ncof], kx, ky, xe, ye)
+            out[pre + "ex"], out[pre + "ey"], out[pre + "ez"] = xe, ye, np.asarray(zz).ravel()
+        i += 1
+    out["ncase"] = i
+    np.savez_compressed(os.path.join(HERE, "regrid_golden.npz"), **out)
+    iers = [int(out[f"g{j}_par"][6]) for j in range(i)]
+    print("regrid cases:", i, "ier histogram:", {v: iers.count(v) for v in sorted(set(iers))})
+
+
 if __name__ == "__main__":
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
     make_mncurf()
     make_curfit()
     make_splev()
-    for f in ("mncurf_golden.npz", "curfit_golden.npz", "splev_golden.npz"):
+    make_regrid()
+    for f in ("mncurf_golden.npz", "curfit_golden.npz", "splev_golden.npz", "regrid_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

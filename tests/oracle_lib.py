@@ -190,3 +190,68 @@ def splev_batch(t, n, c, k, x, e=0, nthreads=0):
     lib().orc_splev_batch(C.c_int32(nspl), _d(t), _i(n), _d(c), C.c_int32(ldt), C.c_int32(k),
                           _d(x), _d(y), C.c_int32(m), C.c_int32(e), _i(ier), C.c_int32(nthreads))
     return y, ier
+
+
+# ------------------------------------------------------------------ gridded surfaces (dims = 2)
+def regrid_lwrk(mx, my, kx, ky, nxest, nyest):
+    """minimum lwrk, kwrk of regrid at dims=2 (core:16789-16797)"""
+    maxm, maxnest, maxk1 = max(mx, my), max(nxest, nyest), max(kx, ky) + 1
+    maxk2 = maxk1 + 1
+    nkx, nky = nxest - kx - 1, nyest - ky - 1
+    mm = max(maxnest, maxm, my, nkx, nky)
+    mynx = 2 * nkx * my
+    lwrk = 4 + maxnest * 2 + maxm * maxk1 * 2 + 2 * maxnest * maxk2 * 2 + mm + mynx
+    kwrk = 3 + maxm * 2 + maxnest * 2
+    return lwrk, kwrk
+
+
+def regrid(iopt, x, y, z, xb, xe, yb, ye, kx, ky, s, nxest, nyest, nx=0, ny=0, tx=None, ty=None,
+           c=None, wrk=None, iwrk=None, lwrk=None, kwrk=None):
+    """orc_regrid with the argument list of fp_regrid_c.  Returns dict(nx,tx,ny,ty,c,fp,ier,wrk,iwrk)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    z = np.ascontiguousarray(z, dtype=np.float64).ravel()
+    mx, my = x.size, y.size
+    lw, kw = regrid_lwrk(mx, my, kx, ky, nxest, nyest)
+    lwrk = max(lw, 8) if lwrk is None else lwrk
+    kwrk = max(kw, 8) if kwrk is None else kwrk
+    tx = np.zeros(max(nxest, 1)) if tx is None else np.ascontiguousarray(tx, dtype=np.float64).copy()
+    ty = np.zeros(max(nyest, 1)) if ty is None else np.ascontiguousarray(ty, dtype=np.float64).copy()
+    ncmax = max((nxest - kx - 1) * (nyest - ky - 1), 1)
+    c = np.zeros(ncmax) if c is None else c
+    wrk = np.zeros(max(lwrk, 8)) if wrk is None else wrk
+    iwrk = np.zeros(max(kwrk, 8), dtype=np.int32) if iwrk is None else iwrk
+    nx_, ny_ = C.c_int32(int(nx)), C.c_int32(int(ny))
+    fp_, ier_ = C.c_double(0.0), C.c_int32(0)
+    L = lib()
+    L.orc_regrid.restype = None
+    L.orc_regrid(C.c_int32(iopt), C.c_int32(mx), _d(x), C.c_int32(my), _d(y), _d(z),
+                 C.c_double(xb), C.c_double(xe), C.c_double(yb), C.c_double(ye), C.c_int32(kx),
+                 C.c_int32(ky), C.c_double(s), C.c_int32(nxest), C.c_int32(nyest), C.byref(nx_),
+                 _d(tx), C.byref(ny_), _d(ty), _d(c), C.byref(fp_), _d(wrk), C.c_int32(lwrk),
+                 _i(iwrk), C.c_int32(kwrk), C.byref(ier_))
+    return dict(nx=nx_.value, tx=tx, ny=ny_.value, ty=ty, c=c, fp=fp_.value, ier=ier_.value,
+                wrk=wrk, iwrk=iwrk)
+
+
+def bispev(tx, nx, ty, ny, c, kx, ky, x, y):
+    tx = np.ascontiguousarray(tx, dtype=np.float64)
+    ty = np.ascontiguousarray(ty, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    mx, my = x.size, y.size
+    z = np.zeros(max(mx * my, 1))
+    lwrk = (kx + 1) * mx + (ky + 1) * my
+    wrk = np.zeros(max(lwrk, 1))
+    iwrk = np.zeros(max(mx + my, 1), dtype=np.int32)
+    L = lib()
+    L.orc_bispev.restype = C.c_int32
+    ier = L.orc_bispev(_d(tx), C.c_int32(nx), _d(ty), C.c_int32(ny), _d(c), C.c_int32(kx),
+                       C.c_int32(ky), _d(x), C.c_int32(mx), _d(y), C.c_int32(my), _d(z), _d(wrk),
+                       C.c_int32(lwrk), _i(iwrk), C.c_int32(mx + my))
+    return z[:mx * my].reshape(mx, my), int(ier)
+
+
+def set_netlib_compat(on):
+    lib().orc_set_netlib_compat(C.c_int32(1 if on else 0))

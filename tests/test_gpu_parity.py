@@ -571,3 +571,109 @@ def test_full_size_properties(eng):
     for b in range(S):
         nb = o["n"][b]
         assert _same(tg[b, :nb], o["t"][b, :nb]) and _same(cg[b, :nb - 4], o["c"][b, :nb - 4])
+
+
+# ------------------------------------------------------------------ gridded surfaces (dims = 2)
+from refdata import DAREGR_X, DAREGR_Y, DAREGR_Z, MNREGR_STEPS  # noqa: E402
+
+# regrid: n, knots, ier exact; c and fp within rel 1e-10 (fp is a grid-wide sum whose
+# association order a parallel reduction cannot share with the reference)
+GRID_RTOL = 1e-10
+
+
+def _grid_close(a, b, scale):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) <= GRID_RTOL * max(1.0, scale)
+
+
+def _check_regrid(r, o, kx, ky):
+    assert (r["ier"], r["nx"], r["ny"]) == (o["ier"], o["nx"], o["ny"])
+    assert _same(r["tx"][:o["nx"]], o["tx"][:o["nx"]]) and _same(r["ty"][:o["ny"]], o["ty"][:o["ny"]])
+    nc = (o["nx"] - kx - 1) * (o["ny"] - ky - 1)
+    assert _grid_close(r["c"][:nc], o["c"][:nc], np.abs(o["c"][:nc]).max())
+    assert abs(r["fp"] - o["fp"]) <= GRID_RTOL * max(1.0, abs(o["fp"]))
+
+
+def test_regrid_golden_cases_match_oracle(F):
+    g = np.load(os.path.join(G, "regrid_golden.npz"))
+    nfit = 0
+    for i in range(int(g["ncase"])):
+        p = f"g{i}_"
+        kx, ky, nxest, nyest = (int(v) for v in g[p + "par"][:4])
+        x, y, z, s = g[p + "x"], g[p + "y"], g[p + "z"], float(g[p + "s"])
+        o = O.regrid(0, x, y, z, x[0], x[-1], y[0], y[-1], kx, ky, s, nxest, nyest)
+        r = F.regrid(0, x, y, z, x[0], x[-1], y[0], y[-1], kx, ky, s, nxest, nyest)
+        if o["ier"] == 10:
+            assert r["ier"] == 10
+            continue
+        _check_regrid(r, o, kx, ky)
+        # evaluation on the data grid and on an off-grid, partly out-of-support grid: same
+        # operation order as the reference => bit-identical to the oracle
+        for (xe, ye) in ((x, y), (np.linspace(x[0] - 0.2, x[-1] + 0.2, 41), np.linspace(y[0], y[-1], 23))):
+            zo, io = O.bispev(o["tx"], o["nx"], o["ty"], o["ny"], o["c"], kx, ky, xe, ye)
+            zg, ig = F.bispev(o["tx"], o["nx"], o["ty"], o["ny"], o["c"], kx, ky, xe, ye)
+            assert ig == io == 0 and _same(zg, zo), i
+        nfit += 1
+    assert nfit >= 45
+
+
+def test_mnregr_sequence_on_gpu(F):
+    """reference test mnregr (test/fitpack_tests.f90:3170-3362) through fp_regrid_c / fp_bispev_c,
+    step by step against the oracle (iopt=1 continuations carry tx, ty, wrk, iwrk)."""
+    x, y, z = DAREGR_X, DAREGR_Y, DAREGR_Z
+    nxest = nyest = 17
+
+    def fresh():
+        return dict(tx=np.zeros(nxest), ty=np.zeros(nyest), wrk=np.zeros(2000), iwrk=np.zeros(200, np.int32),
+                    nx=0, ny=0)
+    sg, so = fresh(), fresh()
+    for (iopt, kx, ky, s) in MNREGR_STEPS:
+        for st in (sg, so):
+            if iopt == -1:
+                st["nx"] = st["ny"] = 11
+                st["tx"][:] = 0.0
+                st["ty"][:] = 0.0
+                st["tx"][kx + 1:kx + 4] = [-0.5, 0.0, 0.5]
+                st["ty"][ky + 1:ky + 4] = [-0.5, 0.0, 0.5]
+        o = O.regrid(iopt, x, y, z, x[0], x[-1], y[0], y[-1], kx, ky, s, nxest, nyest, nx=so["nx"],
+                     ny=so["ny"], tx=so["tx"], ty=so["ty"], wrk=so["wrk"], iwrk=so["iwrk"], lwrk=2000,
+                     kwrk=200)
+        r = F.regrid(iopt, x, y, z, x[0], x[-1], y[0], y[-1], kx, ky, s, nxest, nyest, nx=sg["nx"],
+                     ny=sg["ny"], tx=sg["tx"], ty=sg["ty"], wrk=sg["wrk"], iwrk=sg["iwrk"])
+        assert r["ier"] <= 0
+        _check_regrid(r, o, kx, ky)
+        so.update(nx=o["nx"], ny=o["ny"], tx=o["tx"], ty=o["ty"])
+        sg.update(nx=r["nx"], ny=r["ny"])
+        zg, ig = F.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], kx, ky, x, y)
+        assert ig == 0
+        assert abs(float(((z.reshape(11, 11) - zg) ** 2).sum()) - r["fp"]) < 1e-10
+
+
+def test_regrid_input_errors_and_device_grid(F, eng):
+    import torch
+    x, y, z = DAREGR_X, DAREGR_Y, DAREGR_Z
+    ok = dict(iopt=0, x=x, y=y, z=z, xb=x[0], xe=x[-1], yb=y[0], ye=y[-1], kx=3, ky=3, s=0.1,
+              nxest=15, nyest=15)
+    for bad in (dict(kx=0), dict(ky=6), dict(iopt=2), dict(nxest=7), dict(s=-1.0), dict(xb=-1.0),
+                dict(ye=1.0), dict(s=0.0, nyest=14), dict(x=x[::-1].copy())):
+        assert F.regrid(**{**ok, **bad})["ier"] == 10, bad
+    assert F.regrid(**ok, wrk=np.zeros(10))["ier"] == 10
+    r = F.regrid(**ok)
+    assert F.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], 3, 3, x[::-1].copy(), y)[1] == 10
+    # a larger grid resident in HBM (device-pointer entry points), smoothing and least-squares
+    rng = np.random.default_rng(77)
+    mx, my = 300, 517
+    xs, ys = np.linspace(-1.5, 1.5, mx), np.sort(rng.uniform(-1.5, 1.5, my))
+    ys[0], ys[-1] = -1.5, 1.5
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    zz = np.exp(-(X ** 2 + Y ** 2)) + 0.3 * np.sin(2 * X) * np.cos(1.5 * Y) + 0.05 * rng.standard_normal(X.shape)
+    zd = torch.from_numpy(zz).to(eng.device)
+    for (kx, ky, s) in ((3, 3, mx * my * 0.0025), (5, 2, mx * my * 0.0026)):
+        o = O.regrid(0, xs, ys, zz, -1.5, 1.5, -1.5, 1.5, kx, ky, s, 60, 60)
+        r = F.regrid(0, xs, ys, zd, -1.5, 1.5, -1.5, 1.5, kx, ky, s, 60, 60, engine=eng)
+        assert o["ier"] == 0 and eng.grid_fpgrre_calls >= 3
+        _check_regrid(r, o, kx, ky)
+        out = torch.empty((mx, my), device=eng.device, dtype=torch.float64)
+        zg, ig = F.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], kx, ky, xs, ys, out=out, engine=eng)
+        zo, io = O.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], kx, ky, xs, ys)
+        assert ig == io == 0 and _same(zg.cpu().numpy(), zo)
+        assert abs(float(((zd - zg) ** 2).sum()) - r["fp"]) <= 1e-9 * r["fp"]

@@ -245,3 +245,126 @@ def test_batch_driver_equals_single_calls():
         assert np.array_equal(out["t"][b, :r["n"]], r["t"][:r["n"]])
         assert np.array_equal(out["c"][b, :r["n"] - 4], r["c"][:r["n"] - 4])
         assert tuple(out["stats"][b]) == r["stats"]
+
+
+# ------------------------------------------------------------------ gridded surfaces (dims = 2)
+from refdata import DAREGR_X, DAREGR_Y, DAREGR_Z, MNREGR_STEPS  # noqa: E402
+
+
+def _regrid_cases():
+    g = np.load(os.path.join(G, "regrid_golden.npz"))
+    for i in range(int(g["ncase"])):
+        p = f"g{i}_"
+        kx, ky, nxest, nyest, nx, ny, ier = (int(v) for v in g[p + "par"])
+        yield dict(i=i, x=g[p + "x"], y=g[p + "y"], z=g[p + "z"], kx=kx, ky=ky, nxest=nxest,
+                   nyest=nyest, nx=nx, ny=ny, ier=ier, s=float(g[p + "s"]), fp=float(g[p + "fp"]),
+                   tx=g[p + "tx"], ty=g[p + "ty"], c=g[p + "c"],
+                   ex=g[p + "ex"] if p + "ex" in g.files else None,
+                   ey=g[p + "ey"] if p + "ey" in g.files else None,
+                   ez=g[p + "ez"] if p + "ez" in g.files else None)
+
+
+def test_regrid_and_bispev_golden_bit_exact_in_netlib_mode():
+    """scipy's C translation of netlib regrid/bispev is reproduced bit for bit (n, knots, c, fp,
+    ier, values) with the documented reference-vs-netlib deviations switched off."""
+    O.set_netlib_compat(True)
+    try:
+        ncase = ncapped = 0
+        for q in _regrid_cases():
+            x, y = q["x"], q["y"]
+            r = O.regrid(0, x, y, q["z"], x[0], x[-1], y[0], y[-1], q["kx"], q["ky"], q["s"],
+                         q["nxest"], q["nyest"])
+            if q["ier"] != -1 and (q["nx"] == x.size + q["kx"] + 1 or q["ny"] == y.size + q["ky"] + 1):
+                # An axis was driven to the interpolation cap m+k+1 by knot insertion: scipy's C
+                # translation then rewrites the OTHER axis' knots (observed: one knot inserted
+                # without a count update), which neither netlib's fpregr nor the reference
+                # (core:12254-12264, plain `exit add_knots`) does.  Not comparable; 6 of 49 cases.
+                ncapped += 1
+                continue
+            assert r["ier"] == q["ier"], q["i"]
+            if q["ier"] == 10:
+                continue
+            assert (r["nx"], r["ny"]) == (q["nx"], q["ny"]), q["i"]
+            assert np.array_equal(r["tx"][:q["nx"]], q["tx"]) and np.array_equal(r["ty"][:q["ny"]], q["ty"])
+            assert np.array_equal(r["c"][:q["c"].size], q["c"]), q["i"]
+            assert r["fp"] == q["fp"], q["i"]
+            if q["ez"] is not None:
+                zz, ie = O.bispev(q["tx"], q["nx"], q["ty"], q["ny"], q["c"], q["kx"], q["ky"],
+                                  q["ex"], q["ey"])
+                assert ie == 0 and np.array_equal(zz.ravel(), q["ez"]), q["i"]
+            ncase += 1
+        assert ncase >= 40 and ncapped <= 6
+    finally:
+        O.set_netlib_compat(False)
+
+
+def _grid_residual(r, kx, ky, x, y, z):
+    zz, ie = O.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], kx, ky, x, y)
+    assert ie == 0
+    return float(((z.reshape(x.size, y.size) - zz) ** 2).sum())
+
+
+def test_regrid_reference_mode_properties():
+    """Default (reference) mode: same code with the reference's knot-direction arbiter and sum
+    association.  Self-consistency gates in the style of test/fitpack_grid_nd_tests.f90:1-21."""
+    for q in _regrid_cases():
+        x, y = q["x"], q["y"]
+        r = O.regrid(0, x, y, q["z"], x[0], x[-1], y[0], y[-1], q["kx"], q["ky"], q["s"],
+                     q["nxest"], q["nyest"])
+        if q["ier"] == 10:
+            assert r["ier"] == 10
+            continue
+        assert r["ier"] in (-2, -1, 0, 1, 2, 3)
+        res = _grid_residual(r, q["kx"], q["ky"], x, y, q["z"])
+        assert abs(res - r["fp"]) <= 1e-9 * max(1.0, res), (q["i"], res, r["fp"])
+        if r["ier"] == 0:
+            assert abs(r["fp"] - q["s"]) < 1e-3 * q["s"]
+        if r["ier"] == -1:
+            assert (r["nx"], r["ny"]) == (x.size + q["kx"] + 1, y.size + q["ky"] + 1) and res < 1e-18
+        if r["ier"] == -2:
+            assert (r["nx"], r["ny"]) == (2 * q["kx"] + 2, 2 * q["ky"] + 2)
+        for (t, n, k, xx) in ((r["tx"], r["nx"], q["kx"], x), (r["ty"], r["ny"], q["ky"], y)):
+            assert O.fpchec(xx, t[:n], n, k) == 0   # Schoenberg-Whitney holds for the chosen knots
+
+
+def test_mnregr_sequence_reference_assertions():
+    """reference test mnregr (test/fitpack_tests.f90:3170-3362): six regrid calls incl. iopt=1
+    continuations and prescribed knots, each followed by bispev; all must succeed."""
+    x, y, z = DAREGR_X, DAREGR_Y, DAREGR_Z
+    nxest = nyest = 17
+    state = dict(tx=np.zeros(nxest), ty=np.zeros(nyest), wrk=np.zeros(2000),
+                 iwrk=np.zeros(200, np.int32), nx=0, ny=0)
+    fps = []
+    for (iopt, kx, ky, s) in MNREGR_STEPS:
+        if iopt == -1:
+            state["nx"] = state["ny"] = 11
+            state["tx"][:] = 0.0
+            state["ty"][:] = 0.0
+            state["tx"][kx + 1:kx + 4] = [-0.5, 0.0, 0.5]
+            state["ty"][ky + 1:ky + 4] = [-0.5, 0.0, 0.5]
+        r = O.regrid(iopt, x, y, z, x[0], x[-1], y[0], y[-1], kx, ky, s, nxest, nyest,
+                     nx=state["nx"], ny=state["ny"], tx=state["tx"], ty=state["ty"],
+                     wrk=state["wrk"], iwrk=state["iwrk"], lwrk=2000, kwrk=200)
+        assert r["ier"] <= 0, (iopt, kx, ky, s, r["ier"])
+        state.update(nx=r["nx"], ny=r["ny"], tx=r["tx"], ty=r["ty"])
+        zz, ie = O.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], kx, ky, x, y)
+        assert ie == 0
+        res = float(((z.reshape(11, 11) - zz) ** 2).sum())
+        assert abs(res - r["fp"]) < 1e-10
+        fps.append(r["fp"])
+    assert fps[3] == 0.0 and abs(fps[1] - 0.22) < 0.22e-3     # interpolation; smoothing hit s
+    assert (state["nx"], state["ny"]) == (11, 11)
+
+
+def test_regrid_and_bispev_input_errors():
+    x, y, z = DAREGR_X, DAREGR_Y, DAREGR_Z
+    ok = dict(iopt=0, x=x, y=y, z=z, xb=x[0], xe=x[-1], yb=y[0], ye=y[-1], kx=3, ky=3, s=0.1,
+              nxest=15, nyest=15)
+    assert O.regrid(**ok)["ier"] <= 0
+    for bad in (dict(kx=0), dict(ky=6), dict(iopt=2), dict(nxest=7), dict(s=-1.0), dict(xb=-1.0),
+                dict(ye=1.0), dict(s=0.0, nyest=14), dict(x=x[::-1].copy())):
+        assert O.regrid(**{**ok, **bad})["ier"] == 10, bad
+    assert O.regrid(**ok, lwrk=10)["ier"] == 10
+    r = O.regrid(**ok)
+    zz, ie = O.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], 3, 3, x[::-1].copy(), y)
+    assert ie == 10
