@@ -14,6 +14,8 @@ own batch -- independent curves, no collective in the data path ("scaling": "wea
             buffers, H2D + tile transpose + fit + D2H all inside the timed region.
 `splev`   : second half of the metric (BASELINE config 5 shape: 2^20 k=5 splines x 954 points per
             GPU): GB/s at 16.5 algorithmic bytes/point, exact and fast modes, own roofline.
+`regrid`  : BASELINE config 4 (one 4096 x 4096 gridded smoothing fit, z resident in HBM) and
+            config 5b (bispev on that grid), with the serial CPU port timed on a 1024^2 sample.
 `roofline`: fit kernel against measured HBM peak (it is FP64 issue/latency bound, so this
             fraction is tiny by nature) -- the meaningful bound is in `fp64`.
 The reference arm times the CPU restatement of the reference algorithm (oracle/, OpenMP over
@@ -37,6 +39,7 @@ S = M * SIGMA * SIGMA  # 2.56
 B_PER_GPU = 1 << 20
 SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
 SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 22, 512, 3, 28   # config 3 shape, 2^22 curves/GPU
+GRID_M, GRID_K, GRID_SIGMA, GRID_NEST = 4096, 3, 0.05, 128          # config 4: 4096 x 4096 grid, kx=ky=3
 # DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum,
 # profiles/r01_final_kernels.md, profiles/r01_final_launches.md); the bench itself never runs under ncu.
 NCU_FIT_DRAM_BYTES_PER_FIT = 8.1 * (6.558e9 + 1.593e9) / 2.5e5 + (51.47e9 + 10.02e9) / (0.94 * 262144)
@@ -53,6 +56,7 @@ def parse():
     ap.add_argument("--curves", type=int, default=B_PER_GPU, help="curves per GPU per step")
     ap.add_argument("--no-splev", action="store_true")
     ap.add_argument("--no-shared", action="store_true")
+    ap.add_argument("--no-regrid", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -438,6 +442,92 @@ def main():
         del ysh, sho, r
         torch.cuda.empty_cache()
 
+    # ---------------------------------------------------------------- gridded surface (configs 4, 5b)
+    grid = None
+    if not args.no_regrid:
+        torch.cuda.empty_cache()
+        gm, gk = GRID_M, GRID_K
+        gx = np.linspace(-1.5, 1.5, gm)
+        gg = torch.Generator(device=dev)
+        gg.manual_seed(4 + rank)
+        GX = torch.from_numpy(gx).to(dev)[:, None]
+        GY = torch.from_numpy(gx).to(dev)[None, :]
+        gz = (torch.exp(-(GX ** 2 + GY ** 2)) + 0.3 * torch.sin(2 * GX) * torch.cos(1.5 * GY)
+              + GRID_SIGMA * torch.randn((gm, gm), generator=gg, device=dev, dtype=torch.float64))
+        gs = gm * gm * GRID_SIGMA ** 2
+
+        def grid_fit():
+            return fitpack_b200.regrid(0, gx, gx, gz, -1.5, 1.5, -1.5, 1.5, gk, gk, gs, GRID_NEST,
+                                       GRID_NEST, engine=eng)
+        for _ in range(max(1, min(args.warmup, 2))):
+            rg = grid_fit()
+        gsteps = max(1, min(args.steps, 3))
+        barrier()
+        l0 = eng.launches
+        ev0.record()
+        for _ in range(gsteps):
+            rg = grid_fit()
+        ev1.record()
+        barrier()
+        g_ms = max_over_ranks(ev0.elapsed_time(ev1) / gsteps)
+        ncalls = int(eng.grid_fpgrre_calls)
+        g_launch = int(eng.launches - l0)
+        gout = torch.empty((gm, gm), device=dev, dtype=torch.float64)
+        for _ in range(3):
+            fitpack_b200.bispev(rg["tx"], rg["nx"], rg["ty"], rg["ny"], rg["c"], gk, gk, gx, gx,
+                                out=gout, engine=eng)
+        torch.cuda.synchronize()
+        ev_ms = eng.last_kernel_ms()
+        resid = float(((gz - gout) ** 2).sum().item())
+        assert rg["ier"] == 0 and abs(resid - rg["fp"]) <= 1e-9 * rg["fp"], "regrid fp != residual of bispev"
+        # algorithmic bytes of one fpgrre solve: z is read twice (x reduction, residual pass)
+        g_bytes = 2 * 8 * gm * gm
+        grid = {
+            "config": {"workload": "gridded smoothing fit regrid: %d x %d grid in HBM, kx=ky=%d, "
+                                   "s=mx*my*sigma^2=%.0f, nest=%d (config 4); then bispev on the "
+                                   "same grid (config 5b)" % (gm, gm, gk, gs, GRID_NEST)},
+            "value": world / (g_ms * 1e-3), "unit": "grid fits/s", "ms_per_fit": g_ms,
+            "fpgrre_solves_per_fit": ncalls, "ms_per_fpgrre_solve": g_ms / max(ncalls, 1),
+            "nx": rg["nx"], "ny": rg["ny"], "ier": rg["ier"], "gpu_launches": g_launch,
+            "roofline": {"bound": "hbm", "kernel": "fpgrre solve (grid_plan + 2 x grid_apply + "
+                         "grid_resid): latency bound by the sequential Givens chain of the band QR "
+                         "(one rotation depends on the previous one), HBM fraction small by nature",
+                         "achieved": ncalls * g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": ncalls * g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_solve": g_bytes},
+            "bispev": {"ms": ev_ms, "value": gm * gm * 8 / (ev_ms * 1e-3) / 1e9, "unit": "GB/s",
+                       "roofline": {"bound": "hbm", "kernel": "grid_bispev_kernel",
+                                    "achieved": gm * gm * 8 / (ev_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                    "unit": "GB/s", "frac": gm * gm * 8 / (ev_ms * 1e-3) / 1e9 / hbm_peak,
+                                    "traffic": None, "peak_source": peak_src,
+                                    "algorithmic_bytes_per_point": 8}}}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            import oracle_lib as O
+            cm = 1024   # bounded CPU sample: the same surface on a 1024 x 1024 grid
+            cx = np.linspace(-1.5, 1.5, cm)
+            czz = gz[::gm // cm, ::gm // cm].contiguous().cpu().numpy()
+            t0 = time.perf_counter()
+            oc = O.regrid(0, cx, cx, czz, -1.5, 1.5, -1.5, 1.5, gk, gk, cm * cm * GRID_SIGMA ** 2,
+                          GRID_NEST, GRID_NEST)
+            dtc = time.perf_counter() - t0
+            czd = torch.from_numpy(czz).to(dev)
+            t0 = time.perf_counter()
+            og = fitpack_b200.regrid(0, cx, cx, czd, -1.5, 1.5, -1.5, 1.5, gk, gk,
+                                     cm * cm * GRID_SIGMA ** 2, GRID_NEST, GRID_NEST, engine=eng)
+            torch.cuda.synchronize()
+            dtg = time.perf_counter() - t0
+            grid["cpu_baseline"] = {
+                "value": 1.0 / dtc, "unit": "grid fits/s", "cores": 1, "kind": "port",
+                "sample": "one %d x %d regrid of the same surface (oracle port, serial like the "
+                          "reference); this GPU path on the same sample: %.1f ms vs %.1f ms CPU; "
+                          "same knots: %s" % (cm, cm, dtg * 1e3, dtc * 1e3,
+                                              bool(oc["nx"] == og["nx"] and oc["ny"] == og["ny"]
+                                                   and np.array_equal(oc["tx"], og["tx"])
+                                                   and np.array_equal(oc["ty"], og["ty"])))}
+        del gz, gout, GX, GY
+        torch.cuda.empty_cache()
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -471,7 +561,7 @@ def main():
                              % (2 * B * M * 8 / 1e9),
                        "success_fraction": ok_frac, "gathered_summary_curves": gathered},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "fp64": fp64, "splev": splev, "shared_lsq": shared,
+            "roofline": roof, "fp64": fp64, "splev": splev, "shared_lsq": shared, "regrid": grid,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

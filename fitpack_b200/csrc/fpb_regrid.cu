@@ -48,6 +48,8 @@ namespace {
 constexpr int kCs = 8;   // (cos,sin) slots per rotation-list row (band <= k+2 <= 7)
 constexpr int kAs = 8;   // row stride of the band / discontinuity matrices (k+2 <= 7 columns)
 constexpr int kSp = 6;   // row stride of the basis tables (k+1 <= 6 values)
+constexpr int kPlanChunk = 256;   // grid points staged per step for the sequential plan thread
+constexpr int kApplyChunk = 128;  // rotation-list rows staged per step in the apply kernel
 
 struct AxisDev {
     const double *x;  // [m] grid coordinates
@@ -108,7 +110,7 @@ __device__ void disc_row(const double *t, int n, int lmk, double *brow)
 }
 
 template <int K>
-__device__ void plan_axis(const AxisDev &A, double p)
+__device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *nr_s, double (*b_s)[kAs])
 {
     constexpr int K1 = K + 1, K2 = K + 2;
     const int n = A.n, m = A.m, nk1 = n - K1;
@@ -130,8 +132,10 @@ __device__ void plan_axis(const AxisDev &A, double p)
             disc_row<K>(A.t, n, lmk, A.b + (size_t)(lmk - 1) * kAs);
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    // ---- matrix half of the band QR (core:7222-7300), one thread ----
+    // ---- matrix half of the band QR (core:7222-7300): ONE thread, because every rotation depends
+    // on the previous one.  The other threads stage the basis rows / interval numbers of the next
+    // kPlanChunk grid points into shared memory so that the sequential thread never waits on a
+    // global load (its own stores are fire-and-forget).
     const double pinv = (p > 0.0) ? 1.0 / p : 1.0;
     double W[K2][K2];  // window of band rows base .. base+K2-1
 #pragma unroll
@@ -152,51 +156,75 @@ __device__ void plan_axis(const AxisDev &A, double p)
         for (int q = 0; q < K2; ++q) W[K2 - 1][q] = 0.0;
         ++base;
     };
-    for (int it = 0; it < m; ++it) {
-        const int number = A.nr[it];
-        for (;;) {
-            double h[K2];
-            int irot, src;
-            if (nrold == number) {
-                h[K2 - 1] = 0.0;  // h(iband) = 0 when iband = k2; overwritten below when iband = k1
-#pragma unroll
-                for (int j = 0; j < K1; ++j) h[j] = A.sp[(size_t)it * kSp + j];
-                irot = number;
-                src = it;
-            } else if (p <= 0.0) {
-                ++nrold;
-                continue;
-            } else {
-                iband = K2;
-#pragma unroll
-                for (int j = 0; j < K2; ++j) h[j] = mul(A.b[(size_t)nrold * kAs + j], pinv);
-                irot = nrold;
-                src = -1;
+    for (int it0 = 0; it0 < m; it0 += kPlanChunk) {
+        const int cnt = min(kPlanChunk, m - it0);
+        __syncthreads();  // the previous chunk is consumed
+        for (int e = threadIdx.x; e < cnt * K1; e += blockDim.x)
+            sp_s[e / K1][e % K1] = A.sp[(size_t)(it0 + e / K1) * kSp + e % K1];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) nr_s[e] = A.nr[it0 + e];
+        // smoothing rows this chunk can reach: b(nr(it0-1)+1 ..), at most one per grid point + 1
+        const int b0 = (it0 > 0) ? A.nr[it0 - 1] : 0;
+        if (p > 0.0)
+            for (int e = threadIdx.x; e < kPlanChunk * K2; e += blockDim.x) {
+                const int row = b0 + e / K2;
+                if (row < nk1 - K1) b_s[e / K2][e % K2] = A.b[(size_t)row * kAs + e % K2];
             }
-            while (base < irot) retire();
-            int skip = 0;
+        __syncthreads();
+        if (threadIdx.x != 0) continue;
+        for (int ii = 0; ii < cnt; ++ii) {
+            const int it = it0 + ii;
+            const int number = nr_s[ii];
+            for (;;) {
+                double h[K2];
+                int irot, src;
+                if (nrold == number) {
+                    h[K2 - 1] = 0.0;  // h(iband) = 0 when iband = k2; overwritten below when iband = k1
 #pragma unroll
-            for (int i = 0; i < K2; ++i) {
-                if (i < iband) {
-                    const double piv = h[i];
-                    double cs = 1.0, sn = 0.0;
-                    if (fp_is_zero(piv)) {
-                        skip |= 1 << i;
-                    } else {
-                        givens(piv, W[i][0], cs, sn);
+                    for (int j = 0; j < K1; ++j) h[j] = sp_s[ii][j];
+                    irot = number;
+                    src = it;
+                } else if (p <= 0.0) {
+                    ++nrold;
+                    continue;
+                } else {
+                    iband = K2;
+                    const int bi = nrold - b0;
+                    if (bi < kPlanChunk) {
 #pragma unroll
-                        for (int q = 1; q < K2; ++q)
-                            if (i + q < iband) rota(cs, sn, h[i + q], W[i][q]);
+                        for (int j = 0; j < K2; ++j) h[j] = mul(b_s[bi][j], pinv);
+                    } else {  // more interior knots than grid points in this chunk: read through
+#pragma unroll
+                        for (int j = 0; j < K2; ++j) h[j] = mul(A.b[(size_t)nrold * kAs + j], pinv);
                     }
-                    A.rcs[(size_t)r * kCs + i] = make_double2(cs, sn);
+                    irot = nrold;
+                    src = -1;
                 }
+                while (base < irot) retire();
+                int skip = 0;
+#pragma unroll
+                for (int i = 0; i < K2; ++i) {
+                    if (i < iband) {
+                        const double piv = h[i];
+                        double cs = 1.0, sn = 0.0;
+                        if (fp_is_zero(piv)) {
+                            skip |= 1 << i;
+                        } else {
+                            givens(piv, W[i][0], cs, sn);
+#pragma unroll
+                            for (int q = 1; q < K2; ++q)
+                                if (i + q < iband) rota(cs, sn, h[i + q], W[i][q]);
+                        }
+                        A.rcs[(size_t)r * kCs + i] = make_double2(cs, sn);
+                    }
+                }
+                A.rmeta[r] = make_int4(src, irot, iband, skip);
+                ++r;
+                if (nrold == number) break;
+                ++nrold;
             }
-            A.rmeta[r] = make_int4(src, irot, iband, skip);
-            ++r;
-            if (nrold == number) break;
-            ++nrold;
         }
     }
+    if (threadIdx.x != 0) return;
 #pragma unroll
     for (int i = 0; i < K2; ++i) retire();
     A.info[0] = r;
@@ -205,19 +233,34 @@ __device__ void plan_axis(const AxisDev &A, double p)
 
 __global__ void __launch_bounds__(256) grid_plan_kernel(AxisDev X, AxisDev Y, double p)
 {
+    __shared__ double sp_s[kPlanChunk][kSp];
+    __shared__ int nr_s[kPlanChunk];
+    __shared__ double b_s[kPlanChunk][kAs];  // discontinuity rows the current chunk can reach
     const AxisDev &A = (blockIdx.x == 0) ? X : Y;
     switch (A.k) {
-    case 1: plan_axis<1>(A, p); break;
-    case 2: plan_axis<2>(A, p); break;
-    case 3: plan_axis<3>(A, p); break;
-    case 4: plan_axis<4>(A, p); break;
-    case 5: plan_axis<5>(A, p); break;
+    case 1: plan_axis<1>(A, p, sp_s, nr_s, b_s); break;
+    case 2: plan_axis<2>(A, p, sp_s, nr_s, b_s); break;
+    case 3: plan_axis<3>(A, p, sp_s, nr_s, b_s); break;
+    case 4: plan_axis<4>(A, p, sp_s, nr_s, b_s); break;
+    case 5: plan_axis<5>(A, p, sp_s, nr_s, b_s); break;
     default: break;
     }
 }
 
 // Right-hand-side half of one reduction pass.  Thread j owns right-hand side j: source row `s`
 // contributes in[s*in_ld + j]; the reduced column goes to out[j*out_ld + row], row < nout.
+// The source values are streamed through a per-thread ring in shared memory filled by cp.async
+// (kRing rows ahead, no register is tied to a load in flight), the rotation list is staged per
+// chunk by the whole CTA.
+constexpr int kRing = 16;
+
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src)
+                 : "memory");
+}
+
 template <int K>
 __global__ void __launch_bounds__(64) grid_apply_kernel(const double *__restrict__ in, long long in_ld,
                                                         int nrhs, const int4 *__restrict__ rmeta,
@@ -227,46 +270,64 @@ __global__ void __launch_bounds__(64) grid_apply_kernel(const double *__restrict
                                                         int nout)
 {
     constexpr int K2 = K + 2;
-    constexpr int D = 4;  // source rows requested ahead of use
+    __shared__ int4 meta_s[kApplyChunk];
+    __shared__ double2 cs_s[kApplyChunk][K2];
+    __shared__ double ring[kRing][64];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nrhs) return;
+    const bool live = j < nrhs;
+    const int jj = live ? j : nrhs - 1;  // idle threads shadow the last column (no stores)
     const int nrows = info[0];
     double W[K2];
 #pragma unroll
     for (int i = 0; i < K2; ++i) W[i] = 0.0;
     int base = 0;
-    double *o = out + (size_t)j * out_ld;
-    double pre[D];
+    double *o = out + (size_t)jj * out_ld;
+    const double *src = in + jj;
 #pragma unroll
-    for (int u = 0; u < D; ++u) pre[u] = (u < nsrc) ? in[(size_t)u * in_ld + j] : 0.0;
-    for (int r = 0; r < nrows; ++r) {
-        const int4 mt = __ldg(&rmeta[r]);
-        while (base < mt.y) {
-            if (base < nout) o[base] = W[0];
+    for (int u = 0; u < kRing; ++u) {  // one commit group per source row, empty past the end
+        if (u < nsrc) cp_async8(&ring[u][threadIdx.x], src + (size_t)u * in_ld);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    for (int r0 = 0; r0 < nrows; r0 += kApplyChunk) {
+        const int cnt = min(kApplyChunk, nrows - r0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) meta_s[e] = rmeta[r0 + e];
+        for (int e = threadIdx.x; e < cnt * K2; e += blockDim.x)
+            cs_s[e / K2][e % K2] = rcs[(size_t)(r0 + e / K2) * kCs + e % K2];
+        __syncthreads();
+        for (int rr = 0; rr < cnt; ++rr) {
+            const int4 mt = meta_s[rr];
+            while (base < mt.y) {
+                if (live && base < nout) o[base] = W[0];
 #pragma unroll
-            for (int i = 0; i < K2 - 1; ++i) W[i] = W[i + 1];
-            W[K2 - 1] = 0.0;
-            ++base;
-        }
-        double right = 0.0;
-        if (mt.x >= 0) {  // data rows come in order 0, 1, 2, ...
-            right = pre[0];
+                for (int i = 0; i < K2 - 1; ++i) W[i] = W[i + 1];
+                W[K2 - 1] = 0.0;
+                ++base;
+            }
+            double right = 0.0;
+            if (mt.x >= 0) {  // data rows come in order 0, 1, 2, ...: row mt.x sits in slot mt.x % kRing
+                asm volatile("cp.async.wait_group %0;\n" ::"n"(kRing - 1) : "memory");
+                double *slot = &ring[mt.x & (kRing - 1)][threadIdx.x];
+                right = *slot;
+                const int nx = mt.x + kRing;
+                if (nx < nsrc) cp_async8(slot, src + (size_t)nx * in_ld);
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+            }
 #pragma unroll
-            for (int u = 0; u < D - 1; ++u) pre[u] = pre[u + 1];
-            const int nx = mt.x + D;
-            pre[D - 1] = (nx < nsrc) ? in[(size_t)nx * in_ld + j] : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < K2; ++i) {
-            if (i < mt.z && !((mt.w >> i) & 1)) {
-                const double2 cs = __ldg(&rcs[(size_t)r * kCs + i]);
-                rota(cs.x, cs.y, right, W[i]);
+            for (int i = 0; i < K2; ++i) {
+                if (i < mt.z && !((mt.w >> i) & 1)) {
+                    const double2 cs = cs_s[rr][i];
+                    rota(cs.x, cs.y, right, W[i]);
+                }
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < K2; ++i)
-        if (base + i < nout) o[base + i] = W[i];
+        for (int i = 0; i < K2; ++i)
+            if (base + i < nout) o[base + i] = W[i];
+    }
 }
 
 void launch_apply(int k, const double *in, long long in_ld, int nrhs, const AxisDev &A, int nsrc,
@@ -406,35 +467,62 @@ __global__ void grid_eval_basis_kernel(const double *__restrict__ xg, int m, con
     lidx[i] = l - k1;
 }
 
-constexpr int kEvRows = 16, kEvCols = 128;
+constexpr int kEvRows = 32, kEvCols = 128;
 
-// z(i1,i2) = sum_cx wx(cx,i1) * dot(c(lx+cx, ly : ly+ky), wy(:,i2))   (core:2219-2222 order)
+// z(i1,i2) = sum_cx wx(cx,i1) * dot(c(lx+cx, ly : ly+ky), wy(:,i2))   (core:2219-2222 order).
+// One thread per output column, kEvRows rows per CTA.  The (kx+1) x (ky+1) coefficient support of
+// a thread only changes when the row's x interval changes, so it is kept in registers across rows
+// (the kernel is otherwise bound by the LSU: 16 coefficient loads per 8-byte output).
+// KX1/KY1 = compile-time k+1 (0: run-time degrees, up to 6 x 6 with predicates).
+template <int KX1, int KY1>
 __global__ void __launch_bounds__(kEvCols) grid_bispev_kernel(
     const double *__restrict__ c, int nk1y, const double *__restrict__ wx, const int *__restrict__ lx,
-    int k1x, int mx, const double *__restrict__ wyt, const int *__restrict__ ly, int k1y, int my,
+    int k1x_rt, int mx, const double *__restrict__ wyt, const int *__restrict__ ly, int k1y_rt, int my,
     double *__restrict__ z)
 {
+    constexpr int NX = KX1 ? KX1 : 6, NY = KY1 ? KY1 : 6;
+    const int k1x = KX1 ? KX1 : k1x_rt, k1y = KY1 ? KY1 : k1y_rt;
+    __shared__ double wx_s[kEvRows][kSp];
+    __shared__ int lx_s[kEvRows];
+    const int r0 = blockIdx.y * kEvRows;
+    for (int e = threadIdx.x; e < kEvRows * kSp; e += kEvCols) {
+        const int i1 = r0 + e / kSp;
+        wx_s[e / kSp][e % kSp] = (i1 < mx) ? wx[(size_t)i1 * kSp + e % kSp] : 0.0;
+    }
+    for (int e = threadIdx.x; e < kEvRows; e += kEvCols) lx_s[e] = (r0 + e < mx) ? lx[r0 + e] : -1;
+    __syncthreads();
     const int i2 = blockIdx.x * kEvCols + threadIdx.x;
     if (i2 >= my) return;
-    const int r0 = blockIdx.y * kEvRows;
-    double wy[6];
+    double wy[NY];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) wy[q] = (q < k1y) ? wyt[(size_t)i2 * kSp + q] : 0.0;
+    for (int q = 0; q < NY; ++q) wy[q] = (q < k1y) ? wyt[(size_t)i2 * kSp + q] : 0.0;
     const int l2 = ly[i2];
-    for (int rr = 0; rr < kEvRows; ++rr) {
-        const int i1 = r0 + rr;
-        if (i1 >= mx) break;
-        const double *cc = c + (size_t)lx[i1] * nk1y + l2;
-        double sp = 0.0;
-        for (int cx = 0; cx < k1x; ++cx) {
-            const double pw = wx[(size_t)i1 * kSp + cx];
-            double dot = 0.0;
+    double cs[NX][NY];
+    int lcur = -1;
+    const int nrow = min(kEvRows, mx - r0);
+    for (int rr = 0; rr < nrow; ++rr) {
+        const int l1 = lx_s[rr];
+        if (l1 != lcur) {  // uniform across the CTA
+            lcur = l1;
+            const double *cc = c + (size_t)l1 * nk1y + l2;
 #pragma unroll
-            for (int cy = 0; cy < 6; ++cy)
-                if (cy < k1y) dot = add(dot, mul(__ldg(&cc[(size_t)cx * nk1y + cy]), wy[cy]));
-            sp = add(sp, mul(pw, dot));
+            for (int cx = 0; cx < NX; ++cx)
+#pragma unroll
+                for (int cy = 0; cy < NY; ++cy)
+                    cs[cx][cy] = (cx < k1x && cy < k1y) ? __ldg(&cc[(size_t)cx * nk1y + cy]) : 0.0;
         }
-        z[(size_t)i1 * my + i2] = sp;
+        double sp = 0.0;
+#pragma unroll
+        for (int cx = 0; cx < NX; ++cx) {
+            if (cx < k1x) {
+                double dot = 0.0;
+#pragma unroll
+                for (int cy = 0; cy < NY; ++cy)
+                    if (cy < k1y) dot = add(dot, mul(cs[cx][cy], wy[cy]));
+                sp = add(sp, mul(wx_s[rr][cx], dot));
+            }
+        }
+        z[(size_t)(r0 + rr) * my + i2] = sp;
     }
 }
 
@@ -977,8 +1065,19 @@ int32_t bispev_run(fpb_engine *eng, const double *tx, int nx, const double *ty, 
     grid_eval_basis_kernel<<<(mx + 127) / 128, 128, 0, st>>>(dx, mx, dt, nx, kx, dw, dl);
     grid_eval_basis_kernel<<<(my + 127) / 128, 128, 0, st>>>(dx + mx, my, dt + nx, ny, ky, dw + (size_t)mx * kSp, dl + mx);
     cudaEventRecord(eng->ev0, st);
-    grid_bispev_kernel<<<dim3((my + kEvCols - 1) / kEvCols, (mx + kEvRows - 1) / kEvRows), kEvCols, 0, st>>>(
-        dc, nk1y, dw, dl, kx + 1, mx, dw + (size_t)mx * kSp, dl + mx, ky + 1, my, z_dev);
+    {
+        const dim3 gridd((my + kEvCols - 1) / kEvCols, (mx + kEvRows - 1) / kEvRows);
+        const double *dwy = dw + (size_t)mx * kSp;
+        const int *dly = dl + mx;
+#define FPB_BISPEV(A, B) grid_bispev_kernel<A, B><<<gridd, kEvCols, 0, st>>>(dc, nk1y, dw, dl, kx + 1, mx, dwy, dly, ky + 1, my, z_dev)
+        if (kx == ky && kx == 1) FPB_BISPEV(2, 2);
+        else if (kx == ky && kx == 2) FPB_BISPEV(3, 3);
+        else if (kx == ky && kx == 3) FPB_BISPEV(4, 4);
+        else if (kx == ky && kx == 4) FPB_BISPEV(5, 5);
+        else if (kx == ky && kx == 5) FPB_BISPEV(6, 6);
+        else FPB_BISPEV(0, 0);
+#undef FPB_BISPEV
+    }
     cudaEventRecord(eng->ev1, st);
     eng->timed = true;
     eng->launches += 3;
