@@ -75,6 +75,12 @@ SYMBOLS = {
     "fp_bispev_dev_c": (_I32, [_VP, _VP, _I32, _VP, _I32, _VP, _I32, _I32, _VP, _I32, _VP, _I32,
                                _VP, _VP]),
     "fpb_engine_grid_fpgrre_calls": (_I64, [_VP]),
+    "fp_splder_c": (None, [_VP, _I32, _VP, _I32, _I32, _VP, _VP, _I32, _I32, _VP, _VP]),
+    "fp_spalde_c": (None, [_VP, _I32, _VP, _I32, _F64, _VP, _VP]),
+    "fp_splint_c": (_F64, [_VP, _I32, _VP, _I32, _F64, _F64, _VP]),
+    "fitpack_curve_c_integral": (_F64, [_VP, _F64, _F64]),
+    "fitpack_curve_c_derivative": (_F64, [_VP, _F64, _I32, _VP]),
+    "fitpack_curve_c_all_derivatives": (_I32, [_VP, _F64, _VP]),
 }
 
 _lib = None

@@ -14,7 +14,8 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libfitpack_b200.so")
 
-SOURCES = ["fpb_curfit.cu", "fpb_splev.cu", "fpb_shared.cu", "fpb_util.cu", "fpb_regrid.cu", "fpb_engine.cu",
+SOURCES = ["fpb_curfit.cu", "fpb_splev.cu", "fpb_shared.cu", "fpb_util.cu", "fpb_regrid.cu", "fpb_calculus.cu",
+           "fpb_engine.cu",
            "fpb_curve.cpp"]
 
 # -fmad=false: the reference is built without FMA contraction (gfortran, baseline x86-64);

@@ -198,3 +198,39 @@ def bispev(tx, nx, ty, ny, c, kx, ky, x, y, out=None, engine=None):
     if ier <= FPB_ERR_CUDA:
         raise FitpackB200Error("fp_bispev_c: %s" % lib().fpb_last_error().decode())
     return z[:mx * my].reshape(mx, my), int(ier)
+
+
+# ------------------------------------------------------------------ spline calculus
+def splder(t, n, c, k, nu, x, e=OUTSIDE_EXTRAPOLATE):
+    """splder (reference core:17699-17802) through fp_splder_c; returns (y, ier, wrk)."""
+    t, c, x = _f64(t), _f64(c), _f64(x)
+    m = x.size
+    y = np.zeros(max(m, 1))
+    wrk = np.zeros(max(int(n), 1))
+    ier_ = C.c_int32(0)
+    lib().fp_splder_c(_p(t), int(n), _p(c), int(k), int(nu), _p(x), _p(y), m, int(e), _p(wrk),
+                      C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_splder_c: %s" % lib().fpb_last_error().decode())
+    return y[:m], ier_.value, wrk
+
+
+def spalde(t, n, c, k1, x):
+    """spalde (reference core:16865-16895) through fp_spalde_c; returns (d[k1], ier)."""
+    t, c = _f64(t), _f64(c)
+    d = np.zeros(max(int(k1), 1))
+    ier_ = C.c_int32(0)
+    lib().fp_spalde_c(_p(t), int(n), _p(c), int(k1), float(x), _p(d), C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_spalde_c: %s" % lib().fpb_last_error().decode())
+    return d, ier_.value
+
+
+def splint(t, n, c, k, a, b):
+    """splint (reference core:17919-17939) through fp_splint_c; returns (integral, wrk)."""
+    t, c = _f64(t), _f64(c)
+    wrk = np.zeros(max(int(n), 1))
+    v = lib().fp_splint_c(_p(t), int(n), _p(c), int(k), float(a), float(b), _p(wrk))
+    if v != v and lib().fpb_device_count() == 0:
+        raise FitpackB200Error("fp_splint_c: %s" % lib().fpb_last_error().decode())
+    return float(v), wrk

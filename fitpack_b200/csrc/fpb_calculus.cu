@@ -1,0 +1,346 @@
+// fpb_calculus.cu -- spline calculus on a fitted curve: splder, spalde, splint,
+// the routines behind fitpack_curve_c_derivative / _all_derivatives / _integral.
+//
+// Reference: splder core:17699-17802, spalde core:16865-16895, fpader core:1546-1603,
+// splint core:17919-17939, fpintb core:8058-8166; C binding src/fitpack_core_c.f90:157-175,
+// 207-213 ("core" = src/fitpack_core.F90).
+//
+// The derivative of order nu of a degree-k spline is the degree k-nu spline on the knots
+// t(nu+1 : n-nu) whose coefficients come from de Boor's difference recurrence (core:17736-17753);
+// a one-thread kernel runs that recurrence (O(n*nu), serial) and the EVALUATION then goes through
+// the same splev kernel as fp_splev_c (identical arithmetic: fpbspl of degree k-nu + dot product),
+// so many-point derivative evaluation is as parallel as splev.  spalde / splint are O(k^2) / O(n)
+// scalar recurrences per call: one-thread kernels, same IEEE operations in the same order (no FMA).
+#include "fpb_common.cuh"
+#include "fpb_engine.h"
+
+#include <cstring>
+#include <vector>
+
+#include "../../include/fitpack_b200.h"
+
+namespace fpb {
+
+namespace {
+
+// fp_knot_interval, core:2432-2473: smallest l >= l_start with x < t(l+1), capped at l_max
+__device__ __forceinline__ int knot_interval(const double *t, double x, int l_start, int l_max)
+{
+    int l = l_start;
+    while (l < l_max && x >= t[l]) ++l;
+    return l;
+}
+
+// derivative coefficients, core:17736-17753
+__global__ void deriv_coef_kernel(const double *__restrict__ t, int n, const double *__restrict__ c,
+                                  int k, int nu, double *__restrict__ wrk)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int k1 = k + 1, nk1 = n - k1;
+    auto T = [&](int i) { return t[i - 1]; };
+    for (int i = 0; i < nk1; ++i) wrk[i] = c[i];
+    int l = 1, nk2 = nk1;
+    for (int j = 1; j <= nu; ++j) {
+        const double ak = (double)(k1 - j);
+        nk2 = nk2 - 1;
+        int l1 = l;
+        for (int i = 1; i <= nk2; ++i) {
+            l1 = l1 + 1;
+            const int l2 = l1 + k1 - j;
+            const double fac = sub(T(l2), T(l1));
+            if (fac > 0.0) wrk[i - 1] = mul(ak, sub(wrk[i], wrk[i - 1])) / fac;
+        }
+        l = l + 1;
+    }
+}
+
+// nu == k: the derivative is piecewise constant, y = wrk(l-k) (core:17793-17796)
+__global__ void flat_deriv_kernel(const double *__restrict__ t, int n, const double *__restrict__ wrk,
+                                  int k, const double *__restrict__ x, double *__restrict__ y, int m, int e)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int k1 = k + 1, nk1 = n - k1;
+    const double tb = t[k1 - 1], te = t[nk1];
+    const double arg = x[i];
+    if ((arg < tb || arg > te) && e == 1) {
+        y[i] = 0.0;
+        return;
+    }
+    int l = k1;  // rightmost l in [k1, nk1] with t(l) <= arg (floor k1)
+    while (l < nk1 && arg >= t[l]) ++l;
+    y[i] = wrk[l - k - 1];
+}
+
+// spalde + fpader, core:16865-16895, 1546-1603
+__global__ void spalde_kernel(const double *__restrict__ t, int n, const double *__restrict__ c, int k1,
+                              double x, double *__restrict__ d, int *__restrict__ ier)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    auto T = [&](int i) { return t[i - 1]; };
+    const int nk1 = n - k1;
+    *ier = IER_INPUT;
+    if (x < T(k1) || x > T(nk1 + 1)) return;
+    const int l = knot_interval(t, x, k1, nk1);
+    if (T(l) >= T(l + 1)) return;
+    *ier = IER_OK;
+    double h[8], dd[8];
+    const int lk = l - k1;
+    for (int i = 1; i <= k1; ++i) h[i] = c[i + lk - 1];
+    int kj = k1;
+    double fac = 1.0;
+    for (int j = 1; j <= k1; ++j) {
+        int ki = kj;
+        if (j > 1) {
+            int i = k1;
+            for (int jj = j; jj <= k1; ++jj) {
+                const int li = i + lk, lj = li + kj;
+                h[i] = sub(h[i], h[i - 1]) / sub(T(lj), T(li));
+                --i;
+            }
+        }
+        for (int i = j; i <= k1; ++i) dd[i] = h[i];
+        if (j < k1) {
+            for (int jj = j + 1; jj <= k1; ++jj) {
+                ki = ki - 1;
+                int i = k1;
+                for (int j2 = jj; j2 <= k1; ++j2) {
+                    const int li = i + lk, lj = li + ki;
+                    dd[i] = add(mul(sub(x, T(li)), dd[i]), mul(sub(T(lj), x), dd[i - 1])) / sub(T(lj), T(li));
+                    --i;
+                }
+            }
+        }
+        d[j - 1] = mul(dd[k1], fac);
+        const double ak = (double)(k1 - j);
+        fac = mul(fac, ak);
+        kj = kj - 1;
+    }
+}
+
+// splint + fpintb, core:17919-17939, 8058-8166: bint(nk1) and the integral out[0]
+__global__ void splint_kernel(const double *__restrict__ t, int n, const double *__restrict__ c, int k,
+                              double x, double y, double *__restrict__ bint, double *__restrict__ out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    auto T = [&](int i) { return t[i - 1]; };
+    const int k1 = k + 1, nk1 = n - k1;
+    const double ak = (double)k1;
+    for (int i = 0; i < nk1; ++i) bint[i] = 0.0;
+    bool done = fp_equal(x, y);
+    double a = fmin(x, y), b = fmax(x, y);
+    const bool lmin = x > y;
+    if (!done) {
+        a = fmax(T(k1), a);
+        b = fmin(T(nk1 + 1), b);
+        if (a > b) done = true;
+    }
+    if (!done) {
+        double aint[8], h[8], h1[8];
+        int l = k1, ia = 0;
+        double arg = a;
+        for (int it = 1; it <= 2; ++it) {
+            l = knot_interval(t, arg, l, nk1);
+            aint[1] = sub(arg, T(l)) / sub(T(l + 1), T(l));
+            for (int i = 2; i <= k1; ++i) aint[i] = 0.0;
+            h1[1] = 1.0;
+            for (int j = 1; j <= k; ++j) {
+                h[1] = 0.0;
+                for (int i = 1; i <= j; ++i) {
+                    const int li = l + i, lj = li - j;
+                    const double f = h1[i] / sub(T(li), T(lj));
+                    h[i] = add(h[i], mul(f, sub(T(li), arg)));
+                    h[i + 1] = mul(f, sub(arg, T(lj)));
+                }
+                const int j1 = j + 1;
+                for (int i = 1; i <= j1; ++i) {
+                    const int li = l + i, lj = li - j1;
+                    aint[i] = add(aint[i], mul(h[i], sub(arg, T(lj))) / sub(T(li), T(lj)));
+                    h1[i] = h[i];
+                }
+            }
+            if (it < 2) {
+                int lk = l - k;
+                ia = lk;
+                for (int i = 1; i <= k1; ++i) {
+                    bint[lk - 1] = -aint[i];
+                    ++lk;
+                }
+                arg = b;
+            }
+        }
+        int lk = l - k;
+        const int ib = lk - 1;
+        for (int i = 1; i <= k1; ++i) {
+            bint[lk - 1] = add(bint[lk - 1], aint[i]);
+            ++lk;
+        }
+        for (int i = ia; i <= ib; ++i) bint[i - 1] = add(bint[i - 1], 1.0);
+        const double f = 1.0 / ak;
+        for (int i = 1; i <= nk1; ++i) bint[i - 1] = mul(mul(bint[i - 1], sub(T(i + k1), T(i))), f);
+        if (lmin)
+            for (int i = 0; i < nk1; ++i) bint[i] = -bint[i];
+    }
+    double s = 0.0;
+    for (int i = 0; i < nk1; ++i) s = add(s, mul(c[i], bint[i]));
+    out[0] = s;
+}
+
+struct DevSel {
+    int prev = -1;
+    bool ok = true;
+    explicit DevSel(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cuda_ok(cudaSetDevice(dev), "cudaSetDevice");
+    }
+    ~DevSel()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// upload knots and coefficients of one spline into the engine's calculus buffers
+bool upload_spline(fpb_engine *eng, const double *t, const double *c, int n, double **dt, double **dc,
+                   double **dw)
+{
+    DevBuf *B = eng->calc;
+    if (!B[0].reserve((size_t)n * 8) || !B[1].reserve((size_t)n * 8) || !B[2].reserve((size_t)n * 8 + 64))
+        return false;
+    *dt = B[0].as<double>();
+    *dc = B[1].as<double>();
+    *dw = B[2].as<double>();
+    return cuda_ok(cudaMemcpyAsync(*dt, t, (size_t)n * 8, cudaMemcpyHostToDevice, eng->stream), "H2D t") &&
+           cuda_ok(cudaMemcpyAsync(*dc, c, (size_t)n * 8, cudaMemcpyHostToDevice, eng->stream), "H2D c");
+}
+
+}  // namespace
+
+}  // namespace fpb
+
+using namespace fpb;
+
+extern "C" {
+
+// reference: src/fitpack_core_c.f90:157-165 -> splder core:17699-17802
+void fp_splder_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP_SIZE nu, const FP_REAL *x,
+                 FP_REAL *y, FP_SIZE m, FP_FLAG e, FP_REAL *wrk, FP_FLAG *ier)
+{
+    *ier = FPB_INPUT_ERROR;
+    if (nu < 0 || nu > k) return;
+    if (m < 1) return;
+    if (k < 1 || k > 5 || n < 2 * (k + 1)) return;  // not a valid spline: nothing safe to evaluate
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    DevSel g(eng->device);
+    const int nk1 = n - k - 1;
+    double *dt, *dc, *dw;
+    if (!upload_spline(eng, t, c, n, &dt, &dc, &dw)) {
+        *ier = FPB_ERR_ALLOC;
+        return;
+    }
+    deriv_coef_kernel<<<1, 32, 0, eng->stream>>>(dt, n, dc, k, nu, dw);
+    eng->launches++;
+    if (!cuda_ok(cudaMemcpyAsync(wrk, dw, (size_t)nk1 * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H wrk") ||
+        !cuda_ok(cudaStreamSynchronize(eng->stream), "sync")) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    const int kk = k - nu;
+    if (kk >= 1) {
+        // degree k-nu spline on t(nu+1 : n-nu): evaluated by the splev kernel.  splder has no
+        // "nearest boundary" policy: anything but 1 / 2 extrapolates (core:17764-17775)
+        const FP_FLAG es = (e == 1) ? 1 : (e == 2) ? 2 : 0;
+        FP_FLAG ie = FPB_INPUT_ERROR;
+        fp_splev_c(t + nu, n - 2 * nu, wrk, kk, x, y, m, es, &ie);
+        *ier = (ie == FPB_INVALID_RANGE) ? FPB_INSUFFICIENT_STORAGE : ie;  // splder reports code 1
+        return;
+    }
+    DevBuf *B = eng->calc;
+    if (!B[3].reserve((size_t)m * 8) || !B[4].reserve((size_t)m * 8)) {
+        *ier = FPB_ERR_ALLOC;
+        return;
+    }
+    bool ok = cuda_ok(cudaMemcpyAsync(B[3].ptr, x, (size_t)m * 8, cudaMemcpyHostToDevice, eng->stream), "H2D x");
+    if (ok) {
+        flat_deriv_kernel<<<(m + 127) / 128, 128, 0, eng->stream>>>(dt, n, dw, k, B[3].as<double>(),
+                                                                     B[4].as<double>(), m, e);
+        eng->launches++;
+    }
+    long long upto = m;
+    int result = FPB_OK;
+    if (e == 2) {  // y is filled up to the first point outside the support (core:17771-17773)
+        const double tb = t[k], te = t[n - k - 1];
+        for (long long i = 0; i < m; ++i)
+            if (x[i] < tb || x[i] > te) {
+                upto = i;
+                result = FPB_INSUFFICIENT_STORAGE;
+                break;
+            }
+    }
+    if (ok && upto > 0)
+        ok = cuda_ok(cudaMemcpyAsync(y, B[4].ptr, (size_t)upto * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H y");
+    ok = ok && cuda_ok(cudaStreamSynchronize(eng->stream), "sync");
+    *ier = ok ? result : FPB_ERR_CUDA;
+}
+
+// reference: src/fitpack_core_c.f90:168-175 -> spalde core:16865-16895
+void fp_spalde_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k1, FP_REAL x, FP_REAL *d,
+                 FP_FLAG *ier)
+{
+    *ier = FPB_INPUT_ERROR;
+    if (k1 < 2 || k1 > 6 || n < 2 * k1) return;
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    DevSel g(eng->device);
+    double *dt, *dc, *dw;
+    if (!upload_spline(eng, t, c, n, &dt, &dc, &dw)) {
+        *ier = FPB_ERR_ALLOC;
+        return;
+    }
+    int *dier = reinterpret_cast<int *>(dw + 6);
+    spalde_kernel<<<1, 32, 0, eng->stream>>>(dt, n, dc, k1, x, dw, dier);
+    eng->launches++;
+    double hd[8];
+    if (!cuda_ok(cudaMemcpyAsync(hd, dw, 8 * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H d") ||
+        !cuda_ok(cudaStreamSynchronize(eng->stream), "sync")) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    int hier;
+    std::memcpy(&hier, &hd[6], sizeof(int));
+    *ier = hier;
+    if (hier == FPB_OK)
+        for (int j = 0; j < k1; ++j) d[j] = hd[j];
+}
+
+// reference: src/fitpack_core_c.f90:207-213 -> splint core:17919-17939
+FP_REAL fp_splint_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP_REAL a, FP_REAL b,
+                    FP_REAL *wrk)
+{
+    const double nan = __builtin_nan("");
+    if (k < 1 || k > 5 || n < 2 * (k + 1)) return nan;
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) return nan;
+    DevSel g(eng->device);
+    const int nk1 = n - k - 1;
+    double *dt, *dc, *dw;
+    if (!upload_spline(eng, t, c, n, &dt, &dc, &dw)) return nan;
+    splint_kernel<<<1, 32, 0, eng->stream>>>(dt, n, dc, k, a, b, dw, dw + n);
+    eng->launches++;
+    std::vector<double> h((size_t)n + 1);
+    if (!cuda_ok(cudaMemcpyAsync(h.data(), dw, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H") ||
+        !cuda_ok(cudaStreamSynchronize(eng->stream), "sync"))
+        return nan;
+    if (wrk)
+        for (int i = 0; i < nk1; ++i) wrk[i] = h[i];
+    return h[n];
+}
+
+}  // extern "C"

@@ -291,6 +291,41 @@ void fitpack_curve_c_eval_many(fitpack_curve_c *self, FP_SIZE npts, FP_REAL *x, 
     if (ierr) *ierr = ier;
 }
 
+// curve_derivative / curve_derivatives, fitpack_curves.f90:499-532, 606-618 (C handle :294-307):
+// order < 0 is taken as 0; the curve's bc is passed as splder's extrapolation flag
+FP_REAL fitpack_curve_c_derivative(fitpack_curve_c *self, FP_REAL x, FP_SIZE order, FP_SIZE *ierr)
+{
+    Curve *cv = ensure(self);
+    double y = 0.0;
+    int ier = FPB_INPUT_ERROR;
+    if (cv && cv->knots >= 2 * (cv->order + 1)) {
+        std::vector<double> wk(cv->knots);
+        fp_splder_c(cv->t.data(), cv->knots, cv->c.data(), cv->order, order > 0 ? order : 0, &x, &y, 1,
+                    cv->bc, wk.data(), &ier);
+    }
+    if (ierr) *ierr = ier;
+    return y;
+}
+
+// curve_all_derivatives, fitpack_curves.f90:543-565 (C handle :310-323): ddx(1:order+1)
+FP_FLAG fitpack_curve_c_all_derivatives(fitpack_curve_c *self, FP_REAL x, FP_REAL *ddx)
+{
+    Curve *cv = ensure(self);
+    int ier = FPB_INPUT_ERROR;
+    if (cv && ddx && cv->knots >= 2 * (cv->order + 1))
+        fp_spalde_c(cv->t.data(), cv->knots, cv->c.data(), cv->order + 1, x, ddx, &ier);
+    return ier;
+}
+
+// integral, fitpack_curves.f90 (splint over [from, to]; C handle :263-274)
+FP_REAL fitpack_curve_c_integral(fitpack_curve_c *self, FP_REAL from, FP_REAL to)
+{
+    Curve *cv = ensure(self);
+    if (!cv || cv->knots < 2 * (cv->order + 1)) return 0.0;
+    std::vector<double> wk(cv->knots);
+    return fp_splint_c(cv->t.data(), cv->knots, cv->c.data(), cv->order, from, to, wk.data());
+}
+
 FP_REAL fitpack_curve_c_smoothing(fitpack_curve_c *self)
 {
     Curve *cv = ensure(self);

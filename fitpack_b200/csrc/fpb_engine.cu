@@ -175,6 +175,7 @@ void fpb_engine_destroy(fpb_engine *eng)
     eng->plan_ier.release();
     for (auto &b : eng->scratch) b.release();
     for (auto &b : eng->grid) b.release();
+    for (auto &b : eng->calc) b.release();
     if (eng->grid_pinned) cudaFreeHost(eng->grid_pinned);
     if (eng->ev0) cudaEventDestroy(eng->ev0);
     if (eng->ev1) cudaEventDestroy(eng->ev1);

@@ -96,6 +96,22 @@ class FitpackCurve:
                                         C.addressof(ier))
         return y[:x.size], ier.value
 
+    def dfdx(self, x, order=1):
+        """ddx, ierr = curve%dfdx(x, order)  (scalar x; fitpack_curves.f90:606-618)"""
+        ier = C.c_int32(0)
+        v = lib().fitpack_curve_c_derivative(C.addressof(self._h), float(x), int(order), C.addressof(ier))
+        return v, ier.value
+
+    def dfdx_all(self, x):
+        """ddx(1:order+1), ierr = curve%dfdx_all(x)  (fitpack_curves.f90:543-565)"""
+        d = np.zeros(self.degree() + 1)
+        ier = lib().fitpack_curve_c_all_derivatives(C.addressof(self._h), float(x), d.ctypes.data)
+        return d, ier
+
+    def integral(self, a, b):
+        """curve%integral(from, to)  (splint)"""
+        return lib().fitpack_curve_c_integral(C.addressof(self._h), float(a), float(b))
+
     # accessors (public components of the Fortran type)
     def smoothing(self):
         return lib().fitpack_curve_c_smoothing(C.addressof(self._h))

@@ -109,6 +109,9 @@ FP_FLAG fitpack_curve_c_fit          (fitpack_curve_c *self, FP_REAL *smoothing,
 FP_FLAG fitpack_curve_c_interpolating(fitpack_curve_c *self, FP_SIZE *order);
 FP_REAL fitpack_curve_c_eval_one     (fitpack_curve_c *self, FP_REAL x, FP_FLAG *ierr);
 void    fitpack_curve_c_eval_many    (fitpack_curve_c *self, FP_SIZE npts, FP_REAL *x, FP_REAL *y, FP_FLAG *ierr);
+FP_REAL fitpack_curve_c_integral     (fitpack_curve_c *self, FP_REAL from, FP_REAL to);
+FP_REAL fitpack_curve_c_derivative   (fitpack_curve_c *self, FP_REAL x, FP_SIZE order, FP_SIZE *ierr);
+FP_FLAG fitpack_curve_c_all_derivatives(fitpack_curve_c *self, FP_REAL x, FP_REAL *ddx);
 FP_REAL fitpack_curve_c_smoothing    (fitpack_curve_c *self);
 FP_REAL fitpack_curve_c_mse          (fitpack_curve_c *self);
 FP_SIZE fitpack_curve_c_degree       (fitpack_curve_c *self);
@@ -223,6 +226,20 @@ int32_t fp_splev_batch_c(FP_SIZE nspl, const FP_REAL *t, const FP_SIZE *n, const
 /* device tile transpose helper: dst[j*ld_dst + i] = src[i*ld_src + j], i<rows, j<cols */
 int32_t fpb_transpose_dev(fpb_engine *eng, const FP_REAL *src, int64_t ld_src, FP_REAL *dst,
                           int64_t ld_dst, int64_t rows, int64_t cols);
+
+/* ----------------------------------------------------------- spline calculus -- */
+/* reference: include/fitpack_core_c.h:134-138,149-150; src/fitpack_core_c.f90:157-175,207-213
+   -> splder core:17699-17802, spalde core:16865-16895, splint core:17919-17939.
+   Host pointers, same argument lists.  splder: e = 0 extrapolate, 1 zero, 2 => ier=1 at the first
+   point outside the support (any other value extrapolates); wrk(n) returns the derivative's
+   B-spline coefficients.  spalde: d(j) = s^(j-1)(x), j = 1..k1.  splint: wrk(n) returns the
+   integrals of the normalized B-splines. */
+void fp_splder_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP_SIZE nu, const FP_REAL *x,
+                 FP_REAL *y, FP_SIZE m, FP_FLAG e, FP_REAL *wrk, FP_FLAG *ier);
+void fp_spalde_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k1, FP_REAL x, FP_REAL *d,
+                 FP_FLAG *ier);
+FP_REAL fp_splint_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP_REAL a, FP_REAL b,
+                    FP_REAL *wrk);
 
 /* ---------------------------------------------------------- gridded surfaces -- */
 /*

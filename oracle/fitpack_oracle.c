@@ -1288,3 +1288,211 @@ int32_t orc_bispev(const double *tx, int32_t nx, const double *ty, int32_t ny, c
     free(lidx[0]);
     return IER_OK;
 }
+
+/* =====================================================================================
+ * Spline calculus on a fitted curve: splder, spalde/fpader, splint/fpintb
+ * ===================================================================================== */
+
+/* splder, core:17699-17802.  wrk(n) holds the derivative's B-spline coefficients on exit. */
+void orc_splder(const double *t, int32_t n, const double *c, int32_t k, int32_t nu, const double *x,
+                double *y, int32_t m, int32_t e, double *wrk, int32_t *ier)
+{
+    const double *T = t - 1;
+    double *W = wrk - 1;
+    double h[ORC_MAX_ORDER + 1];
+    int k1, k2, k3, nk1, nk2, kk, l, l1, l2, i, j, q;
+    double tb, te;
+    *ier = IER_INPUT;
+    if (nu < 0 || nu > k) return;
+    if (m < 1) return;
+    kk = k - nu;
+    *ier = IER_OK;
+    k1 = k + 1;
+    k3 = k1 + 1;
+    nk1 = n - k1;
+    tb = T[k1];
+    te = T[nk1 + 1];
+    l = 1;
+    for (i = 1; i <= nk1; ++i) W[i] = c[i - 1];
+    if (nu != 0) {
+        nk2 = nk1;
+        for (j = 1; j <= nu; ++j) {
+            const double ak = (double)(k1 - j);
+            nk2 = nk2 - 1;
+            l1 = l;
+            for (i = 1; i <= nk2; ++i) {
+                double fac;
+                l1 = l1 + 1;
+                l2 = l1 + k1 - j;
+                fac = T[l2] - T[l1];
+                if (fac > 0.0) W[i] = ak * (W[i + 1] - W[i]) / fac;
+            }
+            l = l + 1;
+        }
+    }
+    l = k1;
+    l1 = l + 1;
+    k2 = k1 - nu;
+    j = 1;
+    for (i = 1; i <= m; ++i) {
+        double arg = x[i - 1];
+        if (arg < tb || arg > te) {
+            if (e == 1) { y[i - 1] = 0.0; continue; }
+            if (e == 2) { *ier = IER_STORAGE; return; }
+        }
+        while (!(arg >= T[l] || l1 == k3)) { l1 = l; l = l - 1; j = j - 1; }
+        while (!(arg < T[l1] || l == nk1)) { l = l1; l1 = l + 1; j = j + 1; }
+        if (nu == 0 || k != nu) {
+            double sp = 0.0;
+            orc_fpbspl(t, n, kk, arg, l, h);
+            for (q = 1; q <= k2; ++q) sp = sp + h[q - 1] * W[l - k + q - 1];
+            y[i - 1] = sp;
+        } else {
+            y[i - 1] = W[j];
+        }
+    }
+}
+
+/* fpader, core:1546-1603 */
+static void fpader(const double *t, const double *c, int k1, double x, int l, double *d)
+{
+    const double *T = t - 1, *Cc = c - 1;
+    double *D = d - 1;
+    double h[ORC_MAX_ORDER + 2], *H = h - 1;
+    int i, ik, j, jj, j1, j2, ki, kj, li, lj, lk;
+    double ak, fac;
+    lk = l - k1;
+    for (i = 1; i <= k1; ++i) {
+        ik = i + lk;
+        H[i] = Cc[ik];
+    }
+    kj = k1;
+    fac = 1.0;
+    for (j = 1; j <= k1; ++j) {
+        ki = kj;
+        j1 = j + 1;
+        if (j > 1) {
+            i = k1;
+            for (jj = j; jj <= k1; ++jj) {
+                li = i + lk;
+                lj = li + kj;
+                H[i] = (H[i] - H[i - 1]) / (T[lj] - T[li]);
+                i = i - 1;
+            }
+        }
+        for (i = j; i <= k1; ++i) D[i] = H[i];
+        if (j < k1) {
+            for (jj = j1; jj <= k1; ++jj) {
+                ki = ki - 1;
+                i = k1;
+                for (j2 = jj; j2 <= k1; ++j2) {
+                    li = i + lk;
+                    lj = li + ki;
+                    D[i] = ((x - T[li]) * D[i] + (T[lj] - x) * D[i - 1]) / (T[lj] - T[li]);
+                    i = i - 1;
+                }
+            }
+        }
+        D[j] = D[k1] * fac;
+        ak = (double)(k1 - j);
+        fac = fac * ak;
+        kj = kj - 1;
+    }
+}
+
+/* spalde, core:16865-16895 : all derivatives d(j) = s^(j-1)(x), j = 1..k1 */
+void orc_spalde(const double *t, int32_t n, const double *c, int32_t k1, double x, double *d,
+                int32_t *ier)
+{
+    const double *T = t - 1;
+    int nk1 = n - k1, l;
+    *ier = IER_INPUT;
+    if (x < T[k1] || x > T[nk1 + 1]) return;
+    l = orc_knot_interval(t, x, k1, nk1);
+    if (T[l] >= T[l + 1]) return;
+    *ier = IER_OK;
+    fpader(t, c, k1, x, l, d);
+}
+
+/* fpintb, core:8058-8166 : integrals of the normalized B-splines over [x, y] */
+static void fpintb(const double *t, int n, double *bint, int nk1, double x, double y)
+{
+    const double *T = t - 1;
+    double *B = bint - 1;
+    double aint[8], h[ORC_MAX_ORDER + 2], h1[8];
+    double *AI = aint - 1, *H = h - 1, *H1 = h1 - 1;
+    int i, ia, ib, it, j, j1, k, k1, l, li, lj, lk, lmin;
+    double a, ak, arg, b, f;
+    k1 = n - nk1;
+    ak = (double)k1;
+    k = k1 - 1;
+    for (i = 1; i <= nk1; ++i) B[i] = 0.0;
+    if (orc_equal(x, y)) return;
+    a = x < y ? x : y;
+    b = x > y ? x : y;
+    lmin = x > y;
+    if (T[k1] > a) a = T[k1];
+    if (T[nk1 + 1] < b) b = T[nk1 + 1];
+    if (a > b) return;
+    l = k1;
+    arg = a;
+    ia = 0;
+    for (it = 1; it <= 2; ++it) {
+        l = orc_knot_interval(t, arg, l, nk1);
+        AI[1] = (arg - T[l]) / (T[l + 1] - T[l]);
+        for (i = 2; i <= k1; ++i) AI[i] = 0.0;
+        H1[1] = 1.0;
+        for (j = 1; j <= k; ++j) {
+            H[1] = 0.0;
+            for (i = 1; i <= j; ++i) {
+                li = l + i;
+                lj = li - j;
+                f = H1[i] / (T[li] - T[lj]);
+                H[i] = H[i] + f * (T[li] - arg);
+                H[i + 1] = f * (arg - T[lj]);
+            }
+            j1 = j + 1;
+            for (i = 1; i <= j1; ++i) {
+                li = l + i;
+                lj = li - j1;
+                AI[i] = AI[i] + H[i] * (arg - T[lj]) / (T[li] - T[lj]);
+                H1[i] = H[i];
+            }
+        }
+        if (it < 2) {
+            lk = l - k;
+            ia = lk;
+            for (i = 1; i <= k1; ++i) {
+                B[lk] = -AI[i];
+                lk = lk + 1;
+            }
+            arg = b;
+        }
+    }
+    lk = l - k;
+    ib = lk - 1;
+    for (i = 1; i <= k1; ++i) {
+        B[lk] = B[lk] + AI[i];
+        lk = lk + 1;
+    }
+    if (ib >= ia)
+        for (i = ia; i <= ib; ++i) B[i] = B[i] + 1.0;
+    f = 1.0 / ak;
+    for (i = 1; i <= nk1; ++i) {
+        j = i + k1;
+        B[i] = B[i] * (T[j] - T[i]) * f;
+    }
+    if (lmin)
+        for (i = 1; i <= nk1; ++i) B[i] = -B[i];
+}
+
+/* splint, core:17919-17939 : integral of s over [a, b]; wrk(n) receives the B-spline integrals */
+double orc_splint(const double *t, int32_t n, const double *c, int32_t k, double a, double b,
+                  double *wrk)
+{
+    int nk1 = n - k - 1, i;
+    double s = 0.0;
+    fpintb(t, n, wrk, nk1, a, b);
+    for (i = 0; i < nk1; ++i) s = s + c[i] * wrk[i];
+    return s;
+}

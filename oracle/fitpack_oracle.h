@@ -108,6 +108,15 @@ int32_t orc_bispev(const double *tx, int32_t nx, const double *ty, int32_t ny, c
                    int32_t kx, int32_t ky, const double *x, int32_t mx, const double *y, int32_t my,
                    double *z, double *wrk, int32_t lwrk, int32_t *iwrk, int32_t kwrk);
 
+/* splder core:17699-17802, spalde core:16865-16895 (+fpader 1546-1603), splint core:17919-17939
+   (+fpintb 8058-8166): argument lists of fp_splder_c / fp_spalde_c / fp_splint_c */
+void orc_splder(const double *t, int32_t n, const double *c, int32_t k, int32_t nu, const double *x,
+                double *y, int32_t m, int32_t e, double *wrk, int32_t *ier);
+void orc_spalde(const double *t, int32_t n, const double *c, int32_t k1, double x, double *d,
+                int32_t *ier);
+double orc_splint(const double *t, int32_t n, const double *c, int32_t k, double a, double b,
+                  double *wrk);
+
 int32_t orc_max_threads(void);
 
 /* tests only: switch the documented reference-vs-netlib deviations off (see .c) */

@@ -282,6 +282,42 @@ def make_regrid():
     print("regrid cases:", i, "ier histogram:", {v: iers.count(v) for v in sorted(set(iers))})
 
 
+def make_calculus():
+    """splder / spalde / splint vectors (scipy's C translation; no reference-vs-netlib deviation
+    touches these routines)."""
+    rng = np.random.default_rng(31337)
+    out = {}
+    idx = 0
+    for k in range(1, 6):
+        for trial in range(5):
+            nint = int(rng.integers(0, 14))
+            t = np.concatenate([np.zeros(k + 1), np.sort(rng.uniform(0, 1, nint)), np.ones(k + 1)])
+            n = t.size
+            c = np.zeros(n)
+            c[:n - k - 1] = rng.standard_normal(n - k - 1)
+            x = rng.uniform(-0.2, 1.2, 64)
+            x[:3] = [0.0, 1.0, 0.5]
+            p = f"s{idx}_"
+            out[p + "t"], out[p + "c"], out[p + "x"], out[p + "k"] = t, c, x, k
+            for nu in range(0, k + 1):
+                for e in (0, 1):
+                    y, ier = _fitpack.splder(t, c, k, nu, x, e)
+                    out[p + f"d{nu}_e{e}"] = np.asarray(y)
+            xs = np.array([0.0, 0.3, 1.0, 0.77])
+            out[p + "ax"] = xs
+            out[p + "ad"] = np.stack([np.ravel(_fitpack.spalde(t, c, k + 1, np.array([v]))[0]) for v in xs])
+            ab = np.array([[0, 1], [0.2, 0.7], [0.9, 0.1], [-1, 2], [0.3, 0.3]], float)
+            out[p + "ab"] = ab
+            vals = []
+            for a, b in ab:
+                v = _fitpack.splint(t, c, k, a, b)
+                vals.append(float(v[0] if isinstance(v, tuple) else v))
+            out[p + "iv"] = np.array(vals)
+            idx += 1
+    out["nspline"] = idx
+    np.savez_compressed(os.path.join(HERE, "calculus_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     import sys
     sys.path.insert(0, os.path.dirname(HERE))
@@ -289,5 +325,7 @@ if __name__ == "__main__":
     make_curfit()
     make_splev()
     make_regrid()
-    for f in ("mncurf_golden.npz", "curfit_golden.npz", "splev_golden.npz", "regrid_golden.npz"):
+    make_calculus()
+    for f in ("mncurf_golden.npz", "curfit_golden.npz", "splev_golden.npz", "regrid_golden.npz",
+              "calculus_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

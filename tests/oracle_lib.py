@@ -255,3 +255,36 @@ def bispev(tx, nx, ty, ny, c, kx, ky, x, y):
 
 def set_netlib_compat(on):
     lib().orc_set_netlib_compat(C.c_int32(1 if on else 0))
+
+
+# ------------------------------------------------------------------ spline calculus
+def splder(t, n, c, k, nu, x, e=0):
+    t, c, x = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, c, x))
+    m = x.size
+    y = np.zeros(max(m, 1))
+    wrk = np.zeros(max(n, 1))
+    ier = C.c_int32(0)
+    L = lib()
+    L.orc_splder.restype = None
+    L.orc_splder(_d(t), C.c_int32(n), _d(c), C.c_int32(k), C.c_int32(nu), _d(x), _d(y), C.c_int32(m),
+                 C.c_int32(e), _d(wrk), C.byref(ier))
+    return y[:m], ier.value, wrk
+
+
+def spalde(t, n, c, k1, x):
+    t, c = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, c))
+    d = np.zeros(k1)
+    ier = C.c_int32(0)
+    L = lib()
+    L.orc_spalde.restype = None
+    L.orc_spalde(_d(t), C.c_int32(n), _d(c), C.c_int32(k1), C.c_double(x), _d(d), C.byref(ier))
+    return d, ier.value
+
+
+def splint(t, n, c, k, a, b):
+    t, c = (np.ascontiguousarray(v, dtype=np.float64) for v in (t, c))
+    wrk = np.zeros(max(n, 1))
+    L = lib()
+    L.orc_splint.restype = C.c_double
+    v = L.orc_splint(_d(t), C.c_int32(n), _d(c), C.c_int32(k), C.c_double(a), C.c_double(b), _d(wrk))
+    return float(v), wrk

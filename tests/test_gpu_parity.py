@@ -677,3 +677,55 @@ def test_regrid_input_errors_and_device_grid(F, eng):
         zo, io = O.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], kx, ky, xs, ys)
         assert ig == io == 0 and _same(zg.cpu().numpy(), zo)
         assert abs(float(((zd - zg) ** 2).sum()) - r["fp"]) <= 1e-9 * r["fp"]
+
+
+# ------------------------------------------------------------------ spline calculus
+def test_splder_spalde_splint_bit_exact(F):
+    g = np.load(os.path.join(G, "calculus_golden.npz"))
+    for i in range(int(g["nspline"])):
+        p = f"s{i}_"
+        t, c, x, k = g[p + "t"], g[p + "c"], g[p + "x"], int(g[p + "k"])
+        n = t.size
+        for nu in range(k + 1):
+            for e in (0, 1, 2, 3):
+                yo, io, wo = O.splder(t, n, c, k, nu, x, e)
+                yg, ig, wg = F.splder(t, n, c, k, nu, x, e)
+                assert ig == io, (i, nu, e)
+                nk1 = n - k - 1
+                assert _same(wg[:nk1], wo[:nk1])
+                if io == 0:
+                    assert _same(yg, yo), (i, nu, e)
+                    if e in (0, 1):
+                        assert _same(yg, g[p + f"d{nu}_e{e}"])
+                else:  # e=2: values up to the first point outside the support
+                    first = int(np.argmax((x < t[k]) | (x > t[n - k - 1])))
+                    assert io == 1 and _same(yg[:first], yo[:first])
+        for xx, dref in zip(g[p + "ax"], g[p + "ad"]):
+            d, ier = F.spalde(t, n, c, k + 1, float(xx))
+            assert ier == 0 and _same(d, dref)
+        assert F.spalde(t, n, c, k + 1, 1.5)[1] == 10
+        for (a, b), vref in zip(g[p + "ab"], g[p + "iv"]):
+            v, wrk = F.splint(t, n, c, k, float(a), float(b))
+            assert v == vref and _same(wrk[:n - k - 1], O.splint(t, n, c, k, float(a), float(b))[1][:n - k - 1])
+    assert F.splder(t, n, c, k, k + 1, x, 0)[1] == 10 and F.splder(t, n, c, k, 0, x[:0], 0)[1] == 10
+
+
+def test_curve_handle_calculus(F):
+    """fitpack_curve_c_derivative / _all_derivatives / _integral on a sine fit, the checks of the
+    reference's test_cpp_sine_fit (test/test_curve.cpp:31-93): derivatives 1e-3 rel, integral."""
+    x = np.linspace(0, np.pi, 200)
+    cv = F.FitpackCurve()
+    assert cv.new_fit(x, np.sin(x), None, 0.0) <= 0
+    for xx in (0.3, 1.0, 2.5):
+        d1, ier = cv.dfdx(xx, 1)
+        assert ier == 0 and abs(d1 - np.cos(xx)) < 1e-3
+        d2, ier = cv.dfdx(xx, 2)
+        assert ier == 0 and abs(d2 + np.sin(xx)) < 1e-2
+        dall, ier = cv.dfdx_all(xx)
+        assert ier == 0 and dall.size == 4 and abs(dall[1] - d1) < 1e-12 and abs(dall[0] - np.sin(xx)) < 1e-6
+        # against the oracle on the same knots/coefficients: bit-exact
+        t, c, n = cv.t, cv.c, cv.knots
+        assert d1 == O.splder(t[:n], n, c[:n], 3, 1, np.array([xx]), 3)[0][0]
+        assert _same(dall, O.spalde(t[:n], n, c[:n], 4, xx)[0])
+    assert abs(cv.integral(0.0, np.pi) - 2.0) < 1e-8
+    assert cv.integral(0.0, np.pi) == O.splint(cv.t, cv.knots, cv.c, 3, 0.0, np.pi)[0]

@@ -368,3 +368,53 @@ def test_regrid_and_bispev_input_errors():
     r = O.regrid(**ok)
     zz, ie = O.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], 3, 3, x[::-1].copy(), y)
     assert ie == 10
+
+
+# ------------------------------------------------------------------ spline calculus
+def _calculus_cases():
+    g = np.load(os.path.join(G, "calculus_golden.npz"))
+    for i in range(int(g["nspline"])):
+        yield g, f"s{i}_"
+
+
+def test_splder_spalde_splint_golden_bit_exact():
+    nchk = 0
+    for g, p in _calculus_cases():
+        t, c, x, k = g[p + "t"], g[p + "c"], g[p + "x"], int(g[p + "k"])
+        n = t.size
+        for nu in range(k + 1):
+            for e in (0, 1):
+                y, ier, wrk = O.splder(t, n, c, k, nu, x, e)
+                assert ier == 0 and np.array_equal(y, g[p + f"d{nu}_e{e}"]), (p, nu, e)
+                nchk += 1
+        for xx, dref in zip(g[p + "ax"], g[p + "ad"]):
+            d, ier = O.spalde(t, n, c, k + 1, float(xx))
+            assert ier == 0 and np.array_equal(d, dref)
+        for (a, b), vref in zip(g[p + "ab"], g[p + "iv"]):
+            v, _ = O.splint(t, n, c, k, float(a), float(b))
+            assert v == vref
+    assert nchk >= 150
+
+
+def test_calculus_semantics():
+    t = np.array([0., 0, 0, 0, 0.5, 1, 1, 1, 1])
+    c = np.array([1., 2, -1, 3, 0.5, 0, 0, 0, 0])
+    x = np.array([0.25, 1.5, 0.75])
+    # e=2: ier=1 at the first outside point, y filled up to it (core:17771-17773)
+    y, ier, _ = O.splder(t, 9, c, 3, 1, x, 2)
+    assert ier == 1
+    assert y[0] == O.splder(t, 9, c, 3, 1, x[:1], 0)[0][0]
+    # e=3 is not a splder policy: extrapolates like 0
+    assert np.array_equal(O.splder(t, 9, c, 3, 2, x, 3)[0], O.splder(t, 9, c, 3, 2, x, 0)[0])
+    assert O.splder(t, 9, c, 3, 4, x, 0)[1] == 10 and O.splder(t, 9, c, 3, -1, x, 0)[1] == 10
+    # nu = 0 is splev
+    assert np.array_equal(O.splder(t, 9, c, 3, 0, x, 0)[0], O.splev(t, 9, c, 3, x, 0)[0])
+    # spalde outside the support -> 10; d[0] is the spline value
+    assert O.spalde(t, 9, c, 4, 1.5)[1] == 10
+    d, ier = O.spalde(t, 9, c, 4, 0.25)
+    assert ier == 0 and abs(d[0] - O.splev(t, 9, c, 3, np.array([0.25]))[0][0]) < 1e-15
+    # integral is antisymmetric in its limits and additive
+    a1, _ = O.splint(t, 9, c, 3, 0.1, 0.9)
+    a2, _ = O.splint(t, 9, c, 3, 0.9, 0.1)
+    a3 = O.splint(t, 9, c, 3, 0.1, 0.4)[0] + O.splint(t, 9, c, 3, 0.4, 0.9)[0]
+    assert a1 == -a2 and abs(a1 - a3) < 1e-14
