@@ -41,9 +41,9 @@ SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
 SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 22, 512, 3, 28   # config 3 shape, 2^22 curves/GPU
 GRID_M, GRID_K, GRID_SIGMA, GRID_NEST = 4096, 3, 0.05, 128          # config 4: 4096 x 4096 grid, kx=ky=3
 # DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum,
-# profiles/r01_final_kernels.md, profiles/r01_final_launches.md); the bench itself never runs under ncu.
+# profiles/r01_final_kernels.md, profiles/r01b_kernels.md); the bench itself never runs under ncu.
 NCU_FIT_DRAM_BYTES_PER_FIT = 8.1 * (6.558e9 + 1.593e9) / 2.5e5 + (51.47e9 + 10.02e9) / (0.94 * 262144)
-NCU_SPLEV_DRAM_BYTES_PER_POINT = (8.546e9 + 7.964e9) / (1048576 * 954)
+NCU_SPLEV_DRAM_BYTES_PER_POINT = (8.561e9 + 7.965e9) / (1048576 * 954)   # profiles/r01b_kernels.md
 NCU_SHARED_DRAM_BYTES_PER_CURVE = (17.18e9 + 1.104e9) / 4194304
 
 
@@ -389,7 +389,7 @@ def main():
             splev[name] = {
                 "value": world * bytes_alg / (ms_step * 1e-3) / 1e9, "unit": "GB/s",
                 "gpts_per_s": world * ns * ms / (ms_step * 1e-3) / 1e9, "ms_per_step": ms_step,
-                "roofline": {"bound": "hbm", "kernel": "splev_kernel<5> mode=%s" % name,
+                "roofline": {"bound": "hbm", "kernel": ("splev_fast_kernel<5>" if mode == 1 else "splev_kernel<5> (exact)"),
                              "achieved": bytes_alg / (kms * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": bytes_alg / (kms * 1e-3) / 1e9 / hbm_peak,
                              "traffic": (NCU_SPLEV_DRAM_BYTES_PER_POINT * ns * ms) if mode == 1 else None,

@@ -23,6 +23,7 @@ module fitpack_b200
                                             FPB_ERR_ARG = -101, FPB_ERR_ALLOC = -102
 
    public :: fp_curfit_c, fp_splev_c, fp_curfit_batch_c, fp_splev_batch_c
+   public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c
    public :: fp_curfit_batch_dev_c, fp_curfit_shared_dev_c, fp_splev_batch_dev_c
    public :: fpb_engine_create, fpb_engine_destroy, fpb_engine_synchronize, fpb_device_count
    public :: curfit_batch, splev_batch
@@ -50,6 +51,58 @@ module fitpack_b200
          integer(FP_FLAG), intent(in), value :: e
          integer(FP_FLAG), intent(out)       :: ier
       end subroutine fp_splev_c
+
+      ! gridded surfaces and spline calculus: same interfaces as the reference's regrid_c, bispev_c,
+      ! splder_c, spalde_c, splint_c (src/fitpack_core_c.f90:253-290, 404-415, 157-175, 207-213)
+      subroutine fp_regrid_c(iopt,mx,x,my,y,z,xb,xe,yb,ye,kx,ky,s,nxest,nyest, &
+                             nx,tx,ny,ty,c,fp,wrk,lwrk,iwrk,kwrk,ier) bind(C,name="fp_regrid_c")
+         import
+         real   (FP_REAL), intent(in), value :: xb,xe,yb,ye,s
+         real   (FP_REAL), intent(out)       :: fp
+         integer(FP_SIZE), intent(in), value :: iopt,mx,my,kx,ky,nxest,nyest,lwrk,kwrk
+         integer(FP_SIZE), intent(inout)     :: nx,ny
+         integer(FP_FLAG), intent(out)       :: ier
+         real   (FP_REAL), intent(in)        :: x(mx),y(my),z(mx*my)
+         real   (FP_REAL), intent(inout)     :: tx(nxest),ty(nyest),c((nxest-kx-1)*(nyest-ky-1)),wrk(lwrk)
+         integer(FP_SIZE), intent(inout)     :: iwrk(kwrk)
+      end subroutine fp_regrid_c
+
+      integer(FP_FLAG) function fp_bispev_c(tx,nx,ty,ny,c,kx,ky,x,mx,y,my,z,wrk,lwrk,iwrk,kwrk) &
+                                bind(C,name="fp_bispev_c")
+         import
+         integer(FP_SIZE), intent(in), value :: nx,ny,kx,ky,mx,my,lwrk,kwrk
+         integer(FP_SIZE), intent(inout)     :: iwrk(kwrk)
+         real   (FP_REAL), intent(in)        :: tx(nx),ty(ny),c((nx-kx-1)*(ny-ky-1)),x(mx),y(my)
+         real   (FP_REAL), intent(out)       :: z(mx*my)
+         real   (FP_REAL), intent(inout)     :: wrk(lwrk)
+      end function fp_bispev_c
+
+      subroutine fp_splder_c(t,n,c,k,nu,x,y,m,e,wrk,ier) bind(C,name="fp_splder_c")
+         import
+         integer(FP_SIZE), intent(in), value :: n,k,nu,m
+         integer(FP_FLAG), intent(in), value :: e
+         integer(FP_FLAG), intent(out)       :: ier
+         real   (FP_REAL), intent(in)        :: t(n),c(n),x(m)
+         real   (FP_REAL), intent(out)       :: y(m)
+         real   (FP_REAL), intent(inout)     :: wrk(n)
+      end subroutine fp_splder_c
+
+      subroutine fp_spalde_c(t,n,c,k1,x,d,ier) bind(C,name="fp_spalde_c")
+         import
+         integer(FP_SIZE), intent(in), value :: n,k1
+         integer(FP_FLAG), intent(out)       :: ier
+         real   (FP_REAL), intent(in), value :: x
+         real   (FP_REAL), intent(in)        :: t(n),c(n)
+         real   (FP_REAL), intent(out)       :: d(k1)
+      end subroutine fp_spalde_c
+
+      real(FP_REAL) function fp_splint_c(t,n,c,k,a,b,wrk) bind(C,name="fp_splint_c")
+         import
+         real   (FP_REAL), intent(in), value :: a,b
+         integer(FP_SIZE), intent(in), value :: n,k
+         real   (FP_REAL), intent(in)        :: t(n),c(n)
+         real   (FP_REAL), intent(inout)     :: wrk(n)
+      end function fp_splint_c
 
       ! (B) batches of independent curves, host arrays.  Fortran arrays x(m,nbatch) are exactly
       ! the "curve-major" [nbatch][m] C layout the library expects.
