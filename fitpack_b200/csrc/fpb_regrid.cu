@@ -132,29 +132,79 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
             disc_row<K>(A.t, n, lmk, A.b + (size_t)(lmk - 1) * kAs);
     }
     __syncthreads();
-    // ---- matrix half of the band QR (core:7222-7300): ONE thread, because every rotation depends
-    // on the previous one.  The other threads stage the basis rows / interval numbers of the next
-    // kPlanChunk grid points into shared memory so that the sequential thread never waits on a
-    // global load (its own stores are fire-and-forget).
+    // ---- matrix half of the band QR (core:7222-7300) -- a systolic pipeline in warp 0 ----
+    // Rotation i of a row needs (a) the row as left by its rotation i-1 and (b) band row irot+i as
+    // left by the PREVIOUS row's rotation i.  Lane i therefore owns band row irot+i and performs
+    // rotation i of every row; a row enters at lane 0 and moves one lane per step (its remaining
+    // elements travel by __shfl_up, already shifted so that the pivot is always element 0).  k+2
+    // rotations of consecutive rows run concurrently and the serial chain is one rotation per row
+    // instead of k+1.  When the first band row advances (a new knot interval) the pipeline drains
+    // and the band rows move down the lanes.  The arithmetic of every rotation is unchanged
+    // (fpgivs / fprota, same operands, same order).  The other warps stage the basis rows /
+    // interval numbers / discontinuity rows of the next kPlanChunk grid points in shared memory.
     const double pinv = (p > 0.0) ? 1.0 / p : 1.0;
-    double W[K2][K2];  // window of band rows base .. base+K2-1
+    const int lane = threadIdx.x & 31;
+    const bool w0 = threadIdx.x < 32;
+    double W[K2], hcur[K2];   // my band row; the row I am rotating (pivot first)
 #pragma unroll
-    for (int i = 0; i < K2; ++i)
+    for (int q = 0; q < K2; ++q) {
+        W[q] = 0.0;
+        hcur[q] = 0.0;
+    }
+    int rcur = -1, bcur = 0;  // list index and band of the row in my lane (-1: bubble)
+    int irot_cur = 0, nrold = 0, iband = K1, r = 0;
+    // one pipeline step: every lane hands its row to the next lane, lane 0 takes the new row
+    auto step = [&](bool inject, const double (&hnew)[K2], int rnew, int bnew) {
+        double hin[K2];
 #pragma unroll
-        for (int q = 0; q < K2; ++q) W[i][q] = 0.0;
-    int base = 0, nrold = 0, iband = K1, r = 0;
-    auto retire = [&]() {
-        if (base < nk1) {
+        for (int q = 0; q < K2 - 1; ++q) hin[q] = __shfl_up_sync(0xffffffffu, hcur[q + 1], 1);
+        hin[K2 - 1] = 0.0;
+        int rin = __shfl_up_sync(0xffffffffu, rcur, 1);
+        int bin = __shfl_up_sync(0xffffffffu, bcur, 1);
+        if (lane == 0) {
+            rin = inject ? rnew : -1;
+            bin = bnew;
 #pragma unroll
-            for (int q = 0; q < K2; ++q) A.a[(size_t)base * kAs + q] = W[0][q];
+            for (int q = 0; q < K2; ++q) hin[q] = hnew[q];
+        }
+        if (rin >= 0 && lane < bin) {
+            const double piv = hin[0];
+            double cs = 1.0, sn = 0.0;  // identity == "pivot is zero: skip" (core:6043)
+            if (!fp_is_zero(piv)) {
+                givens(piv, W[0], cs, sn);
+#pragma unroll
+                for (int q = 1; q < K2; ++q)
+                    if (lane + q < bin) rota(cs, sn, hin[q], W[q]);
+            }
+            A.rcs[(size_t)rin * kCs + lane] = make_double2(cs, sn);
+        }
+        rcur = rin;
+        bcur = bin;
+#pragma unroll
+        for (int q = 0; q < K2; ++q) hcur[q] = hin[q];
+    };
+    const double hzero[K2] = {};
+    // first band row moves from irot_cur to irot_new: finish the rows in flight, retire the band
+    // rows that are final, pass the others down the lanes
+    auto advance = [&](int irot_new) {
+        for (int q = 0; q < K2 - 1; ++q) step(false, hzero, -1, 0);
+        rcur = -1;
+        const int d = irot_new - irot_cur;
+        if (lane < K2 && lane < d && irot_cur + lane < nk1) {
+#pragma unroll
+            for (int q = 0; q < K2; ++q) A.a[(size_t)(irot_cur + lane) * kAs + q] = W[q];
         }
 #pragma unroll
-        for (int i = 0; i < K2 - 1; ++i)
+        for (int q = 0; q < K2; ++q) {
+            const double v = __shfl_down_sync(0xffffffffu, W[q], (unsigned)min(d, 31));
+            W[q] = (d < K2 && lane + d < K2) ? v : 0.0;
+        }
+        // band rows jumped over without ever being touched stay zero (as in the reference)
+        for (int row = irot_cur + K2 + lane; row < irot_new && row < nk1; row += 32) {
 #pragma unroll
-            for (int q = 0; q < K2; ++q) W[i][q] = W[i + 1][q];
-#pragma unroll
-        for (int q = 0; q < K2; ++q) W[K2 - 1][q] = 0.0;
-        ++base;
+            for (int q = 0; q < K2; ++q) A.a[(size_t)row * kAs + q] = 0.0;
+        }
+        irot_cur = irot_new;
     };
     for (int it0 = 0; it0 < m; it0 += kPlanChunk) {
         const int cnt = min(kPlanChunk, m - it0);
@@ -170,11 +220,11 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
                 if (row < nk1 - K1) b_s[e / K2][e % K2] = A.b[(size_t)row * kAs + e % K2];
             }
         __syncthreads();
-        if (threadIdx.x != 0) continue;
+        if (!w0) continue;
         for (int ii = 0; ii < cnt; ++ii) {
             const int it = it0 + ii;
             const int number = nr_s[ii];
-            for (;;) {
+            for (;;) {  // warp-uniform control flow (core:7236-7262)
                 double h[K2];
                 int irot, src;
                 if (nrold == number) {
@@ -199,36 +249,21 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
                     irot = nrold;
                     src = -1;
                 }
-                while (base < irot) retire();
-                int skip = 0;
-#pragma unroll
-                for (int i = 0; i < K2; ++i) {
-                    if (i < iband) {
-                        const double piv = h[i];
-                        double cs = 1.0, sn = 0.0;
-                        if (fp_is_zero(piv)) {
-                            skip |= 1 << i;
-                        } else {
-                            givens(piv, W[i][0], cs, sn);
-#pragma unroll
-                            for (int q = 1; q < K2; ++q)
-                                if (i + q < iband) rota(cs, sn, h[i + q], W[i][q]);
-                        }
-                        A.rcs[(size_t)r * kCs + i] = make_double2(cs, sn);
-                    }
-                }
-                A.rmeta[r] = make_int4(src, irot, iband, skip);
+                if (irot != irot_cur) advance(irot);
+                if (lane == 0) A.rmeta[r] = make_int4(src, irot, iband, 0);
+                step(true, h, r, iband);
                 ++r;
                 if (nrold == number) break;
                 ++nrold;
             }
         }
     }
-    if (threadIdx.x != 0) return;
-#pragma unroll
-    for (int i = 0; i < K2; ++i) retire();
-    A.info[0] = r;
-    A.info[1] = iband;
+    if (!w0) return;
+    advance(irot_cur + K2);  // drain and retire every band row still in the lanes
+    if (lane == 0) {
+        A.info[0] = r;
+        A.info[1] = iband;
+    }
 }
 
 __global__ void __launch_bounds__(256) grid_plan_kernel(AxisDev X, AxisDev Y, double p)
@@ -315,9 +350,10 @@ __global__ void __launch_bounds__(64) grid_apply_kernel(const double *__restrict
             }
 #pragma unroll
             for (int i = 0; i < K2; ++i) {
-                if (i < mt.z && !((mt.w >> i) & 1)) {
+                if (i < mt.z) {
                     const double2 cs = cs_s[rr][i];
-                    rota(cs.x, cs.y, right, W[i]);
+                    // (1, 0) marks a skipped (zero) pivot; no real rotation has sin == 0
+                    if (cs.y != 0.0) rota(cs.x, cs.y, right, W[i]);
                 }
             }
         }
