@@ -282,12 +282,17 @@ __global__ void __launch_bounds__(256) grid_plan_kernel(AxisDev X, AxisDev Y, do
     }
 }
 
-// Right-hand-side half of one reduction pass.  Thread j owns right-hand side j: source row `s`
-// contributes in[s*in_ld + j]; the reduced column goes to out[j*out_ld + row], row < nout.
-// The source values are streamed through a per-thread ring in shared memory filled by cp.async
-// (kRing rows ahead, no register is tied to a load in flight), the rotation list is staged per
-// chunk by the whole CTA.
+// Right-hand-side half of one reduction pass.  Right-hand side j: source row `s` contributes
+// in[s*in_ld + j]; the reduced column goes to out[j*out_ld + row], row < nout.
+// Same systolic scheme as the plan, per right-hand side: a group of 8 lanes owns one column, lane i
+// holds the column's entry of band row irot+i and applies rotation i of every row (4 mul + 2 add),
+// the running right-hand-side value moves one lane per step by __shfl_up.  The serial chain per
+// column is one rotation per row instead of k+1 (k+2 with smoothing rows).  The source values are
+// streamed through a per-column ring in shared memory filled by cp.async (kRing rows ahead), the
+// rotation list is staged per chunk by the whole CTA; the pipeline drains at chunk ends and when
+// the first band row advances.
 constexpr int kRing = 16;
+constexpr int kApplyThreads = 128, kApplyCols = kApplyThreads / 8;
 
 __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
 {
@@ -297,32 +302,51 @@ __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
 }
 
 template <int K>
-__global__ void __launch_bounds__(64) grid_apply_kernel(const double *__restrict__ in, long long in_ld,
-                                                        int nrhs, const int4 *__restrict__ rmeta,
-                                                        const double2 *__restrict__ rcs,
-                                                        const int *__restrict__ info, int nsrc,
-                                                        double *__restrict__ out, long long out_ld,
-                                                        int nout)
+__global__ void __launch_bounds__(kApplyThreads) grid_apply_kernel(
+    const double *__restrict__ in, long long in_ld, int nrhs, const int4 *__restrict__ rmeta,
+    const double2 *__restrict__ rcs, const int *__restrict__ info, int nsrc, double *__restrict__ out,
+    long long out_ld, int nout)
 {
     constexpr int K2 = K + 2;
     __shared__ int4 meta_s[kApplyChunk];
     __shared__ double2 cs_s[kApplyChunk][K2];
-    __shared__ double ring[kRing][64];
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double ring[kRing][kApplyCols];
+    const int l8 = threadIdx.x & 7, col = threadIdx.x >> 3;
+    const int j = blockIdx.x * kApplyCols + col;
     const bool live = j < nrhs;
-    const int jj = live ? j : nrhs - 1;  // idle threads shadow the last column (no stores)
+    const int jj = live ? j : nrhs - 1;  // idle groups shadow the last column (no stores)
     const int nrows = info[0];
-    double W[K2];
-#pragma unroll
-    for (int i = 0; i < K2; ++i) W[i] = 0.0;
-    int base = 0;
     double *o = out + (size_t)jj * out_ld;
     const double *src = in + jj;
+    const bool feeder = l8 == 0;
+    if (feeder) {
 #pragma unroll
-    for (int u = 0; u < kRing; ++u) {  // one commit group per source row, empty past the end
-        if (u < nsrc) cp_async8(&ring[u][threadIdx.x], src + (size_t)u * in_ld);
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        for (int u = 0; u < kRing; ++u) {  // one commit group per source row, empty past the end
+            if (u < nsrc) cp_async8(&ring[u][col], src + (size_t)u * in_ld);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
     }
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(&ring[0][col]);
+    double W = 0.0, right = 0.0;
+    int irot_cur = 0;
+    // Lane i works on the row injected i steps ago; `rstart` is the local index of the first row
+    // injected since the last drain, so lane i's row is rr - i when that is >= rstart (else a
+    // bubble).  Only the running right-hand-side value travels between lanes.  Each lane looks up
+    // its own (cos, sin) ONE STEP AHEAD (prep), so that the serial chain of a step is just
+    // shuffle -> rotation.
+    auto prep = [&](int my, int lo, int hi, double2 &cs) -> bool {  // row `my` valid in [lo, hi)
+        const int myc = min(max(my, 0), kApplyChunk - 1);
+        const int band = meta_s[myc].z;
+        cs = cs_s[myc][min(l8, K2 - 1)];
+        // (1, 0) marks a skipped (zero) pivot; no real rotation has sin == 0
+        return my >= lo && my < hi && l8 < band && cs.y != 0.0;
+    };
+    auto step = [&](double rnew, const double2 &cs, bool act) {
+        double rin = __shfl_up_sync(0xffffffffu, right, 1, 8);
+        if (feeder) rin = rnew;
+        if (act) rota(cs.x, cs.y, rin, W);
+        right = rin;
+    };
     for (int r0 = 0; r0 < nrows; r0 += kApplyChunk) {
         const int cnt = min(kApplyChunk, nrows - r0);
         __syncthreads();
@@ -330,52 +354,107 @@ __global__ void __launch_bounds__(64) grid_apply_kernel(const double *__restrict
         for (int e = threadIdx.x; e < cnt * K2; e += blockDim.x)
             cs_s[e / K2][e % K2] = rcs[(size_t)(r0 + e / K2) * kCs + e % K2];
         __syncthreads();
-        for (int rr = 0; rr < cnt; ++rr) {
-            const int4 mt = meta_s[rr];
-            while (base < mt.y) {
-                if (live && base < nout) o[base] = W[0];
-#pragma unroll
-                for (int i = 0; i < K2 - 1; ++i) W[i] = W[i + 1];
-                W[K2 - 1] = 0.0;
-                ++base;
+        int rstart = 0;
+        // drain: K2-1 bubble steps finish the rows in flight (rows < rr of this chunk)
+        auto drain = [&](int rr) {
+            for (int q = 0; q < K2 - 1; ++q) {
+                double2 cs;
+                const bool act = prep(rr + q - l8, rstart, rr, cs);
+                step(0.0, cs, act);
             }
-            double right = 0.0;
-            if (mt.x >= 0) {  // data rows come in order 0, 1, 2, ...: row mt.x sits in slot mt.x % kRing
+            rstart = rr;
+        };
+        // first band row moves to irot_new: retire the rows that are final, pass the rest down
+        auto advance = [&](int irot_new, int rr) {
+            drain(rr);
+            const int d = irot_new - irot_cur;
+            if (live && l8 < K2 && l8 < d && irot_cur + l8 < nout) o[irot_cur + l8] = W;
+            const double v = __shfl_down_sync(0xffffffffu, W, (unsigned)min(d, 7), 8);
+            W = (d < K2 && l8 + d < K2) ? v : 0.0;
+            if (live)
+                for (int row = irot_cur + K2 + l8; row < irot_new && row < nout; row += 8) o[row] = 0.0;
+            irot_cur = irot_new;
+        };
+        auto fetch = [&](int srow) -> double {
+            double v = 0.0;
+            if (srow >= 0 && feeder) {  // data rows come in order: row srow sits in slot srow % kRing
                 asm volatile("cp.async.wait_group %0;\n" ::"n"(kRing - 1) : "memory");
-                double *slot = &ring[mt.x & (kRing - 1)][threadIdx.x];
-                right = *slot;
-                const int nx = mt.x + kRing;
-                if (nx < nsrc) cp_async8(slot, src + (size_t)nx * in_ld);
+                const int sl = srow & (kRing - 1);
+                v = ring[sl][col];
+                const int nx = srow + kRing;
+                if (nx < nsrc) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(ring_u32 + (uint32_t)sl * (kApplyCols * 8)),
+                                 "l"(src + (size_t)nx * in_ld)
+                                 : "memory");
+                }
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
             }
-#pragma unroll
-            for (int i = 0; i < K2; ++i) {
-                if (i < mt.z) {
-                    const double2 cs = cs_s[rr][i];
-                    // (1, 0) marks a skipped (zero) pivot; no real rotation has sin == 0
-                    if (cs.y != 0.0) rota(cs.x, cs.y, right, W[i]);
-                }
-            }
+            return v;
+        };
+        // Software pipeline over the list rows: the list entry is read two rows ahead, the source
+        // value and my (cos, sin) / band one row ahead, so that nothing loaded in an iteration is
+        // used in the same iteration and a step costs shuffle -> rotation.
+        const int4 none = make_int4(-1, 0, 0, 0);
+        int4 cur = meta_s[0];
+        int4 m1 = (1 < cnt) ? meta_s[1] : none;
+        double crn = fetch(cur.x);
+        double2 ccs;
+        int cband;
+        bool cval;
+        {
+            const int myc = min(max(0 - l8, 0), kApplyChunk - 1);
+            cband = meta_s[myc].z;
+            ccs = cs_s[myc][min(l8, K2 - 1)];
+            cval = (0 - l8) >= 0;
         }
+        for (int rr = 0; rr < cnt; ++rr) {
+            const int4 m2 = (rr + 2 < cnt) ? meta_s[rr + 2] : none;
+            if (cur.y != irot_cur) {  // rare: drain, move the band rows, only lane 0 has a row now
+                advance(cur.y, rr);
+                const int my = rr - l8;
+                const int myc = min(max(my, 0), kApplyChunk - 1);
+                cband = meta_s[myc].z;
+                ccs = cs_s[myc][min(l8, K2 - 1)];
+                cval = my >= rstart;
+            }
+            // requests for row rr+1 (m1 is already in registers)
+            double nrn = 0.0;
+            double2 ncs = make_double2(1.0, 0.0);
+            int nband = 0;
+            bool nval = false;
+            if (rr + 1 < cnt) {
+                nrn = fetch(m1.x);
+                const int my = rr + 1 - l8;
+                const int myc = min(max(my, 0), kApplyChunk - 1);
+                nband = meta_s[myc].z;
+                ncs = cs_s[myc][min(l8, K2 - 1)];
+                nval = my >= ((m1.y != cur.y) ? rr + 1 : rstart);
+            }
+            // (1, 0) marks a skipped (zero) pivot; no real rotation has sin == 0
+            step(crn, ccs, cval && l8 < cband && ccs.y != 0.0);
+            cur = m1;
+            m1 = m2;
+            crn = nrn;
+            ccs = ncs;
+            cband = nband;
+            cval = nval;
+        }
+        drain(cnt);  // the next chunk overwrites the staged rotations
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < K2; ++i)
-            if (base + i < nout) o[base + i] = W[i];
-    }
+    if (feeder) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (live && l8 < K2 && irot_cur + l8 < nout) o[irot_cur + l8] = W;  // rows still in the lanes
 }
 
 void launch_apply(int k, const double *in, long long in_ld, int nrhs, const AxisDev &A, int nsrc,
                   double *out, long long out_ld, int nout, cudaStream_t st)
 {
-    const int blocks = (nrhs + 63) / 64;
+    const int blocks = (nrhs + kApplyCols - 1) / kApplyCols;
     switch (k) {
-    case 1: grid_apply_kernel<1><<<blocks, 64, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
-    case 2: grid_apply_kernel<2><<<blocks, 64, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
-    case 3: grid_apply_kernel<3><<<blocks, 64, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
-    case 4: grid_apply_kernel<4><<<blocks, 64, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
-    case 5: grid_apply_kernel<5><<<blocks, 64, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 1: grid_apply_kernel<1><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 2: grid_apply_kernel<2><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 3: grid_apply_kernel<3><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 4: grid_apply_kernel<4><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 5: grid_apply_kernel<5><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
     default: break;
     }
 }
