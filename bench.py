@@ -44,7 +44,7 @@ GRID_M, GRID_K, GRID_SIGMA, GRID_NEST = 4096, 3, 0.05, 128          # config 4: 
 # profiles/r01_final_kernels.md, profiles/r01b_kernels.md); the bench itself never runs under ncu.
 NCU_FIT_DRAM_BYTES_PER_FIT = 8.1 * (6.558e9 + 1.593e9) / 2.5e5 + (51.47e9 + 10.02e9) / (0.94 * 262144)
 NCU_SPLEV_DRAM_BYTES_PER_POINT = (8.561e9 + 7.965e9) / (1048576 * 954)   # profiles/r01b_kernels.md
-NCU_SHARED_DRAM_BYTES_PER_CURVE = (17.18e9 + 1.104e9) / 4194304
+NCU_SHARED_DRAM_BYTES_PER_CURVE = (17.85e9 + 1.839e9) / 4194304   # shared_apply2 (r01b)
 
 
 def parse():
@@ -412,33 +412,39 @@ def main():
         tsh[ks + 1:ks + 1 + nint] = torch.linspace(0, 1, nint + 2, device=dev, dtype=f64)[1:-1]
         ysh = torch.randn((ms, Bs), generator=gsh, device=dev, dtype=f64)   # point-major
         sho = {}
-        for _ in range(max(1, args.warmup)):
-            r = eng.curfit_shared(xs_, ysh, tsh, k=ks, out=sho)
-            sho = {"c": r["c"], "fp": r["fp"], "ier": r["ier"]}
-        barrier()
-        l0 = eng.launches
-        ev0.record()
-        for _ in range(args.steps):
-            r = eng.curfit_shared(xs_, ysh, tsh, k=ks, out=sho)
-        ev1.record()
-        barrier()
-        ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-        kms = eng.last_kernel_ms()
         nk1 = nn - ks - 1
         bytes_curve = 8 * ms + 8 * nk1 + 12
         flops_curve = ms * (1 + 6 * (ks + 1) + 2) + nk1 * (2 * ks + 1)
-        assert int(r["ier"].cpu()[0]) == 0
-        shared = {
-            "config": {"workload": "shared-abscissa least squares (iopt=-1): %d curves x %d points per "
-                                   "GPU, k=3, %d interior knots (config 3 shape)" % (Bs, ms, nint)},
-            "value": world * Bs / (ms_step * 1e-3), "unit": "fits/s", "ms_per_step": ms_step,
-            "gpu_launches": int(eng.launches - l0),
-            "roofline": {"bound": "hbm", "kernel": "shared_apply_kernel<3>",
-                         "achieved": Bs * bytes_curve / (kms * 1e-3) / 1e9, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": Bs * bytes_curve / (kms * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": NCU_SHARED_DRAM_BYTES_PER_CURVE * Bs, "peak_source": peak_src,
-                         "algorithmic_bytes_per_curve": bytes_curve},
-            "fp64_gflops": Bs * flops_curve / (kms * 1e-3) / 1e9}
+        shared = {"config": {"workload": "shared-abscissa least squares (iopt=-1): %d curves x %d points per "
+                                         "GPU, k=3, %d interior knots (config 3 shape)" % (Bs, ms, nint)}}
+        l0 = eng.launches
+        for smode, sname in ((0, "exact"), (1, "fast")):
+            for _ in range(max(1, args.warmup)):
+                r = eng.curfit_shared(xs_, ysh, tsh, k=ks, out=sho, mode=smode)
+                sho = {"c": r["c"], "fp": r["fp"], "ier": r["ier"]}
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                r = eng.curfit_shared(xs_, ysh, tsh, k=ks, out=sho, mode=smode)
+            ev1.record()
+            barrier()
+            ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+            kms = eng.last_kernel_ms()
+            assert int(r["ier"].cpu()[0]) == 0
+            blk = {"value": world * Bs / (ms_step * 1e-3), "unit": "fits/s", "ms_per_step": ms_step,
+                   "arithmetic": "reference rotations, 4 mul + 2 add, bit-identical to curfit(iopt=-1)"
+                                 if smode == 0 else "FMA rotations (2 mul + 2 fma), within 1e-12 of exact",
+                   "roofline": {"bound": "hbm", "kernel": "shared_apply2_kernel<3,%s>" % ("FMA" if smode else "exact"),
+                                "achieved": Bs * bytes_curve / (kms * 1e-3) / 1e9, "peak": hbm_peak,
+                                "unit": "GB/s", "frac": Bs * bytes_curve / (kms * 1e-3) / 1e9 / hbm_peak,
+                                "traffic": NCU_SHARED_DRAM_BYTES_PER_CURVE * Bs, "peak_source": peak_src,
+                                "algorithmic_bytes_per_curve": bytes_curve},
+                   "fp64_gflops": Bs * (flops_curve if smode == 0 else flops_curve * 17.0 / 27.0) / (kms * 1e-3) / 1e9}
+            if smode == 0:
+                shared.update(blk)   # exact mode is the headline of this block
+            else:
+                shared["fast"] = blk
+        shared["gpu_launches"] = int(eng.launches - l0)
         del ysh, sho, r
         torch.cuda.empty_cache()
 

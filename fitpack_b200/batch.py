@@ -156,7 +156,7 @@ class Engine:
         return res
 
     def curfit_shared(self, x, y, t, k=3, w=None, xb=None, xe=None, layout="point_major",
-                      out=None):
+                      out=None, mode=0):
         """Shared-abscissa least squares (iopt=-1): x [m], t [n] (interior knots in place),
         y [m][B] (point_major) or [B][m].  Returns dict(c [B][n-k-1], fp [B], ier [1], t)."""
         _chk_f64(y, "y"); _chk_f64(x, "x"); _chk_f64(w, "w"); _chk_f64(t, "t")
@@ -182,6 +182,7 @@ class Engine:
         if ier_t is None:
             ier_t = torch.zeros(1, device=dev, dtype=torch.int32)
         self.use_torch_stream()
+        check(lib().fpb_engine_set_shared_mode(self._h, int(mode)), "set_shared_mode")
         rc = lib().fp_curfit_shared_dev_c(self._h, B, m, _ptr(x), _ptr(w), _ptr(y), sb, si,
                                           float(xb), float(xe), int(k), n, _ptr(t), _ptr(c_t),
                                           c_t.stride(0), _ptr(fp_t), _ptr(ier_t))

@@ -208,6 +208,13 @@ int32_t fpb_engine_synchronize(fpb_engine *eng)
 
 int64_t fpb_engine_launch_count(const fpb_engine *eng) { return eng ? eng->launches : 0; }
 
+int32_t fpb_engine_set_shared_mode(fpb_engine *eng, int32_t mode)
+{
+    if (!eng || (mode != 0 && mode != 1)) return FPB_ERR_ARG;
+    eng->shared_fast = mode;
+    return FPB_STATUS_OK;
+}
+
 double fpb_engine_last_kernel_ms(fpb_engine *eng)
 {
     if (!eng || !eng->timed) return -1.0;
@@ -416,7 +423,8 @@ int32_t fp_curfit_shared_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE m, const
     begin_timing(eng);
     if (nbatch > 0) {
         if (!cuda_ok(launch_shared_apply(nbatch, m, k, n, y, y_sb, y_si, plan, w,
-                                         eng->plan_meta.as<int>(), c, ldc, fp, eng->nsm, eng->stream),
+                                         eng->plan_meta.as<int>(), c, ldc, fp, eng->nsm, eng->stream,
+                                         eng->shared_fast),
                      "shared apply kernel"))
             return FPB_ERR_CUDA;
         eng->launches += 2;

@@ -46,6 +46,7 @@ struct fpb_engine {
     double *grid_pinned = nullptr;
     size_t grid_pinned_bytes = 0;
     int64_t grid_fpgrre_calls = 0;
+    int shared_fast = 0;              // shared-abscissa LSQ: 0 exact rotations, 1 FMA (fast)
     fpb::DevBuf calc[6];              // spline calculus (fpb_calculus.cu)
 };
 

@@ -70,7 +70,8 @@ cudaError_t launch_shared_plan(const double *x, const double *w, int m, double x
                                int n, double *t, const SharedPlan &plan, cudaStream_t stream);
 cudaError_t launch_shared_apply(int nbatch, int m, int k, int n, const double *y, long long y_sb,
                                 long long y_si, const SharedPlan &plan, const double *w, int *meta,
-                                double *c, long long ldc, double *fp, int nsm, cudaStream_t stream);
+                                double *c, long long ldc, double *fp, int nsm, cudaStream_t stream,
+                                int fast);
 
 // ---- evaluation ----
 struct SplevParams {

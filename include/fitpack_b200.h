@@ -138,6 +138,13 @@ void    fpb_engine_destroy(fpb_engine *eng);
 int32_t fpb_engine_set_stream(fpb_engine *eng, void *cuda_stream);
 int32_t fpb_engine_reset_stream(fpb_engine *eng);
 int32_t fpb_engine_synchronize(fpb_engine *eng);
+/* arithmetic of the shared-abscissa least-squares path (fp_curfit_shared_dev_c):
+   FPB_SHARED_EXACT (default): the reference's rotations, 4 mul + 2 add, bit-identical to
+   curfit(iopt=-1) per curve;  FPB_SHARED_FAST: fused multiply-add rotations (2 mul + 2 fma),
+   c and fp within rounding (tests: 1e-12 relative to max|c|, max(1,fp)). */
+#define FPB_SHARED_EXACT 0
+#define FPB_SHARED_FAST  1
+int32_t fpb_engine_set_shared_mode(fpb_engine *eng, int32_t mode);
 /* number of kernels this engine has launched since creation (bench bookkeeping) */
 int64_t fpb_engine_launch_count(const fpb_engine *eng);
 /* device time in ms of the last dominant kernel (fit or splev), measured with

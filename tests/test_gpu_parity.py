@@ -729,3 +729,31 @@ def test_curve_handle_calculus(F):
         assert _same(dall, O.spalde(t[:n], n, c[:n], 4, xx)[0])
     assert abs(cv.integral(0.0, np.pi) - 2.0) < 1e-8
     assert cv.integral(0.0, np.pi) == O.splint(cv.t, cv.knots, cv.c, 3, 0.0, np.pi)[0]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_shared_lsq_two_curve_kernel_exact_and_fast(eng, k):
+    """The two-curves-per-thread shape (point-major, unit weights, even batch): EXACT mode is
+    bit-identical to curfit(iopt=-1) per curve; FAST mode (FMA rotations) within 1e-12 relative
+    to max|c| / max(1, fp) (stated tolerance)."""
+    import torch
+    rng = np.random.default_rng(60 + k)
+    B, m, nint = 390, 300, 17     # 390 curves: 3 full 128-curve tiles + a partial one
+    x = np.linspace(0, 1, m)
+    _, y = synth_curves(rng, B, m)
+    n = 2 * (k + 1) + nint
+    t = np.zeros(n)
+    t[k + 1:k + 1 + nint] = np.sort(rng.uniform(0.02, 0.98, nint))
+    dev = eng.device
+    xd, yd = torch.from_numpy(x).to(dev), torch.from_numpy(np.ascontiguousarray(y.T)).to(dev)
+    ex = eng.curfit_shared(xd, yd, torch.from_numpy(t.copy()).to(dev), k=k, mode=0)
+    assert int(ex["ier"].cpu()[0]) == 0
+    ce, fpe = ex["c"].cpu().numpy().copy(), ex["fp"].cpu().numpy().copy()
+    for b in list(range(0, B, 11)) + [B - 2, B - 1]:
+        o = O.curfit(-1, x, y[b], None, 0.0, 1.0, k, 0.0, n, n=n, t=t.copy())
+        assert fpe[b] == o["fp"] and _same(ce[b, :n - k - 1], o["c"][:n - k - 1]), (k, b)
+    fa = eng.curfit_shared(xd, yd, torch.from_numpy(t.copy()).to(dev), k=k, mode=1)
+    cf, fpf = fa["c"].cpu().numpy(), fa["fp"].cpu().numpy()
+    scale = np.maximum(1.0, np.abs(ce).max(axis=1))[:, None]
+    assert (np.abs(cf - ce) / scale).max() < 1e-12
+    assert (np.abs(fpf - fpe) / np.maximum(1.0, fpe)).max() < 1e-12
