@@ -302,6 +302,10 @@ def main():
             "note": "fit kernel is FP64 issue/latency bound (~%.0f kflop per 4.4 KB): HBM "
                     "fraction is tiny by construction; see fp64" % (flops / B / 1e3)}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    # the same kernels measured by the bytes they actually move (ncu): workspace traffic puts the
+    # pipeline at about half of the HBM peak, next to its FP64-pipe share (see fp64)
+    roof["traffic_gbs"] = roof["traffic"] / (fit_ms * 1e-3) / 1e9
+    roof["traffic_frac_of_peak"] = roof["traffic_gbs"] / hbm_peak
     dmul_dadd = eng.probe_fp64_gops(False)
     dfma = eng.probe_fp64_gops(True)
     fp64 = {"achieved_gflops": flops / (fit_ms * 1e-3) / 1e9,
