@@ -757,3 +757,86 @@ def test_shared_lsq_two_curve_kernel_exact_and_fast(eng, k):
     scale = np.maximum(1.0, np.abs(ce).max(axis=1))[:, None]
     assert (np.abs(cf - ce) / scale).max() < 1e-12
     assert (np.abs(fpf - fpe) / np.maximum(1.0, fpe)).max() < 1e-12
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_splev_fast_multiple_knots_unsorted_and_policies(eng, k):
+    """FAST evaluation on splines with coincident interior knots (flagged lookup cells, the
+    division fallback of the record builder), unsorted / out-of-support points and every policy:
+    same interval indices as the exact mode, values within 1e-12 * max(1, max|c|)."""
+    import torch
+    rng = np.random.default_rng(90 + k)
+    B, ldt, m = 96, 48, 515          # odd m: the register-pipelined (non-TMA) point path
+    t = np.zeros((B, ldt))
+    c = np.zeros((B, ldt))
+    n = np.zeros(B, np.int32)
+    for b in range(B):
+        nint = int(rng.integers(0, ldt - 2 * (k + 1) + 1))
+        interior = np.sort(rng.uniform(0.05, 0.95, nint))
+        if nint >= 4:   # double and (for k >= 2) triple knots, plus two knots 1e-13 apart
+            interior[1] = interior[0]
+            if k >= 2 and nint >= 6:
+                interior[4] = interior[5] = interior[3]
+            interior[-1] = interior[-2] + 1e-13
+            interior = np.sort(interior)
+        nb = 2 * (k + 1) + nint
+        t[b, :nb] = np.concatenate([np.zeros(k + 1), interior, np.ones(k + 1)])
+        c[b, :nb - k - 1] = rng.standard_normal(nb - k - 1)
+        n[b] = nb
+    x = rng.uniform(-0.2, 1.2, (B, m))
+    x[:, :6] = [0.0, 1.0, -0.2, 1.2, 0.5, 0.05]
+    for b in range(B):
+        if n[b] > 2 * (k + 1):
+            x[b, 6] = t[b, k + 1]          # exactly on a (possibly multiple) knot
+    dev = eng.device
+    td, cd, nd, xd = (torch.from_numpy(a).to(dev) for a in (t, c, n, x))
+    for xin in (xd, torch.sort(xd, dim=1).values[:, :514].contiguous()):   # odd and even m
+        for e in (0, 1, 3):
+            ex = eng.splev_batch(td, nd, cd, k, xin, e=e, mode=0, want_idx=True)
+            fa = eng.splev_batch(td, nd, cd, k, xin, e=e, mode=1, want_idx=True)
+            assert torch.equal(ex["lidx"], fa["lidx"]), (k, e)
+            scale = np.maximum(1.0, np.abs(c).max(axis=1))[:, None]
+            ye, yf = ex["y"].cpu().numpy(), fa["y"].cpu().numpy()
+            # extrapolation grows like |x - support|^k: compare relative to the value too
+            err = np.abs(ye - yf) / np.maximum(scale, np.abs(ye))
+            assert err.max() < 1e-12, (k, e, err.max())
+        assert torch.equal(eng.splev_batch(td, nd, cd, k, xin, e=2, mode=1)["ier"],
+                           eng.splev_batch(td, nd, cd, k, xin, e=2, mode=0)["ier"])
+    # against the oracle for a few rows (exact mode is bit-identical, so FAST is within tolerance)
+    yo, _ = O.splev_batch(t[:8], n[:8], c[:8], k, x[:8])
+    yf = eng.splev_batch(td[:8], nd[:8], cd[:8], k, xd[:8].contiguous(), e=0, mode=1)["y"].cpu().numpy()
+    assert (np.abs(yf - yo) / np.maximum(np.maximum(1.0, np.abs(c[:8]).max(axis=1))[:, None], np.abs(yo))).max() < 1e-12
+
+
+def test_regrid_full_size_properties(F, eng):
+    """BASELINE config 4 at full size (4096 x 4096, kx=ky=3, s = mx*my*sigma^2): size-independent
+    properties -- ier = 0 => |fp - s| < 1e-3 s, fp == residual recomputed through bispev (config 5b),
+    knots clamped / increasing and satisfying Schoenberg-Whitney, and the same knots as the oracle
+    on a 512 x 512 sub-sample of the same surface."""
+    import torch
+    m, k, sigma, nest = 4096, 3, 0.05, 128
+    x = np.linspace(-1.5, 1.5, m)
+    g = torch.Generator(device=eng.device)
+    g.manual_seed(4)
+    X = torch.from_numpy(x).to(eng.device)[:, None]
+    Y = torch.from_numpy(x).to(eng.device)[None, :]
+    z = torch.exp(-(X ** 2 + Y ** 2)) + 0.3 * torch.sin(2 * X) * torch.cos(1.5 * Y) \
+        + sigma * torch.randn((m, m), generator=g, device=eng.device, dtype=torch.float64)
+    s = m * m * sigma ** 2
+    r = F.regrid(0, x, x, z, -1.5, 1.5, -1.5, 1.5, k, k, s, nest, nest, engine=eng)
+    assert r["ier"] == 0 and abs(r["fp"] - s) < 1e-3 * s
+    out = torch.empty((m, m), device=eng.device, dtype=torch.float64)
+    zz, ie = F.bispev(r["tx"], r["nx"], r["ty"], r["ny"], r["c"], k, k, x, x, out=out, engine=eng)
+    assert ie == 0
+    res = float(((z - zz) ** 2).sum())
+    assert abs(res - r["fp"]) <= 1e-9 * r["fp"]
+    for t, n in ((r["tx"], r["nx"]), (r["ty"], r["ny"])):
+        assert np.all(t[:k + 1] == -1.5) and np.all(t[n - k - 1:n] == 1.5)
+        assert np.all(np.diff(t[k:n - k]) > 0) and O.fpchec(x, t[:n], n, k) == 0
+    # oracle on a sub-sample (every 8th point): identical discrete outputs, c/fp within 1e-10
+    xs = x[::8].copy()
+    zs = z[::8, ::8].contiguous()
+    ss = xs.size ** 2 * sigma ** 2
+    rg = F.regrid(0, xs, xs, zs, xs[0], xs[-1], xs[0], xs[-1], k, k, ss, nest, nest, engine=eng)
+    ro = O.regrid(0, xs, xs, zs.cpu().numpy(), xs[0], xs[-1], xs[0], xs[-1], k, k, ss, nest, nest)
+    _check_regrid(rg, ro, k, k)
