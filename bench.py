@@ -553,6 +553,27 @@ def main():
         t0 = time.perf_counter()
         O.curfit_batch(0, xs[:sample], ys[:sample], None, K, S, NEST, nthreads=nthr)
         dt = time.perf_counter() - t0
+        if splev is not None:
+            # second half of the metric: splev of the CPU port on the config-5 shape (k=5, n=32,
+            # 954 points per spline), OpenMP over splines, bounded sample
+            ks_, nn_, ms_ = SPLEV_K, SPLEV_N, SPLEV_M
+            nsp = 16384
+            tt = np.zeros((nsp, nn_))
+            ni_ = nn_ - 2 * (ks_ + 1)
+            tt[:, ks_ + 1:ks_ + 1 + ni_] = np.linspace(0, 1, ni_ + 2)[1:-1]
+            tt[:, ks_ + 1 + ni_:] = 1.0
+            cc = rng.standard_normal((nsp, nn_))
+            xx = np.sort(rng.uniform(0, 1, (nsp, ms_)), axis=1)
+            nv = np.full(nsp, nn_, np.int32)
+            O.splev_batch(tt[:256], nv[:256], cc[:256], ks_, xx[:256], nthreads=nthr)
+            t0s = time.perf_counter()
+            O.splev_batch(tt, nv, cc, ks_, xx, nthreads=nthr)
+            dts = time.perf_counter() - t0s
+            splev["cpu_baseline"] = {
+                "value": nsp * ms_ * splev["algorithmic_bytes_per_point"] / dts / 1e9, "unit": "GB/s",
+                "gpts_per_s": nsp * ms_ / dts / 1e9, "cores": nthr, "kind": "port",
+                "sample": "%d k=5 splines x %d points, oracle splev (reference arithmetic), OpenMP over "
+                          "splines" % (nsp, ms_)}
         cpu = {"value": sample / dt, "unit": "fits/s", "cores": nthr, "kind": "port",
                "sample": "%d config-2 curves, oracle port of the reference algorithm, OpenMP over "
                          "curves (reference is Fortran: no compiler in this image)" % sample}

@@ -10,15 +10,15 @@
 // Structure of one fpgrre call (Kronecker form A_y C A_x^T = Q, core:7052-7060):
 //   grid_plan_kernel   one CTA per axis.  All threads: basis values sp / interval numbers nr of
 //                      the grid coordinates (fpbspl) and the discontinuity rows b (fpdisc).
-//                      One thread: the matrix half of the band QR -- the Givens rotations depend
-//                      only on (grid, knots, p), never on z -- recorded as a rotation list
-//                      {source row, first band row, band, skipped pivots, (cos,sin)[band]}.
-//   grid_apply_kernel  the right-hand-side half, one thread per independent right-hand side:
-//                      pass x: my columns of z (coalesced 8 B loads across threads), pass y:
-//                      nk1x rows of the reduced buffer.  Each thread walks the rotation list with a
-//                      (k+2)-row register window of its right-hand side: 4 mul + 2 add per rotation,
-//                      no sqrt, no division ("one rotation, many right-hand sides": the access
-//                      pattern of fp_rotate_row_block).
+//                      Warp 0: the matrix half of the band QR -- the Givens rotations depend
+//                      only on (grid, knots, p), never on z -- as a systolic pipeline (lane i
+//                      performs rotation i of every row) that also records a rotation TAPE: per
+//                      pipeline step the (cos,sin) of every lane and a control word {source row
+//                      entering, band rows to move down the lanes}.
+//   grid_apply_kernel  the right-hand-side half: 8 lanes per independent right-hand side replay
+//                      the tape (pass x: my columns of z, pass y: nk1x rows of the reduced
+//                      buffer): 4 mul + 2 add per step, no sqrt, no division ("one rotation, many
+//                      right-hand sides": the access pattern of fp_rotate_row_block).
 //   grid_backsub_kernel   per-line banded back-substitution (fpback, core:1808-1838): axis y, then x.
 //   grid_resid_kernel  squared residual of every grid cell (reference operation order), reduced to
 //                      per-row / per-column sums in a FIXED order (tile partials, no atomics).
@@ -58,9 +58,10 @@ struct AxisDev {
     int *nr;          // [m]
     double *a;        // [n][kAs] triangular band factor (row-major)
     double *b;        // [n][kAs] discontinuity rows
-    int4 *rmeta;      // [m + n] rotation list: {source row or -1, first band row, band, skip bits}
-    double2 *rcs;     // [m + n][kCs]
-    int *info;        // [0] rows in the list, [1] band width of the factor (k+1 or k+2)
+    int2 *ctl;        // [steps] rotation tape control: {source row entering at this step or -1,
+                      //         band rows to move down the lanes before this step}
+    double2 *rcs;     // [steps][kCs] rotation tape: (cos,sin) of lane i at this step, (1,0) = none
+    int *info;        // [0] steps on the tape, [1] band width of the factor (k+1 or k+2)
     int m, n, k;
 };
 
@@ -151,10 +152,13 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
         W[q] = 0.0;
         hcur[q] = 0.0;
     }
-    int rcur = -1, bcur = 0;  // list index and band of the row in my lane (-1: bubble)
-    int irot_cur = 0, nrold = 0, iband = K1, r = 0;
-    // one pipeline step: every lane hands its row to the next lane, lane 0 takes the new row
-    auto step = [&](bool inject, const double (&hnew)[K2], int rnew, int bnew) {
+    int rcur = -1, bcur = 0;  // row in my lane (>= 0: a row, -1: bubble) and its band
+    int irot_cur = 0, nrold = 0, iband = K1;
+    int s_tape = 0, pend_d = 0;  // tape position; band-row shift to announce with the next step
+    // one pipeline step: every lane hands its row to the next lane, lane 0 takes the new row.
+    // The step is also one line of the rotation TAPE the apply kernels replay: lane i's (cos,sin)
+    // (identity when it has no rotation) and a control word {source row entering, pending shift}.
+    auto step = [&](bool inject, const double (&hnew)[K2], int src, int bnew) {
         double hin[K2];
 #pragma unroll
         for (int q = 0; q < K2 - 1; ++q) hin[q] = __shfl_up_sync(0xffffffffu, hcur[q + 1], 1);
@@ -162,26 +166,29 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
         int rin = __shfl_up_sync(0xffffffffu, rcur, 1);
         int bin = __shfl_up_sync(0xffffffffu, bcur, 1);
         if (lane == 0) {
-            rin = inject ? rnew : -1;
+            rin = inject ? 0 : -1;
             bin = bnew;
 #pragma unroll
             for (int q = 0; q < K2; ++q) hin[q] = hnew[q];
+            A.ctl[s_tape] = make_int2(inject ? src : -1, pend_d);
         }
+        double cs = 1.0, sn = 0.0;  // identity == "no rotation" / "pivot is zero: skip" (core:6043)
         if (rin >= 0 && lane < bin) {
             const double piv = hin[0];
-            double cs = 1.0, sn = 0.0;  // identity == "pivot is zero: skip" (core:6043)
             if (!fp_is_zero(piv)) {
                 givens(piv, W[0], cs, sn);
 #pragma unroll
                 for (int q = 1; q < K2; ++q)
                     if (lane + q < bin) rota(cs, sn, hin[q], W[q]);
             }
-            A.rcs[(size_t)rin * kCs + lane] = make_double2(cs, sn);
         }
+        if (lane < kCs) A.rcs[(size_t)s_tape * kCs + lane] = make_double2(cs, sn);
         rcur = rin;
         bcur = bin;
 #pragma unroll
         for (int q = 0; q < K2; ++q) hcur[q] = hin[q];
+        ++s_tape;
+        pend_d = 0;
     };
     const double hzero[K2] = {};
     // first band row moves from irot_cur to irot_new: finish the rows in flight, retire the band
@@ -205,6 +212,7 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
             for (int q = 0; q < K2; ++q) A.a[(size_t)row * kAs + q] = 0.0;
         }
         irot_cur = irot_new;
+        pend_d = d;
     };
     for (int it0 = 0; it0 < m; it0 += kPlanChunk) {
         const int cnt = min(kPlanChunk, m - it0);
@@ -250,9 +258,7 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
                     src = -1;
                 }
                 if (irot != irot_cur) advance(irot);
-                if (lane == 0) A.rmeta[r] = make_int4(src, irot, iband, 0);
-                step(true, h, r, iband);
-                ++r;
+                step(true, h, src, iband);
                 if (nrold == number) break;
                 ++nrold;
             }
@@ -261,7 +267,7 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
     if (!w0) return;
     advance(irot_cur + K2);  // drain and retire every band row still in the lanes
     if (lane == 0) {
-        A.info[0] = r;
+        A.info[0] = s_tape;
         A.info[1] = iband;
     }
 }
@@ -303,22 +309,23 @@ __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
 
 template <int K>
 __global__ void __launch_bounds__(kApplyThreads) grid_apply_kernel(
-    const double *__restrict__ in, long long in_ld, int nrhs, const int4 *__restrict__ rmeta,
+    const double *__restrict__ in, long long in_ld, int nrhs, const int2 *__restrict__ ctl,
     const double2 *__restrict__ rcs, const int *__restrict__ info, int nsrc, double *__restrict__ out,
     long long out_ld, int nout)
 {
     constexpr int K2 = K + 2;
-    __shared__ int4 meta_s[kApplyChunk];
-    __shared__ double2 cs_s[kApplyChunk][K2];
+    __shared__ int2 ctl_s[kApplyChunk + 1];
+    __shared__ double2 tape_s[kApplyChunk][kCs];
     __shared__ double ring[kRing][kApplyCols];
     const int l8 = threadIdx.x & 7, col = threadIdx.x >> 3;
     const int j = blockIdx.x * kApplyCols + col;
     const bool live = j < nrhs;
     const int jj = live ? j : nrhs - 1;  // idle groups shadow the last column (no stores)
-    const int nrows = info[0];
+    const int nsteps = info[0];
     double *o = out + (size_t)jj * out_ld;
     const double *src = in + jj;
     const bool feeder = l8 == 0;
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(&ring[0][col]);
     if (feeder) {
 #pragma unroll
         for (int u = 0; u < kRing; ++u) {  // one commit group per source row, empty past the end
@@ -326,120 +333,57 @@ __global__ void __launch_bounds__(kApplyThreads) grid_apply_kernel(
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
     }
-    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(&ring[0][col]);
+    // source value of the row entering at a step (lane 0 of the group); rows come in order
+    auto fetch = [&](int srow) -> double {
+        double v = 0.0;
+        if (srow >= 0 && feeder) {
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(kRing - 1) : "memory");
+            const int sl = srow & (kRing - 1);
+            v = ring[sl][col];
+            const int nx = srow + kRing;
+            if (nx < nsrc) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(ring_u32 + (uint32_t)sl * (kApplyCols * 8)),
+                             "l"(src + (size_t)nx * in_ld)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        return v;
+    };
     double W = 0.0, right = 0.0;
     int irot_cur = 0;
-    // Lane i works on the row injected i steps ago; `rstart` is the local index of the first row
-    // injected since the last drain, so lane i's row is rr - i when that is >= rstart (else a
-    // bubble).  Only the running right-hand-side value travels between lanes.  Each lane looks up
-    // its own (cos, sin) ONE STEP AHEAD (prep), so that the serial chain of a step is just
-    // shuffle -> rotation.
-    auto prep = [&](int my, int lo, int hi, double2 &cs) -> bool {  // row `my` valid in [lo, hi)
-        const int myc = min(max(my, 0), kApplyChunk - 1);
-        const int band = meta_s[myc].z;
-        cs = cs_s[myc][min(l8, K2 - 1)];
-        // (1, 0) marks a skipped (zero) pivot; no real rotation has sin == 0
-        return my >= lo && my < hi && l8 < band && cs.y != 0.0;
-    };
-    auto step = [&](double rnew, const double2 &cs, bool act) {
-        double rin = __shfl_up_sync(0xffffffffu, right, 1, 8);
-        if (feeder) rin = rnew;
-        if (act) rota(cs.x, cs.y, rin, W);
-        right = rin;
-    };
-    for (int r0 = 0; r0 < nrows; r0 += kApplyChunk) {
-        const int cnt = min(kApplyChunk, nrows - r0);
+    for (int s0 = 0; s0 < nsteps; s0 += kApplyChunk) {
+        const int cnt = min(kApplyChunk, nsteps - s0);
         __syncthreads();
-        for (int e = threadIdx.x; e < cnt; e += blockDim.x) meta_s[e] = rmeta[r0 + e];
-        for (int e = threadIdx.x; e < cnt * K2; e += blockDim.x)
-            cs_s[e / K2][e % K2] = rcs[(size_t)(r0 + e / K2) * kCs + e % K2];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) ctl_s[e] = ctl[s0 + e];
+        if (threadIdx.x == 0) ctl_s[cnt] = make_int2(-1, 0);
+        for (int e = threadIdx.x; e < cnt * kCs; e += blockDim.x) tape_s[e / kCs][e % kCs] = rcs[(size_t)s0 * kCs + e];
         __syncthreads();
-        int rstart = 0;
-        // drain: K2-1 bubble steps finish the rows in flight (rows < rr of this chunk)
-        auto drain = [&](int rr) {
-            for (int q = 0; q < K2 - 1; ++q) {
-                double2 cs;
-                const bool act = prep(rr + q - l8, rstart, rr, cs);
-                step(0.0, cs, act);
+        // replay: everything a step needs was requested one step earlier
+        int2 cw = ctl_s[0];
+        double rnew = fetch(cw.x);
+        double2 cs = tape_s[0][l8];
+        for (int ss = 0; ss < cnt; ++ss) {
+            const int2 cn = ctl_s[ss + 1];
+            const double2 csn = tape_s[min(ss + 1, kApplyChunk - 1)][l8];
+            const double rnext = fetch(cn.x);
+            if (cw.y) {  // rare: the first band row advances by d: retire final rows, move the rest down
+                const int d = cw.y;
+                if (live && l8 < K2 && l8 < d && irot_cur + l8 < nout) o[irot_cur + l8] = W;
+                const double v = __shfl_down_sync(0xffffffffu, W, (unsigned)min(d, 7), 8);
+                W = (d < K2 && l8 + d < K2) ? v : 0.0;
+                if (live)
+                    for (int row = irot_cur + K2 + l8; row < irot_cur + d && row < nout; row += 8) o[row] = 0.0;
+                irot_cur += d;
             }
-            rstart = rr;
-        };
-        // first band row moves to irot_new: retire the rows that are final, pass the rest down
-        auto advance = [&](int irot_new, int rr) {
-            drain(rr);
-            const int d = irot_new - irot_cur;
-            if (live && l8 < K2 && l8 < d && irot_cur + l8 < nout) o[irot_cur + l8] = W;
-            const double v = __shfl_down_sync(0xffffffffu, W, (unsigned)min(d, 7), 8);
-            W = (d < K2 && l8 + d < K2) ? v : 0.0;
-            if (live)
-                for (int row = irot_cur + K2 + l8; row < irot_new && row < nout; row += 8) o[row] = 0.0;
-            irot_cur = irot_new;
-        };
-        auto fetch = [&](int srow) -> double {
-            double v = 0.0;
-            if (srow >= 0 && feeder) {  // data rows come in order: row srow sits in slot srow % kRing
-                asm volatile("cp.async.wait_group %0;\n" ::"n"(kRing - 1) : "memory");
-                const int sl = srow & (kRing - 1);
-                v = ring[sl][col];
-                const int nx = srow + kRing;
-                if (nx < nsrc) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(ring_u32 + (uint32_t)sl * (kApplyCols * 8)),
-                                 "l"(src + (size_t)nx * in_ld)
-                                 : "memory");
-                }
-                asm volatile("cp.async.commit_group;\n" ::: "memory");
-            }
-            return v;
-        };
-        // Software pipeline over the list rows: the list entry is read two rows ahead, the source
-        // value and my (cos, sin) / band one row ahead, so that nothing loaded in an iteration is
-        // used in the same iteration and a step costs shuffle -> rotation.
-        const int4 none = make_int4(-1, 0, 0, 0);
-        int4 cur = meta_s[0];
-        int4 m1 = (1 < cnt) ? meta_s[1] : none;
-        double crn = fetch(cur.x);
-        double2 ccs;
-        int cband;
-        bool cval;
-        {
-            const int myc = min(max(0 - l8, 0), kApplyChunk - 1);
-            cband = meta_s[myc].z;
-            ccs = cs_s[myc][min(l8, K2 - 1)];
-            cval = (0 - l8) >= 0;
+            double rin = __shfl_up_sync(0xffffffffu, right, 1, 8);
+            if (feeder) rin = rnew;
+            if (cs.y != 0.0) rota(cs.x, cs.y, rin, W);  // (1, 0): no rotation for this lane at this step
+            right = rin;
+            cw = cn;
+            cs = csn;
+            rnew = rnext;
         }
-        for (int rr = 0; rr < cnt; ++rr) {
-            const int4 m2 = (rr + 2 < cnt) ? meta_s[rr + 2] : none;
-            if (cur.y != irot_cur) {  // rare: drain, move the band rows, only lane 0 has a row now
-                advance(cur.y, rr);
-                const int my = rr - l8;
-                const int myc = min(max(my, 0), kApplyChunk - 1);
-                cband = meta_s[myc].z;
-                ccs = cs_s[myc][min(l8, K2 - 1)];
-                cval = my >= rstart;
-            }
-            // requests for row rr+1 (m1 is already in registers)
-            double nrn = 0.0;
-            double2 ncs = make_double2(1.0, 0.0);
-            int nband = 0;
-            bool nval = false;
-            if (rr + 1 < cnt) {
-                nrn = fetch(m1.x);
-                const int my = rr + 1 - l8;
-                const int myc = min(max(my, 0), kApplyChunk - 1);
-                nband = meta_s[myc].z;
-                ncs = cs_s[myc][min(l8, K2 - 1)];
-                nval = my >= ((m1.y != cur.y) ? rr + 1 : rstart);
-            }
-            // (1, 0) marks a skipped (zero) pivot; no real rotation has sin == 0
-            step(crn, ccs, cval && l8 < cband && ccs.y != 0.0);
-            cur = m1;
-            m1 = m2;
-            crn = nrn;
-            ccs = ncs;
-            cband = nband;
-            cval = nval;
-        }
-        drain(cnt);  // the next chunk overwrites the staged rotations
     }
     if (feeder) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     if (live && l8 < K2 && irot_cur + l8 < nout) o[irot_cur + l8] = W;  // rows still in the lanes
@@ -450,11 +394,11 @@ void launch_apply(int k, const double *in, long long in_ld, int nrhs, const Axis
 {
     const int blocks = (nrhs + kApplyCols - 1) / kApplyCols;
     switch (k) {
-    case 1: grid_apply_kernel<1><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
-    case 2: grid_apply_kernel<2><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
-    case 3: grid_apply_kernel<3><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
-    case 4: grid_apply_kernel<4><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
-    case 5: grid_apply_kernel<5><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.rmeta, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 1: grid_apply_kernel<1><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.ctl, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 2: grid_apply_kernel<2><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.ctl, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 3: grid_apply_kernel<3><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.ctl, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 4: grid_apply_kernel<4><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.ctl, A.rcs, A.info, nsrc, out, out_ld, nout); break;
+    case 5: grid_apply_kernel<5><<<blocks, kApplyThreads, 0, st>>>(in, in_ld, nrhs, A.ctl, A.rcs, A.info, nsrc, out, out_ld, nout); break;
     default: break;
     }
 }
@@ -803,8 +747,8 @@ struct GridFit {
         bool ok = B[GB_X].reserve(mtot * 8) && B[GB_T].reserve(ntot * 8) &&
                   B[GB_SP].reserve(mtot * kSp * 8) && B[GB_NR].reserve(mtot * 4) &&
                   B[GB_A].reserve(ntot * kAs * 8) && B[GB_B].reserve(ntot * kAs * 8) &&
-                  B[GB_META].reserve((mtot + ntot) * sizeof(int4)) &&
-                  B[GB_CS].reserve((mtot + ntot) * kCs * sizeof(double2)) && B[GB_INFO].reserve(64) &&
+                  B[GB_META].reserve((mtot + 8 * ntot + 64) * sizeof(int2)) &&
+                  B[GB_CS].reserve((mtot + 8 * ntot + 64) * kCs * sizeof(double2)) && B[GB_INFO].reserve(64) &&
                   B[GB_Q].reserve((size_t)my * nkx * 8) && B[GB_C].reserve((size_t)nkx * nky * 8) &&
                   B[GB_PART].reserve(((size_t)ntc * mx + (size_t)ntr * my) * 8) &&
                   B[GB_SUMS].reserve(mtot * 8);
@@ -831,8 +775,8 @@ struct GridFit {
             A.nr = B[GB_NR].as<int>() + mo;
             A.a = B[GB_A].as<double>() + no * kAs;
             A.b = B[GB_B].as<double>() + no * kAs;
-            A.rmeta = B[GB_META].as<int4>() + (mo + no);
-            A.rcs = B[GB_CS].as<double2>() + (mo + no) * kCs;
+            A.ctl = B[GB_META].as<int2>() + (mo + 8 * no + 32 * d);
+            A.rcs = B[GB_CS].as<double2>() + (mo + 8 * no + 32 * d) * kCs;
             A.info = B[GB_INFO].as<int>() + 4 * d;
             A.m = m[d];
             A.k = k[d];
