@@ -1496,3 +1496,418 @@ double orc_splint(const double *t, int32_t n, const double *c, int32_t k, double
     for (i = 0; i < nk1; ++i) s = s + c[i] * wrk[i];
     return s;
 }
+
+/* =====================================================================================
+ * Parametric curves: parcur / fppara and curev.  Same skeleton as fpcurf
+ * with idim right-hand sides sharing one band matrix (fp_rotate_row_vec / _shifted_vec).
+ * Layouts follow the reference: x(idim,m) coordinate-fastest, c((d-1)*n + i), z likewise.
+ * ===================================================================================== */
+
+/* Fortran NORM2 as gfortran evaluates it (scaled form of libgfortran's norm2_r8 / the
+   inline expansion in trans-intrinsic.cc); netlib parcur uses sqrt(sum d**2). */
+static double f_norm2(const double *v, int nd)
+{
+    double result = 0.0, scale = 1.0;
+    int i;
+    for (i = 0; i < nd; ++i) {
+        if (v[i] != 0.0) {
+            double a = fabs(v[i]), val;
+            if (scale < a) {
+                val = scale / a;
+                result = 1.0 + result * val * val;
+                scale = a;
+            } else {
+                val = a / scale;
+                result += val * val;
+            }
+        }
+    }
+    return scale * sqrt(result);
+}
+
+/* core:5742-5771 */
+static void rotate_row_vec(double *h, int band, double *a, int nest, double *xi, double *z,
+                           int j_start, int n, int idim)
+{
+    double *H = h - 1;
+    int i, j = j_start, q, d;
+    for (i = 1; i <= band; ++i) {
+        double piv, cs, sn;
+        ++j;
+        piv = H[i];
+        if (g_netlib_compat ? (piv == 0.0) : orc_equal(piv, 0.0)) continue;
+        fpgivs(piv, &a[j - 1], &cs, &sn);
+        for (d = 0; d < idim; ++d) fprota(cs, sn, &xi[d], &z[d * n + (j - 1)]);
+        for (q = 1; q <= band - i; ++q) fprota(cs, sn, &H[i + q], &a[q * nest + (j - 1)]);
+    }
+}
+
+/* core:5845-5862 (no zero-pivot skip in the vector variant) */
+static void rotate_shifted_vec(double *h, int band, double *a, int nest, double *xi, double *z,
+                               int j_start, int j_end, int n, int idim)
+{
+    double *H = h - 1;
+    int j, q, d;
+    for (j = j_start; j <= j_end; ++j) {
+        double piv = H[1], cs, sn;
+        fpgivs(piv, &a[j - 1], &cs, &sn);
+        for (d = 0; d < idim; ++d) fprota(cs, sn, &xi[d], &z[d * n + (j - 1)]);
+        if (j < j_end) {
+            int i2 = j_end - j;
+            if (i2 > band - 1) i2 = band - 1;
+            i2 += 1;
+            for (q = 2; q <= i2; ++q) fprota(cs, sn, &H[q], &a[(q - 1) * nest + (j - 1)]);
+            for (q = 1; q < i2; ++q) H[q] = H[q + 1];
+            H[i2] = 0.0;
+        }
+    }
+}
+
+/* core:8822-9177 */
+static void fppara(int iopt, int idim, int m, const double *u, const double *x, const double *w,
+                   double ub, double ue, int k, double s, int nest, double tol, int maxit, int k1,
+                   int k2, int32_t *n_io, double *t, int nc, double *c, double *fp_out,
+                   double *fpint, double *z, double *a, double *b, double *g, double *q,
+                   int32_t *nrdata, int32_t *ier_io)
+{
+    const double *U = u - 1, *W = w - 1, *X = x - 1;
+    double *T = t - 1, *C = c - 1, *FPI = fpint - 1;
+    int32_t *NRD = nrdata - 1;
+    double acc, fac, fpart, fpms, fpold, fp0, f1, f2 = 0.0, f3, p, pinv, p1, p2 = 0.0, p3, rn, store,
+           term, ui, wi, fp = 0.0;
+    int i, it, iter, j, jj, j1, j2, l, l0, nk1, nmax, nmin, nplus, npl1, nrint, n8, n = *n_io,
+        ier = *ier_io;
+    int check1, check3;
+    double h[ORC_MAX_ORDER + 1], xi[10];
+
+    fpold = 0.0;
+    fp0 = 0.0;
+    nplus = 0;
+    fpms = DBL_MAX;
+    nk1 = n - k1;
+    acc = tol * s;
+    nmax = m + k1;
+    nmin = 2 * k1;
+
+    if (iopt >= 0) {                                            /* core:8870-8921 */
+        if (s <= 0.0) {
+            n = nmax;
+            if (nmax > nest) { *ier_io = IER_STORAGE; *n_io = n; return; }
+            interp_knots(u, m, k, t);
+        } else {
+            if (iopt != 0 && n != nmin) {
+                fp0 = FPI[n];
+                fpold = FPI[n - 1];
+                nplus = NRD[n];
+            }
+            if (fp0 <= s || iopt == 0 || n == nmin) { n = nmin; fpold = 0.0; nplus = 0; NRD[1] = m - 2; }
+        }
+    }
+
+    iter = 0;
+    for (;;) {                                                  /* main_loop core:8926-9096 */
+        if (!(g_netlib_compat ? (iter < m) : (iter <= m))) break;
+        ++iter;
+        if (n == nmin) ier = IER_LSQ;
+        nrint = n - nmin + 1;
+        nk1 = n - k1;
+        for (i = 1; i <= k1; ++i) T[i] = ub;
+        for (i = nk1 + 1; i <= n; ++i) T[i] = ue;
+        fp = 0.0;
+        for (i = 0; i < nc; ++i) z[i] = 0.0;
+        for (j = 0; j < k1; ++j)
+            for (i = 0; i < nk1; ++i) a[j * nest + i] = 0.0;
+        l = k1;
+        g_stats.lsq_passes++;
+        for (it = 1; it <= m; ++it) {                           /* coefs core:8950-8974 */
+            ui = U[it];
+            wi = W[it];
+            for (j = 0; j < idim; ++j) xi[j] = x[(it - 1) * idim + j] * wi;
+            l = orc_knot_interval(t, ui, l, nk1);
+            orc_fpbspl(t, n, k, ui, l, h);
+            for (j = 0; j < k1; ++j) { q[j * m + (it - 1)] = h[j]; h[j] = wi * h[j]; }
+            rotate_row_vec(h, k1, a, nest, xi, z, l - k1, n, idim);
+            if (g_netlib_compat) {
+                for (j = 0; j < idim; ++j) fp = fp + xi[j] * xi[j];
+            } else {                                            /* fp + sum(xi**2), core:8972 */
+                double sq = 0.0;
+                for (j = 0; j < idim; ++j) sq = sq + xi[j] * xi[j];
+                fp = fp + sq;
+            }
+        }
+        if (ier == IER_LSQ) fp0 = fp;
+        FPI[n - 1] = fpold;
+        FPI[n] = fp0;
+        NRD[n] = nplus;
+        j1 = 0;
+        for (j2 = 0; j2 < idim; ++j2) {                         /* core:8981-8985 */
+            fpback(a, z + j1, nk1, k1, c + j1, nest);
+            j1 += n;
+        }
+        if (iopt < 0) goto done;
+        fpms = fp - s;
+        if (fabs(fpms) < acc) goto done;
+        if (fpms < 0.0) break;
+        if (n == nmax) { ier = IER_INTERP; goto done; }
+        if (n == nest) { ier = IER_STORAGE; goto done; }
+        if (ier == IER_OK) {                                    /* core:9008-9016 */
+            int h2, mx;
+            npl1 = nplus * 2;
+            rn = (double)nplus;
+            if (fpold - fp > acc) npl1 = f_int(rn * fpms / (fpold - fp));
+            h2 = nplus / 2;
+            mx = npl1;
+            if (h2 > mx) mx = h2;
+            if (1 > mx) mx = 1;
+            nplus = (nplus * 2 < mx) ? nplus * 2 : mx;
+        } else {
+            nplus = 1;
+            ier = IER_OK;
+        }
+        fpold = fp;
+        fpart = 0.0;                                            /* core:9023-9052 */
+        i = 1;
+        l = k2;
+        jj = 0;
+        {
+            int newk = 0;
+            for (it = 1; it <= m; ++it) {
+                if (U[it] >= T[l] && l <= nk1) { newk = 1; ++l; }
+                term = 0.0;
+                l0 = l - k2;
+                for (j2 = 1; j2 <= idim; ++j2) {
+                    fac = 0.0;
+                    for (j = 1; j <= k1; ++j) fac = fac + C[l0 + j] * q[(j - 1) * m + (it - 1)];
+                    ++jj;
+                    store = W[it] * (fac - X[jj]);
+                    term = term + store * store;
+                    l0 += n;
+                }
+                fpart = fpart + term;
+                if (newk) {
+                    store = term * 0.5;
+                    FPI[i] = fpart - store;
+                    ++i;
+                    fpart = store;
+                    newk = 0;
+                }
+            }
+        }
+        FPI[nrint] = fpart;
+        for (l = 1; l <= nplus; ++l) {                          /* core:9055-9084 */
+            fpknot(u, m, t, &n, fpint, nrdata, &nrint, nest, 1);
+            if (n == nmax) {
+                interp_knots(u, m, k, t);
+                iter = 0;
+                break;
+            }
+            if (n == nest) break;
+        }
+    }
+
+    if (ier == IER_LSQ) goto done;                              /* core:9091 */
+
+    /* part 2, core:9112-9170 */
+    fpdisc(t, n, k2, b, nest);
+    p1 = 0.0;
+    f1 = fp0 - s;
+    p3 = -1.0;
+    f3 = fpms;
+    p = 0.0;
+    for (i = 1; i <= nk1; ++i) p = p + a[i - 1];
+    rn = (double)nk1;
+    p = g_netlib_compat ? rn / p : p / rn;                      /* core:9119: sum(a(:,1))/nk1 */
+    check1 = 0;
+    check3 = 0;
+    n8 = n - nmin;
+    iter = 0;
+    while (iter < maxit) {
+        ++iter;
+        g_stats.p_iters++;
+        pinv = 1.0 / p;
+        for (i = 0; i < nc; ++i) c[i] = z[i];
+        for (j = 0; j < k1; ++j)
+            for (i = 0; i < nk1; ++i) g[j * nest + i] = a[j * nest + i];
+        for (i = 0; i < nk1; ++i) g[(k2 - 1) * nest + i] = 0.0;
+        for (it = 1; it <= n8; ++it) {
+            for (j = 0; j < k2; ++j) h[j] = b[j * nest + (it - 1)] * pinv;
+            for (j = 0; j < idim; ++j) xi[j] = 0.0;
+            rotate_shifted_vec(h, k2, g, nest, xi, c, it, nk1, n, idim);
+        }
+        j1 = 0;
+        for (j2 = 0; j2 < idim; ++j2) {
+            fpback(g, c + j1, nk1, k2, c + j1, nest);
+            j1 += n;
+        }
+        fp = 0.0;
+        l = k2;
+        jj = 0;
+        for (it = 1; it <= m; ++it) {                           /* get_fp core:9147-9159 */
+            if (U[it] >= T[l] && l <= nk1) ++l;
+            l0 = l - k2;
+            term = 0.0;
+            for (j2 = 1; j2 <= idim; ++j2) {
+                fac = 0.0;
+                for (j = 1; j <= k1; ++j) fac = fac + C[l0 + j] * q[(j - 1) * m + (it - 1)];
+                ++jj;
+                store = fac - X[jj];
+                term = term + store * store;
+                l0 += n;
+            }
+            /* term*w(it)**2 (core:9158); scipy's hand translation of netlib evaluates it left to
+               right as (term*w)*w -- netlib's own Fortran is term*(w*w) like the reference */
+            fp = g_netlib_compat ? fp + term * W[it] * W[it] : fp + term * (W[it] * W[it]);
+        }
+        fpms = fp - s;
+        if (fabs(fpms) < acc) goto done;
+        if (!root_iterate(&p1, &f1, &p2, &f2, &p3, &f3, &p, fpms, acc, &check1, &check3)) {
+            ier = IER_S_SMALL;
+            goto done;
+        }
+    }
+    ier = IER_MAXIT;
+
+done:
+    *n_io = n;
+    *fp_out = fp;
+    *ier_io = ier;
+}
+
+/* parcur, core:15201-15285 (argument list of fp_parcur_c; ub, ue, u are in/out) */
+void orc_parcur(int32_t iopt, int32_t ipar, int32_t idim, int32_t m, double *u, int32_t mx,
+                const double *x, const double *w, double *ub, double *ue, int32_t k, double s,
+                int32_t nest, int32_t *n, double *t, int32_t nc, double *c, double *fp, double *wrk,
+                int32_t lwrk, int32_t *iwrk, int32_t *ier)
+{
+    const double tol = 1.0e-03;
+    const int maxit = 20;
+    int k1 = k + 1, k2 = k1 + 1, nmin = 2 * k1, lwest, ncc, i, j;
+    int ifp, iz, ia, ib, ig, iq;
+
+    *ier = IER_INPUT;
+    if (iopt < -1 || iopt > 1) return;
+    if (ipar < 0 || ipar > 1) return;
+    if (idim <= 0 || idim > 10) return;
+    if (k <= 0 || k > 5) return;
+    if (m < k1 || nest < nmin) return;
+    ncc = nest * idim;
+    if (mx < m * idim || nc < ncc) return;
+    lwest = m * k1 + nest * (6 + idim + 3 * k);
+    if (lwrk < lwest) return;
+    if (ipar == 0 && iopt <= 0) {                               /* core:15238-15253 */
+        double d[10];
+        u[0] = 0.0;
+        for (i = 1; i < m; ++i) {
+            if (g_netlib_compat) {
+                double dist = 0.0;
+                for (j = 0; j < idim; ++j) {
+                    double df = x[i * idim + j] - x[(i - 1) * idim + j];
+                    dist = dist + df * df;
+                }
+                u[i] = u[i - 1] + sqrt(dist);
+            } else {
+                for (j = 0; j < idim; ++j) d[j] = x[i * idim + j] - x[(i - 1) * idim + j];
+                u[i] = u[i - 1] + f_norm2(d, idim);
+            }
+        }
+        if (u[m - 1] <= 0.0) return;
+        for (i = 1; i < m; ++i) u[i] = u[i] / u[m - 1];
+        *ub = 0.0;
+        *ue = 1.0;
+        u[m - 1] = *ue;
+    }
+    if (*ub > u[0] || *ue < u[m - 1] || w[0] <= 0.0) return;
+    for (i = 0; i < m - 1; ++i)
+        if (u[i] >= u[i + 1] || w[i + 1] <= 0.0) return;
+    if (iopt < 0) {
+        if (*n < nmin || *n > nest) return;
+        j = *n;
+        for (i = 1; i <= k1; ++i) {
+            t[i - 1] = *ub;
+            t[j - 1] = *ue;
+            --j;
+        }
+        *ier = orc_fpchec(u, m, t, *n, k);
+        if (*ier != 0) return;
+    } else {
+        if (s < 0.0) return;
+        if (orc_equal(s, 0.0) && nest < (m + k1)) return;
+        *ier = IER_OK;
+    }
+    ifp = 0;
+    iz = ifp + nest;
+    ia = iz + ncc;
+    ib = ia + nest * k1;
+    ig = ib + nest * k2;
+    iq = ig + nest * k2;
+    fppara(iopt, idim, m, u, x, w, *ub, *ue, k, s, nest, tol, maxit, k1, k2, n, t, ncc, c, fp,
+           wrk + ifp, wrk + iz, wrk + ia, wrk + ib, wrk + ig, wrk + iq, iwrk, ier);
+}
+
+/* curev, core:1126-1182 (argument list of fp_curev_c) */
+void orc_curev(int32_t idim, const double *t, int32_t n, const double *c, int32_t nc, int32_t k,
+               const double *u, int32_t m, double *x, int32_t mx, int32_t *ier)
+{
+    int k1 = k + 1, nk1 = n - k1, l = k1, i, j, d;
+    double tb, te, h[ORC_MAX_ORDER + 1];
+    (void)nc;
+    *ier = IER_INPUT;
+    if (m < 1) return;
+    for (i = 1; i < m; ++i)
+        if (u[i] < u[i - 1]) return;
+    if (mx < m * idim) return;
+    *ier = IER_OK;
+    tb = t[k1 - 1];
+    te = t[nk1];
+    for (i = 0; i < m; ++i) {
+        double arg = u[i];
+        int ll;
+        if (arg < tb) arg = tb;                                 /* min(max(u,tb),te) */
+        if (arg > te) arg = te;
+        l = orc_knot_interval(t, arg, l, nk1);
+        orc_fpbspl(t, n, k, arg, l, h);
+        ll = l - k1;
+        for (d = 0; d < idim; ++d) {
+            double sum = 0.0;
+            for (j = 0; j < k1; ++j) sum = sum + h[j] * c[ll + j];
+            x[i * idim + d] = sum;
+            ll += n;
+        }
+    }
+}
+
+/* batch driver (CPU baseline): x [nbatch][m][idim], u [nbatch][m] in/out, w NULL => 1,
+   t [nbatch][nest], c [nbatch][nest*idim] */
+void orc_parcur_batch(int32_t nbatch, int32_t iopt, int32_t ipar, int32_t idim, int32_t m, double *u,
+                      const double *x, const double *w, double *ub, double *ue, int32_t k, double s,
+                      int32_t nest, int32_t *n, double *t, double *c, double *fp, int32_t *ier,
+                      int32_t nthreads)
+{
+    int lwrk = m * (k + 1) + nest * (6 + idim + 3 * k);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        double *wrk = (double *)malloc(sizeof(double) * (size_t)lwrk);
+        int32_t *iwrk = (int32_t *)malloc(sizeof(int32_t) * (size_t)nest);
+        double *ones = NULL;
+        int32_t b;
+        if (!w) {
+            int i;
+            ones = (double *)malloc(sizeof(double) * (size_t)m);
+            for (i = 0; i < m; ++i) ones[i] = 1.0;
+        }
+#pragma omp for schedule(dynamic, 16)
+        for (b = 0; b < nbatch; ++b)
+            orc_parcur(iopt, ipar, idim, m, u + (size_t)b * m, m * idim, x + (size_t)b * m * idim,
+                       w ? w + (size_t)b * m : ones, &ub[b], &ue[b], k, s, nest, &n[b],
+                       t + (size_t)b * nest, nest * idim, c + (size_t)b * nest * idim, &fp[b], wrk,
+                       lwrk, iwrk, &ier[b]);
+        free(wrk);
+        free(iwrk);
+        free(ones);
+    }
+}

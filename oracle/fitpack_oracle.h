@@ -117,6 +117,19 @@ void orc_spalde(const double *t, int32_t n, const double *c, int32_t k1, double 
 double orc_splint(const double *t, int32_t n, const double *c, int32_t k, double a, double b,
                   double *wrk);
 
+/* parcur core:15201-15285 + fppara 8822-9177 (argument list of fp_parcur_c), curev core:1126-1182
+   (argument list of fp_curev_c).  x(idim,m) coordinate-fastest; c((d-1)*n + i). */
+void orc_parcur(int32_t iopt, int32_t ipar, int32_t idim, int32_t m, double *u, int32_t mx,
+                const double *x, const double *w, double *ub, double *ue, int32_t k, double s,
+                int32_t nest, int32_t *n, double *t, int32_t nc, double *c, double *fp, double *wrk,
+                int32_t lwrk, int32_t *iwrk, int32_t *ier);
+void orc_curev(int32_t idim, const double *t, int32_t n, const double *c, int32_t nc, int32_t k,
+               const double *u, int32_t m, double *x, int32_t mx, int32_t *ier);
+void orc_parcur_batch(int32_t nbatch, int32_t iopt, int32_t ipar, int32_t idim, int32_t m, double *u,
+                      const double *x, const double *w, double *ub, double *ue, int32_t k, double s,
+                      int32_t nest, int32_t *n, double *t, double *c, double *fp, int32_t *ier,
+                      int32_t nthreads);
+
 int32_t orc_max_threads(void);
 
 /* tests only: switch the documented reference-vs-netlib deviations off (see .c) */

@@ -318,14 +318,124 @@ def make_calculus():
     np.savez_compressed(os.path.join(HERE, "calculus_golden.npz"), **out)
 
 
+
+# ------------------------------------------------------------------ parametric curves
+def parcur_lwrk(m, k, nest, idim):
+    return m * (k + 1) + nest * (6 + idim + 3 * k)
+
+
+def scipy_parcur(iopt, ipar, idim, u, x, w, ub, ue, k, s, nest, t=None, wrk=None, iwrk=None):
+    """x [m][idim] (memory order of Fortran x(idim,m)); returns t, c [idim][nk1], dict."""
+    t = np.array([], float) if t is None else t
+    wrk = np.array([], float) if wrk is None else wrk
+    iwrk = np.array([], np.int32) if iwrk is None else iwrk
+    return _fitpack.parcur(np.ascontiguousarray(x).ravel().copy(), w, u.copy(), ub, ue, k, iopt,
+                           ipar, s, t, nest, wrk, iwrk, 0)
+
+
+def synth_param_curve(rng, m, idim, sigma=0.05):
+    th = np.sort(rng.uniform(0, 2 * np.pi, m))
+    th = np.unique(th)
+    cols = []
+    for d in range(idim):
+        f = rng.uniform(0.5, 3)
+        cols.append(rng.uniform(.5, 2) * np.cos(f * th + rng.uniform(0, 6)))
+    x = np.stack(cols, 1) + sigma * rng.standard_normal((th.size, idim))
+    return th, x
+
+
+def make_parcur():
+    """parcur (ipar 0/1, iopt 0/-1 and 0 -> 1 continuations) + curev-by-splev(e=3) goldens."""
+    rng = np.random.default_rng(4242)
+    rec = dict(k=[], m=[], idim=[], ipar=[], iopt=[], s=[], nest=[], ub=[], ue=[], n=[], fp=[], ier=[],
+               xoff=[], uoff=[], toff=[], coff=[], s0=[])
+    xcat, ucat, uincat, wcat, tcat, ccat, evcat = [], [], [], [], [], [], []
+    xoff = uoff = toff = coff = 0
+    for trial in range(150):
+        k = int(rng.integers(1, 6))
+        idim = int(rng.choice([1, 2, 2, 3, 3, 4, 7, 10]))
+        m = int(rng.integers(k + 3, 120))
+        th, x = synth_param_curve(rng, m, idim)
+        m = th.size
+        w = np.ones(m) if rng.random() < 0.5 else rng.uniform(0.5, 2, m)
+        ipar = int(rng.random() < 0.4)
+        s = float(rng.choice([0.0, m * 0.0025 * idim, m * 0.0005, m * 0.05, 1e-9, 500.0]))
+        nest = int(rng.choice([m + k + 1, max(2 * k + 2, m // 3), max(2 * k + 3, m // 2)]))
+        mode = rng.choice(["fit", "lsq", "cont"], p=[0.6, 0.2, 0.2])
+        u_in = th.copy() if ipar else np.zeros(m)
+        ub, ue = (th[0] - 0.1 * (trial % 2), th[-1] + 0.05 * (trial % 3)) if ipar else (0.0, 1.0)
+        s0 = -1.0
+        if mode == "fit":
+            iopt = 0
+            t, c, o = scipy_parcur(0, ipar, idim, u_in, x, w, ub, ue, k, s, nest)
+        elif mode == "lsq":
+            iopt = -1
+            nint = int(rng.integers(1, max(2, min(8, m - k - 2))))
+            if ipar:
+                lo, hi = ub, ue
+                uu = th
+            else:
+                lo, hi = 0.0, 1.0
+                # netlib chord-length parameter (to place interior knots inside the data)
+                d = np.sqrt(((x[1:] - x[:-1]) ** 2).sum(1))
+                uu = np.concatenate([[0], np.cumsum(d)]) / d.sum()
+            tin = np.zeros(nint + 2 * k + 2)
+            tin[k + 1:k + 1 + nint] = np.quantile(uu, np.linspace(0, 1, nint + 2)[1:-1])
+            nest = tin.size
+            t, c, o = scipy_parcur(-1, ipar, idim, u_in, x, w, lo, hi, k, 0.0, nest, t=tin)
+            ub, ue = lo, hi
+            s = 0.0
+        else:
+            # iopt=0 with a large s, then iopt=1 continuation with the final s
+            iopt = 1
+            s0 = float(max(s * 20, m * 0.5))
+            t0, c0, o0 = scipy_parcur(0, ipar, idim, u_in, x, w, ub, ue, k, s0, nest)
+            if o0["ier"] > 0:
+                continue
+            tt = np.zeros(nest)
+            tt[:len(t0)] = t0
+            t, c, o = scipy_parcur(1, ipar, idim, o0["u"], x, w, o0["ub"], o0["ue"], k, s, nest,
+                                   t=tt[:len(t0)].copy(), wrk=o0["wrk"], iwrk=o0["iwrk"])
+        ier = int(o["ier"])
+        fp = float(o["fp"])
+        if not np.isfinite(fp) and ier != 10:
+            continue
+        n = 0 if ier == 10 else len(t)
+        nk1 = n - k - 1
+        ev = np.zeros(0)
+        if ier != 10:
+            ue_pts = np.sort(rng.uniform(o["ub"] - 0.1, o["ue"] + 0.1, 23))
+            cm = np.asarray(c).reshape(idim, nk1)
+            ev = np.stack([np.asarray(_fitpack.splev(np.asarray(t), np.concatenate([cm[d], np.zeros(k + 1)]),
+                                                      k, ue_pts, 3)[0]) for d in range(idim)], 1).ravel()
+            ev = np.concatenate([ue_pts, ev])
+        for key, v in (("k", k), ("m", m), ("idim", idim), ("ipar", ipar), ("iopt", iopt), ("s", s),
+                       ("nest", nest), ("ub", ub), ("ue", ue), ("n", n), ("fp", fp), ("ier", ier),
+                       ("xoff", xoff), ("uoff", uoff), ("toff", toff), ("coff", coff), ("s0", s0)):
+            rec[key].append(v)
+        xcat.append(x.ravel()); uincat.append(u_in); ucat.append(np.asarray(o["u"])); wcat.append(w)
+        tcat.append(np.asarray(t)[:n]); ccat.append(np.asarray(c).ravel()[:max(nk1, 0) * idim])
+        evcat.append(ev)
+        xoff += x.size; uoff += m; toff += n; coff += max(nk1, 0) * idim
+    ints = ("k", "m", "idim", "ipar", "iopt", "nest", "n", "ier")
+    out = {key: np.array(v, np.int32 if key in ints else (np.int64 if key.endswith("off") else float))
+           for key, v in rec.items()}
+    evoff = np.cumsum([0] + [e.size for e in evcat])[:-1]
+    np.savez_compressed(os.path.join(HERE, "parcur_golden.npz"), x=np.concatenate(xcat),
+                        u_in=np.concatenate(uincat), u=np.concatenate(ucat), w=np.concatenate(wcat),
+                        t=np.concatenate(tcat), c=np.concatenate(ccat), ev=np.concatenate(evcat),
+                        evoff=np.array(evoff, np.int64), **out)
+    print("parcur cases:", len(rec["k"]), "ier histogram:",
+          {int(v): int((np.array(rec["ier"]) == v).sum()) for v in np.unique(rec["ier"])},
+          "iopt:", {int(v): int((np.array(rec["iopt"]) == v).sum()) for v in np.unique(rec["iopt"])})
+
 if __name__ == "__main__":
     import sys
     sys.path.insert(0, os.path.dirname(HERE))
-    make_mncurf()
-    make_curfit()
-    make_splev()
-    make_regrid()
-    make_calculus()
-    for f in ("mncurf_golden.npz", "curfit_golden.npz", "splev_golden.npz", "regrid_golden.npz",
-              "calculus_golden.npz"):
+    makers = dict(mncurf=make_mncurf, curfit=make_curfit, splev=make_splev, regrid=make_regrid,
+                  calculus=make_calculus, parcur=make_parcur)
+    # python make_golden.py [name ...]: regenerate only the named fixtures (default: all)
+    for name in (sys.argv[1:] or list(makers)):
+        makers[name]()
+        f = name + "_golden.npz"
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -288,3 +288,66 @@ def splint(t, n, c, k, a, b):
     L.orc_splint.restype = C.c_double
     v = L.orc_splint(_d(t), C.c_int32(n), _d(c), C.c_int32(k), C.c_double(a), C.c_double(b), _d(wrk))
     return float(v), wrk
+
+
+# ------------------------------------------------------------------ parametric curves
+def parcur_lwrk(m, k, nest, idim):
+    return m * (k + 1) + nest * (6 + idim + 3 * k)
+
+
+def parcur(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=0.0, ue=1.0, n=0, t=None, wrk=None,
+           iwrk=None, c=None):
+    """orc_parcur with the reference's argument list (core:15201).  x is [m][idim] (the memory
+    order of Fortran's x(idim,m)).  Returns dict(n,t,c,fp,ier,u,ub,ue,wrk,iwrk)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    m = x.shape[0]
+    w = np.ones(m) if w is None else np.ascontiguousarray(w, dtype=np.float64)
+    u = np.zeros(m) if u is None else np.array(u, dtype=np.float64)
+    lwrk = parcur_lwrk(m, k, nest, idim) if wrk is None else wrk.size
+    t = np.zeros(max(nest, 1)) if t is None else np.array(t, dtype=np.float64)
+    c = np.zeros(max(nest * idim, 1)) if c is None else np.array(c, dtype=np.float64)
+    wrk = np.zeros(max(lwrk, 1)) if wrk is None else wrk
+    iwrk = np.zeros(max(nest, 1), dtype=np.int32) if iwrk is None else iwrk
+    n_, fp_, ier_ = C.c_int32(int(n)), C.c_double(0.0), C.c_int32(0)
+    ub_, ue_ = C.c_double(ub), C.c_double(ue)
+    L = lib()
+    L.orc_parcur.restype = None
+    L.orc_parcur(C.c_int32(iopt), C.c_int32(ipar), C.c_int32(idim), C.c_int32(m), _d(u),
+                 C.c_int32(m * idim), _d(x), _d(w), C.byref(ub_), C.byref(ue_), C.c_int32(k),
+                 C.c_double(s), C.c_int32(nest), C.byref(n_), _d(t), C.c_int32(nest * idim), _d(c),
+                 C.byref(fp_), _d(wrk), C.c_int32(lwrk), _i(iwrk), C.byref(ier_))
+    return dict(n=n_.value, t=t, c=c, fp=fp_.value, ier=ier_.value, u=u, ub=ub_.value, ue=ue_.value,
+                wrk=wrk, iwrk=iwrk)
+
+
+def curev(idim, t, n, c, k, u):
+    t, c, u = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, c, u))
+    m = u.size
+    x = np.zeros(max(m * idim, 1))
+    ier = C.c_int32(0)
+    L = lib()
+    L.orc_curev.restype = None
+    L.orc_curev(C.c_int32(idim), _d(t), C.c_int32(n), _d(c), C.c_int32(c.size), C.c_int32(k), _d(u),
+                C.c_int32(m), _d(x), C.c_int32(m * idim), C.byref(ier))
+    return x[:m * idim].reshape(m, idim), ier.value
+
+
+def parcur_batch(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=None, ue=None, nthreads=0):
+    """x [B][m][idim]; returns dict(n,t,c,fp,ier,u,ub,ue) with c [B][nest*idim]."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    B, m = x.shape[0], x.shape[1]
+    u = np.zeros((B, m)) if u is None else np.array(u, dtype=np.float64)
+    ub = np.zeros(B) if ub is None else np.array(ub, dtype=np.float64)
+    ue = np.ones(B) if ue is None else np.array(ue, dtype=np.float64)
+    n = np.zeros(B, np.int32)
+    t = np.zeros((B, nest))
+    c = np.zeros((B, nest * idim))
+    fp = np.zeros(B)
+    ier = np.zeros(B, np.int32)
+    wp = None if w is None else _d(np.ascontiguousarray(w, dtype=np.float64))
+    L = lib()
+    L.orc_parcur_batch.restype = None
+    L.orc_parcur_batch(C.c_int32(B), C.c_int32(iopt), C.c_int32(ipar), C.c_int32(idim), C.c_int32(m),
+                       _d(u), _d(x), wp, _d(ub), _d(ue), C.c_int32(k), C.c_double(s), C.c_int32(nest),
+                       _i(n), _d(t), _d(c), _d(fp), _i(ier), C.c_int32(nthreads))
+    return dict(n=n, t=t, c=c, fp=fp, ier=ier, u=u, ub=ub, ue=ue)

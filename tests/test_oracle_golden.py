@@ -418,3 +418,107 @@ def test_calculus_semantics():
     a2, _ = O.splint(t, 9, c, 3, 0.9, 0.1)
     a3 = O.splint(t, 9, c, 3, 0.1, 0.4)[0] + O.splint(t, 9, c, 3, 0.4, 0.9)[0]
     assert a1 == -a2 and abs(a1 - a3) < 1e-14
+
+
+# ------------------------------------------------------------------ parametric curves
+def _parcur_cases():
+    g = np.load(os.path.join(G, "parcur_golden.npz"))
+    for i in range(g["k"].size):
+        k, m, idim = int(g["k"][i]), int(g["m"][i]), int(g["idim"][i])
+        xo, uo = int(g["xoff"][i]), int(g["uoff"][i])
+        yield i, g, dict(k=k, m=m, idim=idim, ipar=int(g["ipar"][i]), iopt=int(g["iopt"][i]),
+                         s=float(g["s"][i]), nest=int(g["nest"][i]), ub=float(g["ub"][i]),
+                         ue=float(g["ue"][i]), s0=float(g["s0"][i]),
+                         x=g["x"][xo:xo + m * idim].reshape(m, idim), w=g["w"][uo:uo + m],
+                         u_in=g["u_in"][uo:uo + m], u=g["u"][uo:uo + m])
+
+
+def run_parcur_case(fn, cs, g, i):
+    """Replay golden case i through a parcur implementation `fn` with oracle_lib.parcur's signature."""
+    k, idim, nest = cs["k"], cs["idim"], cs["nest"]
+    if cs["iopt"] == 0:
+        return fn(0, cs["ipar"], idim, cs["x"], cs["w"], k, cs["s"], nest, u=cs["u_in"], ub=cs["ub"],
+                  ue=cs["ue"])
+    if cs["iopt"] == -1:
+        n = int(g["n"][i]) if int(g["ier"][i]) != 10 else nest
+        to = int(g["toff"][i])
+        t = np.zeros(nest)
+        if int(g["ier"][i]) != 10:
+            t[:n] = g["t"][to:to + n]
+        return fn(-1, cs["ipar"], idim, cs["x"], cs["w"], k, 0.0, nest, u=cs["u_in"], ub=cs["ub"],
+                  ue=cs["ue"], n=n, t=t)
+    r0 = fn(0, cs["ipar"], idim, cs["x"], cs["w"], k, cs["s0"], nest, u=cs["u_in"], ub=cs["ub"], ue=cs["ue"])
+    return fn(1, cs["ipar"], idim, cs["x"], cs["w"], k, cs["s"], nest, u=r0["u"], ub=r0["ub"], ue=r0["ue"],
+              n=r0["n"], t=r0["t"], wrk=r0["wrk"], iwrk=r0["iwrk"])
+
+
+def check_parcur_case(r, cs, g, i, exact=True, rtol=0.0):
+    k, idim = cs["k"], cs["idim"]
+    assert r["ier"] == int(g["ier"][i]), i
+    if r["ier"] == 10:
+        return
+    n = int(g["n"][i])
+    assert r["n"] == n, i
+    nk1 = n - k - 1
+    to, co = int(g["toff"][i]), int(g["coff"][i])
+    assert np.array_equal(r["t"][:n], g["t"][to:to + n]), i
+    assert np.array_equal(r["u"], cs["u"]), i
+    cc = np.concatenate([r["c"][d * n:d * n + nk1] for d in range(idim)])
+    gc = g["c"][co:co + nk1 * idim]
+    if exact:
+        assert np.array_equal(cc, gc), i
+        assert r["fp"] == float(g["fp"][i]), i
+    else:
+        assert np.allclose(cc, gc, rtol=rtol, atol=rtol * np.abs(gc).max()), i
+        assert abs(r["fp"] - float(g["fp"][i])) <= rtol * max(abs(float(g["fp"][i])), 1e-300), i
+
+
+def test_parcur_and_curev_golden_bit_exact_in_netlib_mode():
+    """scipy's C translation of netlib parcur/fppara: the oracle with the documented reference
+    deviations switched to the netlib form (initial p = nk1/sum(a) instead of the reference's
+    sum(a)/nk1 core:9119, fp accumulated coordinate by coordinate instead of fp+sum(xi**2)
+    core:8972, chord lengths by sqrt(sum d^2) instead of NORM2 core:15243, fpknot seeding, loop
+    bound) must reproduce n, knots, u, c, fp, ier bit for bit; curev == splev(e=3) per coordinate."""
+    O.set_netlib_compat(1)
+    try:
+        ncase = 0
+        for i, g, cs in _parcur_cases():
+            r = run_parcur_case(O.parcur, cs, g, i)
+            check_parcur_case(r, cs, g, i)
+            ncase += 1
+            if r["ier"] != 10:
+                eo = int(g["evoff"][i])
+                pts = g["ev"][eo:eo + 23]
+                want = g["ev"][eo + 23:eo + 23 * (1 + cs["idim"])].reshape(23, cs["idim"])
+                got, ier = O.curev(cs["idim"], r["t"], r["n"], r["c"], cs["k"], pts)
+                assert ier == 0 and np.array_equal(got, want), i
+        assert ncase > 140
+    finally:
+        O.set_netlib_compat(0)
+
+
+def test_parcur_reference_mode_properties():
+    """Default (reference) mode: same discrete outcome as netlib on regular data, fp equals the
+    residual recomputed through curev, ier=0 => |fp-s| < 1e-3 s, knots pass fpchec; curev rejects
+    decreasing parameters (core:1145) and clamps outside [tb,te]."""
+    nchk = 0
+    for i, g, cs in _parcur_cases():
+        if cs["iopt"] != 0 or int(g["ier"][i]) == 10:
+            continue
+        r = run_parcur_case(O.parcur, cs, g, i)
+        assert r["ier"] == int(g["ier"][i]) and r["n"] == int(g["n"][i]), i
+        ev, ier = O.curev(cs["idim"], r["t"], r["n"], r["c"], cs["k"], r["u"])
+        assert ier == 0
+        res = ((cs["w"][:, None] * (ev - cs["x"])) ** 2).sum()
+        assert abs(res - r["fp"]) <= 1e-9 * max(1.0, res, cs["s"]), i
+        if r["ier"] == 0:
+            assert abs(r["fp"] - cs["s"]) < 1e-3 * cs["s"], i
+        assert O.fpchec(r["u"], r["t"], r["n"], cs["k"]) == 0, i
+        nchk += 1
+    assert nchk > 60
+    t = np.array([0., 0, 0, 0, 1, 1, 1, 1])
+    c = np.arange(16.0)
+    _, ier = O.curev(2, t, 8, c, 3, np.array([0.5, 0.4]))
+    assert ier == 10
+    v, ier = O.curev(2, t, 8, c, 3, np.array([-1.0, 2.0]))
+    assert ier == 0 and np.array_equal(v, [[0., 8.], [3., 11.]])
