@@ -155,6 +155,55 @@ class Engine:
             res["stats"] = stats_t
         return res
 
+    def parcur_batch(self, x, w=None, k=3, s=0.0, nest=None, iopt=0, ipar=0, u=None, ub=None, ue=None,
+                     n=None, t=None, fpint=None, nrdata=None, want_stats=False):
+        """Batched parcur on device tensors, point-major: x is [m][idim][B] (coordinate d of point i
+        of curve b at x[i, d, b]), u / w are [m][B].  ipar=0: u is computed on the device (returned).
+        ub/ue: None (data range) or [B] tensors.  Returns dict(n, t, c, fp, ier, u[, stats]) with
+        c [B][nest*idim] (coordinate d at c[b, d*n[b] : d*n[b]+n[b]-k-1])."""
+        _chk_f64(x, "x"); _chk_f64(w, "w"); _chk_f64(u, "u")
+        m, idim, B = x.shape
+        if not x.is_contiguous():
+            raise ValueError("x must be a contiguous [m][idim][B] tensor")
+        dev = x.device
+        f64, i32 = torch.float64, torch.int32
+        if u is None:
+            u = torch.zeros((m, B), device=dev, dtype=f64)
+        nest = int(nest if nest is not None else m + k + 1)
+        if torch.is_tensor(s):
+            s_t, s_stride = s.to(device=dev, dtype=f64).contiguous(), 1
+        else:
+            s_t, s_stride = torch.full((1,), float(s), device=dev, dtype=f64), 0
+        n_t = n if n is not None else torch.zeros(B, device=dev, dtype=i32)
+        t_t = t if t is not None else torch.zeros((B, nest), device=dev, dtype=f64)
+        c_t = torch.zeros((B, nest * idim), device=dev, dtype=f64)
+        fp_t = torch.zeros(B, device=dev, dtype=f64)
+        ier_t = torch.zeros(B, device=dev, dtype=i32)
+        stats_t = torch.zeros((B, 2), device=dev, dtype=i32) if want_stats else None
+        self.use_torch_stream()
+        rc = lib().fp_parcur_batch_dev_c(
+            self._h, B, int(iopt), int(ipar), idim, m, _ptr(u), 1, u.stride(0), _ptr(x), 1, x.stride(0),
+            x.stride(1), _ptr(w), 1, 0 if w is None else w.stride(0), _ptr(ub), _ptr(ue), 1, int(k),
+            _ptr(s_t), s_stride, nest, _ptr(n_t), _ptr(t_t), _ptr(c_t), _ptr(fp_t), _ptr(ier_t),
+            _ptr(fpint), _ptr(nrdata), _ptr(stats_t))
+        check(rc, "fp_parcur_batch_dev_c")
+        res = dict(n=n_t, t=t_t, c=c_t, fp=fp_t, ier=ier_t, u=u, _keep=(s_t,))
+        if want_stats:
+            res["stats"] = stats_t
+        return res
+
+    def curev_batch(self, idim, t, n, c, k, u):
+        """curev for many curves: t [B][ldt], c [B][ldc], u [B][m] -> (x [B][m][idim], ier [B])."""
+        _chk_f64(t, "t"); _chk_f64(c, "c"); _chk_f64(u, "u")
+        B, m = u.shape
+        x = torch.zeros((B, m, idim), device=u.device, dtype=torch.float64)
+        ier = torch.zeros(B, device=u.device, dtype=torch.int32)
+        self.use_torch_stream()
+        rc = lib().fp_curev_batch_dev_c(self._h, B, int(idim), _ptr(t), _ptr(n), _ptr(c), t.stride(0),
+                                        c.stride(0), int(k), _ptr(u.contiguous()), _ptr(x), m, _ptr(ier))
+        check(rc, "fp_curev_batch_dev_c")
+        return x, ier
+
     def curfit_shared(self, x, y, t, k=3, w=None, xb=None, xe=None, layout="point_major",
                       out=None, mode=0):
         """Shared-abscissa least squares (iopt=-1): x [m], t [n] (interior knots in place),

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libfitpack_b200.so")
 
-SOURCES = ["fpb_curfit.cu", "fpb_splev.cu", "fpb_shared.cu", "fpb_util.cu", "fpb_regrid.cu", "fpb_calculus.cu",
+SOURCES = ["fpb_curfit.cu", "fpb_curfit_d2.cu", "fpb_curfit_d3.cu", "fpb_curfit_d0.cu", "fpb_splev.cu", "fpb_shared.cu", "fpb_util.cu", "fpb_regrid.cu", "fpb_calculus.cu", "fpb_parcur.cu",
            "fpb_engine.cu",
            "fpb_curve.cpp"]
 
@@ -70,7 +70,10 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
         objs.append(o)
-        if force or _stale(o, [s] + headers):
+        deps = [s] + headers
+        if src.startswith("fpb_curfit_d"):
+            deps.append(os.path.join(CSRC, "fpb_curfit.cu"))
+        if force or _stale(o, deps):
             jobs.append((s, o))
 
     def compile_one(job):
@@ -87,7 +90,7 @@ def build(force=False, verbose=False):
         return o
 
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(6, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
     if force or jobs or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]

@@ -234,3 +234,70 @@ def splint(t, n, c, k, a, b):
     if v != v and lib().fpb_device_count() == 0:
         raise FitpackB200Error("fp_splint_c: %s" % lib().fpb_last_error().decode())
     return float(v), wrk
+
+
+# ------------------------------------------------------------------ parametric curves
+def parcur_lwrk(m, k, nest, idim):
+    return m * (k + 1) + nest * (6 + idim + 3 * k)
+
+
+def parcur(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=0.0, ue=1.0, n=0, t=None, wrk=None, iwrk=None,
+           c=None):
+    """parcur (reference core:15201-15285) through fp_parcur_c.  x is [m][idim] (memory order of
+    Fortran's x(idim,m)).  Returns dict(n,t,c,fp,ier,u,ub,ue,wrk,iwrk); pass t/n/u/ub/ue/wrk/iwrk
+    back for an iopt=1 continuation."""
+    x = _f64(x)
+    m = x.shape[0]
+    w = np.ones(m) if w is None else _f64(w)
+    u = np.zeros(m) if u is None else np.array(u, dtype=np.float64)
+    idim_, k_, nest_ = max(idim, 1), max(k, 0), max(nest, 0)
+    if wrk is None:
+        wrk = np.zeros(max(parcur_lwrk(m, k_, nest_, idim_), 1))
+    t = np.zeros(max(nest, 1)) if t is None else np.array(t, dtype=np.float64)
+    c = np.zeros(max(nest_ * idim_, 1)) if c is None else np.array(c, dtype=np.float64)
+    iwrk = np.zeros(max(nest, 1), dtype=np.int32) if iwrk is None else iwrk
+    n_, fp_, ier_ = C.c_int32(int(n)), C.c_double(0.0), C.c_int32(0)
+    ub_, ue_, s_ = C.c_double(ub), C.c_double(ue), C.c_double(s)
+    lib().fp_parcur_c(int(iopt), int(ipar), int(idim), m, _p(u), x.size, _p(x), _p(w), C.addressof(ub_),
+                      C.addressof(ue_), int(k), C.addressof(s_), int(nest), C.addressof(n_), _p(t),
+                      c.size, _p(c), C.addressof(fp_), _p(wrk), wrk.size, _p(iwrk), C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_parcur_c: %s" % lib().fpb_last_error().decode())
+    return dict(n=n_.value, t=t, c=c, fp=fp_.value, ier=ier_.value, u=u, ub=ub_.value, ue=ue_.value,
+                wrk=wrk, iwrk=iwrk)
+
+
+def curev(idim, t, n, c, k, u):
+    """curev (reference core:1126-1182) through fp_curev_c; returns (x [m][idim], ier)."""
+    t, c, u = _f64(t), _f64(c), _f64(u)
+    m = u.size
+    x = np.zeros(max(m * max(idim, 1), 1))
+    ier_ = C.c_int32(0)
+    lib().fp_curev_c(int(idim), _p(t), int(n), _p(c), c.size, int(k), _p(u), m, _p(x), m * idim,
+                     C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_curev_c: %s" % lib().fpb_last_error().decode())
+    return x[:m * idim].reshape(m, idim), ier_.value
+
+
+def parcur_batch(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=None, ue=None, n=None, t=None,
+                 fpint=None, nrdata=None):
+    """Many independent parametric curves, host arrays (fp_parcur_batch_c).  x [B][m][idim]."""
+    x = _f64(x)
+    B, m = x.shape[0], x.shape[1]
+    u = np.zeros((B, m)) if u is None else np.array(u, dtype=np.float64)
+    ub = np.zeros(B) if ub is None else np.array(ub, dtype=np.float64)
+    ue = np.ones(B) if ue is None else np.array(ue, dtype=np.float64)
+    w = None if w is None else _f64(w)
+    n_arr = np.zeros(B, dtype=np.int32) if n is None else np.array(n, dtype=np.int32)
+    t_arr = np.zeros((B, nest)) if t is None else np.array(t, dtype=np.float64)
+    c_arr = np.zeros((B, nest * idim))
+    fp = np.zeros(B)
+    ier = np.zeros(B, dtype=np.int32)
+    fpint = np.zeros((B, nest)) if fpint is None else fpint
+    nrdata = np.zeros((B, nest), dtype=np.int32) if nrdata is None else nrdata
+    rc = lib().fp_parcur_batch_c(B, int(iopt), int(ipar), int(idim), m, _p(u), _p(x), _p(w), _p(ub), _p(ue),
+                                 int(k), float(s), int(nest), _p(n_arr), _p(t_arr), _p(c_arr), _p(fp),
+                                 _p(ier), _p(fpint), _p(nrdata))
+    check(rc, "fp_parcur_batch_c")
+    return dict(n=n_arr, t=t_arr, c=c_arr, fp=fp, ier=ier, u=u, ub=ub, ue=ue, fpint=fpint, nrdata=nrdata)

@@ -34,8 +34,20 @@
 //    on the device; the host only reads one counter every other pass to know
 //    when the "needs another pass" list is empty.  Per-curve ier is an output, a
 //    bad curve never aborts the batch.
+//
+// Parametric curves (parcur/fppara, core:15201-15285 / 8822-9177) run through the SAME pipeline:
+// the kernels are templated on IDIM, the number of coordinate curves that share one knot vector
+// and one band matrix (fp_rotate_row_vec core:5742-5771, fp_rotate_shifted_vec core:5845-5862:
+// one Givens rotation, idim right-hand sides).  IDIM = 1, 2, 3 are compiled as separate
+// translation units (fpb_curfit_d2.cu ... include this file with FPB_FIT_IDIM set); IDIM = 0 is
+// the run-time fallback for idim = 4..10.  p.par selects parcur's argument checks and the few
+// places where fppara's arithmetic differs from fpcurf's.
 #include "fpb_common.cuh"
 #include "fpb_kernels.h"
+
+#ifndef FPB_FIT_IDIM
+#define FPB_FIT_IDIM 1
+#endif
 
 namespace fpb {
 
@@ -50,6 +62,8 @@ constexpr unsigned FULL = 0xffffffffu;
 #define T_(i) WS(p.off_t, (i) - 1)
 #define C_(i) WS(p.off_c, (i) - 1)
 #define Z_(i) WS(p.off_z, (i) - 1)
+#define CD_(d, i) WS(p.off_c + (d) * p.nestp, (i) - 1) /* coordinate d */
+#define ZD_(d, i) WS(p.off_z + (d) * p.nestp, (i) - 1)
 #define FPI_(i) WS(p.off_fpint, (i) - 1)
 #define A_(i, j) WS(p.off_a, ((i) - 1) * K1 + ((j) - 1))
 #define G_(i, j) WS(p.off_g, ((i) - 1) * K2 + ((j) - 1))
@@ -80,7 +94,7 @@ __device__ __forceinline__ void interp_knots(const FitParams &p, double *wsd, co
 // a warp-uniform range so that the loads coalesce; `on` masks the lane.
 template <int BAND>
 __device__ __forceinline__ void back_subst(const FitParams &p, double *wsd, int offm, int offz,
-                                           int nk1, bool on)
+                                           int offc, int nk1, bool on)
 {
     const int hi = __reduce_max_sync(FULL, on ? nk1 : 0);
     double cw[BAND - 1];
@@ -94,7 +108,7 @@ __device__ __forceinline__ void back_subst(const FitParams &p, double *wsd, int 
             for (int q = 1; q <= BAND - 1; ++q)
                 if (q <= cnt) store = sub(store, mul(cw[q - 1], WS(offm, (i - 1) * BAND + q)));
             const double ci = store / WS(offm, (i - 1) * BAND);
-            C_(i) = ci;
+            WS(offc, i - 1) = ci;
 #pragma unroll
             for (int q = BAND - 2; q >= 1; --q) cw[q] = cw[q - 1];
             cw[0] = ci;
@@ -103,34 +117,35 @@ __device__ __forceinline__ void back_subst(const FitParams &p, double *wsd, int 
 }
 
 // sum of squared residuals of the current c over all points using the stored
-// basis values q (get_fp loop, core:5061-5069); when FPINT is set also the
-// per-interval split of core:4942-4966.  Loads of 4 consecutive points are
+// basis values q (get_fp loop, core:5061-5069 / fppara core:9147-9159); when FPINT is set also the
+// per-interval split of core:4942-4966 (fppara core:9023-9052).  Loads of consecutive points are
 // issued together (they do not depend on the interval walk) to cover HBM latency.
-template <int K, bool FPINT, bool HAS_W>
+template <int K, bool FPINT, bool HAS_W, int IDIM>
 __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd, const double *xp,
                                                 const double *yp, const double *wp, size_t x_si,
-                                                size_t y_si, size_t w_si, int m, int nk1,
-                                                int nrint, bool on)
+                                                size_t y_si, size_t y_sd, size_t w_si, int m,
+                                                int nk1, int nrint, bool on)
 {
-    constexpr int K1 = K + 1, K2 = K + 2, U = 2;
-    double cw[K1];
+    constexpr int K1 = K + 1, K2 = K + 2, U = 2, ND = IDIM > 0 ? IDIM : kMaxIdim;
+    const int nd = IDIM > 0 ? IDIM : p.idim;
+    double cw[ND][K1];
     double fpart = 0.0, tl = 0.0;
     int l = K2, i = 1;
-    if (on) {
 #pragma unroll
-        for (int j = 0; j < K1; ++j) cw[j] = C_(j + 1);
-        tl = T_(l);
-    } else {
+    for (int d = 0; d < ND; ++d) {
 #pragma unroll
-        for (int j = 0; j < K1; ++j) cw[j] = 0.0;
+        for (int j = 0; j < K1; ++j) cw[d][j] = (on && d < nd) ? CD_(d, j + 1) : 0.0;
     }
+    if (on) tl = T_(l);
     for (int it0 = 0; it0 < m; it0 += U) {
-        double xv[U], yv[U], wv[U], qv[U][K1];
+        double xv[U], yv[U][ND], wv[U], qv[U][K1];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int it = min(it0 + u, m - 1);
             xv[u] = xp[(size_t)it * x_si];
-            yv[u] = yp[(size_t)it * y_si];
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (d < nd) yv[u][d] = yp[(size_t)it * y_si + (size_t)d * y_sd];
             wv[u] = HAS_W ? wp[(size_t)it * w_si] : 1.0;
             if (on) {
 #pragma unroll
@@ -146,16 +161,32 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
                         newk = true;
                         ++l;
 #pragma unroll
-                        for (int j = 0; j < K; ++j) cw[j] = cw[j + 1];
-                        cw[K] = C_(l - 1);
+                        for (int d = 0; d < ND; ++d) {
+                            if (d < nd) {
+#pragma unroll
+                                for (int j = 0; j < K; ++j) cw[d][j] = cw[d][j + 1];
+                                cw[d][K] = CD_(d, l - 1);
+                            }
+                        }
                         tl = T_(l);
                     }
+                    // fpcurf: (w*(s(x)-y))**2; fppara part 1: sum_d (w*(s_d(u)-x_d))**2 (identical
+                    // for one coordinate); fppara part 2: (sum_d (s_d(u)-x_d)**2) * w**2
+                    const bool late_w = HAS_W && !FPINT && p.par;
                     double term = 0.0;
 #pragma unroll
-                    for (int j = 0; j < K1; ++j) term = add(term, mul(cw[j], qv[u][j]));
-                    term = sub(term, yv[u]);
-                    if (HAS_W) term = mul(wv[u], term);
-                    term = mul(term, term);
+                    for (int d = 0; d < ND; ++d) {
+                        if (d < nd) {
+                            double fac = 0.0;
+#pragma unroll
+                            for (int j = 0; j < K1; ++j) fac = add(fac, mul(cw[d][j], qv[u][j]));
+                            fac = sub(fac, yv[u][d]);
+                            if (HAS_W && !late_w) fac = mul(wv[u], fac);
+                            fac = mul(fac, fac);
+                            term = (d == 0) ? fac : add(term, fac);
+                        }
+                    }
+                    if (late_w) term = mul(term, mul(wv[u], wv[u]));
                     fpart = add(fpart, term);
                     if (FPINT && newk) {
                         const double store = mul(term, 0.5);
@@ -178,19 +209,22 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
 // [element][thread] layout): that keeps the kernel at <= 80 registers, i.e. 24 warps per SM
 // instead of 16 -- the pass is bound by dependent FP64 issue latency, so warps are throughput.
 // A row is written to the workspace exactly once per pass, when the window leaves it.
-template <int K, bool HAS_W>
+template <int K, bool HAS_W, int IDIM>
 __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, double *rs,
                                            const double *xp, const double *yp, const double *wp,
-                                           size_t x_si, size_t y_si, size_t w_si, int m, int nk1,
-                                           bool on)
+                                           size_t x_si, size_t y_si, size_t y_sd, size_t w_si, int m,
+                                           int nk1, bool on)
 {
-    constexpr int K1 = K + 1, NT = kFitThreads;
+    constexpr int K1 = K + 1, NT = kFitThreads, ND = IDIM > 0 ? IDIM : kMaxIdim;
+    const int nd = IDIM > 0 ? IDIM : p.idim;
 #define RS_(slot, q) rs[((slot) * K1 + (q)) * NT]
-#define ZS_(slot) rs[(K1 * K1 + (slot)) * NT]
+#define ZS_(slot, d) rs[(K1 * K1 + (slot) * nd + (d)) * NT]
     double tw[2 * K], h[K1];
 #pragma unroll
     for (int r = 0; r < K1; ++r) {
-        ZS_(r) = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (d < nd) ZS_(r, d) = 0.0;
 #pragma unroll
         for (int q = 0; q < K1; ++q) RS_(r, q) = 0.0;
     }
@@ -204,16 +238,24 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
     }
     double fp = 0.0;
     // the next point's data is requested one iteration ahead
-    double xn = xp[0], yn = yp[0], wn = HAS_W ? wp[0] : 1.0;
+    double xn = xp[0], yn[ND], wn = HAS_W ? wp[0] : 1.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+        if (d < nd) yn[d] = yp[(size_t)d * y_sd];
     for (int it = 0; it < m; ++it) {
         const double xi = xn;
         const double wi = wn;
         // w == NULL means unit weights: y*1 and h*1 are exact, so the products are skipped
-        double yi = HAS_W ? mul(yn, wi) : yn;
+        double yi[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (d < nd) yi[d] = HAS_W ? mul(yn[d], wi) : yn[d];
         {
             const int nx = min(it + 1, m - 1);
             xn = xp[(size_t)nx * x_si];
-            yn = yp[(size_t)nx * y_si];
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (d < nd) yn[d] = yp[(size_t)nx * y_si + (size_t)d * y_sd];
             if (HAS_W) wn = wp[(size_t)nx * w_si];
         }
         if (on) {
@@ -227,8 +269,13 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
                     A_(row, q + 1) = RS_(s0, q);
                     RS_(s0, q) = 0.0;
                 }
-                Z_(row) = ZS_(s0);
-                ZS_(s0) = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    if (d < nd) {
+                        ZD_(d, row) = ZS_(s0, d);
+                        ZS_(s0, d) = 0.0;
+                    }
+                }
                 s0 = (s0 + 1 == K1) ? 0 : s0 + 1;
 #pragma unroll
                 for (int j = 0; j < 2 * K - 1; ++j) tw[j] = tw[j + 1];
@@ -241,17 +288,24 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
                 Q_(it, j) = h[j];
                 if (HAS_W) h[j] = mul(wi, h[j]);
             }
-            // fp_rotate_row (core:5691-5717): pivot i <-> band row l-K1+1+i
+            // fp_rotate_row / fp_rotate_row_vec (core:5691-5717 / 5742-5771): pivot i <-> band row
+            // l-K1+1+i; one rotation serves all coordinates
             int sl = s0;
 #pragma unroll
             for (int i = 0; i < K1; ++i) {
                 const double piv = h[i];
                 if (!fp_is_zero(piv)) {
-                    double cs, sn, d = RS_(sl, 0), z = ZS_(sl);
-                    givens(piv, d, cs, sn);
-                    RS_(sl, 0) = d;
-                    rota(cs, sn, yi, z);
-                    ZS_(sl) = z;
+                    double cs, sn, dg = RS_(sl, 0);
+                    givens(piv, dg, cs, sn);
+                    RS_(sl, 0) = dg;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        if (d < nd) {
+                            double z = ZS_(sl, d);
+                            rota(cs, sn, yi[d], z);
+                            ZS_(sl, d) = z;
+                        }
+                    }
 #pragma unroll
                     for (int q = 1; q <= K - i; ++q) {
                         double r = RS_(sl, q);
@@ -261,7 +315,12 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
                 }
                 sl = (sl + 1 == K1) ? 0 : sl + 1;
             }
-            fp = add(fp, mul(yi, yi));
+            // fp = fp + yi**2 (core:4895); fppara: fp + sum(xi**2) (core:8972)
+            double sq = mul(yi[0], yi[0]);
+#pragma unroll
+            for (int d = 1; d < ND; ++d)
+                if (d < nd) sq = add(sq, mul(yi[d], yi[d]));
+            fp = add(fp, sq);
         }
     }
     if (on) {
@@ -273,8 +332,13 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
                 A_(row, q + 1) = RS_(s0, q);
                 RS_(s0, q) = 0.0;
             }
-            Z_(row) = ZS_(s0);
-            ZS_(s0) = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                if (d < nd) {
+                    ZD_(d, row) = ZS_(s0, d);
+                    ZS_(s0, d) = 0.0;
+                }
+            }
             s0 = (s0 + 1 == K1) ? 0 : s0 + 1;
             ++l;
         }
@@ -284,7 +348,9 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
             const int row = l - K1 + 1 + r;
 #pragma unroll
             for (int q = 0; q < K1; ++q) A_(row, q + 1) = RS_(sl, q);
-            Z_(row) = ZS_(sl);
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (d < nd) ZD_(d, row) = ZS_(sl, d);
             sl = (sl + 1 == K1) ? 0 : sl + 1;
         }
     }
@@ -346,11 +412,12 @@ __device__ __forceinline__ void list_append(int *list, int *count, bool cond, in
 // Between passes a curve lives in global memory only: n, t (in the caller's output arrays),
 // nrdata(1:nrint) and the scalars fpold, fp0, nplus, iter.
 // ---------------------------------------------------------------------------------------
-template <int K, bool HAS_W>
+template <int K, bool HAS_W, int IDIM>
 __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
                          double *__restrict__ wsd, int *__restrict__ wsi, double *rs)
 {
     constexpr int K1 = K + 1, K2 = K + 2;
+    const int nd = IDIM > 0 ? IDIM : p.idim;
     const int m = p.m, nest = p.nest, iopt = p.iopt;
     const int nmax = m + K1, nmin = 2 * K1;
     const int bb = valid ? b : 0;
@@ -380,10 +447,21 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
         bool bad = false;
         double prev = xp[0];
         if (xb > prev) bad = true;
-        for (int it = 1; it < m; ++it) {  // any(x(1:m-1) > x(2:m))
-            const double cur = xp[(size_t)it * p.x_si];
-            if (prev > cur) bad = true;
-            prev = cur;
+        if (!p.par) {
+            for (int it = 1; it < m; ++it) {  // any(x(1:m-1) > x(2:m))
+                const double cur = xp[(size_t)it * p.x_si];
+                if (prev > cur) bad = true;
+                prev = cur;
+            }
+        } else {
+            // parcur (core:15255-15256): strictly increasing parameters, positive weights
+            if (HAS_W && wp[0] <= 0.0) bad = true;
+            for (int it = 1; it < m; ++it) {
+                const double cur = xp[(size_t)it * p.x_si];
+                if (prev >= cur) bad = true;
+                if (HAS_W && wp[(size_t)it * p.w_si] <= 0.0) bad = true;
+                prev = cur;
+            }
         }
         if (xe < prev) bad = true;
         if (state == ST_LOOP) {
@@ -495,8 +573,9 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             for (int i = nk1 + 1; i <= n; ++i) T_(i) = xe;
             ran_pass = true;
         }
-        const double fp_pass = lsq_pass<K, HAS_W>(p, wsd, rs, xp, yp, wp, (size_t)p.x_si, (size_t)p.y_si,
-                                                  (size_t)p.w_si, m, nk1, on);
+        const double fp_pass = lsq_pass<K, HAS_W, IDIM>(p, wsd, rs, xp, yp, wp, (size_t)p.x_si,
+                                                        (size_t)p.y_si, (size_t)p.y_sd, (size_t)p.w_si,
+                                                        m, nk1, on);
         if (on) {
             fp = fp_pass;
             if (ier == IER_LSQ) fp0 = fp;
@@ -504,7 +583,8 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             FPI_(n) = fp0;
             NRD_(n) = nplus;
         }
-        back_subst<K1>(p, wsd, p.off_a, p.off_z, nk1, on);
+        for (int d = 0; d < nd; ++d)
+            back_subst<K1>(p, wsd, p.off_a, p.off_z + d * p.nestp, p.off_c + d * p.nestp, nk1, on);
         if (on) {
             if (iopt < 0) {
                 state = ST_DONE;
@@ -530,8 +610,9 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             fpold = fp;
         }
         if (__any_sync(FULL, on))
-            (void)residual_pass<K, true, HAS_W>(p, wsd, xp, yp, wp, (size_t)p.x_si, (size_t)p.y_si,
-                                                (size_t)p.w_si, m, nk1, nrint, on);
+            (void)residual_pass<K, true, HAS_W, IDIM>(p, wsd, xp, yp, wp, (size_t)p.x_si,
+                                                      (size_t)p.y_si, (size_t)p.y_sd, (size_t)p.w_si, m,
+                                                      nk1, nrint, on);
         // add_new_knots, core:4968-4996 with fpknot core:8199-8275 inlined
         {
             const int maxplus = __reduce_max_sync(FULL, on ? nplus : 0);
@@ -633,8 +714,11 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             for (int i = 1; i <= n; ++i) p.t[(size_t)b * nest + (i - 1)] = T_(i);
             if (state == ST_DONE) {
                 if (!(ier == IER_STORAGE && iopt >= 0 && s <= 0.0)) p.fp[b] = fp;
+                // coordinate d's coefficients start at c(d*n) (fppara core:8981-8985)
                 const int nk = n - K1;
-                for (int i = 1; i <= nk; ++i) p.c[(size_t)b * nest + (i - 1)] = C_(i);
+                for (int d = 0; d < nd; ++d)
+                    for (int i = 1; i <= nk; ++i)
+                        p.c[(size_t)b * p.c_sb + (size_t)d * n + (i - 1)] = CD_(d, i);
             }
             if (state != ST_LOOP) {
                 // knots are final: the continuation state the caller may keep (iopt=1 next time)
@@ -664,11 +748,12 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
 // values q of the accepted knot set are regenerated by one LSQ pass (bit-identical to the
 // last pass of part 1), which keeps no per-curve matrix state alive between kernels.
 // ---------------------------------------------------------------------------------------
-template <int K, bool HAS_W>
+template <int K, bool HAS_W, int IDIM>
 __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__restrict__ wsd,
                            int *__restrict__ wsi, double *rs)
 {
-    constexpr int K1 = K + 1, K2 = K + 2;
+    constexpr int K1 = K + 1, K2 = K + 2, ND = IDIM > 0 ? IDIM : kMaxIdim;
+    const int nd = IDIM > 0 ? IDIM : p.idim;
     (void)wsi;
     const int m = p.m, nest = p.nest;
     const int nmin = 2 * K1;
@@ -696,19 +781,23 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
     {
         constexpr int U = 4;
         for (int it0 = 0; it0 < m; it0 += U) {
-            double xv[U], yv[U], wv[U];
+            double xv[U], yv[U][ND], wv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int it = min(it0 + u, m - 1);
                 xv[u] = xp[(size_t)it * p.x_si];
-                yv[u] = yp[(size_t)it * p.y_si];
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    if (d < nd) yv[u][d] = yp[(size_t)it * p.y_si + (size_t)d * p.y_sd];
                 wv[u] = HAS_W ? wp[(size_t)it * p.w_si] : 1.0;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (it0 + u < m) {
                     WS(p.off_x, it0 + u) = xv[u];
-                    WS(p.off_y, it0 + u) = yv[u];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d)
+                        if (d < nd) WS(p.off_y + d * m, it0 + u) = yv[u][d];
                     if (HAS_W) WS(p.off_w, it0 + u) = wv[u];
                 }
             }
@@ -716,7 +805,8 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
     }
     const double *xg = &WS(p.off_x, 0), *yg = &WS(p.off_y, 0);
     const double *wg = HAS_W ? &WS(p.off_w, 0) : nullptr;
-    double fp = lsq_pass<K, HAS_W>(p, wsd, rs, xg, yg, wg, 32, 32, 32, m, nk1, on2);
+    const size_t yg_sd = (size_t)m * 32;
+    double fp = lsq_pass<K, HAS_W, IDIM>(p, wsd, rs, xg, yg, wg, 32, 32, yg_sd, 32, m, nk1, on2);
     double fpms = sub(fp, s);
     // fpdisc, core:5453-5495
     {
@@ -750,7 +840,8 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
         const int hi = __reduce_max_sync(FULL, on2 ? nk1 : 0);
         for (int i = 1; i <= hi; ++i)
             if (on2 && i <= nk1) pp = add(pp, A_(i, 1));
-        if (on2) pp = (double)nk1 / pp;
+        // fpcurf: p = nk1/sum(a(:,1)) (core:5031-5033); fppara: p = sum(a(:,1))/nk1 (core:9119)
+        if (on2) pp = p.par ? pp / (double)nk1 : (double)nk1 / pp;
     }
     int it2 = 0;
     while (__any_sync(FULL, state == ST_PART2)) {
@@ -770,7 +861,9 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
         const int hi8 = __reduce_max_sync(FULL, on ? n8 : 0);
         for (int i = 1; i <= hi; ++i) {
             if (on && i <= nk1) {
-                C_(i) = Z_(i);
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    if (d < nd) CD_(d, i) = ZD_(d, i);
 #pragma unroll
                 for (int q = 1; q <= K1; ++q) G_(i, q) = A_(i, q);
                 G_(i, K2) = 0.0;
@@ -781,35 +874,47 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
             double h[K2];
 #pragma unroll
             for (int q = 0; q < K2; ++q) h[q] = row_on ? mul(B_(it, q + 1), pinv) : 0.0;
-            double yi = 0.0;
-            // fp_rotate_shifted, core:5800-5820.  Row j+1 of G (and c(j+1)) is requested before
-            // the div/sqrt chain of row j starts: the sweep is otherwise bound by L2 latency.
-            double gn[K2], cn = 0.0;
+            double yi[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) yi[d] = 0.0;
+            // fp_rotate_shifted / _vec, core:5800-5820 / 5845-5862.  Row j+1 of G (and c(j+1)) is
+            // requested before the div/sqrt chain of row j starts: the sweep is otherwise bound by
+            // L2 latency.  The vector variant has no zero-pivot skip.
+            double gn[K2], cn[ND];
             {
                 const bool pre = row_on && it <= nk1;
 #pragma unroll
                 for (int q = 0; q < K2; ++q) gn[q] = pre ? G_(it, q + 1) : 0.0;
-                cn = pre ? C_(it) : 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) cn[d] = (pre && d < nd) ? CD_(d, it) : 0.0;
             }
             for (int j = it; j <= hi; ++j) {
-                double gc[K2], cj = cn;
+                double gc[K2], cj[ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) cj[d] = cn[d];
 #pragma unroll
                 for (int q = 0; q < K2; ++q) gc[q] = gn[q];
                 {
                     const bool pre = row_on && (j + 1) <= nk1;
 #pragma unroll
                     for (int q = 0; q < K2; ++q) gn[q] = pre ? G_(j + 1, q + 1) : 0.0;
-                    cn = pre ? C_(j + 1) : 0.0;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) cn[d] = (pre && d < nd) ? CD_(d, j + 1) : 0.0;
                 }
                 if (row_on && j <= nk1) {
                     const double piv = h[0];
                     const int noff = min(nk1 - j, K1);
-                    if (!fp_is_zero(piv)) {
+                    if (p.par || !fp_is_zero(piv)) {
                         double cs, sn;
                         givens(piv, gc[0], cs, sn);
                         G_(j, 1) = gc[0];
-                        rota(cs, sn, yi, cj);
-                        C_(j) = cj;
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) {
+                            if (d < nd) {
+                                rota(cs, sn, yi[d], cj[d]);
+                                CD_(d, j) = cj[d];
+                            }
+                        }
 #pragma unroll
                         for (int q = 1; q <= K1; ++q) {
                             if (q <= noff) {
@@ -824,8 +929,10 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
                 }
             }
         }
-        back_subst<K2>(p, wsd, p.off_g, p.off_c, nk1, on);
-        const double fpn = residual_pass<K, false, HAS_W>(p, wsd, xg, yg, wg, 32, 32, 32, m, nk1, 0, on);
+        for (int d = 0; d < nd; ++d)
+            back_subst<K2>(p, wsd, p.off_g, p.off_c + d * p.nestp, p.off_c + d * p.nestp, nk1, on);
+        const double fpn = residual_pass<K, false, HAS_W, IDIM>(p, wsd, xg, yg, wg, 32, 32, yg_sd, 32, m,
+                                                                nk1, 0, on);
         if (on) {
             fp = fpn;
             fpms = sub(fp, s);
@@ -889,14 +996,16 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
     if (valid) {
         p.ier[b] = ier;
         p.fp[b] = fp;
-        for (int i = 1; i <= nk1; ++i) p.c[(size_t)b * nest + (i - 1)] = C_(i);
+        for (int d = 0; d < nd; ++d)
+            for (int i = 1; i <= nk1; ++i)
+                p.c[(size_t)b * p.c_sb + (size_t)d * n + (i - 1)] = CD_(d, i);
         if (p.stats) p.stats[2 * (size_t)b + 1] = p_iters;
     }
 }
 
 // persistent warps; tiles of 32 list entries are handed out through an atomic counter
-template <int K, bool HAS_W>
-__global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K))
+template <int K, bool HAS_W, int IDIM>
+__global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K, IDIM))
     curfit_pass_kernel(FitParams p, const int *__restrict__ in_list, const int *in_count,
                        int *out_list, int *out_count, int *p2_list, int *p2_count, int first)
 {
@@ -916,7 +1025,7 @@ __global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K))
         const bool valid = base + lane < count;
         int b = 0;
         if (valid) b = first ? (int)(base + lane) : in_list[base + lane];
-        const int st = pass_tile<K, HAS_W>(p, b, valid, first != 0, wsd, wsi, rs);
+        const int st = pass_tile<K, HAS_W, IDIM>(p, b, valid, first != 0, wsd, wsi, rs);
         __syncwarp();
         list_append(out_list, out_count, valid && st == ST_LOOP, b, lane);
         const bool to2 = valid && st == ST_PART2;
@@ -925,8 +1034,8 @@ __global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K))
     }
 }
 
-template <int K, bool HAS_W>
-__global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K))
+template <int K, bool HAS_W, int IDIM>
+__global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K, IDIM))
     curfit_part2_kernel(FitParams p, const int *__restrict__ list, const int *count_ptr)
 {
     extern __shared__ double fit_smem[];
@@ -944,11 +1053,42 @@ __global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K))
         if (base >= count) break;
         const bool valid = base + lane < count;
         const int b = valid ? list[base + lane] : 0;
-        part2_tile<K, HAS_W>(p, b, valid, wsd, wsi, rs);
+        part2_tile<K, HAS_W, IDIM>(p, b, valid, wsd, wsi, rs);
         __syncwarp();
     }
 }
 
+template <int K, bool HAS_W>
+cudaError_t launch_pass_kw(const FitParams &p, int grid, cudaStream_t st, const int *in_list,
+                           const int *in_count, int *out_list, int *out_count, int *p2_list,
+                           int *p2_count, int first)
+{
+    constexpr int D = FPB_FIT_IDIM;
+    const unsigned smem = fit_smem_bytes(p.k, p.idim);
+    auto kern = curfit_pass_kernel<K, HAS_W, D>;
+    if (smem > 48u * 1024u) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, kFitThreads, smem, st>>>(p, in_list, in_count, out_list, out_count, p2_list, p2_count, first);
+    return cudaGetLastError();
+}
+
+template <int K, bool HAS_W>
+cudaError_t launch_part2_kw(const FitParams &p, int grid, cudaStream_t st, const int *list, const int *count)
+{
+    constexpr int D = FPB_FIT_IDIM;
+    const unsigned smem = fit_smem_bytes(p.k, p.idim);
+    auto kern = curfit_part2_kernel<K, HAS_W, D>;
+    if (smem > 48u * 1024u) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, kFitThreads, smem, st>>>(p, list, count);
+    return cudaGetLastError();
+}
+
+#if FPB_FIT_IDIM == 1
 // counting sort of the part-2 list by knot count, largest first: curves of one warp then
 // do the same amount of work per p-iteration, and the longest curves start first.
 __global__ void p2_offsets_kernel(int *hist, int nbins)
@@ -973,29 +1113,87 @@ __global__ void p2_scatter_kernel(const int *list, const int *count_ptr, const i
     }
 }
 
-template <int K>
-void launch_pass_k(const FitParams &p, int grid, cudaStream_t st, const int *in_list,
-                   const int *in_count, int *out_list, int *out_count, int *p2_list, int *p2_count,
-                   int first)
+// chord-length parameters of parcur (ipar=0, core:15238-15253): u(1)=0, u(i)=u(i-1)+norm2(dx),
+// normalised to [0,1] with u(m)=1 exactly.  NORM2 is evaluated as gfortran does (scaled form).
+// A curve of zero total length keeps its un-normalised u (all zero) and is rejected with ier=10
+// by the strict-monotonicity check of the first pass, as in the reference.
+__global__ void parcur_param_kernel(int nbatch, int m, int idim, const double *x, long long x_sb,
+                                    long long x_si, long long x_sd, double *u, long long u_sb,
+                                    long long u_si)
 {
-    if (p.w)
-        curfit_pass_kernel<K, true><<<grid, kFitThreads, fit_smem_bytes(K), st>>>(p, in_list, in_count, out_list,
-                                                                   out_count, p2_list, p2_count, first);
-    else
-        curfit_pass_kernel<K, false><<<grid, kFitThreads, fit_smem_bytes(K), st>>>(p, in_list, in_count, out_list,
-                                                                    out_count, p2_list, p2_count, first);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbatch) return;
+    const double *xp = x + (size_t)b * x_sb;
+    double *up = u + (size_t)b * u_sb;
+    double prev[kMaxIdim], acc = 0.0;
+    for (int d = 0; d < idim; ++d) prev[d] = xp[(size_t)d * x_sd];
+    up[0] = 0.0;
+    for (int i = 1; i < m; ++i) {
+        double result = 0.0, scale = 1.0;
+        for (int d = 0; d < idim; ++d) {
+            const double cur = xp[(size_t)i * x_si + (size_t)d * x_sd];
+            const double df = sub(cur, prev[d]);
+            prev[d] = cur;
+            if (df != 0.0) {
+                const double a = fabs(df);
+                if (scale < a) {
+                    const double val = scale / a;
+                    result = add(1.0, mul(mul(result, val), val));
+                    scale = a;
+                } else {
+                    const double val = a / scale;
+                    result = add(result, mul(val, val));
+                }
+            }
+        }
+        acc = add(acc, mul(scale, sqrt(result)));
+        up[(size_t)i * u_si] = acc;
+    }
+    if (acc <= 0.0) return;
+    for (int i = 1; i < m; ++i) up[(size_t)i * u_si] = up[(size_t)i * u_si] / acc;
+    up[(size_t)(m - 1) * u_si] = 1.0;
 }
-
-template <int K>
-void launch_part2_k(const FitParams &p, int grid, cudaStream_t st, const int *list, const int *count)
-{
-    if (p.w) curfit_part2_kernel<K, true><<<grid, kFitThreads, fit_smem_bytes(K), st>>>(p, list, count);
-    else curfit_part2_kernel<K, false><<<grid, kFitThreads, fit_smem_bytes(K), st>>>(p, list, count);
-}
+#endif
 
 }  // namespace
 
-FitLayout fit_layout(int m, int k, int nest)
+// per-IDIM entry points (one translation unit each)
+#define FPB_CAT2(a, b) a##b
+#define FPB_CAT(a, b) FPB_CAT2(a, b)
+cudaError_t FPB_CAT(launch_curfit_pass_d, FPB_FIT_IDIM)(const FitParams &p, int grid, cudaStream_t st,
+                                                       const int *in_list, const int *in_count,
+                                                       int *out_list, int *out_count, int *p2_list,
+                                                       int *p2_count, int first)
+{
+#define FPB_CASE(KK)                                                                                       \
+    case KK:                                                                                               \
+        return p.w ? launch_pass_kw<KK, true>(p, grid, st, in_list, in_count, out_list, out_count, p2_list, \
+                                              p2_count, first)                                             \
+                   : launch_pass_kw<KK, false>(p, grid, st, in_list, in_count, out_list, out_count,        \
+                                               p2_list, p2_count, first);
+    switch (p.k) {
+        FPB_CASE(1) FPB_CASE(2) FPB_CASE(3) FPB_CASE(4) FPB_CASE(5)
+    default: return cudaErrorInvalidValue;
+    }
+#undef FPB_CASE
+}
+
+cudaError_t FPB_CAT(launch_curfit_part2_d, FPB_FIT_IDIM)(const FitParams &p, int grid, cudaStream_t st,
+                                                        const int *list, const int *count)
+{
+#define FPB_CASE(KK)                                                              \
+    case KK:                                                                      \
+        return p.w ? launch_part2_kw<KK, true>(p, grid, st, list, count)          \
+                   : launch_part2_kw<KK, false>(p, grid, st, list, count);
+    switch (p.k) {
+        FPB_CASE(1) FPB_CASE(2) FPB_CASE(3) FPB_CASE(4) FPB_CASE(5)
+    default: return cudaErrorInvalidValue;
+    }
+#undef FPB_CASE
+}
+
+#if FPB_FIT_IDIM == 1
+FitLayout fit_layout(int m, int k, int nest, int idim)
 {
     const int k1 = k + 1, k2 = k + 2;
     FitLayout L;
@@ -1004,52 +1202,46 @@ FitLayout fit_layout(int m, int k, int nest)
     L.nestp = nestp;
     int off = 0;
     L.off_t = off; off += nestp;
-    L.off_c = off; off += nestp;
-    L.off_z = off; off += nestp;
+    L.off_c = off; off += nestp * idim;
+    L.off_z = off; off += nestp * idim;
     L.off_fpint = off; off += nestp;
     L.off_a = off; off += nestp * k1;
     L.off_g = off; off += nestp * k2;
     L.off_b = off; off += nestp * k2;
     L.off_q = off; off += m * k1;
     L.off_x = off; off += m;   // part 2: the curve's own data, gathered once
-    L.off_y = off; off += m;
+    L.off_y = off; off += m * idim;
     L.off_w = off; off += m;
     L.ws_per_lane = off;
     return L;
 }
 
-int fit_max_resident_warps(int k, int nsm)
+int fit_max_resident_warps(int k, int idim, int nsm)
 {
-    return nsm * fit_blocks_per_sm(k) * (kFitThreads / 32);
+    return nsm * fit_blocks_per_sm(k, idim_class(idim)) * (kFitThreads / 32);
 }
 
 cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t stream,
                                const int *in_list, const int *in_count, int *out_list,
                                int *out_count, int *p2_list, int *p2_count, int first)
 {
-    switch (p.k) {
-    case 1: launch_pass_k<1>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
-    case 2: launch_pass_k<2>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
-    case 3: launch_pass_k<3>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
-    case 4: launch_pass_k<4>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
-    case 5: launch_pass_k<5>(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first); break;
-    default: return cudaErrorInvalidValue;
+    switch (idim_class(p.idim)) {
+    case 1: return launch_curfit_pass_d1(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first);
+    case 2: return launch_curfit_pass_d2(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first);
+    case 3: return launch_curfit_pass_d3(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first);
+    default: return launch_curfit_pass_d0(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first);
     }
-    return cudaGetLastError();
 }
 
 cudaError_t launch_curfit_part2(const FitParams &p, int grid_blocks, cudaStream_t stream,
                                 const int *list, const int *count)
 {
-    switch (p.k) {
-    case 1: launch_part2_k<1>(p, grid_blocks, stream, list, count); break;
-    case 2: launch_part2_k<2>(p, grid_blocks, stream, list, count); break;
-    case 3: launch_part2_k<3>(p, grid_blocks, stream, list, count); break;
-    case 4: launch_part2_k<4>(p, grid_blocks, stream, list, count); break;
-    case 5: launch_part2_k<5>(p, grid_blocks, stream, list, count); break;
-    default: return cudaErrorInvalidValue;
+    switch (idim_class(p.idim)) {
+    case 1: return launch_curfit_part2_d1(p, grid_blocks, stream, list, count);
+    case 2: return launch_curfit_part2_d2(p, grid_blocks, stream, list, count);
+    case 3: return launch_curfit_part2_d3(p, grid_blocks, stream, list, count);
+    default: return launch_curfit_part2_d0(p, grid_blocks, stream, list, count);
     }
-    return cudaGetLastError();
 }
 
 cudaError_t launch_p2_sort(const int *list, const int *count, const int *n_arr, int *hist,
@@ -1059,5 +1251,15 @@ cudaError_t launch_p2_sort(const int *list, const int *count, const int *n_arr, 
     p2_scatter_kernel<<<nsm * 4, 256, 0, stream>>>(list, count, n_arr, hist, nbins, sorted);
     return cudaGetLastError();
 }
+
+cudaError_t launch_parcur_param(int nbatch, int m, int idim, const double *x, long long x_sb,
+                                long long x_si, long long x_sd, double *u, long long u_sb,
+                                long long u_si, cudaStream_t stream)
+{
+    parcur_param_kernel<<<(nbatch + 127) / 128, 128, 0, stream>>>(nbatch, m, idim, x, x_sb, x_si, x_sd, u,
+                                                                 u_sb, u_si);
+    return cudaGetLastError();
+}
+#endif
 
 }  // namespace fpb

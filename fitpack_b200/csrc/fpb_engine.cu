@@ -255,39 +255,18 @@ void fitpack_message_c(FP_FLAG ierr, char *msg)
 
 // ------------------------------------------------------------------ device API
 
-int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m,
-                              const FP_REAL *x, int64_t x_sb, int64_t x_si, const FP_REAL *y,
-                              int64_t y_sb, int64_t y_si, const FP_REAL *w, int64_t w_sb,
-                              int64_t w_si, const FP_REAL *xb, const FP_REAL *xe, FP_SIZE xbe_stride,
-                              FP_SIZE k, const FP_REAL *s, FP_SIZE s_stride, FP_SIZE nest,
-                              FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
-                              FP_REAL *fpint, FP_SIZE *nrdata, FP_SIZE *stats)
+} // extern "C"
+
+namespace fpb {
+// The pass pipeline shared by curfit (idim = 1) and parcur: `p` arrives with the caller's arrays,
+// strides and scalars set; this fills in the engine-owned workspace / state and runs the passes.
+int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
 {
-    if (!eng) {
-        set_last_error("null engine");
-        return FPB_ERR_ARG;
-    }
-    if (nbatch <= 0) return FPB_STATUS_OK;
-    if (!x || !y || !s || !n || !t || !c || !fp || !ier || (xb && !xe) || (!xb && xe)) {
-        set_last_error("fp_curfit_batch_dev_c: null required pointer");
-        return FPB_ERR_ARG;
-    }
-    if (iopt == 1 && (!fpint || !nrdata)) {
-        set_last_error("fp_curfit_batch_dev_c: iopt=1 needs the fpint/nrdata state arrays");
-        return FPB_ERR_ARG;
-    }
-    DeviceGuard g(eng->device);
-    if (!g.ok) return FPB_ERR_CUDA;
-    // call-level part of the curfit data check (core:1265-1268): every curve gets ier=10
-    if (k <= 0 || k > 5 || iopt < -1 || iopt > 1 || m < k + 1 || nest < 2 * (k + 1)) {
-        if (!cuda_ok(launch_fill_i32(ier, FPB_INPUT_ERROR, nbatch, eng->stream), "fill ier"))
-            return FPB_ERR_CUDA;
-        eng->launches++;
-        return FPB_STATUS_OK;
-    }
-    const FitLayout L = fit_layout(m, k, nest);
+    const int nbatch = p.nbatch, iopt = p.iopt, m = p.m, k = p.k, nest = p.nest;
+    int *n = p.n;
+    const FitLayout L = fit_layout(m, k, nest, p.idim);
     long long blocks_needed = ((long long)nbatch + kFitThreads - 1) / kFitThreads;
-    const int max_warps = fit_max_resident_warps(k, eng->nsm);
+    const int max_warps = fit_max_resident_warps(k, p.idim, eng->nsm);
     long long grid = std::min<long long>(blocks_needed, max_warps / (kFitThreads / 32));
     const size_t warps = (size_t)grid * (kFitThreads / 32);
     const size_t nb = (size_t)nbatch;
@@ -308,14 +287,7 @@ int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_
     cudaStream_t st = eng->stream;
     if (!cuda_ok(cudaMemsetAsync(cnt, 0, (hist_off + (size_t)L.nestp + 8) * sizeof(int), st), "memset"))
         return FPB_ERR_CUDA;
-    FitParams p;
-    p.nbatch = nbatch; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest; p.nestp = L.nestp;
-    p.x = x; p.y = y; p.w = w;
-    p.x_sb = x_sb; p.x_si = x_si; p.y_sb = y_sb; p.y_si = y_si; p.w_sb = w_sb; p.w_si = w_si;
-    p.xb = xb; p.xe = xe; p.xbe_stride = xbe_stride;
-    p.s = s; p.s_stride = s_stride;
-    p.n = n; p.t = t; p.c = c; p.fp = fp; p.ier = ier;
-    p.fpint = fpint; p.nrdata = nrdata; p.stats = stats;
+    p.nestp = L.nestp;
     p.ws = eng->ws.as<double>(); p.wsi = eng->wsi.as<int>();
     p.counter = reinterpret_cast<unsigned *>(cnt);
     p.off_t = L.off_t; p.off_c = L.off_c; p.off_z = L.off_z; p.off_fpint = L.off_fpint;
@@ -382,6 +354,53 @@ int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_
     }
     end_timing(eng);
     return FPB_STATUS_OK;
+}
+
+}  // namespace fpb
+
+extern "C" {
+
+
+int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m,
+                              const FP_REAL *x, int64_t x_sb, int64_t x_si, const FP_REAL *y,
+                              int64_t y_sb, int64_t y_si, const FP_REAL *w, int64_t w_sb,
+                              int64_t w_si, const FP_REAL *xb, const FP_REAL *xe, FP_SIZE xbe_stride,
+                              FP_SIZE k, const FP_REAL *s, FP_SIZE s_stride, FP_SIZE nest,
+                              FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier,
+                              FP_REAL *fpint, FP_SIZE *nrdata, FP_SIZE *stats)
+{
+    if (!eng) {
+        set_last_error("null engine");
+        return FPB_ERR_ARG;
+    }
+    if (nbatch <= 0) return FPB_STATUS_OK;
+    if (!x || !y || !s || !n || !t || !c || !fp || !ier || (xb && !xe) || (!xb && xe)) {
+        set_last_error("fp_curfit_batch_dev_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    if (iopt == 1 && (!fpint || !nrdata)) {
+        set_last_error("fp_curfit_batch_dev_c: iopt=1 needs the fpint/nrdata state arrays");
+        return FPB_ERR_ARG;
+    }
+    DeviceGuard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    // call-level part of the curfit data check (core:1265-1268): every curve gets ier=10
+    if (k <= 0 || k > 5 || iopt < -1 || iopt > 1 || m < k + 1 || nest < 2 * (k + 1)) {
+        if (!cuda_ok(launch_fill_i32(ier, FPB_INPUT_ERROR, nbatch, eng->stream), "fill ier"))
+            return FPB_ERR_CUDA;
+        eng->launches++;
+        return FPB_STATUS_OK;
+    }
+    FitParams p;
+    p.nbatch = nbatch; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest; p.nestp = 0;
+    p.x = x; p.y = y; p.w = w;
+    p.x_sb = x_sb; p.x_si = x_si; p.y_sb = y_sb; p.y_si = y_si; p.w_sb = w_sb; p.w_si = w_si;
+    p.xb = xb; p.xe = xe; p.xbe_stride = xbe_stride;
+    p.s = s; p.s_stride = s_stride;
+    p.n = n; p.t = t; p.c = c; p.fp = fp; p.ier = ier;
+    p.fpint = fpint; p.nrdata = nrdata; p.stats = stats;
+    p.idim = 1; p.par = 0; p.y_sd = 0; p.c_sb = nest;
+    return run_fit_pipeline(eng, p);
 }
 
 int32_t fp_curfit_shared_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE m, const FP_REAL *x,

@@ -53,4 +53,6 @@ struct fpb_engine {
 namespace fpb {
 // default engine of a device (created on first use, lives until process exit)
 fpb_engine *default_engine(int device);
+// the curfit / parcur pass pipeline (fpb_engine.cu): `p` carries the caller's arrays and scalars
+int32_t run_fit_pipeline(fpb_engine *eng, FitParams p);
 }

@@ -11,9 +11,20 @@ constexpr int kFitThreads = 128;  // threads per CTA of the fit kernel (4 warps 
 #ifndef FPB_FIT_BLOCKS_K3
 #define FPB_FIT_BLOCKS_K3 5
 #endif
-constexpr int fit_blocks_per_sm(int k) { return k <= 3 ? FPB_FIT_BLOCKS_K3 : (k == 4 ? 4 : 3); }
-// shared-memory band window: (k+1)^2 + (k+1) doubles per thread
-constexpr unsigned fit_smem_bytes(int k) { return (unsigned)(((k + 1) * (k + 1) + (k + 1)) * kFitThreads * sizeof(double)); }
+constexpr int kMaxIdim = 10;      // MAX_IDIM of the reference (core:115)
+// the fit kernels are compiled for idim = 1, 2, 3 and a run-time variant (class 0) for 4..10
+constexpr int idim_class(int idim) { return idim <= 3 ? idim : 0; }
+constexpr int fit_blocks_per_sm(int k, int idim_cls = 1)
+{
+    return idim_cls == 1 ? (k <= 3 ? FPB_FIT_BLOCKS_K3 : (k == 4 ? 4 : 3))
+         : idim_cls == 0 ? 2
+                         : (k <= 3 ? 4 : 3);
+}
+// shared-memory band window: (k+1)^2 + (k+1)*idim doubles per thread
+constexpr unsigned fit_smem_bytes(int k, int idim = 1)
+{
+    return (unsigned)(((k + 1) * (k + 1) + (k + 1) * idim) * kFitThreads * sizeof(double));
+}
 
 // per-lane workspace layout of the fit kernel, in elements of 8 bytes
 struct FitLayout {
@@ -21,13 +32,17 @@ struct FitLayout {
     int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q, off_x, off_y, off_w;
     int ws_per_lane;
 };
-FitLayout fit_layout(int m, int k, int nest);
-int fit_max_resident_warps(int k, int nsm);
+FitLayout fit_layout(int m, int k, int nest, int idim = 1);
+int fit_max_resident_warps(int k, int idim, int nsm);
 
 struct FitParams {
     int nbatch, iopt, m, k, nest, nestp;
-    const double *x, *y, *w;
+    int idim;               // coordinate curves per fit (1 for curfit)
+    int par;                // 1: parcur/fppara semantics (checks, initial p, no zero-pivot skip)
+    const double *x, *y, *w;  // x: abscissae / curve parameters u; y: ordinates / coordinates
     long long x_sb, x_si, y_sb, y_si, w_sb, w_si;
+    long long y_sd;         // stride between the coordinates of one point in y
+    long long c_sb;         // stride between curves in c (nest*idim)
     const double *xb, *xe;
     int xbe_stride;
     const double *s;
@@ -53,6 +68,18 @@ cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t
                                int *out_count, int *p2_list, int *p2_count, int first);
 cudaError_t launch_curfit_part2(const FitParams &p, int grid_blocks, cudaStream_t stream,
                                 const int *list, const int *count);
+#define FPB_DECL_FIT_D(D)                                                                           \
+    cudaError_t launch_curfit_pass_d##D(const FitParams &p, int grid, cudaStream_t st,               \
+                                        const int *in_list, const int *in_count, int *out_list,      \
+                                        int *out_count, int *p2_list, int *p2_count, int first);     \
+    cudaError_t launch_curfit_part2_d##D(const FitParams &p, int grid, cudaStream_t st,              \
+                                         const int *list, const int *count);
+FPB_DECL_FIT_D(0) FPB_DECL_FIT_D(1) FPB_DECL_FIT_D(2) FPB_DECL_FIT_D(3)
+#undef FPB_DECL_FIT_D
+// chord-length parameters of parcur (ipar = 0), one thread per curve
+cudaError_t launch_parcur_param(int nbatch, int m, int idim, const double *x, long long x_sb,
+                                long long x_si, long long x_sd, double *u, long long u_sb,
+                                long long u_si, cudaStream_t stream);
 cudaError_t launch_p2_sort(const int *list, const int *count, const int *n_arr, int *hist,
                            int nbins, int *sorted, int nsm, cudaStream_t stream);
 

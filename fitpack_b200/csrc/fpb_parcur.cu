@@ -1,0 +1,391 @@
+// fpb_parcur.cu -- parametric curves: batched parcur (smoothing fit of idim coordinate curves
+// sharing one knot vector) and curev (evaluation), SURVEY 8f rank 2.
+//
+//   parcur  src/fitpack_core.F90:15201-15285 (argument checks, chord-length parameters)
+//   fppara  src/fitpack_core.F90:8822-9177   (knot loop, vector-RHS LSQ, p-iteration)
+//   curev   src/fitpack_core.F90:1126-1182
+//   C binding: fp_parcur_c / fp_curev_c, src/fitpack_core_c.f90:90-100, 178-184
+//
+// The fit itself is the pass pipeline of fpb_curfit.cu instantiated for IDIM coordinates (one
+// Givens rotation, idim right-hand sides); this file holds the evaluation kernel and the entry
+// points.  curev computes the k+1 basis values of a point ONCE and reuses them for all idim
+// coordinates (the reference does the same); values are bit-identical to the reference's
+// operation order (no FMA).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../../include/fitpack_b200.h"
+#include "fpb_common.cuh"
+#include "fpb_engine.h"
+
+namespace fpb {
+
+namespace {
+
+constexpr unsigned FULLW = 0xffffffffu;
+
+// One warp per curve, lanes over the evaluation points.  Knots and coefficients are a few
+// hundred bytes per curve and are read through L1 (every lane of the warp reads the same
+// curve's tables); x is written in the reference's layout x(idim,m), i.e. idim consecutive
+// doubles per point.
+template <int K>
+__global__ void __launch_bounds__(256)
+    curev_kernel(int nspl, int idim, const double *__restrict__ t, const int *__restrict__ n,
+                 const double *__restrict__ c, int ldt, long long ldc, const double *__restrict__ u,
+                 double *__restrict__ x, int m, int *__restrict__ ier)
+{
+    constexpr int K1 = K + 1;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long j = warp0; j < nspl; j += nwarps) {
+        const int nj = n[j];
+        if (nj < 2 * K1 || nj > ldt) {  // not a spline of degree K
+            if (lane == 0) ier[j] = IER_INPUT;
+            continue;
+        }
+        const double *tj = t + j * ldt, *cj = c + j * ldc, *uj = u + j * (long long)m;
+        double *xj = x + j * (long long)m * idim;
+        // any(u(2:m) < u(1:m-1)) -> ier = 10, nothing evaluated (core:1145)
+        bool bad = false;
+        for (int i = lane + 1; i < m; i += 32) bad = bad || (uj[i] < uj[i - 1]);
+        if (__any_sync(FULLW, bad)) {
+            if (lane == 0) ier[j] = IER_INPUT;
+            continue;
+        }
+        if (lane == 0) ier[j] = IER_OK;
+        const int nk1 = nj - K1;
+        const double tb = tj[K1 - 1], te = tj[nk1];
+        for (int i = lane; i < m; i += 32) {
+            double arg = uj[i];
+            if (arg < tb) arg = tb;  // min(max(u,tb),te)
+            if (arg > te) arg = te;
+            // fp_knot_interval from l=k1 over non-decreasing arguments (core:2432-2473): the
+            // smallest l in [k1, nk1] with arg < t(l+1), nk1 when there is none
+            int lo = K1, hi = nk1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (arg < tj[mid]) hi = mid;  // t(mid+1), 0-based tj[mid]
+                else lo = mid + 1;
+            }
+            const int l = lo;
+            double tw[2 * K], h[K1];
+#pragma unroll
+            for (int q = 0; q < 2 * K; ++q) tw[q] = tj[l - K + q];  // t(l-K+1+q)
+            bspl<K>(tw, arg, h);
+            const double *cl = cj + (l - K1);
+            for (int d = 0; d < idim; ++d) {
+                double sum = 0.0;
+#pragma unroll
+                for (int q = 0; q < K1; ++q) sum = add(sum, mul(h[q], cl[q]));
+                xj[(long long)i * idim + d] = sum;
+                cl += nj;
+            }
+        }
+    }
+}
+
+template <int K>
+void launch_curev_k(int nspl, int idim, const double *t, const int *n, const double *c, int ldt,
+                    long long ldc, const double *u, double *x, int m, int *ier, int nsm, cudaStream_t st)
+{
+    long long blocks = ((long long)nspl + 7) / 8;
+    blocks = std::min<long long>(blocks, (long long)nsm * 8);
+    curev_kernel<K><<<(int)blocks, 256, 0, st>>>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier);
+}
+
+cudaError_t launch_curev(int nspl, int idim, const double *t, const int *n, const double *c, int ldt,
+                         long long ldc, int k, const double *u, double *x, int m, int *ier, int nsm,
+                         cudaStream_t st)
+{
+    switch (k) {
+    case 1: launch_curev_k<1>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
+    case 2: launch_curev_k<2>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
+    case 3: launch_curev_k<3>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
+    case 4: launch_curev_k<4>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
+    case 5: launch_curev_k<5>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+struct Guard {
+    int prev = -1;
+    bool ok = false;
+    explicit Guard(int dev)
+    {
+        ok = cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~Guard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+}  // namespace fpb
+
+using namespace fpb;
+
+extern "C" {
+
+int32_t fp_parcur_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim,
+                              FP_SIZE m, FP_REAL *u, int64_t u_sb, int64_t u_si, const FP_REAL *x,
+                              int64_t x_sb, int64_t x_si, int64_t x_sd, const FP_REAL *w, int64_t w_sb,
+                              int64_t w_si, const FP_REAL *ub, const FP_REAL *ue, FP_SIZE ube_stride,
+                              FP_SIZE k, const FP_REAL *s, FP_SIZE s_stride, FP_SIZE nest, FP_SIZE *n,
+                              FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier, FP_REAL *fpint,
+                              FP_SIZE *nrdata, FP_SIZE *stats)
+{
+    if (!eng) {
+        set_last_error("null engine");
+        return FPB_ERR_ARG;
+    }
+    if (nbatch <= 0) return FPB_STATUS_OK;
+    if (!u || !x || !s || !n || !t || !c || !fp || !ier || (ub && !ue) || (!ub && ue)) {
+        set_last_error("fp_parcur_batch_dev_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    if (iopt == 1 && (!fpint || !nrdata)) {
+        set_last_error("fp_parcur_batch_dev_c: iopt=1 needs the fpint/nrdata state arrays");
+        return FPB_ERR_ARG;
+    }
+    Guard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    // call-level part of parcur's data check (core:15221-15232): every curve gets ier=10
+    if (iopt < -1 || iopt > 1 || ipar < 0 || ipar > 1 || idim <= 0 || idim > kMaxIdim || k <= 0 || k > 5 ||
+        m < k + 1 || nest < 2 * (k + 1)) {
+        if (!cuda_ok(launch_fill_i32(ier, FPB_INPUT_ERROR, nbatch, eng->stream), "fill ier"))
+            return FPB_ERR_CUDA;
+        eng->launches++;
+        return FPB_STATUS_OK;
+    }
+    const bool chord = (ipar == 0 && iopt <= 0);
+    if (chord) {  // u(i) = normalised cumulative chord length, ub = 0, ue = 1 (core:15238-15253)
+        if (!cuda_ok(launch_parcur_param(nbatch, m, idim, x, x_sb, x_si, x_sd, u, u_sb, u_si, eng->stream),
+                     "parcur parameter kernel"))
+            return FPB_ERR_CUDA;
+        eng->launches++;
+    }
+    FitParams p;
+    std::memset(&p, 0, sizeof p);
+    p.nbatch = nbatch; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest;
+    p.idim = idim; p.par = 1;
+    p.x = u; p.x_sb = u_sb; p.x_si = u_si;
+    p.y = x; p.y_sb = x_sb; p.y_si = x_si; p.y_sd = x_sd;
+    p.w = w; p.w_sb = w_sb; p.w_si = w_si;
+    // chord-length parameters run over [0,1] exactly (u(1)=0, u(m)=1): the data range
+    p.xb = chord ? nullptr : ub; p.xe = chord ? nullptr : ue; p.xbe_stride = ube_stride;
+    p.s = s; p.s_stride = s_stride;
+    p.n = n; p.t = t; p.c = c; p.fp = fp; p.ier = ier;
+    p.fpint = fpint; p.nrdata = nrdata; p.stats = stats;
+    p.c_sb = (long long)nest * idim;
+    return run_fit_pipeline(eng, p);
+}
+
+int32_t fp_curev_batch_dev_c(fpb_engine *eng, FP_SIZE nspl, FP_SIZE idim, const FP_REAL *t,
+                             const FP_SIZE *n, const FP_REAL *c, FP_SIZE ldt, int64_t ldc, FP_SIZE k,
+                             const FP_REAL *u, FP_REAL *x, FP_SIZE m, FP_FLAG *ier)
+{
+    if (!eng || !t || !n || !c || !u || !x || !ier) {
+        set_last_error("fp_curev_batch_dev_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    if (nspl <= 0) return FPB_STATUS_OK;
+    Guard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    if (m < 1 || idim < 1 || idim > kMaxIdim || k < 1 || k > 5) {  // core:1142
+        if (!cuda_ok(launch_fill_i32(ier, FPB_INPUT_ERROR, nspl, eng->stream), "fill ier")) return FPB_ERR_CUDA;
+        eng->launches++;
+        return FPB_STATUS_OK;
+    }
+    if (!cuda_ok(launch_curev(nspl, idim, t, n, c, ldt, ldc, k, u, x, m, ier, eng->nsm, eng->stream),
+                 "curev kernel"))
+        return FPB_ERR_CUDA;
+    eng->launches++;
+    return FPB_STATUS_OK;
+}
+
+// Host-pointer batch: x [nbatch][m][idim] (= Fortran x(idim,m,nbatch)), u [nbatch][m] in/out,
+// w [nbatch][m] or NULL (unit weights), ub/ue [nbatch] in/out, t [nbatch][nest] (in for iopt != 0),
+// c [nbatch][nest*idim], fpint/nrdata [nbatch][nest] (the wrk(1:nest)/iwrk state of the
+// reference; may be NULL when iopt = 0 and no continuation is wanted).
+int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u,
+                          const FP_REAL *x, const FP_REAL *w, FP_REAL *ub, FP_REAL *ue, FP_SIZE k,
+                          FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
+                          FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata)
+{
+    if (nbatch <= 0) return FPB_STATUS_OK;
+    if (!u || !x || !ub || !ue || !n || !t || !c || !fp || !ier) {
+        set_last_error("fp_parcur_batch_c: null required pointer");
+        return FPB_ERR_ARG;
+    }
+    if (iopt < -1 || iopt > 1 || ipar < 0 || ipar > 1 || idim <= 0 || idim > kMaxIdim || k <= 0 || k > 5 ||
+        m < k + 1 || nest < 2 * (k + 1)) {
+        for (FP_SIZE b = 0; b < nbatch; ++b) ier[b] = FPB_INPUT_ERROR;
+        return FPB_STATUS_OK;
+    }
+    if (iopt == 1 && (!fpint || !nrdata)) {
+        set_last_error("fp_parcur_batch_c: iopt=1 needs the fpint/nrdata state arrays");
+        return FPB_ERR_ARG;
+    }
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) return FPB_ERR_CUDA;  // no device: there is no CPU path
+    Guard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    cudaStream_t st = eng->stream;
+    const bool chord = (ipar == 0 && iopt <= 0);
+    const size_t per_curve = (size_t)m * (idim + 2) * 16 + (size_t)nest * (idim + 3) * 8 + 64;
+    const long long chunk = std::max<long long>(128, (long long)(((size_t)6 << 30) / per_curve) / 128 * 128);
+    enum { XC, XP, UC, UP, WC, WP, SS, BE, NN, TT, CC, FP_IER };
+    DevBuf *B = eng->scratch;
+    for (long long b0 = 0; b0 < nbatch; b0 += chunk) {
+        const long long nb = std::min<long long>(chunk, nbatch - b0);
+        const long long ld = (nb + 31) / 32 * 32;  // point-major leading dimension
+        const size_t md = (size_t)m * idim;
+        // TT holds t [nb][nest] doubles, fpint [nb][nest] doubles and nrdata [nb][nest] ints
+        if (!B[XC].reserve(nb * md * 8) || !B[XP].reserve(ld * md * 8) || !B[UC].reserve((size_t)nb * m * 8) ||
+            !B[UP].reserve((size_t)ld * m * 8) || !B[WC].reserve((size_t)nb * m * 8) ||
+            !B[WP].reserve((size_t)ld * m * 8) || !B[SS].reserve(64) || !B[BE].reserve((size_t)nb * 16) ||
+            !B[NN].reserve((size_t)nb * 8) || !B[TT].reserve((size_t)nb * nest * 20) ||
+            !B[CC].reserve((size_t)nb * nest * idim * 8) || !B[FP_IER].reserve((size_t)nb * 16))
+            return FPB_ERR_ALLOC;
+        double *d_xc = B[XC].as<double>(), *d_xp = B[XP].as<double>(), *d_uc = B[UC].as<double>(),
+               *d_up = B[UP].as<double>(), *d_wc = B[WC].as<double>(), *d_wp = B[WP].as<double>(),
+               *d_s = B[SS].as<double>(), *d_ub = B[BE].as<double>(), *d_ue = d_ub + nb,
+               *d_t = B[TT].as<double>(), *d_fpint = d_t + (size_t)nb * nest, *d_c = B[CC].as<double>(),
+               *d_fp = B[FP_IER].as<double>();
+        int *d_n = B[NN].as<int>(), *d_ier = reinterpret_cast<int *>(d_fp + nb),
+            *d_nrd = reinterpret_cast<int *>(d_fpint + (size_t)nb * nest);
+        const bool keep = fpint && nrdata;
+        bool ok = cuda_ok(cudaMemcpyAsync(d_xc, x + (size_t)b0 * md, nb * md * 8, cudaMemcpyHostToDevice, st), "H2D x");
+        if (!chord)
+            ok = ok && cuda_ok(cudaMemcpyAsync(d_uc, u + (size_t)b0 * m, (size_t)nb * m * 8, cudaMemcpyHostToDevice, st), "H2D u");
+        if (w) ok = ok && cuda_ok(cudaMemcpyAsync(d_wc, w + (size_t)b0 * m, (size_t)nb * m * 8, cudaMemcpyHostToDevice, st), "H2D w");
+        ok = ok && cuda_ok(cudaMemcpyAsync(d_s, &s, 8, cudaMemcpyHostToDevice, st), "H2D s");
+        if (!chord) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(d_ub, ub + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st), "H2D ub");
+            ok = ok && cuda_ok(cudaMemcpyAsync(d_ue, ue + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st), "H2D ue");
+        }
+        if (iopt != 0) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(d_n, n + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st), "H2D n");
+            ok = ok && cuda_ok(cudaMemcpyAsync(d_t, t + (size_t)b0 * nest, (size_t)nb * nest * 8, cudaMemcpyHostToDevice, st), "H2D t");
+        }
+        if (iopt == 1) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(d_fpint, fpint + (size_t)b0 * nest, (size_t)nb * nest * 8, cudaMemcpyHostToDevice, st), "H2D fpint");
+            ok = ok && cuda_ok(cudaMemcpyAsync(d_nrd, nrdata + (size_t)b0 * nest, (size_t)nb * nest * 4, cudaMemcpyHostToDevice, st), "H2D nrdata");
+        }
+        if (!ok) return FPB_ERR_CUDA;
+        // curve-major -> point-major: element (i,d) of curve b at d_xp[(i*idim+d)*ld + b]
+        ok = cuda_ok(launch_transpose(d_xc, (long long)md, d_xp, ld, nb, (long long)md, st), "transpose x");
+        if (!chord) ok = ok && cuda_ok(launch_transpose(d_uc, m, d_up, ld, nb, m, st), "transpose u");
+        if (w) ok = ok && cuda_ok(launch_transpose(d_wc, m, d_wp, ld, nb, m, st), "transpose w");
+        if (!ok) return FPB_ERR_CUDA;
+        eng->launches += 1 + (chord ? 0 : 1) + (w ? 1 : 0);
+        const int32_t rc = fp_parcur_batch_dev_c(eng, (FP_SIZE)nb, iopt, ipar, idim, m, d_up, 1, ld, d_xp, 1,
+                                                 (int64_t)idim * ld, ld, w ? d_wp : nullptr, 1, ld,
+                                                 chord ? nullptr : d_ub, chord ? nullptr : d_ue, 1, k, d_s, 0,
+                                                 nest, d_n, d_t, d_c, d_fp, d_ier, keep ? d_fpint : nullptr,
+                                                 keep ? d_nrd : nullptr, nullptr);
+        if (rc != FPB_STATUS_OK) return rc;
+        if (chord) {  // the parameters are an output
+            ok = cuda_ok(launch_transpose(d_up, ld, d_uc, m, m, nb, st), "transpose u back");
+            eng->launches++;
+            ok = ok && cuda_ok(cudaMemcpyAsync(u + (size_t)b0 * m, d_uc, (size_t)nb * m * 8, cudaMemcpyDeviceToHost, st), "D2H u");
+            if (!ok) return FPB_ERR_CUDA;
+        }
+        ok = cuda_ok(cudaMemcpyAsync(n + b0, d_n, (size_t)nb * 4, cudaMemcpyDeviceToHost, st), "D2H n");
+        ok = ok && cuda_ok(cudaMemcpyAsync(t + (size_t)b0 * nest, d_t, (size_t)nb * nest * 8, cudaMemcpyDeviceToHost, st), "D2H t");
+        ok = ok && cuda_ok(cudaMemcpyAsync(c + (size_t)b0 * nest * idim, d_c, (size_t)nb * nest * idim * 8, cudaMemcpyDeviceToHost, st), "D2H c");
+        std::vector<double> hfp((size_t)nb);
+        std::vector<int> hier((size_t)nb);
+        ok = ok && cuda_ok(cudaMemcpyAsync(hfp.data(), d_fp, (size_t)nb * 8, cudaMemcpyDeviceToHost, st), "D2H fp");
+        ok = ok && cuda_ok(cudaMemcpyAsync(hier.data(), d_ier, (size_t)nb * 4, cudaMemcpyDeviceToHost, st), "D2H ier");
+        if (keep && iopt >= 0) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(fpint + (size_t)b0 * nest, d_fpint, (size_t)nb * nest * 8, cudaMemcpyDeviceToHost, st), "D2H fpint");
+            ok = ok && cuda_ok(cudaMemcpyAsync(nrdata + (size_t)b0 * nest, d_nrd, (size_t)nb * nest * 4, cudaMemcpyDeviceToHost, st), "D2H nrdata");
+        }
+        ok = ok && cuda_ok(cudaStreamSynchronize(st), "sync");
+        if (!ok) return FPB_ERR_CUDA;
+        for (long long b = 0; b < nb; ++b) {
+            ier[b0 + b] = hier[(size_t)b];
+            // fp is an output only where fppara ran (the reference leaves it untouched on ier=10)
+            if (hier[(size_t)b] != FPB_INPUT_ERROR) fp[b0 + b] = hfp[(size_t)b];
+            if (chord) {
+                ub[b0 + b] = 0.0;
+                ue[b0 + b] = 1.0;
+            }
+        }
+    }
+    return FPB_STATUS_OK;
+}
+
+// ---- the reference's own flat entry points: a batch of one curve ----
+
+void fp_parcur_c(FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u, FP_SIZE mx,
+                 const FP_REAL *x, FP_REAL *w, FP_REAL *ub, FP_REAL *ue, FP_SIZE k, FP_REAL *s,
+                 FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_SIZE nc, FP_REAL *c, FP_REAL *fp, FP_REAL *wrk,
+                 FP_SIZE lwrk, FP_SIZE *iwrk, FP_FLAG *ier)
+{
+    // data check that does not need the data, core:15221-15236
+    *ier = FPB_INPUT_ERROR;
+    if (iopt < -1 || iopt > 1) return;
+    if (ipar < 0 || ipar > 1) return;
+    if (idim <= 0 || idim > kMaxIdim) return;
+    if (k <= 0 || k > 5) return;
+    if (m < k + 1 || nest < 2 * (k + 1)) return;
+    if (mx < m * idim || nc < nest * idim) return;
+    if (lwrk < m * (k + 1) + nest * (6 + idim + 3 * k)) return;
+    // wrk(1:nest) is fpint and iwrk(1:nest) is nrdata (core:15275-15283): the iopt=1 state
+    FP_FLAG ier1 = FPB_INPUT_ERROR;
+    const int32_t rc = fp_parcur_batch_c(1, iopt, ipar, idim, m, u, x, w, ub, ue, k, *s, nest, n, t, c, fp,
+                                         &ier1, wrk, iwrk);
+    *ier = (rc != FPB_STATUS_OK) ? rc : ier1;
+}
+
+void fp_curev_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE nc, FP_SIZE k,
+                const FP_REAL *u, FP_SIZE m, FP_REAL *x, FP_SIZE mx, FP_FLAG *ier)
+{
+    *ier = FPB_INPUT_ERROR;
+    if (m < 1) return;                 // core:1142
+    if (mx < m * idim) return;         // core:1148
+    if (idim < 1 || idim > kMaxIdim || k < 1 || k > 5 || n < 2 * (k + 1) || nc < n * (idim - 1) + n - k - 1) return;
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    Guard g(eng->device);
+    cudaStream_t st = eng->stream;
+    DevBuf *B = eng->scratch;
+    const size_t ncu = (size_t)n * (idim - 1) + (size_t)(n - k - 1);  // coefficients actually read
+    if (!B[0].reserve((size_t)n * 8) || !B[1].reserve(ncu * 8 + 64) || !B[2].reserve(64) ||
+        !B[3].reserve((size_t)m * 8) || !B[4].reserve((size_t)m * idim * 8)) {
+        *ier = FPB_ERR_ALLOC;
+        return;
+    }
+    bool ok = cuda_ok(cudaMemcpyAsync(B[0].ptr, t, (size_t)n * 8, cudaMemcpyHostToDevice, st), "H2D");
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[1].ptr, c, ncu * 8, cudaMemcpyHostToDevice, st), "H2D");
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[2].ptr, &n, 4, cudaMemcpyHostToDevice, st), "H2D");
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[3].ptr, u, (size_t)m * 8, cudaMemcpyHostToDevice, st), "H2D");
+    if (!ok) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    const int32_t rc = fp_curev_batch_dev_c(eng, 1, idim, B[0].as<double>(), B[2].as<int>(), B[1].as<double>(),
+                                            n, (int64_t)ncu, k, B[3].as<double>(), B[4].as<double>(), m,
+                                            B[2].as<int>() + 4);
+    if (rc != FPB_STATUS_OK) {
+        *ier = rc;
+        return;
+    }
+    FP_FLAG h = FPB_INPUT_ERROR;
+    ok = cuda_ok(cudaMemcpyAsync(&h, B[2].as<int>() + 4, 4, cudaMemcpyDeviceToHost, st), "D2H") &&
+         cuda_ok(cudaStreamSynchronize(st), "sync");
+    if (ok && h == FPB_OK)
+        ok = cuda_ok(cudaMemcpy(x, B[4].ptr, (size_t)m * idim * 8, cudaMemcpyDeviceToHost), "D2H x");
+    *ier = ok ? h : FPB_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -286,6 +286,50 @@ int32_t fp_bispev_dev_c(fpb_engine *eng, const FP_REAL *tx, FP_SIZE nx, const FP
 /* number of fpgrre solves (knot sets + smoothing-parameter iterations) of the last regrid call */
 int64_t fpb_engine_grid_fpgrre_calls(const fpb_engine *eng);
 
+/* -------------------------------------------------------- parametric curves -- */
+/*
+ * parcur / curev: smoothing fit of idim coordinate curves x_d(u) that share one
+ * knot vector, and its evaluation.  Same names and argument lists as the reference's C binding:
+ *   fp_parcur_c  include/fitpack_core_c.h:109-112, src/fitpack_core_c.f90:90-100
+ *                -> parcur core:15201-15285, fppara core:8822-9177
+ *   fp_curev_c   include/fitpack_core_c.h:140-141, src/fitpack_core_c.f90:178-184 -> curev core:1126-1182
+ * x is x(idim,m) (coordinate fastest), c holds coordinate d at c[d*n .. d*n + n-k-2], u/ub/ue are
+ * in/out (ipar=0: u = normalised chord length, ub=0, ue=1), wrk(1:nest)/iwrk(1:nest) carry the
+ * iopt=1 continuation state.  idim <= 10, lwrk >= m*(k+1)+nest*(6+idim+3*k), nc >= nest*idim.
+ */
+void fp_parcur_c(FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u, FP_SIZE mx,
+                 const FP_REAL *x, FP_REAL *w, FP_REAL *ub, FP_REAL *ue, FP_SIZE k, FP_REAL *s,
+                 FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_SIZE nc, FP_REAL *c, FP_REAL *fp, FP_REAL *wrk,
+                 FP_SIZE lwrk, FP_SIZE *iwrk, FP_FLAG *ier);
+void fp_curev_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE nc, FP_SIZE k,
+                const FP_REAL *u, FP_SIZE m, FP_REAL *x, FP_SIZE mx, FP_FLAG *ier);
+
+/* NEW: many independent parametric curves.  Host pointers, curve-major: x [nbatch][m][idim],
+   u [nbatch][m] in/out, w [nbatch][m] or NULL (unit weights), ub/ue [nbatch] in/out,
+   t [nbatch][nest], c [nbatch][nest*idim], fpint/nrdata [nbatch][nest] continuation state (NULL
+   allowed unless iopt=1).  Per-curve ier; returns FPB_STATUS_*. */
+int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u,
+                          const FP_REAL *x, const FP_REAL *w, FP_REAL *ub, FP_REAL *ue, FP_SIZE k,
+                          FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
+                          FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata);
+/* Device pointers + strides (elements): u[b*u_sb + i*u_si], x[b*x_sb + i*x_si + d*x_sd],
+   w[b*w_sb + i*w_si] (NULL = unit weights); the fast layout is point-major (u_sb = 1, u_si = ld;
+   x_sb = 1, x_si = idim*ld, x_sd = ld).  ub/ue NULL = the data range [u(1), u(m)] (always used
+   when ipar=0 and iopt<=0, where u is computed on the device).  Outputs as
+   fp_curfit_batch_dev_c, c [nbatch][nest*idim]. */
+int32_t fp_parcur_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim,
+                              FP_SIZE m, FP_REAL *u, int64_t u_sb, int64_t u_si, const FP_REAL *x,
+                              int64_t x_sb, int64_t x_si, int64_t x_sd, const FP_REAL *w, int64_t w_sb,
+                              int64_t w_si, const FP_REAL *ub, const FP_REAL *ue, FP_SIZE ube_stride,
+                              FP_SIZE k, const FP_REAL *s, FP_SIZE s_stride, FP_SIZE nest, FP_SIZE *n,
+                              FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier, FP_REAL *fpint,
+                              FP_SIZE *nrdata, FP_SIZE *stats);
+/* curev for many curves: t [nspl][ldt], c [nspl][ldc] (coordinate d at d*n[j]), u [nspl][m]
+   non-decreasing, x [nspl][m][idim]; per-curve ier (10 = decreasing u or invalid n). */
+int32_t fp_curev_batch_dev_c(fpb_engine *eng, FP_SIZE nspl, FP_SIZE idim, const FP_REAL *t,
+                             const FP_SIZE *n, const FP_REAL *c, FP_SIZE ldt, int64_t ldc, FP_SIZE k,
+                             const FP_REAL *u, FP_REAL *x, FP_SIZE m, FP_FLAG *ier);
+
 #ifdef __cplusplus
 }
 #endif

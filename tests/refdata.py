@@ -57,3 +57,15 @@ DAREGR_Z = np.array([
 # mnregr call sequence: (iopt, kx, ky, s); the last one is iopt=-1 with interior knots -0.5, 0, 0.5
 MNREGR_STEPS = [(0, 3, 3, 10.0), (1, 3, 3, 0.22), (1, 3, 3, 0.1), (1, 3, 3, 0.0), (0, 5, 5, 0.2),
                 (-1, 3, 3, 0.0)]
+
+
+def synth_param_curves(rng, B, m, idim, sigma=0.05):
+    """Noisy Lissajous-like parametric curves, [B][m][idim] (memory order of Fortran x(idim,m))."""
+    th = np.sort(rng.uniform(0, 2 * np.pi, (B, m)), axis=1)
+    th += np.arange(m)[None, :] * 1e-9  # strictly increasing
+    cols = []
+    for d in range(idim):
+        f = rng.uniform(0.5, 3, (B, 1))
+        cols.append(rng.uniform(.5, 2, (B, 1)) * np.cos(f * th + rng.uniform(0, 6, (B, 1))))
+    x = np.stack(cols, 2) + sigma * rng.standard_normal((B, m, idim))
+    return np.ascontiguousarray(th), np.ascontiguousarray(x)

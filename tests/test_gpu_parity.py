@@ -840,3 +840,114 @@ def test_regrid_full_size_properties(F, eng):
     rg = F.regrid(0, xs, xs, zs, xs[0], xs[-1], xs[0], xs[-1], k, k, ss, nest, nest, engine=eng)
     ro = O.regrid(0, xs, xs, zs.cpu().numpy(), xs[0], xs[-1], xs[0], xs[-1], k, k, ss, nest, nest)
     _check_regrid(rg, ro, k, k)
+
+
+# ------------------------------------------------------------------ parametric curves
+def test_parcur_golden_cases_flat_abi_bit_exact(F):
+    """Every parcur golden case (idim 1..10, k 1..5, ipar 0/1, iopt -1/0 and 0->1 continuations,
+    all ier classes) through fp_parcur_c against the oracle in reference mode: n, knots, u, ub/ue,
+    c, fp, ier and the continuation state bit-exact; then fp_curev_c on the result."""
+    from test_oracle_golden import _parcur_cases, run_parcur_case
+    ncase = 0
+    for i, g, cs in _parcur_cases():
+        ro = run_parcur_case(O.parcur, cs, g, i)
+        rg = run_parcur_case(F.parcur, cs, g, i)
+        assert rg["ier"] == ro["ier"], i
+        ncase += 1
+        if ro["ier"] == 10:
+            continue
+        n, k, idim = ro["n"], cs["k"], cs["idim"]
+        assert rg["n"] == n, i
+        assert _same(rg["t"][:n], ro["t"][:n]), i
+        assert _same(rg["u"], ro["u"]) and rg["ub"] == ro["ub"] and rg["ue"] == ro["ue"], i
+        for d in range(idim):
+            assert _same(rg["c"][d * n:d * n + n - k - 1], ro["c"][d * n:d * n + n - k - 1]), (i, d)
+        assert rg["fp"] == ro["fp"], i
+        if cs["iopt"] >= 0 and not (ro["ier"] == 1 and cs["s"] <= 0):
+            # continuation state (core:8910-8914): fpint(n-1:n) in wrk, nrdata(n) and the per-interval
+            # counts nrdata(1:nrint) in iwrk; other slots are stale scratch
+            nrint = n - 2 * (k + 1) + 1
+            assert _same(rg["wrk"][n - 2:n], ro["wrk"][n - 2:n]) and rg["iwrk"][n - 1] == ro["iwrk"][n - 1], i
+            if cs["s"] > 0:
+                assert _same(rg["iwrk"][:nrint], ro["iwrk"][:nrint]), i
+        pts = np.sort(np.random.default_rng(i).uniform(ro["ub"] - 0.1, ro["ue"] + 0.1, 37))
+        xo, io = O.curev(idim, ro["t"], n, ro["c"], k, pts)
+        xg, ig = F.curev(idim, rg["t"], n, rg["c"], k, pts)
+        assert ig == io == 0 and _same(xg, xo), i
+    assert ncase > 140
+
+
+def test_curev_input_errors(F):
+    t = np.array([0., 0, 0, 0, 1, 1, 1, 1])
+    c = np.arange(16.0)
+    _, ier = F.curev(2, t, 8, c, 3, np.array([0.5, 0.4]))
+    assert ier == 10
+    v, ier = F.curev(2, t, 8, c, 3, np.array([-1.0, 2.0]))
+    assert ier == 0 and _same(v, [[0., 8.], [3., 11.]])
+    r = F.parcur(0, 0, 11, np.zeros((10, 11)), None, 3, 1.0, 20)
+    assert r["ier"] == 10
+    r = F.parcur(0, 0, 2, np.zeros((10, 2)), None, 3, 1.0, 20)   # zero total length (core:15248)
+    assert r["ier"] == 10
+    r = F.parcur(0, 1, 2, np.random.default_rng(0).normal(size=(10, 2)), None, 3, 1.0, 20,
+                 u=np.array([0., 1, 2, 2, 4, 5, 6, 7, 8, 9]), ub=0.0, ue=9.0)   # u not strictly increasing
+    assert r["ier"] == 10
+    w = np.ones(10); w[4] = 0.0
+    r = F.parcur(0, 0, 2, np.random.default_rng(0).normal(size=(10, 2)), w, 3, 1.0, 20)  # w <= 0
+    assert r["ier"] == 10
+
+
+@pytest.mark.parametrize("idim,k,weights,ipar", [(2, 3, False, 0), (3, 3, True, 0), (1, 3, False, 1),
+                                                 (5, 2, True, 1), (3, 5, False, 1), (2, 1, True, 0)])
+def test_parcur_batch_bit_exact_vs_oracle(F, eng, idim, k, weights, ipar):
+    """Batches of parametric curves through the pass pipeline instantiated for idim coordinates
+    (host-pointer entry point and device-pointer Engine call) against the oracle, bit-exact; then
+    curev for the whole batch."""
+    import torch
+    from refdata import synth_param_curves
+    rng = np.random.default_rng(100 * idim + k)
+    B, m = 1500, 96
+    th, x = synth_param_curves(rng, B, m, idim)
+    w = rng.uniform(0.5, 2.0, (B, m)) if weights else None
+    nest = m + k + 1
+    s = m * 0.0025 * idim * (1.7 if weights else 1.0)
+    kw = dict(u=th, ub=th[:, 0].copy(), ue=th[:, -1].copy()) if ipar else {}
+    ro = O.parcur_batch(0, ipar, idim, x, w, k, s, nest, **kw)
+    rg = F.parcur_batch(0, ipar, idim, x, w, k, s, nest, **kw)
+    assert _same(rg["ier"], ro["ier"]) and _same(rg["n"], ro["n"])
+    assert set(np.unique(ro["ier"])) <= {0, -1, -2, 1, 2, 3}
+    assert _same(rg["u"], ro["u"]) and _same(rg["fp"], ro["fp"])
+    assert _same(rg["ub"], ro["ub"]) and _same(rg["ue"], ro["ue"])
+    for b in range(B):
+        n = ro["n"][b]
+        assert _same(rg["t"][b, :n], ro["t"][b, :n]), b
+        for d in range(idim):
+            assert _same(rg["c"][b, d * n:d * n + n - k - 1], ro["c"][b, d * n:d * n + n - k - 1]), (b, d)
+    # device-pointer call, point-major tensors
+    dev = torch.device("cuda", 0)
+    xd = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 2, 0))).to(dev)
+    wd = None if w is None else torch.from_numpy(np.ascontiguousarray(w.T)).to(dev)
+    kd = {}
+    if ipar:
+        kd = dict(u=torch.from_numpy(np.ascontiguousarray(th.T)).to(dev),
+                  ub=torch.from_numpy(th[:, 0].copy()).to(dev), ue=torch.from_numpy(th[:, -1].copy()).to(dev))
+    rd = eng.parcur_batch(xd, wd, k=k, s=s, nest=nest, ipar=ipar, want_stats=True, **kd)
+    assert _same(rd["n"].cpu().numpy(), ro["n"]) and _same(rd["fp"].cpu().numpy(), ro["fp"])
+    assert _same(rd["u"].cpu().numpy().T, ro["u"]) and _same(rd["ier"].cpu().numpy(), ro["ier"])
+    cd, td = rd["c"].cpu().numpy(), rd["t"].cpu().numpy()
+    for b in range(B):
+        n = ro["n"][b]
+        assert _same(td[b, :n], ro["t"][b, :n]), b
+        for d in range(idim):
+            assert _same(cd[b, d * n:d * n + n - k - 1], ro["c"][b, d * n:d * n + n - k - 1]), (b, d)
+    # evaluation of the whole batch at the data parameters
+    ud = torch.from_numpy(ro["u"]).to(dev)
+    xe, ie = eng.curev_batch(idim, rd["t"], rd["n"], rd["c"], k, ud)
+    xe = xe.cpu().numpy()
+    assert int(ie.abs().max()) == 0
+    for b in range(0, B, 50):
+        xo, io = O.curev(idim, ro["t"][b], ro["n"][b], ro["c"][b], k, ro["u"][b])
+        assert io == 0 and _same(xe[b], xo), b
+    # fp equals the weighted residual recomputed through curev (reference grid-test style gate)
+    wn = np.ones((B, m)) if w is None else w
+    res = ((wn[:, :, None] * (xe - x)) ** 2).sum(axis=(1, 2))
+    assert np.allclose(res, ro["fp"], rtol=1e-9, atol=1e-12)
