@@ -40,6 +40,7 @@ B_PER_GPU = 1 << 20
 SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
 SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 22, 512, 3, 28   # config 3 shape, 2^22 curves/GPU
 GRID_M, GRID_K, GRID_SIGMA, GRID_NEST = 4096, 3, 0.05, 128          # config 4: 4096 x 4096 grid, kx=ky=3
+PARCUR_B, PARCUR_M, PARCUR_IDIM = 1 << 19, 256, 2                   # parametric curves
 # DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum,
 # profiles/r01_final_kernels.md, profiles/r01b_kernels.md); the bench itself never runs under ncu.
 NCU_FIT_DRAM_BYTES_PER_FIT = 8.1 * (6.558e9 + 1.593e9) / 2.5e5 + (51.47e9 + 10.02e9) / (0.94 * 262144)
@@ -57,6 +58,7 @@ def parse():
     ap.add_argument("--no-splev", action="store_true")
     ap.add_argument("--no-shared", action="store_true")
     ap.add_argument("--no-regrid", action="store_true")
+    ap.add_argument("--no-parcur", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -452,6 +454,90 @@ def main():
         del ysh, sho, r
         torch.cuda.empty_cache()
 
+    # ---------------------------------------------------------------- parametric curves
+    parc = None
+    if not args.no_parcur:
+        torch.cuda.empty_cache()
+        f64 = torch.float64
+        Bp, mp, dp, kp, sig = PARCUR_B, PARCUR_M, PARCUR_IDIM, 3, 0.05
+        gp = torch.Generator(device=dev)
+        gp.manual_seed(21 + rank)
+        th = torch.sort(torch.rand((mp, Bp), generator=gp, device=dev, dtype=f64) * 6.283185307179586, dim=0).values
+        th = th + torch.arange(mp, device=dev, dtype=f64)[:, None] * 1e-9
+        fr = 0.5 + 2.5 * torch.rand((1, dp, Bp), generator=gp, device=dev, dtype=f64)
+        ph = 6.0 * torch.rand((1, dp, Bp), generator=gp, device=dev, dtype=f64)
+        am = 0.5 + 1.5 * torch.rand((1, dp, Bp), generator=gp, device=dev, dtype=f64)
+        xp_ = (am * torch.cos(fr * th[:, None, :] + ph)
+               + sig * torch.randn((mp, dp, Bp), generator=gp, device=dev, dtype=f64)).contiguous()
+        del th, fr, ph, am
+        sp_ = mp * dp * sig * sig
+        nestp_ = mp + kp + 1
+        for _ in range(max(1, min(args.warmup, 2))):
+            rp = eng.parcur_batch(xp_, None, k=kp, s=sp_, nest=nestp_, ipar=0, want_stats=True)
+        barrier()
+        l0 = eng.launches
+        ev0.record()
+        for _ in range(args.steps):
+            rp = eng.parcur_batch(xp_, None, k=kp, s=sp_, nest=nestp_, ipar=0, want_stats=True)
+        ev1.record()
+        barrier()
+        p_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        p_launch = int(eng.launches - l0)
+        stp = rp["stats"].to(f64)
+        n_p = rp["n"].to(f64)
+        okp = float((rp["ier"] <= 0).to(f64).mean().item())
+        # curev of every fitted curve at its own parameters: 8 B read + 8*idim B written per point
+        ud = rp["u"].t().contiguous()
+        for _ in range(2):
+            xev, iev = eng.curev_batch(dp, rp["t"], rp["n"], rp["c"], kp, ud)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            xev, iev = eng.curev_batch(dp, rp["t"], rp["n"], rp["c"], kp, ud)
+        ev1.record()
+        barrier()
+        c_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        cur_bytes = Bp * mp * 8.0 * (1 + dp)
+        pbytes = Bp * (8.0 * mp * (dp + 1) + 8.0 * float(n_p.mean().item()) * (dp + 1) + 16)
+        parc = {
+            "config": {"workload": "batched parametric smoothing fit parcur: %d curves x %d points x idim=%d "
+                                   "per GPU, k=3, ipar=0 (chord-length parameters on the device), "
+                                   "s=m*idim*sigma^2=%.2f, nest=%d; then curev of every curve at its "
+                                   "data parameters" % (Bp, mp, dp, sp_, nestp_)},
+            "value": world * Bp / (p_ms * 1e-3), "unit": "fits/s", "ms_per_step": p_ms,
+            "success_fraction": okp, "mean_n": float(n_p.mean().item()),
+            "mean_lsq_passes": float(stp[:, 0].mean().item()), "mean_p_iters": float(stp[:, 1].mean().item()),
+            "gpu_launches": p_launch,
+            "roofline": {"bound": "hbm", "kernel": "fit pipeline instantiated for idim=%d (curfit_pass_kernel<3,.,%d> "
+                         "x R + curfit_part2_kernel): FP64 issue/latency bound like config 2, HBM fraction "
+                         "small by construction" % (dp, dp),
+                         "achieved": pbytes / (p_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": pbytes / (p_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_fit": pbytes / Bp},
+            "curev": {"ms": c_ms, "value": world * cur_bytes / (c_ms * 1e-3) / 1e9, "unit": "GB/s",
+                      "gpts_per_s": world * Bp * mp / (c_ms * 1e-3) / 1e9,
+                      "roofline": {"bound": "hbm", "kernel": "curev_kernel<3> (exact arithmetic)",
+                                   "achieved": cur_bytes / (c_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                   "unit": "GB/s", "frac": cur_bytes / (c_ms * 1e-3) / 1e9 / hbm_peak,
+                                   "traffic": None, "peak_source": peak_src,
+                                   "algorithmic_bytes_per_point": 8.0 * (1 + dp)}}}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            import oracle_lib as O
+            nthr_ = host_threads()
+            ns_ = 8192
+            xs_h = np.ascontiguousarray(xp_[:, :, :ns_].permute(2, 0, 1).cpu().numpy())
+            t0 = time.perf_counter()
+            oc = O.parcur_batch(0, 0, dp, xs_h, None, kp, sp_, nestp_, nthreads=nthr_)
+            dtp = time.perf_counter() - t0
+            same = bool(np.array_equal(oc["n"], rp["n"][:ns_].cpu().numpy())
+                        and np.array_equal(oc["fp"], rp["fp"][:ns_].cpu().numpy()))
+            parc["cpu_baseline"] = {"value": ns_ / dtp, "unit": "fits/s", "cores": nthr_, "kind": "port",
+                                    "sample": "first %d curves of the same batch, oracle port of parcur/fppara, "
+                                              "OpenMP over curves; n and fp bit-identical to the GPU result: %s"
+                                              % (ns_, same)}
+        del xp_, rp, xev, ud
+        torch.cuda.empty_cache()
+
     # ---------------------------------------------------------------- gridded surface (configs 4, 5b)
     grid = None
     if not args.no_regrid:
@@ -592,7 +678,7 @@ def main():
                              % (2 * B * M * 8 / 1e9),
                        "success_fraction": ok_frac, "gathered_summary_curves": gathered},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "fp64": fp64, "splev": splev, "shared_lsq": shared, "regrid": grid,
+            "roofline": roof, "fp64": fp64, "splev": splev, "shared_lsq": shared, "parcur": parc, "regrid": grid,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -24,6 +24,7 @@ module fitpack_b200
 
    public :: fp_curfit_c, fp_splev_c, fp_curfit_batch_c, fp_splev_batch_c
    public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c
+   public :: fp_parcur_c, fp_curev_c, fp_parcur_batch_c
    public :: fp_curfit_batch_dev_c, fp_curfit_shared_dev_c, fp_splev_batch_dev_c
    public :: fpb_engine_create, fpb_engine_destroy, fpb_engine_synchronize, fpb_device_count
    public :: curfit_batch, splev_batch
@@ -76,6 +77,43 @@ module fitpack_b200
          real   (FP_REAL), intent(out)       :: z(mx*my)
          real   (FP_REAL), intent(inout)     :: wrk(lwrk)
       end function fp_bispev_c
+
+      ! parametric curves: same interfaces as the reference's parcur_c / curev_c
+      ! (src/fitpack_core_c.f90:90-100, 178-184); fp_parcur_batch_c is the batch form (new)
+      subroutine fp_parcur_c(iopt,ipar,idim,m,u,mx,x,w,ub,ue,k,s,nest,n,t,nc,c,fp,wrk,lwrk,iwrk,ier) &
+                             bind(C,name="fp_parcur_c")
+         import
+         real   (FP_REAL), intent(inout)       :: ub,ue,s
+         real   (FP_REAL), intent(out)         :: fp
+         integer(FP_SIZE), intent(in),   value :: iopt,ipar,idim,m,mx,k,nest,lwrk,nc
+         integer(FP_SIZE), intent(inout)       :: n
+         integer(FP_FLAG), intent(out)         :: ier
+         real   (FP_REAL), intent(in)          :: x(idim,m)
+         real   (FP_REAL), intent(inout)       :: u(m),w(m),t(nest),c(nc),wrk(lwrk)
+         integer(FP_SIZE), intent(inout)       :: iwrk(nest)
+      end subroutine fp_parcur_c
+
+      subroutine fp_curev_c(idim,t,n,c,nc,k,u,m,x,mx,ier) bind(C,name="fp_curev_c")
+         import
+         integer(FP_SIZE), intent(in), value :: idim,n,nc,k,m,mx
+         integer(FP_FLAG), intent(out)       :: ier
+         real   (FP_REAL), intent(in)        :: t(n),c(nc),u(m)
+         real   (FP_REAL), intent(out)       :: x(mx)
+      end subroutine fp_curev_c
+
+      ! x(idim,m,nbatch), u(m,nbatch), w(m,nbatch) (c_null_ptr-style optional: pass w as a
+      ! type(c_ptr) interface variant if unit weights are wanted), c(nest*idim,nbatch)
+      integer(c_int32_t) function fp_parcur_batch_c(nbatch,iopt,ipar,idim,m,u,x,w,ub,ue,k,s,nest, &
+                                                    n,t,c,fp,ier,fpint,nrdata) bind(C,name="fp_parcur_batch_c")
+         import
+         integer(FP_SIZE), intent(in), value :: nbatch,iopt,ipar,idim,m,k,nest
+         real   (FP_REAL), intent(in), value :: s
+         real   (FP_REAL), intent(inout)     :: u(m,nbatch),ub(nbatch),ue(nbatch)
+         real   (FP_REAL), intent(in)        :: x(idim,m,nbatch),w(m,nbatch)
+         integer(FP_SIZE), intent(inout)     :: n(nbatch),nrdata(nest,nbatch)
+         real   (FP_REAL), intent(inout)     :: t(nest,nbatch),c(nest*idim,nbatch),fp(nbatch),fpint(nest,nbatch)
+         integer(FP_FLAG), intent(out)       :: ier(nbatch)
+      end function fp_parcur_batch_c
 
       subroutine fp_splder_c(t,n,c,k,nu,x,y,m,e,wrk,ier) bind(C,name="fp_splder_c")
          import
