@@ -1911,3 +1911,595 @@ void orc_parcur_batch(int32_t nbatch, int32_t iopt, int32_t ipar, int32_t idim, 
         free(ones);
     }
 }
+
+/* =====================================================================================
+ * Periodic curves: percur / fpperi.  The triangular factor is kept as
+ * two blocks, a band matrix a1 and the k wrap-around columns a2 (fp_rotate_row_2mat, fpbacp).
+ * ===================================================================================== */
+#define M2(a, i, j) (a)[((j) - 1) * nest + ((i) - 1)]  /* Fortran a(i,j), leading dimension nest */
+
+/* fpchep, core:2689-2770 */
+int32_t orc_fpchep(const double *x, int32_t m, const double *t, int32_t n, int32_t k)
+{
+    const double *X = x - 1, *T = t - 1;
+    int k1 = k + 1, k2 = k1 + 1, nk1 = n - k1, nk2 = nk1 + 1, m1 = m - 1;
+    int i, i1, i2, j, j1, l, l1, l2, mm;
+    double per, tj, tl, xi;
+    if (nk1 < k1 || n > m + 2 * k) return IER_INPUT;
+    j = n;
+    for (i = 1; i <= k; ++i) {
+        if (T[i] > T[i + 1]) return IER_INPUT;
+        if (T[j] < T[j - 1]) return IER_INPUT;
+        --j;
+    }
+    for (i = k2; i <= nk2; ++i)
+        if (T[i] <= T[i - 1]) return IER_INPUT;
+    if (X[1] < T[k1] || X[m] > T[nk2]) return IER_INPUT;
+    l1 = k1;
+    l2 = 1;
+    for (l = 1; l <= m; ++l) {
+        xi = X[l];
+        while (!(xi < T[l1 + 1] || l == nk1)) {
+            ++l1;
+            ++l2;
+            if (l2 > k1) goto found_l;
+        }
+    }
+    l = m;
+found_l:
+    per = T[nk2] - T[k1];
+    for (i1 = 2; i1 <= l; ++i1) {
+        int ok = 1;
+        i = i1 - 1;
+        mm = i + m1;
+        for (j = k1; j <= nk1 && ok; ++j) {
+            tj = T[j];
+            j1 = j + k1;
+            tl = T[j1];
+            xi = -DBL_MAX;
+            while (xi <= tj) {
+                ++i;
+                if (i > mm) { ok = 0; break; }
+                i2 = i - m1;
+                xi = (i2 <= 0) ? X[i] : X[i2] + per;
+            }
+            if (ok && xi >= tl) ok = 0;
+        }
+        if (ok) return IER_OK;
+    }
+    return IER_INPUT;
+}
+
+/* fp_rotate_row_2mat, core:5968-6009 */
+static void rotate_row_2mat(double *h1, int band1, double *h2, int band2, double *a1, double *a2,
+                            int nest, double *yi, double *z, int j1_start, int j1_end)
+{
+    double *H1 = h1 - 1, *H2 = h2 - 1, *Z = z - 1;
+    int j, q, i2, ij;
+    for (j = j1_start; j <= j1_end; ++j) {
+        double piv = H1[1], cs, sn;
+        if (g_netlib_compat ? (piv == 0.0) : orc_equal(piv, 0.0)) {
+            for (q = 1; q < band1; ++q) H1[q] = H1[q + 1];
+            H1[band1] = 0.0;
+            continue;
+        }
+        fpgivs(piv, &M2(a1, j, 1), &cs, &sn);
+        fprota(cs, sn, yi, &Z[j]);
+        for (q = 1; q <= band2; ++q) fprota(cs, sn, &H2[q], &M2(a2, j, q));
+        if (j < j1_end) {
+            i2 = j1_end - j;
+            if (i2 > band1 - 1) i2 = band1 - 1;
+            i2 += 1;
+            for (q = 2; q <= i2; ++q) fprota(cs, sn, &H1[q], &M2(a1, j, q));
+            for (q = 1; q < i2; ++q) H1[q] = H1[q + 1];
+            H1[i2] = 0.0;
+        }
+    }
+    for (j = 1; j <= band2; ++j) {
+        double piv, cs, sn;
+        ij = j1_end + j;
+        if (ij <= 0) continue;
+        piv = H2[j];
+        if (g_netlib_compat ? (piv == 0.0) : orc_equal(piv, 0.0)) continue;
+        fpgivs(piv, &M2(a2, ij, j), &cs, &sn);
+        fprota(cs, sn, yi, &Z[ij]);
+        for (q = j + 1; q <= band2; ++q) fprota(cs, sn, &H2[q], &M2(a2, ij, q));
+    }
+}
+
+/* fpbacp, core:1869-1921 : a (n2 x n2 band, width k1) and b (n x k); c may alias z */
+static void fpbacp(const double *a, const double *b, const double *z, int n, int k, int k1, double *c,
+                   int nest)
+{
+    const double *Z = z - 1;
+    double *C = c - 1, store;
+    int i, i1, j, l, l0, l1, n2 = n - k;
+    (void)k1;
+    l = n;
+    for (i = 1; i <= k; ++i) {
+        store = Z[l];
+        j = k + 2 - i;
+        if (i != 1) {
+            l0 = l;
+            for (l1 = j; l1 <= k; ++l1) {
+                ++l0;
+                store = store - C[l0] * M2(b, l, l1);
+            }
+        }
+        C[l] = store / M2(b, l, j - 1);
+        --l;
+        if (l == 0) return;
+    }
+    for (i = 1; i <= n2; ++i) {
+        store = Z[i];
+        l = n2;
+        for (j = 1; j <= k; ++j) {
+            ++l;
+            store = store - C[l] * M2(b, i, j);
+        }
+        C[i] = store;
+    }
+    i = n2;
+    C[i] = C[i] / M2(a, i, 1);
+    if (i == 1) return;
+    for (j = 2; j <= n2; ++j) {
+        --i;
+        store = C[i];
+        i1 = (j <= k) ? j - 1 : k;
+        l = i;
+        for (l0 = 1; l0 <= i1; ++l0) {
+            ++l;
+            store = store - C[l] * M2(a, i, l0 + 1);
+        }
+        C[i] = store / M2(a, i, 1);
+    }
+}
+
+/* fpperi_reset_interp, core:10220-10257; returns done */
+static int peri_reset_interp(int k, int m, int n, int *kk, int *kk1, const double *x, const double *y,
+                             double *t, double *c, double *fp, double per, double fp0, double s,
+                             double *fpint, int32_t *nrdata)
+{
+    const double *X = x - 1, *Y = y - 1;
+    double *T = t - 1, *C = c - 1;
+    int m1 = m - 1, i;
+    if (k % 2 != 0) {
+        for (i = 2; i <= m1; ++i) T[k + i] = X[i];
+        if (s <= 0.0) {
+            *kk = k - 1;
+            *kk1 = k;
+            if (*kk <= 0) {
+                T[1] = T[m] - per;
+                T[2] = X[1];
+                T[m + 1] = X[m];
+                T[m + 2] = T[3] + per;
+                for (i = 1; i <= m1; ++i) C[i] = Y[i];
+                C[m] = Y[1];
+                *fp = 0.0;
+                fpint[n - 2] = 0.0;
+                fpint[n - 1] = fp0;
+                nrdata[n - 1] = 0;
+                return 1;
+            }
+        }
+    } else {
+        for (i = 2; i <= m1; ++i) T[k + i] = 0.5 * (X[i] + X[i - 1]);
+    }
+    return 0;
+}
+
+/* fpperi, core:9668-10192 */
+static void fpperi(int iopt, const double *x, const double *y, const double *w, int m, int k, double s,
+                   int nest, double tol, int maxit, int k1, int k2, int32_t *n_io, double *t, double *c,
+                   double *fp_io, double *fpint, double *z, double *a1, double *a2, double *b, double *g1,
+                   double *g2, double *q, int32_t *nrdata, int32_t *ier_io)
+{
+    const double *X = x - 1, *Y = y - 1, *W = w - 1;
+    double *T = t - 1, *C = c - 1, *FPI = fpint - 1, *Z = z - 1;
+    int32_t *NRD = nrdata - 1;
+    double acc, cs, c1, d1, fpart, fpms, fpold, fp0, f1, f2 = 0.0, f3, p, per, pinv, p1, p2 = 0.0, p3, sn,
+           store, term, wi, xi, yi, rn, fp = *fp_io;
+    int i, ik, it, iter, i1, i2, j, jk, jper, j1, j2, kk, kk1, l, l0, l1, l5, mm, m1, newk, nk1, nk2, nmax,
+        nmin, nplus, npl1, nrint, n10 = 0, n11, n7 = 0, n8, n = *n_io, ier;
+    int check1, check3;
+    double h[ORC_MAX_ORDER + 1], h1[7], h2[6];
+
+    fpold = 0.0;
+    fp0 = 0.0;
+    nplus = 0;
+    fpms = DBL_MAX;
+    acc = tol * s;
+    nmax = m + 2 * k;
+    m1 = m - 1;
+    kk = k;
+    kk1 = k1;
+    nmin = 2 * k1;
+    ier = IER_OK;
+    per = X[m] - X[1];
+
+    if (iopt >= 0) {
+        if (s <= 0.0 && nmax != nmin) {                         /* core:9725-9742 */
+            n = nmax;
+            if (n > nest) { ier = IER_STORAGE; goto done; }
+            if (peri_reset_interp(k, m, n, &kk, &kk1, x, y, t, c, &fp, per, fp0, s, fpint, nrdata)) {
+                ier = IER_INTERP;
+                goto done;
+            }
+        } else {
+            if (iopt != 0 && n != nmin) {
+                fp0 = FPI[n];
+                fpold = FPI[n - 1];
+                nplus = NRD[n];
+            }
+            if (iopt == 0 || n == nmin || (iopt != 0 && n != nmin && s >= fp0)) {
+                fp0 = 0.0;                                       /* core:9760-9771 */
+                d1 = 0.0;
+                c1 = 0.0;
+                for (it = 1; it <= m1; ++it) {
+                    wi = W[it];
+                    yi = Y[it] * wi;
+                    fpgivs(wi, &d1, &cs, &sn);
+                    fprota(cs, sn, &yi, &c1);
+                    fp0 = fp0 + yi * yi;
+                }
+                c1 = c1 / d1;
+                fpms = fp0 - s;
+                if (fpms < acc || nmax == nmin) {               /* core:9776-9795 */
+                    ier = IER_LSQ;
+                    for (i = 1; i <= k1; ++i) {
+                        rn = (double)(k1 - i);
+                        T[i] = X[1] - rn * per;
+                        C[i] = c1;
+                        j = i + k1;
+                        rn = (double)(i - 1);
+                        T[j] = X[m] + rn * per;
+                    }
+                    n = nmin;
+                    fp = fp0;
+                    FPI[n - 1] = 0.0;
+                    FPI[n] = fp0;
+                    NRD[n] = 0;
+                    goto done;
+                }
+                fpold = fp0;
+                if (nmin >= nest) { ier = IER_STORAGE; goto done; }
+                nplus = 1;                                       /* core:9804-9811 */
+                n = nmin + 1;
+                mm = (m + 1) / 2;
+                T[k2] = X[mm];
+                NRD[1] = mm - 2;
+                NRD[2] = m1 - mm;
+            }
+        }
+    }
+
+    iter = 0;
+    for (;;) {                                                  /* update_knots core:9818-10060 */
+        int restart = 0;
+        if (!(iter < m)) break;
+        ++iter;
+        nrint = n - nmin + 1;
+        T[k1] = X[1];
+        nk1 = n - k1;
+        nk2 = nk1 + 1;
+        T[nk2] = X[m];
+        for (j = 1; j <= k; ++j) {
+            i1 = nk2 + j;
+            i2 = nk2 - j;
+            j1 = k1 + j;
+            j2 = k1 - j;
+            T[i1] = T[j1] + per;
+            T[j2] = T[i2] - per;
+        }
+        for (i = 1; i <= nk1; ++i) Z[i] = 0.0;
+        for (j = 1; j <= kk1; ++j)
+            for (i = 1; i <= nk1; ++i) M2(a1, i, j) = 0.0;
+        n7 = nk1 - k;
+        n10 = n7 - kk;
+        jper = 0;
+        fp = 0.0;
+        l = k1;
+        g_stats.lsq_passes++;
+        for (it = 1; it <= m1; ++it) {                          /* get_coefs core:9860-9937 */
+            xi = X[it];
+            wi = W[it];
+            yi = Y[it] * wi;
+            l = orc_knot_interval(t, xi, l, nk1);
+            orc_fpbspl(t, n, k, xi, l, h);
+            for (j = 0; j < k1; ++j) { q[j * m + (it - 1)] = h[j]; h[j] = h[j] * wi; }
+            l5 = l - k1;
+            if (l5 >= n10) {
+                if (jper == 0) {                                 /* initialise a2, core:9884-9897 */
+                    for (j = 1; j <= kk; ++j)
+                        for (i = 1; i <= n7; ++i) M2(a2, i, j) = 0.0;
+                    jk = n10 + 1;
+                    for (i = 1; i <= kk; ++i) {
+                        ik = jk;
+                        for (j = 1; j <= kk1; ++j) {
+                            if (ik <= 0) break;
+                            M2(a2, ik, i) = M2(a1, ik, j);
+                            --ik;
+                        }
+                        ++jk;
+                    }
+                    jper = 1;
+                }
+                for (i = 0; i < 7; ++i) h1[i] = 0.0;
+                for (i = 0; i < 6; ++i) h2[i] = 0.0;
+                j = l5 - n10;
+                for (i = 1; i <= kk1; ++i) {
+                    ++j;
+                    l0 = j;
+                    l1 = l0 - kk;
+                    while (l1 > (n10 > 0 ? n10 : 0)) {
+                        l0 = l1 - n10;
+                        l1 = l0 - kk;
+                    }
+                    if (l1 > 0) h1[l1 - 1] = h[i - 1];
+                    else h2[l0 - 1] = h2[l0 - 1] + h[i - 1];
+                }
+                rotate_row_2mat(h1, kk1, h2, kk, a1, a2, nest, &yi, z, 1, n10);
+            } else {
+                rotate_row(h, kk1, a1, nest, &yi, z, l5);
+            }
+            fp = fp + yi * yi;
+        }
+        FPI[n - 1] = fpold;
+        FPI[n] = fp0;
+        NRD[n] = nplus;
+        fpbacp(a1, a2, z, n7, kk, kk1, c, nest);
+        for (i = 1; i <= k; ++i) C[n7 + i] = C[i];
+        fpms = fp - s;
+        if (iopt < 0 || fabs(fpms) < acc) goto done;
+        if (fpms < 0.0) break;
+        if (n == nmax) { ier = IER_INTERP; goto done; }
+        if (n == nest) { ier = IER_STORAGE; goto done; }
+        {                                                       /* core:9972-9975 */
+            int hh, mx;
+            npl1 = nplus * 2;
+            if (fpold - fp > acc) npl1 = f_int(((double)nplus * fpms) / (fpold - fp));
+            hh = nplus / 2;
+            mx = npl1;
+            if (hh > mx) mx = hh;
+            if (1 > mx) mx = 1;
+            nplus = (nplus * 2 < mx) ? nplus * 2 : mx;
+        }
+        fpold = fp;
+        fpart = 0.0;                                            /* core:9979-10007 */
+        i = 1;
+        l = k1;
+        newk = 0;
+        for (it = 1; it <= m1; ++it) {
+            if (X[it] >= T[l]) { newk = 1; ++l; }
+            term = 0.0;
+            l0 = l - k2;
+            for (j = 1; j <= k1; ++j) {
+                ++l0;
+                term = term + C[l0] * q[(j - 1) * m + (it - 1)];
+            }
+            term = W[it] * (term - Y[it]);
+            term = term * term;
+            fpart = fpart + term;
+            if (newk) {
+                if (l > k2) {
+                    store = term * 0.5;
+                    FPI[i] = fpart - store;
+                    ++i;
+                    fpart = store;
+                } else {
+                    FPI[nrint] = term;
+                }
+                newk = 0;
+            }
+        }
+        FPI[nrint] = FPI[nrint] + fpart;
+        for (l = 1; l <= nplus; ++l) {                          /* core:10009-10032 */
+            fpknot(x, m, t, &n, fpint, nrdata, &nrint, nest, 1);
+            if (n == nmax) {
+                if (peri_reset_interp(k, m, n, &kk, &kk1, x, y, t, c, &fp, per, fp0, s, fpint, nrdata)) {
+                    ier = IER_INTERP;
+                    goto done;
+                }
+                iter = 0;
+                restart = 1;
+                break;
+            }
+            if (n == nest) break;
+        }
+        (void)restart;
+    }
+
+    /* part 2, core:10060-10190 */
+    fpdisc(t, n, k2, b, nest);
+    p = 0.0;
+    p1 = 0.0;
+    f1 = fp0 - s;
+    p3 = -1.0;
+    f3 = fpms;
+    n11 = n10 - 1;
+    n8 = n7 - 1;
+    l = n7;
+    for (i = 1; i <= k; ++i) {
+        j = k + 1 - i;
+        p = p + M2(a2, l, j);
+        --l;
+        if (l == 0) break;
+    }
+    if (l != 0) {
+        if (g_netlib_compat) {
+            for (i = 1; i <= n10; ++i) p = p + M2(a1, i, 1);
+        } else {                                                /* p + sum(a1(1:n10,1)), core:10081 */
+            double sm = 0.0;
+            for (i = 1; i <= n10; ++i) sm = sm + M2(a1, i, 1);
+            p = p + sm;
+        }
+    }
+    rn = (double)n7;
+    p = rn / p;
+    check1 = 0;
+    check3 = 0;
+    for (iter = 1; iter <= maxit; ++iter) {                     /* find_root core:10088-10186 */
+        g_stats.p_iters++;
+        pinv = 1.0 / p;
+        for (i = 1; i <= n7; ++i) {
+            C[i] = Z[i];
+            for (j = 1; j <= k1; ++j) M2(g1, i, j) = M2(a1, i, j);
+            M2(g1, i, k2) = 0.0;
+            M2(g2, i, 1) = 0.0;
+            for (j = 1; j <= k; ++j) M2(g2, i, j + 1) = M2(a2, i, j);
+        }
+        l = n10;
+        for (j = 1; j <= k1; ++j) {
+            if (l <= 0) break;
+            M2(g2, l, 1) = M2(a1, l, j);
+            --l;
+        }
+        for (it = 1; it <= n8; ++it) {                          /* n8_rows core:10117-10162 */
+            yi = 0.0;
+            for (i = 0; i < 7; ++i) h1[i] = 0.0;
+            for (i = 0; i < 6; ++i) h2[i] = 0.0;
+            if (it <= n11) {
+                l = it;
+                l0 = it;
+                for (j = 1; j <= k2; ++j) {
+                    if (l0 == n10) {
+                        l0 = 1;
+                        for (l1 = j; l1 <= k2; ++l1) {
+                            h2[l0 - 1] = M2(b, it, l1) * pinv;
+                            ++l0;
+                        }
+                        break;
+                    }
+                    h1[j - 1] = M2(b, it, j) * pinv;
+                    ++l0;
+                }
+            } else {
+                l = 1;
+                i = it - n10;
+                for (j = 1; j <= k2; ++j) {
+                    ++i;
+                    l0 = i;
+                    l1 = l0 - k1;
+                    while (l1 > (n11 > 0 ? n11 : 0)) {
+                        l0 = l1 - n11;
+                        l1 = l0 - k1;
+                    }
+                    if (l1 > 0) h1[l1 - 1] = M2(b, it, j) * pinv;
+                    else h2[l0 - 1] = h2[l0 - 1] + M2(b, it, j) * pinv;
+                }
+            }
+            rotate_row_2mat(h1, k2, h2, k1, g1, g2, nest, &yi, c, l, n11);
+        }
+        fpbacp(g1, g2, c, n7, k1, k2, c, nest);
+        for (i = 1; i <= k; ++i) C[n7 + i] = C[i];
+        fp = 0.0;
+        l = k1;
+        for (it = 1; it <= m1; ++it) {
+            if (X[it] >= T[l]) ++l;
+            l0 = l - k2;
+            term = 0.0;
+            for (j = 1; j <= k1; ++j) term = term + C[l0 + j] * q[(j - 1) * m + (it - 1)];
+            term = W[it] * (term - Y[it]);
+            fp = fp + term * term;
+        }
+        fpms = fp - s;
+        if (fabs(fpms) < acc) goto done;
+        if (iter == maxit) { ier = IER_MAXIT; goto done; }
+        if (!root_iterate(&p1, &f1, &p2, &f2, &p3, &f3, &p, fpms, acc, &check1, &check3)) {
+            ier = IER_S_SMALL;
+            goto done;
+        }
+    }
+
+done:
+    *n_io = n;
+    *fp_io = fp;
+    *ier_io = ier;
+}
+
+/* percur, core:15784-15863 (argument list of fp_percur_c) */
+void orc_percur(int32_t iopt, int32_t m, const double *x, const double *y, const double *w, int32_t k,
+                double s, int32_t nest, int32_t *n, double *t, double *c, double *fp, double *wrk,
+                int32_t lwrk, int32_t *iwrk, int32_t *ier)
+{
+    const double tol = 1.0e-03;
+    const int maxit = 20;
+    int k1 = k + 1, k2 = k1 + 1, nmin = 2 * k1, m1 = m - 1, lwest, i, i1, i2, j1, j2;
+    int ifp, iz, ia1, ia2, ib, ig1, ig2, iq;
+    double per;
+    *ier = IER_INPUT;
+    lwest = m * k1 + nest * (8 + 5 * k);
+    if (k <= 0 || k > 5) return;
+    if (iopt < -1 || iopt > 1) return;
+    if (m < 2 || nest < nmin) return;
+    if (lwrk < lwest) return;
+    for (i = 0; i < m1; ++i)
+        if (w[i] <= 0.0) return;
+    for (i = 0; i < m1; ++i)
+        if (x[i] >= x[i + 1]) return;
+    if (iopt >= 0) {
+        if (s < 0.0) return;
+        if (orc_equal(s, 0.0) && nest < (m + 2 * k)) return;
+    } else {
+        double *T = t - 1;
+        if (*n <= nmin || *n > nest) return;
+        per = x[m - 1] - x[0];
+        j1 = k1;
+        T[j1] = x[0];
+        i1 = *n - k;
+        T[i1] = x[m - 1];
+        j2 = j1;
+        i2 = i1;
+        for (i = 1; i <= k; ++i) {
+            ++i1; --i2; ++j1; --j2;
+            T[j2] = T[i2] - per;
+            T[i1] = T[j1] + per;
+        }
+        *ier = orc_fpchep(x, m, t, *n, k);
+        if (*ier != 0) return;
+    }
+    *ier = IER_OK;
+    ifp = 0;
+    iz = ifp + nest;
+    ia1 = iz + nest;
+    ia2 = ia1 + nest * k1;
+    ib = ia2 + nest * k;
+    ig1 = ib + nest * k2;
+    ig2 = ig1 + nest * k2;
+    iq = ig2 + nest * k1;
+    fpperi(iopt, x, y, w, m, k, s, nest, tol, maxit, k1, k2, n, t, c, fp, wrk + ifp, wrk + iz, wrk + ia1,
+           wrk + ia2, wrk + ib, wrk + ig1, wrk + ig2, wrk + iq, iwrk, ier);
+}
+
+/* batch driver (CPU baseline): x, y, w [nbatch][m] (w NULL => 1) */
+void orc_percur_batch(int32_t nbatch, int32_t iopt, int32_t m, const double *x, const double *y,
+                      const double *w, int32_t k, double s, int32_t nest, int32_t *n, double *t, double *c,
+                      double *fp, int32_t *ier, int32_t nthreads)
+{
+    int lwrk = m * (k + 1) + nest * (8 + 5 * k);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        double *wrk = (double *)malloc(sizeof(double) * (size_t)lwrk);
+        int32_t *iwrk = (int32_t *)malloc(sizeof(int32_t) * (size_t)nest);
+        double *ones = NULL;
+        int32_t b;
+        if (!w) {
+            int i;
+            ones = (double *)malloc(sizeof(double) * (size_t)m);
+            for (i = 0; i < m; ++i) ones[i] = 1.0;
+        }
+#pragma omp for schedule(dynamic, 16)
+        for (b = 0; b < nbatch; ++b)
+            orc_percur(iopt, m, x + (size_t)b * m, y + (size_t)b * m, w ? w + (size_t)b * m : ones, k, s,
+                       nest, &n[b], t + (size_t)b * nest, c + (size_t)b * nest, &fp[b], wrk, lwrk, iwrk,
+                       &ier[b]);
+        free(wrk);
+        free(iwrk);
+        free(ones);
+    }
+}

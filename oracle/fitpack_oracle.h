@@ -130,6 +130,15 @@ void orc_parcur_batch(int32_t nbatch, int32_t iopt, int32_t ipar, int32_t idim, 
                       int32_t nest, int32_t *n, double *t, double *c, double *fp, int32_t *ier,
                       int32_t nthreads);
 
+/* percur core:15784-15863 + fpperi 9668-10192 (argument list of fp_percur_c); fpchep core:2689-2770 */
+void orc_percur(int32_t iopt, int32_t m, const double *x, const double *y, const double *w, int32_t k,
+                double s, int32_t nest, int32_t *n, double *t, double *c, double *fp, double *wrk,
+                int32_t lwrk, int32_t *iwrk, int32_t *ier);
+int32_t orc_fpchep(const double *x, int32_t m, const double *t, int32_t n, int32_t k);
+void orc_percur_batch(int32_t nbatch, int32_t iopt, int32_t m, const double *x, const double *y,
+                      const double *w, int32_t k, double s, int32_t nest, int32_t *n, double *t, double *c,
+                      double *fp, int32_t *ier, int32_t nthreads);
+
 int32_t orc_max_threads(void);
 
 /* tests only: switch the documented reference-vs-netlib deviations off (see .c) */

@@ -429,11 +429,91 @@ def make_parcur():
           {int(v): int((np.array(rec["ier"]) == v).sum()) for v in np.unique(rec["ier"])},
           "iopt:", {int(v): int((np.array(rec["iopt"]) == v).sum()) for v in np.unique(rec["iopt"])})
 
+
+# ------------------------------------------------------------------ periodic curves
+def percur_lwrk(m, k, nest):
+    return m * (k + 1) + nest * (8 + 5 * k)
+
+
+def scipy_percur(iopt, x, y, w, k, s, nest, t_in=None, wrk=None, iwrk=None):
+    m = x.size
+    t = np.zeros(nest) if t_in is None else t_in.copy()
+    wrk = np.zeros(percur_lwrk(m, k, t.size)) if wrk is None else wrk
+    iwrk = np.zeros(t.size, np.int32) if iwrk is None else iwrk
+    n, t, c, fp, ier = _fitpack.percur(iopt, x, y, w, k, s, t, wrk, iwrk)
+    return int(n), np.asarray(t), np.asarray(c), float(fp), int(ier), wrk, iwrk
+
+
+def make_percur():
+    """percur: iopt=0 over all degrees / s regimes / weights, iopt=-1 with given interior knots and
+    iopt=0 -> 1 continuations (state carried in wrk/iwrk)."""
+    rng = np.random.default_rng(909)
+    rec = dict(k=[], m=[], iopt=[], s=[], s0=[], nest=[], n=[], fp=[], ier=[], off=[], toff=[])
+    xcat, ycat, wcat, tcat, ccat = [], [], [], [], []
+    off = toff = 0
+    for trial in range(220):
+        k = int(rng.integers(1, 6))
+        m = int(rng.integers(k + 3, 140))
+        x = np.unique(np.sort(rng.uniform(0, 2 * np.pi, m)))
+        if rng.random() < 0.25:
+            x = np.linspace(0, 2 * np.pi, m)
+        m = x.size
+        y = rng.uniform(.5, 2) * np.sin(x * rng.integers(1, 4) + rng.uniform(0, 6)) \
+            + 0.3 * np.cos(2 * x) + 0.1 * rng.standard_normal(m)
+        y[-1] = y[0]
+        w = np.ones(m) if rng.random() < 0.5 else rng.uniform(0.5, 2, m)
+        s = float(rng.choice([0.0, m * 0.01, m * 0.001, m * 0.1, 1e-8, 500.0]))
+        nest = int(rng.choice([m + 2 * k, max(2 * k + 3, m // 3), max(2 * k + 3, m // 2)]))
+        mode = rng.choice(["fit", "lsq", "cont"], p=[0.6, 0.2, 0.2])
+        s0 = -1.0
+        if mode == "fit":
+            iopt = 0
+            n, t, c, fp, ier, _, _ = scipy_percur(0, x, y, w, k, s, nest)
+        elif mode == "lsq":
+            iopt = -1
+            nint = int(rng.integers(1, max(2, min(9, m - 3))))
+            tin = np.zeros(nint + 2 * k + 2)
+            tin[k + 1:k + 1 + nint] = np.quantile(x, np.linspace(0, 1, nint + 2)[1:-1])
+            nest = tin.size
+            n, t, c, fp, ier, _, _ = scipy_percur(-1, x, y, w, k, 0.0, nest, t_in=tin)
+            s = 0.0
+        else:
+            # scipy's wrapper takes n = nest = len(t) on a continuation, so the replayable case is:
+            # fit with a small s0 (many knots), then iopt=1 with a larger s on exactly those knots
+            # (nest = n0): the state fp0/fpold/nplus is read back from wrk/iwrk and part 2 runs
+            iopt = 1
+            s0 = float(rng.choice([m * 0.001, m * 0.01]))
+            s = float(s0 * rng.uniform(2, 30))
+            n0, t0, c0, fp0, ier0, wrk, iwrk = scipy_percur(0, x, y, w, k, s0, nest)
+            if ier0 > 0 or n0 <= 2 * k + 2:
+                continue
+            n, t, c, fp, ier = _fitpack.percur(1, x, y, w, k, s, t0[:n0].copy(), wrk, iwrk)
+            n, t, c, fp, ier = int(n), np.asarray(t), np.asarray(c), float(fp), int(ier)
+        if not np.isfinite(fp) and ier != 10:
+            continue
+        if ier == 10:
+            n = 0
+        for key, v in (("k", k), ("m", m), ("iopt", iopt), ("s", s), ("s0", s0), ("nest", nest), ("n", n),
+                       ("fp", fp), ("ier", ier), ("off", off), ("toff", toff)):
+            rec[key].append(v)
+        xcat.append(x); ycat.append(y); wcat.append(w)
+        tcat.append(t[:n]); ccat.append(c[:n])
+        off += m
+        toff += n
+    ints = ("k", "m", "iopt", "nest", "n", "ier")
+    out = {key: np.array(v, np.int32 if key in ints else (np.int64 if key.endswith("off") else float))
+           for key, v in rec.items()}
+    np.savez_compressed(os.path.join(HERE, "percur_golden.npz"), x=np.concatenate(xcat), y=np.concatenate(ycat),
+                        w=np.concatenate(wcat), t=np.concatenate(tcat), c=np.concatenate(ccat), **out)
+    print("percur cases:", len(rec["k"]), "ier histogram:",
+          {int(v): int((np.array(rec["ier"]) == v).sum()) for v in np.unique(rec["ier"])},
+          "iopt:", {int(v): int((np.array(rec["iopt"]) == v).sum()) for v in np.unique(rec["iopt"])})
+
 if __name__ == "__main__":
     import sys
     sys.path.insert(0, os.path.dirname(HERE))
     makers = dict(mncurf=make_mncurf, curfit=make_curfit, splev=make_splev, regrid=make_regrid,
-                  calculus=make_calculus, parcur=make_parcur)
+                  calculus=make_calculus, parcur=make_parcur, percur=make_percur)
     # python make_golden.py [name ...]: regenerate only the named fixtures (default: all)
     for name in (sys.argv[1:] or list(makers)):
         makers[name]()

@@ -351,3 +351,53 @@ def parcur_batch(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=None, ue=None, n
                        _d(u), _d(x), wp, _d(ub), _d(ue), C.c_int32(k), C.c_double(s), C.c_int32(nest),
                        _i(n), _d(t), _d(c), _d(fp), _i(ier), C.c_int32(nthreads))
     return dict(n=n, t=t, c=c, fp=fp, ier=ier, u=u, ub=ub, ue=ue)
+
+
+# ------------------------------------------------------------------ periodic curves
+def percur_lwrk(m, k, nest):
+    return m * (k + 1) + nest * (8 + 5 * k)
+
+
+def percur(iopt, x, y, w, k, s, nest, n=0, t=None, wrk=None, iwrk=None, c=None, fp=0.0):
+    """orc_percur with the reference's argument list (core:15784)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    m = x.size
+    w = np.ones(m) if w is None else np.ascontiguousarray(w, dtype=np.float64)
+    lwrk = percur_lwrk(m, k, nest) if wrk is None else wrk.size
+    t = np.zeros(max(nest, 1)) if t is None else np.array(t, dtype=np.float64)
+    c = np.zeros(max(nest, 1)) if c is None else np.array(c, dtype=np.float64)
+    wrk = np.zeros(max(lwrk, 1)) if wrk is None else wrk
+    iwrk = np.zeros(max(nest, 1), dtype=np.int32) if iwrk is None else iwrk
+    n_, fp_, ier_ = C.c_int32(int(n)), C.c_double(float(fp)), C.c_int32(0)
+    L = lib()
+    L.orc_percur.restype = None
+    L.orc_percur(C.c_int32(iopt), C.c_int32(m), _d(x), _d(y), _d(w), C.c_int32(k), C.c_double(s),
+                 C.c_int32(nest), C.byref(n_), _d(t), _d(c), C.byref(fp_), _d(wrk), C.c_int32(lwrk),
+                 _i(iwrk), C.byref(ier_))
+    return dict(n=n_.value, t=t, c=c, fp=fp_.value, ier=ier_.value, wrk=wrk, iwrk=iwrk)
+
+
+def fpchep(x, t, n, k):
+    x, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, t))
+    L = lib()
+    L.orc_fpchep.restype = C.c_int32
+    return int(L.orc_fpchep(_d(x), C.c_int32(x.size), _d(t), C.c_int32(n), C.c_int32(k)))
+
+
+def percur_batch(iopt, x, y, w, k, s, nest, nthreads=0):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    B, m = y.shape
+    n = np.zeros(B, np.int32)
+    t = np.zeros((B, nest))
+    c = np.zeros((B, nest))
+    fp = np.zeros(B)
+    ier = np.zeros(B, np.int32)
+    wp = None if w is None else _d(np.ascontiguousarray(w, dtype=np.float64))
+    L = lib()
+    L.orc_percur_batch.restype = None
+    L.orc_percur_batch(C.c_int32(B), C.c_int32(iopt), C.c_int32(m), _d(x), _d(y), wp, C.c_int32(k),
+                       C.c_double(s), C.c_int32(nest), _i(n), _d(t), _d(c), _d(fp), _i(ier),
+                       C.c_int32(nthreads))
+    return dict(n=n, t=t, c=c, fp=fp, ier=ier)
