@@ -301,3 +301,42 @@ def parcur_batch(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=None, ue=None, n
                                  _p(ier), _p(fpint), _p(nrdata))
     check(rc, "fp_parcur_batch_c")
     return dict(n=n_arr, t=t_arr, c=c_arr, fp=fp, ier=ier, u=u, ub=ub, ue=ue, fpint=fpint, nrdata=nrdata)
+
+
+# ------------------------------------------------------------------ periodic curves
+def percur_lwrk(m, k, nest):
+    return m * (k + 1) + nest * (8 + 5 * k)
+
+
+def percur(iopt, x, y, w, k, s, nest, n=0, t=None, wrk=None, iwrk=None, c=None, fp=0.0):
+    """percur (reference core:15784-15863) through fp_percur_c; same conventions as curfit()."""
+    x, y = _f64(x), _f64(y)
+    m = x.size
+    w = np.ones(m) if w is None else _f64(w)
+    if wrk is None:
+        wrk = np.zeros(max(percur_lwrk(m, max(k, 0), max(nest, 0)), 1))
+    t = np.zeros(max(nest, 1)) if t is None else np.array(t, dtype=np.float64)
+    c = np.zeros(max(nest, 1)) if c is None else np.array(c, dtype=np.float64)
+    iwrk = np.zeros(max(nest, 1), dtype=np.int32) if iwrk is None else iwrk
+    n_, fp_, ier_ = C.c_int32(int(n)), C.c_double(float(fp)), C.c_int32(0)
+    lib().fp_percur_c(int(iopt), m, _p(x), _p(y), _p(w), int(k), float(s), int(nest), C.addressof(n_), _p(t),
+                      _p(c), C.addressof(fp_), _p(wrk), wrk.size, _p(iwrk), C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_percur_c: %s" % lib().fpb_last_error().decode())
+    return dict(n=n_.value, t=t, c=c, fp=fp_.value, ier=ier_.value, wrk=wrk, iwrk=iwrk)
+
+
+def percur_batch(iopt, x, y, w, k, s, nest, n=None, t=None, fpint=None, nrdata=None):
+    """Many independent periodic fits, host arrays curve-major (fp_percur_batch_c)."""
+    x, y = _f64(x), _f64(y)
+    B, m = y.shape
+    w = None if w is None else _f64(w)
+    n_arr = np.zeros(B, dtype=np.int32) if n is None else np.array(n, dtype=np.int32)
+    t_arr = np.zeros((B, nest)) if t is None else np.array(t, dtype=np.float64)
+    c_arr = np.zeros((B, nest))
+    fp = np.zeros(B)
+    ier = np.zeros(B, dtype=np.int32)
+    rc = lib().fp_percur_batch_c(B, int(iopt), m, _p(x), _p(y), _p(w), int(k), float(s), int(nest), _p(n_arr),
+                                 _p(t_arr), _p(c_arr), _p(fp), _p(ier), _p(fpint), _p(nrdata))
+    check(rc, "fp_percur_batch_c")
+    return dict(n=n_arr, t=t_arr, c=c_arr, fp=fp, ier=ier)

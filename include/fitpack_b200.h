@@ -330,6 +330,29 @@ int32_t fp_curev_batch_dev_c(fpb_engine *eng, FP_SIZE nspl, FP_SIZE idim, const 
                              const FP_SIZE *n, const FP_REAL *c, FP_SIZE ldt, int64_t ldc, FP_SIZE k,
                              const FP_REAL *u, FP_REAL *x, FP_SIZE m, FP_FLAG *ier);
 
+/* ---------------------------------------------------------- periodic curves -- */
+/*
+ * percur: periodic smoothing spline, period x(m)-x(1); y(m) and w(m) are not
+ * used (core:15744-15783).  Same name and argument list as the reference's C binding:
+ *   fp_percur_c  include/fitpack_core_c.h:104-106, src/fitpack_core_c.f90:77-87
+ *                -> percur core:15784-15863, fpperi core:9668-10192
+ * lwrk >= m*(k+1)+nest*(8+5*k); wrk(1:nest)/iwrk(1:nest) carry the iopt=1 state.  Evaluate the
+ * result with fp_splev_c.
+ */
+void fp_percur_c(FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE k,
+                 FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_REAL *wrk,
+                 FP_SIZE lwrk, FP_SIZE *iwrk, FP_FLAG *ier);
+/* NEW: many independent periodic fits; host pointers curve-major (x, y, w [nbatch][m], w NULL = 1) */
+int32_t fp_percur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y,
+                          const FP_REAL *w, FP_SIZE k, FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t,
+                          FP_REAL *c, FP_REAL *fp, FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata);
+/* device pointers + strides as fp_curfit_batch_dev_c (point-major is the fast layout) */
+int32_t fp_percur_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x,
+                              int64_t x_sb, int64_t x_si, const FP_REAL *y, int64_t y_sb, int64_t y_si,
+                              const FP_REAL *w, int64_t w_sb, int64_t w_si, FP_SIZE k, const FP_REAL *s,
+                              FP_SIZE s_stride, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
+                              FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata);
+
 #ifdef __cplusplus
 }
 #endif

@@ -951,3 +951,55 @@ def test_parcur_batch_bit_exact_vs_oracle(F, eng, idim, k, weights, ipar):
     wn = np.ones((B, m)) if w is None else w
     res = ((wn[:, :, None] * (xe - x)) ** 2).sum(axis=(1, 2))
     assert np.allclose(res, ro["fp"], rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------ periodic curves
+def test_percur_golden_cases_flat_abi_bit_exact(F):
+    """Every percur golden case (k 1..5, iopt -1/0 and 0->1 continuations, all ier classes) through
+    fp_percur_c against the oracle in reference mode: n, knots, c, fp, ier and the continuation state
+    bit-exact; the result evaluated with fp_splev_c is periodic."""
+    from test_oracle_golden import _percur_cases, run_percur_case
+    ncase = 0
+    for i, g, cs in _percur_cases():
+        ro = run_percur_case(O.percur, cs, g, i)
+        rg = run_percur_case(F.percur, cs, g, i)
+        assert rg["ier"] == ro["ier"], i
+        ncase += 1
+        if ro["ier"] == 10:
+            continue
+        n, k = ro["n"], cs["k"]
+        assert rg["n"] == n, i
+        if not (ro["ier"] == 1 and ro["fp"] == 0.0 and n > len(ro["t"])):
+            nn = min(n, len(ro["t"]))
+            assert _same(rg["t"][:nn], ro["t"][:nn]), i
+            assert _same(rg["c"][:nn - k - 1], ro["c"][:nn - k - 1]), i
+        assert rg["fp"] == ro["fp"], i
+        if cs["iopt"] >= 0 and ro["ier"] <= 0:
+            assert _same(rg["wrk"][n - 2:n], ro["wrk"][n - 2:n]) and rg["iwrk"][n - 1] == ro["iwrk"][n - 1], i
+        if ro["ier"] <= 0:
+            yg, ig = F.splev(rg["t"], n, rg["c"], k, cs["x"][[0, -1]])
+            assert ig == 0 and abs(yg[0] - yg[1]) <= 1e-9 * max(1.0, abs(yg[0])), i
+    assert ncase > 190
+
+
+@pytest.mark.parametrize("k,weights,m", [(3, False, 96), (3, True, 64), (5, False, 80), (1, True, 50),
+                                         (2, False, 70), (4, True, 60)])
+def test_percur_batch_bit_exact_vs_oracle(F, k, weights, m):
+    """Batches of periodic fits (host-pointer entry point -> device kernel) against the oracle."""
+    rng = np.random.default_rng(7 * k + m)
+    B = 1200
+    x = np.sort(rng.uniform(0, 2 * np.pi, (B, m)), axis=1) + np.arange(m)[None, :] * 1e-9
+    f = rng.integers(1, 4, (B, 1))
+    y = rng.uniform(.5, 2, (B, 1)) * np.sin(f * x + rng.uniform(0, 6, (B, 1))) + 0.1 * rng.standard_normal((B, m))
+    w = rng.uniform(0.5, 2.0, (B, m)) if weights else None
+    nest = m + 2 * k
+    for s in (m * 0.01 * (1.7 if weights else 1.0), 0.0):
+        ro = O.percur_batch(0, x, y, w, k, s, nest)
+        rg = F.percur_batch(0, x, y, w, k, s, nest)
+        assert _same(rg["ier"], ro["ier"]) and _same(rg["n"], ro["n"])
+        assert _same(rg["fp"], ro["fp"])
+        for b in range(B):
+            n = ro["n"][b]
+            assert _same(rg["t"][b, :n], ro["t"][b, :n]), (s, b)
+            assert _same(rg["c"][b, :n - k - 1], ro["c"][b, :n - k - 1]), (s, b)
+        assert set(np.unique(ro["ier"])) <= {0, -1, -2, 1, 2, 3}
