@@ -41,6 +41,7 @@ SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
 SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 22, 512, 3, 28   # config 3 shape, 2^22 curves/GPU
 GRID_M, GRID_K, GRID_SIGMA, GRID_NEST = 4096, 3, 0.05, 128          # config 4: 4096 x 4096 grid, kx=ky=3
 PARCUR_B, PARCUR_M, PARCUR_IDIM = 1 << 19, 256, 2                   # parametric curves
+PERCUR_B, PERCUR_M = 1 << 18, 256                                   # periodic curves
 # DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum,
 # profiles/r01_final_kernels.md, profiles/r01b_kernels.md); the bench itself never runs under ncu.
 NCU_FIT_DRAM_BYTES_PER_FIT = 8.1 * (6.558e9 + 1.593e9) / 2.5e5 + (51.47e9 + 10.02e9) / (0.94 * 262144)
@@ -59,6 +60,7 @@ def parse():
     ap.add_argument("--no-shared", action="store_true")
     ap.add_argument("--no-regrid", action="store_true")
     ap.add_argument("--no-parcur", action="store_true")
+    ap.add_argument("--no-percur", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -538,6 +540,62 @@ def main():
         del xp_, rp, xev, ud
         torch.cuda.empty_cache()
 
+    # ---------------------------------------------------------------- periodic curves
+    perc = None
+    if not args.no_percur:
+        torch.cuda.empty_cache()
+        f64 = torch.float64
+        Bq, mq, kq, sigq = PERCUR_B, PERCUR_M, 3, 0.1
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(31 + rank)
+        xq = torch.sort(torch.rand((mq, Bq), generator=gq, device=dev, dtype=f64) * 6.283185307179586, dim=0).values
+        xq = (xq + torch.arange(mq, device=dev, dtype=f64)[:, None] * 1e-9).contiguous()
+        frq = torch.randint(1, 4, (1, Bq), generator=gq, device=dev).to(f64)
+        yq = ((0.5 + 1.5 * torch.rand((1, Bq), generator=gq, device=dev, dtype=f64))
+              * torch.sin(frq * xq + 6.0 * torch.rand((1, Bq), generator=gq, device=dev, dtype=f64))
+              + sigq * torch.randn((mq, Bq), generator=gq, device=dev, dtype=f64)).contiguous()
+        sq_ = mq * sigq * sigq
+        nestq = mq + 2 * kq
+        for _ in range(max(1, min(args.warmup, 2))):
+            rq = eng.percur_batch(xq, yq, None, k=kq, s=sq_, nest=nestq)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            rq = eng.percur_batch(xq, yq, None, k=kq, s=sq_, nest=nestq)
+        ev1.record()
+        barrier()
+        q_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        nq = rq["n"].to(f64)
+        qbytes = Bq * (2 * 8.0 * mq + 16.0 * float(nq.mean().item()) + 16)
+        perc = {
+            "config": {"workload": "batched periodic smoothing fit percur: %d curves x %d points per GPU, k=3, "
+                                   "s=m*sigma^2=%.2f, nest=%d" % (Bq, mq, sq_, nestq)},
+            "value": world * Bq / (q_ms * 1e-3), "unit": "fits/s", "ms_per_step": q_ms,
+            "success_fraction": float((rq["ier"] <= 0).to(f64).mean().item()),
+            "mean_n": float(nq.mean().item()), "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "kernel": "percur_kernel<3> (one thread per curve, whole fpperi): FP64 "
+                         "issue/latency bound, lanes idle behind the slowest curve of a warp; HBM fraction "
+                         "small by construction", "achieved": qbytes / (q_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": qbytes / (q_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_fit": qbytes / Bq}}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            import oracle_lib as O
+            nthr_ = host_threads()
+            ns_ = 8192
+            xh_ = np.ascontiguousarray(xq[:, :ns_].t().cpu().numpy())
+            yh_ = np.ascontiguousarray(yq[:, :ns_].t().cpu().numpy())
+            t0 = time.perf_counter()
+            oq = O.percur_batch(0, xh_, yh_, None, kq, sq_, nestq, nthreads=nthr_)
+            dtq = time.perf_counter() - t0
+            same = bool(np.array_equal(oq["n"], rq["n"][:ns_].cpu().numpy())
+                        and np.array_equal(oq["fp"], rq["fp"][:ns_].cpu().numpy()))
+            perc["cpu_baseline"] = {"value": ns_ / dtq, "unit": "fits/s", "cores": nthr_, "kind": "port",
+                                    "sample": "first %d curves of the same batch, oracle port of percur/fpperi, "
+                                              "OpenMP over curves; n and fp bit-identical to the GPU result: %s"
+                                              % (ns_, same)}
+        del xq, yq, rq
+        torch.cuda.empty_cache()
+
     # ---------------------------------------------------------------- gridded surface (configs 4, 5b)
     grid = None
     if not args.no_regrid:
@@ -678,7 +736,7 @@ def main():
                              % (2 * B * M * 8 / 1e9),
                        "success_fraction": ok_frac, "gathered_summary_curves": gathered},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "fp64": fp64, "splev": splev, "shared_lsq": shared, "parcur": parc, "regrid": grid,
+            "roofline": roof, "fp64": fp64, "splev": splev, "shared_lsq": shared, "parcur": parc, "percur": perc, "regrid": grid,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

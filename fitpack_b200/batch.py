@@ -204,6 +204,32 @@ class Engine:
         check(rc, "fp_curev_batch_dev_c")
         return x, ier
 
+    def percur_batch(self, x, y, w=None, k=3, s=0.0, nest=None, iopt=0, n=None, t=None, fpint=None,
+                     nrdata=None):
+        """Batched percur on device tensors, point-major: x, y, w are [m][B].  Returns dict(n, t, c,
+        fp, ier) (t, c: [B][nest]); evaluate with splev_batch."""
+        _chk_f64(x, "x"); _chk_f64(y, "y"); _chk_f64(w, "w")
+        m, B = y.shape
+        dev = y.device
+        f64, i32 = torch.float64, torch.int32
+        nest = int(nest if nest is not None else m + 2 * k)
+        if torch.is_tensor(s):
+            s_t, s_stride = s.to(device=dev, dtype=f64).contiguous(), 1
+        else:
+            s_t, s_stride = torch.full((1,), float(s), device=dev, dtype=f64), 0
+        n_t = n if n is not None else torch.zeros(B, device=dev, dtype=i32)
+        t_t = t if t is not None else torch.zeros((B, nest), device=dev, dtype=f64)
+        c_t = torch.zeros((B, nest), device=dev, dtype=f64)
+        fp_t = torch.zeros(B, device=dev, dtype=f64)
+        ier_t = torch.zeros(B, device=dev, dtype=i32)
+        self.use_torch_stream()
+        rc = lib().fp_percur_batch_dev_c(
+            self._h, B, int(iopt), m, _ptr(x), 1, x.stride(0), _ptr(y), 1, y.stride(0), _ptr(w), 1,
+            0 if w is None else w.stride(0), int(k), _ptr(s_t), s_stride, nest, _ptr(n_t), _ptr(t_t),
+            _ptr(c_t), _ptr(fp_t), _ptr(ier_t), _ptr(fpint), _ptr(nrdata))
+        check(rc, "fp_percur_batch_dev_c")
+        return dict(n=n_t, t=t_t, c=c_t, fp=fp_t, ier=ier_t, _keep=(s_t,))
+
     def curfit_shared(self, x, y, t, k=3, w=None, xb=None, xe=None, layout="point_major",
                       out=None, mode=0):
         """Shared-abscissa least squares (iopt=-1): x [m], t [n] (interior knots in place),
