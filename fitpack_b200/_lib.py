@@ -42,6 +42,9 @@ SYMBOLS = {
     "fitpack_curve_c_get_c": (_I32, [_VP, _I32, _VP]),
     "fitpack_curve_c_set_knots": (_I32, [_VP, _I32, _VP]),
     "fitpack_curve_c_iopt": (_I32, [_VP]),
+    "fitpack_curve_c_comm_size": (_I32, [_VP]),
+    "fitpack_curve_c_comm_pack": (None, [_VP, _VP]),
+    "fitpack_curve_c_comm_expand": (None, [_VP, _VP]),
     "fpb_engine_create": (_I32, [_I32, C.POINTER(_VP)]),
     "fpb_engine_destroy": (None, [_VP]),
     "fpb_engine_set_stream": (_I32, [_VP, _VP]),

@@ -100,6 +100,7 @@ struct Curve {
     int bc = FPB_OUTSIDE_NEAREST_BND;
     int knots = 0;
     std::vector<double> t;
+    std::vector<double> wrk_fou;  // (nest,2) workspace of fourier_coefficients, :71, :259
 
     void destroy()  // fitpack_curves.f90:182-201 + fitter_destroy_base
     {
@@ -138,6 +139,7 @@ struct Curve {
         c.assign(nest, 0.0);
         lwrk = m * (kMaxK + 1) + nest * (8 + 5 * kMaxK);
         wrk.assign(lwrk, 0.0);
+        wrk_fou.assign(static_cast<size_t>(nest) * 2, 0.0);
     }
 
     // curve_fit_automatic_knots, fitpack_curves.f90:431-488
@@ -207,9 +209,175 @@ Curve *ensure(fitpack_curve_c *h)
     return static_cast<Curve *>(h->cptr);
 }
 
+
+// ---- comm wire format (fitter_core_comm_* src/fitpack_fitters.f90:105-147, curve_comm_*
+// src/fitpack_curves.f90:821-895, FP_*_COMM_* core:18654-18956): a flat array of doubles;
+// scalars stored as doubles; every array = header (one double per dimension holding the
+// lower/upper bound as two int32, or -99999999 twice when not allocated) + raw payload
+// (int32 payloads padded to a whole double).  An empty vector here = "not allocated".
+constexpr int32_t kNotAlloc = -99999999;  // FP_NOT_ALLOC, core:34
+
+size_t comm_size_r(const std::vector<double> &a, int rank = 1) { return rank + a.size(); }
+size_t comm_size_i(const std::vector<int> &a) { return 1 + (a.size() + 1) / 2; }
+
+double *pack_bounds(double *buf, int32_t lo, int32_t hi)
+{
+    const int32_t b[2] = {lo, hi};
+    std::memcpy(buf, b, sizeof b);
+    return buf + 1;
+}
+
+double *pack_r(double *buf, const std::vector<double> &a)
+{
+    if (a.empty()) return pack_bounds(buf, kNotAlloc, kNotAlloc);
+    buf = pack_bounds(buf, 1, static_cast<int32_t>(a.size()));
+    std::memcpy(buf, a.data(), a.size() * sizeof(double));
+    return buf + a.size();
+}
+
+double *pack_r2(double *buf, const std::vector<double> &a, int rows)  // (rows, size/rows), column-major
+{
+    if (a.empty() || rows <= 0) return pack_bounds(pack_bounds(buf, kNotAlloc, kNotAlloc), kNotAlloc, kNotAlloc);
+    buf = pack_bounds(buf, 1, rows);
+    buf = pack_bounds(buf, 1, static_cast<int32_t>(a.size() / rows));
+    std::memcpy(buf, a.data(), a.size() * sizeof(double));
+    return buf + a.size();
+}
+
+double *pack_i(double *buf, const std::vector<int> &a)
+{
+    if (a.empty()) return pack_bounds(buf, kNotAlloc, kNotAlloc);
+    buf = pack_bounds(buf, 1, static_cast<int32_t>(a.size()));
+    const size_t nd = (a.size() + 1) / 2;
+    std::memset(buf, 0, nd * sizeof(double));
+    std::memcpy(buf, a.data(), a.size() * sizeof(int));
+    return buf + nd;
+}
+
+const double *expand_bounds(const double *buf, int32_t &lo, int32_t &hi)
+{
+    int32_t b[2];
+    std::memcpy(b, buf, sizeof b);
+    lo = b[0];
+    hi = b[1];
+    return buf + 1;
+}
+
+const double *expand_r(const double *buf, std::vector<double> &a)
+{
+    int32_t lo, hi;
+    buf = expand_bounds(buf, lo, hi);
+    a.clear();
+    if (lo == kNotAlloc || hi == kNotAlloc) return buf;
+    const size_t n = hi >= lo ? static_cast<size_t>(hi - lo + 1) : 0;
+    a.assign(buf, buf + n);
+    return buf + n;
+}
+
+const double *expand_r2(const double *buf, std::vector<double> &a)
+{
+    int32_t lo1, hi1, lo2, hi2;
+    buf = expand_bounds(buf, lo1, hi1);
+    buf = expand_bounds(buf, lo2, hi2);
+    a.clear();
+    if (lo1 == kNotAlloc || hi1 == kNotAlloc || lo2 == kNotAlloc || hi2 == kNotAlloc) return buf;
+    const size_t n = static_cast<size_t>(std::max(hi1 - lo1 + 1, 0)) * static_cast<size_t>(std::max(hi2 - lo2 + 1, 0));
+    a.assign(buf, buf + n);
+    return buf + n;
+}
+
+const double *expand_i(const double *buf, std::vector<int> &a)
+{
+    int32_t lo, hi;
+    buf = expand_bounds(buf, lo, hi);
+    a.clear();
+    if (lo == kNotAlloc || hi == kNotAlloc) return buf;
+    const size_t n = hi >= lo ? static_cast<size_t>(hi - lo + 1) : 0;
+    a.resize(n);
+    std::memcpy(a.data(), buf, n * sizeof(int));
+    return buf + (n + 1) / 2;
+}
+
+size_t curve_comm_size(const Curve &cv)
+{
+    return 5 + comm_size_r(cv.c) + comm_size_r(cv.wrk) + comm_size_i(cv.iwrk) + 7 + comm_size_r(cv.x) +
+           comm_size_r(cv.y) + comm_size_r(cv.sp) + comm_size_r(cv.w) + comm_size_r(cv.t) +
+           comm_size_r(cv.wrk_fou, 2);
+}
+
+void curve_comm_pack(const Curve &cv, double *buf)
+{
+    *buf++ = static_cast<double>(cv.iopt);
+    *buf++ = cv.smoothing;
+    *buf++ = cv.fp;
+    *buf++ = static_cast<double>(cv.lwrk);
+    *buf++ = static_cast<double>(cv.liwrk);
+    buf = pack_r(buf, cv.c);
+    buf = pack_r(buf, cv.wrk);
+    buf = pack_i(buf, cv.iwrk);
+    *buf++ = static_cast<double>(cv.m);
+    *buf++ = static_cast<double>(cv.order);
+    *buf++ = static_cast<double>(cv.knots);
+    *buf++ = static_cast<double>(cv.bc);
+    *buf++ = static_cast<double>(cv.nest);
+    *buf++ = cv.xleft;
+    *buf++ = cv.xright;
+    buf = pack_r(buf, cv.x);
+    buf = pack_r(buf, cv.y);
+    buf = pack_r(buf, cv.sp);
+    buf = pack_r(buf, cv.w);
+    buf = pack_r(buf, cv.t);
+    pack_r2(buf, cv.wrk_fou, cv.nest);
+}
+
+void curve_comm_expand(Curve &cv, const double *buf)
+{
+    cv.iopt = static_cast<int>(std::lround(*buf++));
+    cv.smoothing = *buf++;
+    cv.fp = *buf++;
+    cv.lwrk = static_cast<int>(std::lround(*buf++));
+    cv.liwrk = static_cast<int>(std::lround(*buf++));
+    buf = expand_r(buf, cv.c);
+    buf = expand_r(buf, cv.wrk);
+    buf = expand_i(buf, cv.iwrk);
+    cv.m = static_cast<int>(std::lround(*buf++));
+    cv.order = static_cast<int>(std::lround(*buf++));
+    cv.knots = static_cast<int>(std::lround(*buf++));
+    cv.bc = static_cast<int>(std::lround(*buf++));
+    cv.nest = static_cast<int>(std::lround(*buf++));
+    cv.xleft = *buf++;
+    cv.xright = *buf++;
+    buf = expand_r(buf, cv.x);
+    buf = expand_r(buf, cv.y);
+    buf = expand_r(buf, cv.sp);
+    buf = expand_r(buf, cv.w);
+    buf = expand_r(buf, cv.t);
+    expand_r2(buf, cv.wrk_fou);
+}
+
 }  // namespace
 
 extern "C" {
+
+// comm_size / comm_pack / comm_expand of type(fitpack_curve) (src/fitpack_curves.f90:821-895): the
+// buffers are interchangeable with the ones the reference's Fortran objects produce
+FP_SIZE fitpack_curve_c_comm_size(fitpack_curve_c *self)
+{
+    Curve *cv = ensure(self);
+    return cv ? static_cast<FP_SIZE>(curve_comm_size(*cv)) : 0;
+}
+
+void fitpack_curve_c_comm_pack(fitpack_curve_c *self, FP_REAL *buffer)
+{
+    Curve *cv = ensure(self);
+    if (cv && buffer) curve_comm_pack(*cv, buffer);
+}
+
+void fitpack_curve_c_comm_expand(fitpack_curve_c *self, const FP_REAL *buffer)
+{
+    Curve *cv = ensure(self);
+    if (cv && buffer) curve_comm_expand(*cv, buffer);
+}
 
 void fitpack_curve_c_allocate(fitpack_curve_c *self) { (void)ensure(self); }
 

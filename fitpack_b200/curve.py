@@ -112,6 +112,19 @@ class FitpackCurve:
         """curve%integral(from, to)  (splint)"""
         return lib().fitpack_curve_c_integral(C.addressof(self._h), float(a), float(b))
 
+    # parallel communication (curve%comm_size / comm_pack / comm_expand, fitpack_curves.f90:821-895)
+    def comm_size(self):
+        return lib().fitpack_curve_c_comm_size(C.addressof(self._h))
+
+    def comm_pack(self):
+        buf = np.zeros(self.comm_size())
+        lib().fitpack_curve_c_comm_pack(C.addressof(self._h), buf.ctypes.data)
+        return buf
+
+    def comm_expand(self, buffer):
+        buffer = _f64(buffer)
+        lib().fitpack_curve_c_comm_expand(C.addressof(self._h), buffer.ctypes.data)
+
     # accessors (public components of the Fortran type)
     def smoothing(self):
         return lib().fitpack_curve_c_smoothing(C.addressof(self._h))

@@ -125,6 +125,14 @@ FP_SIZE fitpack_curve_c_get_t        (fitpack_curve_c *self, FP_SIZE nmax, FP_RE
 FP_SIZE fitpack_curve_c_get_c        (fitpack_curve_c *self, FP_SIZE nmax, FP_REAL *c);
 FP_SIZE fitpack_curve_c_set_knots    (fitpack_curve_c *self, FP_SIZE n, const FP_REAL *t);
 FP_FLAG fitpack_curve_c_iopt         (fitpack_curve_c *self);
+/* comm_size / comm_pack / comm_expand of type(fitpack_curve) (src/fitpack_curves.f90:821-895,
+   src/fitpack_fitters.f90:105-147, wire helpers core:18654-18956): a fitted curve as a flat array of
+   FP_REAL, same wire format as the reference (scalars as doubles; arrays = bounds header packed as
+   two int32 per dimension, -99999999 when not allocated, + raw payload), so a buffer produced by
+   either side expands on the other -- the shipping format for fitted batches between ranks. */
+FP_SIZE fitpack_curve_c_comm_size    (fitpack_curve_c *self);
+void    fitpack_curve_c_comm_pack    (fitpack_curve_c *self, FP_REAL *buffer);
+void    fitpack_curve_c_comm_expand  (fitpack_curve_c *self, const FP_REAL *buffer);
 
 /* ------------------------------------------------------------------ (C) -- */
 typedef struct fpb_engine fpb_engine;   /* one per GPU: stream + workspace   */

@@ -1003,3 +1003,27 @@ def test_percur_batch_bit_exact_vs_oracle(F, k, weights, m):
             assert _same(rg["t"][b, :n], ro["t"][b, :n]), (s, b)
             assert _same(rg["c"][b, :n - k - 1], ro["c"][b, :n - k - 1]), (s, b)
         assert set(np.unique(ro["ier"])) <= {0, -1, -2, 1, 2, 3}
+
+
+def test_curve_comm_roundtrip_fitted():
+    """reference test_curve_comm_roundtrip (test/fitpack_curve_tests.f90:1342-1432): a fitted curve
+    packed into the comm buffer and expanded into a fresh object evaluates identically, keeps
+    knots / mse / smoothing, and continues fitting (iopt=1 state travels in wrk/iwrk)."""
+    from fitpack_b200.curve import FitpackCurve
+    rng = np.random.default_rng(11)
+    x = np.sort(rng.uniform(0, 2 * np.pi, 80))
+    y = np.sin(x) + 0.05 * rng.standard_normal(80)
+    a = FitpackCurve()
+    assert a.new_fit(x, y, smoothing=0.5) <= 0
+    buf = a.comm_pack()
+    assert buf.size == a.comm_size()
+    b = FitpackCurve()
+    b.comm_expand(buf)
+    xe = np.linspace(0, 2 * np.pi, 101)
+    ya, ia = a.eval(xe)
+    yb, ib = b.eval(xe)
+    assert ia == ib == 0 and _same(ya, yb)
+    assert b.knots == a.knots and b.mse() == a.mse() and b.smoothing() == a.smoothing() and b.iopt == a.iopt
+    assert _same(a.t, b.t) and _same(a.c, b.c)
+    assert a.fit(smoothing=0.2) <= 0 and b.fit(smoothing=0.2) <= 0   # continuation from the shipped state
+    assert a.knots == b.knots and a.mse() == b.mse() and _same(a.c, b.c)
