@@ -1035,7 +1035,7 @@ __global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K, IDIM))
 }
 
 template <int K, bool HAS_W, int IDIM>
-__global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K, IDIM))
+__global__ void __launch_bounds__(kFitThreads, fit_p2_blocks_per_sm(K, IDIM))
     curfit_part2_kernel(FitParams p, const int *__restrict__ list, const int *count_ptr)
 {
     extern __shared__ double fit_smem[];
@@ -1218,7 +1218,14 @@ FitLayout fit_layout(int m, int k, int nest, int idim)
 
 int fit_max_resident_warps(int k, int idim, int nsm)
 {
-    return nsm * fit_blocks_per_sm(k, idim_class(idim)) * (kFitThreads / 32);
+    const int c = idim_class(idim);
+    return nsm * (fit_blocks_per_sm(k, c) > fit_p2_blocks_per_sm(k, c) ? fit_blocks_per_sm(k, c) : fit_p2_blocks_per_sm(k, c)) *
+           (kFitThreads / 32);
+}
+
+int fit_p2_resident_warps(int k, int idim, int nsm)
+{
+    return nsm * fit_p2_blocks_per_sm(k, idim_class(idim)) * (kFitThreads / 32);
 }
 
 cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t stream,

@@ -266,9 +266,14 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     int *n = p.n;
     const FitLayout L = fit_layout(m, k, nest, p.idim);
     long long blocks_needed = ((long long)nbatch + kFitThreads - 1) / kFitThreads;
+    // the workspace is sized for the larger of the two kernels' resident grids
     const int max_warps = fit_max_resident_warps(k, p.idim, eng->nsm);
-    long long grid = std::min<long long>(blocks_needed, max_warps / (kFitThreads / 32));
-    const size_t warps = (size_t)grid * (kFitThreads / 32);
+    const long long grid_ws = std::min<long long>(blocks_needed, max_warps / (kFitThreads / 32));
+    long long grid = std::min<long long>(blocks_needed,
+                                         (long long)eng->nsm * fit_blocks_per_sm(k, idim_class(p.idim)));
+    const long long grid_p2 = std::min<long long>(blocks_needed, fit_p2_resident_warps(k, p.idim, eng->nsm) /
+                                                                     (kFitThreads / 32));
+    const size_t warps = (size_t)grid_ws * (kFitThreads / 32);
     const size_t nb = (size_t)nbatch;
     // counters: [0] tile queue head, [4] list A count, [5] list B count, [6] part-2 count
     const size_t hist_off = 64;  // ints
@@ -346,7 +351,7 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
                 !cuda_ok(cudaMemsetAsync(cnt, 0, sizeof(int), st), "memset"))
                 return FPB_ERR_CUDA;
             eng->launches += 2;
-            long long g2 = std::min<long long>(grid, ((long long)n2 + kFitThreads - 1) / kFitThreads);
+            long long g2 = std::min<long long>(grid_p2, ((long long)n2 + kFitThreads - 1) / kFitThreads);
             if (!cuda_ok(launch_curfit_part2(p, (int)g2, st, p2_sorted, p2_count), "curfit part-2 kernel"))
                 return FPB_ERR_CUDA;
             eng->launches++;

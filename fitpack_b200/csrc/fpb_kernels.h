@@ -20,6 +20,15 @@ constexpr int fit_blocks_per_sm(int k, int idim_cls = 1)
          : idim_cls == 0 ? 2
                          : (k <= 3 ? 4 : 3);
 }
+// the part-2 kernel (smoothing-parameter iteration: one long dependent rotation chain per curve) may
+// be compiled for a different number of resident CTAs than the pass kernel
+#ifndef FPB_FIT_P2_BLOCKS_K3
+#define FPB_FIT_P2_BLOCKS_K3 FPB_FIT_BLOCKS_K3
+#endif
+constexpr int fit_p2_blocks_per_sm(int k, int idim_cls = 1)
+{
+    return (idim_cls == 1 && k <= 3) ? FPB_FIT_P2_BLOCKS_K3 : fit_blocks_per_sm(k, idim_cls);
+}
 // shared-memory band window: (k+1)^2 + (k+1)*idim doubles per thread
 constexpr unsigned fit_smem_bytes(int k, int idim = 1)
 {
@@ -34,6 +43,7 @@ struct FitLayout {
 };
 FitLayout fit_layout(int m, int k, int nest, int idim = 1);
 int fit_max_resident_warps(int k, int idim, int nsm);
+int fit_p2_resident_warps(int k, int idim, int nsm);
 
 struct FitParams {
     int nbatch, iopt, m, k, nest, nestp;
