@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -551,7 +553,7 @@ struct FitStage {
     std::vector<double> keep_t, keep_c;
 };
 
-int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, long long b0, long long b1, FP_SIZE iopt,
+int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long long b0, long long b1, FP_SIZE iopt,
                             FP_SIZE m, const FP_REAL *x, const FP_REAL *y, const FP_REAL *w,
                             FP_SIZE shared_x, const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k,
                             FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
@@ -570,15 +572,37 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, long long b0, long long
     }
     cudaStream_t st = eng->stream, s_in = eng->s_in, s_out = eng->s_out;
     const long long total = b1 - b0;
+    // FPB_HOST_TRACE=1: wall-clock timeline of the staging pipeline on stderr (tuning aid)
+    static const bool trace = std::getenv("FPB_HOST_TRACE") != nullptr;
+    static const auto t_epoch = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what, long long ci) {
+        if (!trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_epoch).count();
+        std::fprintf(stderr, "[fpb host %p] %9.2f ms  chunk %lld  %s\n", (void *)eng, ms, ci, what);
+    };
     // bytes per curve on the device: x,y,w curve-major + point-major, outputs t,c (+state)
     const size_t per_curve = (size_t)m * 8 * 6 + (size_t)nest * 8 * 2 + (size_t)nest * 12 + 64;
     long long chunk = (long long)(((size_t)6 << 30) / per_curve);  // <= 6 GB per staging set
+    const long long cap = std::max<long long>(chunk - chunk % 128, 128);
     if (nsplit > 1) chunk = std::min(chunk, std::max<long long>((total + nsplit - 1) / nsplit, 65536));
     chunk = std::max<long long>(chunk - chunk % 128, 128);
     const bool state = (fpint && nrdata);
     enum { XC, YC, WC, XP, YP, WP, TT, CC, NN, FP_, IER, AUX };
     FitStage stage[2];
-    const long long nchunks = (total + chunk - 1) / chunk;
+    // chunk boundaries; with exactly two chunks the first one may be smaller (first_frac of the
+    // slice): its host->device transfer is what the GPU has to wait for before it can start
+    std::vector<long long> cuts;
+    cuts.push_back(0);
+    if (nsplit == 2 && first_frac > 0.0 && first_frac < 1.0 && total >= 2 * 65536) {
+        long long c1 = (long long)(first_frac * (double)total);
+        c1 = std::max<long long>(65536, c1 - c1 % 128);
+        if (c1 < total && total - c1 <= cap) {
+            cuts.push_back(c1);
+            chunk = total - c1;
+        }
+    }
+    while (cuts.back() < total) cuts.push_back(std::min(total, cuts.back() + chunk));
+    const long long nchunks = (long long)cuts.size() - 1;
     auto bufs = [&](int set) { return set ? eng->scratch2 : eng->scratch; };
 
     auto copy_in = [&](int set, long long c0, long long nb) -> int32_t {
@@ -650,6 +674,7 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, long long b0, long long
         FitStage &S = stage[set];
         if (!S.pending) return true;
         if (!cuda_ok(cudaStreamSynchronize(s_out), "sync")) return false;
+        stamp("t/c copied out (stage retired)", S.c0);
         for (size_t i = 0; i < S.bad.size(); ++i) {
             std::memcpy(t + (size_t)(S.c0 + S.bad[i]) * nest, &S.keep_t[i * S.nmax_used],
                         (size_t)S.nmax_used * 8);
@@ -661,22 +686,26 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, long long b0, long long
     };
 
     if (nchunks > 0) {
-        const int32_t rc = copy_in(0, b0, std::min(chunk, total));
+        const int32_t rc = copy_in(0, b0, cuts[1] - cuts[0]);
         if (rc != FPB_STATUS_OK) return rc;
     }
     for (long long ci = 0; ci < nchunks; ++ci) {
         const int set = (int)(ci & 1);
-        const long long c0 = b0 + ci * chunk;
-        const long long nb = std::min(chunk, b1 - c0);
+        const long long c0 = b0 + cuts[ci];
+        const long long nb = cuts[ci + 1] - cuts[ci];
         DevBuf *B = bufs(set);
         // prefetch the next chunk into the other staging set while this one is fitted
         if (ci + 1 < nchunks) {
-            const long long c1 = c0 + chunk;
+            const long long c1 = b0 + cuts[ci + 1];
             if (!retire(1 - set)) return FPB_ERR_CUDA;
-            const int32_t rc = copy_in(1 - set, c1, std::min(chunk, b1 - c1));
+            const int32_t rc = copy_in(1 - set, c1, cuts[ci + 2] - cuts[ci + 1]);
             if (rc != FPB_STATUS_OK) return rc;
         }
         double *aux = B[AUX].as<double>();
+        if (trace) {
+            cudaEventSynchronize(eng->ev_in[set]);
+            stamp("inputs on device", ci);
+        }
         bool ok = cuda_ok(cudaStreamWaitEvent(st, eng->ev_in[set], 0), "wait");
         const double *dx, *dw = nullptr;
         long long x_sb, x_si, w_sb = 0, w_si = 0;
@@ -719,6 +748,7 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, long long b0, long long
         ok = ok && cuda_ok(cudaMemcpyAsync(ier + c0, B[IER].ptr, (size_t)nb * 4,
                                            cudaMemcpyDeviceToHost, st), "D2H ier");
         if (!ok || !cuda_ok(cudaStreamSynchronize(st), "sync")) return FPB_ERR_CUDA;
+        stamp("fit done, n/fp/ier on host", ci);
         // knots/coefficients: only the leading max(n) columns carry information
         FitStage &S = stage[set];
         S.c0 = c0;
@@ -793,11 +823,11 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     if (const char *e = std::getenv("FPB_HOST_WORKERS")) workers = std::max(1, std::min(2, std::atoi(e)));
     if (const char *e = std::getenv("FPB_HOST_CHUNKS")) nsplit = std::max(1, std::atoi(e));
     if (total < 4 * 65536) {
-        return fit_slice_pipelined(e0, 1, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest, n, t,
+        return fit_slice_pipelined(e0, 1, 0.0, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest, n, t,
                                    c, fp, ier, fpint, nrdata);
     }
     if (workers == 1) {
-        return fit_slice_pipelined(e0, 2 * nsplit, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s,
+        return fit_slice_pipelined(e0, 2 * nsplit, 0.0, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s,
                                    nest, n, t, c, fp, ier, fpint, nrdata);
     }
     fpb_engine *e1 = default_engine(device + 32);  // second engine of the same device
@@ -808,9 +838,13 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     std::thread th[2];
     fpb_engine *eng2[2] = {e0, e1};
     const long long lo[2] = {b0, b0 + half}, hi[2] = {b0 + half, b1};
+    // first-chunk fraction of each worker's slice (0.5 = equal halves)
+    double frac[2] = {0.5, 0.5};
+    if (const char *e = std::getenv("FPB_HOST_FIRST_FRAC")) frac[0] = std::atof(e);
+    if (const char *e = std::getenv("FPB_HOST_FIRST_FRAC1")) frac[1] = std::atof(e);
     for (int wk = 0; wk < 2; ++wk) {
         th[wk] = std::thread([&, wk]() {
-            rc[wk] = fit_slice_pipelined(eng2[wk], nsplit, lo[wk], hi[wk], iopt, m, x, y, w, shared_x,
+            rc[wk] = fit_slice_pipelined(eng2[wk], nsplit, frac[wk], lo[wk], hi[wk], iopt, m, x, y, w, shared_x,
                                          xb, xe, k, s, nest, n, t, c, fp, ier, fpint, nrdata);
             if (rc[wk] != FPB_STATUS_OK) err[wk] = fpb_last_error();
         });
