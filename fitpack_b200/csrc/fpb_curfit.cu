@@ -1193,11 +1193,12 @@ cudaError_t FPB_CAT(launch_curfit_part2_d, FPB_FIT_IDIM)(const FitParams &p, int
 }
 
 #if FPB_FIT_IDIM == 1
-FitLayout fit_layout(int m, int k, int nest, int idim)
+FitLayout fit_layout(int m, int k, int nest, int idim, int periodic)
 {
     const int k1 = k + 1, k2 = k + 2;
     FitLayout L;
-    int nestp = nest < m + k1 ? nest : m + k1;
+    const int ncap = periodic ? m + 2 * k : m + k1;  // knots a curve can reach (interpolation)
+    int nestp = nest < ncap ? nest : ncap;
     if (nestp < 2 * k1) nestp = 2 * k1;
     L.nestp = nestp;
     int off = 0;
@@ -1212,6 +1213,8 @@ FitLayout fit_layout(int m, int k, int nest, int idim)
     L.off_x = off; off += m;   // part 2: the curve's own data, gathered once
     L.off_y = off; off += m * idim;
     L.off_w = off; off += m;
+    L.off_a2 = off; off += periodic ? nestp * k : 0;
+    L.off_g2 = off; off += periodic ? nestp * k1 : 0;
     L.ws_per_lane = off;
     return L;
 }
@@ -1232,6 +1235,8 @@ cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t
                                const int *in_list, const int *in_count, int *out_list,
                                int *out_count, int *p2_list, int *p2_count, int first)
 {
+    if (p.periodic)
+        return launch_percur_pass(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first);
     switch (idim_class(p.idim)) {
     case 1: return launch_curfit_pass_d1(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first);
     case 2: return launch_curfit_pass_d2(p, grid_blocks, stream, in_list, in_count, out_list, out_count, p2_list, p2_count, first);
@@ -1243,6 +1248,7 @@ cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t
 cudaError_t launch_curfit_part2(const FitParams &p, int grid_blocks, cudaStream_t stream,
                                 const int *list, const int *count)
 {
+    if (p.periodic) return launch_percur_part2(p, grid_blocks, stream, list, count);
     switch (idim_class(p.idim)) {
     case 1: return launch_curfit_part2_d1(p, grid_blocks, stream, list, count);
     case 2: return launch_curfit_part2_d2(p, grid_blocks, stream, list, count);

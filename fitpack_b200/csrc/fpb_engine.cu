@@ -266,15 +266,16 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
 {
     const int nbatch = p.nbatch, iopt = p.iopt, m = p.m, k = p.k, nest = p.nest;
     int *n = p.n;
-    const FitLayout L = fit_layout(m, k, nest, p.idim);
+    const FitLayout L = fit_layout(m, k, nest, p.idim, p.periodic);
     long long blocks_needed = ((long long)nbatch + kFitThreads - 1) / kFitThreads;
     // the workspace is sized for the larger of the two kernels' resident grids
-    const int max_warps = fit_max_resident_warps(k, p.idim, eng->nsm);
+    const int max_warps = p.periodic ? percur_resident_warps(eng->nsm) : fit_max_resident_warps(k, p.idim, eng->nsm);
     const long long grid_ws = std::min<long long>(blocks_needed, max_warps / (kFitThreads / 32));
-    long long grid = std::min<long long>(blocks_needed,
-                                         (long long)eng->nsm * fit_blocks_per_sm(k, idim_class(p.idim)));
-    const long long grid_p2 = std::min<long long>(blocks_needed, fit_p2_resident_warps(k, p.idim, eng->nsm) /
-                                                                     (kFitThreads / 32));
+    long long grid = std::min<long long>(
+        blocks_needed, p.periodic ? (long long)max_warps / (kFitThreads / 32)
+                                  : (long long)eng->nsm * fit_blocks_per_sm(k, idim_class(p.idim)));
+    const long long grid_p2 = std::min<long long>(
+        blocks_needed, (p.periodic ? max_warps : fit_p2_resident_warps(k, p.idim, eng->nsm)) / (kFitThreads / 32));
     const size_t warps = (size_t)grid_ws * (kFitThreads / 32);
     const size_t nb = (size_t)nbatch;
     // counters: [0] tile queue head, [4] list A count, [5] list B count, [6] part-2 count
@@ -300,6 +301,7 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     p.off_t = L.off_t; p.off_c = L.off_c; p.off_z = L.off_z; p.off_fpint = L.off_fpint;
     p.off_a = L.off_a; p.off_g = L.off_g; p.off_b = L.off_b; p.off_q = L.off_q;
     p.off_x = L.off_x; p.off_y = L.off_y; p.off_w = L.off_w;
+    p.off_a2 = L.off_a2; p.off_g2 = L.off_g2;
     p.ws_per_lane = L.ws_per_lane;
     p.st_nplus = eng->st_i.as<int>(); p.st_iter = p.st_nplus + nb;
     p.st_fpold = eng->st_d.as<double>(); p.st_fp0 = p.st_fpold + nb;
@@ -406,7 +408,7 @@ int32_t fp_curfit_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_
     p.s = s; p.s_stride = s_stride;
     p.n = n; p.t = t; p.c = c; p.fp = fp; p.ier = ier;
     p.fpint = fpint; p.nrdata = nrdata; p.stats = stats;
-    p.idim = 1; p.par = 0; p.y_sd = 0; p.c_sb = nest;
+    p.idim = 1; p.par = 0; p.periodic = 0; p.y_sd = 0; p.c_sb = nest;
     return run_fit_pipeline(eng, p);
 }
 

@@ -39,9 +39,10 @@ constexpr unsigned fit_smem_bytes(int k, int idim = 1)
 struct FitLayout {
     int nestp;  // knots a curve can actually reach: min(nest, m+k+1)
     int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q, off_x, off_y, off_w;
+    int off_a2, off_g2;  // periodic fits: wrap-around column blocks (nestp x k, nestp x (k+1))
     int ws_per_lane;
 };
-FitLayout fit_layout(int m, int k, int nest, int idim = 1);
+FitLayout fit_layout(int m, int k, int nest, int idim = 1, int periodic = 0);
 int fit_max_resident_warps(int k, int idim, int nsm);
 int fit_p2_resident_warps(int k, int idim, int nsm);
 
@@ -49,6 +50,7 @@ struct FitParams {
     int nbatch, iopt, m, k, nest, nestp;
     int idim;               // coordinate curves per fit (1 for curfit)
     int par;                // 1: parcur/fppara semantics (checks, initial p, no zero-pivot skip)
+    int periodic;           // 1: percur/fpperi (fpb_percur.cu kernels, two-block factor)
     const double *x, *y, *w;  // x: abscissae / curve parameters u; y: ordinates / coordinates
     long long x_sb, x_si, y_sb, y_si, w_sb, w_si;
     long long y_sd;         // stride between the coordinates of one point in y
@@ -67,6 +69,7 @@ struct FitParams {
     int *wsi;               // [resident warps][nestp][32]   (nrdata)
     unsigned int *counter;  // tile queue head, zeroed before every launch
     int off_t, off_c, off_z, off_fpint, off_a, off_g, off_b, off_q, off_x, off_y, off_w, ws_per_lane;
+    int off_a2, off_g2;
     // per-curve state carried between passes (engine-owned)
     int *st_nplus, *st_iter;
     double *st_fpold, *st_fp0;
@@ -86,6 +89,13 @@ cudaError_t launch_curfit_part2(const FitParams &p, int grid_blocks, cudaStream_
                                          const int *list, const int *count);
 FPB_DECL_FIT_D(0) FPB_DECL_FIT_D(1) FPB_DECL_FIT_D(2) FPB_DECL_FIT_D(3)
 #undef FPB_DECL_FIT_D
+// periodic fits (fpb_percur.cu): same launch signatures as the curfit kernels
+cudaError_t launch_percur_pass(const FitParams &p, int grid, cudaStream_t st, const int *in_list,
+                               const int *in_count, int *out_list, int *out_count, int *p2_list,
+                               int *p2_count, int first);
+cudaError_t launch_percur_part2(const FitParams &p, int grid, cudaStream_t st, const int *list,
+                                const int *count);
+int percur_resident_warps(int nsm);
 // chord-length parameters of parcur (ipar = 0), one thread per curve
 cudaError_t launch_parcur_param(int nbatch, int m, int idim, const double *x, long long x_sb,
                                 long long x_si, long long x_sd, double *u, long long u_sb,
