@@ -41,7 +41,7 @@ SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
 SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 22, 512, 3, 28   # config 3 shape, 2^22 curves/GPU
 GRID_M, GRID_K, GRID_SIGMA, GRID_NEST = 4096, 3, 0.05, 128          # config 4: 4096 x 4096 grid, kx=ky=3
 PARCUR_B, PARCUR_M, PARCUR_IDIM = 1 << 19, 256, 2                   # parametric curves
-PERCUR_B, PERCUR_M = 1 << 18, 256                                   # periodic curves
+PERCUR_B, PERCUR_M = 1 << 20, 256                                   # periodic curves
 # DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum,
 # profiles/r01_final_kernels.md, profiles/r01b_kernels.md); the bench itself never runs under ncu.
 NCU_FIT_DRAM_BYTES_PER_FIT = 8.1 * (6.558e9 + 1.593e9) / 2.5e5 + (51.47e9 + 10.02e9) / (0.94 * 262144)
@@ -559,12 +559,14 @@ def main():
         for _ in range(max(1, min(args.warmup, 2))):
             rq = eng.percur_batch(xq, yq, None, k=kq, s=sq_, nest=nestq)
         barrier()
+        lq0 = eng.launches
         ev0.record()
         for _ in range(args.steps):
             rq = eng.percur_batch(xq, yq, None, k=kq, s=sq_, nest=nestq)
         ev1.record()
         barrier()
         q_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        q_launch = int(eng.launches - lq0)
         nq = rq["n"].to(f64)
         qbytes = Bq * (2 * 8.0 * mq + 16.0 * float(nq.mean().item()) + 16)
         perc = {
@@ -572,10 +574,10 @@ def main():
                                    "s=m*sigma^2=%.2f, nest=%d" % (Bq, mq, sq_, nestq)},
             "value": world * Bq / (q_ms * 1e-3), "unit": "fits/s", "ms_per_step": q_ms,
             "success_fraction": float((rq["ier"] <= 0).to(f64).mean().item()),
-            "mean_n": float(nq.mean().item()), "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "kernel": "percur_kernel<3> (one thread per curve, whole fpperi): FP64 "
-                         "issue/latency bound, lanes idle behind the slowest curve of a warp; HBM fraction "
-                         "small by construction", "achieved": qbytes / (q_ms * 1e-3) / 1e9, "peak": hbm_peak,
+            "mean_n": float(nq.mean().item()), "gpu_launches": q_launch,
+            "roofline": {"bound": "hbm", "kernel": "percur pipeline: percur_pass_kernel<3> x R + percur_part2_kernel<3> "
+                         "(one thread per curve, re-bucketed per knot set): FP64 issue/latency bound (two-block "
+                         "Givens chains), HBM fraction small by construction", "achieved": qbytes / (q_ms * 1e-3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": qbytes / (q_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_fit": qbytes / Bq}}
         if rank == 0 and world == 1 and not args.no_cpu:

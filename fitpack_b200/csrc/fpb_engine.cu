@@ -269,7 +269,7 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     const FitLayout L = fit_layout(m, k, nest, p.idim, p.periodic);
     long long blocks_needed = ((long long)nbatch + kFitThreads - 1) / kFitThreads;
     // the workspace is sized for the larger of the two kernels' resident grids
-    const int max_warps = p.periodic ? percur_resident_warps(eng->nsm) : fit_max_resident_warps(k, p.idim, eng->nsm);
+    const int max_warps = p.periodic ? percur_resident_warps(k, eng->nsm) : fit_max_resident_warps(k, p.idim, eng->nsm);
     const long long grid_ws = std::min<long long>(blocks_needed, max_warps / (kFitThreads / 32));
     long long grid = std::min<long long>(
         blocks_needed, p.periodic ? (long long)max_warps / (kFitThreads / 32)

@@ -95,7 +95,7 @@ cudaError_t launch_percur_pass(const FitParams &p, int grid, cudaStream_t st, co
                                int *p2_count, int first);
 cudaError_t launch_percur_part2(const FitParams &p, int grid, cudaStream_t st, const int *list,
                                 const int *count);
-int percur_resident_warps(int nsm);
+int percur_resident_warps(int k, int nsm);
 // chord-length parameters of parcur (ipar = 0), one thread per curve
 cudaError_t launch_parcur_param(int nbatch, int m, int idim, const double *x, long long x_sb,
                                 long long x_si, long long x_sd, double *u, long long u_sb,

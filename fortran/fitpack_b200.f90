@@ -24,7 +24,8 @@ module fitpack_b200
 
    public :: fp_curfit_c, fp_splev_c, fp_curfit_batch_c, fp_splev_batch_c
    public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c
-   public :: fp_parcur_c, fp_curev_c, fp_parcur_batch_c
+   public :: fp_parcur_c, fp_curev_c, fp_parcur_batch_c, fp_percur_c, fp_percur_batch_c
+   public :: fitpack_curve_c_comm_size, fitpack_curve_c_comm_pack, fitpack_curve_c_comm_expand
    public :: fp_curfit_batch_dev_c, fp_curfit_shared_dev_c, fp_splev_batch_dev_c
    public :: fpb_engine_create, fpb_engine_destroy, fpb_engine_synchronize, fpb_device_count
    public :: curfit_batch, splev_batch
@@ -114,6 +115,48 @@ module fitpack_b200
          real   (FP_REAL), intent(inout)     :: t(nest,nbatch),c(nest*idim,nbatch),fp(nbatch),fpint(nest,nbatch)
          integer(FP_FLAG), intent(out)       :: ier(nbatch)
       end function fp_parcur_batch_c
+
+      ! periodic curves: same interface as the reference's percur_c (src/fitpack_core_c.f90:77-87);
+      ! fp_percur_batch_c is the batch form (new)
+      subroutine fp_percur_c(iopt,m,x,y,w,k,s,nest,n,t,c,fp,wrk,lwrk,iwrk,ier) bind(C,name="fp_percur_c")
+         import
+         real   (FP_REAL), intent(in),    value :: s
+         real   (FP_REAL), intent(inout)        :: fp
+         integer(FP_SIZE), intent(inout)        :: n
+         integer(FP_FLAG), intent(inout)        :: ier
+         integer(FP_SIZE), intent(in),    value :: iopt,m,k,nest,lwrk
+         real   (FP_REAL), intent(in)           :: x(m),y(m),w(m)
+         real   (FP_REAL), intent(inout)        :: t(nest),c(nest),wrk(lwrk)
+         integer(FP_SIZE), intent(inout)        :: iwrk(nest)
+      end subroutine fp_percur_c
+
+      integer(c_int32_t) function fp_percur_batch_c(nbatch,iopt,m,x,y,w,k,s,nest,n,t,c,fp,ier,fpint,nrdata) &
+                                                    bind(C,name="fp_percur_batch_c")
+         import
+         integer(FP_SIZE), intent(in), value :: nbatch,iopt,m,k,nest
+         real   (FP_REAL), intent(in), value :: s
+         real   (FP_REAL), intent(in)        :: x(m,nbatch),y(m,nbatch),w(m,nbatch)
+         integer(FP_SIZE), intent(inout)     :: n(nbatch),nrdata(nest,nbatch)
+         real   (FP_REAL), intent(inout)     :: t(nest,nbatch),c(nest,nbatch),fp(nbatch),fpint(nest,nbatch)
+         integer(FP_FLAG), intent(out)       :: ier(nbatch)
+      end function fp_percur_batch_c
+
+      ! comm buffers of a curve handle, same wire format as curve%comm_pack / comm_expand
+      ! (src/fitpack_curves.f90:821-895): `self` is the type(c_ptr) wrapper struct of the handle ABI
+      integer(FP_SIZE) function fitpack_curve_c_comm_size(self) bind(C,name="fitpack_curve_c_comm_size")
+         import
+         type(c_ptr), intent(inout) :: self
+      end function fitpack_curve_c_comm_size
+      subroutine fitpack_curve_c_comm_pack(self,buffer) bind(C,name="fitpack_curve_c_comm_pack")
+         import
+         type(c_ptr), intent(inout) :: self
+         real(FP_REAL), intent(out) :: buffer(*)
+      end subroutine fitpack_curve_c_comm_pack
+      subroutine fitpack_curve_c_comm_expand(self,buffer) bind(C,name="fitpack_curve_c_comm_expand")
+         import
+         type(c_ptr), intent(inout) :: self
+         real(FP_REAL), intent(in)  :: buffer(*)
+      end subroutine fitpack_curve_c_comm_expand
 
       subroutine fp_splder_c(t,n,c,k,nu,x,y,m,e,wrk,ier) bind(C,name="fp_splder_c")
          import
