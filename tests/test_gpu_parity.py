@@ -1027,3 +1027,54 @@ def test_curve_comm_roundtrip_fitted():
     assert _same(a.t, b.t) and _same(a.c, b.c)
     assert a.fit(smoothing=0.2) <= 0 and b.fit(smoothing=0.2) <= 0   # continuation from the shipped state
     assert a.knots == b.knots and a.mse() == b.mse() and _same(a.c, b.c)
+
+
+def test_parcur_percur_batches_with_invalid_curves(F):
+    """A bad curve never aborts the batch: curves with non-increasing parameters / abscissae, zero
+    total length, non-positive weights get ier=10 (outputs untouched) and the others are fitted
+    exactly as if alone; nbatch = 0 and call-level argument errors behave like the reference."""
+    from refdata import synth_param_curves
+    rng = np.random.default_rng(77)
+    B, m, k = 257, 40, 3          # ragged: not a multiple of the warp size
+    th, x = synth_param_curves(rng, B, m, 2)
+    w = np.ones((B, m))
+    bad = [3, 64, 65, 200, 256]
+    x[3] = 0.0                    # zero total length (core:15248)
+    w[64, 7] = 0.0                # non-positive weight
+    w[65, 0] = -1.0
+    x[200, 10:12] = x[200, 9]     # repeated point -> u not strictly increasing
+    w[256, m - 1] = 0.0
+    nest, s = m + k + 1, m * 2 * 0.0025
+    ro = O.parcur_batch(0, 0, 2, x, w, k, s, nest)
+    rg = F.parcur_batch(0, 0, 2, x, w, k, s, nest)
+    assert _same(rg["ier"], ro["ier"]) and all(ro["ier"][b] == 10 for b in bad)
+    good = ro["ier"] != 10
+    assert good.sum() == B - len(bad)
+    assert _same(rg["n"][good], ro["n"][good]) and _same(rg["fp"][good], ro["fp"][good])
+    for b in np.nonzero(good)[0]:
+        n = ro["n"][b]
+        assert _same(rg["t"][b, :n], ro["t"][b, :n]), b
+        for d in range(2):
+            assert _same(rg["c"][b, d * n:d * n + n - k - 1], ro["c"][b, d * n:d * n + n - k - 1]), (b, d)
+    # periodic
+    xs = np.sort(rng.uniform(0, 6, (B, m)), axis=1) + np.arange(m)[None, :] * 1e-9
+    ys = np.sin(xs) + 0.1 * rng.standard_normal((B, m))
+    wp = np.ones((B, m))
+    xs[5, 20] = xs[5, 19]         # not strictly increasing
+    wp[100, 3] = 0.0
+    wp[101, m - 1] = -5.0         # the last weight is never looked at (core:15817)
+    ro = O.percur_batch(0, xs, ys, wp, k, m * 0.01, m + 2 * k)
+    rg = F.percur_batch(0, xs, ys, wp, k, m * 0.01, m + 2 * k)
+    assert _same(rg["ier"], ro["ier"]) and ro["ier"][5] == 10 and ro["ier"][100] == 10 and ro["ier"][101] != 10
+    good = ro["ier"] != 10
+    assert _same(rg["n"][good], ro["n"][good]) and _same(rg["fp"][good], ro["fp"][good])
+    for b in np.nonzero(good)[0]:
+        n = ro["n"][b]
+        assert _same(rg["t"][b, :n], ro["t"][b, :n]) and _same(rg["c"][b, :n - k - 1], ro["c"][b, :n - k - 1]), b
+    # call-level argument errors: every curve ier=10, nothing else touched
+    r = F.parcur_batch(0, 0, 2, x[:4], None, 7, s, nest)
+    assert (r["ier"] == 10).all()
+    r = F.percur_batch(0, xs[:4], ys[:4], None, 3, 1.0, 5)        # nest < 2k+2
+    assert (r["ier"] == 10).all()
+    r = F.percur_batch(0, xs[:0], ys[:0], None, 3, 1.0, 20)       # empty batch
+    assert r["ier"].size == 0
