@@ -533,6 +533,15 @@ def main():
             dtp = time.perf_counter() - t0
             same = bool(np.array_equal(oc["n"], rp["n"][:ns_].cpu().numpy())
                         and np.array_equal(oc["fp"], rp["fp"][:ns_].cpu().numpy()))
+            t0 = time.perf_counter()
+            xo_, io_ = O.curev_batch(dp, oc["t"], oc["n"], oc["c"], kp, oc["u"], nthreads=nthr_)
+            dtc_ = time.perf_counter() - t0
+            same_ev = bool(np.array_equal(xo_, xev[:ns_].cpu().numpy()))
+            parc["curev"]["cpu_baseline"] = {
+                "value": ns_ * mp * 8.0 * (1 + dp) / dtc_ / 1e9, "unit": "GB/s", "gpts_per_s": ns_ * mp / dtc_ / 1e9,
+                "cores": nthr_, "kind": "port",
+                "sample": "%d curves x %d points, oracle curev, OpenMP over curves; values bit-identical to the "
+                          "GPU result: %s" % (ns_, mp, same_ev)}
             parc["cpu_baseline"] = {"value": ns_ / dtp, "unit": "fits/s", "cores": nthr_, "kind": "port",
                                     "sample": "first %d curves of the same batch, oracle port of parcur/fppara, "
                                               "OpenMP over curves; n and fp bit-identical to the GPU result: %s"

@@ -25,20 +25,27 @@ namespace {
 
 constexpr unsigned FULLW = 0xffffffffu;
 
-// One warp per curve, lanes over the evaluation points.  Knots and coefficients are a few
-// hundred bytes per curve and are read through L1 (every lane of the warp reads the same
-// curve's tables); x is written in the reference's layout x(idim,m), i.e. idim consecutive
-// doubles per point.
+// One warp per curve, lanes over the evaluation points (32 consecutive points per step).  The
+// curve's knots and the coefficients of all coordinates are staged once in the warp's slice of
+// shared memory; x is written in the reference's layout x(idim,m), i.e. idim consecutive doubles per
+// point.  u is non-decreasing (checked first: any(u(2:m) < u(1:m-1)) -> ier = 10, nothing written,
+// core:1145), so the knot interval of a point is found by a short linear walk that starts from the
+// interval the previous 32-point step ended in -- the same interval fp_knot_interval returns.
+constexpr int kCurevWarps = 8;
+
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCurevWarps * 32)
     curev_kernel(int nspl, int idim, const double *__restrict__ t, const int *__restrict__ n,
                  const double *__restrict__ c, int ldt, long long ldc, const double *__restrict__ u,
-                 double *__restrict__ x, int m, int *__restrict__ ier)
+                 double *__restrict__ x, int m, int *__restrict__ ier, int smem_ld)
 {
     constexpr int K1 = K + 1;
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    extern __shared__ double curev_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *ts = curev_smem + (size_t)wib * smem_ld * (1 + idim);  // knots, then idim coefficient rows
+    double *cs = ts + smem_ld;
+    const long long warp0 = (long long)blockIdx.x * kCurevWarps + wib;
+    const long long nwarps = (long long)gridDim.x * kCurevWarps;
     for (long long j = warp0; j < nspl; j += nwarps) {
         const int nj = n[j];
         if (nj < 2 * K1 || nj > ldt) {  // not a spline of degree K
@@ -47,7 +54,6 @@ __global__ void __launch_bounds__(256)
         }
         const double *tj = t + j * ldt, *cj = c + j * ldc, *uj = u + j * (long long)m;
         double *xj = x + j * (long long)m * idim;
-        // any(u(2:m) < u(1:m-1)) -> ier = 10, nothing evaluated (core:1145)
         bool bad = false;
         for (int i = lane + 1; i < m; i += 32) bad = bad || (uj[i] < uj[i - 1]);
         if (__any_sync(FULLW, bad)) {
@@ -56,43 +62,58 @@ __global__ void __launch_bounds__(256)
         }
         if (lane == 0) ier[j] = IER_OK;
         const int nk1 = nj - K1;
-        const double tb = tj[K1 - 1], te = tj[nk1];
-        for (int i = lane; i < m; i += 32) {
-            double arg = uj[i];
+        __syncwarp();
+        for (int i = lane; i < nj; i += 32) ts[i] = tj[i];
+        for (int d = 0; d < idim; ++d)
+            for (int i = lane; i < nk1; i += 32) cs[d * smem_ld + i] = cj[(long long)d * nj + i];
+        __syncwarp();
+        const double tb = ts[K1 - 1], te = ts[nk1];
+        int lbase = K1;  // interval (1-based) the previous step's last point fell in
+        for (int i0 = 0; i0 < m; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < m;
+            double arg = act ? uj[i] : te;
             if (arg < tb) arg = tb;  // min(max(u,tb),te)
             if (arg > te) arg = te;
-            // fp_knot_interval from l=k1 over non-decreasing arguments (core:2432-2473): the
-            // smallest l in [k1, nk1] with arg < t(l+1), nk1 when there is none
-            int lo = K1, hi = nk1;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (arg < tj[mid]) hi = mid;  // t(mid+1), 0-based tj[mid]
-                else lo = mid + 1;
-            }
-            const int l = lo;
-            double tw[2 * K], h[K1];
+            int l = lbase;
+            while (l < nk1 && arg >= ts[l]) ++l;  // ts[l] = t(l+1)
+            lbase = __shfl_sync(FULLW, l, min(31, m - 1 - i0));
+            if (act) {
+                double tw[2 * K], h[K1];
 #pragma unroll
-            for (int q = 0; q < 2 * K; ++q) tw[q] = tj[l - K + q];  // t(l-K+1+q)
-            bspl<K>(tw, arg, h);
-            const double *cl = cj + (l - K1);
-            for (int d = 0; d < idim; ++d) {
-                double sum = 0.0;
+                for (int q = 0; q < 2 * K; ++q) tw[q] = ts[l - K + q];  // t(l-K+1+q)
+                bspl<K>(tw, arg, h);
+                const double *cl = cs + (l - K1);
+                for (int d = 0; d < idim; ++d) {
+                    double sum = 0.0;
 #pragma unroll
-                for (int q = 0; q < K1; ++q) sum = add(sum, mul(h[q], cl[q]));
-                xj[(long long)i * idim + d] = sum;
-                cl += nj;
+                    for (int q = 0; q < K1; ++q) sum = add(sum, mul(h[q], cl[q]));
+                    xj[(long long)i * idim + d] = sum;
+                    cl += smem_ld;
+                }
             }
         }
     }
 }
 
 template <int K>
-void launch_curev_k(int nspl, int idim, const double *t, const int *n, const double *c, int ldt,
-                    long long ldc, const double *u, double *x, int m, int *ier, int nsm, cudaStream_t st)
+cudaError_t launch_curev_k(int nspl, int idim, const double *t, const int *n, const double *c, int ldt,
+                           long long ldc, const double *u, double *x, int m, int *ier, int nsm, cudaStream_t st)
 {
-    long long blocks = ((long long)nspl + 7) / 8;
-    blocks = std::min<long long>(blocks, (long long)nsm * 8);
-    curev_kernel<K><<<(int)blocks, 256, 0, st>>>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier);
+    const int smem_ld = (ldt + 1) & ~1;
+    const size_t smem = (size_t)kCurevWarps * smem_ld * (1 + idim) * sizeof(double);
+    if (smem > 200u * 1024u) return cudaErrorInvalidValue;  // more than ~3000 knots x coordinates per curve
+    auto kern = curev_kernel<K>;
+    if (smem > 48u * 1024u) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = smem > 0 ? (int)((size_t)200 * 1024 / smem) : 8;
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    long long blocks = ((long long)nspl + kCurevWarps - 1) / kCurevWarps;
+    blocks = std::min<long long>(blocks, (long long)nsm * per_sm);
+    kern<<<(int)blocks, kCurevWarps * 32, smem, st>>>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, smem_ld);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_curev(int nspl, int idim, const double *t, const int *n, const double *c, int ldt,
@@ -100,14 +121,13 @@ cudaError_t launch_curev(int nspl, int idim, const double *t, const int *n, cons
                          cudaStream_t st)
 {
     switch (k) {
-    case 1: launch_curev_k<1>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
-    case 2: launch_curev_k<2>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
-    case 3: launch_curev_k<3>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
-    case 4: launch_curev_k<4>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
-    case 5: launch_curev_k<5>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st); break;
+    case 1: return launch_curev_k<1>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st);
+    case 2: return launch_curev_k<2>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st);
+    case 3: return launch_curev_k<3>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st);
+    case 4: return launch_curev_k<4>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st);
+    case 5: return launch_curev_k<5>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, nsm, st);
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 struct Guard {

@@ -2503,3 +2503,20 @@ void orc_percur_batch(int32_t nbatch, int32_t iopt, int32_t m, const double *x, 
         free(ones);
     }
 }
+
+/* curev over many curves (CPU baseline): t [nspl][ldt], c [nspl][ldc], u [nspl][m], x [nspl][m][idim] */
+void orc_curev_batch(int32_t nspl, int32_t idim, const double *t, const int32_t *n, const double *c,
+                     int32_t ldt, int64_t ldc, int32_t k, const double *u, double *x, int32_t m,
+                     int32_t *ier, int32_t nthreads)
+{
+    int32_t b;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads)
+    for (b = 0; b < nspl; ++b)
+        orc_curev(idim, t + (size_t)b * ldt, n[b], c + (size_t)b * ldc, (int32_t)ldc, k, u + (size_t)b * m, m,
+                  x + (size_t)b * m * idim, m * idim, &ier[b]);
+}

@@ -139,6 +139,10 @@ void orc_percur_batch(int32_t nbatch, int32_t iopt, int32_t m, const double *x, 
                       const double *w, int32_t k, double s, int32_t nest, int32_t *n, double *t, double *c,
                       double *fp, int32_t *ier, int32_t nthreads);
 
+void orc_curev_batch(int32_t nspl, int32_t idim, const double *t, const int32_t *n, const double *c,
+                     int32_t ldt, int64_t ldc, int32_t k, const double *u, double *x, int32_t m,
+                     int32_t *ier, int32_t nthreads);
+
 int32_t orc_max_threads(void);
 
 /* tests only: switch the documented reference-vs-netlib deviations off (see .c) */

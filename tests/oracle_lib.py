@@ -401,3 +401,18 @@ def percur_batch(iopt, x, y, w, k, s, nest, nthreads=0):
                        C.c_double(s), C.c_int32(nest), _i(n), _d(t), _d(c), _d(fp), _i(ier),
                        C.c_int32(nthreads))
     return dict(n=n, t=t, c=c, fp=fp, ier=ier)
+
+
+def curev_batch(idim, t, n, c, k, u, nthreads=0):
+    """orc_curev_batch: t [B][ldt], c [B][ldc], u [B][m] -> (x [B][m][idim], ier [B])."""
+    t, c, u = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, c, u))
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    B, m = u.shape
+    x = np.zeros((B, m, idim))
+    ier = np.zeros(B, np.int32)
+    L = lib()
+    L.orc_curev_batch.restype = None
+    L.orc_curev_batch(C.c_int32(B), C.c_int32(idim), _d(t), _i(n), _d(c), C.c_int32(t.shape[1]),
+                      C.c_int64(c.shape[1]), C.c_int32(k), _d(u), _d(x), C.c_int32(m), _i(ier),
+                      C.c_int32(nthreads))
+    return x, ier
