@@ -859,18 +859,12 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
         }
         const int hi = __reduce_max_sync(FULL, on ? nk1 : 0);
         const int hi8 = __reduce_max_sync(FULL, on ? n8 : 0);
-        for (int i = 1; i <= hi; ++i) {
-            if (on && i <= nk1) {
-#pragma unroll
-                for (int d = 0; d < ND; ++d)
-                    if (d < nd) CD_(d, i) = ZD_(d, i);
-#pragma unroll
-                for (int q = 1; q <= K1; ++q) G_(i, q) = A_(i, q);
-                G_(i, K2) = 0.0;
-            }
-        }
+        // g := a, g(:,k2) := 0, c := z (core:5047-5049) is fused into the sweep of the first smoothing
+        // row, which visits every row 1..nk1 anyway: that sweep reads (a, z) instead of (g, c) and
+        // writes every row it passes, rotated or not (n8 >= 1 for every curve that reaches part 2)
         for (int it = 1; it <= hi8; ++it) {
             const bool row_on = on && it <= n8;
+            const bool first_row = (it == 1);
             double h[K2];
 #pragma unroll
             for (int q = 0; q < K2; ++q) h[q] = row_on ? mul(B_(it, q + 1), pinv) : 0.0;
@@ -884,9 +878,11 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
             {
                 const bool pre = row_on && it <= nk1;
 #pragma unroll
-                for (int q = 0; q < K2; ++q) gn[q] = pre ? G_(it, q + 1) : 0.0;
+                for (int q = 0; q < K2; ++q)
+                    gn[q] = pre ? (first_row ? (q < K1 ? A_(it, q + 1) : 0.0) : G_(it, q + 1)) : 0.0;
 #pragma unroll
-                for (int d = 0; d < ND; ++d) cn[d] = (pre && d < nd) ? CD_(d, it) : 0.0;
+                for (int d = 0; d < ND; ++d)
+                    cn[d] = (pre && d < nd) ? (first_row ? ZD_(d, it) : CD_(d, it)) : 0.0;
             }
             for (int j = it; j <= hi; ++j) {
                 double gc[K2], cj[ND];
@@ -897,9 +893,11 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
                 {
                     const bool pre = row_on && (j + 1) <= nk1;
 #pragma unroll
-                    for (int q = 0; q < K2; ++q) gn[q] = pre ? G_(j + 1, q + 1) : 0.0;
+                    for (int q = 0; q < K2; ++q)
+                        gn[q] = pre ? (first_row ? (q < K1 ? A_(j + 1, q + 1) : 0.0) : G_(j + 1, q + 1)) : 0.0;
 #pragma unroll
-                    for (int d = 0; d < ND; ++d) cn[d] = (pre && d < nd) ? CD_(d, j + 1) : 0.0;
+                    for (int d = 0; d < ND; ++d)
+                        cn[d] = (pre && d < nd) ? (first_row ? ZD_(d, j + 1) : CD_(d, j + 1)) : 0.0;
                 }
                 if (row_on && j <= nk1) {
                     const double piv = h[0];
@@ -907,21 +905,28 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
                     if (p.par || !fp_is_zero(piv)) {
                         double cs, sn;
                         givens(piv, gc[0], cs, sn);
-                        G_(j, 1) = gc[0];
+                        if (!first_row) G_(j, 1) = gc[0];
 #pragma unroll
                         for (int d = 0; d < ND; ++d) {
                             if (d < nd) {
                                 rota(cs, sn, yi[d], cj[d]);
-                                CD_(d, j) = cj[d];
+                                if (!first_row) CD_(d, j) = cj[d];
                             }
                         }
 #pragma unroll
                         for (int q = 1; q <= K1; ++q) {
                             if (q <= noff) {
                                 rota(cs, sn, h[q], gc[q]);
-                                G_(j, q + 1) = gc[q];
+                                if (!first_row) G_(j, q + 1) = gc[q];
                             }
                         }
+                    }
+                    if (first_row) {
+#pragma unroll
+                        for (int q = 0; q < K2; ++q) G_(j, q + 1) = gc[q];
+#pragma unroll
+                        for (int d = 0; d < ND; ++d)
+                            if (d < nd) CD_(d, j) = cj[d];
                     }
 #pragma unroll
                     for (int q = 0; q < K1; ++q) h[q] = h[q + 1];
