@@ -165,6 +165,18 @@ def fit_flops(n, passes, piters, m=M, k=K):
     return passes * per_pass + piters * per_it
 
 
+def fit_divsqrt(n, passes, piters, m=M, k=K):
+    """IEEE divisions and square roots per fit (same counters): fpbspl k(k+1)/2 divisions per point,
+    3 divisions + 1 square root per Givens rotation (fpgivs), one division per back-substituted row."""
+    k1 = k + 1
+    nk1 = n - k1
+    n8 = n - 2 * k1
+    steps = n8 * nk1 - n8 * (n8 - 1) / 2          # rotations of one p-iteration
+    ndiv = passes * (m * (k * (k + 1) / 2 + 3 * k1) + nk1) + piters * (3 * steps + nk1 + 1)
+    nsqrt = passes * (m * k1) + piters * steps
+    return ndiv, nsqrt
+
+
 def run_reference(args, rank, world):
     """CPU arm: the reference algorithm (oracle port; the Fortran cannot be built here) with all
     host threads, each step a bounded sample of the same workload."""
@@ -312,12 +324,27 @@ def main():
     roof["traffic_frac_of_peak"] = roof["traffic_gbs"] / hbm_peak
     dmul_dadd = eng.probe_fp64_gops(False)
     dfma = eng.probe_fp64_gops(True)
+    ndiv_t, nsqrt_t = fit_divsqrt(n_f, stats[:, 0], stats[:, 1])
+    ndiv, nsqrt = float(ndiv_t.sum().item()), float(nsqrt_t.sum().item())
+    ddiv = eng.probe_fp64_gops(2)
+    dsqrt = eng.probe_fp64_gops(3)
+    # FP64 issue slots: one per mul/add, (mul rate / div rate) per IEEE division, likewise sqrt
+    slots = None
+    if dmul_dadd > 0 and ddiv > 0 and dsqrt > 0:
+        slots = (flops - ndiv - nsqrt) + ndiv * (dmul_dadd / ddiv) + nsqrt * (dmul_dadd / dsqrt)
     fp64 = {"achieved_gflops": flops / (fit_ms * 1e-3) / 1e9,
             "peak_gops_dmul_dadd": dmul_dadd, "peak_gops_dfma": dfma,
             "frac_of_unfused_peak": flops / (fit_ms * 1e-3) / 1e9 / dmul_dadd if dmul_dadd > 0 else None,
             "flops_per_fit": flops / B, "mean_lsq_passes": float(stats[:, 0].mean().item()),
             "mean_p_iters": float(stats[:, 1].mean().item()), "mean_n": mean_n,
-            "max_n": int(n.max().item())}
+            "max_n": int(n.max().item()),
+            "peak_gops_ddiv": ddiv, "peak_gops_dsqrt": dsqrt,
+            "div_per_fit": ndiv / B, "sqrt_per_fit": nsqrt / B,
+            "issue_slots_per_fit": None if slots is None else slots / B,
+            "fits_per_s_at_fp64_issue_roofline": None if slots is None else dmul_dadd * 1e9 / (slots / B),
+            "frac_of_fp64_issue_roofline": None if slots is None else (B / (fit_ms * 1e-3)) / (dmul_dadd * 1e9 / (slots / B)),
+            "note": "the bound of this pipeline: measured rates of unfused DMUL/DADD, IEEE division and square "
+                    "root on this GPU; a correctly rounded division costs ~13.6 FP64 issue slots"}
 
     # ---------------------------------------------------------------- fit: end to end (host buffers)
     e2e = None

@@ -64,9 +64,10 @@ class Engine:
         return lib().fpb_engine_launch_count(self._h)
 
     def probe_fp64_gops(self, fused=False):
-        """measured FP64 instruction rate (1e9/s): DMUL+DADD pairs (fused=False) or DFMA"""
+        """measured FP64 instruction rate (1e9/s): DMUL+DADD pairs (fused=False / 0), DFMA (True / 1),
+        IEEE divisions (2) or IEEE square roots (3)"""
         self.use_torch_stream()
-        return lib().fpb_probe_fp64_gops(self._h, 1 if fused else 0)
+        return lib().fpb_probe_fp64_gops(self._h, int(fused))
 
     def last_kernel_ms(self):
         return lib().fpb_engine_last_kernel_ms(self._h)
