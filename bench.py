@@ -43,8 +43,11 @@ GRID_M, GRID_K, GRID_SIGMA, GRID_NEST = 4096, 3, 0.05, 128          # config 4: 
 PARCUR_B, PARCUR_M, PARCUR_IDIM = 1 << 19, 256, 2                   # parametric curves
 PERCUR_B, PERCUR_M = 1 << 20, 256                                   # periodic curves
 # DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum,
-# profiles/r01_final_kernels.md, profiles/r01b_kernels.md); the bench itself never runs under ncu.
-NCU_FIT_DRAM_BYTES_PER_FIT = 8.1 * (6.558e9 + 1.593e9) / 2.5e5 + (51.47e9 + 10.02e9) / (0.94 * 262144)
+# profiles/r01d_kernels.md, profiles/r01b_kernels.md); the bench itself never runs under ncu.
+# fit pipeline at 2^20 curves (profiles/r01d_kernels.md + the per-launch times of
+# profiles/r01d_profile.sh's fit launch list): the captured mid pass moved 22.83 + 3.93 GB in 5.95 ms;
+# the 20 pass launches of one fit take 107.9 ms in total; part 2 moved 214.9 + 41.0 GB.
+NCU_FIT_DRAM_BYTES_PER_FIT = ((22.83e9 + 3.928e9) / 5.953 * 107.94 + (214.9e9 + 41.03e9)) / 1048576
 NCU_SPLEV_DRAM_BYTES_PER_POINT = (8.561e9 + 7.965e9) / (1048576 * 954)   # profiles/r01b_kernels.md
 NCU_SHARED_DRAM_BYTES_PER_CURVE = (17.85e9 + 1.839e9) / 4194304   # shared_apply2 (r01b)
 
@@ -311,7 +314,7 @@ def main():
     roof = {"bound": "hbm", "kernel": "fit pipeline: curfit_pass_kernel<3> x R + curfit_part2_kernel<3>",
             "achieved": alg_bytes / (fit_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "traffic": NCU_FIT_DRAM_BYTES_PER_FIT * B, "traffic_source": "ncu dram bytes per fit "
-            "(pass + part-2 kernels, profiles/r01_final_kernels.md) x curves per launch sequence; "
+            "(pass + part-2 kernels, profiles/r01d_kernels.md) x curves per launch sequence; "
             "workspace traffic (stored basis values, G copies, per-pass state), not re-reads of the input",
             "peak_source": peak_src,
             "algorithmic_bytes_per_fit": alg_bytes / B,
