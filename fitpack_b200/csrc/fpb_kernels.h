@@ -11,6 +11,9 @@ constexpr int kFitThreads = 128;  // threads per CTA of the fit kernel (4 warps 
 #ifndef FPB_FIT_BLOCKS_K3
 #define FPB_FIT_BLOCKS_K3 5
 #endif
+#ifndef FPB_FIT_BLOCKS_DN
+#define FPB_FIT_BLOCKS_DN 5   // idim = 2, 3 instantiations, k <= 3 (scan at idim 2: 3 -> 2.95, 4 -> 3.33, 5 -> 3.41 M fits/s)
+#endif
 constexpr int kMaxIdim = 10;      // MAX_IDIM of the reference (core:115)
 // the fit kernels are compiled for idim = 1, 2, 3 and a run-time variant (class 0) for 4..10
 constexpr int idim_class(int idim) { return idim <= 3 ? idim : 0; }
@@ -18,7 +21,7 @@ constexpr int fit_blocks_per_sm(int k, int idim_cls = 1)
 {
     return idim_cls == 1 ? (k <= 3 ? FPB_FIT_BLOCKS_K3 : (k == 4 ? 4 : 3))
          : idim_cls == 0 ? 2
-                         : (k <= 3 ? 4 : 3);
+                         : (k <= 3 ? FPB_FIT_BLOCKS_DN : 3);
 }
 // the part-2 kernel (smoothing-parameter iteration: one long dependent rotation chain per curve) may
 // be compiled for a different number of resident CTAs than the pass kernel
