@@ -193,12 +193,16 @@ class Engine:
             res["stats"] = stats_t
         return res
 
-    def curev_batch(self, idim, t, n, c, k, u):
-        """curev for many curves: t [B][ldt], c [B][ldc], u [B][m] -> (x [B][m][idim], ier [B])."""
+    def curev_batch(self, idim, t, n, c, k, u, out=None):
+        """curev for many curves: t [B][ldt], c [B][ldc], u [B][m] -> (x [B][m][idim], ier [B]);
+        out = (x, ier) reuses the result tensors of an earlier call."""
         _chk_f64(t, "t"); _chk_f64(c, "c"); _chk_f64(u, "u")
         B, m = u.shape
-        x = torch.zeros((B, m, idim), device=u.device, dtype=torch.float64)
-        ier = torch.zeros(B, device=u.device, dtype=torch.int32)
+        if out is not None:
+            x, ier = out
+        else:
+            x = torch.zeros((B, m, idim), device=u.device, dtype=torch.float64)
+            ier = torch.zeros(B, device=u.device, dtype=torch.int32)
         self.use_torch_stream()
         rc = lib().fp_curev_batch_dev_c(self._h, B, int(idim), _ptr(t), _ptr(n), _ptr(c), t.stride(0),
                                         c.stride(0), int(k), _ptr(u.contiguous()), _ptr(x), m, _ptr(ier))
