@@ -341,6 +341,10 @@ def main():
             "flops_per_fit": flops / B, "mean_lsq_passes": float(stats[:, 0].mean().item()),
             "mean_p_iters": float(stats[:, 1].mean().item()), "mean_n": mean_n,
             "max_n": int(n.max().item()),
+            # distribution of the per-curve work: percentiles 50 / 90 / 99 / 100
+            "n_percentiles": [int(v) for v in torch.quantile(n_f[:1 << 20], torch.tensor([.5, .9, .99, 1.], device=dev, dtype=torch.float64)).tolist()],
+            "lsq_passes_percentiles": [int(v) for v in torch.quantile(stats[:1 << 20, 0], torch.tensor([.5, .9, .99, 1.], device=dev, dtype=torch.float64)).tolist()],
+            "p_iters_percentiles": [int(v) for v in torch.quantile(stats[:1 << 20, 1], torch.tensor([.5, .9, .99, 1.], device=dev, dtype=torch.float64)).tolist()],
             "peak_gops_ddiv": ddiv, "peak_gops_dsqrt": dsqrt,
             "div_per_fit": ndiv / B, "sqrt_per_fit": nsqrt / B,
             "issue_slots_per_fit": None if slots is None else slots / B,
