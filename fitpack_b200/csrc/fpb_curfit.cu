@@ -859,79 +859,70 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
         }
         const int hi = __reduce_max_sync(FULL, on ? nk1 : 0);
         const int hi8 = __reduce_max_sync(FULL, on ? n8 : 0);
-        // g := a, g(:,k2) := 0, c := z (core:5047-5049) is fused into the sweep of the first smoothing
-        // row, which visits every row 1..nk1 anyway: that sweep reads (a, z) instead of (g, c) and
-        // writes every row it passes, rotated or not (n8 >= 1 for every curve that reaches part 2)
-        for (int it = 1; it <= hi8; ++it) {
-            const bool row_on = on && it <= n8;
-            const bool first_row = (it == 1);
-            double h[K2];
-#pragma unroll
-            for (int q = 0; q < K2; ++q) h[q] = row_on ? mul(B_(it, q + 1), pinv) : 0.0;
-            double yi[ND];
-#pragma unroll
-            for (int d = 0; d < ND; ++d) yi[d] = 0.0;
-            // fp_rotate_shifted / _vec, core:5800-5820 / 5845-5862.  Row j+1 of G (and c(j+1)) is
-            // requested before the div/sqrt chain of row j starts: the sweep is otherwise bound by
-            // L2 latency.  The vector variant has no zero-pivot skip.
-            double gn[K2], cn[ND];
-            {
-                const bool pre = row_on && it <= nk1;
-#pragma unroll
-                for (int q = 0; q < K2; ++q)
-                    gn[q] = pre ? (first_row ? (q < K1 ? A_(it, q + 1) : 0.0) : G_(it, q + 1)) : 0.0;
+        // The smoothing rows b(it,:)/p are rotated into g TWO AT A TIME (fp_rotate_shifted / _vec,
+        // core:5800-5820 / 5845-5862): band row j passes through row `it`'s rotation and, one step
+        // later and still in registers, through row `it+1`'s, and is stored once.  Row it+1 at band
+        // row j needs only what row `it` left in band row j and its own state from band row j-1, so
+        // the arithmetic and its order are exactly the reference's; the band matrix, which part 2
+        // re-reads from DRAM (its working set plus the point streams exceed L2: 82 % of the HBM peak,
+        // profiles/r01g_kernels.md), is read and written half as often.
+        // g := a, g(:,k2) := 0, c := z (core:5047-5049) is fused into the first pair's sweep, which
+        // visits every row 1..nk1: it reads (a, z) instead of (g, c) and stores every row it passes,
+        // rotated or not (n8 >= 1 for every curve that reaches part 2).
+        // One rotation step of a smoothing row against band row (g, c) with `noff` columns to its right.
+        auto sweep_step = [&](double (&h)[K2], double (&y)[ND], double (&g)[K2], double (&c)[ND], int noff) {
+            const double piv = h[0];
+            if (p.par || !fp_is_zero(piv)) {  // the vector variant has no zero-pivot skip
+                double cs, sn;
+                givens(piv, g[0], cs, sn);
 #pragma unroll
                 for (int d = 0; d < ND; ++d)
-                    cn[d] = (pre && d < nd) ? (first_row ? ZD_(d, it) : CD_(d, it)) : 0.0;
+                    if (d < nd) rota(cs, sn, y[d], c[d]);
+#pragma unroll
+                for (int q = 1; q <= K1; ++q)
+                    if (q <= noff) rota(cs, sn, h[q], g[q]);
             }
-            for (int j = it; j <= hi; ++j) {
-                double gc[K2], cj[ND];
 #pragma unroll
-                for (int d = 0; d < ND; ++d) cj[d] = cn[d];
+            for (int q = 0; q < K1; ++q) h[q] = h[q + 1];
+            h[K1] = 0.0;
+        };
+        for (int it = 1; it <= hi8; it += 2) {
+            const bool a_on = on && it <= n8, b_on = on && (it + 1) <= n8;
+            const bool first_pair = (it == 1);
+            double hA[K2], hB[K2], yA[ND], yB[ND], gp[K2], cp[ND];
 #pragma unroll
-                for (int q = 0; q < K2; ++q) gc[q] = gn[q];
-                {
-                    const bool pre = row_on && (j + 1) <= nk1;
+            for (int q = 0; q < K2; ++q) {
+                hA[q] = a_on ? mul(B_(it, q + 1), pinv) : 0.0;
+                hB[q] = b_on ? mul(B_(it + 1, q + 1), pinv) : 0.0;
+                gp[q] = 0.0;
+            }
 #pragma unroll
-                    for (int q = 0; q < K2; ++q)
-                        gn[q] = pre ? (first_row ? (q < K1 ? A_(j + 1, q + 1) : 0.0) : G_(j + 1, q + 1)) : 0.0;
+            for (int d = 0; d < ND; ++d) yA[d] = yB[d] = cp[d] = 0.0;
+            for (int j = it; j <= hi + 1; ++j) {
+                // band row j is requested first; row it+1's step on band row j-1 (in registers) covers
+                // the latency
+                const bool a_act = a_on && j <= nk1;
+                double ga[K2], ca[ND];
+#pragma unroll
+                for (int q = 0; q < K2; ++q)
+                    ga[q] = a_act ? (first_pair ? (q < K1 ? A_(j, q + 1) : 0.0) : G_(j, q + 1)) : 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    ca[d] = (a_act && d < nd) ? (first_pair ? ZD_(d, j) : CD_(d, j)) : 0.0;
+                const int jb = j - 1;
+                if (a_on && jb >= it && jb <= nk1) {
+                    if (b_on && jb >= it + 1) sweep_step(hB, yB, gp, cp, min(nk1 - jb, K1));
+#pragma unroll
+                    for (int q = 0; q < K2; ++q) G_(jb, q + 1) = gp[q];
 #pragma unroll
                     for (int d = 0; d < ND; ++d)
-                        cn[d] = (pre && d < nd) ? (first_row ? ZD_(d, j + 1) : CD_(d, j + 1)) : 0.0;
+                        if (d < nd) CD_(d, jb) = cp[d];
                 }
-                if (row_on && j <= nk1) {
-                    const double piv = h[0];
-                    const int noff = min(nk1 - j, K1);
-                    if (p.par || !fp_is_zero(piv)) {
-                        double cs, sn;
-                        givens(piv, gc[0], cs, sn);
-                        if (!first_row) G_(j, 1) = gc[0];
+                if (a_act) sweep_step(hA, yA, ga, ca, min(nk1 - j, K1));
 #pragma unroll
-                        for (int d = 0; d < ND; ++d) {
-                            if (d < nd) {
-                                rota(cs, sn, yi[d], cj[d]);
-                                if (!first_row) CD_(d, j) = cj[d];
-                            }
-                        }
+                for (int q = 0; q < K2; ++q) gp[q] = ga[q];
 #pragma unroll
-                        for (int q = 1; q <= K1; ++q) {
-                            if (q <= noff) {
-                                rota(cs, sn, h[q], gc[q]);
-                                if (!first_row) G_(j, q + 1) = gc[q];
-                            }
-                        }
-                    }
-                    if (first_row) {
-#pragma unroll
-                        for (int q = 0; q < K2; ++q) G_(j, q + 1) = gc[q];
-#pragma unroll
-                        for (int d = 0; d < ND; ++d)
-                            if (d < nd) CD_(d, j) = cj[d];
-                    }
-#pragma unroll
-                    for (int q = 0; q < K1; ++q) h[q] = h[q + 1];
-                    h[K1] = 0.0;
-                }
+                for (int d = 0; d < ND; ++d) cp[d] = ca[d];
             }
         }
         for (int d = 0; d < nd; ++d)
