@@ -147,3 +147,29 @@ def test_fuzz_curfit_given_knots_bit_exact(F):
                 nn = ro["n"][b]
                 assert _same(rg["t"][b, :nn], ro["t"][b, :nn]) and _same(rg["c"][b, :nn - k - 1], ro["c"][b, :nn - k - 1]), (k, m, b)
     assert n10 > 20 and nok > 1000
+
+
+def test_minimal_sizes_bit_exact(F):
+    """Smallest legal problems: m = k+1 / k+2 points (curfit, parcur), m = 2, 3, 4 (percur), nest from the
+    minimum 2k+2 up -- every ier class these produce (-2, -1, 0, 1, 10) must match the oracle."""
+    rng = np.random.default_rng(5)
+    B = 40
+    for k in (1, 2, 3, 4, 5):
+        for m in (k + 1, k + 2):
+            x = np.sort(rng.uniform(0, 1, (B, m)), axis=1) + np.arange(m) * 1e-6
+            y = rng.standard_normal((B, m))
+            xx = np.stack([y, y[:, ::-1]], 2)
+            for s in (0.0, 0.01, 10.0):
+                for nest in (2 * k + 2, m + k + 1, m + k + 5):
+                    _check_fit(F.curfit_batch(0, x, y, None, k, s, nest), O.curfit_batch(0, x, y, None, k, s, nest),
+                               k, tag=("curfit", k, m, s, nest))
+                    kw = dict(u=x, ub=x[:, 0].copy(), ue=x[:, -1].copy())
+                    _check_fit(F.parcur_batch(0, 1, 2, xx, None, k, s, nest, **kw),
+                               O.parcur_batch(0, 1, 2, xx, None, k, s, nest, **kw), k, 2, tag=("parcur", k, m, s, nest))
+        for m in (2, 3, 4, k + 2):
+            x = np.sort(rng.uniform(0, 6, (B, m)), axis=1) + np.arange(m) * 1e-6
+            y = rng.standard_normal((B, m))
+            for s in (0.0, 0.01, 10.0):
+                for nest in (2 * k + 2, 2 * k + 3, m + 2 * k, m + 2 * k + 3):
+                    _check_fit(F.percur_batch(0, x, y, None, k, s, nest), O.percur_batch(0, x, y, None, k, s, nest),
+                               k, tag=("percur", k, m, s, nest))
