@@ -1078,3 +1078,27 @@ def test_parcur_percur_batches_with_invalid_curves(F):
     assert (r["ier"] == 10).all()
     r = F.percur_batch(0, xs[:0], ys[:0], None, 3, 1.0, 20)       # empty batch
     assert r["ier"].size == 0
+
+
+def test_host_batch_sharded_over_the_nodes_gpus(F):
+    """fp_curfit_batch_c / fp_splev_batch_c with ngpus = all visible GPUs (contiguous
+    slices of the batch, one engine per device, no collective): identical to the single-GPU result
+    and to the oracle."""
+    import torch
+    ng = torch.cuda.device_count()
+    rng = np.random.default_rng(31)
+    B, m, k, s, nest = 3000, 64, 3, 0.64, 68
+    x, y = synth_curves(rng, B, m)
+    ro = O.curfit_batch(0, x, y, None, k, s, nest)
+    r1 = F.curfit_batch(0, x, y, None, k, s, nest, ngpus=1)
+    rn = F.curfit_batch(0, x, y, None, k, s, nest, ngpus=ng)
+    for r in (r1, rn):
+        assert _same(r["n"], ro["n"]) and _same(r["ier"], ro["ier"]) and _same(r["fp"], ro["fp"])
+        for b in range(0, B, 7):
+            n = ro["n"][b]
+            assert _same(r["t"][b, :n], ro["t"][b, :n]) and _same(r["c"][b, :n - k - 1], ro["c"][b, :n - k - 1])
+    xe = np.sort(rng.uniform(-0.1, 1.1, (B, 50)), axis=1)
+    y1, i1 = F.splev_batch(ro["t"], ro["n"], ro["c"], k, xe, e=0, mode=0, ngpus=1)
+    yn, i_n = F.splev_batch(ro["t"], ro["n"], ro["c"], k, xe, e=0, mode=0, ngpus=ng)
+    yo, _ = O.splev_batch(ro["t"], ro["n"], ro["c"], k, xe)
+    assert _same(y1, yo) and _same(yn, yo) and not i1.any() and not i_n.any()
