@@ -86,14 +86,14 @@ SYMBOLS = {
                            _I32, _VP, _VP, _VP, _I32, _VP, _VP]),
     "fp_curev_c": (None, [_I32, _VP, _I32, _VP, _I32, _I32, _VP, _I32, _VP, _I32, _VP]),
     "fp_parcur_batch_c": (_I32, [_I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _F64, _I32,
-                                 _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+                                 _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32]),
     "fp_parcur_batch_dev_c": (_I32, [_VP, _I32, _I32, _I32, _I32, _I32, _VP, _I64, _I64, _VP, _I64, _I64,
                                      _I64, _VP, _I64, _I64, _VP, _VP, _I32, _I32, _VP, _I32, _I32, _VP,
                                      _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "fp_curev_batch_dev_c": (_I32, [_VP, _I32, _I32, _VP, _VP, _VP, _I32, _I64, _I32, _VP, _VP, _I32, _VP]),
     "fp_percur_c": (None, [_I32, _I32, _VP, _VP, _VP, _I32, _F64, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP]),
     "fp_percur_batch_c": (_I32, [_I32, _I32, _I32, _VP, _VP, _VP, _I32, _F64, _I32, _VP, _VP, _VP, _VP, _VP,
-                                 _VP, _VP]),
+                                 _VP, _VP, _I32]),
     "fp_percur_batch_dev_c": (_I32, [_VP, _I32, _I32, _I32, _VP, _I64, _I64, _VP, _I64, _I64, _VP, _I64, _I64,
                                      _I32, _VP, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "fitpack_curve_c_integral": (_F64, [_VP, _F64, _F64]),

@@ -281,7 +281,7 @@ def curev(idim, t, n, c, k, u):
 
 
 def parcur_batch(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=None, ue=None, n=None, t=None,
-                 fpint=None, nrdata=None):
+                 fpint=None, nrdata=None, ngpus=1):
     """Many independent parametric curves, host arrays (fp_parcur_batch_c).  x [B][m][idim]."""
     x = _f64(x)
     B, m = x.shape[0], x.shape[1]
@@ -298,7 +298,7 @@ def parcur_batch(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=None, ue=None, n
     nrdata = np.zeros((B, nest), dtype=np.int32) if nrdata is None else nrdata
     rc = lib().fp_parcur_batch_c(B, int(iopt), int(ipar), int(idim), m, _p(u), _p(x), _p(w), _p(ub), _p(ue),
                                  int(k), float(s), int(nest), _p(n_arr), _p(t_arr), _p(c_arr), _p(fp),
-                                 _p(ier), _p(fpint), _p(nrdata))
+                                 _p(ier), _p(fpint), _p(nrdata), int(ngpus))
     check(rc, "fp_parcur_batch_c")
     return dict(n=n_arr, t=t_arr, c=c_arr, fp=fp, ier=ier, u=u, ub=ub, ue=ue, fpint=fpint, nrdata=nrdata)
 
@@ -326,7 +326,7 @@ def percur(iopt, x, y, w, k, s, nest, n=0, t=None, wrk=None, iwrk=None, c=None, 
     return dict(n=n_.value, t=t, c=c, fp=fp_.value, ier=ier_.value, wrk=wrk, iwrk=iwrk)
 
 
-def percur_batch(iopt, x, y, w, k, s, nest, n=None, t=None, fpint=None, nrdata=None):
+def percur_batch(iopt, x, y, w, k, s, nest, n=None, t=None, fpint=None, nrdata=None, ngpus=1):
     """Many independent periodic fits, host arrays curve-major (fp_percur_batch_c)."""
     x, y = _f64(x), _f64(y)
     B, m = y.shape
@@ -337,6 +337,6 @@ def percur_batch(iopt, x, y, w, k, s, nest, n=None, t=None, fpint=None, nrdata=N
     fp = np.zeros(B)
     ier = np.zeros(B, dtype=np.int32)
     rc = lib().fp_percur_batch_c(B, int(iopt), m, _p(x), _p(y), _p(w), int(k), float(s), int(nest), _p(n_arr),
-                                 _p(t_arr), _p(c_arr), _p(fp), _p(ier), _p(fpint), _p(nrdata))
+                                 _p(t_arr), _p(c_arr), _p(fp), _p(ier), _p(fpint), _p(nrdata), int(ngpus))
     check(rc, "fp_percur_batch_c")
     return dict(n=n_arr, t=t_arr, c=c_arr, fp=fp, ier=ier)

@@ -950,6 +950,14 @@ template <class F> int32_t shard_over_gpus(long long total, int ngpus, long long
 
 }  // namespace
 
+namespace fpb {
+int32_t shard_units_over_gpus(long long total, int ngpus, long long align,
+                              const std::function<int32_t(fpb_engine *, long long, long long)> &fn)
+{
+    return shard_over_gpus(total, ngpus, align, fn);
+}
+}  // namespace fpb
+
 extern "C" {
 
 int32_t fp_curfit_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x,

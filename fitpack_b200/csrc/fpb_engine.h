@@ -4,6 +4,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <functional>
 #include <string>
 
 #include "fpb_kernels.h"
@@ -55,4 +56,8 @@ namespace fpb {
 fpb_engine *default_engine(int device);
 // the curfit / parcur pass pipeline (fpb_engine.cu): `p` carries the caller's arrays and scalars
 int32_t run_fit_pipeline(fpb_engine *eng, FitParams p);
+// contiguous slices [b0, b1) of `total` units over the first `ngpus` devices (<= 0: all), one host
+// thread + default engine per device; fn(engine, b0, b1) runs on each (no collective)
+int32_t shard_units_over_gpus(long long total, int ngpus, long long align,
+                              const std::function<int32_t(fpb_engine *, long long, long long)> &fn);
 }

@@ -234,7 +234,7 @@ int32_t fp_curev_batch_dev_c(fpb_engine *eng, FP_SIZE nspl, FP_SIZE idim, const 
 int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u,
                           const FP_REAL *x, const FP_REAL *w, FP_REAL *ub, FP_REAL *ue, FP_SIZE k,
                           FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
-                          FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata)
+                          FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata, FP_SIZE ngpus)
 {
     if (nbatch <= 0) return FPB_STATUS_OK;
     if (!u || !x || !ub || !ue || !n || !t || !c || !fp || !ier) {
@@ -250,8 +250,8 @@ int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE id
         set_last_error("fp_parcur_batch_c: iopt=1 needs the fpint/nrdata state arrays");
         return FPB_ERR_ARG;
     }
-    fpb_engine *eng = default_engine(-1);
-    if (!eng) return FPB_ERR_CUDA;  // no device: there is no CPU path
+    // contiguous slices of the batch per GPU, one host thread + engine per device (no collective)
+    return shard_units_over_gpus(nbatch, ngpus, 128, [&](fpb_engine *eng, long long s0, long long s1) -> int32_t {
     Guard g(eng->device);
     if (!g.ok) return FPB_ERR_CUDA;
     cudaStream_t st = eng->stream;
@@ -260,8 +260,8 @@ int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE id
     const long long chunk = std::max<long long>(128, (long long)(((size_t)6 << 30) / per_curve) / 128 * 128);
     enum { XC, XP, UC, UP, WC, WP, SS, BE, NN, TT, CC, FP_IER };
     DevBuf *B = eng->scratch;
-    for (long long b0 = 0; b0 < nbatch; b0 += chunk) {
-        const long long nb = std::min<long long>(chunk, nbatch - b0);
+    for (long long b0 = s0; b0 < s1; b0 += chunk) {
+        const long long nb = std::min<long long>(chunk, s1 - b0);
         const long long ld = (nb + 31) / 32 * 32;  // point-major leading dimension
         const size_t md = (size_t)m * idim;
         // TT holds t [nb][nest] doubles, fpint [nb][nest] doubles and nrdata [nb][nest] ints
@@ -339,6 +339,7 @@ int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE id
         }
     }
     return FPB_STATUS_OK;
+    });
 }
 
 // ---- the reference's own flat entry points: a batch of one curve ----
@@ -360,7 +361,7 @@ void fp_parcur_c(FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u
     // wrk(1:nest) is fpint and iwrk(1:nest) is nrdata (core:15275-15283): the iopt=1 state
     FP_FLAG ier1 = FPB_INPUT_ERROR;
     const int32_t rc = fp_parcur_batch_c(1, iopt, ipar, idim, m, u, x, w, ub, ue, k, *s, nest, n, t, c, fp,
-                                         &ier1, wrk, iwrk);
+                                         &ier1, wrk, iwrk, 1);
     *ier = (rc != FPB_STATUS_OK) ? rc : ier1;
 }
 

@@ -105,9 +105,9 @@ module fitpack_b200
       ! x(idim,m,nbatch), u(m,nbatch), w(m,nbatch) (c_null_ptr-style optional: pass w as a
       ! type(c_ptr) interface variant if unit weights are wanted), c(nest*idim,nbatch)
       integer(c_int32_t) function fp_parcur_batch_c(nbatch,iopt,ipar,idim,m,u,x,w,ub,ue,k,s,nest, &
-                                                    n,t,c,fp,ier,fpint,nrdata) bind(C,name="fp_parcur_batch_c")
+                                                    n,t,c,fp,ier,fpint,nrdata,ngpus) bind(C,name="fp_parcur_batch_c")
          import
-         integer(FP_SIZE), intent(in), value :: nbatch,iopt,ipar,idim,m,k,nest
+         integer(FP_SIZE), intent(in), value :: nbatch,iopt,ipar,idim,m,k,nest,ngpus
          real   (FP_REAL), intent(in), value :: s
          real   (FP_REAL), intent(inout)     :: u(m,nbatch),ub(nbatch),ue(nbatch)
          real   (FP_REAL), intent(in)        :: x(idim,m,nbatch),w(m,nbatch)
@@ -130,10 +130,10 @@ module fitpack_b200
          integer(FP_SIZE), intent(inout)        :: iwrk(nest)
       end subroutine fp_percur_c
 
-      integer(c_int32_t) function fp_percur_batch_c(nbatch,iopt,m,x,y,w,k,s,nest,n,t,c,fp,ier,fpint,nrdata) &
+      integer(c_int32_t) function fp_percur_batch_c(nbatch,iopt,m,x,y,w,k,s,nest,n,t,c,fp,ier,fpint,nrdata,ngpus) &
                                                     bind(C,name="fp_percur_batch_c")
          import
-         integer(FP_SIZE), intent(in), value :: nbatch,iopt,m,k,nest
+         integer(FP_SIZE), intent(in), value :: nbatch,iopt,m,k,nest,ngpus
          real   (FP_REAL), intent(in), value :: s
          real   (FP_REAL), intent(in)        :: x(m,nbatch),y(m,nbatch),w(m,nbatch)
          integer(FP_SIZE), intent(inout)     :: n(nbatch),nrdata(nest,nbatch)

@@ -315,11 +315,12 @@ void fp_curev_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_
 /* NEW: many independent parametric curves.  Host pointers, curve-major: x [nbatch][m][idim],
    u [nbatch][m] in/out, w [nbatch][m] or NULL (unit weights), ub/ue [nbatch] in/out,
    t [nbatch][nest], c [nbatch][nest*idim], fpint/nrdata [nbatch][nest] continuation state (NULL
-   allowed unless iopt=1).  Per-curve ier; returns FPB_STATUS_*. */
+   allowed unless iopt=1).  ngpus: contiguous slices of the batch over that many GPUs of the node
+   (<= 0: all), no collective.  Per-curve ier; returns FPB_STATUS_*. */
 int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u,
                           const FP_REAL *x, const FP_REAL *w, FP_REAL *ub, FP_REAL *ue, FP_SIZE k,
                           FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
-                          FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata);
+                          FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata, FP_SIZE ngpus);
 /* Device pointers + strides (elements): u[b*u_sb + i*u_si], x[b*x_sb + i*x_si + d*x_sd],
    w[b*w_sb + i*w_si] (NULL = unit weights); the fast layout is point-major (u_sb = 1, u_si = ld;
    x_sb = 1, x_si = idim*ld, x_sd = ld).  ub/ue NULL = the data range [u(1), u(m)] (always used
@@ -353,7 +354,7 @@ void fp_percur_c(FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y, co
 /* NEW: many independent periodic fits; host pointers curve-major (x, y, w [nbatch][m], w NULL = 1) */
 int32_t fp_percur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y,
                           const FP_REAL *w, FP_SIZE k, FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t,
-                          FP_REAL *c, FP_REAL *fp, FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata);
+                          FP_REAL *c, FP_REAL *fp, FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata, FP_SIZE ngpus);
 /* device pointers + strides as fp_curfit_batch_dev_c (point-major is the fast layout) */
 int32_t fp_percur_batch_dev_c(fpb_engine *eng, FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x,
                               int64_t x_sb, int64_t x_si, const FP_REAL *y, int64_t y_sb, int64_t y_si,

@@ -1102,3 +1102,16 @@ def test_host_batch_sharded_over_the_nodes_gpus(F):
     yn, i_n = F.splev_batch(ro["t"], ro["n"], ro["c"], k, xe, e=0, mode=0, ngpus=ng)
     yo, _ = O.splev_batch(ro["t"], ro["n"], ro["c"], k, xe)
     assert _same(y1, yo) and _same(yn, yo) and not i1.any() and not i_n.any()
+    # parametric and periodic batches sharded the same way
+    from refdata import synth_param_curves
+    th, xp = synth_param_curves(rng, 1500, 48, 2)
+    op = O.parcur_batch(0, 0, 2, xp, None, 3, 48 * 2 * 0.0025, 52)
+    rp = F.parcur_batch(0, 0, 2, xp, None, 3, 48 * 2 * 0.0025, 52, ngpus=ng)
+    assert _same(rp["n"], op["n"]) and _same(rp["fp"], op["fp"]) and _same(rp["u"], op["u"]) and _same(rp["ier"], op["ier"])
+    yq = np.sin(th) + 0.1 * rng.standard_normal(th.shape)
+    oq = O.percur_batch(0, th, yq, None, 3, 48 * 0.01, 54)
+    rq = F.percur_batch(0, th, yq, None, 3, 48 * 0.01, 54, ngpus=ng)
+    assert _same(rq["n"], oq["n"]) and _same(rq["fp"], oq["fp"]) and _same(rq["ier"], oq["ier"])
+    for b in range(0, 1500, 11):
+        n = oq["n"][b]
+        assert _same(rq["t"][b, :n], oq["t"][b, :n]) and _same(rq["c"][b, :n - 4], oq["c"][b, :n - 4])
