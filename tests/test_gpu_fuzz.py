@@ -2,10 +2,15 @@
 the oracle, every output bit-exact.  Covers what the golden files only sample: all degrees, short /
 odd point counts, tight and loose nest, zero / tiny / huge smoothing factors, weights, jittered and
 clustered abscissae -- for curfit, parcur (idim 1, 2, 3, 5) and percur."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle_lib as O
+
+# FPB_FUZZ_SEED=<int> shifts every generator seed: `for s in 1 2 3; do FPB_FUZZ_SEED=$s pytest ...` widens the sweep
+SEED = int(os.environ.get("FPB_FUZZ_SEED", "0")) * 1000003
 
 pytestmark = pytest.mark.gpu
 
@@ -54,7 +59,7 @@ def _check_fit(rg, ro, k, idim=1, tag=None):
 
 
 def test_fuzz_curfit_bit_exact(F):
-    rng = np.random.default_rng(20261020)
+    rng = np.random.default_rng(20261020 + SEED)
     hist = np.zeros(13, int)
     B = 160
     for k in (1, 2, 3, 4, 5):
@@ -74,7 +79,7 @@ def test_fuzz_curfit_bit_exact(F):
 
 
 def test_fuzz_parcur_bit_exact(F):
-    rng = np.random.default_rng(20261021)
+    rng = np.random.default_rng(20261021 + SEED)
     hist = np.zeros(13, int)
     B = 120
     for idim in (1, 2, 3, 5):
@@ -95,7 +100,7 @@ def test_fuzz_parcur_bit_exact(F):
 
 
 def test_fuzz_percur_bit_exact(F):
-    rng = np.random.default_rng(20261022)
+    rng = np.random.default_rng(20261022 + SEED)
     hist = np.zeros(13, int)
     B = 160
     for k in (1, 2, 3, 4, 5):
@@ -116,7 +121,7 @@ def test_fuzz_percur_bit_exact(F):
 def test_fuzz_curfit_given_knots_bit_exact(F):
     """iopt = -1: random interior knot sets, some violating the Schoenberg-Whitney conditions (fpchec
     -> ier = 10 for that curve only), per-curve knot counts."""
-    rng = np.random.default_rng(20261023)
+    rng = np.random.default_rng(20261023 + SEED)
     B = 200
     n10 = nok = 0
     for k in (1, 3, 5):
@@ -152,7 +157,7 @@ def test_fuzz_curfit_given_knots_bit_exact(F):
 def test_minimal_sizes_bit_exact(F):
     """Smallest legal problems: m = k+1 / k+2 points (curfit, parcur), m = 2, 3, 4 (percur), nest from the
     minimum 2k+2 up -- every ier class these produce (-2, -1, 0, 1, 10) must match the oracle."""
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(5 + SEED)
     B = 40
     for k in (1, 2, 3, 4, 5):
         for m in (k + 1, k + 2):
