@@ -372,6 +372,8 @@ void fp_curev_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_
     if (m < 1) return;                 // core:1142
     if (mx < m * idim) return;         // core:1148
     if (idim < 1 || idim > kMaxIdim || k < 1 || k > 5 || n < 2 * (k + 1) || nc < n * (idim - 1) + n - k - 1) return;
+    for (FP_SIZE i = 1; i < m; ++i)    // any(u(2:m) < u(1:m-1)), core:1145 (checked here: the points are
+        if (u[i] < u[i - 1]) return;   // spread over many warps below, each sees only its own chunk)
     fpb_engine *eng = default_engine(-1);
     if (!eng) {
         *ier = FPB_ERR_CUDA;
@@ -380,30 +382,53 @@ void fp_curev_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_
     Guard g(eng->device);
     cudaStream_t st = eng->stream;
     DevBuf *B = eng->scratch;
+    // one curve, its m points spread over the device: chunks of `chunk` points, every chunk a "curve"
+    // of the batch kernel with its own copy of the (small) knot and coefficient tables
+    const int chunk = m > 8192 ? 2048 : m;
+    const long long nchunks = ((long long)m + chunk - 1) / chunk;
+    const size_t padded = (size_t)nchunks * chunk;
     const size_t ncu = (size_t)n * (idim - 1) + (size_t)(n - k - 1);  // coefficients actually read
-    if (!B[0].reserve((size_t)n * 8) || !B[1].reserve(ncu * 8 + 64) || !B[2].reserve(64) ||
-        !B[3].reserve((size_t)m * 8) || !B[4].reserve((size_t)m * idim * 8)) {
+    const size_t ldc = (ncu + 1) & ~(size_t)1;
+    const int ldt = (n + 1) & ~1;
+    std::vector<double> ht((size_t)nchunks * ldt, 0.0), hc((size_t)nchunks * ldc, 0.0);
+    std::vector<int> hn((size_t)nchunks, n);
+    for (long long q = 0; q < nchunks; ++q) {
+        std::memcpy(&ht[(size_t)q * ldt], t, (size_t)n * 8);
+        std::memcpy(&hc[(size_t)q * ldc], c, ncu * 8);
+    }
+    if (!B[0].reserve(ht.size() * 8) || !B[1].reserve(hc.size() * 8) || !B[2].reserve((size_t)nchunks * 8) ||
+        !B[3].reserve(padded * 8) || !B[4].reserve(padded * idim * 8)) {
         *ier = FPB_ERR_ALLOC;
         return;
     }
-    bool ok = cuda_ok(cudaMemcpyAsync(B[0].ptr, t, (size_t)n * 8, cudaMemcpyHostToDevice, st), "H2D");
-    ok = ok && cuda_ok(cudaMemcpyAsync(B[1].ptr, c, ncu * 8, cudaMemcpyHostToDevice, st), "H2D");
-    ok = ok && cuda_ok(cudaMemcpyAsync(B[2].ptr, &n, 4, cudaMemcpyHostToDevice, st), "H2D");
+    int *d_n = B[2].as<int>(), *d_ier = d_n + nchunks;
+    bool ok = cuda_ok(cudaMemcpyAsync(B[0].ptr, ht.data(), ht.size() * 8, cudaMemcpyHostToDevice, st), "H2D");
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[1].ptr, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice, st), "H2D");
+    ok = ok && cuda_ok(cudaMemcpyAsync(d_n, hn.data(), (size_t)nchunks * 4, cudaMemcpyHostToDevice, st), "H2D");
     ok = ok && cuda_ok(cudaMemcpyAsync(B[3].ptr, u, (size_t)m * 8, cudaMemcpyHostToDevice, st), "H2D");
+    std::vector<double> pad;
+    if (ok && padded > (size_t)m) {  // the tail chunk repeats the last parameter (keeps it monotone)
+        pad.assign(padded - m, u[m - 1]);
+        ok = cuda_ok(cudaMemcpyAsync(B[3].as<double>() + m, pad.data(), pad.size() * 8, cudaMemcpyHostToDevice, st),
+                     "H2D pad");
+    }
+    ok = ok && cuda_ok(cudaStreamSynchronize(st), "sync");  // the host vectors go out of use here
     if (!ok) {
         *ier = FPB_ERR_CUDA;
         return;
     }
-    const int32_t rc = fp_curev_batch_dev_c(eng, 1, idim, B[0].as<double>(), B[2].as<int>(), B[1].as<double>(),
-                                            n, (int64_t)ncu, k, B[3].as<double>(), B[4].as<double>(), m,
-                                            B[2].as<int>() + 4);
+    const int32_t rc = fp_curev_batch_dev_c(eng, (FP_SIZE)nchunks, idim, B[0].as<double>(), d_n, B[1].as<double>(),
+                                            ldt, (int64_t)ldc, k, B[3].as<double>(), B[4].as<double>(), chunk, d_ier);
     if (rc != FPB_STATUS_OK) {
         *ier = rc;
         return;
     }
-    FP_FLAG h = FPB_INPUT_ERROR;
-    ok = cuda_ok(cudaMemcpyAsync(&h, B[2].as<int>() + 4, 4, cudaMemcpyDeviceToHost, st), "D2H") &&
+    std::vector<int> hier((size_t)nchunks, FPB_INPUT_ERROR);
+    ok = cuda_ok(cudaMemcpyAsync(hier.data(), d_ier, (size_t)nchunks * 4, cudaMemcpyDeviceToHost, st), "D2H") &&
          cuda_ok(cudaStreamSynchronize(st), "sync");
+    FP_FLAG h = FPB_OK;
+    for (long long q = 0; ok && q < nchunks; ++q)
+        if (hier[(size_t)q] != FPB_OK) h = hier[(size_t)q];
     if (ok && h == FPB_OK)
         ok = cuda_ok(cudaMemcpy(x, B[4].ptr, (size_t)m * idim * 8, cudaMemcpyDeviceToHost), "D2H x");
     *ier = ok ? h : FPB_ERR_CUDA;

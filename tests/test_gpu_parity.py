@@ -1115,3 +1115,21 @@ def test_host_batch_sharded_over_the_nodes_gpus(F):
     for b in range(0, 1500, 11):
         n = oq["n"][b]
         assert _same(rq["t"][b, :n], oq["t"][b, :n]) and _same(rq["c"][b, :n - 4], oq["c"][b, :n - 4])
+
+
+def test_curev_flat_abi_long_point_vector(F):
+    """fp_curev_c on ONE curve with many points: the points are spread over the device in chunks;
+    values bit-identical to the oracle, decreasing parameters anywhere -> ier = 10, x untouched."""
+    rng = np.random.default_rng(8)
+    k, idim = 3, 3
+    t = np.concatenate([np.zeros(4), np.sort(rng.uniform(0, 1, 9)), np.ones(4)])
+    n = t.size
+    c = rng.standard_normal(n * idim)
+    for m in (1, 33, 8192, 8193, 50001):
+        u = np.sort(rng.uniform(-0.05, 1.05, m))
+        xo, io = O.curev(idim, t, n, c, k, u)
+        xg, ig = F.curev(idim, t, n, c, k, u)
+        assert ig == io == 0 and _same(xg, xo), m
+    u[40000] = u[39999] - 1e-3
+    xg, ig = F.curev(idim, t, n, c, k, u)
+    assert ig == 10 and not xg.any()
