@@ -25,8 +25,9 @@ class Engine:
     def __init__(self, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("fitpack_b200 needs a CUDA device; there is no CPU fallback")
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None
-                                   else torch.device(device).index or 0)
+        idx = None if device is None else torch.device(device).index
+        # an index-less "cuda" means the CURRENT device (one process per GPU sets it to its local rank)
+        self.device = torch.device("cuda", torch.cuda.current_device() if idx is None else idx)
         h = C.c_void_p()
         check(lib().fpb_engine_create(self.device.index, C.byref(h)), "fpb_engine_create")
         self._h = h

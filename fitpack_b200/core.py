@@ -281,7 +281,7 @@ def curev(idim, t, n, c, k, u):
 
 
 def parcur_batch(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=None, ue=None, n=None, t=None,
-                 fpint=None, nrdata=None, ngpus=1):
+                 fpint=None, nrdata=None, ngpus=1, c=None):
     """Many independent parametric curves, host arrays (fp_parcur_batch_c).  x [B][m][idim]."""
     x = _f64(x)
     B, m = x.shape[0], x.shape[1]
@@ -291,7 +291,7 @@ def parcur_batch(iopt, ipar, idim, x, w, k, s, nest, u=None, ub=None, ue=None, n
     w = None if w is None else _f64(w)
     n_arr = np.zeros(B, dtype=np.int32) if n is None else np.array(n, dtype=np.int32)
     t_arr = np.zeros((B, nest)) if t is None else np.array(t, dtype=np.float64)
-    c_arr = np.zeros((B, nest * idim))
+    c_arr = np.zeros((B, nest * idim)) if c is None else np.array(c, dtype=np.float64).reshape(B, nest * idim)
     fp = np.zeros(B)
     ier = np.zeros(B, dtype=np.int32)
     fpint = np.zeros((B, nest)) if fpint is None else fpint

@@ -230,6 +230,7 @@ void fp_splder_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP_SI
     if (nu < 0 || nu > k) return;
     if (m < 1) return;
     if (k < 1 || k > 5 || n < 2 * (k + 1)) return;  // not a valid spline: nothing safe to evaluate
+    HostApiLock api_lock(-1);  // per-device serialisation (fpb_engine.h)
     fpb_engine *eng = default_engine(-1);
     if (!eng) {
         *ier = FPB_ERR_CUDA;
@@ -293,6 +294,7 @@ void fp_spalde_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k1, FP_R
 {
     *ier = FPB_INPUT_ERROR;
     if (k1 < 2 || k1 > 6 || n < 2 * k1) return;
+    HostApiLock api_lock(-1);  // per-device serialisation (fpb_engine.h)
     fpb_engine *eng = default_engine(-1);
     if (!eng) {
         *ier = FPB_ERR_CUDA;
@@ -326,6 +328,7 @@ FP_REAL fp_splint_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP
 {
     const double nan = __builtin_nan("");
     if (k < 1 || k > 5 || n < 2 * (k + 1)) return nan;
+    HostApiLock api_lock(-1);  // per-device serialisation (fpb_engine.h)
     fpb_engine *eng = default_engine(-1);
     if (!eng) return nan;
     DevSel g(eng->device);

@@ -74,6 +74,20 @@ fpb_engine *default_engine(int device)
     return g_engines[device];
 }
 
+static std::recursive_mutex g_host_api_mu[32];
+
+HostApiLock::HostApiLock(int device)
+{
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;  // no device: callers fail later
+    slot = device & 31;
+    g_host_api_mu[slot].lock();
+}
+
+HostApiLock::~HostApiLock()
+{
+    if (slot >= 0) g_host_api_mu[slot].unlock();
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -209,6 +223,16 @@ int32_t fpb_engine_synchronize(fpb_engine *eng)
 }
 
 int64_t fpb_engine_launch_count(const fpb_engine *eng) { return eng ? eng->launches : 0; }
+
+int64_t fpb_default_engine_launch_count(int32_t device)
+{
+    if (device < 0 || device >= 32) return 0;
+    std::lock_guard<std::mutex> lk(g_engines_mu);
+    int64_t total = 0;  // both default engines of the device (the second one is the overlap worker)
+    if (g_engines[device]) total += g_engines[device]->launches;
+    if (g_engines[device + 32]) total += g_engines[device + 32]->launches;
+    return total;
+}
 
 int32_t fpb_engine_set_shared_mode(fpb_engine *eng, int32_t mode)
 {
@@ -807,8 +831,6 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long
 // between two host workers, each with its own engine (stream, workspace, staging) running the
 // pipelined loop on two chunks: the copies of one chunk and the sparsely populated tail of its
 // fit overlap the other worker's compute.  Calls for one device are serialised by a mutex.
-std::mutex g_host_api_mu[64];
-
 int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_SIZE m,
                        const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
                        const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
@@ -817,7 +839,7 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
 {
     if (device < 0 && !cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return FPB_ERR_CUDA;
     if (device >= 32) return FPB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(g_host_api_mu[device]);
+    HostApiLock lk(device);
     fpb_engine *e0 = default_engine(device);
     if (!e0) return FPB_ERR_CUDA;
     const long long total = b1 - b0;
@@ -916,6 +938,7 @@ template <class F> int32_t shard_over_gpus(long long total, int ngpus, long long
     if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
     if (total < (long long)ngpus * align) ngpus = (int)std::max<long long>(1, total / std::max<long long>(align, 1));
     if (ngpus <= 1) {
+        HostApiLock lk(-1);
         fpb_engine *e = default_engine(-1);
         if (!e) return FPB_ERR_CUDA;
         return fn(e, 0LL, total);
@@ -929,6 +952,7 @@ template <class F> int32_t shard_over_gpus(long long total, int ngpus, long long
         const long long b0 = std::min(total, per * d), b1 = std::min(total, per * (d + 1));
         th.emplace_back([&, d, b0, b1]() {
             if (b0 >= b1) return;
+            HostApiLock lk(d);
             fpb_engine *e = default_engine(d);
             if (!e) {
                 rc[d] = FPB_ERR_CUDA;
@@ -1033,6 +1057,7 @@ void fp_splev_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, const 
 {
     *ier = FPB_INPUT_ERROR;
     if (m < 1) return;  // core:17844-17845
+    HostApiLock lk(-1);
     fpb_engine *eng = default_engine(-1);
     if (!eng) {
         *ier = FPB_ERR_CUDA;
@@ -1042,7 +1067,8 @@ void fp_splev_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, const 
     DeviceGuard g(eng->device);
     cudaStream_t st = eng->stream;
     DevBuf *B = eng->scratch;
-    const int chunk = 4096;
+    // up to 4096 points: one chunk of exactly m points (no padding, no extra copy or sync)
+    const int chunk = m <= 4096 ? m : 4096;
     const long long nchunks = ((long long)m + chunk - 1) / chunk;
     const size_t padded = (size_t)nchunks * chunk;
     const int ldt = std::max((n + 1) & ~1, 2 * (k + 1));

@@ -54,6 +54,19 @@ struct fpb_engine {
 namespace fpb {
 // default engine of a device (created on first use, lives until process exit)
 fpb_engine *default_engine(int device);
+// Thread-safety contract of the host-pointer entry points: the reference's
+// curfit/splev/regrid/parcur/percur are `pure` (core:1240, 17826, 16732, 15201, 15784), i.e. safe to call
+// from several threads on distinct buffers.  Here every host-pointer entry point stages through the
+// device's default engine (scratch buffers, stream), so each of them holds this per-device lock for
+// the duration of the call: concurrent callers are correct, and serialised per GPU.  Recursive, because
+// the batch entry points take it per shard and then call the single-device paths.
+struct HostApiLock {
+    explicit HostApiLock(int device);  // device < 0: the calling thread's current device
+    ~HostApiLock();
+    HostApiLock(const HostApiLock &) = delete;
+    HostApiLock &operator=(const HostApiLock &) = delete;
+    int slot = -1;
+};
 // the curfit / parcur pass pipeline (fpb_engine.cu): `p` carries the caller's arrays and scalars
 int32_t run_fit_pipeline(fpb_engine *eng, FitParams p);
 // contiguous slices [b0, b1) of `total` units over the first `ngpus` devices (<= 0: all), one host

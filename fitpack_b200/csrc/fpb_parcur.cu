@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(kCurevWarps * 32)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double *ts = curev_smem + (size_t)wib * smem_ld * (1 + idim);  // knots, then idim coefficient rows
     double *cs = ts + smem_ld;
-    const long long warp0 = (long long)blockIdx.x * kCurevWarps + wib;
-    const long long nwarps = (long long)gridDim.x * kCurevWarps;
+    const int wpb = blockDim.x >> 5;  // warps per CTA: kCurevWarps unless the tables of a long curve need the room
+    const long long warp0 = (long long)blockIdx.x * wpb + wib;
+    const long long nwarps = (long long)gridDim.x * wpb;
     for (long long j = warp0; j < nspl; j += nwarps) {
         const int nj = n[j];
         if (nj < 2 * K1 || nj > ldt) {  // not a spline of degree K
@@ -101,8 +102,18 @@ cudaError_t launch_curev_k(int nspl, int idim, const double *t, const int *n, co
                            long long ldc, const double *u, double *x, int m, int *ier, int nsm, cudaStream_t st)
 {
     const int smem_ld = (ldt + 1) & ~1;
-    const size_t smem = (size_t)kCurevWarps * smem_ld * (1 + idim) * sizeof(double);
-    if (smem > 200u * 1024u) return cudaErrorInvalidValue;  // more than ~3000 knots x coordinates per curve
+    // 8 warps per CTA; curves with many knots x coordinates get fewer warps so that their tables still
+    // fit the 200 KB a CTA may claim (one warp: n*(1+idim) <= 25 600 doubles)
+    int warps = kCurevWarps;
+    size_t smem = (size_t)warps * smem_ld * (1 + idim) * sizeof(double);
+    while (smem > 200u * 1024u && warps > 1) {
+        warps >>= 1;
+        smem = (size_t)warps * smem_ld * (1 + idim) * sizeof(double);
+    }
+    if (smem > 200u * 1024u) {
+        set_last_error("curev: knot/coefficient tables of one curve exceed 200 KB of shared memory (n*(1+idim) > 25600)");
+        return cudaErrorInvalidValue;
+    }
     auto kern = curev_kernel<K>;
     if (smem > 48u * 1024u) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -110,9 +121,9 @@ cudaError_t launch_curev_k(int nspl, int idim, const double *t, const int *n, co
     }
     int per_sm = smem > 0 ? (int)((size_t)200 * 1024 / smem) : 8;
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    long long blocks = ((long long)nspl + kCurevWarps - 1) / kCurevWarps;
+    long long blocks = ((long long)nspl + warps - 1) / warps;
     blocks = std::min<long long>(blocks, (long long)nsm * per_sm);
-    kern<<<(int)blocks, kCurevWarps * 32, smem, st>>>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, smem_ld);
+    kern<<<(int)blocks, warps * 32, smem, st>>>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, smem_ld);
     return cudaGetLastError();
 }
 
@@ -288,10 +299,12 @@ int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE id
             ok = ok && cuda_ok(cudaMemcpyAsync(d_ub, ub + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st), "H2D ub");
             ok = ok && cuda_ok(cudaMemcpyAsync(d_ue, ue + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, st), "H2D ue");
         }
-        if (iopt != 0) {
-            ok = ok && cuda_ok(cudaMemcpyAsync(d_n, n + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st), "H2D n");
-            ok = ok && cuda_ok(cudaMemcpyAsync(d_t, t + (size_t)b0 * nest, (size_t)nb * nest * 8, cudaMemcpyHostToDevice, st), "H2D t");
-        }
+        // n, t, c are inputs for iopt != 0 -- and for every iopt the caller's values must survive a curve
+        // rejected with ier=10 (the pass kernel writes nothing but ier for it, the reference leaves them
+        // untouched, core:15255-15262), so they always round-trip through the device
+        ok = ok && cuda_ok(cudaMemcpyAsync(d_n, n + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st), "H2D n");
+        ok = ok && cuda_ok(cudaMemcpyAsync(d_t, t + (size_t)b0 * nest, (size_t)nb * nest * 8, cudaMemcpyHostToDevice, st), "H2D t");
+        ok = ok && cuda_ok(cudaMemcpyAsync(d_c, c + (size_t)b0 * nest * idim, (size_t)nb * nest * idim * 8, cudaMemcpyHostToDevice, st), "H2D c");
         if (iopt == 1) {
             ok = ok && cuda_ok(cudaMemcpyAsync(d_fpint, fpint + (size_t)b0 * nest, (size_t)nb * nest * 8, cudaMemcpyHostToDevice, st), "H2D fpint");
             ok = ok && cuda_ok(cudaMemcpyAsync(d_nrd, nrdata + (size_t)b0 * nest, (size_t)nb * nest * 4, cudaMemcpyHostToDevice, st), "H2D nrdata");
@@ -374,6 +387,7 @@ void fp_curev_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_
     if (idim < 1 || idim > kMaxIdim || k < 1 || k > 5 || n < 2 * (k + 1) || nc < n * (idim - 1) + n - k - 1) return;
     for (FP_SIZE i = 1; i < m; ++i)    // any(u(2:m) < u(1:m-1)), core:1145 (checked here: the points are
         if (u[i] < u[i - 1]) return;   // spread over many warps below, each sees only its own chunk)
+    HostApiLock api_lock(-1);  // per-device serialisation (fpb_engine.h)
     fpb_engine *eng = default_engine(-1);
     if (!eng) {
         *ier = FPB_ERR_CUDA;

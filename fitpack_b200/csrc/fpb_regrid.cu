@@ -1194,6 +1194,7 @@ void fp_regrid_c(FP_SIZE iopt, FP_SIZE mx, const FP_REAL *x, FP_SIZE my, const F
 {
     *ier = FPB_INPUT_ERROR;
     if (mx < 1 || my < 1) return;
+    HostApiLock api_lock(-1);  // per-device serialisation (fpb_engine.h)
     fpb_engine *eng = default_engine(-1);
     if (!eng) {
         *ier = FPB_ERR_CUDA;
@@ -1246,6 +1247,7 @@ FP_FLAG fp_bispev_c(const FP_REAL *tx, FP_SIZE nx, const FP_REAL *ty, FP_SIZE ny
     (void)iwrk;
     const long long lwest = (long long)(kx + 1) * mx + (long long)(ky + 1) * my;
     if (lwrk < lwest || kwrk < (mx + my) || mx < 1 || my < 1) return FPB_INPUT_ERROR;
+    HostApiLock api_lock(-1);  // per-device serialisation (fpb_engine.h)
     fpb_engine *eng = default_engine(-1);
     if (!eng) return FPB_ERR_CUDA;
     DevGuard g(eng->device);

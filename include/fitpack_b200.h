@@ -155,6 +155,10 @@ int32_t fpb_engine_synchronize(fpb_engine *eng);
 int32_t fpb_engine_set_shared_mode(fpb_engine *eng, int32_t mode);
 /* number of kernels this engine has launched since creation (bench bookkeeping) */
 int64_t fpb_engine_launch_count(const fpb_engine *eng);
+/* same counter for the DEFAULT engine of `device` -- the one the host-pointer entry points
+   (fp_curfit_c, fp_curfit_batch_c, ...) run on; 0 when that device has not been used yet.  Lets a
+   caller verify that a batch sharded with ngpus > 1 really ran on several GPUs. */
+int64_t fpb_default_engine_launch_count(int32_t device);
 /* device time in ms of the last dominant kernel (fit or splev), measured with
    CUDA events on the engine's stream; valid after fpb_engine_synchronize */
 double  fpb_engine_last_kernel_ms(fpb_engine *eng);
