@@ -38,16 +38,22 @@ M, K, SIGMA, NEST = 256, 3, 0.1, 359
 S = M * SIGMA * SIGMA  # 2.56
 B_PER_GPU = 1 << 20
 SPLEV_NSPL, SPLEV_M, SPLEV_K, SPLEV_N = 1 << 20, 954, 5, 32
-SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 22, 512, 3, 28   # config 3 shape, 2^22 curves/GPU
+SHARED_B, SHARED_M, SHARED_K, SHARED_NINT = 1 << 24, 512, 3, 28   # config 3 AT ITS STATED SIZE: 2^24 curves x 512 points on one GPU (68.7 GB of y)
 GRID_M, GRID_K, GRID_SIGMA, GRID_NEST = 4096, 3, 0.05, 128          # config 4: 4096 x 4096 grid, kx=ky=3
 PARCUR_B, PARCUR_M, PARCUR_IDIM = 1 << 19, 256, 2                   # parametric curves
 PERCUR_B, PERCUR_M = 1 << 20, 256                                   # periodic curves
-# DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum,
-# profiles/r01d_kernels.md, profiles/r01b_kernels.md); the bench itself never runs under ncu.
-# fit pipeline at 2^20 curves (profiles/r01d_kernels.md + the per-launch times of
-# profiles/r01d_profile.sh's fit launch list): the captured mid pass moved 22.83 + 3.93 GB in 5.95 ms;
-# the 20 pass launches of one fit take 107.9 ms in total; part 2 moved 214.9 + 41.0 GB.
-NCU_FIT_DRAM_BYTES_PER_FIT = ((22.83e9 + 3.928e9) / 5.953 * 107.94 + (214.9e9 + 41.03e9)) / 1048576
+# DRAM traffic per unit measured with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum); the bench
+# itself never runs under ncu.  The fit pipeline's figure is read from profiles/fit_traffic.json, which is
+# rewritten whenever a new capture of the pass / part-2 kernels is committed (it names its source round).
+def fit_traffic_record():
+    try:
+        with open(os.path.join(ROOT, "profiles", "fit_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_fit"]), str(d["source"])
+    except Exception:
+        return None, "no committed ncu capture (profiles/fit_traffic.json missing)"
+
+
 NCU_SPLEV_DRAM_BYTES_PER_POINT = (8.561e9 + 7.965e9) / (1048576 * 954)   # profiles/r01b_kernels.md
 NCU_SHARED_DRAM_BYTES_PER_CURVE = (17.85e9 + 1.839e9) / 4194304   # shared_apply2 (r01b)
 
@@ -59,6 +65,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--curves", type=int, default=B_PER_GPU, help="curves per GPU per step")
+    ap.add_argument("--shared-curves", type=int, default=SHARED_B, help="config-3 curves per GPU")
     ap.add_argument("--no-splev", action="store_true")
     ap.add_argument("--no-shared", action="store_true")
     ap.add_argument("--no-regrid", action="store_true")
@@ -138,22 +145,28 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def synth_device(torch, dev, B, m, seed):
-    """C2 synthetic batch generated in HBM, point-major [m][B]."""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    f64 = torch.float64
-    x = torch.rand((m, B), generator=g, device=dev, dtype=f64)
-    x.mul_(2).sub_(1).mul_(0.3)
-    x.add_(torch.arange(m, device=dev, dtype=f64)[:, None]).div_(m - 1)
-    x[0] = 0.0
-    x[-1] = 1.0
-    A = torch.rand((1, B), generator=g, device=dev, dtype=f64) * 1.5 + 0.5
-    f = torch.rand((1, B), generator=g, device=dev, dtype=f64) * 3 + 1
-    ph = torch.rand((1, B), generator=g, device=dev, dtype=f64) * (2 * 3.141592653589793)
-    y = torch.sin(x * (2 * 3.141592653589793) * f + ph).mul_(A)
-    y.add_(torch.randn((m, B), generator=g, device=dev, dtype=f64), alpha=SIGMA)
+SEED = 1234
+PARITY_SAMPLE = 8192     # curves of the SAME batch re-fitted by the oracle (n, fp, ier bit-identical)
+
+
+def synth_device(torch, dev, b0, B, m):
+    """Config-2 batch generated in HBM, point-major [m][B]: curves b0 .. b0+B-1 of the counter-based
+    generator tests/synthdata.py -- the CPU arm regenerates the same curves bit for bit."""
+    import synthdata
+    x = torch.empty((m, B), device=dev, dtype=torch.float64)
+    y = torch.empty((m, B), device=dev, dtype=torch.float64)
+    step = 1 << 18
+    for c0 in range(0, B, step):
+        nb = min(step, B - c0)
+        xc, yc = synthdata.c2_curves(torch, b0 + c0, nb, m, SIGMA, SEED, device=dev)
+        x[:, c0:c0 + nb] = xc
+        y[:, c0:c0 + nb] = yc
     return x, y
+
+
+def synth_host(np, b0, B, m):
+    import synthdata
+    return synthdata.c2_curves(np, b0, B, m, SIGMA, SEED)
 
 
 def fit_flops(n, passes, piters, m=M, k=K):
@@ -186,12 +199,15 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import numpy as np
+    o3 = os.path.join(ROOT, "oracle", "libfitpack_oracle_O3.so")
+    build_kind = "-O2 -ffp-contract=off"
+    if os.path.exists(o3):   # the CPU arm is timed at -O3 (same source, still no FMA)
+        os.environ["FITPACK_ORACLE_LIB"] = o3
+        build_kind = "-O3 -ffp-contract=off"
     import oracle_lib as O
-    from refdata import synth_curves
     # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on explicitly
     threads = host_threads()
-    rng = np.random.default_rng(1234)
-    x, y = synth_curves(rng, 65536, M, SIGMA)
+    x, y = synth_host(np, 0, 65536, M)   # the first 65536 curves of rank 0's GPU batch, bit for bit
     t0 = time.perf_counter()
     O.curfit_batch(0, x[:256], y[:256], None, K, S, NEST, nthreads=threads)
     rate = 256 / (time.perf_counter() - t0)
@@ -206,7 +222,8 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     assert (out["ier"] <= 0).all()
-    desc = "first %d curves of the config-2 generator per step (bounded CPU sample)" % sample
+    desc = ("first %d curves of the GPU arm's rank-0 batch (counter-based generator, bit-identical inputs) "
+            "per step; oracle port built %s (no FMA: the reference's arithmetic)" % (sample, build_kind))
     print(json.dumps({
         "impl": "reference", "metric": "curve fits/sec (256-pt, k=3)", "value": value,
         "unit": "fits/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -269,7 +286,7 @@ def main():
     eng = Engine(dev)
     B = args.curves
     hbm_peak, peak_src = measured_peaks()
-    x, y = synth_device(torch, dev, B, M, 1234 + rank)
+    x, y = synth_device(torch, dev, rank * B, B, M)
     out = {}
     # ---------------------------------------------------------------- fit: device-resident
     for _ in range(args.warmup):
@@ -311,20 +328,21 @@ def main():
         gathered = int(n_all.numel())
     alg_bytes = B * (2 * 8 * M + 16 * mean_n + 16)
     fit_ms = kernel_ms[-1]
+    traffic_per_fit, traffic_src = fit_traffic_record()
     roof = {"bound": "hbm", "kernel": "fit pipeline: curfit_pass_kernel<3> x R + curfit_part2_kernel<3>",
             "achieved": alg_bytes / (fit_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "traffic": NCU_FIT_DRAM_BYTES_PER_FIT * B, "traffic_source": "ncu dram bytes per fit "
-            "(pass + part-2 kernels, profiles/r01d_kernels.md) x curves per launch sequence; "
-            "workspace traffic (stored basis values, G copies, per-pass state), not re-reads of the input",
+            "traffic": None if traffic_per_fit is None else traffic_per_fit * B,
+            "traffic_source": traffic_src,
             "peak_source": peak_src,
             "algorithmic_bytes_per_fit": alg_bytes / B,
             "note": "fit kernel is FP64 issue/latency bound (~%.0f kflop per 4.4 KB): HBM "
                     "fraction is tiny by construction; see fp64" % (flops / B / 1e3)}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    # the same kernels measured by the bytes they actually move (ncu): workspace traffic puts the
-    # pipeline at about half of the HBM peak, next to its FP64-pipe share (see fp64)
-    roof["traffic_gbs"] = roof["traffic"] / (fit_ms * 1e-3) / 1e9
-    roof["traffic_frac_of_peak"] = roof["traffic_gbs"] / hbm_peak
+    # the same kernels measured by the bytes they actually move (ncu): workspace traffic next to the
+    # FP64-pipe share (see fp64)
+    if traffic_per_fit is not None:
+        roof["traffic_gbs"] = roof["traffic"] / (fit_ms * 1e-3) / 1e9
+        roof["traffic_frac_of_peak"] = roof["traffic_gbs"] / hbm_peak
     dmul_dadd = eng.probe_fp64_gops(False)
     dfma = eng.probe_fp64_gops(True)
     ndiv_t, nsqrt_t = fit_divsqrt(n_f, stats[:, 0], stats[:, 1])
@@ -353,6 +371,35 @@ def main():
             "note": "the bound of this pipeline: measured rates of unfused DMUL/DADD, IEEE division and square "
                     "root on this GPU; a correctly rounded division costs ~13.6 FP64 issue slots"}
 
+    roof["fp64_bound"] = {
+        "probe_gops": {"dmul_dadd": dmul_dadd, "dfma": dfma, "ddiv": ddiv, "dsqrt": dsqrt},
+        "probe_source": "fpb_probe_fp64_gops on this GPU, this run (MEASURED_PEAKS.json has no FP64 figure)",
+        "achieved_gflops": fp64["achieved_gflops"], "frac_of_unfused_peak": fp64["frac_of_unfused_peak"],
+        "issue_slots_per_fit": fp64["issue_slots_per_fit"],
+        "frac_of_fp64_issue_roofline": fp64["frac_of_fp64_issue_roofline"],
+        "mean_lsq_passes": fp64["mean_lsq_passes"], "mean_p_iters": fp64["mean_p_iters"], "mean_n": mean_n}
+    roof["secondary"] = []   # the other kernels of the metric, filled in below (driver keeps `roofline`)
+
+    # ---------------------------------------------------------------- parity sample on the SAME batch
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        import oracle_lib as O
+        ns_ = min(PARITY_SAMPLE, B)
+        xs_h, ys_h = synth_host(np, 0, ns_, M)
+        same_in = bool(np.array_equal(xs_h, x[:, :ns_].t().cpu().numpy())
+                       and np.array_equal(ys_h, y[:, :ns_].t().cpu().numpy()))
+        op = O.curfit_batch(0, xs_h, ys_h, None, K, S, NEST, nthreads=host_threads())
+        n_h, fp_h, ier_h = (res[kk][:ns_].cpu().numpy() for kk in ("n", "fp", "ier"))
+        t_h, c_h = res["t"][:ns_].cpu().numpy(), res["c"][:ns_].cpu().numpy()
+        same_tc = all(np.array_equal(t_h[b, :op["n"][b]], op["t"][b, :op["n"][b]])
+                      and np.array_equal(c_h[b, :op["n"][b] - K - 1], op["c"][b, :op["n"][b] - K - 1])
+                      for b in range(ns_))
+        parity = {"curves": ns_, "inputs_bit_identical_host_vs_device": same_in,
+                  "n_ier_identical": bool(np.array_equal(n_h, op["n"]) and np.array_equal(ier_h, op["ier"])),
+                  "fp_bit_identical": bool(np.array_equal(fp_h, op["fp"])),
+                  "t_c_bit_identical": bool(same_tc),
+                  "what": "first %d curves of this batch re-fitted by the CPU oracle (reference algorithm)" % ns_}
+
     # ---------------------------------------------------------------- fit: end to end (host buffers)
     e2e = None
     if not args.no_e2e:
@@ -377,7 +424,7 @@ def main():
                 raise RuntimeError("fp_curfit_batch_c failed: " + L.fpb_last_error().decode())
 
         e2e_step()  # warm-up (allocates the staging buffers)
-        esteps = max(1, min(args.steps, 2))
+        esteps = max(1, args.steps)     # timed over the same number of steps as `value`
         barrier()
         t0 = time.perf_counter()
         for _ in range(esteps):
@@ -436,6 +483,11 @@ def main():
                              "unit": "GB/s", "frac": bytes_alg / (kms * 1e-3) / 1e9 / hbm_peak,
                              "traffic": (NCU_SPLEV_DRAM_BYTES_PER_POINT * ns * ms) if mode == 1 else None,
                              "peak_source": peak_src}}
+        for name in ("fast", "exact"):
+            rr = dict(splev[name]["roofline"])
+            rr.update({"value_gbs": splev[name]["value"], "gpts_per_s": splev[name]["gpts_per_s"],
+                       "ms_per_step": splev[name]["ms_per_step"], "workload": splev["config"]["workload"]})
+            roof["secondary"].append(rr)
         splev["gpu_launches"] = 2 * args.steps
         del t, c, nvec, xe, so, r
         torch.cuda.empty_cache()
@@ -445,20 +497,23 @@ def main():
     if not args.no_shared:
         torch.cuda.empty_cache()
         f64 = torch.float64
-        Bs, ms, ks, nint = SHARED_B, SHARED_M, SHARED_K, SHARED_NINT
+        Bs, ms, ks, nint = args.shared_curves, SHARED_M, SHARED_K, SHARED_NINT
         gsh = torch.Generator(device=dev)
         gsh.manual_seed(7 + rank)
         xs_ = torch.linspace(0, 1, ms, device=dev, dtype=f64)
         nn = 2 * (ks + 1) + nint
         tsh = torch.zeros(nn, device=dev, dtype=f64)
         tsh[ks + 1:ks + 1 + nint] = torch.linspace(0, 1, nint + 2, device=dev, dtype=f64)[1:-1]
-        ysh = torch.randn((ms, Bs), generator=gsh, device=dev, dtype=f64)   # point-major
+        ysh = torch.empty((ms, Bs), device=dev, dtype=f64)   # point-major; 68.7 GB at 2^24 curves
+        for r0 in range(0, ms, 64):                           # filled in row blocks (no second 68 GB temporary)
+            ysh[r0:r0 + 64].normal_(generator=gsh)
         sho = {}
         nk1 = nn - ks - 1
         bytes_curve = 8 * ms + 8 * nk1 + 12
         flops_curve = ms * (1 + 6 * (ks + 1) + 2) + nk1 * (2 * ks + 1)
         shared = {"config": {"workload": "shared-abscissa least squares (iopt=-1): %d curves x %d points per "
-                                         "GPU, k=3, %d interior knots (config 3 shape)" % (Bs, ms, nint)}}
+                                         "GPU, k=3, %d interior knots (config 3%s)"
+                                         % (Bs, ms, nint, " at its stated size" if Bs == 1 << 24 else " shape")}}
         l0 = eng.launches
         for smode, sname in ((0, "exact"), (1, "fast")):
             for _ in range(max(1, args.warmup)):
@@ -487,6 +542,36 @@ def main():
             else:
                 shared["fast"] = blk
         shared["gpu_launches"] = int(eng.launches - l0)
+        for blk in (shared, shared["fast"]):
+            rr = dict(blk["roofline"])
+            rr.update({"value_fits_per_s": blk["value"], "ms_per_step": blk["ms_per_step"],
+                       "workload": shared["config"]["workload"]})
+            roof["secondary"].append(rr)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            # CPU baseline of this block + parity on the SAME curves: the first and the last 4096 curves of the
+            # batch (the last ones sit 2^33 elements into y: an index-width error would show there) re-fitted by
+            # the oracle's per-curve curfit(iopt=-1); exact mode must agree bit for bit
+            import oracle_lib as O
+            nthr_ = host_threads()
+            eng.curfit_shared(xs_, ysh, tsh, k=ks, out=sho, mode=0)
+            torch.cuda.synchronize()
+            ns_ = min(4096, Bs // 2)
+            sel = torch.cat([torch.arange(ns_, device=dev), torch.arange(Bs - ns_, Bs, device=dev)])
+            y_h = np.ascontiguousarray(ysh[:, sel].t().cpu().numpy())
+            t_h = np.zeros((2 * ns_, nn))
+            t_h[:] = tsh.cpu().numpy()
+            n_h = np.full(2 * ns_, nn, np.int32)
+            t0 = time.perf_counter()
+            oc = O.curfit_batch(-1, xs_.cpu().numpy(), y_h, None, ks, 0.0, nn, xb=0.0, xe=1.0, shared_x=True,
+                                n=n_h, t=t_h, nthreads=nthr_)
+            dts_ = time.perf_counter() - t0
+            c_g = sho["c"][sel].cpu().numpy()
+            fp_g = sho["fp"][sel].cpu().numpy()
+            shared["cpu_baseline"] = {
+                "value": 2 * ns_ / dts_, "unit": "fits/s", "cores": nthr_, "kind": "port",
+                "sample": "first and last %d curves of the same batch, oracle curfit(iopt=-1) per curve, OpenMP over "
+                          "curves; c and fp bit-identical to the GPU result (exact mode): %s"
+                          % (ns_, bool(np.array_equal(c_g[:, :nk1], oc["c"][:, :nk1]) and np.array_equal(fp_g, oc["fp"])))}
         del ysh, sho, r
         torch.cuda.empty_cache()
 
@@ -731,10 +816,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle_lib as O
-        from refdata import synth_curves
         rng = np.random.default_rng(1234)
         nthr = host_threads()
-        xs, ys = synth_curves(rng, 65536, M, SIGMA)
+        xs, ys = synth_host(np, 0, 65536, M)    # the first 65536 curves of the batch the GPU fitted
         t0 = time.perf_counter()
         O.curfit_batch(0, xs[:512], ys[:512], None, K, S, NEST, nthreads=nthr)
         rate = 512 / (time.perf_counter() - t0)
@@ -764,8 +848,9 @@ def main():
                 "sample": "%d k=5 splines x %d points, oracle splev (reference arithmetic), OpenMP over "
                           "splines" % (nsp, ms_)}
         cpu = {"value": sample / dt, "unit": "fits/s", "cores": nthr, "kind": "port",
-               "sample": "%d config-2 curves, oracle port of the reference algorithm, OpenMP over "
-                         "curves (reference is Fortran: no compiler in this image)" % sample}
+               "sample": "first %d curves of the SAME batch (counter-based generator, inputs bit-identical to the "
+                         "device batch), oracle port of the reference algorithm built -O2 -ffp-contract=off, OpenMP "
+                         "over curves (reference is Fortran: no compiler in this image)" % sample}
 
     if rank == 0:
         line = {
@@ -779,7 +864,10 @@ def main():
                        "curves_per_gpu": B, "layout": "point-major SoA in HBM",
                        "l2": "inputs (%.1f GB/step) exceed the 126 MB L2; no flush needed"
                              % (2 * B * M * 8 / 1e9),
-                       "success_fraction": ok_frac, "gathered_summary_curves": gathered},
+                       "success_fraction": ok_frac, "gathered_summary_curves": gathered,
+                       "generator": "counter-based (tests/synthdata.py): curve b of rank r = global curve r*B+b, "
+                                    "bit-identical on host and device",
+                       "parity_sample": parity},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "fp64": fp64, "splev": splev, "shared_lsq": shared, "parcur": parc, "percur": perc, "regrid": grid,
             "cpu_baseline": cpu,
