@@ -55,7 +55,7 @@ def build_variant(tag, defines):
             raise RuntimeError(r.stdout + r.stderr)
         objs.append(o)
     out = os.path.join(HERE, "libfitpack_b200_%s.so" % tag)
-    subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-lcudart", "-ldl"])
     return out
 
 
@@ -93,7 +93,7 @@ def build(force=False, verbose=False):
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -288,6 +288,7 @@ namespace fpb {
 // strides and scalars set; this fills in the engine-owned workspace / state and runs the passes.
 int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
 {
+    NvtxRange nvtx_pipeline(p.periodic ? "fpb:percur pipeline" : (p.par ? "fpb:parcur pipeline" : "fpb:curfit pipeline"));
     const int nbatch = p.nbatch, iopt = p.iopt, m = p.m, k = p.k, nest = p.nest;
     int *n = p.n;
     const FitLayout L = fit_layout(m, k, nest, p.idim, p.periodic);
@@ -509,6 +510,7 @@ int32_t fp_splev_batch_dev_c(fpb_engine *eng, FP_SIZE nspl, const FP_REAL *t, co
         set_last_error("fp_splev_batch_dev_c: k must be 1..5, ldt >= 2k+2, mode 0/1, e 0..3");
         return FPB_ERR_ARG;
     }
+    NvtxRange nvtx_splev("fpb:splev batch");
     SplevParams p;
     p.nspl = nspl; p.ldt = ldt; p.k = k; p.m = m; p.e = e; p.mode = mode; p.nshared = nshared;
     p.t = t; p.c = c; p.x = x; p.n = n; p.y = y; p.ier = ier; p.lidx = lidx;
@@ -585,6 +587,7 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long
                             FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
                             FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata)
 {
+    NvtxRange nvtx_slice("fpb:host slice (H2D | transpose+fit | D2H)");
     DeviceGuard g(eng->device);
     if (!g.ok) return FPB_ERR_CUDA;
     if (!eng->s_in) {

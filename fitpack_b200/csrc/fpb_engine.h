@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <functional>
+#include <nvtx3/nvToolsExt.h>
 #include <string>
 
 #include "fpb_kernels.h"
@@ -60,6 +61,15 @@ fpb_engine *default_engine(int device);
 // device's default engine (scratch buffers, stream), so each of them holds this per-device lock for
 // the duration of the call: concurrent callers are correct, and serialised per GPU.  Recursive, because
 // the batch entry points take it per shard and then call the single-device paths.
+// NVTX range (tracing hooks) -- shows the pipeline stages in Nsight timelines; a no-op
+// when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 struct HostApiLock {
     explicit HostApiLock(int device);  // device < 0: the calling thread's current device
     ~HostApiLock();

@@ -9,7 +9,7 @@ built from the classical parabolic approximation refined once (max error ~1e-3, 
 sigma = 0.1, so the fits see the same problem as with a true sine); the noise is the sum of four uniforms
 scaled to unit variance.
 
-    x[b, i] = (i + 0.3 (2 u - 1)) / (m - 1),  x[b, 0] = 0, x[b, m-1] = 1       (jittered grid, sorted)
+    x[b, i] = (i + 0.3 (2 u - 1)) * (1/(m - 1)),  x[b, 0] = 0, x[b, m-1] = 1   (jittered grid, sorted)
     y[b, i] = A_b * wave(f_b * x + p_b) + sigma * noise,   A in [0.5, 2), f in [1, 4), p in [0, 1)
 
 `c2_curves(np, ...)` returns curve-major [nb][m] arrays; `c2_curves(torch, ..., device=dev)` the same values
@@ -91,7 +91,9 @@ def _c2_body(xp, base, i, fi, m, sigma, is_torch):
         return _hash_uniform(xp, ctr + k(_s64(s * _KT)))
 
     u = stream(pt, 1)
-    x = (fi + (u * 2.0 - 1.0) * 0.3) / float(m - 1)
+    # multiply by the reciprocal instead of dividing: torch's CUDA division by a Python scalar is itself
+    # implemented as a multiplication by 1/scalar, numpy's is a true division -- a product is the same everywhere
+    x = (fi + (u * 2.0 - 1.0) * 0.3) * (1.0 / float(m - 1))
     first, last = (i == 0), (i == m - 1)
     x = xp.where(first, xp.zeros_like(x), x)
     x = xp.where(last, xp.ones_like(x), x)

@@ -58,7 +58,7 @@ def test_flat_entry_points_are_reentrant_from_8_host_threads(F):
             xe = np.sort(rng.uniform(-0.05, 1.05, 10 + 3 * m))
             o = O.curfit(0, x, y, None, 0.0, 1.0, k, s, nest)
             yo, io = O.splev(o["t"], o["n"], o["c"], k, xe, e=0)
-            do, ido = O.splder(o["t"], o["n"], o["c"], k, 1, xe, e=0)
+            do = O.splder(o["t"], o["n"], o["c"], k, 1, xe, e=0)[0]
             ue = np.clip(xe, 0.0, 1.0)
             co, ico = O.curev(1, o["t"], o["n"], o["c"][:o["n"]], k, ue)
             per.append(dict(m=m, k=k, x=x, y=y, s=s, nest=nest, xe=xe, ue=ue, o=o, yo=yo, do=do, co=co))
@@ -77,7 +77,7 @@ def test_flat_entry_points_are_reentrant_from_8_host_threads(F):
                 assert _same(g["t"][:n], o["t"][:n]) and _same(g["c"][:n - j["k"] - 1], o["c"][:n - j["k"] - 1]), (tid, "t/c")
                 yg, ig = F.splev(g["t"], n, g["c"], j["k"], j["xe"], e=0)
                 assert ig == 0 and _same(yg, j["yo"]), (tid, "splev")
-                dg, idg = F.splder(g["t"], n, g["c"], j["k"], 1, j["xe"], e=0)
+                dg, idg = F.splder(g["t"], n, g["c"], j["k"], 1, j["xe"], e=0)[:2]
                 assert idg == 0 and _same(dg, j["do"]), (tid, "splder")
                 cg, icg = F.curev(1, g["t"], n, g["c"][:n], j["k"], j["ue"])
                 assert icg == 0 and _same(np.asarray(cg).ravel(), np.asarray(j["co"]).ravel()), (tid, "curev")
@@ -90,6 +90,15 @@ def test_flat_entry_points_are_reentrant_from_8_host_threads(F):
     for t in th:
         t.join()
     assert not errors, errors[:3]
+
+
+def test_counter_based_generator_is_bit_identical_on_host_and_device():
+    """tests/synthdata.py: the config-2 curves bench.py fits on the GPU are the curves its CPU arm fits"""
+    import torch
+    import synthdata
+    xh, yh = synthdata.c2_curves(np, 1000, 3000, 256, 0.1, 1234)
+    xd, yd = synthdata.c2_curves(torch, 1000, 3000, 256, 0.1, 1234, device=torch.device("cuda", 0))
+    assert _same(xh, xd.t().cpu().numpy()) and _same(yh, yd.t().cpu().numpy())
 
 
 def test_parcur_batch_rejected_rows_keep_the_callers_n_t_c(F):
