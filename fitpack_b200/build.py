@@ -43,7 +43,7 @@ def build_variant(tag, defines):
     """Experimental side build (tuning only): same sources with extra -D flags, written to
     libfitpack_b200_<tag>.so; select it at run time with FITPACK_B200_LIB=<path>."""
     nvcc = nvcc_path()
-    bdir = os.path.join(HERE, "_build", "var_" + tag)
+    bdir = os.path.join("/tmp", "fitpack_b200_var_" + tag)   # objects out of tree: the GPU snapshot is size-capped
     os.makedirs(bdir, exist_ok=True)
     objs = []
     for src in SOURCES:

@@ -71,6 +71,123 @@ constexpr unsigned FULL = 0xffffffffu;
 #define Q_(it, j) WS(p.off_q, (it) * K1 + (j))  /* it 0-based, j 0-based */
 #define NRD_(i) wsi[(size_t)((i) - 1) * 32]
 
+// Build switches (A/B tuning, profiles/scripts/ab_fit.py): the defaults are the shipped configuration.
+//  FPB_FIT_STOREQ = 1: the least-squares pass stores the basis values q(m,k+1) in the workspace and the
+//  residual passes read them back (what the reference does, core:1295 / 4886); 0: the residual passes
+//  recompute them with bspl_tab -- bit-identical, and 2/3 of the pipeline's DRAM traffic disappears.
+#ifndef FPB_FIT_STOREQ
+#define FPB_FIT_STOREQ 0
+#endif
+//  FPB_FIT_SPAN_SMEM = 1: the span reciprocals of bspl_tab live in shared memory (after the stream ring)
+//  instead of registers.
+#ifndef FPB_FIT_SPAN_SMEM
+#define FPB_FIT_SPAN_SMEM 0
+#endif
+#if FPB_FIT_SPAN_SMEM
+#define FPB_SPAN_STRIDE kFitThreads
+#else
+#define FPB_SPAN_STRIDE 0
+#endif
+
+//  FPB_FIT_STREAM = 1: point streams through a cp.async ring in shared memory; 0: plain loads, one point of
+//  register lookahead.   FPB_FIT_FASTDIV = 1: fpbspl through the span-reciprocal table (bspl_tab).
+#ifndef FPB_FIT_FASTDIV
+#define FPB_FIT_FASTDIV 1
+#endif
+//  FPB_FIT_GIVENS_SHARED = 1: cos and sin of a rotation share one reciprocal refinement (givens_shared).
+#ifndef FPB_FIT_GIVENS_SHARED
+#define FPB_FIT_GIVENS_SHARED 1
+#endif
+#if FPB_FIT_GIVENS_SHARED
+#define FPB_GIVENS givens_shared
+#else
+#define FPB_GIVENS givens
+#endif
+//  FPB_FIT_PFDIST: the plain-load point streams ask L2 for the rows they will read this many points later.
+#ifndef FPB_FIT_PFDIST
+#define FPB_FIT_PFDIST 0   // measured: per-lane L2 prefetches cost more than they hide (profiles/r02_ab.md)
+#endif
+
+// ---- point streams ---------------------------------------------------------------------------------
+// x(i), y(i,:), w(i) of the thread's curve.  ASYNC: they flow through a ring of `depth` slots in shared
+// memory filled by 8-byte cp.async copies issued `depth` points ahead, so the DRAM/L2 latency of the stream
+// is covered without holding the values in registers.  Ring element e of slot s sits at
+// ring[(s*E + e) * NT], E = 1 + nd + HAS_W doubles per point.  !ASYNC: plain loads, the next point is
+// requested while the current one is processed.
+template <int ND, bool HAS_W, bool ASYNC>
+struct PointStream {
+    double *ring;
+    const double *xp, *yp, *wp;
+    size_t x_si, y_si, y_sd, w_si;
+    int nd, m, depth, E;
+    double xn, yn[ND], wn;   // !ASYNC: the prefetched point
+    __device__ __forceinline__ void issue(int it) const
+    {
+        const int ii = min(it, m - 1);
+        double *slot = ring + (size_t)((it & (depth - 1)) * E) * kFitThreads;
+        cp_async8(slot, xp + (size_t)ii * x_si);
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (d < nd) cp_async8(slot + (size_t)(1 + d) * kFitThreads, yp + (size_t)ii * y_si + (size_t)d * y_sd);
+        if (HAS_W) cp_async8(slot + (size_t)(1 + nd) * kFitThreads, wp + (size_t)ii * w_si);
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void load(int it)
+    {
+        const int ii = min(it, m - 1);
+        xn = xp[(size_t)ii * x_si];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (d < nd) yn[d] = yp[(size_t)ii * y_si + (size_t)d * y_sd];
+        wn = HAS_W ? wp[(size_t)ii * w_si] : 1.0;
+        if (FPB_FIT_PFDIST > 0) {
+            const int ip = min(it + FPB_FIT_PFDIST, m - 1);
+            prefetch_l2(xp + (size_t)ip * x_si);
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (d < nd) prefetch_l2(yp + (size_t)ip * y_si + (size_t)d * y_sd);
+            if (HAS_W) prefetch_l2(wp + (size_t)ip * w_si);
+        }
+    }
+    __device__ __forceinline__ void start()
+    {
+        if (ASYNC) {
+            for (int d = 0; d < depth; ++d) issue(d);
+        } else {
+            load(0);
+        }
+    }
+    // point `it` (called for it = 0, 1, 2, ... in order); requests a later point
+    __device__ __forceinline__ void fetch(int it, double &x, double (&y)[ND], double &w)
+    {
+        if (ASYNC) {
+            // point `it` has landed once at most depth-1 younger groups are pending
+            if (depth == 8) cp_async_wait<7>();
+            else if (depth == 4) cp_async_wait<3>();
+            else if (depth == 2) cp_async_wait<1>();
+            else cp_async_wait<0>();
+            const double *sl = ring + (size_t)((it & (depth - 1)) * E) * kFitThreads;
+            x = sl[0];
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (d < nd) y[d] = sl[(size_t)(1 + d) * kFitThreads];
+            w = HAS_W ? sl[(size_t)(1 + nd) * kFitThreads] : 1.0;
+            issue(it + depth);
+        } else {
+            x = xn;
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (d < nd) y[d] = yn[d];
+            w = wn;
+            load(it + 1);
+        }
+    }
+    __device__ __forceinline__ void drain() const
+    {
+        if (ASYNC) cp_async_wait<0>();
+    }
+};
+
 // interpolation knots, core:4806-4816 / 4975-4985
 template <int K>
 __device__ __forceinline__ void interp_knots(const FitParams &p, double *wsd, const double *xp, int m)
@@ -116,18 +233,22 @@ __device__ __forceinline__ void back_subst(const FitParams &p, double *wsd, int 
     }
 }
 
-// sum of squared residuals of the current c over all points using the stored
-// basis values q (get_fp loop, core:5061-5069 / fppara core:9147-9159); when FPINT is set also the
-// per-interval split of core:4942-4966 (fppara core:9023-9052).  Loads of consecutive points are
-// issued together (they do not depend on the interval walk) to cover HBM latency.
+// sum of squared residuals of the current c over all points (get_fp loop, core:5061-5069 / fppara
+// core:9147-9159); when FPINT is set also the per-interval split of core:4942-4966 (fppara
+// core:9023-9052).  The reference multiplies c with the basis values q(it,:) the least-squares pass
+// stored; here they are recomputed with bspl_tab from the same knots in the same interval (the walk of
+// fp_knot_interval, `lq`) -- the same bits -- while the coefficient window follows the reference's own,
+// lagging interval counter `l` of this loop (at most one step per point).
 template <int K, bool FPINT, bool HAS_W, int IDIM>
-__device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd, const double *xp,
-                                                const double *yp, const double *wp, size_t x_si,
-                                                size_t y_si, size_t y_sd, size_t w_si, int m,
+__device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd, double *ring,
+                                                const double *xp, const double *yp, const double *wp,
+                                                size_t x_si, size_t y_si, size_t y_sd, size_t w_si, int m,
                                                 int nk1, int nrint, bool on)
 {
-    constexpr int K1 = K + 1, K2 = K + 2, U = 2, ND = IDIM > 0 ? IDIM : kMaxIdim;
+    constexpr int K1 = K + 1, K2 = K + 2, ND = IDIM > 0 ? IDIM : kMaxIdim;
     const int nd = IDIM > 0 ? IDIM : p.idim;
+    PointStream<ND, HAS_W, FPB_FIT_STREAM != 0> ps{ring, xp, yp, wp, x_si, y_si, y_sd, w_si, nd, m, p.sdepth,
+                                                   1 + nd + (HAS_W ? 1 : 0)};
     double cw[ND][K1];
     double fpart = 0.0, tl = 0.0;
     int l = K2, i = 1;
@@ -137,67 +258,85 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
         for (int j = 0; j < K1; ++j) cw[d][j] = (on && d < nd) ? CD_(d, j + 1) : 0.0;
     }
     if (on) tl = T_(l);
-    for (int it0 = 0; it0 < m; it0 += U) {
-        double xv[U], yv[U][ND], wv[U], qv[U][K1];
+#if !FPB_FIT_STOREQ
+    double tw[2 * K];
+    int lq = K1;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = min(it0 + u, m - 1);
-            xv[u] = xp[(size_t)it * x_si];
-#pragma unroll
-            for (int d = 0; d < ND; ++d)
-                if (d < nd) yv[u][d] = yp[(size_t)it * y_si + (size_t)d * y_sd];
-            wv[u] = HAS_W ? wp[(size_t)it * w_si] : 1.0;
-            if (on) {
-#pragma unroll
-                for (int j = 0; j < K1; ++j) qv[u][j] = Q_(it, j);
-            }
-        }
+    for (int j = 0; j < 2 * K; ++j) tw[j] = on ? T_(lq - K + 1 + j) : 0.0;
+    double tnx = (on && lq + K + 1 <= nk1 + K1) ? T_(lq + K + 1) : 0.0;  // knot that enters at the next advance
+#if FPB_FIT_FASTDIV
+    SpanTab<K, FPB_SPAN_STRIDE> sp;
+    sp.rs = ring + (size_t)(ps.depth * ps.E) * kFitThreads;
+    span_init<K, FPB_SPAN_STRIDE>(sp, tw);
+#endif
+#endif
+    ps.start();
+    for (int it = 0; it < m; ++it) {
+        double xv, yv[ND], wv;
+        ps.fetch(it, xv, yv, wv);
         if (on) {
+            double qv[K1];
+#if FPB_FIT_STOREQ
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (it0 + u < m) {
-                    bool newk = false;
-                    if (xv[u] >= tl && l <= nk1) {
-                        newk = true;
-                        ++l;
+            for (int j = 0; j < K1; ++j) qv[j] = Q_(it, j);
+#else
+            while (lq < nk1 && xv >= tw[K]) {
 #pragma unroll
-                        for (int d = 0; d < ND; ++d) {
-                            if (d < nd) {
+                for (int j = 0; j < 2 * K - 1; ++j) tw[j] = tw[j + 1];
+                ++lq;
+                tw[2 * K - 1] = tnx;
+                if (lq + K + 1 <= nk1 + K1) tnx = T_(lq + K + 1);
+#if FPB_FIT_FASTDIV
+                span_advance<K, FPB_SPAN_STRIDE>(sp, tw);
+#endif
+            }
+#if FPB_FIT_FASTDIV
+            bspl_tab<K, FPB_SPAN_STRIDE>(tw, sp, xv, qv);
+#else
+            bspl<K>(tw, xv, qv);
+#endif
+#endif
+            bool newk = false;
+            if (xv >= tl && l <= nk1) {
+                newk = true;
+                ++l;
 #pragma unroll
-                                for (int j = 0; j < K; ++j) cw[d][j] = cw[d][j + 1];
-                                cw[d][K] = CD_(d, l - 1);
-                            }
-                        }
-                        tl = T_(l);
-                    }
-                    // fpcurf: (w*(s(x)-y))**2; fppara part 1: sum_d (w*(s_d(u)-x_d))**2 (identical
-                    // for one coordinate); fppara part 2: (sum_d (s_d(u)-x_d)**2) * w**2
-                    const bool late_w = HAS_W && !FPINT && p.par;
-                    double term = 0.0;
+                for (int d = 0; d < ND; ++d) {
+                    if (d < nd) {
 #pragma unroll
-                    for (int d = 0; d < ND; ++d) {
-                        if (d < nd) {
-                            double fac = 0.0;
-#pragma unroll
-                            for (int j = 0; j < K1; ++j) fac = add(fac, mul(cw[d][j], qv[u][j]));
-                            fac = sub(fac, yv[u][d]);
-                            if (HAS_W && !late_w) fac = mul(wv[u], fac);
-                            fac = mul(fac, fac);
-                            term = (d == 0) ? fac : add(term, fac);
-                        }
-                    }
-                    if (late_w) term = mul(term, mul(wv[u], wv[u]));
-                    fpart = add(fpart, term);
-                    if (FPINT && newk) {
-                        const double store = mul(term, 0.5);
-                        FPI_(i) = sub(fpart, store);
-                        ++i;
-                        fpart = store;
+                        for (int j = 0; j < K; ++j) cw[d][j] = cw[d][j + 1];
+                        cw[d][K] = CD_(d, l - 1);
                     }
                 }
+                tl = T_(l);
+            }
+            // fpcurf: (w*(s(x)-y))**2; fppara part 1: sum_d (w*(s_d(u)-x_d))**2 (identical
+            // for one coordinate); fppara part 2: (sum_d (s_d(u)-x_d)**2) * w**2
+            const bool late_w = HAS_W && !FPINT && p.par;
+            double term = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                if (d < nd) {
+                    double fac = 0.0;
+#pragma unroll
+                    for (int j = 0; j < K1; ++j) fac = add(fac, mul(cw[d][j], qv[j]));
+                    fac = sub(fac, yv[d]);
+                    if (HAS_W && !late_w) fac = mul(wv, fac);
+                    fac = mul(fac, fac);
+                    term = (d == 0) ? fac : add(term, fac);
+                }
+            }
+            if (late_w) term = mul(term, mul(wv, wv));
+            fpart = add(fpart, term);
+            if (FPINT && newk) {
+                const double store = mul(term, 0.5);
+                FPI_(i) = sub(fpart, store);
+                ++i;
+                fpart = store;
             }
         }
     }
+    ps.drain();
     if (FPINT && on) FPI_(nrint) = fpart;
     return fpart;
 }
@@ -206,17 +345,19 @@ __device__ __forceinline__ double residual_pass(const FitParams &p, double *wsd,
 // right-hand sides.  A point in knot interval l only touches band rows l-k..l and x is sorted,
 // so only k+1 rows of R (+ right-hand sides) are live at any time.  They sit in a per-thread
 // circular window in SHARED memory (column `rs` of the CTA's buffer, conflict-free
-// [element][thread] layout): that keeps the kernel at <= 80 registers, i.e. 24 warps per SM
+// [element][thread] layout): that keeps the kernel at 96 registers, i.e. 20 warps per SM
 // instead of 16 -- the pass is bound by dependent FP64 issue latency, so warps are throughput.
 // A row is written to the workspace exactly once per pass, when the window leaves it.
 template <int K, bool HAS_W, int IDIM>
-__device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, double *rs,
+__device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, double *rs, double *ring,
                                            const double *xp, const double *yp, const double *wp,
                                            size_t x_si, size_t y_si, size_t y_sd, size_t w_si, int m,
                                            int nk1, bool on)
 {
     constexpr int K1 = K + 1, NT = kFitThreads, ND = IDIM > 0 ? IDIM : kMaxIdim;
     const int nd = IDIM > 0 ? IDIM : p.idim;
+    PointStream<ND, HAS_W, FPB_FIT_STREAM != 0> ps{ring, xp, yp, wp, x_si, y_si, y_sd, w_si, nd, m, p.sdepth,
+                                                   1 + nd + (HAS_W ? 1 : 0)};
 #define RS_(slot, q) rs[((slot) * K1 + (q)) * NT]
 #define ZS_(slot, d) rs[(K1 * K1 + (slot) * nd + (d)) * NT]
     double tw[2 * K], h[K1];
@@ -229,34 +370,24 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
         for (int q = 0; q < K1; ++q) RS_(r, q) = 0.0;
     }
     int l = K1, s0 = 0;  // s0: window slot holding band row l-K1+1
-    if (on) {
 #pragma unroll
-        for (int j = 0; j < 2 * K; ++j) tw[j] = T_(l - K + 1 + j);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 2 * K; ++j) tw[j] = 0.0;
-    }
+    for (int j = 0; j < 2 * K; ++j) tw[j] = on ? T_(l - K + 1 + j) : 0.0;
+    double tnx = (on && l + K + 1 <= nk1 + K1) ? T_(l + K + 1) : 0.0;  // knot that enters at the next advance
+#if FPB_FIT_FASTDIV
+    SpanTab<K, FPB_SPAN_STRIDE> sp;
+    sp.rs = ring + (size_t)(ps.depth * ps.E) * NT;
+    span_init<K, FPB_SPAN_STRIDE>(sp, tw);
+#endif
     double fp = 0.0;
-    // the next point's data is requested one iteration ahead
-    double xn = xp[0], yn[ND], wn = HAS_W ? wp[0] : 1.0;
-#pragma unroll
-    for (int d = 0; d < ND; ++d)
-        if (d < nd) yn[d] = yp[(size_t)d * y_sd];
+    ps.start();
     for (int it = 0; it < m; ++it) {
-        const double xi = xn;
-        const double wi = wn;
+        double xi, yi[ND], wi;
+        ps.fetch(it, xi, yi, wi);
         // w == NULL means unit weights: y*1 and h*1 are exact, so the products are skipped
-        double yi[ND];
-#pragma unroll
-        for (int d = 0; d < ND; ++d)
-            if (d < nd) yi[d] = HAS_W ? mul(yn[d], wi) : yn[d];
-        {
-            const int nx = min(it + 1, m - 1);
-            xn = xp[(size_t)nx * x_si];
+        if (HAS_W) {
 #pragma unroll
             for (int d = 0; d < ND; ++d)
-                if (d < nd) yn[d] = yp[(size_t)nx * y_si + (size_t)d * y_sd];
-            if (HAS_W) wn = wp[(size_t)nx * w_si];
+                if (d < nd) yi[d] = mul(yi[d], wi);
         }
         if (on) {
             // fp_knot_interval (core:2432-2473) == linear walk from the previous interval
@@ -280,40 +411,50 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
 #pragma unroll
                 for (int j = 0; j < 2 * K - 1; ++j) tw[j] = tw[j + 1];
                 ++l;
-                tw[2 * K - 1] = T_(l + K);
+                tw[2 * K - 1] = tnx;
+                if (l + K + 1 <= nk1 + K1) tnx = T_(l + K + 1);
+#if FPB_FIT_FASTDIV
+                span_advance<K, FPB_SPAN_STRIDE>(sp, tw);
+#endif
             }
+#if FPB_FIT_FASTDIV
+            bspl_tab<K, FPB_SPAN_STRIDE>(tw, sp, xi, h);
+#else
             bspl<K>(tw, xi, h);
+#endif
 #pragma unroll
             for (int j = 0; j < K1; ++j) {
+#if FPB_FIT_STOREQ
                 Q_(it, j) = h[j];
+#endif
                 if (HAS_W) h[j] = mul(wi, h[j]);
             }
             // fp_rotate_row / fp_rotate_row_vec (core:5691-5717 / 5742-5771): pivot i <-> band row
             // l-K1+1+i; one rotation serves all coordinates
-            int sl = s0;
+            int sl_ = s0;
 #pragma unroll
             for (int i = 0; i < K1; ++i) {
                 const double piv = h[i];
                 if (!fp_is_zero(piv)) {
-                    double cs, sn, dg = RS_(sl, 0);
-                    givens(piv, dg, cs, sn);
-                    RS_(sl, 0) = dg;
+                    double cs, sn, dg = RS_(sl_, 0);
+                    FPB_GIVENS(piv, dg, cs, sn);
+                    RS_(sl_, 0) = dg;
 #pragma unroll
                     for (int d = 0; d < ND; ++d) {
                         if (d < nd) {
-                            double z = ZS_(sl, d);
+                            double z = ZS_(sl_, d);
                             rota(cs, sn, yi[d], z);
-                            ZS_(sl, d) = z;
+                            ZS_(sl_, d) = z;
                         }
                     }
 #pragma unroll
                     for (int q = 1; q <= K - i; ++q) {
-                        double r = RS_(sl, q);
+                        double r = RS_(sl_, q);
                         rota(cs, sn, h[i + q], r);
-                        RS_(sl, q) = r;
+                        RS_(sl_, q) = r;
                     }
                 }
-                sl = (sl + 1 == K1) ? 0 : sl + 1;
+                sl_ = (sl_ + 1 == K1) ? 0 : sl_ + 1;
             }
             // fp = fp + yi**2 (core:4895); fppara: fp + sum(xi**2) (core:8972)
             double sq = mul(yi[0], yi[0]);
@@ -323,6 +464,7 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
             fp = add(fp, sq);
         }
     }
+    ps.drain();
     if (on) {
         // rows never reached by the data stay zero, exactly as in the reference
         while (l < nk1) {
@@ -342,16 +484,16 @@ __device__ __forceinline__ double lsq_pass(const FitParams &p, double *wsd, doub
             s0 = (s0 + 1 == K1) ? 0 : s0 + 1;
             ++l;
         }
-        int sl = s0;
+        int sl_ = s0;
 #pragma unroll
         for (int r = 0; r < K1; ++r) {
             const int row = l - K1 + 1 + r;
 #pragma unroll
-            for (int q = 0; q < K1; ++q) A_(row, q + 1) = RS_(sl, q);
+            for (int q = 0; q < K1; ++q) A_(row, q + 1) = RS_(sl_, q);
 #pragma unroll
             for (int d = 0; d < ND; ++d)
-                if (d < nd) ZD_(d, row) = ZS_(sl, d);
-            sl = (sl + 1 == K1) ? 0 : sl + 1;
+                if (d < nd) ZD_(d, row) = ZS_(sl_, d);
+            sl_ = (sl_ + 1 == K1) ? 0 : sl_ + 1;
         }
     }
 #undef RS_
@@ -414,7 +556,7 @@ __device__ __forceinline__ void list_append(int *list, int *count, bool cond, in
 // ---------------------------------------------------------------------------------------
 template <int K, bool HAS_W, int IDIM>
 __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
-                         double *__restrict__ wsd, int *__restrict__ wsi, double *rs)
+                         double *__restrict__ wsd, int *__restrict__ wsi, double *rs, double *ring)
 {
     constexpr int K1 = K + 1, K2 = K + 2;
     const int nd = IDIM > 0 ? IDIM : p.idim;
@@ -573,7 +715,7 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             for (int i = nk1 + 1; i <= n; ++i) T_(i) = xe;
             ran_pass = true;
         }
-        const double fp_pass = lsq_pass<K, HAS_W, IDIM>(p, wsd, rs, xp, yp, wp, (size_t)p.x_si,
+        const double fp_pass = lsq_pass<K, HAS_W, IDIM>(p, wsd, rs, ring, xp, yp, wp, (size_t)p.x_si,
                                                         (size_t)p.y_si, (size_t)p.y_sd, (size_t)p.w_si,
                                                         m, nk1, on);
         if (on) {
@@ -610,7 +752,7 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
             fpold = fp;
         }
         if (__any_sync(FULL, on))
-            (void)residual_pass<K, true, HAS_W, IDIM>(p, wsd, xp, yp, wp, (size_t)p.x_si,
+            (void)residual_pass<K, true, HAS_W, IDIM>(p, wsd, ring, xp, yp, wp, (size_t)p.x_si,
                                                       (size_t)p.y_si, (size_t)p.y_sd, (size_t)p.w_si, m,
                                                       nk1, nrint, on);
         // add_new_knots, core:4968-4996 with fpknot core:8199-8275 inlined
@@ -728,7 +870,29 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
                         p.nrdata[(size_t)b * nest + (i - 1)] = NRD_(i);
                     }
                 }
-                if (state == ST_PART2) p.st_fp0[b] = fp0;
+                if (state == ST_PART2) {
+                    p.st_fp0[b] = fp0;
+                    // hand the triangular system of this (accepted) knot set to part 2
+                    long long off = -1;
+                    const int rowlen = K1 + nd;
+                    if (p.az_pool && ran_pass) {
+                        const unsigned long long need = (unsigned long long)(n - K1) * rowlen;
+                        const unsigned long long at = atomicAdd(p.az_cursor, need);
+                        if (at + need <= (unsigned long long)p.az_cap) off = (long long)at;
+                    }
+                    if (p.az_off) p.az_off[b] = off;
+                    if (off >= 0) {
+                        double *dst = p.az_pool + off;
+                        const int nk = n - K1;
+                        for (int i = 1; i <= nk; ++i) {
+#pragma unroll
+                            for (int q = 0; q < K1; ++q) dst[q] = A_(i, q + 1);
+                            for (int d = 0; d < nd; ++d) dst[K1 + d] = ZD_(d, i);
+                            dst += rowlen;
+                        }
+                        p.st_fpold[b] = fp;   // fp of the least-squares spline on these knots
+                    }
+                }
             } else {
                 p.st_nplus[b] = nplus;
                 p.st_iter[b] = iter;
@@ -750,7 +914,7 @@ __device__ int pass_tile(const FitParams &p, int b, bool valid, bool first,
 // ---------------------------------------------------------------------------------------
 template <int K, bool HAS_W, int IDIM>
 __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__restrict__ wsd,
-                           int *__restrict__ wsi, double *rs)
+                           int *__restrict__ wsi, double *rs, double *ring)
 {
     constexpr int K1 = K + 1, K2 = K + 2, ND = IDIM > 0 ? IDIM : kMaxIdim;
     const int nd = IDIM > 0 ? IDIM : p.idim;
@@ -806,7 +970,31 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
     const double *xg = &WS(p.off_x, 0), *yg = &WS(p.off_y, 0);
     const double *wg = HAS_W ? &WS(p.off_w, 0) : nullptr;
     const size_t yg_sd = (size_t)m * 32;
-    double fp = lsq_pass<K, HAS_W, IDIM>(p, wsd, rs, xg, yg, wg, 32, 32, yg_sd, 32, m, nk1, on2);
+    // (R, z) of the accepted knot set: normally handed over by the pass that accepted it (the same values
+    // the pass below would regenerate); curves without stored rows (pool exhausted, or part 2 reached without
+    // a pass in the last launch) run the least-squares pass again
+#if FPB_FIT_STOREQ
+    const long long az = -1;   // the stored basis values come from this pass
+#else
+    const long long az = (valid && p.az_off) ? p.az_off[b] : -1;
+#endif
+    double fp = 0.0;
+    if (__any_sync(FULL, on2 && az < 0)) {
+        const double fpl = lsq_pass<K, HAS_W, IDIM>(p, wsd, rs, ring, xg, yg, wg, 32, 32, yg_sd, 32, m, nk1,
+                                                    on2 && az < 0);
+        if (az < 0) fp = fpl;
+    }
+    if (on2 && az >= 0) {
+        const double *src = p.az_pool + az;
+        const int rowlen = K1 + nd;
+        for (int i = 1; i <= nk1; ++i) {
+#pragma unroll
+            for (int q = 0; q < K1; ++q) A_(i, q + 1) = src[q];
+            for (int d = 0; d < nd; ++d) ZD_(d, i) = src[K1 + d];
+            src += rowlen;
+        }
+        fp = p.st_fpold[b];
+    }
     double fpms = sub(fp, s);
     // fpdisc, core:5453-5495
     {
@@ -874,7 +1062,7 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
             const double piv = h[0];
             if (p.par || !fp_is_zero(piv)) {  // the vector variant has no zero-pivot skip
                 double cs, sn;
-                givens(piv, g[0], cs, sn);
+                FPB_GIVENS(piv, g[0], cs, sn);
 #pragma unroll
                 for (int d = 0; d < ND; ++d)
                     if (d < nd) rota(cs, sn, y[d], c[d]);
@@ -927,7 +1115,7 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
         }
         for (int d = 0; d < nd; ++d)
             back_subst<K2>(p, wsd, p.off_g, p.off_c + d * p.nestp, p.off_c + d * p.nestp, nk1, on);
-        const double fpn = residual_pass<K, false, HAS_W, IDIM>(p, wsd, xg, yg, wg, 32, 32, yg_sd, 32, m,
+        const double fpn = residual_pass<K, false, HAS_W, IDIM>(p, wsd, ring, xg, yg, wg, 32, 32, yg_sd, 32, m,
                                                                 nk1, 0, on);
         if (on) {
             fp = fpn;
@@ -1007,6 +1195,7 @@ __global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K, IDIM))
 {
     extern __shared__ double fit_smem[];
     double *rs = fit_smem + threadIdx.x;
+    double *ring = rs + (size_t)((K + 1) * (K + 1) + (K + 1) * (IDIM > 0 ? IDIM : p.idim)) * kFitThreads;  // after the band window
     const int lane = threadIdx.x & 31;
     const int warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double *wsd = p.ws + (size_t)warp_slot * p.ws_per_lane * 32 + lane;
@@ -1021,7 +1210,7 @@ __global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K, IDIM))
         const bool valid = base + lane < count;
         int b = 0;
         if (valid) b = first ? (int)(base + lane) : in_list[base + lane];
-        const int st = pass_tile<K, HAS_W, IDIM>(p, b, valid, first != 0, wsd, wsi, rs);
+        const int st = pass_tile<K, HAS_W, IDIM>(p, b, valid, first != 0, wsd, wsi, rs, ring);
         __syncwarp();
         list_append(out_list, out_count, valid && st == ST_LOOP, b, lane);
         const bool to2 = valid && st == ST_PART2;
@@ -1036,6 +1225,7 @@ __global__ void __launch_bounds__(kFitThreads, fit_p2_blocks_per_sm(K, IDIM))
 {
     extern __shared__ double fit_smem[];
     double *rs = fit_smem + threadIdx.x;
+    double *ring = rs + (size_t)((K + 1) * (K + 1) + (K + 1) * (IDIM > 0 ? IDIM : p.idim)) * kFitThreads;  // after the band window
     const int lane = threadIdx.x & 31;
     const int warp_slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double *wsd = p.ws + (size_t)warp_slot * p.ws_per_lane * 32 + lane;
@@ -1049,7 +1239,7 @@ __global__ void __launch_bounds__(kFitThreads, fit_p2_blocks_per_sm(K, IDIM))
         if (base >= count) break;
         const bool valid = base + lane < count;
         const int b = valid ? list[base + lane] : 0;
-        part2_tile<K, HAS_W, IDIM>(p, b, valid, wsd, wsi, rs);
+        part2_tile<K, HAS_W, IDIM>(p, b, valid, wsd, wsi, rs, ring);
         __syncwarp();
     }
 }
@@ -1060,7 +1250,7 @@ cudaError_t launch_pass_kw(const FitParams &p, int grid, cudaStream_t st, const 
                            int *p2_count, int first)
 {
     constexpr int D = FPB_FIT_IDIM;
-    const unsigned smem = fit_smem_bytes(p.k, p.idim);
+    const unsigned smem = fit_smem_bytes_stream(p.k, p.idim, HAS_W, p.sdepth);
     auto kern = curfit_pass_kernel<K, HAS_W, D>;
     if (smem > 48u * 1024u) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1074,7 +1264,7 @@ template <int K, bool HAS_W>
 cudaError_t launch_part2_kw(const FitParams &p, int grid, cudaStream_t st, const int *list, const int *count)
 {
     constexpr int D = FPB_FIT_IDIM;
-    const unsigned smem = fit_smem_bytes(p.k, p.idim);
+    const unsigned smem = fit_smem_bytes_stream(p.k, p.idim, HAS_W, p.sdepth);
     auto kern = curfit_part2_kernel<K, HAS_W, D>;
     if (smem > 48u * 1024u) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1205,7 +1395,7 @@ FitLayout fit_layout(int m, int k, int nest, int idim, int periodic)
     L.off_a = off; off += nestp * k1;
     L.off_g = off; off += nestp * k2;
     L.off_b = off; off += nestp * k2;
-    L.off_q = off; off += m * k1;
+    L.off_q = off; off += (periodic || FPB_FIT_STOREQ) ? m * k1 : 0;  // stored basis values: percur only
     L.off_x = off; off += m;   // part 2: the curve's own data, gathered once
     L.off_y = off; off += m * idim;
     L.off_w = off; off += m;

@@ -169,6 +169,13 @@ void fpb_engine_destroy(fpb_engine *eng)
     cudaStreamSynchronize(eng->stream);
     eng->ws.release();
     eng->wsi.release();
+    eng->ws2.release();
+    eng->wsi2.release();
+    eng->az_pool.release();
+    eng->az_off.release();
+    if (eng->s_p2) cudaStreamDestroy(eng->s_p2);
+    for (int i = 0; i < 2; ++i)
+        if (eng->ev_p2[i]) cudaEventDestroy(eng->ev_p2[i]);
     eng->counter.release();
     eng->lists.release();
     eng->st_i.release();
@@ -303,11 +310,15 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
         blocks_needed, (p.periodic ? max_warps : fit_p2_resident_warps(k, p.idim, eng->nsm)) / (kFitThreads / 32));
     const size_t warps = (size_t)grid_ws * (kFitThreads / 32);
     const size_t nb = (size_t)nbatch;
-    // counters: [0] tile queue head, [4] list A count, [5] list B count, [6] part-2 count
+    // counters: [0] tile queue head, [4] list A count, [5] list B count, [6] part-2 count,
+    // [8] part-2 count at the moment the early part-2 launch was cut off, [9] length of the rest,
+    // [12] tile queue head of the early part-2 launch; two histograms of n follow (early / rest)
     const size_t hist_off = 64;  // ints
+    const size_t hist_len = (size_t)L.nestp + 8;
+    const size_t cnt_ints = hist_off + 2 * hist_len;
     if (!eng->ws.reserve(warps * (size_t)L.ws_per_lane * 32 * sizeof(double)) ||
         !eng->wsi.reserve(warps * (size_t)L.nestp * 32 * sizeof(int)) ||
-        !eng->counter.reserve((hist_off + (size_t)L.nestp + 8) * sizeof(int)) ||
+        !eng->counter.reserve(cnt_ints * sizeof(int)) ||
         !eng->lists.reserve(4 * nb * sizeof(int)) ||
         !eng->st_i.reserve(2 * nb * sizeof(int)) || !eng->st_d.reserve(2 * nb * sizeof(double)) ||
         !eng->st_nrd.reserve(nb * (size_t)L.nestp * sizeof(int)))
@@ -318,9 +329,14 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     }
     int *cnt = eng->counter.as<int>();
     cudaStream_t st = eng->stream;
-    if (!cuda_ok(cudaMemsetAsync(cnt, 0, (hist_off + (size_t)L.nestp + 8) * sizeof(int), st), "memset"))
+    if (!cuda_ok(cudaMemsetAsync(cnt, 0, cnt_ints * sizeof(int), st), "memset"))
         return FPB_ERR_CUDA;
     p.nestp = L.nestp;
+    {
+        const int cls = idim_class(p.idim);
+        const int blocks = std::max(fit_blocks_per_sm(k, cls), fit_p2_blocks_per_sm(k, cls));
+        p.sdepth = fit_stream_depth(k, p.idim, p.w != nullptr, blocks);
+    }
     p.ws = eng->ws.as<double>(); p.wsi = eng->wsi.as<int>();
     p.counter = reinterpret_cast<unsigned *>(cnt);
     p.off_t = L.off_t; p.off_c = L.off_c; p.off_z = L.off_z; p.off_fpint = L.off_fpint;
@@ -331,11 +347,37 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     p.st_nplus = eng->st_i.as<int>(); p.st_iter = p.st_nplus + nb;
     p.st_fpold = eng->st_d.as<double>(); p.st_fp0 = p.st_fpold + nb;
     p.st_nrd = eng->st_nrd.as<int>();
-    p.hist = cnt + hist_off;
+    // pool for the (R, z) rows of accepted knot sets: room for 96 rows per curve on average (config 2 uses
+    // 17), at most 8 GB; curves that do not fit regenerate the rows in part 2
+    p.az_pool = nullptr; p.az_cursor = nullptr; p.az_cap = 0; p.az_off = nullptr;
+    static const bool no_handover = std::getenv("FPB_FIT_NO_HANDOVER") != nullptr;
+    if (!p.periodic && iopt >= 0 && !no_handover) {
+        const long long rowlen = (k + 1) + p.idim;
+        long long cap = (long long)nb * std::min<long long>(L.nestp, 96) * rowlen;
+        cap = std::min<long long>(cap, ((long long)8 << 30) / 8);
+        if (eng->az_pool.reserve((size_t)cap * sizeof(double)) && eng->az_off.reserve(nb * sizeof(long long))) {
+            p.az_pool = eng->az_pool.as<double>();
+            p.az_off = eng->az_off.as<long long>();
+            p.az_cap = cap;
+            p.az_cursor = reinterpret_cast<unsigned long long *>(cnt + 16);   // zeroed with the counters
+        }
+    }
+    int *hist_early = cnt + hist_off, *hist_rest = cnt + hist_off + hist_len;
+    p.hist = hist_early;
     int *list[2] = {eng->lists.as<int>(), eng->lists.as<int>() + nb};
     int *p2_list = eng->lists.as<int>() + 2 * nb, *p2_sorted = eng->lists.as<int>() + 3 * nb;
     int *lcount[2] = {cnt + 4, cnt + 5};
-    int *p2_count = cnt + 6;
+    int *p2_count = cnt + 6, *p2_early_count = cnt + 8, *p2_rest_count = cnt + 9;
+
+    // Early part 2 (curfit / parcur, large batches): once the curves that still need a finer knot set no
+    // longer fill the GPU, the passes that remain are a chain of sparsely populated, latency-bound launches
+    // (about 10 of ~20 launches, 6 % of the time at config 2).  Part 2 of every curve accepted so far starts
+    // right then on a second stream with its own workspace and one CTA slot per SM left free for the tail;
+    // the rest of the part-2 list follows after the last pass.
+    const long long capacity = grid * (long long)kFitThreads;   // curves one resident wave of the pass kernel holds
+    static const bool no_overlap = std::getenv("FPB_FIT_NO_OVERLAP") != nullptr;
+    const bool may_overlap = !no_overlap && !p.periodic && iopt >= 0 && (long long)nbatch >= 4 * capacity;
+    int early = -1;   // part-2 list length when the early launch was cut off (-1: no early launch)
 
     begin_timing(eng);
     // pass 1 over the whole batch (identity list), then passes over the shrinking list of curves
@@ -347,13 +389,51 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     int cur = 0, remaining = (iopt < 0) ? 0 : nbatch;  // iopt=-1: a single pass settles every curve
     const int max_rounds = 2 * (m + 4) + 8;  // fpcurf's own bound on knot sets, with one restart
     for (int round = 1; round <= max_rounds && remaining > 0; ++round) {
-        if (round >= 3 && (round & 1)) {
-            if (!cuda_ok(cudaMemcpyAsync(eng->h_count, lcount[cur], sizeof(int),
-                                         cudaMemcpyDeviceToHost, st), "count D2H") ||
+        const bool near_tail = may_overlap && early < 0 && remaining <= 4 * capacity;
+        if (round >= 3 && ((round & 1) || near_tail)) {
+            // [4],[5],[6]: both list lengths and the part-2 count in one copy
+            if (!cuda_ok(cudaMemcpyAsync(eng->h_count, cnt + 4, 3 * sizeof(int), cudaMemcpyDeviceToHost, st),
+                         "count D2H") ||
                 !cuda_ok(cudaStreamSynchronize(st), "sync"))
                 return FPB_ERR_CUDA;
-            remaining = eng->h_count[0];
+            remaining = eng->h_count[cur];
             if (remaining <= 0) break;
+            const int n2_now = eng->h_count[2];
+            if (may_overlap && early < 0 && remaining <= capacity && n2_now >= 4 * capacity) {
+                // ---- cut the part-2 list here and start its first section on the second stream ----
+                if (!eng->s_p2) {
+                    if (!cuda_ok(cudaStreamCreateWithFlags(&eng->s_p2, cudaStreamNonBlocking), "stream") ||
+                        !cuda_ok(cudaEventCreateWithFlags(&eng->ev_p2[0], cudaEventDisableTiming), "event") ||
+                        !cuda_ok(cudaEventCreateWithFlags(&eng->ev_p2[1], cudaEventDisableTiming), "event"))
+                        return FPB_ERR_CUDA;
+                }
+                const int blocks_early = std::max(1, fit_p2_blocks_per_sm(k, idim_class(p.idim)) - 1);
+                const long long grid_early = std::min<long long>((long long)eng->nsm * blocks_early,
+                                                                 ((long long)n2_now + kFitThreads - 1) / kFitThreads);
+                const size_t warps2 = (size_t)grid_early * (kFitThreads / 32);
+                if (!eng->ws2.reserve(warps2 * (size_t)L.ws_per_lane * 32 * sizeof(double)) ||
+                    !eng->wsi2.reserve(warps2 * (size_t)L.nestp * 32 * sizeof(int)))
+                    return FPB_ERR_ALLOC;
+                early = n2_now;
+                eng->h_count[8] = early;
+                if (!cuda_ok(cudaMemcpyAsync(p2_early_count, eng->h_count + 8, sizeof(int), cudaMemcpyHostToDevice, st),
+                             "early count") ||
+                    !cuda_ok(cudaEventRecord(eng->ev_p2[0], st), "event") ||
+                    !cuda_ok(cudaStreamWaitEvent(eng->s_p2, eng->ev_p2[0], 0), "wait"))
+                    return FPB_ERR_CUDA;
+                FitParams pe = p;
+                pe.ws = eng->ws2.as<double>();
+                pe.wsi = eng->wsi2.as<int>();
+                pe.counter = reinterpret_cast<unsigned *>(cnt + 12);
+                if (!cuda_ok(launch_p2_sort(p2_list, p2_early_count, n, hist_early, L.nestp + 1, p2_sorted, eng->nsm,
+                                            eng->s_p2), "part-2 sort") ||
+                    !cuda_ok(launch_curfit_part2(pe, (int)grid_early, eng->s_p2, p2_sorted, p2_early_count),
+                             "curfit part-2 kernel (early)") ||
+                    !cuda_ok(cudaEventRecord(eng->ev_p2[1], eng->s_p2), "event"))
+                    return FPB_ERR_CUDA;
+                eng->launches += 3;
+                p.hist = hist_rest;   // curves accepted from now on are counted for the second section
+            }
         }
         // reset the queue head and the output list length
         if (!cuda_ok(cudaMemsetAsync(cnt, 0, sizeof(int), st), "memset") ||
@@ -374,18 +454,29 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
             !cuda_ok(cudaStreamSynchronize(st), "sync"))
             return FPB_ERR_CUDA;
         const int n2 = eng->h_count[0];
-        if (n2 > 0) {
-            if (!cuda_ok(launch_p2_sort(p2_list, p2_count, n, p.hist, L.nestp + 1, p2_sorted, eng->nsm,
-                                        st), "part-2 sort") ||
+        const int first = early < 0 ? 0 : early;   // entries [first, n2) of the part-2 list are still to do
+        if (n2 > first) {
+            const int *count_ptr = p2_count;
+            if (early >= 0) {
+                eng->h_count[9] = n2 - first;
+                if (!cuda_ok(cudaMemcpyAsync(p2_rest_count, eng->h_count + 9, sizeof(int), cudaMemcpyHostToDevice, st),
+                             "rest count"))
+                    return FPB_ERR_CUDA;
+                count_ptr = p2_rest_count;
+            }
+            if (!cuda_ok(launch_p2_sort(p2_list + first, count_ptr, n, p.hist, L.nestp + 1, p2_sorted + first,
+                                        eng->nsm, st), "part-2 sort") ||
                 !cuda_ok(cudaMemsetAsync(cnt, 0, sizeof(int), st), "memset"))
                 return FPB_ERR_CUDA;
             eng->launches += 2;
-            long long g2 = std::min<long long>(grid_p2, ((long long)n2 + kFitThreads - 1) / kFitThreads);
-            if (!cuda_ok(launch_curfit_part2(p, (int)g2, st, p2_sorted, p2_count), "curfit part-2 kernel"))
+            long long g2 = std::min<long long>(grid_p2, ((long long)(n2 - first) + kFitThreads - 1) / kFitThreads);
+            if (!cuda_ok(launch_curfit_part2(p, (int)g2, st, p2_sorted + first, count_ptr), "curfit part-2 kernel"))
                 return FPB_ERR_CUDA;
             eng->launches++;
         }
     }
+    if (early >= 0 && !cuda_ok(cudaStreamWaitEvent(st, eng->ev_p2[1], 0), "join"))   // the caller's stream sees all of it
+        return FPB_ERR_CUDA;
     end_timing(eng);
     return FPB_STATUS_OK;
 }

@@ -35,6 +35,10 @@ struct fpb_engine {
     bool timed = false;
     int64_t launches = 0;
     fpb::DevBuf ws, wsi, counter;     // fit kernel workspace
+    fpb::DevBuf az_pool, az_off;      // (R, z) rows handed from the accepting pass to part 2
+    fpb::DevBuf ws2, wsi2;            // second workspace: part 2 of the early finishers overlaps the tail passes
+    cudaStream_t s_p2 = nullptr;      // stream of that early part-2 launch
+    cudaEvent_t ev_p2[2] = {nullptr, nullptr};
     fpb::DevBuf lists, st_i, st_d, st_nrd;  // pass pipeline: curve lists and per-curve state
     int *h_count = nullptr;           // pinned host word for list-length read-back
     fpb::DevBuf plan_cs, plan_w, plan_row, plan_skip, plan_R, plan_ier, plan_meta;  // shared-x plan

@@ -38,6 +38,29 @@ constexpr unsigned fit_smem_bytes(int k, int idim = 1)
     return (unsigned)(((k + 1) * (k + 1) + (k + 1) * idim) * kFitThreads * sizeof(double));
 }
 
+// curfit / parcur kernels: band window + the cp.async ring of the point streams (`depth` slots of
+// x, y(1:idim) and, with weights, w per thread)
+constexpr int fit_window_doubles(int k, int idim) { return (k + 1) * (k + 1) + (k + 1) * idim; }
+constexpr unsigned fit_smem_bytes_stream(int k, int idim, bool has_w, int depth)
+{
+    // + k(k+1)/2 span reciprocals per thread (bspl_tab)
+    return (unsigned)((fit_window_doubles(k, idim) + depth * (1 + idim + (has_w ? 1 : 0)) + k * (k + 1) / 2) *
+                      kFitThreads * sizeof(double));
+}
+// deepest ring (8, 4 or 2 slots) that still lets `blocks` CTAs share the SM's 227 KB (1 KB reserved per CTA)
+#ifndef FPB_FIT_STREAM
+#define FPB_FIT_STREAM 0   // measured (profiles/r02_ab.md): the cp.async ring loses to plain loads + L2 prefetch
+#endif
+#ifndef FPB_FIT_STREAM_MAXDEPTH
+#define FPB_FIT_STREAM_MAXDEPTH 8
+#endif
+constexpr int fit_stream_depth(int k, int idim, bool has_w, int blocks)
+{
+    return !FPB_FIT_STREAM ? 0 : FPB_FIT_STREAM_MAXDEPTH < 8 ? FPB_FIT_STREAM_MAXDEPTH : (fit_smem_bytes_stream(k, idim, has_w, 8) + 1024u) * (unsigned)blocks <= 227u * 1024u   ? 8
+           : (fit_smem_bytes_stream(k, idim, has_w, 4) + 1024u) * (unsigned)blocks <= 227u * 1024u ? 4
+                                                                                                   : 2;
+}
+
 // per-lane workspace layout of the fit kernel, in elements of 8 bytes
 struct FitLayout {
     int nestp;  // knots a curve can actually reach: min(nest, m+k+1)
@@ -51,6 +74,7 @@ int fit_p2_resident_warps(int k, int idim, int nsm);
 
 struct FitParams {
     int nbatch, iopt, m, k, nest, nestp;
+    int sdepth;             // slots of the point-stream ring (fit_stream_depth)
     int idim;               // coordinate curves per fit (1 for curfit)
     int par;                // 1: parcur/fppara semantics (checks, initial p, no zero-pivot skip)
     int periodic;           // 1: percur/fpperi (fpb_percur.cu kernels, two-block factor)
@@ -78,6 +102,13 @@ struct FitParams {
     double *st_fpold, *st_fp0;
     int *st_nrd;            // [nbatch][nestp]  nrdata(1:nrint)
     int *hist;              // [nestp+1] histogram of n over the part-2 list
+    // triangular system (R, z) of the accepted knot set, handed from the last pass to part 2 so that part 2
+    // does not have to regenerate it: rows of (k+1)+idim doubles, allocated from a pool through az_cursor;
+    // az_off[b] = first element of curve b's rows, or -1 (pool full / no pass ran: part 2 recomputes)
+    double *az_pool;
+    unsigned long long *az_cursor;
+    long long az_cap;       // pool capacity in doubles
+    long long *az_off;      // [nbatch]
 };
 cudaError_t launch_curfit_pass(const FitParams &p, int grid_blocks, cudaStream_t stream,
                                const int *in_list, const int *in_count, int *out_list,

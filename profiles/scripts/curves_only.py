@@ -17,7 +17,7 @@ g = torch.Generator(device=dev); g.manual_seed(5)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 m = 256
 if kind == "fit":
-    x, y = bench.synth_device(torch, dev, B, bench.M, 1234)
+    x, y = bench.synth_device(torch, dev, 0, B, bench.M)
     run = lambda: eng.curfit_batch(x, y, None, k=3, s=bench.S, nest=bench.NEST, want_stats=True)
 elif kind in ("parcur", "curev"):
     d = 2
