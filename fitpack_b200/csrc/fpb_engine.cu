@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -53,7 +54,7 @@ void DevBuf::release()
 }
 
 static std::mutex g_engines_mu;
-static fpb_engine *g_engines[64] = {nullptr};
+static fpb_engine *g_engines[256] = {nullptr};   // slot device + 32*w: engine of host worker w (0..7)
 
 fpb_engine *default_engine(int device)
 {
@@ -63,10 +64,10 @@ fpb_engine *default_engine(int device)
             return nullptr;
         }
     }
-    if (device >= 64) return nullptr;
+    if (device >= 256) return nullptr;
     std::lock_guard<std::mutex> lk(g_engines_mu);
     if (!g_engines[device]) {
-        // slots 32..63 hold a second engine for devices 0..31 (copy/compute overlap workers)
+        // slots 32.. hold further engines for devices 0..31 (copy/compute overlap workers)
         fpb_engine *e = nullptr;
         if (fpb_engine_create(device & 31, &e) != FPB_STATUS_OK) return nullptr;
         g_engines[device] = e;
@@ -182,6 +183,10 @@ void fpb_engine_destroy(fpb_engine *eng)
     eng->st_d.release();
     eng->st_nrd.release();
     if (eng->h_count) cudaFreeHost(eng->h_count);
+    for (int i = 0; i < 2; ++i) {
+        if (eng->h_pack[i]) cudaFreeHost(eng->h_pack[i]);
+        if (eng->h_off[i]) cudaFreeHost(eng->h_off[i]);
+    }
     for (auto &b : eng->scratch2) b.release();
     if (eng->s_in) cudaStreamDestroy(eng->s_in);
     if (eng->s_out) cudaStreamDestroy(eng->s_out);
@@ -235,9 +240,9 @@ int64_t fpb_default_engine_launch_count(int32_t device)
 {
     if (device < 0 || device >= 32) return 0;
     std::lock_guard<std::mutex> lk(g_engines_mu);
-    int64_t total = 0;  // both default engines of the device (the second one is the overlap worker)
-    if (g_engines[device]) total += g_engines[device]->launches;
-    if (g_engines[device + 32]) total += g_engines[device + 32]->launches;
+    int64_t total = 0;  // all default engines of the device (engines 1..3 are the overlap workers)
+    for (int w = 0; w < 8; ++w)
+        if (g_engines[device + 32 * w]) total += g_engines[device + 32 * w]->launches;
     return total;
 }
 
@@ -377,6 +382,9 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     const long long capacity = grid * (long long)kFitThreads;   // curves one resident wave of the pass kernel holds
     static const bool no_overlap = std::getenv("FPB_FIT_NO_OVERLAP") != nullptr;
     const bool may_overlap = !no_overlap && !p.periodic && iopt >= 0 && (long long)nbatch >= 4 * capacity;
+    // tuning knobs (profiles/r02_ab.md): cut-off point in units of capacity/4, CTAs per SM left to the tail
+    static const int early_at4 = std::getenv("FPB_FIT_EARLY_AT4") ? std::atoi(std::getenv("FPB_FIT_EARLY_AT4")) : 4;
+    static const int early_free = std::getenv("FPB_FIT_EARLY_FREE") ? std::atoi(std::getenv("FPB_FIT_EARLY_FREE")) : 1;
     int early = -1;   // part-2 list length when the early launch was cut off (-1: no early launch)
 
     begin_timing(eng);
@@ -389,7 +397,7 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     int cur = 0, remaining = (iopt < 0) ? 0 : nbatch;  // iopt=-1: a single pass settles every curve
     const int max_rounds = 2 * (m + 4) + 8;  // fpcurf's own bound on knot sets, with one restart
     for (int round = 1; round <= max_rounds && remaining > 0; ++round) {
-        const bool near_tail = may_overlap && early < 0 && remaining <= 4 * capacity;
+        const bool near_tail = may_overlap && early < 0 && remaining <= std::max<long long>(4, early_at4) * capacity;
         if (round >= 3 && ((round & 1) || near_tail)) {
             // [4],[5],[6]: both list lengths and the part-2 count in one copy
             if (!cuda_ok(cudaMemcpyAsync(eng->h_count, cnt + 4, 3 * sizeof(int), cudaMemcpyDeviceToHost, st),
@@ -399,7 +407,7 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
             remaining = eng->h_count[cur];
             if (remaining <= 0) break;
             const int n2_now = eng->h_count[2];
-            if (may_overlap && early < 0 && remaining <= capacity && n2_now >= 4 * capacity) {
+            if (may_overlap && early < 0 && remaining <= capacity * early_at4 / 4 && n2_now >= 2 * capacity) {
                 // ---- cut the part-2 list here and start its first section on the second stream ----
                 if (!eng->s_p2) {
                     if (!cuda_ok(cudaStreamCreateWithFlags(&eng->s_p2, cudaStreamNonBlocking), "stream") ||
@@ -407,7 +415,7 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
                         !cuda_ok(cudaEventCreateWithFlags(&eng->ev_p2[1], cudaEventDisableTiming), "event"))
                         return FPB_ERR_CUDA;
                 }
-                const int blocks_early = std::max(1, fit_p2_blocks_per_sm(k, idim_class(p.idim)) - 1);
+                const int blocks_early = std::max(1, fit_p2_blocks_per_sm(k, idim_class(p.idim)) - early_free);
                 const long long grid_early = std::min<long long>((long long)eng->nsm * blocks_early,
                                                                  ((long long)n2_now + kFitThreads - 1) / kFitThreads);
                 const size_t warps2 = (size_t)grid_early * (kFitThreads / 32);
@@ -668,11 +676,33 @@ struct FitStage {
     long long c0 = 0, nb = 0;
     int nmax_used = 0;
     bool pending = false;          // t/c copy-out in flight on s_out
-    std::vector<long long> bad;    // rows rejected with ier=10: the caller's t/c must survive
+    bool packed = false;           // dense copy-out (iopt >= 0): scatter on the host when it has landed
+    long long total = 0;           // doubles in each of the two dense arrays
+    std::vector<long long> bad;    // rows rejected with ier=10: the caller's t/c must survive (2-D copy only)
     std::vector<double> keep_t, keep_c;
 };
 
-int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long long b0, long long b1, FP_SIZE iopt,
+bool reserve_pinned(void **ptr, size_t *have, size_t want)
+{
+    if (want <= *have) return true;
+    if (*ptr) cudaFreeHost(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+    const size_t cap = (want + want / 4 + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+    if (!cuda_ok(cudaHostAlloc(ptr, cap, cudaHostAllocDefault), "cudaHostAlloc")) return false;
+    *have = cap;
+    return true;
+}
+
+// One host worker's share of a host-pointer batch fit: the chunks `chunk_ids` of the slice (boundaries in
+// `cuts`), software-pipelined over three streams of the worker's engine: while chunk i is fitted on the
+// engine's stream, chunk i+1 is copied in (s_in) and the knots/coefficients of chunk i-1 are copied out
+// (s_out).  Two staging sets alternate.  Knots and coefficients travel back DENSE (pack_tc_kernel: t(1:n),
+// c(1:n-k-1) of every fitted curve, 5x fewer bytes than the leading columns of the [nb][nest] arrays at
+// config 2) into pinned staging and are scattered into the caller's arrays by this thread.  Pinned caller
+// memory makes the input copies asynchronous; with pageable memory the result is the same, only not overlapped.
+int32_t fit_slice_pipelined(fpb_engine *eng, const std::vector<long long> &cuts, const std::vector<int> &chunk_ids,
+                            long long b0, FP_SIZE iopt,
                             FP_SIZE m, const FP_REAL *x, const FP_REAL *y, const FP_REAL *w,
                             FP_SIZE shared_x, const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k,
                             FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp,
@@ -691,7 +721,6 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long
                 return FPB_ERR_CUDA;
     }
     cudaStream_t st = eng->stream, s_in = eng->s_in, s_out = eng->s_out;
-    const long long total = b1 - b0;
     // FPB_HOST_TRACE=1: wall-clock timeline of the staging pipeline on stderr (tuning aid)
     static const bool trace = std::getenv("FPB_HOST_TRACE") != nullptr;
     static const auto t_epoch = std::chrono::steady_clock::now();
@@ -700,29 +729,15 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_epoch).count();
         std::fprintf(stderr, "[fpb host %p] %9.2f ms  chunk %lld  %s\n", (void *)eng, ms, ci, what);
     };
-    // bytes per curve on the device: x,y,w curve-major + point-major, outputs t,c (+state)
-    const size_t per_curve = (size_t)m * 8 * 6 + (size_t)nest * 8 * 2 + (size_t)nest * 12 + 64;
-    long long chunk = (long long)(((size_t)6 << 30) / per_curve);  // <= 6 GB per staging set
-    const long long cap = std::max<long long>(chunk - chunk % 128, 128);
-    if (nsplit > 1) chunk = std::min(chunk, std::max<long long>((total + nsplit - 1) / nsplit, 65536));
-    chunk = std::max<long long>(chunk - chunk % 128, 128);
     const bool state = (fpint && nrdata);
-    enum { XC, YC, WC, XP, YP, WP, TT, CC, NN, FP_, IER, AUX };
+    const bool pack = (iopt >= 0);   // iopt = -1: t is an input with clamped ends, the plain 2-D copy stays
+    enum { XC, YC, WC, XP, YP, WP, TT, CC, NN, FP_, IER, AUX, TP, CP, OFF, CUR };
     FitStage stage[2];
-    // chunk boundaries; with exactly two chunks the first one may be smaller (first_frac of the
-    // slice): its host->device transfer is what the GPU has to wait for before it can start
-    std::vector<long long> cuts;
-    cuts.push_back(0);
-    if (nsplit == 2 && first_frac > 0.0 && first_frac < 1.0 && total >= 2 * 65536) {
-        long long c1 = (long long)(first_frac * (double)total);
-        c1 = std::max<long long>(65536, c1 - c1 % 128);
-        if (c1 < total && total - c1 <= cap) {
-            cuts.push_back(c1);
-            chunk = total - c1;
-        }
-    }
-    while (cuts.back() < total) cuts.push_back(std::min(total, cuts.back() + chunk));
-    const long long nchunks = (long long)cuts.size() - 1;
+    std::future<void> scatter[2];   // host-side scatter of a retired stage's dense t/c
+    auto scatter_done = [&](int set) {
+        if (scatter[set].valid()) scatter[set].get();
+    };
+    const long long nchunks = (long long)chunk_ids.size();
     auto bufs = [&](int set) { return set ? eng->scratch2 : eng->scratch; };
 
     auto copy_in = [&](int set, long long c0, long long nb) -> int32_t {
@@ -735,7 +750,7 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long
             !B[WP].reserve((w && !shared_x) ? pts : 8) || !B[TT].reserve((size_t)nb * nest * 8) ||
             !B[CC].reserve((size_t)nb * nest * 8) || !B[NN].reserve((size_t)nb * 4) ||
             !B[FP_].reserve((size_t)nb * 8) || !B[IER].reserve((size_t)nb * 4) ||
-            !B[AUX].reserve(aux_bytes))
+            !B[AUX].reserve(aux_bytes) || !B[OFF].reserve((size_t)nb * 8) || !B[CUR].reserve(64))
             return FPB_ERR_ALLOC;
         double *aux = B[AUX].as<double>();  // [0]=s [1]=xb [2]=xe, then optional state
         eng->h_aux[set][0] = s;
@@ -789,36 +804,54 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long
         return ok ? FPB_STATUS_OK : FPB_ERR_CUDA;
     };
 
-    // finish the copy-out of a stage: wait for s_out, restore rejected rows
+    // finish the copy-out of a stage: wait for s_out; dense form: scatter into the caller's rows;
+    // 2-D form: restore rejected rows
     auto retire = [&](int set) -> bool {
         FitStage &S = stage[set];
         if (!S.pending) return true;
         if (!cuda_ok(cudaStreamSynchronize(s_out), "sync")) return false;
         stamp("t/c copied out (stage retired)", S.c0);
-        for (size_t i = 0; i < S.bad.size(); ++i) {
-            std::memcpy(t + (size_t)(S.c0 + S.bad[i]) * nest, &S.keep_t[i * S.nmax_used],
-                        (size_t)S.nmax_used * 8);
-            std::memcpy(c + (size_t)(S.c0 + S.bad[i]) * nest, &S.keep_c[i * S.nmax_used],
-                        (size_t)S.nmax_used * 8);
+        if (S.packed) {
+            // the scatter into the caller's rows (two small strided copies per curve) runs on a helper thread:
+            // this thread goes on to launch the next fit
+            const double *tp = eng->h_pack[set], *cp = eng->h_pack[set] + S.total;
+            const long long *off = eng->h_off[set];
+            const long long c0s = S.c0, nbs = S.nb;
+            scatter[set] = std::async(std::launch::async, [=]() {
+                for (long long b = 0; b < nbs; ++b) {
+                    if (off[b] < 0) continue;
+                    const int nn = n[c0s + b];
+                    std::memcpy(t + (size_t)(c0s + b) * nest, tp + off[b], (size_t)nn * 8);
+                    if (nn - k - 1 > 0) std::memcpy(c + (size_t)(c0s + b) * nest, cp + off[b], (size_t)(nn - k - 1) * 8);
+                }
+            });
+        } else {
+            for (size_t i = 0; i < S.bad.size(); ++i) {
+                std::memcpy(t + (size_t)(S.c0 + S.bad[i]) * nest, &S.keep_t[i * S.nmax_used],
+                            (size_t)S.nmax_used * 8);
+                std::memcpy(c + (size_t)(S.c0 + S.bad[i]) * nest, &S.keep_c[i * S.nmax_used],
+                            (size_t)S.nmax_used * 8);
+            }
         }
         S.pending = false;
         return true;
     };
 
+    auto chunk_lo = [&](long long ci) { return b0 + cuts[chunk_ids[ci]]; };
+    auto chunk_nb = [&](long long ci) { return cuts[chunk_ids[ci] + 1] - cuts[chunk_ids[ci]]; };
     if (nchunks > 0) {
-        const int32_t rc = copy_in(0, b0, cuts[1] - cuts[0]);
+        const int32_t rc = copy_in(0, chunk_lo(0), chunk_nb(0));
         if (rc != FPB_STATUS_OK) return rc;
     }
     for (long long ci = 0; ci < nchunks; ++ci) {
         const int set = (int)(ci & 1);
-        const long long c0 = b0 + cuts[ci];
-        const long long nb = cuts[ci + 1] - cuts[ci];
+        const long long c0 = chunk_lo(ci);
+        const long long nb = chunk_nb(ci);
         DevBuf *B = bufs(set);
         // prefetch the next chunk into the other staging set while this one is fitted
         if (ci + 1 < nchunks) {
-            const long long c1 = b0 + cuts[ci + 1];
             if (!retire(1 - set)) return FPB_ERR_CUDA;
-            const int32_t rc = copy_in(1 - set, c1, cuts[ci + 2] - cuts[ci + 1]);
+            const int32_t rc = copy_in(1 - set, chunk_lo(ci + 1), chunk_nb(ci + 1));
             if (rc != FPB_STATUS_OK) return rc;
         }
         double *aux = B[AUX].as<double>();
@@ -861,6 +894,24 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long
                                            B[CC].as<double>(), B[FP_].as<double>(),
                                            B[IER].as<int>(), dfpint, dnrd, nullptr);
         if (rc != FPB_STATUS_OK) return rc;
+        FitStage &S = stage[set];
+        scatter_done(set);   // the pinned staging of this set is about to be overwritten
+        if (pack) {
+            // dense t/c: the point-major copies of the inputs (XP/YP) are dead once the fit has run and are
+            // always large enough (2 m >= 2 nest doubles per curve is not guaranteed, so reserve explicitly)
+            if (!B[TP].reserve((size_t)nb * std::min<long long>(nest, m + k + 1) * 8) ||
+                !B[CP].reserve((size_t)nb * std::min<long long>(nest, m + k + 1) * 8) ||
+                !reserve_pinned((void **)&eng->h_off[set], &eng->h_off_bytes[set], (size_t)nb * 8))
+                return FPB_ERR_ALLOC;
+            ok = cuda_ok(cudaMemsetAsync(B[CUR].ptr, 0, 8, st), "memset") &&
+                 cuda_ok(launch_pack_tc((int)nb, nest, k, B[NN].as<int>(), B[IER].as<int>(), B[TT].as<double>(),
+                                        B[CC].as<double>(), B[CUR].as<unsigned long long>(), B[OFF].as<long long>(),
+                                        B[TP].as<double>(), B[CP].as<double>(), eng->nsm, st), "pack kernel") &&
+                 cuda_ok(cudaMemcpyAsync(eng->h_off[set], B[OFF].ptr, (size_t)nb * 8, cudaMemcpyDeviceToHost, st),
+                         "D2H offsets");
+            eng->launches++;
+            if (!ok) return FPB_ERR_CUDA;
+        }
         ok = cuda_ok(cudaMemcpyAsync(n + c0, B[NN].ptr, (size_t)nb * 4, cudaMemcpyDeviceToHost, st),
                      "D2H n");
         ok = ok && cuda_ok(cudaMemcpyAsync(fp + c0, B[FP_].ptr, (size_t)nb * 8,
@@ -869,62 +920,57 @@ int32_t fit_slice_pipelined(fpb_engine *eng, int nsplit, double first_frac, long
                                            cudaMemcpyDeviceToHost, st), "D2H ier");
         if (!ok || !cuda_ok(cudaStreamSynchronize(st), "sync")) return FPB_ERR_CUDA;
         stamp("fit done, n/fp/ier on host", ci);
-        // knots/coefficients: only the leading max(n) columns carry information
-        FitStage &S = stage[set];
         S.c0 = c0;
         S.nb = nb;
         S.bad.clear();
-        int nmax_used = 0;
-        bool any_fit = false;
-        for (long long b = 0; b < nb; ++b) {
-            if (ier[c0 + b] != FPB_INPUT_ERROR) {
-                nmax_used = std::max(nmax_used, (int)n[c0 + b]);
-                any_fit = true;
-            } else if (iopt != -1) {
-                S.bad.push_back(b);
+        S.packed = pack;
+        if (pack) {
+            long long total = 0;
+            for (long long b = 0; b < nb; ++b)
+                if (eng->h_off[set][b] >= 0) total += n[c0 + b];
+            S.total = total;
+            if (total > 0) {
+                if (!reserve_pinned((void **)&eng->h_pack[set], &eng->h_pack_bytes[set], (size_t)total * 16))
+                    return FPB_ERR_ALLOC;
+                ok = cuda_ok(cudaMemcpyAsync(eng->h_pack[set], B[TP].ptr, (size_t)total * 8, cudaMemcpyDeviceToHost,
+                                             s_out), "D2H t (dense)") &&
+                     cuda_ok(cudaMemcpyAsync(eng->h_pack[set] + total, B[CP].ptr, (size_t)total * 8,
+                                             cudaMemcpyDeviceToHost, s_out), "D2H c (dense)");
+                if (state)
+                    ok = ok && cuda_ok(cudaMemcpyAsync(fpint + (size_t)c0 * nest, dfpint, (size_t)nb * nest * 8,
+                                                       cudaMemcpyDeviceToHost, s_out), "D2H fpint") &&
+                         cuda_ok(cudaMemcpyAsync(nrdata + (size_t)c0 * nest, dnrd, (size_t)nb * nest * 4,
+                                                 cudaMemcpyDeviceToHost, s_out), "D2H nrdata");
+                if (!ok) return FPB_ERR_CUDA;
+                S.pending = true;
             }
+            continue;
         }
-        if (iopt == -1) nmax_used = nest;  // clamped end knots may have been written even on ier=10
-        nmax_used = std::min<int>(std::max(nmax_used, 0), nest);
+        // iopt = -1: the leading max(n) columns as a 2-D copy
+        int nmax_used = nest;  // clamped end knots may have been written even on ier=10
         S.nmax_used = nmax_used;
-        if (nmax_used > 0 && (any_fit || iopt == -1)) {
-            // rows whose fit was rejected keep the caller's t/c (2-D copy of the leading columns;
-            // rejected rows are restored from a host backup when the stage retires)
-            S.keep_t.resize(S.bad.size() * (size_t)nmax_used);
-            S.keep_c.resize(S.bad.size() * (size_t)nmax_used);
-            for (size_t i = 0; i < S.bad.size(); ++i) {
-                std::memcpy(&S.keep_t[i * nmax_used], t + (size_t)(c0 + S.bad[i]) * nest,
-                            (size_t)nmax_used * 8);
-                std::memcpy(&S.keep_c[i * nmax_used], c + (size_t)(c0 + S.bad[i]) * nest,
-                            (size_t)nmax_used * 8);
-            }
-            ok = cuda_ok(cudaMemcpy2DAsync(t + (size_t)c0 * nest, (size_t)nest * 8, B[TT].ptr,
-                                           (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
-                                           cudaMemcpyDeviceToHost, s_out), "D2H t");
-            ok = ok && cuda_ok(cudaMemcpy2DAsync(c + (size_t)c0 * nest, (size_t)nest * 8, B[CC].ptr,
-                                                 (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
-                                                 cudaMemcpyDeviceToHost, s_out), "D2H c");
-            if (state && iopt >= 0) {
-                ok = ok && cuda_ok(cudaMemcpyAsync(fpint + (size_t)c0 * nest, dfpint,
-                                                   (size_t)nb * nest * 8, cudaMemcpyDeviceToHost,
-                                                   s_out), "D2H fpint");
-                ok = ok && cuda_ok(cudaMemcpyAsync(nrdata + (size_t)c0 * nest, dnrd,
-                                                   (size_t)nb * nest * 4, cudaMemcpyDeviceToHost,
-                                                   s_out), "D2H nrdata");
-            }
-            if (!ok) return FPB_ERR_CUDA;
-            S.pending = true;
-        }
+        ok = cuda_ok(cudaMemcpy2DAsync(t + (size_t)c0 * nest, (size_t)nest * 8, B[TT].ptr,
+                                       (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
+                                       cudaMemcpyDeviceToHost, s_out), "D2H t");
+        ok = ok && cuda_ok(cudaMemcpy2DAsync(c + (size_t)c0 * nest, (size_t)nest * 8, B[CC].ptr,
+                                             (size_t)nest * 8, (size_t)nmax_used * 8, (size_t)nb,
+                                             cudaMemcpyDeviceToHost, s_out), "D2H c");
+        if (!ok) return FPB_ERR_CUDA;
+        S.pending = true;
     }
-    if (!retire(0) || !retire(1)) return FPB_ERR_CUDA;
-    return FPB_STATUS_OK;
+    const bool ok_end = retire(0) && retire(1);
+    scatter_done(0);
+    scatter_done(1);
+    stamp("all stages scattered", nchunks);
+    return ok_end ? FPB_STATUS_OK : FPB_ERR_CUDA;
 }
 
-// Few, large chunks: the fit pipeline is most efficient on big batches (its tail -- the last
-// knot sets and the longest p-iterations -- has a fixed latency).  A large slice is halved
-// between two host workers, each with its own engine (stream, workspace, staging) running the
-// pipelined loop on two chunks: the copies of one chunk and the sparsely populated tail of its
-// fit overlap the other worker's compute.  Calls for one device are serialised by a mutex.
+// Chunking of one GPU's slice.  The fit pipeline is most efficient on big batches (its tail -- the last
+// knot sets and the longest p-iterations -- is a chain of latency-bound launches), while the first bytes
+// should reach the GPU quickly and the last copy-out should be short.  The slice is cut into `nchunks`
+// pieces dealt round-robin to `workers` host threads, each with its own engine (stream, workspace,
+// staging): the copies of one chunk and the sparsely populated tail of its fit overlap the other workers'
+// compute.  FPB_HOST_WORKERS (1..4) / FPB_HOST_CHUNKS override the defaults.
 int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_SIZE m,
                        const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
                        const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
@@ -937,38 +983,71 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     fpb_engine *e0 = default_engine(device);
     if (!e0) return FPB_ERR_CUDA;
     const long long total = b1 - b0;
-    int workers = 2, nsplit = 2;
-    if (const char *e = std::getenv("FPB_HOST_WORKERS")) workers = std::max(1, std::min(2, std::atoi(e)));
-    if (const char *e = std::getenv("FPB_HOST_CHUNKS")) nsplit = std::max(1, std::atoi(e));
+    int workers = 4;   // measured (profiles/r02_e2e.md): 2 -> 209 ms, 3 -> 213 ms, 4 -> 184 ms, 6 -> 190 ms per 2^20 curves
+    if (const char *e = std::getenv("FPB_HOST_WORKERS")) workers = std::max(1, std::min(8, std::atoi(e)));
+    // bytes per curve on the device: x,y,w curve-major + point-major, outputs t,c (+state, dense copies)
+    const size_t per_curve = (size_t)m * 8 * 6 + (size_t)nest * 8 * 4 + (size_t)nest * 12 + 64;
+    const long long cap = std::max<long long>(128, (long long)(((size_t)10 << 30) / per_curve) / 128 * 128);  // <= 10 GB per staging set
+    // Plan: one SMALL chunk per worker first (2/32, 3/32, 4/32, 5/32 of the slice: the first bytes reach the
+    // GPU after a few ms and every engine has work early), then one large chunk per worker with the rest
+    // (more if a chunk would exceed the staging cap).  FPB_HOST_PLAN="f1,f2,..." overrides the fractions.
+    std::vector<double> frac;
+    if (const char *e = std::getenv("FPB_HOST_PLAN")) {
+        for (const char *q = e; *q;) {
+            char *end = nullptr;
+            const double v = std::strtod(q, &end);
+            if (end == q) break;
+            if (v > 0) frac.push_back(v);
+            q = (*end == ',') ? end + 1 : end;
+        }
+    }
     if (total < 4 * 65536) {
-        return fit_slice_pipelined(e0, 1, 0.0, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest, n, t,
-                                   c, fp, ier, fpint, nrdata);
+        workers = 1;
+        frac.assign(1, 1.0);
+    } else if (frac.empty()) {
+        double used = 0.0;
+        for (int wk = 0; wk < workers; ++wk) {
+            frac.push_back((2.0 + wk) / 32.0);
+            used += frac.back();
+        }
+        for (int wk = 0; wk < workers; ++wk) frac.push_back((1.0 - used) / workers);
     }
-    if (workers == 1) {
-        return fit_slice_pipelined(e0, 2 * nsplit, 0.0, b0, b1, iopt, m, x, y, w, shared_x, xb, xe, k, s,
-                                   nest, n, t, c, fp, ier, fpint, nrdata);
+    std::vector<long long> cuts;
+    cuts.push_back(0);
+    for (size_t i = 0; i < frac.size() && cuts.back() < total; ++i) {
+        long long want = (i + 1 == frac.size()) ? total - cuts.back() : (long long)(frac[i] * (double)total);
+        want = std::max<long long>(128, (want + 127) / 128 * 128);
+        while (want > 0 && cuts.back() < total) {   // split what exceeds the staging cap
+            const long long piece = std::min(std::min(want, cap), total - cuts.back());
+            cuts.push_back(cuts.back() + piece);
+            want -= piece;
+        }
     }
-    fpb_engine *e1 = default_engine(device + 32);  // second engine of the same device
-    if (!e1) return FPB_ERR_CUDA;
-    long long half = (total / 2 + 127) / 128 * 128;
-    int32_t rc[2] = {FPB_STATUS_OK, FPB_STATUS_OK};
-    std::string err[2];
-    std::thread th[2];
-    fpb_engine *eng2[2] = {e0, e1};
-    const long long lo[2] = {b0, b0 + half}, hi[2] = {b0 + half, b1};
-    // first-chunk fraction of each worker's slice (0.5 = equal halves)
-    double frac[2] = {0.5, 0.5};
-    if (const char *e = std::getenv("FPB_HOST_FIRST_FRAC")) frac[0] = std::atof(e);
-    if (const char *e = std::getenv("FPB_HOST_FIRST_FRAC1")) frac[1] = std::atof(e);
-    for (int wk = 0; wk < 2; ++wk) {
-        th[wk] = std::thread([&, wk]() {
-            rc[wk] = fit_slice_pipelined(eng2[wk], nsplit, frac[wk], lo[wk], hi[wk], iopt, m, x, y, w, shared_x,
-                                         xb, xe, k, s, nest, n, t, c, fp, ier, fpint, nrdata);
+    while (cuts.back() < total) cuts.push_back(std::min(total, cuts.back() + cap));
+    const int nc = (int)cuts.size() - 1;
+    workers = std::min(workers, nc);
+    std::vector<std::vector<int>> ids(workers);
+    for (int ci = 0; ci < nc; ++ci) ids[ci % workers].push_back(ci);
+    if (workers == 1)
+        return fit_slice_pipelined(e0, cuts, ids[0], b0, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest, n, t, c, fp,
+                                   ier, fpint, nrdata);
+    std::vector<fpb_engine *> engs(workers);
+    for (int wk = 0; wk < workers; ++wk) {
+        engs[wk] = default_engine(device + 32 * wk);  // engines 1..3 of the same device
+        if (!engs[wk]) return FPB_ERR_CUDA;
+    }
+    std::vector<int32_t> rc(workers, FPB_STATUS_OK);
+    std::vector<std::string> err(workers);
+    std::vector<std::thread> th;
+    for (int wk = 0; wk < workers; ++wk) {
+        th.emplace_back([&, wk]() {
+            rc[wk] = fit_slice_pipelined(engs[wk], cuts, ids[wk], b0, iopt, m, x, y, w, shared_x, xb, xe, k, s, nest,
+                                         n, t, c, fp, ier, fpint, nrdata);
             if (rc[wk] != FPB_STATUS_OK) err[wk] = fpb_last_error();
         });
     }
     for (auto &tt : th) tt.join();
-    for (int wk = 0; wk < 2; ++wk)
+    for (int wk = 0; wk < workers; ++wk)
         if (rc[wk] != FPB_STATUS_OK) {
             set_last_error(err[wk]);
             return rc[wk];

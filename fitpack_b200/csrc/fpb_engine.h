@@ -42,8 +42,13 @@ struct fpb_engine {
     fpb::DevBuf lists, st_i, st_d, st_nrd;  // pass pipeline: curve lists and per-curve state
     int *h_count = nullptr;           // pinned host word for list-length read-back
     fpb::DevBuf plan_cs, plan_w, plan_row, plan_skip, plan_R, plan_ier, plan_meta;  // shared-x plan
-    fpb::DevBuf scratch[12];          // staging for the host-pointer entry points
-    fpb::DevBuf scratch2[12];         // second staging set (copy/compute overlap)
+    fpb::DevBuf scratch[16];          // staging for the host-pointer entry points
+    fpb::DevBuf scratch2[16];         // second staging set (copy/compute overlap)
+    // pinned host staging of the packed knots/coefficients, one per staging set (grow-only)
+    double *h_pack[2] = {nullptr, nullptr};
+    size_t h_pack_bytes[2] = {0, 0};
+    long long *h_off[2] = {nullptr, nullptr};
+    size_t h_off_bytes[2] = {0, 0};
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_fit[2] = {nullptr, nullptr};
     double h_aux[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};

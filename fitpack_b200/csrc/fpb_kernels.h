@@ -169,6 +169,10 @@ cudaError_t launch_splev(const SplevParams &p, int nsm, cudaStream_t stream);
 cudaError_t launch_transpose(const double *src, long long ld_src, double *dst, long long ld_dst,
                              long long rows, long long cols, cudaStream_t stream);
 cudaError_t launch_fill_i32(int *dst, int value, long long count, cudaStream_t stream);
+// dense t(1:n), c(1:n-k-1) of every curve with ier != 10 (D2H staging of the host-pointer batch fit)
+cudaError_t launch_pack_tc(int nb, int nest, int k, const int *n, const int *ier, const double *t, const double *c,
+                           unsigned long long *cursor, long long *off, double *tp, double *cp, int nsm,
+                           cudaStream_t stream);
 cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused, cudaStream_t stream);
 
 }  // namespace fpb

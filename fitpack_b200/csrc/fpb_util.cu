@@ -42,7 +42,66 @@ __global__ void fill_i32_kernel(int *dst, int value, long long count)
         dst[i] = value;
 }
 
+// Pack the meaningful part of every fitted curve -- t(1:n) and c(1:n-k-1) -- into two dense arrays for the
+// device->host copy of the host-pointer entry points: at config 2 the mean knot count is 20 while the rows
+// are nest = 359 doubles wide and the batch maximum is ~108, so the dense form is 5x smaller than the
+// leading-columns 2-D copy it replaces.  One warp packs 32 curves: lengths are prefix-summed in the warp,
+// one atomic per warp reserves the space (the order of the curves in the dense arrays is therefore not
+// deterministic; off[b] records where curve b went), then the warp copies curve after curve with coalesced
+// loads and stores.  Curves rejected with ier = 10 have length 0 (their t, c are not outputs).
+__global__ void __launch_bounds__(256) pack_tc_kernel(int nb, int nest, int k, const int *__restrict__ n,
+                                                      const int *__restrict__ ier, const double *__restrict__ t,
+                                                      const double *__restrict__ c, unsigned long long *cursor,
+                                                      long long *__restrict__ off, double *__restrict__ tp,
+                                                      double *__restrict__ cp)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long b0 = warp * 32; b0 < nb; b0 += nwarps * 32) {
+        const long long b = b0 + lane;
+        int len = 0;
+        if (b < nb && ier[b] != 10) {
+            len = n[b];
+            if (len < 0 || len > nest) len = 0;
+        }
+        int incl = len;   // inclusive prefix sum over the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(cursor, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const long long mine = (long long)base + incl - len;
+        if (b < nb) off[b] = len > 0 ? mine : -1;
+        for (int j = 0; j < 32; ++j) {
+            const int lj = __shfl_sync(0xffffffffu, len, j);
+            if (lj == 0) continue;
+            const long long oj = __shfl_sync(0xffffffffu, mine, j);
+            const double *tj = t + (b0 + j) * nest, *cj = c + (b0 + j) * nest;
+            for (int i = lane; i < lj; i += 32) {
+                tp[oj + i] = tj[i];
+                cp[oj + i] = i < lj - k - 1 ? cj[i] : 0.0;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_pack_tc(int nb, int nest, int k, const int *n, const int *ier, const double *t, const double *c,
+                           unsigned long long *cursor, long long *off, double *tp, double *cp, int nsm,
+                           cudaStream_t stream)
+{
+    if (nb <= 0) return cudaSuccess;
+    long long blocks = ((long long)nb + 255) / 256;
+    if (blocks > (long long)nsm * 8) blocks = (long long)nsm * 8;
+    pack_tc_kernel<<<(unsigned)blocks, 256, 0, stream>>>(nb, nest, k, n, ier, t, c, cursor, off, tp, cp);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_transpose(const double *src, long long ld_src, double *dst, long long ld_dst,
                              long long rows, long long cols, cudaStream_t stream)
