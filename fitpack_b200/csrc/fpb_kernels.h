@@ -157,6 +157,7 @@ cudaError_t launch_shared_apply(int nbatch, int m, int k, int n, const double *y
 // ---- evaluation ----
 struct SplevParams {
     int nspl, ldt, k, m, e, mode, nshared;
+    int tab = 0;            // EXACT: span table of bspl_tab in shared memory (set by launch_splev)
     const double *t, *c, *x;
     const int *n;
     double *y;

@@ -12,6 +12,7 @@
 // coordinates (the reference does the same); values are bit-identical to the reference's
 // operation order (no FMA).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -37,13 +38,19 @@ template <int K>
 __global__ void __launch_bounds__(kCurevWarps * 32)
     curev_kernel(int nspl, int idim, const double *__restrict__ t, const int *__restrict__ n,
                  const double *__restrict__ c, int ldt, long long ldc, const double *__restrict__ u,
-                 double *__restrict__ x, int m, int *__restrict__ ier, int smem_ld)
+                 double *__restrict__ x, int m, int *__restrict__ ier, int smem_ld, int tab)
 {
-    constexpr int K1 = K + 1;
+    constexpr int K1 = K + 1, NS = K * (K + 1) / 2;
     extern __shared__ double curev_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *ts = curev_smem + (size_t)wib * smem_ld * (1 + idim);  // knots, then idim coefficient rows
+    // per warp: knots, idim coefficient rows and (tab) the span table of bspl_tab: NS refined reciprocals
+    // per knot interval + one mask word per interval (fpb_common.cuh) -- same bits, a third of the FP64 work
+    // `tab` = knot intervals the table holds (0: none); curves with more intervals use plain divisions
+    const size_t per_warp = (size_t)smem_ld * (1 + idim) + (tab ? (size_t)NS * tab + (tab + 1) / 2 : 0);
+    double *ts = curev_smem + (size_t)wib * per_warp;
     double *cs = ts + smem_ld;
+    double *spans = ts + (size_t)smem_ld * (1 + idim);
+    unsigned *spmask = reinterpret_cast<unsigned *>(spans + (size_t)NS * tab);
     const int wpb = blockDim.x >> 5;  // warps per CTA: kCurevWarps unless the tables of a long curve need the room
     const long long warp0 = (long long)blockIdx.x * wpb + wib;
     const long long nwarps = (long long)gridDim.x * wpb;
@@ -68,6 +75,19 @@ __global__ void __launch_bounds__(kCurevWarps * 32)
         for (int d = 0; d < idim; ++d)
             for (int i = lane; i < nk1; i += 32) cs[d * smem_ld + i] = cj[(long long)d * nj + i];
         __syncwarp();
+        const bool use_tab = tab > 0 && nk1 - K <= tab;
+        if (use_tab) {
+            for (int li = lane; li < nk1 - K; li += 32) {   // interval l = K1 + li
+                double twi[2 * K];
+#pragma unroll
+                for (int q = 0; q < 2 * K; ++q) twi[q] = ts[li + 1 + q];   // t(l-K+1+q), 0-based l-K+q = li+1+q
+                SpanTab<K, 1> sp;
+                sp.rs = spans + (size_t)li * NS;
+                span_init<K, 1>(sp, twi);
+                spmask[li] = sp.special;
+            }
+            __syncwarp();
+        }
         const double tb = ts[K1 - 1], te = ts[nk1];
         int lbase = K1;  // interval (1-based) the previous step's last point fell in
         for (int i0 = 0; i0 < m; i0 += 32) {
@@ -83,7 +103,14 @@ __global__ void __launch_bounds__(kCurevWarps * 32)
                 double tw[2 * K], h[K1];
 #pragma unroll
                 for (int q = 0; q < 2 * K; ++q) tw[q] = ts[l - K + q];  // t(l-K+1+q)
-                bspl<K>(tw, arg, h);
+                if (use_tab) {
+                    SpanTab<K, 1> sp;
+                    sp.rs = spans + (size_t)(l - K1) * NS;
+                    sp.special = spmask[l - K1];
+                    bspl_tab<K, 1>(tw, sp, arg, h);
+                } else {
+                    bspl<K>(tw, arg, h);
+                }
                 const double *cl = cs + (l - K1);
                 for (int d = 0; d < idim; ++d) {
                     double sum = 0.0;
@@ -103,12 +130,25 @@ cudaError_t launch_curev_k(int nspl, int idim, const double *t, const int *n, co
 {
     const int smem_ld = (ldt + 1) & ~1;
     // 8 warps per CTA; curves with many knots x coordinates get fewer warps so that their tables still
-    // fit the 200 KB a CTA may claim (one warp: n*(1+idim) <= 25 600 doubles)
+    // fit the 200 KB a CTA may claim (one warp: n*(1+idim) <= 25 600 doubles).
+    const int nintmax = smem_ld > 2 * K + 2 ? smem_ld - 2 * K - 1 : 1;
+    const size_t base_d = (size_t)smem_ld * (1 + idim);
+    static const bool no_tab = std::getenv("FPB_CUREV_NO_TAB") != nullptr;
+    // span table for up to 96 knot intervals per curve -- only where it does not cost resident CTAs (measured on
+    // the bench shape, ld = 260: the table halves the residency and evaluation drops from 40 to 34 G points/s)
+    int tab = no_tab ? 0 : (nintmax < 96 ? nintmax : 96);
+    auto resident = [&](size_t doubles) {
+        const size_t b = doubles * sizeof(double) * kCurevWarps;
+        const int r = b > 0 ? (int)((size_t)200 * 1024 / b) : 8;
+        return r > 8 ? 8 : r;
+    };
+    if (tab && resident(base_d + (size_t)(K * (K + 1) / 2) * tab + (tab + 1) / 2) != resident(base_d)) tab = 0;
+    const size_t per_warp = (base_d + (tab ? (size_t)(K * (K + 1) / 2) * tab + (tab + 1) / 2 : 0)) * sizeof(double);
     int warps = kCurevWarps;
-    size_t smem = (size_t)warps * smem_ld * (1 + idim) * sizeof(double);
+    size_t smem = (size_t)warps * per_warp;
     while (smem > 200u * 1024u && warps > 1) {
         warps >>= 1;
-        smem = (size_t)warps * smem_ld * (1 + idim) * sizeof(double);
+        smem = (size_t)warps * per_warp;
     }
     if (smem > 200u * 1024u) {
         set_last_error("curev: knot/coefficient tables of one curve exceed 200 KB of shared memory (n*(1+idim) > 25600)");
@@ -123,7 +163,7 @@ cudaError_t launch_curev_k(int nspl, int idim, const double *t, const int *n, co
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     long long blocks = ((long long)nspl + warps - 1) / warps;
     blocks = std::min<long long>(blocks, (long long)nsm * per_sm);
-    kern<<<(int)blocks, warps * 32, smem, st>>>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, smem_ld);
+    kern<<<(int)blocks, warps * 32, smem, st>>>(nspl, idim, t, n, c, ldt, ldc, u, x, m, ier, smem_ld, tab);
     return cudaGetLastError();
 }
 

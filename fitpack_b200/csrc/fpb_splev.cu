@@ -20,6 +20,8 @@
 //   TMA tiles that runs ahead across spline boundaries, so neither the table
 //   build nor the DRAM latency of the point stream is exposed.  Same interval
 //   indices; values agree with the exact mode to ~1e-15*max|c| (tests: 1e-12).
+#include <cstdlib>
+
 #include "fpb_common.cuh"
 #include "fpb_kernels.h"
 
@@ -113,12 +115,16 @@ static_assert(kFastWarps <= kSplevWarps, "mbarrier header is sized for kSplevWar
 // per-warp shared memory in doubles: two (t, c) buffers [2][2][ld] (the next spline's tables are
 // prefetched while the current one is evaluated); EXACT: + uint16 lookup grid; FAST: + interval
 // records [kRecD*(ld-2K-1)], the 16-byte lookup cells and the ring of x tiles
-__host__ __device__ inline int splev_smem_doubles(int mode, int k, int ld)
+// EXACT with tab != 0: + the span table of bspl_tab (k(k+1)/2 refined reciprocals per knot interval and one
+// mask word per interval): fpbspl's divisions become three FP64 instructions each, same bits.
+// `tab` = number of knot intervals the table holds (0: none); splines with more intervals use plain divisions.
+__host__ __device__ inline int splev_smem_doubles(int mode, int k, int ld, int tab = 0)
 {
     const int cells = splev_grid_cells(ld - 2 * k - 1);
     const int nintmax = (ld - 2 * k - 1 > 1) ? ld - 2 * k - 1 : 1;
-    return ld * 4 + ((mode == 1) ? ((kRecD * nintmax + 1) & ~1) + 2 * cells + kNBuf * kTilePts
-                                 : (cells + 3) / 4);
+    const int d = ld * 4 + ((mode == 1) ? ((kRecD * nintmax + 1) & ~1) + 2 * cells + kNBuf * kTilePts
+                                        : (cells + 3) / 4 + (tab ? (k * (k + 1) / 2) * tab + (tab + 1) / 2 : 0));
+    return (d + 1) & ~1;   // every warp's region starts 16-byte aligned (TMA destinations)
 }
 
 // 1/d by hardware seed + two Newton steps (FAST mode only; d must be a normal number well inside
@@ -158,6 +164,44 @@ __device__ __forceinline__ double eval_exact(const double *ts, const double *cs,
 #pragma unroll
     for (int j = 0; j <= K; ++j) sp = add(sp, mul(cs[l - K - 1 + j], h[j]));  // c(l-K+j)
     return sp;
+}
+
+// EXACT mode with the span table: per knot interval the (refined) reciprocals of the K(K+1)/2 knot spans
+// fpbspl divides by (fpb_common.cuh: the reciprocal-refinement half of the hardware's division sequence,
+// done once per interval instead of once per point).  Each lane owns the intervals li = lane, lane+32, ...
+template <int K>
+__device__ __forceinline__ void build_spans(const double *ts, int n, double *spans, unsigned *spmask, int lane)
+{
+    constexpr int K1 = K + 1, NS = K * (K + 1) / 2;
+    const int nint = n - K1 - K;
+    for (int li = lane; li < nint; li += 32) {
+        const int l = K1 + li;
+        double tw[2 * K];
+#pragma unroll
+        for (int q = 0; q < 2 * K; ++q) tw[q] = ts[l - K + q];
+        SpanTab<K, 1> sp;
+        sp.rs = spans + (size_t)li * NS;
+        span_init<K, 1>(sp, tw);
+        spmask[li] = sp.special;
+    }
+}
+
+template <int K>
+__device__ __forceinline__ double eval_exact_tab(const double *ts, const double *cs, const double *spans,
+                                                 const unsigned *spmask, int l, double arg)
+{
+    constexpr int NS = K * (K + 1) / 2;
+    double tw[2 * K], h[K + 1];
+#pragma unroll
+    for (int j = 0; j < 2 * K; ++j) tw[j] = ts[l - K + j];
+    SpanTab<K, 1> sp;
+    sp.rs = const_cast<double *>(spans) + (size_t)(l - K - 1) * NS;
+    sp.special = spmask[l - K - 1];
+    bspl_tab<K, 1>(tw, sp, arg, h);
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j <= K; ++j) v = add(v, mul(cs[l - K - 1 + j], h[j]));
+    return v;
 }
 
 // FAST mode: convert the spline (ts, cs) into one local Taylor polynomial per knot interval.
@@ -325,12 +369,15 @@ __global__ void __launch_bounds__(kSplevWarps * 32, 2) splev_kernel(SplevParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    const int per_warp = splev_smem_doubles(0, K, smem_ld);
+    const int per_warp = splev_smem_doubles(0, K, smem_ld, p.tab);
     uint64_t *mbars = reinterpret_cast<uint64_t *>(smem_raw);
     double *base = reinterpret_cast<double *>(smem_raw + 8 * kMbarPerWarp * kSplevWarps) + (size_t)warp * per_warp;
     auto tsb = [&](int b) { return base + (size_t)(2 * b) * smem_ld; };  // (t, c) buffer b
     auto csb = [&](int b) { return base + (size_t)(2 * b + 1) * smem_ld; };
     unsigned short *grid = reinterpret_cast<unsigned short *>(base + 4 * smem_ld);
+    double *spans = base + 4 * smem_ld + (splev_grid_cells(smem_ld - 2 * K - 1) + 3) / 4;
+    unsigned *spmask = reinterpret_cast<unsigned *>(spans + (size_t)(K * (K + 1) / 2) * p.tab);
+    bool use_tab = false;   // per spline: its intervals fit the table
     double *ts = tsb(0), *cs = csb(0);
     int tbuf = 0;           // table buffer holding the current spline
     long long staged = -1;  // spline whose tables were prefetched into buffer 1-tbuf (TMA in flight)
@@ -405,6 +452,8 @@ __global__ void __launch_bounds__(kSplevWarps * 32, 2) splev_kernel(SplevParams 
             }
             __syncwarp();
             build_grid<K, false>(ts, n, grid, gcells, inv_h, lane);
+            use_tab = p.tab > 0 && (n - 2 * K - 1) <= p.tab;
+            if (use_tab) build_spans<K>(ts, n, spans, spmask, lane);
             __syncwarp();
             cached = (int)tj;
         }
@@ -438,7 +487,8 @@ __global__ void __launch_bounds__(kSplevWarps * 32, 2) splev_kernel(SplevParams 
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) l[u] = locate(ts, grid, gcells, tb, inv_h, K1, nk1, arg[u]);
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) sp[u] = eval_exact<K>(ts, cs, l[u], arg[u]);
+            for (int u = 0; u < kUnroll; ++u)
+                sp[u] = use_tab ? eval_exact_tab<K>(ts, cs, spans, spmask, l[u], arg[u]) : eval_exact<K>(ts, cs, l[u], arg[u]);
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const int i = i0 + 32 * u;
@@ -746,16 +796,31 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastBlocks) splev_fast_kerne
 
 }  // namespace
 
-cudaError_t launch_splev(const SplevParams &p, int nsm, cudaStream_t stream)
+cudaError_t launch_splev(const SplevParams &p_in, int nsm, cudaStream_t stream)
 {
+    SplevParams p = p_in;
     if (p.nspl <= 0) return cudaSuccess;
     const int smem_ld = (p.ldt + 1) & ~1;  // keep every per-warp region 16 B aligned
-    const size_t per_warp = (size_t)splev_smem_doubles(p.mode, p.k, smem_ld) * sizeof(double);
     const size_t header = 8 * kMbarPerWarp * kSplevWarps;
-    int wpb = (p.mode == 1) ? kFastWarps : kSplevWarps;
+    // EXACT: a span table for up to 96 knot intervals per spline (6 to 12 KB per warp at k = 3..5, small
+    // next to the knot/coefficient staging so that the resident warps stay); longer splines evaluate fpbspl
+    // with plain divisions
+    static const bool no_tab = std::getenv("FPB_SPLEV_NO_TAB") != nullptr;
+    {
+        const int nintmax = (smem_ld - 2 * p.k - 1 > 1) ? smem_ld - 2 * p.k - 1 : 1;
+        p.tab = (p.mode == 0 && !no_tab) ? (nintmax < 96 ? nintmax : 96) : 0;
+    }
     const int reg_blocks = (p.mode == 1) ? kFastBlocks : 2;  // CTAs/SM the register budget allows
     // keep reg_blocks CTAs resident if the tables allow it (227 KB per SM, 1 KB reserved per CTA)
-    while (wpb > 1 && header + per_warp * wpb > (size_t)(227 * 1024) / reg_blocks - 1024) wpb >>= 1;
+    auto warps_for = [&](int tab) {
+        const size_t pw = (size_t)splev_smem_doubles(p.mode, p.k, smem_ld, tab) * sizeof(double);
+        int w = (p.mode == 1) ? kFastWarps : kSplevWarps;
+        while (w > 1 && header + pw * w > (size_t)(227 * 1024) / reg_blocks - 1024) w >>= 1;
+        return w;
+    };
+    if (p.tab && warps_for(p.tab) != warps_for(0)) p.tab = 0;   // never trade resident warps for the table
+    const size_t per_warp = (size_t)splev_smem_doubles(p.mode, p.k, smem_ld, p.tab) * sizeof(double);
+    int wpb = warps_for(p.tab);
     const size_t smem = header + per_warp * wpb;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;  // knot vectors beyond ~4000 entries
     long long blocks = ((long long)p.nspl + wpb - 1) / wpb;
