@@ -624,6 +624,19 @@ def main():
         ev1.record()
         barrier()
         c_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        # FAST mode: one fast-splev pass per coordinate (local polynomials + Horner)
+        for _ in range(2):
+            xfv, ifv = eng.curev_batch(dp, rp["t"], rp["n"], rp["c"], kp, ud, mode=1)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            xfv, ifv = eng.curev_batch(dp, rp["t"], rp["n"], rp["c"], kp, ud, out=(xfv, ifv), mode=1)
+        ev1.record()
+        barrier()
+        cf_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        cscale = torch.clamp(rp["c"].abs().amax(dim=1), min=1.0)[:, None, None]
+        cf_err = float(((xfv - xev).abs() / cscale).max().item())
+        del xfv
         cur_bytes = Bp * mp * 8.0 * (1 + dp)
         pbytes = Bp * (8.0 * mp * (dp + 1) + 8.0 * float(n_p.mean().item()) * (dp + 1) + 16)
         parc = {
@@ -647,7 +660,53 @@ def main():
                                    "achieved": cur_bytes / (c_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                    "unit": "GB/s", "frac": cur_bytes / (c_ms * 1e-3) / 1e9 / hbm_peak,
                                    "traffic": None, "peak_source": peak_src,
-                                   "algorithmic_bytes_per_point": 8.0 * (1 + dp)}}}
+                                   "algorithmic_bytes_per_point": 8.0 * (1 + dp)}},
+            "curev_fast": {"ms": cf_ms, "value": world * cur_bytes / (cf_ms * 1e-3) / 1e9, "unit": "GB/s",
+                           "gpts_per_s": world * Bp * mp / (cf_ms * 1e-3) / 1e9,
+                           "max_err_vs_exact_rel_to_max_c": cf_err,
+                           "roofline": {"bound": "hbm", "kernel": "splev_fast_kernel<3> x idim passes (curev FAST)",
+                                        "achieved": cur_bytes / (cf_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                        "unit": "GB/s", "frac": cur_bytes / (cf_ms * 1e-3) / 1e9 / hbm_peak,
+                                        "traffic": None, "peak_source": peak_src,
+                                        "algorithmic_bytes_per_point": 8.0 * (1 + dp)}}}
+        # dense evaluation (many points per knot interval), compact tables: where FAST is meant to be used
+        Bd, md = min(Bp, 1 << 16), 2048
+        nmx = int(rp["n"][:Bd].max().item())
+        nmx += nmx & 1
+        td_ = rp["t"][:Bd, :nmx].contiguous()
+        cd_ = rp["c"][:Bd, :dp * nmx].contiguous()
+        nd_ = rp["n"][:Bd].contiguous()
+        udn = torch.linspace(0, 1, md, device=dev, dtype=f64)[None, :].expand(Bd, md).contiguous()
+        dense = {}
+        for mode_, nm_ in ((0, "exact"), (1, "fast")):
+            xo_, io_ = eng.curev_batch(dp, td_, nd_, cd_, kp, udn, mode=mode_)
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                xo_, io_ = eng.curev_batch(dp, td_, nd_, cd_, kp, udn, out=(xo_, io_), mode=mode_)
+            ev1.record()
+            barrier()
+            d_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+            dense[nm_] = {"ms": d_ms, "gpts_per_s": world * Bd * md / (d_ms * 1e-3) / 1e9,
+                          "value": world * Bd * md * 8.0 * (1 + dp) / (d_ms * 1e-3) / 1e9, "unit": "GB/s",
+                          "frac_of_hbm_peak": Bd * md * 8.0 * (1 + dp) / (d_ms * 1e-3) / 1e9 / hbm_peak}
+            if mode_ == 0:
+                xex_ = xo_
+            else:
+                dense["max_err_vs_exact_rel_to_max_c"] = float(((xo_ - xex_).abs() / cscale[:Bd]).max().item())
+        dense["workload"] = "%d fitted idim=%d curves x %d points each, compact tables (ldt=%d)" % (Bd, dp, md, nmx)
+        parc["curev_dense"] = dense
+        del xo_, xex_, udn
+        for key_ in ("curev", "curev_fast"):
+            rr = dict(parc[key_]["roofline"])
+            rr.update({"gpts_per_s": parc[key_]["gpts_per_s"], "ms_per_step": parc[key_]["ms"],
+                       "workload": "curev of %d fitted idim=%d curves x %d points" % (Bp, dp, mp)})
+            roof["secondary"].append(rr)
+        roof["secondary"].append({"bound": "hbm", "kernel": "curev FAST, dense evaluation", "unit": "GB/s",
+                                  "achieved": dense["fast"]["value"] / world, "peak": hbm_peak,
+                                  "frac": dense["fast"]["frac_of_hbm_peak"], "traffic": None,
+                                  "peak_source": peak_src, "exact_gbs": dense["exact"]["value"] / world,
+                                  "workload": dense["workload"]})
         if rank == 0 and world == 1 and not args.no_cpu:
             import oracle_lib as O
             nthr_ = host_threads()

@@ -194,9 +194,10 @@ class Engine:
             res["stats"] = stats_t
         return res
 
-    def curev_batch(self, idim, t, n, c, k, u, out=None):
+    def curev_batch(self, idim, t, n, c, k, u, out=None, mode=0):
         """curev for many curves: t [B][ldt], c [B][ldc], u [B][m] -> (x [B][m][idim], ier [B]);
-        out = (x, ier) reuses the result tensors of an earlier call."""
+        out = (x, ier) reuses the result tensors of an earlier call.  mode 0: exact (reference arithmetic,
+        bit-identical), 1: fast (local polynomials + Horner, tolerance 1e-12 * max(1, max|c|))."""
         _chk_f64(t, "t"); _chk_f64(c, "c"); _chk_f64(u, "u")
         B, m = u.shape
         if out is not None:
@@ -205,6 +206,7 @@ class Engine:
             x = torch.zeros((B, m, idim), device=u.device, dtype=torch.float64)
             ier = torch.zeros(B, device=u.device, dtype=torch.int32)
         self.use_torch_stream()
+        check(lib().fpb_engine_set_curev_mode(self._h, int(mode)), "set_curev_mode")
         rc = lib().fp_curev_batch_dev_c(self._h, B, int(idim), _ptr(t), _ptr(n), _ptr(c), t.stride(0),
                                         c.stride(0), int(k), _ptr(u.contiguous()), _ptr(x), m, _ptr(ier))
         check(rc, "fp_curev_batch_dev_c")

@@ -174,6 +174,7 @@ void fpb_engine_destroy(fpb_engine *eng)
     eng->wsi2.release();
     eng->az_pool.release();
     eng->az_off.release();
+    eng->curev_n.release();
     if (eng->s_p2) cudaStreamDestroy(eng->s_p2);
     for (int i = 0; i < 2; ++i)
         if (eng->ev_p2[i]) cudaEventDestroy(eng->ev_p2[i]);
@@ -250,6 +251,13 @@ int32_t fpb_engine_set_shared_mode(fpb_engine *eng, int32_t mode)
 {
     if (!eng || (mode != 0 && mode != 1)) return FPB_ERR_ARG;
     eng->shared_fast = mode;
+    return FPB_STATUS_OK;
+}
+
+int32_t fpb_engine_set_curev_mode(fpb_engine *eng, int32_t mode)
+{
+    if (!eng || (mode != 0 && mode != 1)) return FPB_ERR_ARG;
+    eng->curev_fast = mode;
     return FPB_STATUS_OK;
 }
 

@@ -158,6 +158,10 @@ cudaError_t launch_shared_apply(int nbatch, int m, int k, int n, const double *y
 struct SplevParams {
     int nspl, ldt, k, m, e, mode, nshared;
     int tab = 0;            // EXACT: span table of bspl_tab in shared memory (set by launch_splev)
+    // FAST mode, used by curev's fast path (one launch per coordinate d): coefficients of spline j start at
+    // c[j*ldc + c_mul*n(j)], results go to y[(j*m + i)*y_stride + y_off].  Plain splev: ldc = ldt, 0, 1, 0.
+    long long ldc = 0;      // 0: ldt
+    int c_mul = 0, y_stride = 1, y_off = 0;
     const double *t, *c, *x;
     const int *n;
     double *y;

@@ -124,6 +124,23 @@ __global__ void __launch_bounds__(kCurevWarps * 32)
     }
 }
 
+// fast path: curves whose parameters are not non-decreasing (ier = 10, nothing written, core:1145) get a zero
+// knot count, which makes the evaluation kernel flag and skip them
+__global__ void curev_check_kernel(int nspl, int m, const double *__restrict__ u, const int *__restrict__ n,
+                                   int *__restrict__ n_eff)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long j = warp; j < nspl; j += nwarps) {
+        const double *uj = u + j * (long long)m;
+        bool bad = false;
+        for (int i = lane + 1; i < m; i += 32) bad = bad || (uj[i] < uj[i - 1]);
+        bad = __any_sync(FULLW, bad);
+        if (lane == 0) n_eff[j] = bad ? 0 : n[j];
+    }
+}
+
 template <int K>
 cudaError_t launch_curev_k(int nspl, int idim, const double *t, const int *n, const double *c, int ldt,
                            long long ldc, const double *u, double *x, int m, int *ier, int nsm, cudaStream_t st)
@@ -269,6 +286,27 @@ int32_t fp_curev_batch_dev_c(fpb_engine *eng, FP_SIZE nspl, FP_SIZE idim, const 
     if (m < 1 || idim < 1 || idim > kMaxIdim || k < 1 || k > 5) {  // core:1142
         if (!cuda_ok(launch_fill_i32(ier, FPB_INPUT_ERROR, nspl, eng->stream), "fill ier")) return FPB_ERR_CUDA;
         eng->launches++;
+        return FPB_STATUS_OK;
+    }
+    if (eng->curev_fast) {
+        // FAST: every coordinate is a spline on the shared knots -- one pass of the fast splev kernel per
+        // coordinate (coefficients at c + d*n, results interleaved into x(idim,m)); arguments are clamped to
+        // [t(k+1), t(n-k)] as curev does (core:1163-1165 = splev's e = 3)
+        if (!eng->curev_n.reserve((size_t)nspl * sizeof(int))) return FPB_ERR_ALLOC;
+        int *n_eff = eng->curev_n.as<int>();
+        long long blocks = ((long long)nspl + 7) / 8;
+        blocks = std::min<long long>(blocks, (long long)eng->nsm * 8);
+        curev_check_kernel<<<(int)blocks, 256, 0, eng->stream>>>(nspl, m, u, n, n_eff);
+        if (!cuda_ok(cudaGetLastError(), "curev check kernel")) return FPB_ERR_CUDA;
+        eng->launches++;
+        for (int d = 0; d < idim; ++d) {
+            SplevParams sp;
+            sp.nspl = nspl; sp.ldt = ldt; sp.k = k; sp.m = m; sp.e = 3; sp.mode = 1; sp.nshared = 0;
+            sp.t = t; sp.c = c; sp.x = u; sp.n = n_eff; sp.y = x; sp.ier = ier; sp.lidx = nullptr;
+            sp.ldc = ldc; sp.c_mul = d; sp.y_stride = idim; sp.y_off = d;
+            if (!cuda_ok(launch_splev(sp, eng->nsm, eng->stream), "curev fast kernel")) return FPB_ERR_CUDA;
+            eng->launches++;
+        }
         return FPB_STATUS_OK;
     }
     if (!cuda_ok(launch_curev(nspl, idim, t, n, c, ldt, ldc, k, u, x, m, ier, eng->nsm, eng->stream),

@@ -572,9 +572,9 @@ __device__ __forceinline__ void fast_group(const SplevParams &p, const double *t
         const int i = ibase + 32 * u;
         if (ALLLIVE || live[u]) {
             if (PLAIN) {
-                yg[i] = sp[u];
+                yg[(size_t)i * p.y_stride] = sp[u];
             } else {
-                yg[i] = zero[u] ? 0.0 : sp[u];
+                yg[(size_t)i * p.y_stride] = zero[u] ? 0.0 : sp[u];
                 if (lg) lg[i] = zero[u] ? 0 : lf[u];
             }
         }
@@ -653,9 +653,12 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastBlocks) splev_fast_kerne
         for (int b = 0; b < kNBuf; ++b) produce();
     }
 
+    const long long ldc = p.ldc ? p.ldc : p.ldt;
+    auto coef = [&](long long q, int nq) { return p.c + q * ldc + (long long)p.c_mul * nq; };
     auto tables_tma_ok = [&](long long q, int nq) -> bool {
-        const double *tg = p.t + q * p.ldt, *cg = p.c + q * p.ldt;
-        return ((((uintptr_t)tg) | ((uintptr_t)cg)) & 15) == 0 && (((nq + 1) & ~1) <= p.ldt);
+        const double *tg = p.t + q * p.ldt, *cg = coef(q, nq);
+        return ((((uintptr_t)tg) | ((uintptr_t)cg)) & 15) == 0 && (((nq + 1) & ~1) <= p.ldt) &&
+               ((long long)p.c_mul * nq + ((nq + 1) & ~1) <= ldc);
     };
     auto issue_tables = [&](long long q, int nq, int buf) {
         if (lane == 0) {
@@ -663,7 +666,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastBlocks) splev_fast_kerne
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             mbar_expect_tx(mbar, 2 * bytes);
             tma_load_1d(tsb(buf), p.t + q * p.ldt, bytes, mbar);
-            tma_load_1d(csb(buf), p.c + q * p.ldt, bytes, mbar);
+            tma_load_1d(csb(buf), coef(q, nq), bytes, mbar);
         }
     };
 
@@ -703,10 +706,10 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastBlocks) splev_fast_kerne
                 mbar_wait(mbar, phase);
                 phase ^= 1;
             } else {
-                const double *tg = p.t + tj * p.ldt, *cg = p.c + tj * p.ldt;
+                const double *tg = p.t + tj * p.ldt, *cg = coef(tj, n);
                 for (int i = lane; i < n; i += 32) {
                     tsb(tbuf)[i] = tg[i];
-                    csb(tbuf)[i] = cg[i];
+                    csb(tbuf)[i] = (i < n - K1) ? cg[i] : 0.0;   // only the n-k-1 coefficients are addressable
                 }
             }
             ts = tsb(tbuf);
@@ -727,7 +730,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, kFastBlocks) splev_fast_kerne
         }
         const int nk1 = n - K1;
         const double tb = ts[K1 - 1], te = ts[nk1];
-        double *yg = p.y + j * p.m;
+        double *yg = p.y + (j * p.m) * p.y_stride + p.y_off;
         int *lg = p.lidx ? p.lidx + j * p.m : nullptr;
         bool out_of_range = false;
         if (xt_ok) {

@@ -153,6 +153,13 @@ int32_t fpb_engine_synchronize(fpb_engine *eng);
 #define FPB_SHARED_EXACT 0
 #define FPB_SHARED_FAST  1
 int32_t fpb_engine_set_shared_mode(fpb_engine *eng, int32_t mode);
+/* arithmetic of fp_curev_batch_dev_c: FPB_CUREV_EXACT (default): the reference's de Boor-Cox recurrence and
+   operation order, bit-identical values;  FPB_CUREV_FAST: one local polynomial per knot interval +
+   Horner/FMA through the fast splev kernel, one pass per coordinate (identical knot intervals, values within
+   1e-12 * max(1, max|c|) of exact; ier as in exact mode). */
+#define FPB_CUREV_EXACT 0
+#define FPB_CUREV_FAST  1
+int32_t fpb_engine_set_curev_mode(fpb_engine *eng, int32_t mode);
 /* number of kernels this engine has launched since creation (bench bookkeeping) */
 int64_t fpb_engine_launch_count(const fpb_engine *eng);
 /* same counter for the DEFAULT engine of `device` -- the one the host-pointer entry points

@@ -1,0 +1,49 @@
+"""GPU: curev FAST mode (one fast-splev pass per coordinate) against the oracle's curev: stated tolerance
+1e-12 * max(1, max|c|), identical ier (curves whose parameters decrease are rejected with ier = 10 and left
+untouched), arguments clamped to the knot range like the reference (core:1163-1165)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from refdata import synth_param_curves
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("idim,k", [(1, 3), (2, 3), (3, 5), (2, 1), (5, 2)])
+def test_curev_fast_matches_exact_within_tolerance(idim, k):
+    import torch
+    import fitpack_b200
+    from fitpack_b200.batch import Engine
+    dev = torch.device("cuda", 0)
+    eng = Engine(dev)
+    rng = np.random.default_rng(100 + 10 * idim + k)
+    B, m = 300, 64
+    th, xp = synth_param_curves(rng, B, m, idim)
+    nest = m + k + 1
+    fit = O.parcur_batch(0, 0, idim, xp, None, k, m * idim * 0.0025, nest)
+    ue = np.sort(rng.uniform(-0.05, 1.05, (B, 101)), axis=1)     # odd count: the unaligned point path too
+    ue[7, 50] = ue[7, 49] - 1e-3                                  # a decreasing parameter: ier = 10
+    t_d = torch.from_numpy(fit["t"]).to(dev)
+    n_d = torch.from_numpy(fit["n"]).to(dev)
+    c_d = torch.from_numpy(fit["c"]).to(dev)
+    u_d = torch.from_numpy(ue).to(dev)
+    xo, io = O.curev_batch(idim, fit["t"], fit["n"], fit["c"], k, ue)
+    x0 = torch.full((B, 101, idim), -7.0, device=dev, dtype=torch.float64)
+    i0 = torch.zeros(B, device=dev, dtype=torch.int32)
+    xe, ie = eng.curev_batch(idim, t_d, n_d, c_d, k, u_d, mode=0)
+    xf, jf = eng.curev_batch(idim, t_d, n_d, c_d, k, u_d, out=(x0, i0), mode=1)
+    torch.cuda.synchronize()
+    xe, xf, ie, jf = xe.cpu().numpy(), xf.cpu().numpy(), ie.cpu().numpy(), jf.cpu().numpy()
+    assert np.array_equal(ie, io) and np.array_equal(jf, io) and io[7] == 10 and (np.delete(io, 7) == 0).all()
+    assert (xf[7] == -7.0).all()                                   # rejected curve: nothing written
+    ok = io == 0
+    assert np.array_equal(xe[ok], xo[ok])                          # exact mode: the oracle's bits
+    scale = np.maximum(1.0, np.abs(fit["c"]).max(axis=1))[ok, None, None]
+    assert (np.abs(xf[ok] - xo[ok]) / scale).max() < 1e-12
+    # even point count (TMA point tiles) gives the same values as the odd one on the shared prefix
+    u2 = torch.from_numpy(np.ascontiguousarray(ue[:, :100])).to(dev)
+    x2, j2 = eng.curev_batch(idim, t_d, n_d, c_d, k, u2, mode=1)
+    torch.cuda.synchronize()
+    assert np.array_equal(x2.cpu().numpy()[ok][:, :49], xf[ok][:, :49])
+    eng.close()
