@@ -94,11 +94,14 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef FPB_FIT_FASTDIV
 #define FPB_FIT_FASTDIV 1
 #endif
-//  FPB_FIT_GIVENS_SHARED = 1: cos and sin of a rotation share one reciprocal refinement (givens_shared).
-#ifndef FPB_FIT_GIVENS_SHARED
-#define FPB_FIT_GIVENS_SHARED 1
+//  FPB_FIT_GIVENS: 2 = givens_fast (one straight-line block of fast-path division / sqrt sequences),
+//  1 = givens_shared (cos and sin share one reciprocal refinement), 0 = givens (plain IEEE operators).
+#ifndef FPB_FIT_GIVENS
+#define FPB_FIT_GIVENS 2
 #endif
-#if FPB_FIT_GIVENS_SHARED
+#if FPB_FIT_GIVENS == 2
+#define FPB_GIVENS givens_fast
+#elif FPB_FIT_GIVENS == 1
 #define FPB_GIVENS givens_shared
 #else
 #define FPB_GIVENS givens
