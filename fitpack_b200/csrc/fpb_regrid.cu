@@ -176,7 +176,7 @@ __device__ void plan_axis(const AxisDev &A, double p, double (*sp_s)[kSp], int *
         if (rin >= 0 && lane < bin) {
             const double piv = hin[0];
             if (!fp_is_zero(piv)) {
-                givens(piv, W[0], cs, sn);
+                givens_fast(piv, W[0], cs, sn);   // same bits as givens(), a shorter dependent chain
 #pragma unroll
                 for (int q = 1; q < K2; ++q)
                     if (lane + q < bin) rota(cs, sn, hin[q], W[q]);
