@@ -16,9 +16,15 @@
  * test_fpknot_crash, analytic sine fit), and (ii) golden vectors generated
  * from scipy.interpolate._fitpack (C translation of the same Dierckx
  * algorithms) on inputs where the reference does not deliberately deviate from
- * netlib -- see tests/golden/make_golden.py.  Bit-level agreement with the
- * Fortran build itself is therefore NOT pinned ("parity unpinned" w.r.t. the
- * gfortran binary; pinned w.r.t. the second source).
+ * netlib -- see tests/golden/make_golden.py -- and (iii) directed cases for
+ * every documented reference-vs-netlib deviation with results derived by hand
+ * from the reference source (tests/deviation_cases.py).  Bit-level agreement
+ * with the Fortran build itself is therefore NOT pinned ("parity unpinned"
+ * w.r.t. the gfortran binary; pinned w.r.t. the second source).  The recipe
+ * that closes this on a box with gfortran is oracle/ref_recipe/ (build_ref.sh
+ * builds the reference core + its C binding from /root/reference where they
+ * lie, make_ref_golden.py writes tests/golden/ref_*.npz, tests/test_ref_golden.py
+ * and tests/test_gpu_ref_golden.py consume them).
  */
 #ifndef FITPACK_ORACLE_H
 #define FITPACK_ORACLE_H
