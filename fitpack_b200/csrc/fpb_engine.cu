@@ -389,7 +389,8 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     // the rest of the part-2 list follows after the last pass.
     const long long capacity = grid * (long long)kFitThreads;   // curves one resident wave of the pass kernel holds
     static const bool no_overlap = std::getenv("FPB_FIT_NO_OVERLAP") != nullptr;
-    const bool may_overlap = !no_overlap && !p.periodic && iopt >= 0 && (long long)nbatch >= 4 * capacity;
+    static const bool no_overlap_per = std::getenv("FPB_PER_NO_OVERLAP") != nullptr;
+    const bool may_overlap = !no_overlap && !(p.periodic && no_overlap_per) && iopt >= 0 && (long long)nbatch >= 4 * capacity;
     // tuning knobs (profiles/r02_ab.md): cut-off point in units of capacity/4, CTAs per SM left to the tail
     static const int early_at4 = std::getenv("FPB_FIT_EARLY_AT4") ? std::atoi(std::getenv("FPB_FIT_EARLY_AT4")) : 4;
     static const int early_free = std::getenv("FPB_FIT_EARLY_FREE") ? std::atoi(std::getenv("FPB_FIT_EARLY_FREE")) : 1;
@@ -423,7 +424,9 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
                         !cuda_ok(cudaEventCreateWithFlags(&eng->ev_p2[1], cudaEventDisableTiming), "event"))
                         return FPB_ERR_CUDA;
                 }
-                const int blocks_early = std::max(1, fit_p2_blocks_per_sm(k, idim_class(p.idim)) - early_free);
+                const int blocks_p2 = p.periodic ? max_warps / (kFitThreads / 32) / eng->nsm
+                                                 : fit_p2_blocks_per_sm(k, idim_class(p.idim));
+                const int blocks_early = std::max(1, blocks_p2 - early_free);
                 const long long grid_early = std::min<long long>((long long)eng->nsm * blocks_early,
                                                                  ((long long)n2_now + kFitThreads - 1) / kFitThreads);
                 const size_t warps2 = (size_t)grid_early * (kFitThreads / 32);

@@ -255,6 +255,17 @@ module fitpack_b200
          type(c_ptr), intent(in), value :: eng
       end function fpb_engine_synchronize
 
+      ! arithmetic of fp_curev_batch_dev_c: 0 exact (reference arithmetic), 1 fast (local polynomials + Horner)
+      integer(c_int32_t) function fpb_engine_set_curev_mode(eng,mode) bind(C,name="fpb_engine_set_curev_mode")
+         import :: c_ptr, c_int32_t
+         type(c_ptr), value :: eng
+         integer(c_int32_t), value :: mode
+      end function fpb_engine_set_curev_mode
+      ! kernels launched so far by the default engines of a device (the ones the host-pointer calls run on)
+      integer(c_int64_t) function fpb_default_engine_launch_count(device) bind(C,name="fpb_default_engine_launch_count")
+         import :: c_int32_t, c_int64_t
+         integer(c_int32_t), value :: device
+      end function fpb_default_engine_launch_count
       integer(c_int32_t) function fpb_device_count() bind(C,name="fpb_device_count")
          import
       end function fpb_device_count

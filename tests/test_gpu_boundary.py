@@ -149,3 +149,29 @@ def test_in_process_sharding_really_uses_several_gpus(F):
     assert all(a > b for a, b in zip(after, before)), (before, after)
     for key in ("n", "ier", "fp", "t", "c"):
         assert _same(r1[key], rn[key]), key
+
+
+def test_curfit_batch_rejected_rows_keep_t_c_with_the_dense_copy_out(F):
+    """fp_curfit_batch_c ships t, c back DENSE (pack kernel + host scatter): rows rejected with ier = 10
+    (decreasing abscissae) must keep the caller's n, t, c, fp like the reference's curfit; the rows around them
+    are fitted and land in the right rows (compared with the oracle)."""
+    rng = np.random.default_rng(9)
+    B, m, k, nest = 700, 48, 3, 52
+    x, y = synth_curves(rng, B, m)
+    bad = [0, 13, 255, 256, 699]
+    for b in bad:
+        x[b, 20], x[b, 21] = x[b, 21], x[b, 20]
+    s = m * 0.01
+    n0 = np.full(B, -5, np.int32)
+    t0 = np.full((B, nest), 3.25)
+    r = F.curfit_batch(0, x, y, None, k, s, nest, n=n0.copy(), t=t0.copy())
+    o = O.curfit_batch(0, x, y, None, k, s, nest)
+    assert _same(r["ier"], o["ier"]) and all(o["ier"][b] == 10 for b in bad)
+    for b in bad:
+        assert r["n"][b] == -5 and _same(r["t"][b], t0[b]) and not r["c"][b].any() and r["fp"][b] == 0.0
+    good = np.setdiff1d(np.arange(B), bad)
+    assert _same(r["n"][good], o["n"][good]) and _same(r["fp"][good], o["fp"][good])
+    for b in good[::9]:
+        n = o["n"][b]
+        assert _same(r["t"][b, :n], o["t"][b, :n]) and _same(r["c"][b, :n - k - 1], o["c"][b, :n - k - 1])
+        assert _same(r["t"][b, n:], t0[b, n:])          # beyond n the caller's row is untouched
