@@ -17,23 +17,32 @@
 //   fpback 1808-1838, fpdisc 5453-5495, fpknot 8199-8275,
 //   root_finding_iterate 11641-11691, fprati 11996-12025, fpchec 2507-2570.
 //
-// B200 mapping (DESIGN.md "fit kernel"):
+// B200 mapping:
 //  * inputs are read point-major (SoA): lane b of a warp reads x[i*ld+b], so
 //    every pass over the m points is a stream of fully coalesced 256 B loads;
 //  * the band matrix R is never materialised per point: a point in knot
 //    interval l only touches R rows l-k..l, and x is sorted, so the k+1 active
-//    rows (+ their right-hand sides and the 2k knots fpbspl needs) live in
-//    REGISTERS as a sliding window; a row is written out exactly once per pass,
-//    when the window moves past it;
+//    rows (+ their right-hand sides) live in a per-thread circular window in SHARED
+//    memory ([element][thread], conflict free; registers hold the 2k knots fpbspl needs
+//    and the refined reciprocals of the knot spans); a row is written out exactly once
+//    per pass, when the window moves past it;
+//  * the basis values q(m,k+1) the reference stores in wrk are NOT stored: the residual
+//    passes recompute them, with fpbspl's divisions reduced to the quotient step of the
+//    hardware's own division sequence (bspl_tab, fpb_common.cuh) -- same bits, and two
+//    thirds of the round-1 pipeline's DRAM traffic gone;
+//  * fpgivs is one straight-line block of fast-path division / square-root sequences
+//    (givens_fast) whenever its operands are in range;
 //  * all per-knot state (t, c, z, R, fpint, nrdata, G, B) lives in a per-warp
 //    workspace interleaved by lane ([element][lane]), so loops whose index is
 //    uniform across the warp (back-substitution, p-iteration, fpknot, fpdisc)
 //    are coalesced too; trip counts are made warp-uniform with a max-reduce and
 //    per-lane predicates;
+//  * the pass that accepts a curve's knot set hands its triangular system (R, z) to part 2
+//    through a pool, so part 2 does not regenerate it;
 //  * all decisions (knot insertion, the rational p-search, every exit) are taken
-//    on the device; the host only reads one counter every other pass to know
-//    when the "needs another pass" list is empty.  Per-curve ier is an output, a
-//    bad curve never aborts the batch.
+//    on the device; the host only reads the list lengths (every other pass, every pass
+//    near the tail) to size the next launch and to start part 2 of the early finishers
+//    beside the tail passes.  Per-curve ier is an output, a bad curve never aborts the batch.
 //
 // Parametric curves (parcur/fppara, core:15201-15285 / 8822-9177) run through the SAME pipeline:
 // the kernels are templated on IDIM, the number of coordinate curves that share one knot vector
