@@ -702,6 +702,11 @@ def main():
             rr.update({"gpts_per_s": parc[key_]["gpts_per_s"], "ms_per_step": parc[key_]["ms"],
                        "workload": "curev of %d fitted idim=%d curves x %d points" % (Bp, dp, mp)})
             roof["secondary"].append(rr)
+        roof["secondary"].append({"bound": "fp64-chain", "kernel": parc["roofline"]["kernel"], "unit": "GB/s",
+                                  "achieved": parc["roofline"]["achieved"], "peak": hbm_peak,
+                                  "frac": parc["roofline"]["frac"], "traffic": None, "peak_source": peak_src,
+                                  "value_fits_per_s": parc["value"], "ms_per_step": p_ms,
+                                  "workload": parc["config"]["workload"]})
         roof["secondary"].append({"bound": "hbm", "kernel": "curev FAST, dense evaluation", "unit": "GB/s",
                                   "achieved": dense["fast"]["value"] / world, "peak": hbm_peak,
                                   "frac": dense["fast"]["frac_of_hbm_peak"], "traffic": None,
@@ -773,6 +778,11 @@ def main():
                          "Givens chains), HBM fraction small by construction", "achieved": qbytes / (q_ms * 1e-3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": qbytes / (q_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_fit": qbytes / Bq}}
+        roof["secondary"].append({"bound": "fp64-chain", "kernel": perc["roofline"]["kernel"], "unit": "GB/s",
+                                  "achieved": perc["roofline"]["achieved"], "peak": hbm_peak,
+                                  "frac": perc["roofline"]["frac"], "traffic": None, "peak_source": peak_src,
+                                  "value_fits_per_s": perc["value"], "ms_per_step": q_ms,
+                                  "workload": perc["config"]["workload"]})
         if rank == 0 and world == 1 and not args.no_cpu:
             import oracle_lib as O
             nthr_ = host_threads()
@@ -827,6 +837,15 @@ def main():
                                 out=gout, engine=eng)
         torch.cuda.synchronize()
         ev_ms = eng.last_kernel_ms()
+        # FAST mode of bispev (FMA sums)
+        gfast = torch.empty((gm, gm), device=dev, dtype=torch.float64)
+        for _ in range(3):
+            fitpack_b200.bispev(rg["tx"], rg["nx"], rg["ty"], rg["ny"], rg["c"], gk, gk, gx, gx,
+                                out=gfast, engine=eng, mode=1)
+        torch.cuda.synchronize()
+        evf_ms = eng.last_kernel_ms()
+        bispev_fast_err = float(((gfast - gout).abs().max() / max(1.0, float(np.abs(rg["c"]).max()))).item())
+        del gfast
         resid = float(((gz - gout) ** 2).sum().item())
         assert rg["ier"] == 0 and abs(resid - rg["fp"]) <= 1e-9 * rg["fp"], "regrid fp != residual of bispev"
         # algorithmic bytes of one fpgrre solve: z is read twice (x reduction, residual pass)
@@ -850,7 +869,20 @@ def main():
                                     "achieved": gm * gm * 8 / (ev_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                     "unit": "GB/s", "frac": gm * gm * 8 / (ev_ms * 1e-3) / 1e9 / hbm_peak,
                                     "traffic": None, "peak_source": peak_src,
-                                    "algorithmic_bytes_per_point": 8}}}
+                                    "algorithmic_bytes_per_point": 8}},
+            "bispev_fast": {"ms": evf_ms, "value": gm * gm * 8 / (evf_ms * 1e-3) / 1e9, "unit": "GB/s",
+                            "max_err_vs_exact_rel_to_max_c": bispev_fast_err,
+                            "frac_of_hbm_peak": gm * gm * 8 / (evf_ms * 1e-3) / 1e9 / hbm_peak}}
+        for key_, nm_ in (("bispev", "grid_bispev_kernel (exact)"), ("bispev_fast", "grid_bispev_kernel (FMA sums)")):
+            roof["secondary"].append({"bound": "hbm", "kernel": nm_, "unit": "GB/s", "peak": hbm_peak,
+                                      "achieved": grid[key_]["value"], "frac": grid[key_]["value"] / hbm_peak,
+                                      "traffic": None, "peak_source": peak_src,
+                                      "workload": "bispev on a %d x %d grid, kx=ky=%d" % (gm, gm, gk)})
+        roof["secondary"].append({"bound": "latency", "kernel": "regrid: fpgrre solve (plan + 2 x apply + resid)",
+                                  "ms_per_fit": g_ms, "fpgrre_solves_per_fit": ncalls,
+                                  "achieved": grid["roofline"]["achieved"], "unit": "GB/s", "peak": hbm_peak,
+                                  "frac": grid["roofline"]["frac"], "traffic": None, "peak_source": peak_src,
+                                  "workload": grid["config"]["workload"]})
         if rank == 0 and world == 1 and not args.no_cpu:
             import oracle_lib as O
             cm = 1024   # bounded CPU sample: the same surface on a 1024 x 1024 grid

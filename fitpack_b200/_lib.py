@@ -54,6 +54,7 @@ SYMBOLS = {
     "fpb_default_engine_launch_count": (_I64, [_I32]),
     "fpb_engine_set_shared_mode": (_I32, [_VP, _I32]),
     "fpb_engine_set_curev_mode": (_I32, [_VP, _I32]),
+    "fpb_engine_set_bispev_mode": (_I32, [_VP, _I32]),
     "fpb_engine_last_kernel_ms": (_F64, [_VP]),
     "fpb_probe_fp64_gops": (_F64, [_VP, _I32]),
     "fpb_device_count": (_I32, []),

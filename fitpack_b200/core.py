@@ -177,13 +177,15 @@ def regrid(iopt, x, y, z, xb, xe, yb, ye, kx, ky, s, nxest, nyest, nx=0, ny=0, t
                 iwrk=iwrk)
 
 
-def bispev(tx, nx, ty, ny, c, kx, ky, x, y, out=None, engine=None):
+def bispev(tx, nx, ty, ny, c, kx, ky, x, y, out=None, engine=None, mode=0):
     """bispev (reference core:424-458) through fp_bispev_c; `out`: optional CUDA torch tensor
-    [mx, my] to receive the values in HBM (fp_bispev_dev_c).  Returns (z, ier)."""
+    [mx, my] to receive the values in HBM (fp_bispev_dev_c; mode 0 exact / 1 fast = FMA sums).
+    Returns (z, ier)."""
     tx, ty, c, x, y = _f64(tx), _f64(ty), _f64(c), _f64(x), _f64(y)
     mx, my = x.size, y.size
     if out is not None:
         ier_ = C.c_int32(0)
+        check(lib().fpb_engine_set_bispev_mode(engine.handle, int(mode)), "set_bispev_mode")
         rc = lib().fp_bispev_dev_c(engine.handle, _p(tx), int(nx), _p(ty), int(ny), _p(c), int(kx),
                                    int(ky), _p(x), mx, _p(y), my, C.c_void_p(out.data_ptr()),
                                    C.addressof(ier_))

@@ -254,6 +254,13 @@ int32_t fpb_engine_set_shared_mode(fpb_engine *eng, int32_t mode)
     return FPB_STATUS_OK;
 }
 
+int32_t fpb_engine_set_bispev_mode(fpb_engine *eng, int32_t mode)
+{
+    if (!eng || (mode != 0 && mode != 1)) return FPB_ERR_ARG;
+    eng->bispev_fast = mode;
+    return FPB_STATUS_OK;
+}
+
 int32_t fpb_engine_set_curev_mode(fpb_engine *eng, int32_t mode)
 {
     if (!eng || (mode != 0 && mode != 1)) return FPB_ERR_ARG;

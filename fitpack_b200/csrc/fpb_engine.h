@@ -58,6 +58,7 @@ struct fpb_engine {
     size_t grid_pinned_bytes = 0;
     int64_t grid_fpgrre_calls = 0;
     int shared_fast = 0;              // shared-abscissa LSQ: 0 exact rotations, 1 FMA (fast)
+    int bispev_fast = 0;              // bispev: 0 exact (reference order, no FMA), 1 fast (FMA sums)
     int curev_fast = 0;               // curev: 0 exact (reference arithmetic), 1 fast (local polynomials + Horner)
     fpb::DevBuf curev_n;              // curev fast path: knot counts with rejected curves zeroed
     fpb::DevBuf calc[6];              // spline calculus (fpb_calculus.cu)

@@ -533,7 +533,10 @@ constexpr int kEvRows = 32, kEvCols = 128;
 // a thread only changes when the row's x interval changes, so it is kept in registers across rows
 // (the kernel is otherwise bound by the LSU: 16 coefficient loads per 8-byte output).
 // KX1/KY1 = compile-time k+1 (0: run-time degrees, up to 6 x 6 with predicates).
-template <int KX1, int KY1>
+// FMA = false: the reference's operation order without contraction (bit-identical values); FMA = true (FAST,
+// fpb_engine_set_bispev_mode): the same sums as fused multiply-adds -- half the FP64 instructions, values within
+// 1e-12 * max(1, max|c|) of exact.
+template <int KX1, int KY1, bool FMA>
 __global__ void __launch_bounds__(kEvCols) grid_bispev_kernel(
     const double *__restrict__ c, int nk1y, const double *__restrict__ wx, const int *__restrict__ lx,
     int k1x_rt, int mx, const double *__restrict__ wyt, const int *__restrict__ ly, int k1y_rt, int my,
@@ -577,8 +580,8 @@ __global__ void __launch_bounds__(kEvCols) grid_bispev_kernel(
                 double dot = 0.0;
 #pragma unroll
                 for (int cy = 0; cy < NY; ++cy)
-                    if (cy < k1y) dot = add(dot, mul(cs[cx][cy], wy[cy]));
-                sp = add(sp, mul(wx_s[rr][cx], dot));
+                    if (cy < k1y) dot = FMA ? __fma_rn(cs[cx][cy], wy[cy], dot) : add(dot, mul(cs[cx][cy], wy[cy]));
+                sp = FMA ? __fma_rn(wx_s[rr][cx], dot, sp) : add(sp, mul(wx_s[rr][cx], dot));
             }
         }
         z[(size_t)(r0 + rr) * my + i2] = sp;
@@ -1128,7 +1131,13 @@ int32_t bispev_run(fpb_engine *eng, const double *tx, int nx, const double *ty, 
         const dim3 gridd((my + kEvCols - 1) / kEvCols, (mx + kEvRows - 1) / kEvRows);
         const double *dwy = dw + (size_t)mx * kSp;
         const int *dly = dl + mx;
-#define FPB_BISPEV(A, B) grid_bispev_kernel<A, B><<<gridd, kEvCols, 0, st>>>(dc, nk1y, dw, dl, kx + 1, mx, dwy, dly, ky + 1, my, z_dev)
+#define FPB_BISPEV(A, B)                                                                                              \
+    do {                                                                                                              \
+        if (eng->bispev_fast)                                                                                         \
+            grid_bispev_kernel<A, B, true><<<gridd, kEvCols, 0, st>>>(dc, nk1y, dw, dl, kx + 1, mx, dwy, dly, ky + 1, my, z_dev);  \
+        else                                                                                                          \
+            grid_bispev_kernel<A, B, false><<<gridd, kEvCols, 0, st>>>(dc, nk1y, dw, dl, kx + 1, mx, dwy, dly, ky + 1, my, z_dev); \
+    } while (0)
         if (kx == ky && kx == 1) FPB_BISPEV(2, 2);
         else if (kx == ky && kx == 2) FPB_BISPEV(3, 3);
         else if (kx == ky && kx == 3) FPB_BISPEV(4, 4);

@@ -261,6 +261,11 @@ module fitpack_b200
          type(c_ptr), value :: eng
          integer(c_int32_t), value :: mode
       end function fpb_engine_set_curev_mode
+      integer(c_int32_t) function fpb_engine_set_bispev_mode(eng,mode) bind(C,name="fpb_engine_set_bispev_mode")
+         import :: c_ptr, c_int32_t
+         type(c_ptr), value :: eng
+         integer(c_int32_t), value :: mode
+      end function fpb_engine_set_bispev_mode
       ! kernels launched so far by the default engines of a device (the ones the host-pointer calls run on)
       integer(c_int64_t) function fpb_default_engine_launch_count(device) bind(C,name="fpb_default_engine_launch_count")
          import :: c_int32_t, c_int64_t

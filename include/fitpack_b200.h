@@ -157,6 +157,12 @@ int32_t fpb_engine_set_shared_mode(fpb_engine *eng, int32_t mode);
    operation order, bit-identical values;  FPB_CUREV_FAST: one local polynomial per knot interval +
    Horner/FMA through the fast splev kernel, one pass per coordinate (identical knot intervals, values within
    1e-12 * max(1, max|c|) of exact; ier as in exact mode). */
+/* arithmetic of fp_bispev_dev_c: FPB_BISPEV_EXACT (default): the reference's sums in the reference's order,
+   no FMA, bit-identical values;  FPB_BISPEV_FAST: the same sums as fused multiply-adds (values within
+   1e-12 * max(1, max|c|) of exact; same interval indices, same ier). */
+#define FPB_BISPEV_EXACT 0
+#define FPB_BISPEV_FAST  1
+int32_t fpb_engine_set_bispev_mode(fpb_engine *eng, int32_t mode);
 #define FPB_CUREV_EXACT 0
 #define FPB_CUREV_FAST  1
 int32_t fpb_engine_set_curev_mode(fpb_engine *eng, int32_t mode);

@@ -47,3 +47,32 @@ def test_curev_fast_matches_exact_within_tolerance(idim, k):
     torch.cuda.synchronize()
     assert np.array_equal(x2.cpu().numpy()[ok][:, :49], xf[ok][:, :49])
     eng.close()
+
+
+def test_bispev_fast_matches_exact_within_tolerance():
+    """bispev FAST (the reference's sums as fused multiply-adds): values within 1e-12 * max(1, max|c|) of the
+    exact mode, which itself is the oracle's bits."""
+    import torch
+    import fitpack_b200
+    from fitpack_b200.batch import Engine
+    dev = torch.device("cuda", 0)
+    eng = Engine(dev)
+    rng = np.random.default_rng(4)
+    for kx, ky, mx, my in ((3, 3, 70, 65), (1, 2, 40, 33), (5, 4, 64, 50)):
+        gx, gy = np.linspace(-1.0, 1.0, mx), np.linspace(0.0, 2.0, my)
+        GX, GY = np.meshgrid(gx, gy, indexing="ij")
+        z = np.cos(2 * GX) * np.sin(GY) + 0.05 * rng.standard_normal(GX.shape)
+        nxe, nye = mx + kx + 1, my + ky + 1
+        o = O.regrid(0, gx, gy, z, -1, 1, 0, 2, kx, ky, mx * my * 0.0025, nxe, nye)
+        ex = np.sort(rng.uniform(-1, 1, 90))
+        ey = np.sort(rng.uniform(0, 2, 77))
+        zo, io = O.bispev(o["tx"], o["nx"], o["ty"], o["ny"], o["c"], kx, ky, ex, ey)
+        out0 = torch.empty((90, 77), device=dev, dtype=torch.float64)
+        out1 = torch.empty((90, 77), device=dev, dtype=torch.float64)
+        fitpack_b200.bispev(o["tx"], o["nx"], o["ty"], o["ny"], o["c"], kx, ky, ex, ey, out=out0, engine=eng, mode=0)
+        fitpack_b200.bispev(o["tx"], o["nx"], o["ty"], o["ny"], o["c"], kx, ky, ex, ey, out=out1, engine=eng, mode=1)
+        torch.cuda.synchronize()
+        assert io == 0 and np.array_equal(out0.cpu().numpy(), zo)
+        scale = max(1.0, np.abs(o["c"]).max())
+        assert np.abs(out1.cpu().numpy() - zo).max() / scale < 1e-12
+    eng.close()
