@@ -57,6 +57,7 @@ SYMBOLS = {
     "fpb_engine_set_bispev_mode": (_I32, [_VP, _I32]),
     "fpb_engine_last_kernel_ms": (_F64, [_VP]),
     "fpb_probe_fp64_gops": (_F64, [_VP, _I32]),
+    "fpb_selftest_fastmath": (_I32, [_VP, _I64, _I64, _VP]),
     "fpb_device_count": (_I32, []),
     "fpb_last_error": (C.c_char_p, []),
     "fpb_version": (C.c_char_p, []),

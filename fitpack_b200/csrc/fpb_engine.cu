@@ -650,6 +650,26 @@ int32_t fpb_transpose_dev(fpb_engine *eng, const FP_REAL *src, int64_t ld_src, F
     return FPB_STATUS_OK;
 }
 
+int32_t fpb_selftest_fastmath(fpb_engine *eng, int64_t samples, int64_t seed, int64_t *mismatches)
+{
+    if (!eng || !mismatches || samples <= 0) return FPB_ERR_ARG;
+    DeviceGuard g(eng->device);
+    if (!g.ok || !eng->counter.reserve(256)) return FPB_ERR_CUDA;
+    unsigned long long *d = eng->counter.as<unsigned long long>();
+    const int blocks = eng->nsm * 8;
+    const long long per_thread = (samples + (long long)blocks * 256 - 1) / ((long long)blocks * 256);
+    unsigned long long h[3] = {0, 0, 0};
+    if (!cuda_ok(cudaMemsetAsync(d, 0, 24, eng->stream), "memset") ||
+        !cuda_ok(launch_fastmath_selftest((unsigned long long)seed, blocks, (int)std::min<long long>(per_thread, 1 << 24), d,
+                                          eng->stream), "fastmath self-test") ||
+        !cuda_ok(cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, eng->stream), "D2H") ||
+        !cuda_ok(cudaStreamSynchronize(eng->stream), "sync"))
+        return FPB_ERR_CUDA;
+    eng->launches++;
+    for (int i = 0; i < 3; ++i) mismatches[i] = (int64_t)h[i];
+    return FPB_STATUS_OK;
+}
+
 double fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused)
 {
     if (!eng) return -1.0;

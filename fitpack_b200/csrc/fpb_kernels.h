@@ -179,5 +179,7 @@ cudaError_t launch_pack_tc(int nb, int nest, int k, const int *n, const int *ier
                            unsigned long long *cursor, long long *off, double *tp, double *cp, int nsm,
                            cudaStream_t stream);
 cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused, cudaStream_t stream);
+cudaError_t launch_fastmath_selftest(unsigned long long seed, int blocks, int iters, unsigned long long *mismatch,
+                                     cudaStream_t stream);
 
 }  // namespace fpb

@@ -3,6 +3,7 @@
 // point-major SoA layout ([point][curve]) the fit kernels stream with coalesced
 // loads.  HBM-bound, 16 B/element of traffic; 32x32 tiles staged in shared memory
 // (padded to 33 columns: conflict-free for 8-byte elements in both phases).
+#include "fpb_common.cuh"
 #include "fpb_kernels.h"
 
 namespace fpb {
@@ -183,6 +184,89 @@ cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused,
     }
     if (fused) fp64_probe_kernel<true><<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999, 1e-7);
     else fp64_probe_kernel<false><<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999, 1e-7);
+    return cudaGetLastError();
+}
+}  // namespace fpb
+
+// ---- self-test of the hand-written division / square-root sequences (fpb_common.cuh) against the compiler's
+// IEEE operators on random operands: counts bitwise mismatches of (0) div_refined(a, d, rcp_refined(d)) vs a / d
+// inside the guarded ranges, (1) sqrt_fastpath(x) vs sqrt(x) for x in [1, 2], (2) givens_fast vs givens (cos, sin
+// and the new diagonal) on operands spread over 600 binades incl. zeros, negatives and out-of-range values that
+// must take the fallback.  tests/test_gpu_fastmath.py requires zero mismatches.
+namespace fpb {
+namespace {
+__device__ __forceinline__ unsigned long long sm64(unsigned long long &s)
+{
+    unsigned long long z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+// random significand and sign bit, exponent uniform in [emin, emax]
+__device__ __forceinline__ double rnd_double(unsigned long long &s, int emin, int emax, bool allow_neg)
+{
+    const unsigned long long r = sm64(s), r2 = sm64(s);
+    const unsigned long long e = (unsigned long long)(1023 + emin + (int)(r2 % (unsigned long long)(emax - emin + 1)));
+    unsigned long long b = (r & 0xFFFFFFFFFFFFFULL) | (e << 52);
+    if (allow_neg && (r2 >> 40 & 1)) b |= 0x8000000000000000ULL;
+    return __longlong_as_double((long long)b);
+}
+__global__ void __launch_bounds__(256) fastmath_selftest_kernel(unsigned long long seed, int iters,
+                                                                unsigned long long *mismatch)
+{
+    unsigned long long s = seed + 0x1234567ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    unsigned long long bad_div = 0, bad_sqrt = 0, bad_giv = 0;
+    for (int it = 0; it < iters; ++it) {
+        // (0) division inside the guarded ranges (plus numerator +0)
+        {
+            const double d = rnd_double(s, -400, 400, false);
+            double a = rnd_double(s, -500, 500, false);
+            if ((it & 63) == 0) a = 0.0;
+            if ((it & 7) == 1) {   // quotients close to rounding boundaries: a = q*d nudged by an ulp
+                const double q = rnd_double(s, -3, 3, false);
+                a = __longlong_as_double(__double_as_longlong(__dmul_rn(q, d)) + ((it & 8) ? 1 : -1));
+            }
+            if (rcp_den_ok(d) && rcp_num_ok(a)) {
+                const double q1 = div_refined(a, d, rcp_refined(d));
+                const double q2 = a / d;
+                if (__double_as_longlong(q1) != __double_as_longlong(q2)) ++bad_div;
+            }
+        }
+        // (1) square root on [1, 2]
+        {
+            const double r = rnd_double(s, -60, 0, false);
+            const double x = __dadd_rn(1.0, __dmul_rn(r, r));
+            if (x >= 1.0 && x <= 2.0 &&
+                __double_as_longlong(sqrt_fastpath(x)) != __double_as_longlong(sqrt(x)))
+                ++bad_sqrt;
+        }
+        // (2) fpgivs: wide exponent spread, zeros and out-of-range operands (fallback path) included
+        {
+            double piv = rnd_double(s, -300, 300, true);
+            double ww = rnd_double(s, -300, 300, false);
+            const int sel = it & 31;
+            if (sel == 0) ww = 0.0;
+            else if (sel == 1) piv = rnd_double(s, -1000, -600, true);
+            else if (sel == 2) ww = rnd_double(s, 450, 900, false);
+            else if (sel == 3) ww = __dmul_rn(fabs(piv), 1.0 + 1e-15 * (double)(it & 255));
+            double w1 = ww, w2 = ww, c1, s1, c2, s2;
+            givens_fast(piv, w1, c1, s1);
+            givens(piv, w2, c2, s2);
+            if (__double_as_longlong(w1) != __double_as_longlong(w2) || __double_as_longlong(c1) != __double_as_longlong(c2) ||
+                __double_as_longlong(s1) != __double_as_longlong(s2))
+                ++bad_giv;
+        }
+    }
+    if (bad_div) atomicAdd(&mismatch[0], bad_div);
+    if (bad_sqrt) atomicAdd(&mismatch[1], bad_sqrt);
+    if (bad_giv) atomicAdd(&mismatch[2], bad_giv);
+}
+}  // namespace
+
+cudaError_t launch_fastmath_selftest(unsigned long long seed, int blocks, int iters, unsigned long long *mismatch,
+                                     cudaStream_t stream)
+{
+    fastmath_selftest_kernel<<<blocks, 256, 0, stream>>>(seed, iters, mismatch);
     return cudaGetLastError();
 }
 }  // namespace fpb

@@ -179,6 +179,10 @@ double  fpb_engine_last_kernel_ms(fpb_engine *eng);
    DMUL+DADD pairs (fused=0; the only forms the parity-exact kernels may use) or DFMA
    (fused=1).  Roofline denominator of the fit kernel. */
 double  fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused);
+/* Self-test of the hand-written fast-path sequences the fit kernels use in place of the IEEE operators
+   (DESIGN.md 4.1): `samples` random operand sets per check, bitwise compared on the device with `/`, sqrt() and
+   the plain fpgivs.  mismatches[0..2] = division, square root on [1,2], fpgivs (must all be 0). */
+int32_t fpb_selftest_fastmath(fpb_engine *eng, int64_t samples, int64_t seed, int64_t *mismatches);
 int32_t fpb_device_count(void);
 const char *fpb_last_error(void);
 const char *fpb_version(void);
