@@ -76,3 +76,39 @@ def test_bispev_fast_matches_exact_within_tolerance():
         scale = max(1.0, np.abs(o["c"]).max())
         assert np.abs(out1.cpu().numpy() - zo).max() / scale < 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("k", [2, 3, 5])
+def test_exact_evaluators_with_and_without_the_span_table(k):
+    """Exact splev / curev use a per-interval span table for splines with up to 96 knot intervals and plain
+    divisions beyond: both paths, and a batch that mixes them, must give the oracle's bits."""
+    import torch
+    from fitpack_b200.batch import Engine
+    dev = torch.device("cuda", 0)
+    eng = Engine(dev)
+    rng = np.random.default_rng(50 + k)
+    B, ld, m = 64, 420, 333
+    t = np.zeros((B, ld))
+    c = rng.standard_normal((B, ld))
+    n = np.zeros(B, np.int32)
+    for b in range(B):
+        nint = int(rng.choice([3, 40, 95, 96, 97, 150, 400 - 2 * k]))     # knot intervals: around the table's cap
+        nb = nint + 2 * k + 1
+        inner = np.sort(rng.uniform(0.0, 1.0, nint - 1))
+        t[b, :k + 1] = 0.0
+        t[b, k + 1:k + nint] = inner
+        t[b, k + nint:nb] = 1.0
+        n[b] = nb
+    x = np.sort(rng.uniform(-0.05, 1.05, (B, m)), axis=1)
+    yo, io = O.splev_batch(t, n, c, k, x)
+    r = eng.splev_batch(torch.from_numpy(t).to(dev), torch.from_numpy(n).to(dev), torch.from_numpy(c).to(dev), k,
+                        torch.from_numpy(x).to(dev), e=0, mode=0)
+    torch.cuda.synchronize()
+    assert np.array_equal(r["y"].cpu().numpy(), yo) and not r["ier"].cpu().numpy().any()
+    # curev on the same splines (idim = 1: c(1:n-k-1) of each row), parameters clamped to [0, 1] by curev itself
+    xo, jo = O.curev_batch(1, t, n, c, k, x)
+    xe, je = eng.curev_batch(1, torch.from_numpy(t).to(dev), torch.from_numpy(n).to(dev),
+                             torch.from_numpy(c).to(dev), k, torch.from_numpy(x).to(dev), mode=0)
+    torch.cuda.synchronize()
+    assert np.array_equal(xe.cpu().numpy(), xo) and np.array_equal(je.cpu().numpy(), jo)
+    eng.close()
