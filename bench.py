@@ -378,6 +378,17 @@ def main():
         "issue_slots_per_fit": fp64["issue_slots_per_fit"],
         "frac_of_fp64_issue_roofline": fp64["frac_of_fp64_issue_roofline"],
         "mean_lsq_passes": fp64["mean_lsq_passes"], "mean_p_iters": fp64["mean_p_iters"], "mean_n": mean_n}
+    # dependent-issue latency bound: every warp of the fit kernels is one chain of dependent FP64 instructions
+    # (ILP ~ 1), so a scheduler with W resident warps issues at most W / latency instructions per cycle
+    lat_ma = eng.probe_fp64_gops(4)
+    lat_fma = eng.probe_fp64_gops(5)
+    lat_mufu = eng.probe_fp64_gops(6)
+    roof["fp64_bound"]["dependent_latency_cycles"] = {"dmul_dadd": lat_ma, "dfma": lat_fma, "mufu_rcp64h_plus_dfma_pair_avg": lat_mufu}
+    if lat_fma and lat_fma > 0:
+        roof["fp64_bound"]["issue_rate_bound_per_scheduler"] = {
+            "warps_per_scheduler": 5, "ipc_bound": min(1.0, 5.0 / lat_fma),
+            "note": "20 warps per SM (96 registers) = 5 per scheduler; ncu: issue slots busy 56 % in the pass "
+                    "kernel, 49 % in part 2 (profiles/r02_kernels.md)"}
     roof["secondary"] = []   # the other kernels of the metric, filled in below (driver keeps `roofline`)
 
     # ---------------------------------------------------------------- parity sample on the SAME batch

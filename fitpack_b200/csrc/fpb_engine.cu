@@ -675,6 +675,16 @@ double fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused)
     if (!eng) return -1.0;
     DeviceGuard g(eng->device);
     if (!g.ok || !eng->counter.reserve(256)) return -1.0;
+    if (fused >= 4 && fused <= 6) {   // dependent-issue latency in cycles per instruction (see fpb_util.cu)
+        double *d = eng->counter.as<double>() + 8;
+        double h = -1.0;
+        if (!cuda_ok(launch_fp64_probe(d, 1, 0, fused, eng->stream), "latency probe") ||
+            !cuda_ok(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, eng->stream), "D2H") ||
+            !cuda_ok(cudaStreamSynchronize(eng->stream), "sync"))
+            return -1.0;
+        eng->launches++;
+        return h;
+    }
     const int blocks = eng->nsm * 8, iters = (fused >= 2) ? (1 << 11) : (1 << 14);
     double best = -1.0;
     for (int rep = 0; rep < 4; ++rep) {

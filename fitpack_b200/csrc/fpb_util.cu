@@ -172,8 +172,42 @@ __global__ void __launch_bounds__(256) fp64_divsqrt_probe_kernel(double *out, in
     if (s == 123.456) out[0] = s;
 }
 
+// modes 4..6: DEPENDENT-issue latency in SM cycles of a chain of DMUL/DADD pairs (4), of DFMA (5) and of
+// MUFU.RCP64H + DFMA (6): one warp per SM, clock64() around `iters` dependent instructions; out[0] = cycles
+// per instruction.  The fit kernels are chains of dependent FP64 instructions (ILP ~ 1 per warp), so their
+// issue rate is bounded by (warps per scheduler) / (this latency).
+template <int MODE>
+__global__ void fp64_latency_probe_kernel(double *out, int iters, double a, double b)
+{
+    double v = 1.0 + 1e-9 * threadIdx.x;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        if (MODE == 4) {
+            v = __dmul_rn(v, a);
+            v = __dadd_rn(v, b);
+        } else if (MODE == 5) {
+            v = __fma_rn(v, a, b);
+            v = __fma_rn(v, a, b);
+        } else {
+            double r;
+            asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+            v = __fma_rn(r, a, b);
+        }
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (double)(t1 - t0) / (2.0 * iters);
+    if (v == 123.456) out[1] = v;
+}
+
 cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused, cudaStream_t stream)
 {
+    if (fused >= 4 && fused <= 6) {
+        const int n = 1 << 14;
+        if (fused == 4) fp64_latency_probe_kernel<4><<<1, 32, 0, stream>>>(scratch, n, 0.999999, 1e-7);
+        else if (fused == 5) fp64_latency_probe_kernel<5><<<1, 32, 0, stream>>>(scratch, n, 0.999999, 1e-7);
+        else fp64_latency_probe_kernel<6><<<1, 32, 0, stream>>>(scratch, n, 0.999999, 1e-7);
+        return cudaGetLastError();
+    }
     if (fused == 2) {
         fp64_divsqrt_probe_kernel<2><<<blocks, 256, 0, stream>>>(scratch, iters, 1.75);
         return cudaGetLastError();

@@ -177,7 +177,10 @@ int64_t fpb_default_engine_launch_count(int32_t device);
 double  fpb_engine_last_kernel_ms(fpb_engine *eng);
 /* FP64 pipe probe: achieved 1e9 FP64 instructions/s of a register-resident kernel issuing
    DMUL+DADD pairs (fused=0; the only forms the parity-exact kernels may use) or DFMA
-   (fused=1).  Roofline denominator of the fit kernel. */
+   (fused=1); 2 / 3: IEEE divisions / square roots per second.  Roofline denominators of the fit kernel.
+   fused = 4 / 5 / 6: DEPENDENT-issue latency in SM cycles per instruction of a DMUL+DADD chain, a DFMA chain,
+   a MUFU.RCP64H+DFMA chain (one warp): the fit kernels are chains of dependent FP64 instructions, so their
+   issue rate is bounded by (warps per scheduler) / latency. */
 double  fpb_probe_fp64_gops(fpb_engine *eng, int32_t fused);
 /* Self-test of the hand-written fast-path sequences the fit kernels use in place of the IEEE operators
    (DESIGN.md 4.1): `samples` random operand sets per check, bitwise compared on the device with `/`, sqrt() and
