@@ -89,9 +89,6 @@ constexpr unsigned FULL = 0xffffffffu;
 #endif
 //  FPB_FIT_SPAN_SMEM = 1: the span reciprocals of bspl_tab live in shared memory (after the stream ring)
 //  instead of registers.
-#ifndef FPB_FIT_SPAN_SMEM
-#define FPB_FIT_SPAN_SMEM 0
-#endif
 #if FPB_FIT_SPAN_SMEM
 #define FPB_SPAN_STRIDE kFitThreads
 #else

@@ -41,10 +41,14 @@ constexpr unsigned fit_smem_bytes(int k, int idim = 1)
 // curfit / parcur kernels: band window + the cp.async ring of the point streams (`depth` slots of
 // x, y(1:idim) and, with weights, w per thread)
 constexpr int fit_window_doubles(int k, int idim) { return (k + 1) * (k + 1) + (k + 1) * idim; }
+#ifndef FPB_FIT_SPAN_SMEM
+#define FPB_FIT_SPAN_SMEM 0   // span reciprocals of bspl_tab in registers (1: in shared memory, +9 ms measured)
+#endif
 constexpr unsigned fit_smem_bytes_stream(int k, int idim, bool has_w, int depth)
 {
-    // + k(k+1)/2 span reciprocals per thread (bspl_tab)
-    return (unsigned)((fit_window_doubles(k, idim) + depth * (1 + idim + (has_w ? 1 : 0)) + k * (k + 1) / 2) *
+    // (+ k(k+1)/2 span reciprocals per thread when they live in shared memory)
+    return (unsigned)((fit_window_doubles(k, idim) + depth * (1 + idim + (has_w ? 1 : 0)) +
+                       (FPB_FIT_SPAN_SMEM ? k * (k + 1) / 2 : 0)) *
                       kFitThreads * sizeof(double));
 }
 // deepest ring (8, 4 or 2 slots) that still lets `blocks` CTAs share the SM's 227 KB (1 KB reserved per CTA)
