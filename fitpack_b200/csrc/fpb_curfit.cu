@@ -51,6 +51,8 @@
 // translation units (fpb_curfit_d2.cu ... include this file with FPB_FIT_IDIM set); IDIM = 0 is
 // the run-time fallback for idim = 4..10.  p.par selects parcur's argument checks and the few
 // places where fppara's arithmetic differs from fpcurf's.
+#include <algorithm>
+
 #include "fpb_common.cuh"
 #include "fpb_kernels.h"
 
@@ -1197,7 +1199,9 @@ __device__ void part2_tile(const FitParams &p, int b, bool valid, double *__rest
 }
 
 // persistent warps; tiles of 32 list entries are handed out through an atomic counter
-template <int K, bool HAS_W, int IDIM>
+// STAGED: list entries may carry the "no pass yet" flag (chunks of a host batch joining a running pipeline); a
+// separate instantiation so that the device-resident path keeps its kernel-uniform `first`.
+template <int K, bool HAS_W, int IDIM, bool STAGED>
 __global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K, IDIM))
     curfit_pass_kernel(FitParams p, const int *__restrict__ in_list, const int *in_count,
                        int *out_list, int *out_count, int *p2_list, int *p2_count, int first)
@@ -1219,7 +1223,14 @@ __global__ void __launch_bounds__(kFitThreads, fit_blocks_per_sm(K, IDIM))
         const bool valid = base + lane < count;
         int b = 0;
         if (valid) b = first ? (int)(base + lane) : in_list[base + lane];
-        const int st = pass_tile<K, HAS_W, IDIM>(p, b, valid, first != 0, wsd, wsi, rs, ring);
+        // a list entry with the top bit set is a curve that has not had its first pass yet (chunks of a
+        // host batch join the running pipeline as they arrive, launch_fit_admit)
+        bool fresh = first != 0;
+        if (STAGED) {
+            fresh = fresh || (valid && b < 0);
+            b &= 0x7fffffff;
+        }
+        const int st = pass_tile<K, HAS_W, IDIM>(p, b, valid, fresh, wsd, wsi, rs, ring);
         __syncwarp();
         list_append(out_list, out_count, valid && st == ST_LOOP, b, lane);
         const bool to2 = valid && st == ST_PART2;
@@ -1260,7 +1271,7 @@ cudaError_t launch_pass_kw(const FitParams &p, int grid, cudaStream_t st, const 
 {
     constexpr int D = FPB_FIT_IDIM;
     const unsigned smem = fit_smem_bytes_stream(p.k, p.idim, HAS_W, p.sdepth);
-    auto kern = curfit_pass_kernel<K, HAS_W, D>;
+    auto kern = p.staged ? curfit_pass_kernel<K, HAS_W, D, true> : curfit_pass_kernel<K, HAS_W, D, false>;
     if (smem > 48u * 1024u) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1306,6 +1317,14 @@ __global__ void p2_scatter_kernel(const int *list, const int *count_ptr, const i
         const int pos = atomicAdd(&offsets[min(n_arr[b], nbins - 1)], 1);
         sorted[pos] = b;
     }
+}
+
+// curves c0 .. c0+nc-1 join the pipeline: appended to `list` behind its `base` entries, flagged "no pass yet"
+__global__ void fit_admit_kernel(int *list, int *count, int base, int c0, int nc)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x)
+        list[base + i] = (c0 + i) | (int)0x80000000;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count = base + nc;
 }
 
 // chord-length parameters of parcur (ipar=0, core:15238-15253): u(1)=0, u(i)=u(i-1)+norm2(dx),
@@ -1450,6 +1469,13 @@ cudaError_t launch_curfit_part2(const FitParams &p, int grid_blocks, cudaStream_
     case 3: return launch_curfit_part2_d3(p, grid_blocks, stream, list, count);
     default: return launch_curfit_part2_d0(p, grid_blocks, stream, list, count);
     }
+}
+
+cudaError_t launch_fit_admit(int *list, int *count, int base, int c0, int nc, cudaStream_t stream)
+{
+    if (nc <= 0) return cudaSuccess;
+    fit_admit_kernel<<<std::min((nc + 255) / 256, 1024), 256, 0, stream>>>(list, count, base, c0, nc);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_p2_sort(const int *list, const int *count, const int *n_arr, int *hist,

@@ -6,6 +6,7 @@
 #include "fpb_engine.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <chrono>
 #include <cstdio>
@@ -189,6 +190,7 @@ void fpb_engine_destroy(fpb_engine *eng)
         if (eng->h_off[i]) cudaFreeHost(eng->h_off[i]);
     }
     for (auto &b : eng->scratch2) b.release();
+    for (auto e : eng->ev_chunk) cudaEventDestroy(e);
     if (eng->s_in) cudaStreamDestroy(eng->s_in);
     if (eng->s_out) cudaStreamDestroy(eng->s_out);
     for (int i = 0; i < 2; ++i) {
@@ -313,7 +315,7 @@ void fitpack_message_c(FP_FLAG ierr, char *msg)
 namespace fpb {
 // The pass pipeline shared by curfit (idim = 1) and parcur: `p` arrives with the caller's arrays,
 // strides and scalars set; this fills in the engine-owned workspace / state and runs the passes.
-int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
+int32_t run_fit_pipeline(fpb_engine *eng, FitParams p, const std::vector<FitArrival> *arrivals)
 {
     NvtxRange nvtx_pipeline(p.periodic ? "fpb:percur pipeline" : (p.par ? "fpb:parcur pipeline" : "fpb:curfit pipeline"));
     const int nbatch = p.nbatch, iopt = p.iopt, m = p.m, k = p.k, nest = p.nest;
@@ -331,11 +333,13 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     const size_t warps = (size_t)grid_ws * (kFitThreads / 32);
     const size_t nb = (size_t)nbatch;
     // counters: [0] tile queue head, [4] list A count, [5] list B count, [6] part-2 count,
-    // [8] part-2 count at the moment the early part-2 launch was cut off, [9] length of the rest,
-    // [12] tile queue head of the early part-2 launch; two histograms of n follow (early / rest)
+    // [16..17] cursor of the hand-over pool; from [64] on: one histogram of n per part-2 section, then the
+    // sections' counts and tile-queue heads
     const size_t hist_off = 64;  // ints
     const size_t hist_len = (size_t)L.nestp + 8;
-    const size_t cnt_ints = hist_off + 2 * hist_len;
+    constexpr int kMaxSec = 24;   // part-2 sections on the side stream (+ the final one on the main stream)
+    const size_t sec_off = hist_off + (size_t)(kMaxSec + 1) * hist_len;   // per section: count, tile-queue head
+    const size_t cnt_ints = sec_off + 2 * (kMaxSec + 1) + 8;
     if (!eng->ws.reserve(warps * (size_t)L.ws_per_lane * 32 * sizeof(double)) ||
         !eng->wsi.reserve(warps * (size_t)L.nestp * 32 * sizeof(int)) ||
         !eng->counter.reserve(cnt_ints * sizeof(int)) ||
@@ -344,7 +348,7 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
         !eng->st_nrd.reserve(nb * (size_t)L.nestp * sizeof(int)))
         return FPB_ERR_ALLOC;
     if (!eng->h_count) {
-        if (!cuda_ok(cudaHostAlloc((void **)&eng->h_count, 64, cudaHostAllocDefault), "cudaHostAlloc"))
+        if (!cuda_ok(cudaHostAlloc((void **)&eng->h_count, 1024, cudaHostAllocDefault), "cudaHostAlloc"))
             return FPB_ERR_ALLOC;
     }
     int *cnt = eng->counter.as<int>();
@@ -382,12 +386,14 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
             p.az_cursor = reinterpret_cast<unsigned long long *>(cnt + 16);   // zeroed with the counters
         }
     }
-    int *hist_early = cnt + hist_off, *hist_rest = cnt + hist_off + hist_len;
-    p.hist = hist_early;
+    auto sec_hist = [&](int i) { return cnt + hist_off + (size_t)i * hist_len; };
+    auto sec_count = [&](int i) { return cnt + sec_off + i; };
+    auto sec_head = [&](int i) { return cnt + sec_off + (kMaxSec + 1) + i; };
+    p.hist = sec_hist(0);
     int *list[2] = {eng->lists.as<int>(), eng->lists.as<int>() + nb};
     int *p2_list = eng->lists.as<int>() + 2 * nb, *p2_sorted = eng->lists.as<int>() + 3 * nb;
     int *lcount[2] = {cnt + 4, cnt + 5};
-    int *p2_count = cnt + 6, *p2_early_count = cnt + 8, *p2_rest_count = cnt + 9;
+    int *p2_count = cnt + 6;
 
     // Early part 2 (curfit / parcur, large batches): once the curves that still need a finer knot set no
     // longer fill the GPU, the passes that remain are a chain of sparsely populated, latency-bound launches
@@ -401,20 +407,50 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
     // tuning knobs (profiles/r02_ab.md): cut-off point in units of capacity/4, CTAs per SM left to the tail
     static const int early_at4 = std::getenv("FPB_FIT_EARLY_AT4") ? std::atoi(std::getenv("FPB_FIT_EARLY_AT4")) : 4;
     static const int early_free = std::getenv("FPB_FIT_EARLY_FREE") ? std::atoi(std::getenv("FPB_FIT_EARLY_FREE")) : 1;
-    int early = -1;   // part-2 list length when the early launch was cut off (-1: no early launch)
+    int isec = 0, sec_start = 0;   // side-stream sections launched so far; first part-2 list entry not yet in a section
+    bool tail_done = false;          // the cut at the start of the tail has been made
 
     begin_timing(eng);
-    // pass 1 over the whole batch (identity list), then passes over the shrinking list of curves
-    // that still need a finer knot set.  The host reads the list length every other pass.
-    if (!cuda_ok(launch_curfit_pass(p, (int)grid, st, nullptr, nullptr, list[0], lcount[0], p2_list,
-                                    p2_count, 1), "curfit pass kernel"))
-        return FPB_ERR_CUDA;
-    eng->launches++;
-    int cur = 0, remaining = (iopt < 0) ? 0 : nbatch;  // iopt=-1: a single pass settles every curve
-    const int max_rounds = 2 * (m + 4) + 8;  // fpcurf's own bound on knot sets, with one restart
-    for (int round = 1; round <= max_rounds && remaining > 0; ++round) {
-        const bool near_tail = may_overlap && early < 0 && remaining <= std::max<long long>(4, early_at4) * capacity;
-        if (round >= 3 && ((round & 1) || near_tail)) {
+    // Staged mode (host-pointer path): the chunks of the batch join the pipeline as their data arrives; every
+    // launch then works on whatever is active -- curves of early chunks may be several knot sets ahead of the
+    // late ones (a list entry with the top bit set has not had its first pass).  Otherwise: pass 1 over the
+    // whole batch (identity list), then passes over the shrinking list of curves that still need a finer
+    // knot set; the host reads the list length every other pass.
+    const bool staged = arrivals != nullptr && !arrivals->empty() && iopt >= 0 && !p.periodic;
+    p.staged = staged ? 1 : 0;
+    size_t next_arr = 0;
+    int cur = 0, remaining = 0;
+    if (!staged) {
+        if (!cuda_ok(launch_curfit_pass(p, (int)grid, st, nullptr, nullptr, list[0], lcount[0], p2_list,
+                                        p2_count, 1), "curfit pass kernel"))
+            return FPB_ERR_CUDA;
+        eng->launches++;
+        remaining = (iopt < 0) ? 0 : nbatch;  // iopt=-1: a single pass settles every curve
+    }
+    // admit every chunk that has arrived (at least one when nothing else is active)
+    auto admit = [&]() -> bool {
+        while (next_arr < arrivals->size()) {
+            const FitArrival &a = (*arrivals)[next_arr];
+            if (remaining > 0 && cudaEventQuery(a.ready) != cudaSuccess) break;
+            if (!cuda_ok(cudaStreamWaitEvent(st, a.ready, 0), "wait") ||
+                !cuda_ok(launch_fit_admit(list[cur], lcount[cur], remaining, a.c0, a.nc, st), "admit"))
+                return false;
+            eng->launches++;
+            remaining += a.nc;
+            ++next_arr;
+        }
+        return true;
+    };
+    const bool all_in = true;
+    (void)all_in;
+    const int max_rounds = 2 * (m + 4) + 8 + (staged ? 4 * (int)arrivals->size() : 0);  // fpcurf's own bound on knot sets, with one restart
+    for (int round = 1; round <= max_rounds && (remaining > 0 || (staged && next_arr < arrivals->size())); ++round) {
+        if (staged && next_arr < arrivals->size() && !admit()) return FPB_ERR_CUDA;
+        const bool arrived = !staged || next_arr == arrivals->size();
+        const bool near_tail = may_overlap && isec == 0 && arrived && remaining <= std::max<long long>(4, early_at4) * capacity;
+        // staged: the host needs the exact list length before every launch (the next admission appends behind it);
+        // the read comes after the launch below, so round 1 has nothing to read
+        if (!staged && round >= 3 && ((round & 1) || near_tail)) {
             // [4],[5],[6]: both list lengths and the part-2 count in one copy
             if (!cuda_ok(cudaMemcpyAsync(eng->h_count, cnt + 4, 3 * sizeof(int), cudaMemcpyDeviceToHost, st),
                          "count D2H") ||
@@ -422,9 +458,24 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
                 return FPB_ERR_CUDA;
             remaining = eng->h_count[cur];
             if (remaining <= 0) break;
-            const int n2_now = eng->h_count[2];
-            if (may_overlap && early < 0 && remaining <= capacity * early_at4 / 4 && n2_now >= 2 * capacity) {
-                // ---- cut the part-2 list here and start its first section on the second stream ----
+        }
+        {
+            const int n2_now = eng->h_count[2];   // staged: read after the previous launch (below)
+            const bool fresh_counts = staged ? round >= 2 : (round >= 3 && ((round & 1) || near_tail));
+            // non-staged: ONE cut, when the curves still in part 1 no longer fill the GPU.  staged: the GPU follows
+            // the arriving data with a small active population, so part 2 of the curves accepted so far is started
+            // whenever two resident waves of them have piled up -- it runs beside the passes the whole time
+            // instead of after the last chunk -- plus the final cut as in the non-staged case.
+            const bool tail_cut = arrived && !tail_done && remaining <= capacity * early_at4 / 4 &&
+                                  (long long)(n2_now - sec_start) >= (staged ? capacity / 2 : 2 * capacity);
+            // (staged mode: cutting a section whenever two resident waves of accepted curves have piled up -- part 2
+            // beside the passes all the way -- was measured and lost: 184.5 vs 168.7 ms end to end, the passes crawl
+            // on the one CTA slot per SM the section leaves them; FPB_FIT_PILE_CUTS=1 re-enables it)
+            static const bool pile_cuts = std::getenv("FPB_FIT_PILE_CUTS") != nullptr;
+            const bool pile_cut = pile_cuts && staged && !tail_done && (long long)(n2_now - sec_start) >= 2 * capacity;
+            if (may_overlap && fresh_counts && remaining > 0 && isec < kMaxSec && (pile_cut || tail_cut)) {
+                if (tail_cut) tail_done = true;
+                // ---- cut the part-2 list here and start the section [sec_start, n2_now) on the second stream ----
                 if (!eng->s_p2) {
                     if (!cuda_ok(cudaStreamCreateWithFlags(&eng->s_p2, cudaStreamNonBlocking), "stream") ||
                         !cuda_ok(cudaEventCreateWithFlags(&eng->ev_p2[0], cudaEventDisableTiming), "event") ||
@@ -434,33 +485,36 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
                 const int blocks_p2 = p.periodic ? max_warps / (kFitThreads / 32) / eng->nsm
                                                  : fit_p2_blocks_per_sm(k, idim_class(p.idim));
                 const int blocks_early = std::max(1, blocks_p2 - early_free);
-                const long long grid_early = std::min<long long>((long long)eng->nsm * blocks_early,
-                                                                 ((long long)n2_now + kFitThreads - 1) / kFitThreads);
-                const size_t warps2 = (size_t)grid_early * (kFitThreads / 32);
+                const int nsec = n2_now - sec_start;
+                const long long slots_early = (long long)eng->nsm * blocks_early;
+                const long long grid_early = std::min<long long>(slots_early, ((long long)nsec + kFitThreads - 1) / kFitThreads);
+                const size_t warps2 = (size_t)std::min<long long>(slots_early, blocks_needed) * (kFitThreads / 32);
                 if (!eng->ws2.reserve(warps2 * (size_t)L.ws_per_lane * 32 * sizeof(double)) ||
                     !eng->wsi2.reserve(warps2 * (size_t)L.nestp * 32 * sizeof(int)))
                     return FPB_ERR_ALLOC;
-                early = n2_now;
-                eng->h_count[8] = early;
-                if (!cuda_ok(cudaMemcpyAsync(p2_early_count, eng->h_count + 8, sizeof(int), cudaMemcpyHostToDevice, st),
-                             "early count") ||
+                eng->h_count[32 + isec] = nsec;
+                if (!cuda_ok(cudaMemcpyAsync(sec_count(isec), eng->h_count + 32 + isec, sizeof(int), cudaMemcpyHostToDevice, st),
+                             "section count") ||
                     !cuda_ok(cudaEventRecord(eng->ev_p2[0], st), "event") ||
                     !cuda_ok(cudaStreamWaitEvent(eng->s_p2, eng->ev_p2[0], 0), "wait"))
                     return FPB_ERR_CUDA;
                 FitParams pe = p;
                 pe.ws = eng->ws2.as<double>();
                 pe.wsi = eng->wsi2.as<int>();
-                pe.counter = reinterpret_cast<unsigned *>(cnt + 12);
-                if (!cuda_ok(launch_p2_sort(p2_list, p2_early_count, n, hist_early, L.nestp + 1, p2_sorted, eng->nsm,
-                                            eng->s_p2), "part-2 sort") ||
-                    !cuda_ok(launch_curfit_part2(pe, (int)grid_early, eng->s_p2, p2_sorted, p2_early_count),
+                pe.counter = reinterpret_cast<unsigned *>(sec_head(isec));
+                if (!cuda_ok(launch_p2_sort(p2_list + sec_start, sec_count(isec), n, sec_hist(isec), L.nestp + 1,
+                                            p2_sorted + sec_start, eng->nsm, eng->s_p2), "part-2 sort") ||
+                    !cuda_ok(launch_curfit_part2(pe, (int)grid_early, eng->s_p2, p2_sorted + sec_start, sec_count(isec)),
                              "curfit part-2 kernel (early)") ||
                     !cuda_ok(cudaEventRecord(eng->ev_p2[1], eng->s_p2), "event"))
                     return FPB_ERR_CUDA;
                 eng->launches += 3;
-                p.hist = hist_rest;   // curves accepted from now on are counted for the second section
+                sec_start = n2_now;
+                ++isec;
+                p.hist = sec_hist(isec);   // curves accepted from now on are counted for the next section
             }
         }
+        if (remaining <= 0) continue;   // staged: nothing active, wait for the next chunk
         // reset the queue head and the output list length
         if (!cuda_ok(cudaMemsetAsync(cnt, 0, sizeof(int), st), "memset") ||
             !cuda_ok(cudaMemsetAsync(lcount[1 - cur], 0, sizeof(int), st), "memset"))
@@ -472,6 +526,20 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
             return FPB_ERR_CUDA;
         eng->launches++;
         cur = 1 - cur;
+        if (staged) {   // exact survivor count (and the part-2 count) for the next admission / launch
+            if (!cuda_ok(cudaMemcpyAsync(eng->h_count, cnt + 4, 3 * sizeof(int), cudaMemcpyDeviceToHost, st),
+                         "count D2H") ||
+                !cuda_ok(cudaStreamSynchronize(st), "sync"))
+                return FPB_ERR_CUDA;
+            remaining = eng->h_count[cur];
+            static const bool trace = std::getenv("FPB_HOST_TRACE") != nullptr;
+            if (trace) {
+                static const auto t0 = std::chrono::steady_clock::now();
+                std::fprintf(stderr, "[fpb staged] %9.2f ms  round %d  chunks in %zu/%zu  active %d  part-2 list %d  side sections %d\n",
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+                             round, next_arr, arrivals->size(), remaining, eng->h_count[2], isec);
+            }
+        }
     }
     // part 2 on the curves whose knots were accepted with fp < s
     if (iopt >= 0) {
@@ -480,15 +548,15 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
             !cuda_ok(cudaStreamSynchronize(st), "sync"))
             return FPB_ERR_CUDA;
         const int n2 = eng->h_count[0];
-        const int first = early < 0 ? 0 : early;   // entries [first, n2) of the part-2 list are still to do
+        const int first = sec_start;   // entries [first, n2) of the part-2 list are still to do
         if (n2 > first) {
             const int *count_ptr = p2_count;
-            if (early >= 0) {
-                eng->h_count[9] = n2 - first;
-                if (!cuda_ok(cudaMemcpyAsync(p2_rest_count, eng->h_count + 9, sizeof(int), cudaMemcpyHostToDevice, st),
+            if (isec > 0) {
+                eng->h_count[32 + isec] = n2 - first;
+                if (!cuda_ok(cudaMemcpyAsync(sec_count(isec), eng->h_count + 32 + isec, sizeof(int), cudaMemcpyHostToDevice, st),
                              "rest count"))
                     return FPB_ERR_CUDA;
-                count_ptr = p2_rest_count;
+                count_ptr = sec_count(isec);
             }
             if (!cuda_ok(launch_p2_sort(p2_list + first, count_ptr, n, p.hist, L.nestp + 1, p2_sorted + first,
                                         eng->nsm, st), "part-2 sort") ||
@@ -501,7 +569,7 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p)
             eng->launches++;
         }
     }
-    if (early >= 0 && !cuda_ok(cudaStreamWaitEvent(st, eng->ev_p2[1], 0), "join"))   // the caller's stream sees all of it
+    if (isec > 0 && !cuda_ok(cudaStreamWaitEvent(st, eng->ev_p2[1], 0), "join"))   // the caller's stream sees all of it
         return FPB_ERR_CUDA;
     end_timing(eng);
     return FPB_STATUS_OK;
@@ -1013,6 +1081,194 @@ int32_t fit_slice_pipelined(fpb_engine *eng, const std::vector<long long> &cuts,
     return ok_end ? FPB_STATUS_OK : FPB_ERR_CUDA;
 }
 
+// Wavefront form of the host-pointer batch fit (large fresh fits, iopt = 0): ONE pipeline over the whole slice
+// on one engine.  The inputs stream in as chunks on a copy stream (H2D into two alternating staging sets, tile
+// transpose into the slice-wide point-major arrays); each chunk's curves join the running pipeline at the first
+// launch after they have landed (run_fit_pipeline, staged mode), so the GPU works from the first chunk on and
+// the latency-bound tail of the fit (the sparsely populated last passes, part 2 of the curves with ~100 knots)
+// is paid ONCE per slice instead of once per chunk.  Results come back dense (pack_tc_kernel) and are scattered
+// into the caller's rows by a few helper threads.
+int32_t fit_slice_wavefront(fpb_engine *eng, long long b0, long long b1, FP_SIZE m, const FP_REAL *x,
+                            const FP_REAL *y, const FP_REAL *w, const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k,
+                            FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier)
+{
+    NvtxRange nvtx_slice("fpb:host slice, wavefront (H2D chunks | one pipeline | dense D2H)");
+    DeviceGuard g(eng->device);
+    if (!g.ok) return FPB_ERR_CUDA;
+    if (!eng->s_in) {
+        if (!cuda_ok(cudaStreamCreateWithFlags(&eng->s_in, cudaStreamNonBlocking), "stream") ||
+            !cuda_ok(cudaStreamCreateWithFlags(&eng->s_out, cudaStreamNonBlocking), "stream"))
+            return FPB_ERR_CUDA;
+        for (int i = 0; i < 2; ++i)
+            if (!cuda_ok(cudaEventCreateWithFlags(&eng->ev_in[i], cudaEventDisableTiming), "event") ||
+                !cuda_ok(cudaEventCreateWithFlags(&eng->ev_fit[i], cudaEventDisableTiming), "event"))
+                return FPB_ERR_CUDA;
+    }
+    cudaStream_t st = eng->stream, s_in = eng->s_in;
+    static const bool trace = std::getenv("FPB_HOST_TRACE") != nullptr;
+    const auto t_epoch = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what) {
+        if (!trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_epoch).count();
+        std::fprintf(stderr, "[fpb wavefront %p] %9.2f ms  %s\n", (void *)eng, ms, what);
+    };
+    const long long total = b1 - b0;
+    // chunks: small first (the GPU starts early), then ~1/8 of the slice each
+    int nchunk = 10;
+    if (const char *e = std::getenv("FPB_HOST_WAVE_CHUNKS")) nchunk = std::max(2, std::atoi(e));
+    std::vector<long long> cuts;
+    cuts.push_back(0);
+    {
+        const long long unit = std::max<long long>(128, (total / nchunk + 127) / 128 * 128);
+        long long first = std::max<long long>(128, (unit / 4 + 127) / 128 * 128);
+        cuts.push_back(std::min(total, first));
+        cuts.push_back(std::min(total, first + unit / 2 / 128 * 128 + 128));
+        while (cuts.back() < total) cuts.push_back(std::min(total, cuts.back() + unit));
+    }
+    const int nc = (int)cuts.size() - 1;
+    long long maxchunk = 0;
+    for (int i = 0; i < nc; ++i) maxchunk = std::max(maxchunk, cuts[i + 1] - cuts[i]);
+    enum { XC0, YC0, WC0, XC1, YC1, WC1, XP, YP, WP, TT, CC, NN, FP_, IER, AUX, OFF };   // eng->scratch
+    enum { TP, CP, CUR };                                                                  // eng->scratch2
+    DevBuf *B = eng->scratch, *B2 = eng->scratch2;
+    const size_t cpts = (size_t)maxchunk * m * 8, pts = (size_t)total * m * 8;
+    const long long dense_cap = total * std::min<long long>(nest, m + k + 1);
+    if (!B[XC0].reserve(cpts) || !B[YC0].reserve(cpts) || !B[XC1].reserve(cpts) || !B[YC1].reserve(cpts) ||
+        !B[WC0].reserve(w ? cpts : 8) || !B[WC1].reserve(w ? cpts : 8) || !B[XP].reserve(pts) || !B[YP].reserve(pts) ||
+        !B[WP].reserve(w ? pts : 8) || !B[TT].reserve((size_t)total * nest * 8) || !B[CC].reserve((size_t)total * nest * 8) ||
+        !B[NN].reserve((size_t)total * 4) || !B[FP_].reserve((size_t)total * 8) || !B[IER].reserve((size_t)total * 4) ||
+        !B[AUX].reserve(64) || !B[OFF].reserve((size_t)total * 8) || !B2[TP].reserve((size_t)dense_cap * 8) ||
+        !B2[CP].reserve((size_t)dense_cap * 8) || !B2[CUR].reserve(64) ||
+        !reserve_pinned((void **)&eng->h_off[0], &eng->h_off_bytes[0], (size_t)total * 8))
+        return FPB_ERR_ALLOC;
+    // events, one per chunk (grow-only pool on the engine)
+    while ((int)eng->ev_chunk.size() < nc) {
+        cudaEvent_t e = nullptr;
+        if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return FPB_ERR_CUDA;
+        eng->ev_chunk.push_back(e);
+    }
+    // everything the copy stream will do, enqueued up front (asynchronous for pinned caller memory)
+    double *aux = B[AUX].as<double>();
+    eng->h_aux[0][0] = s;
+    eng->h_aux[0][1] = xb ? *xb : 0.0;
+    eng->h_aux[0][2] = xe ? *xe : 0.0;
+    bool ok = cuda_ok(cudaMemcpyAsync(aux, eng->h_aux[0], 24, cudaMemcpyHostToDevice, st), "H2D s");
+    // outputs the kernel may leave untouched (ier = 10) round-trip unchanged
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[FP_].ptr, fp + b0, (size_t)total * 8, cudaMemcpyHostToDevice, st), "H2D fp");
+    ok = ok && cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + b0, (size_t)total * 4, cudaMemcpyHostToDevice, st), "H2D n");
+    ok = ok && cuda_ok(cudaEventRecord(eng->ev_in[0], st), "event");
+    ok = ok && cuda_ok(cudaStreamWaitEvent(s_in, eng->ev_in[0], 0), "wait");   // the copy stream starts after earlier work on st
+    std::vector<FitArrival> arrivals;
+    for (int ci = 0; ok && ci < nc; ++ci) {
+        const long long c0 = cuts[ci], nb = cuts[ci + 1] - cuts[ci];
+        const int set = ci & 1;
+        double *xc = B[set ? XC1 : XC0].as<double>(), *yc = B[set ? YC1 : YC0].as<double>(),
+               *wc = B[set ? WC1 : WC0].as<double>();
+        const size_t bytes = (size_t)nb * m * 8;
+        ok = ok && cuda_ok(cudaMemcpyAsync(xc, x + (size_t)(b0 + c0) * m, bytes, cudaMemcpyHostToDevice, s_in), "H2D x");
+        ok = ok && cuda_ok(cudaMemcpyAsync(yc, y + (size_t)(b0 + c0) * m, bytes, cudaMemcpyHostToDevice, s_in), "H2D y");
+        if (w) ok = ok && cuda_ok(cudaMemcpyAsync(wc, w + (size_t)(b0 + c0) * m, bytes, cudaMemcpyHostToDevice, s_in), "H2D w");
+        // curve-major chunk -> columns [c0, c0+nb) of the slice-wide point-major arrays (ld = total)
+        ok = ok && cuda_ok(launch_transpose(xc, m, B[XP].as<double>() + c0, total, nb, m, s_in), "transpose x");
+        ok = ok && cuda_ok(launch_transpose(yc, m, B[YP].as<double>() + c0, total, nb, m, s_in), "transpose y");
+        if (w) ok = ok && cuda_ok(launch_transpose(wc, m, B[WP].as<double>() + c0, total, nb, m, s_in), "transpose w");
+        eng->launches += w ? 3 : 2;
+        ok = ok && cuda_ok(cudaEventRecord(eng->ev_chunk[ci], s_in), "event");
+        arrivals.push_back(FitArrival{(int)c0, (int)nb, eng->ev_chunk[ci]});
+    }
+    if (!ok) return FPB_ERR_CUDA;
+    stamp("copies enqueued");
+    FitParams p;
+    std::memset(&p, 0, sizeof p);
+    p.nbatch = (int)total; p.iopt = 0; p.m = m; p.k = k; p.nest = nest;
+    p.x = B[XP].as<double>(); p.y = B[YP].as<double>(); p.w = w ? B[WP].as<double>() : nullptr;
+    p.x_sb = 1; p.x_si = total; p.y_sb = 1; p.y_si = total; p.w_sb = w ? 1 : 0; p.w_si = w ? total : 0;
+    p.xb = xb ? aux + 1 : nullptr; p.xe = xe ? aux + 2 : nullptr; p.xbe_stride = 0;
+    p.s = aux; p.s_stride = 0;
+    p.n = B[NN].as<int>(); p.t = B[TT].as<double>(); p.c = B[CC].as<double>(); p.fp = B[FP_].as<double>();
+    p.ier = B[IER].as<int>();
+    p.idim = 1; p.c_sb = nest;
+    const int32_t rc = run_fit_pipeline(eng, p, &arrivals);
+    if (rc != FPB_STATUS_OK) return rc;
+    stamp("pipeline enqueued");
+    // dense copy-out
+    ok = cuda_ok(cudaMemsetAsync(B2[CUR].ptr, 0, 8, st), "memset") &&
+         cuda_ok(launch_pack_tc((int)total, nest, k, B[NN].as<int>(), B[IER].as<int>(), B[TT].as<double>(),
+                                B[CC].as<double>(), B2[CUR].as<unsigned long long>(), B[OFF].as<long long>(),
+                                B2[TP].as<double>(), B2[CP].as<double>(), eng->nsm, st), "pack kernel") &&
+         cuda_ok(cudaMemcpyAsync(eng->h_off[0], B[OFF].ptr, (size_t)total * 8, cudaMemcpyDeviceToHost, st), "D2H offsets") &&
+         cuda_ok(cudaMemcpyAsync(n + b0, B[NN].ptr, (size_t)total * 4, cudaMemcpyDeviceToHost, st), "D2H n") &&
+         cuda_ok(cudaMemcpyAsync(fp + b0, B[FP_].ptr, (size_t)total * 8, cudaMemcpyDeviceToHost, st), "D2H fp") &&
+         cuda_ok(cudaMemcpyAsync(ier + b0, B[IER].ptr, (size_t)total * 4, cudaMemcpyDeviceToHost, st), "D2H ier") &&
+         cuda_ok(cudaStreamSynchronize(st), "sync");
+    eng->launches++;
+    if (!ok) return FPB_ERR_CUDA;
+    stamp("fit done, n/fp/ier/offsets on host");
+    const long long *off = eng->h_off[0];
+    long long dense = 0;
+    for (long long b = 0; b < total; ++b)
+        if (off[b] >= 0) dense += n[b0 + b];
+    if (dense > 0) {
+        if (!reserve_pinned((void **)&eng->h_pack[0], &eng->h_pack_bytes[0], (size_t)dense * 16)) return FPB_ERR_ALLOC;
+        double *tp = eng->h_pack[0], *cp = eng->h_pack[0] + dense;
+        // the dense arrays come back in pieces; a helper thread scatters each piece's curves as soon as it has
+        // landed -- but the curves of a piece are not contiguous in b (allocation order of the pack kernel), so
+        // every helper walks its own range of b and waits for the piece that holds the curve's data
+        const int npiece = 8;
+        std::vector<cudaEvent_t> evp(npiece);
+        std::vector<long long> pend(npiece + 1, 0);
+        for (int q = 0; q <= npiece; ++q) pend[q] = dense * q / npiece;
+        for (int q = 0; ok && q < npiece; ++q) {
+            ok = cuda_ok(cudaEventCreateWithFlags(&evp[q], cudaEventDisableTiming | cudaEventBlockingSync), "event");
+            const long long lo = pend[q], cnt_ = pend[q + 1] - pend[q];
+            if (cnt_ > 0) {
+                ok = ok && cuda_ok(cudaMemcpyAsync(tp + lo, B2[TP].as<double>() + lo, (size_t)cnt_ * 8, cudaMemcpyDeviceToHost, st), "D2H t (dense)");
+                ok = ok && cuda_ok(cudaMemcpyAsync(cp + lo, B2[CP].as<double>() + lo, (size_t)cnt_ * 8, cudaMemcpyDeviceToHost, st), "D2H c (dense)");
+            }
+            ok = ok && cuda_ok(cudaEventRecord(evp[q], st), "event");
+        }
+        if (!ok) return FPB_ERR_CUDA;
+        // helper threads: one per core this rank may fairly claim (cores / visible GPUs), 2..16; they take blocks of
+        // 2048 curves in order from a shared counter, so all of them work on the pieces that landed first
+        int ndev = 1;
+        cudaGetDeviceCount(&ndev);
+        int nthr = (int)std::thread::hardware_concurrency() / std::max(1, ndev);
+        nthr = std::max(2, std::min(16, nthr));
+        if (const char *e = std::getenv("FPB_HOST_SCATTER_THREADS")) nthr = std::max(1, std::min(32, std::atoi(e)));
+        std::vector<std::thread> th;
+        const int dev = eng->device;
+        std::atomic<long long> next_block{0};
+        const long long blk = 2048;
+        for (int wk = 0; wk < nthr; ++wk) {
+            th.emplace_back([&]() {
+                cudaSetDevice(dev);
+                int reached = -1;   // pieces known to have landed
+                for (;;) {
+                    const long long lo = next_block.fetch_add(blk);
+                    if (lo >= total) break;
+                    const long long hi = std::min(total, lo + blk);
+                    for (long long b = lo; b < hi; ++b) {
+                        if (off[b] < 0) continue;
+                        const int nn = n[b0 + b];
+                        const long long last = off[b] + nn - 1;
+                        int need = 0;
+                        while (need < npiece - 1 && last >= pend[need + 1]) ++need;
+                        while (reached < need) cudaEventSynchronize(evp[++reached]);
+                        std::memcpy(t + (size_t)(b0 + b) * nest, tp + off[b], (size_t)nn * 8);
+                        if (nn - k - 1 > 0) std::memcpy(c + (size_t)(b0 + b) * nest, cp + off[b], (size_t)(nn - k - 1) * 8);
+                    }
+                }
+            });
+        }
+        for (auto &tt : th) tt.join();
+        ok = cuda_ok(cudaStreamSynchronize(st), "sync");
+        for (auto e : evp) cudaEventDestroy(e);
+        if (!ok) return FPB_ERR_CUDA;
+    }
+    stamp("t/c scattered");
+    return FPB_STATUS_OK;
+}
+
 // Chunking of one GPU's slice.  The fit pipeline is most efficient on big batches (its tail -- the last
 // knot sets and the longest p-iterations -- is a chain of latency-bound launches), while the first bytes
 // should reach the GPU quickly and the last copy-out should be short.  The slice is cut into `nchunks`
@@ -1031,6 +1287,15 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     fpb_engine *e0 = default_engine(device);
     if (!e0) return FPB_ERR_CUDA;
     const long long total = b1 - b0;
+    // large fresh fits: one pipeline over the slice, chunks joining as they arrive (FPB_HOST_MODE=workers: the
+    // chunk-per-engine form below)
+    {
+        static const bool force_workers = std::getenv("FPB_HOST_MODE") && std::strcmp(std::getenv("FPB_HOST_MODE"), "workers") == 0;
+        const size_t per_curve_w = (size_t)m * 8 * 2 * (w ? 3 : 2) + (size_t)nest * 8 * 4 + 64;   // slice-wide device bytes per curve
+        if (!force_workers && iopt == 0 && !shared_x && !fpint && !nrdata && total >= 4 * 65536 &&
+            total <= 0x3fffffff && (size_t)total * per_curve_w <= ((size_t)40 << 30))
+            return fit_slice_wavefront(e0, b0, b1, m, x, y, w, xb, xe, k, s, nest, n, t, c, fp, ier);
+    }
     int workers = 4;   // measured (profiles/r02_e2e.md): 2 -> 209 ms, 3 -> 213 ms, 4 -> 184 ms, 6 -> 190 ms per 2^20 curves
     if (const char *e = std::getenv("FPB_HOST_WORKERS")) workers = std::max(1, std::min(8, std::atoi(e)));
     // bytes per curve on the device: x,y,w curve-major + point-major, outputs t,c (+state, dense copies)

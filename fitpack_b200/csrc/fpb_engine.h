@@ -7,6 +7,7 @@
 #include <functional>
 #include <nvtx3/nvToolsExt.h>
 #include <string>
+#include <vector>
 
 #include "fpb_kernels.h"
 
@@ -50,6 +51,7 @@ struct fpb_engine {
     long long *h_off[2] = {nullptr, nullptr};
     size_t h_off_bytes[2] = {0, 0};
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;   // wavefront host path: one 'chunk has landed' event per chunk
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_fit[2] = {nullptr, nullptr};
     double h_aux[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     // gridded surfaces (fpb_regrid.cu): device tables, pinned read-back of the row/column sums
@@ -90,7 +92,13 @@ struct HostApiLock {
     int slot = -1;
 };
 // the curfit / parcur pass pipeline (fpb_engine.cu): `p` carries the caller's arrays and scalars
-int32_t run_fit_pipeline(fpb_engine *eng, FitParams p);
+// `arrivals` (optional): the batch reaches the device in chunks -- chunk i = curves [c0, c0+nc) is usable once
+// `ready` has fired; its curves join the running pipeline at the next launch after that (host-pointer path)
+struct FitArrival {
+    int c0, nc;
+    cudaEvent_t ready;
+};
+int32_t run_fit_pipeline(fpb_engine *eng, FitParams p, const std::vector<FitArrival> *arrivals = nullptr);
 // contiguous slices [b0, b1) of `total` units over the first `ngpus` devices (<= 0: all), one host
 // thread + default engine per device; fn(engine, b0, b1) runs on each (no collective)
 int32_t shard_units_over_gpus(long long total, int ngpus, long long align,

@@ -79,6 +79,7 @@ int fit_p2_resident_warps(int k, int idim, int nsm);
 struct FitParams {
     int nbatch, iopt, m, k, nest, nestp;
     int sdepth;             // slots of the point-stream ring (fit_stream_depth)
+    int staged;             // 1: pass lists may hold "no pass yet" entries (host batches arriving in chunks)
     int idim;               // coordinate curves per fit (1 for curfit)
     int par;                // 1: parcur/fppara semantics (checks, initial p, no zero-pivot skip)
     int periodic;           // 1: percur/fpperi (fpb_percur.cu kernels, two-block factor)
@@ -138,6 +139,8 @@ int percur_resident_warps(int k, int nsm);
 cudaError_t launch_parcur_param(int nbatch, int m, int idim, const double *x, long long x_sb,
                                 long long x_si, long long x_sd, double *u, long long u_sb,
                                 long long u_si, cudaStream_t stream);
+// curves c0 .. c0+nc-1 join a running pipeline: appended to `list` (which holds `base` entries), *count = base+nc
+cudaError_t launch_fit_admit(int *list, int *count, int base, int c0, int nc, cudaStream_t stream);
 cudaError_t launch_p2_sort(const int *list, const int *count, const int *n_arr, int *hist,
                            int nbins, int *sorted, int nsm, cudaStream_t stream);
 

@@ -175,3 +175,47 @@ def test_curfit_batch_rejected_rows_keep_t_c_with_the_dense_copy_out(F):
         n = o["n"][b]
         assert _same(r["t"][b, :n], o["t"][b, :n]) and _same(r["c"][b, :n - k - 1], o["c"][b, :n - k - 1])
         assert _same(r["t"][b, n:], t0[b, n:])          # beyond n the caller's row is untouched
+
+
+@pytest.mark.parametrize("weights", [False, True])
+def test_large_host_batch_takes_the_wavefront_path_and_matches_the_device_path(F, weights):
+    """fp_curfit_batch_c on >= 2^18 fresh fits streams the chunks into ONE running pipeline (staged admission,
+    dense copy-out, threaded scatter): every output must equal the device-resident fit of the same batch, rejected
+    rows must keep the caller's values, and a sample must equal the oracle."""
+    import torch
+    from fitpack_b200.batch import Engine
+    rng = np.random.default_rng(77)
+    B, m, k, nest = 300_000, 24, 3, 28
+    x, y = synth_curves(rng, B, m)
+    w = rng.uniform(0.5, 2.0, (B, m)) if weights else None
+    bad = [0, 5, 131071, 131072, 299_999]
+    for b in bad:
+        x[b, 10], x[b, 11] = x[b, 11], x[b, 10]
+    s = m * 0.01
+    n0 = np.full(B, -7, np.int32)
+    t0 = np.full((B, nest), 1.5)
+    r = F.curfit_batch(0, x, y, w, k, s, nest, n=n0.copy(), t=t0.copy())
+    dev = torch.device("cuda", 0)
+    eng = Engine(dev)
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)
+    yd = torch.from_numpy(np.ascontiguousarray(y.T)).to(dev)
+    wd = None if w is None else torch.from_numpy(np.ascontiguousarray(w.T)).to(dev)
+    d = eng.curfit_batch(xd, yd, wd, k=k, s=s, nest=nest)
+    torch.cuda.synchronize()
+    dn, dier, dfp = d["n"].cpu().numpy(), d["ier"].cpu().numpy(), d["fp"].cpu().numpy()
+    dt, dc = d["t"].cpu().numpy(), d["c"].cpu().numpy()
+    assert _same(r["ier"], dier) and all(dier[b] == 10 for b in bad)
+    good = np.ones(B, bool)
+    good[bad] = False
+    assert _same(r["n"][good], dn[good]) and _same(r["fp"][good], dfp[good])
+    for b in bad:
+        assert r["n"][b] == -7 and _same(r["t"][b], t0[b]) and not r["c"][b].any() and r["fp"][b] == 0.0
+    cols = np.arange(nest)[None, :]
+    tmask = (cols < dn[:, None]) & good[:, None]
+    cmask = (cols < (dn[:, None] - k - 1)) & good[:, None]
+    assert _same(r["t"][tmask], dt[tmask]) and _same(r["c"][cmask], dc[cmask])
+    assert _same(r["t"][~tmask & good[:, None]], t0[~tmask & good[:, None]])      # beyond n: the caller's values
+    idx = rng.choice(np.flatnonzero(good), 400, replace=False)
+    o = O.curfit_batch(0, x[idx], y[idx], None if w is None else w[idx], k, s, nest)
+    assert _same(o["n"], r["n"][idx]) and _same(o["fp"], r["fp"][idx]) and _same(o["ier"], r["ier"][idx])
+    eng.close()
