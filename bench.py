@@ -434,7 +434,8 @@ def main():
             if rc != 0:
                 raise RuntimeError("fp_curfit_batch_c failed: " + L.fpb_last_error().decode())
 
-        e2e_step()  # warm-up (allocates the staging buffers)
+        for _ in range(3):   # warm-up: staging buffers of both host forms (the library measures the copy rate on the
+            e2e_step()       # first call and may switch from the wavefront to the chunk-per-engine form on the next)
         esteps = max(1, args.steps)     # timed over the same number of steps as `value`
         barrier()
         t0 = time.perf_counter()

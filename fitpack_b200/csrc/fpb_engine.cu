@@ -191,6 +191,8 @@ void fpb_engine_destroy(fpb_engine *eng)
     }
     for (auto &b : eng->scratch2) b.release();
     for (auto e : eng->ev_chunk) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i)
+        if (eng->ev_h2d[i]) cudaEventDestroy(eng->ev_h2d[i]);
     if (eng->s_in) cudaStreamDestroy(eng->s_in);
     if (eng->s_out) cudaStreamDestroy(eng->s_out);
     for (int i = 0; i < 2; ++i) {
@@ -1081,6 +1083,27 @@ int32_t fit_slice_pipelined(fpb_engine *eng, const std::vector<long long> &cuts,
     return ok_end ? FPB_STATUS_OK : FPB_ERR_CUDA;
 }
 
+// How many slices copy through this host at the same time: the ranks the launcher put on this node (torchrun's
+// LOCAL_WORLD_SIZE, Open MPI's and Slurm's equivalents, or FPB_LOCAL_RANKS) or, for one process sharding a call
+// over its GPUs, the number of slices in flight.  Two decisions hang on it.  (1) Helper threads per slice = cores /
+// sharers.  (2) Which host form runs: with more than 4 sharers the host side is the bound (8 GPUs behind one host:
+// 23 GB/s H2D and 9 GB/s D2H per GPU instead of 55 / 50), the copies take longer than the fit, and the wavefront
+// form -- which pays its tail and copy-out after the last byte has landed -- loses to the chunk-per-engine form,
+// whose copy-out overlaps later chunks (298.8 vs 267.7 ms per step of 2^20 curves at 8 GPUs; 168.1 vs 182.5 ms
+// at one GPU).  A rate measured on the copy stream was tried as the signal and flapped between forms (ranks are not
+// in step during warm-up: 23..54 GB/s on the same box); the launcher's count is deterministic.
+std::atomic<int> g_slices_in_flight{0};
+int host_sharers()
+{
+    static const int env_ranks = []() {
+        for (const char *name : {"FPB_LOCAL_RANKS", "LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"})
+            if (const char *e = std::getenv(name))
+                if (std::atoi(e) > 0) return std::atoi(e);
+        return 1;
+    }();
+    return std::max(env_ranks, std::max(1, g_slices_in_flight.load()));
+}
+
 // Wavefront form of the host-pointer batch fit (large fresh fits, iopt = 0): ONE pipeline over the whole slice
 // on one engine.  The inputs stream in as chunks on a copy stream (H2D into two alternating staging sets, tile
 // transpose into the slice-wide point-major arrays); each chunk's curves join the running pipeline at the first
@@ -1158,6 +1181,10 @@ int32_t fit_slice_wavefront(fpb_engine *eng, long long b0, long long b1, FP_SIZE
     ok = ok && cuda_ok(cudaMemcpyAsync(B[NN].ptr, n + b0, (size_t)total * 4, cudaMemcpyHostToDevice, st), "H2D n");
     ok = ok && cuda_ok(cudaEventRecord(eng->ev_in[0], st), "event");
     ok = ok && cuda_ok(cudaStreamWaitEvent(s_in, eng->ev_in[0], 0), "wait");   // the copy stream starts after earlier work on st
+    if (!eng->ev_h2d[0]) {
+        ok = ok && cuda_ok(cudaEventCreate(&eng->ev_h2d[0]), "event") && cuda_ok(cudaEventCreate(&eng->ev_h2d[1]), "event");
+    }
+    ok = ok && cuda_ok(cudaEventRecord(eng->ev_h2d[0], s_in), "event");
     std::vector<FitArrival> arrivals;
     for (int ci = 0; ok && ci < nc; ++ci) {
         const long long c0 = cuts[ci], nb = cuts[ci + 1] - cuts[ci];
@@ -1176,6 +1203,7 @@ int32_t fit_slice_wavefront(fpb_engine *eng, long long b0, long long b1, FP_SIZE
         ok = ok && cuda_ok(cudaEventRecord(eng->ev_chunk[ci], s_in), "event");
         arrivals.push_back(FitArrival{(int)c0, (int)nb, eng->ev_chunk[ci]});
     }
+    ok = ok && cuda_ok(cudaEventRecord(eng->ev_h2d[1], s_in), "event");
     if (!ok) return FPB_ERR_CUDA;
     stamp("copies enqueued");
     FitParams p;
@@ -1204,6 +1232,12 @@ int32_t fit_slice_wavefront(fpb_engine *eng, long long b0, long long b1, FP_SIZE
     eng->launches++;
     if (!ok) return FPB_ERR_CUDA;
     stamp("fit done, n/fp/ier/offsets on host");
+    if (trace) {   // what the copy stream achieved (all chunks have landed: the pipeline consumed them)
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, eng->ev_h2d[0], eng->ev_h2d[1]) == cudaSuccess && ms > 0.f)
+            std::fprintf(stderr, "[fpb wavefront %p] copy stream: %.2f ms, %.1f GB/s\n", (void *)eng, ms,
+                         (double)total * m * 8.0 * (w ? 3 : 2) / (ms * 1e-3) / 1e9);
+    }
     const long long *off = eng->h_off[0];
     long long dense = 0;
     for (long long b = 0; b < total; ++b)
@@ -1228,11 +1262,9 @@ int32_t fit_slice_wavefront(fpb_engine *eng, long long b0, long long b1, FP_SIZE
             ok = ok && cuda_ok(cudaEventRecord(evp[q], st), "event");
         }
         if (!ok) return FPB_ERR_CUDA;
-        // helper threads: one per core this rank may fairly claim (cores / visible GPUs), 2..16; they take blocks of
-        // 2048 curves in order from a shared counter, so all of them work on the pieces that landed first
-        int ndev = 1;
-        cudaGetDeviceCount(&ndev);
-        int nthr = (int)std::thread::hardware_concurrency() / std::max(1, ndev);
+        // helper threads: one per core this slice may fairly claim (cores / host_sharers()), 2..16; they take blocks
+        // of 2048 curves in order from a shared counter, so all of them work on the pieces that landed first
+        int nthr = (int)std::thread::hardware_concurrency() / host_sharers();
         nthr = std::max(2, std::min(16, nthr));
         if (const char *e = std::getenv("FPB_HOST_SCATTER_THREADS")) nthr = std::max(1, std::min(32, std::atoi(e)));
         std::vector<std::thread> th;
@@ -1292,7 +1324,9 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     {
         static const bool force_workers = std::getenv("FPB_HOST_MODE") && std::strcmp(std::getenv("FPB_HOST_MODE"), "workers") == 0;
         const size_t per_curve_w = (size_t)m * 8 * 2 * (w ? 3 : 2) + (size_t)nest * 8 * 4 + 64;   // slice-wide device bytes per curve
-        if (!force_workers && iopt == 0 && !shared_x && !fpint && !nrdata && total >= 4 * 65536 &&
+        static const bool force_wave = std::getenv("FPB_HOST_MODE") && std::strcmp(std::getenv("FPB_HOST_MODE"), "wave") == 0;
+        const bool host_bound = !force_wave && host_sharers() > 4;   // see host_sharers()
+        if (!force_workers && !host_bound && iopt == 0 && !shared_x && !fpint && !nrdata && total >= 4 * 65536 &&
             total <= 0x3fffffff && (size_t)total * per_curve_w <= ((size_t)40 << 30))
             return fit_slice_wavefront(e0, b0, b1, m, x, y, w, xb, xe, k, s, nest, n, t, c, fp, ier);
     }
@@ -1434,6 +1468,7 @@ template <class F> int32_t shard_over_gpus(long long total, int ngpus, long long
     std::vector<std::thread> th;
     long long per = (total + ngpus - 1) / ngpus;
     per = (per + align - 1) / align * align;
+    g_slices_in_flight.fetch_add(ngpus);   // before any slice decides how much of the host it may claim
     for (int d = 0; d < ngpus; ++d) {
         const long long b0 = std::min(total, per * d), b1 = std::min(total, per * (d + 1));
         th.emplace_back([&, d, b0, b1]() {
@@ -1450,6 +1485,7 @@ template <class F> int32_t shard_over_gpus(long long total, int ngpus, long long
         });
     }
     for (auto &t : th) t.join();
+    g_slices_in_flight.fetch_sub(ngpus);
     for (int d = 0; d < ngpus; ++d)
         if (rc[d] != FPB_STATUS_OK) {
             set_last_error(err[d]);

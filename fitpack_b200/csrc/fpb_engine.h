@@ -51,6 +51,7 @@ struct fpb_engine {
     long long *h_off[2] = {nullptr, nullptr};
     size_t h_off_bytes[2] = {0, 0};
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};   // timing of the copy stream (wavefront host path)
     std::vector<cudaEvent_t> ev_chunk;   // wavefront host path: one 'chunk has landed' event per chunk
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_fit[2] = {nullptr, nullptr};
     double h_aux[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
