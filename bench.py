@@ -438,9 +438,12 @@ def main():
             e2e_step()       # first call and may switch from the wavefront to the chunk-per-engine form on the next)
         esteps = max(1, args.steps)     # timed over the same number of steps as `value`
         barrier()
+        step_ms = []
         t0 = time.perf_counter()
         for _ in range(esteps):
-            e2e_step()
+            ts = time.perf_counter()
+            e2e_step()           # returns with the results in the caller's host arrays
+            step_ms.append(1e3 * (time.perf_counter() - ts))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt = max_over_ranks(dt)
@@ -456,6 +459,8 @@ def main():
                # n, fp, ier, dense offsets per curve + the dense t(1:n), c(1:n) of every curve
                "d2h_bytes_per_step": int(Be * 24 + 2 * nsum * 8),
                "steps": esteps, "ms_per_step": 1e3 * dt / esteps,
+               "ms_per_step_min_median_max_rank0": [round(min(step_ms), 2), round(sorted(step_ms)[len(step_ms) // 2], 2),
+                                                    round(max(step_ms), 2)],
                "api": "fp_curfit_batch_c (host pointers, pinned)"}
         del xh, yh, th, ch
 
