@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cfloat>
+#include <cmath>
 #include <cstdlib>
 #include <chrono>
 #include <cstdio>
@@ -1307,6 +1309,132 @@ int32_t fit_slice_wavefront(fpb_engine *eng, long long b0, long long b1, FP_SIZE
 // pieces dealt round-robin to `workers` host threads, each with its own engine (stream, workspace,
 // staging): the copies of one chunk and the sparsely populated tail of its fit overlap the other workers'
 // compute.  FPB_HOST_WORKERS (1..4) / FPB_HOST_CHUNKS override the defaults.
+// batch of one from host memory: warp-per-curve kernel (1) or the batch kernels (0); fpb_set_single_curve_kernel
+std::atomic<int> g_solo_on{(std::getenv("FPB_SOLO") && std::atoi(std::getenv("FPB_SOLO")) == 0) ? 0 : 1};
+
+// fpchec, core:2507-2570 (host form: the flat entry point has the knots and abscissae in host memory)
+int host_fpchec(const double *x, int m, const double *t, int n, int k)
+{
+    auto X = [&](int i) { return x[i - 1]; };
+    auto T = [&](int i) { return t[i - 1]; };
+    const int k1 = k + 1, k2 = k1 + 1, nk1 = n - k1, nk2 = nk1 + 1;
+    if (nk1 < k1 || nk1 > m) return FPB_INPUT_ERROR;
+    int j = n;
+    for (int i = 1; i <= k; ++i) {
+        if (T(i) > T(i + 1)) return FPB_INPUT_ERROR;
+        if (T(j) < T(j - 1)) return FPB_INPUT_ERROR;
+        --j;
+    }
+    for (int i = k2; i <= nk2; ++i)
+        if (T(i) <= T(i - 1)) return FPB_INPUT_ERROR;
+    if (X(1) < T(k1) || X(m) > T(nk2)) return FPB_INPUT_ERROR;
+    if (X(1) >= T(k2) || X(m) <= T(nk1)) return FPB_INPUT_ERROR;
+    int i = 1, l = k2;
+    const int nk3 = nk1 - 1;
+    for (j = 2; j <= nk3; ++j) {
+        const double tj = T(j);
+        ++l;
+        const double tl = T(l);
+        while (i < m && X(i) <= tj) {
+            ++i;
+            if (i >= m) return FPB_INPUT_ERROR;
+        }
+        if (X(i) >= tl) return FPB_INPUT_ERROR;
+    }
+    return FPB_OK;
+}
+
+// ONE curve from host memory (fp_curfit_c and, through it, the handle API): curfit's data checks (core:1265-1285) on
+// the host, where the data is; one H2D of a packed block, curfit_solo_kernel (one warp, fpb_curfit_solo.cu), one D2H.
+// Returns false when the curve does not fit the kernel's shared memory (the caller then takes the batch path).
+bool fit_solo_host(fpb_engine *eng, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y, const FP_REAL *w,
+                   FP_REAL xb, FP_REAL xe, FP_SIZE k, FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c,
+                   FP_REAL *fp, FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata, int32_t *status)
+{
+    if (!g_solo_on.load() || solo_smem_bytes(m, k, nest) > kSoloSmemMax) return false;
+    if (iopt == 1 && (!fpint || !nrdata)) return false;
+    *status = FPB_STATUS_OK;
+    const int k1 = k + 1, nmin = 2 * k1, nmax = m + k1;
+    // ---- curfit's checks on the data, core:1271-1285 ----
+    *ier = FPB_INPUT_ERROR;
+    if (xb > x[0] || xe < x[m - 1]) return true;
+    for (int i = 0; i + 1 < m; ++i)
+        if (x[i] > x[i + 1]) return true;
+    int n_in = 0;
+    if (iopt >= 0) {
+        if (s < 0.0 || (std::fabs(s) < DBL_MIN && nest < m + k1)) return true;
+        if (iopt == 1) {
+            n_in = *n;
+            if (!(n_in >= nmin && n_in <= nest && n_in <= nmax)) n_in = nmin;   // garbage n: a fresh start
+        }
+    } else {
+        n_in = *n;
+        if (n_in < nmin || n_in > nest) return true;
+        for (int i = 0, j = n_in - 1; i < k1; ++i, --j) {   // visible to the caller even if fpchec fails (core:1278-1284)
+            t[i] = xb;
+            t[j] = xe;
+        }
+        const int chk = host_fpchec(x, m, t, n_in, k);
+        if (chk != FPB_OK) {
+            *ier = chk;
+            return true;
+        }
+    }
+    // ---- packed block: x y w | t c fpint fp | nrdata n ier ----
+    const size_t od_t = (size_t)3 * m, od_c = od_t + nest, od_f = od_c + nest, od_fp = od_f + nest, nd = od_fp + 1;
+    const size_t bytes = nd * 8 + ((size_t)nest + 2) * 4 + 8;
+    DeviceGuard g(eng->device);
+    auto fail = [&](int32_t rc) {
+        *status = rc;
+        *ier = rc;
+        return true;
+    };
+    if (!g.ok) return fail(FPB_ERR_CUDA);
+    if (!eng->scratch[0].reserve(bytes) || !reserve_pinned((void **)&eng->h_solo, &eng->h_solo_bytes, bytes))
+        return fail(FPB_ERR_ALLOC);
+    double *hd = eng->h_solo, *dd = eng->scratch[0].as<double>();
+    int *hi = reinterpret_cast<int *>(hd + nd), *di = reinterpret_cast<int *>(dd + nd);
+    std::memcpy(hd, x, (size_t)m * 8);
+    std::memcpy(hd + m, y, (size_t)m * 8);
+    if (w) std::memcpy(hd + 2 * (size_t)m, w, (size_t)m * 8);
+    else std::fill(hd + 2 * (size_t)m, hd + 3 * (size_t)m, 1.0);
+    if (iopt != 0) std::memcpy(hd + od_t, t, (size_t)n_in * 8);
+    if (iopt == 1) {
+        std::memcpy(hd + od_f, fpint, (size_t)n_in * 8);
+        std::memcpy(hi, nrdata, (size_t)n_in * 4);
+    }
+    hd[od_fp] = *fp;
+    hi[nest] = n_in;
+    hi[nest + 1] = 0;
+    cudaStream_t st = eng->stream;
+    SoloParams p;
+    p.nbatch = 1; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest;
+    p.xb = xb; p.xe = xe; p.s = s;
+    p.x = dd; p.y = dd + m; p.w = dd + 2 * (size_t)m;
+    p.t = dd + od_t; p.c = dd + od_c; p.fpint = dd + od_f; p.fp = dd + od_fp;
+    p.nrdata = di; p.n = di + nest; p.ier = di + nest + 1;
+    bool ok = cuda_ok(cudaMemcpyAsync(dd, hd, bytes, cudaMemcpyHostToDevice, st), "H2D curve") &&
+              cuda_ok(launch_curfit_solo(p, st), "curfit_solo_kernel") &&
+              cuda_ok(cudaMemcpyAsync(hd + od_t, dd + od_t, bytes - od_t * 8, cudaMemcpyDeviceToHost, st), "D2H fit") &&
+              cuda_ok(cudaStreamSynchronize(st), "sync");
+    eng->launches++;
+    if (!ok) return fail(FPB_ERR_CUDA);
+    const int n_out = hi[nest], ier_out = hi[nest + 1];
+    *n = n_out;
+    *ier = ier_out;
+    const bool untouched = (ier_out == FPB_INSUFFICIENT_STORAGE && iopt >= 0 && s <= 0.0 && nmax > nest);
+    if (!untouched) {
+        *fp = hd[od_fp];
+        if (n_out >= nmin && n_out <= nest) {
+            std::memcpy(t, hd + od_t, (size_t)n_out * 8);
+            std::memcpy(c, hd + od_c, (size_t)(n_out - k1) * 8);
+            if (fpint) std::memcpy(fpint, hd + od_f, (size_t)n_out * 8);
+            if (nrdata) std::memcpy(nrdata, hi, (size_t)n_out * 4);
+        }
+    }
+    return true;
+}
+
 int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_SIZE m,
                        const FP_REAL *x, const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x,
                        const FP_REAL *xb, const FP_REAL *xe, FP_SIZE k, FP_REAL s, FP_SIZE nest,
@@ -1319,6 +1447,15 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     fpb_engine *e0 = default_engine(device);
     if (!e0) return FPB_ERR_CUDA;
     const long long total = b1 - b0;
+    if (total == 1 && !shared_x && m >= 1) {   // a batch of one: the warp-per-curve kernel (latency, not throughput)
+        int32_t status = FPB_STATUS_OK;
+        const double xbv = xb ? *xb : x[(size_t)b0 * m], xev = xe ? *xe : x[(size_t)b0 * m + m - 1];
+        if (fit_solo_host(e0, iopt, m, x + (size_t)b0 * m, y + (size_t)b0 * m, w ? w + (size_t)b0 * m : nullptr, xbv, xev,
+                          k, s, nest, n + b0, t + (size_t)b0 * nest, c + (size_t)b0 * nest, fp + b0, ier + b0,
+                          fpint ? fpint + (size_t)b0 * nest : nullptr, nrdata ? nrdata + (size_t)b0 * nest : nullptr,
+                          &status))
+            return status;
+    }
     // large fresh fits: one pipeline over the slice, chunks joining as they arrive (FPB_HOST_MODE=workers: the
     // chunk-per-engine form below)
     {
@@ -1505,6 +1642,9 @@ int32_t shard_units_over_gpus(long long total, int ngpus, long long align,
 }  // namespace fpb
 
 extern "C" {
+
+int32_t fpb_set_single_curve_kernel(int32_t on) { return g_solo_on.exchange(on ? 1 : 0); }
+
 
 int32_t fp_curfit_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x,
                           const FP_REAL *y, const FP_REAL *w, FP_SIZE shared_x, const FP_REAL *xb,

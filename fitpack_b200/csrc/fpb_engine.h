@@ -55,6 +55,8 @@ struct fpb_engine {
     std::vector<cudaEvent_t> ev_chunk;   // wavefront host path: one 'chunk has landed' event per chunk
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_fit[2] = {nullptr, nullptr};
     double h_aux[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    double *h_solo = nullptr;         // pinned staging of the single-curve fit (fp_curfit_c)
+    size_t h_solo_bytes = 0;
     // gridded surfaces (fpb_regrid.cu): device tables, pinned read-back of the row/column sums
     fpb::DevBuf grid[16];
     double *grid_pinned = nullptr;

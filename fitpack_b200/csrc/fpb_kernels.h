@@ -185,6 +185,22 @@ cudaError_t launch_fill_i32(int *dst, int value, long long count, cudaStream_t s
 cudaError_t launch_pack_tc(int nb, int nest, int k, const int *n, const int *ier, const double *t, const double *c,
                            unsigned long long *cursor, long long *off, double *tp, double *cp, int nsm,
                            cudaStream_t stream);
+// ---- single-curve fit, one warp per curve (fpb_curfit_solo.cu) ----
+struct SoloParams {
+    int nbatch, iopt, m, k, nest;
+    double xb, xe, s;
+    const double *x, *y, *w;   // [nbatch][m]
+    int *n;                    // [nbatch]        in (iopt != 0) / out
+    double *t, *c;             // [nbatch][nest]  in (iopt != 0: t) / out
+    double *fp;                // [nbatch]        in / out (left alone when nothing was computed)
+    int *ier;                  // [nbatch]        out
+    double *fpint;             // [nbatch][nest]  in (iopt = 1) / out
+    int *nrdata;               // [nbatch][nest]  in (iopt = 1) / out
+};
+size_t solo_smem_bytes(int m, int k, int nest);
+constexpr size_t kSoloSmemMax = 200 * 1024;
+cudaError_t launch_curfit_solo(const SoloParams &p, cudaStream_t stream);
+
 cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused, cudaStream_t stream);
 cudaError_t launch_fastmath_selftest(unsigned long long seed, int blocks, int iters, unsigned long long *mismatch,
                                      cudaStream_t stream);

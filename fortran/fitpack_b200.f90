@@ -261,6 +261,11 @@ module fitpack_b200
          type(c_ptr), value :: eng
          integer(c_int32_t), value :: mode
       end function fpb_engine_set_curev_mode
+      ! batch of one from host memory: 1 warp-per-curve kernel (default), 0 batch kernels; returns the previous setting
+      integer(c_int32_t) function fpb_set_single_curve_kernel(on) bind(C,name="fpb_set_single_curve_kernel")
+         import :: c_int32_t
+         integer(c_int32_t), value :: on
+      end function fpb_set_single_curve_kernel
       integer(c_int32_t) function fpb_engine_set_bispev_mode(eng,mode) bind(C,name="fpb_engine_set_bispev_mode")
          import :: c_ptr, c_int32_t
          type(c_ptr), value :: eng

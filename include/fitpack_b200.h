@@ -166,6 +166,12 @@ int32_t fpb_engine_set_bispev_mode(fpb_engine *eng, int32_t mode);
 #define FPB_CUREV_EXACT 0
 #define FPB_CUREV_FAST  1
 int32_t fpb_engine_set_curev_mode(fpb_engine *eng, int32_t mode);
+/* Which kernels a batch of ONE curve from host memory runs on (fp_curfit_c, the fitpack_curve_c_* handle functions,
+   fp_curfit_batch_c with nbatch = 1): 1 (default) the warp-per-curve kernel -- one warp shares the curve, the two
+   band-QR sweeps of fpcurf run as a wavefront over lane groups (fitpack_b200/csrc/fpb_curfit_solo.cu), ~10x lower
+   latency; 0 the batch kernels with one thread per curve.  Same bits either way.  Process-wide; returns the
+   previous setting (the environment variable FPB_SOLO=0 sets the initial one). */
+int32_t fpb_set_single_curve_kernel(int32_t on);
 /* number of kernels this engine has launched since creation (bench bookkeeping) */
 int64_t fpb_engine_launch_count(const fpb_engine *eng);
 /* same counter for the DEFAULT engine of `device` -- the one the host-pointer entry points
