@@ -41,21 +41,22 @@ template <int K> struct SoloCfg {
     static constexpr int G_S = 32 / LG_S;
 };
 
-// fpback core:1808-1838 on lane 0 (row-major band matrix, BAND columns)
+// fpback core:1808-1838 on lane 0.  mat: rows of BAND band entries followed by the right-hand side (row length BAND + 1)
 template <int BAND>
-__device__ __forceinline__ void back_subst_solo(const double *mat, const double *zv, double *cv, int nk1, int lane)
+__device__ __forceinline__ void back_subst_solo(const double *mat, double *cv, int nk1, int lane)
 {
+    constexpr int LD = BAND + 1;
     if (lane == 0) {
         double cw[BAND - 1];
 #pragma unroll
         for (int q = 0; q < BAND - 1; ++q) cw[q] = 0.0;
         for (int i = nk1; i >= 1; --i) {
-            double store = zv[i - 1];
+            double store = mat[(i - 1) * LD + BAND];
             const int cnt = min(nk1 - i, BAND - 1);
 #pragma unroll
             for (int q = 1; q <= BAND - 1; ++q)
-                if (q <= cnt) store = sub(store, mul(cw[q - 1], mat[(i - 1) * BAND + q]));
-            const double ci = store / mat[(i - 1) * BAND];
+                if (q <= cnt) store = sub(store, mul(cw[q - 1], mat[(i - 1) * LD + q]));
+            const double ci = store / mat[(i - 1) * LD];
             cv[i - 1] = ci;
 #pragma unroll
             for (int q = BAND - 2; q >= 1; --q) cw[q] = cw[q - 1];
@@ -74,17 +75,16 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
     const int lane = threadIdx.x, b = blockIdx.x;
     const int m = p.m, nest = p.nest, iopt = p.iopt;
     double *xs = sm, *ys = xs + m, *ws = ys + m, *res = ws + m, *qs = res + m;
-    double *ts = qs + (size_t)m * K1, *cc = ts + nest, *zz = cc + nest, *fpi = zz + nest;
-    double *as = fpi + nest, *gs = as + (size_t)nest * K1, *bs = gs + (size_t)nest * K2;
+    double *ts = qs + (size_t)m * K1, *cc = ts + nest, *fpi = cc + nest;
+    // band matrices with their right-hand sides as one more column: (R | z) rows of K1 + 1, (G | c) rows of K2 + 1
+    double *as = fpi + nest, *gs = as + (size_t)nest * (K1 + 1), *bs = gs + (size_t)nest * (K2 + 1);
     double *hw = bs + (size_t)nest * K2;   // [m][K1 + 1]: the weighted data rows w * (basis values | y)
     int *lidx = reinterpret_cast<int *>(hw + (size_t)m * (K1 + 1)), *llag = lidx + m, *nrd = llag + m, *sst = nrd + nest;
 #define T_(i) ts[(i) - 1]
 #define C_(i) cc[(i) - 1]
-#define Z_(i) zz[(i) - 1]
 #define FPI_(i) fpi[(i) - 1]
 #define NRD_(i) nrd[(i) - 1]
-#define A_(i, j) as[((i) - 1) * K1 + ((j) - 1)]
-#define G_(i, j) gs[((i) - 1) * K2 + ((j) - 1)]
+#define A_(i, j) as[((i) - 1) * (K1 + 1) + ((j) - 1)]
 #define B_(i, j) bs[((i) - 1) * K2 + ((j) - 1)]
 
     {
@@ -167,8 +167,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             ts[lane] = xb;
             ts[nk1 + lane] = xe;
         }
-        for (int i = lane; i < nk1; i += 32) zz[i] = 0.0;
-        for (int i = lane; i < nk1 * K1; i += 32) as[i] = 0.0;
+        for (int i = lane; i < nk1 * (K1 + 1); i += 32) as[i] = 0.0;
         __syncwarp();
         // knot interval and B-spline values of every point, one point per lane (core:4876-4885)
         for (int it = lane; it < m; it += 32) {
@@ -210,46 +209,56 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             }
         }
         // ---- data rows into (R, z) as a wavefront (core:4873-4896) ----
+        // The tick is straight-line code: every load is unconditional (idle lanes read band row 1), the rotation is
+        // computed by every lane (idle lanes rotate (1, 1)), only the stores are predicated, and the row after the
+        // group's next one is fetched at the top of the tick, so no lane waits on shared memory when rows change.
         {
-            constexpr int LG = Cfg::LG_D, G = Cfg::G_D, ST = Cfg::ST_D;
+            constexpr int LG = Cfg::LG_D, G = Cfg::G_D, ST = Cfg::ST_D, NEVER = INT_MAX / 2;
             const int grp = lane / LG, sub_ = lane - grp * LG;
             const bool member = grp < G, isrhs = sub_ == K1;
             const int base = member ? grp * LG : 0;
-            int row = member ? grp : m, first = 0, start = 0;
-            double hv = 0.0;
-            auto load_row = [&]() {
-                if (row < m) {
-                    first = lidx[row] - K;
-                    start = row * ST + first;
-                    hv = hw[row * LG + sub_];
-                }
-            };
-            load_row();
+            int row = member ? grp : NEVER, first = 0, start = NEVER, first_n = 0;
+            double hv = 0.0, hv_n = 0.0;
+            if (row < m) {
+                first = lidx[row] - K;
+                start = row * ST + first;
+                hv = hw[row * LG + sub_];
+            }
+            if (member && row + G < m) {
+                first_n = lidx[row + G] - K;
+                hv_n = hw[(row + G) * LG + sub_];
+            }
             const int tau_end = (m - 1) * ST + lidx[m - 1];
             for (int tau = lidx[0] - K; tau <= tau_end; ++tau) {
+                // the row two ahead (the next one is in first_n, hv_n)
+                const int r2 = min(row, m) + 2 * G < m ? row + 2 * G : m - 1;
+                const int first_2 = lidx[r2] - K;
+                const double hv_2 = hw[r2 * LG + sub_];
                 const int i0 = tau - start;                    // the row's entry that is the pivot now
-                const bool act = member && row < m && i0 >= 0;
-                const int j = first + i0;                      // band row it meets
-                const double piv = __shfl_sync(FULL, hv, base + (act ? i0 : 0));
-                const int q = sub_ - i0;                       // 0: the pivot's lane, > 0: a column to its right
-                const bool pivlane = !isrhs && q == 0;
-                const bool touch = act && (isrhs || q >= 0);
-                double *tgt = isrhs ? &zz[j - 1] : &as[(j - 1) * K1 + (q > 0 ? q : 0)];
+                const bool act = (unsigned)i0 <= (unsigned)K;
+                const int i0c = act ? i0 : 0;
+                double *rowp = as + (act ? first + i0 - 1 : 0) * LG;   // band row it meets: (R(j, :) | z(j))
+                const int q = sub_ - i0c;                      // 0: the pivot's lane, > 0: a column to its right
+                const int col = isrhs ? K1 : max(q, 0);
+                const double wwl = rowp[0], s2 = rowp[col];
+                const double piv = __shfl_sync(FULL, hv, base + i0c);
                 const bool rot = act && !fp_is_zero(piv);
-                double ww = rot ? as[(j - 1) * K1] : 1.0;
-                const double s2 = touch ? *tgt : 0.0;
-                double cs, sn;
-                givens_fast(rot ? piv : 1.0, ww, cs, sn);      // idle lanes rotate (1, 1): no divergence
+                const bool upd = rot && (isrhs || q >= 0);
+                double ww = rot ? wwl : 1.0, cs, sn;
+                givens_fast(rot ? piv : 1.0, ww, cs, sn);
                 const double nb = add(mul(cs, s2), mul(sn, hv));
                 const double na = sub(mul(cs, hv), mul(sn, s2));
-                if (rot && touch) {
-                    *tgt = pivlane ? ww : nb;
-                    if (!pivlane) hv = na;
-                }
-                if (act && i0 == K) {                          // the row is through: its residual, then the next row
-                    if (isrhs) res[row] = mul(hv, hv);
+                if (upd) rowp[col] = col == 0 ? ww : nb;
+                hv = (upd && col != 0) ? na : hv;
+                const bool fin = act && i0 == K;               // the row is through: its residual, then the next row
+                if (fin && isrhs) res[row] = mul(hv, hv);
+                if (fin) {
                     row += G;
-                    load_row();
+                    first = first_n;
+                    hv = hv_n;
+                    start = row < m ? row * ST + first : NEVER;
+                    first_n = first_2;
+                    hv_n = hv_2;
                 }
                 __syncwarp();
             }
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             FPI_(n) = fp0;
             NRD_(n) = nplus;
         }
-        back_subst_solo<K1>(as, zz, cc, nk1, lane);
+        back_subst_solo<K1>(as, cc, nk1, lane);
         if (iopt < 0) {
             done = true;
             break;
@@ -421,65 +430,73 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             ++it2;
             const double pinv = 1.0 / pp;
             // c := z, g := (a | 0), core:5047-5049
-            for (int i = lane; i < nk1; i += 32) cc[i] = zz[i];
-            for (int i = lane; i < nk1 * K2; i += 32) {
-                const int r = i / K2, q = i - r * K2;
-                gs[i] = q < K1 ? as[r * K1 + q] : 0.0;
+            for (int i = lane; i < nk1 * (K2 + 1); i += 32) {
+                const int r = i / (K2 + 1), q = i - r * (K2 + 1);
+                gs[i] = q < K1 ? as[r * (K1 + 1) + q] : (q == K2 ? as[r * (K1 + 1) + K1] : 0.0);
             }
             __syncwarp();
             // ---- smoothing rows b(it,:)/p into (G, c) as a wavefront (core:5052-5057, fp_rotate_shifted 5800-5820) ----
             {
-                constexpr int LG = Cfg::LG_S, G = Cfg::G_S;
+                constexpr int LG = Cfg::LG_S, G = Cfg::G_S, NEVER = INT_MAX / 2;
                 const int grp = lane / LG, sub_ = lane - grp * LG;
                 const bool member = grp < G, isrhs = sub_ == K2;
                 const int base = member ? grp * LG : 0;
+                const int bcol = isrhs ? 0 : sub_;               // column of b this lane reads
                 // lane sub_ < K2 holds the row's entry of band column `col`; the pivot's lane then takes the column
                 // that enters the band with value 0 (the reference shifts the row left instead)
-                int row = member ? grp : n8, start = 0, col = 0;
-                double hv = 0.0;
-                auto load_row = [&]() {
-                    if (row < n8) {
-                        start = sst[row];
-                        col = row + 1 + sub_;
-                        hv = isrhs ? 0.0 : mul(B_(row + 1, sub_ + 1), pinv);
-                    }
-                };
-                load_row();
+                int row = member ? grp : NEVER, start = NEVER, start_n = NEVER, col = 0;
+                double hv = 0.0, hv_n = 0.0;
+                if (row < n8) {
+                    start = sst[row];
+                    col = row + 1 + sub_;
+                    hv = isrhs ? 0.0 : mul(bs[row * K2 + bcol], pinv);
+                }
+                if (member && row + G < n8) {
+                    start_n = sst[row + G];
+                    hv_n = isrhs ? 0.0 : mul(bs[(row + G) * K2 + bcol], pinv);
+                }
                 const int tau_end = sst[n8 - 1] + nk1 - n8;
                 for (int tau = 0; tau <= tau_end; ++tau) {
+                    const bool has2 = min(row, n8) + 2 * G < n8;
+                    const int r2 = has2 ? row + 2 * G : n8 - 1;
+                    const int start_2 = has2 ? sst[r2] : NEVER;
+                    const double hb_2 = bs[r2 * K2 + bcol];
                     const int d0 = tau - start;
-                    const bool act = member && row < n8 && d0 >= 0;
-                    const int j = row + 1 + d0;                  // band row the row meets now
+                    const bool act = d0 >= 0;                    // start = NEVER once the group has no row left
+                    const int j = act ? row + 1 + d0 : 1;        // band row the row meets now
+                    double *rowp = gs + (j - 1) * LG;            // (G(j, :) | c(j))
                     const int ps = act ? d0 % K2 : 0;            // lane of the entry in column j
-                    const double piv = __shfl_sync(FULL, hv, base + ps);
                     const int noff = min(nk1 - j, K2 - 1);
                     const int dc = col - j;
                     const bool pivlane = !isrhs && sub_ == ps;
-                    const bool touch = act && (isrhs || pivlane || (dc >= 1 && dc <= noff));
-                    double *tgt = isrhs ? &cc[j - 1] : &gs[(j - 1) * K2 + (pivlane ? 0 : dc)];
+                    const bool mine = isrhs || pivlane || (dc >= 1 && dc <= noff);
+                    const int tc = isrhs ? K2 : (mine && !pivlane ? dc : 0);
+                    const double wwl = rowp[0], s2 = rowp[tc];
+                    const double piv = __shfl_sync(FULL, hv, base + ps);
                     const bool rot = act && !fp_is_zero(piv);
-                    double ww = rot ? gs[(j - 1) * K2] : 1.0;
-                    const double s2 = touch ? *tgt : 0.0;
-                    double cs, sn;
+                    const bool upd = rot && mine;
+                    double ww = rot ? wwl : 1.0, cs, sn;
                     givens_fast(rot ? piv : 1.0, ww, cs, sn);
                     const double nb = add(mul(cs, s2), mul(sn, hv));
                     const double na = sub(mul(cs, hv), mul(sn, s2));
-                    if (rot && touch) {
-                        *tgt = pivlane ? ww : nb;
-                        if (!pivlane) hv = na;
-                    }
+                    if (upd) rowp[tc] = pivlane ? ww : nb;
+                    hv = (upd && !pivlane) ? na : hv;
                     if (act && pivlane) {
                         hv = 0.0;
                         col = j + K2;
                     }
                     if (act && j == nk1) {
                         row += G;
-                        load_row();
+                        start = row < n8 ? start_n : NEVER;
+                        hv = hv_n;
+                        col = row + 1 + sub_;
+                        start_n = start_2;
+                        hv_n = isrhs ? 0.0 : mul(hb_2, pinv);
                     }
                     __syncwarp();
                 }
             }
-            back_subst_solo<K2>(gs, cc, cc, nk1, lane);
+            back_subst_solo<K2>(gs, cc, nk1, lane);
             // fp = sum of squared residuals in point order, core:5061-5069
             for (int it = lane; it < m; it += 32) {
                 const int l0 = llag[it] - K2;
@@ -565,11 +582,9 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
     }
 #undef T_
 #undef C_
-#undef Z_
 #undef FPI_
 #undef NRD_
 #undef A_
-#undef G_
 #undef B_
 }
 
@@ -578,7 +593,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
 size_t solo_smem_bytes(int m, int k, int nest)
 {
     const size_t k1 = k + 1, k2 = k + 2;
-    const size_t doubles = (size_t)m * (4 + k1 + k1 + 1) + (size_t)nest * (4 + k1 + 2 * k2);
+    const size_t doubles = (size_t)m * (4 + k1 + k1 + 1) + (size_t)nest * (3 + (k1 + 1) + (k2 + 1) + k2);
     return doubles * 8 + ((size_t)2 * m + 2 * (size_t)nest) * 4;
 }
 
