@@ -1,0 +1,153 @@
+"""The warp-per-curve kernel behind fp_curfit_c / the handle API (fitpack_b200/csrc/fpb_curfit_solo.cu) against the
+CPU oracle -- n, knots, ier, c, fp and the continuation state bit for bit -- and the same calls through the batch
+kernels (fpb_set_single_curve_kernel(0)), so that both implementations keep replaying the reference's flat-ABI tests
+(mncurf test/fitpack_tests.f90:1138-1269, the golden vectors, the deviation cases, the handle API)."""
+import contextlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import test_gpu_deviations
+import test_gpu_parity
+from test_gpu_parity import F, _same  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+@contextlib.contextmanager
+def single_curve_kernel(Fm, on):
+    prev = Fm.lib().fpb_set_single_curve_kernel(1 if on else 0)
+    try:
+        yield
+    finally:
+        Fm.lib().fpb_set_single_curve_kernel(prev)
+
+
+def _check(o, g, k):
+    assert (g["n"], g["ier"]) == (o["n"], o["ier"])
+    if o["ier"] == 10:
+        return
+    n = int(o["n"])
+    assert g["fp"] == o["fp"]
+    assert _same(g["t"][:n], o["t"][:n]) and _same(g["c"][:n - k - 1], o["c"][:n - k - 1])
+
+
+def test_default_is_the_warp_per_curve_kernel(F):
+    assert F.lib().fpb_set_single_curve_kernel(1) == 1
+
+
+@pytest.mark.parametrize("name", ["test_mncurf_sequence_bit_exact", "test_curfit_golden_vectors_bit_exact",
+                                  "test_curfit_input_errors_leave_outputs_untouched", "test_curve_handle_api"])
+def test_flat_abi_tests_also_pass_on_the_batch_kernels(F, name):
+    """the tests of test_gpu_parity run on the warp-per-curve kernel by default; here on one thread per curve"""
+    with single_curve_kernel(F, False):
+        getattr(test_gpu_parity, name)(F)
+
+
+def test_deviation_cases_on_both_kernels(F):
+    names = [n for n in dir(test_gpu_deviations) if n.startswith("test_")]
+    assert names
+    for on in (True, False):
+        with single_curve_kernel(F, on):
+            for n in names:
+                getattr(test_gpu_deviations, n)(F)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_random_fits_continuations_and_given_knots_bit_exact(F, k):
+    """iopt = 0, then iopt = 1 with a smaller s on the returned state, then iopt = -1 on the knots found; weights
+    with zeros (skipped rotations), s = 0 (interpolation), s so large that the polynomial is accepted, small nest
+    (ier = 1), m down to 2k+2."""
+    rng = np.random.default_rng(1000 + k)
+    for trial in range(60):
+        m = int(rng.integers(2 * k + 2, 330))
+        x = np.sort(rng.uniform(0, 1, m))
+        x[0], x[-1] = 0.0, 1.0
+        y = np.sin(2 * np.pi * rng.uniform(0.5, 5) * x) + 0.05 * rng.standard_normal(m)
+        w = rng.uniform(0.5, 2.0, m) if trial % 3 else np.ones(m)
+        if trial % 11 == 0:
+            w[rng.integers(0, m)] = 0.0
+        s = float(m * 0.0025 * rng.choice([0.0, 0.03, 0.3, 1.0, 3.0, 3000.0]))
+        nest = int(rng.choice([m + k + 1, max(2 * k + 2, m // 2), max(102, int(np.ceil(1.4 * m)))]))
+        o = O.curfit(0, x, y, w, 0.0, 1.0, k, s, nest)
+        g = F.curfit(0, x, y, w, 0.0, 1.0, k, s, nest)
+        _check(o, g, k)
+        if o["ier"] > 0 or s == 0.0:
+            continue
+        n = int(o["n"])
+        nrint = n - 2 * (k + 1) + 1
+        assert _same(g["wrk"][n - 2:n], o["wrk"][n - 2:n]) and _same(g["iwrk"][:nrint], o["iwrk"][:nrint])
+        assert g["iwrk"][n - 1] == o["iwrk"][n - 1]
+        s2 = s * 0.4
+        o1 = O.curfit(1, x, y, w, 0.0, 1.0, k, s2, nest, n=o["n"], t=o["t"], c=o["c"], fp=o["fp"], wrk=o["wrk"],
+                      iwrk=o["iwrk"])
+        g1 = F.curfit(1, x, y, w, 0.0, 1.0, k, s2, nest, n=g["n"], t=g["t"], c=g["c"], fp=g["fp"], wrk=g["wrk"],
+                      iwrk=g["iwrk"])
+        _check(o1, g1, k)
+        o2 = O.curfit(-1, x, y, w, 0.0, 1.0, k, s2, nest, n=o1["n"], t=o1["t"].copy())
+        g2 = F.curfit(-1, x, y, w, 0.0, 1.0, k, s2, nest, n=g1["n"], t=g1["t"].copy())
+        _check(o2, g2, k)
+
+
+def test_given_knots_rejected_by_fpchec_and_bad_arguments(F):
+    """the data checks of curfit (core:1265-1285) run on the host for a batch of one: same ier, outputs untouched
+    except the clamped end knots (core:1278-1284)"""
+    rng = np.random.default_rng(5)
+    m, k, nest = 40, 3, 50
+    x = np.sort(rng.uniform(0, 1, m))
+    y = rng.standard_normal(m)
+    n = 12
+    for variant in range(4):
+        t = np.zeros(nest)
+        t[k + 1:n - k - 1] = np.linspace(0.1, 0.9, n - 2 * k - 2)
+        if variant == 1:
+            t[k + 2] = t[k + 1]                       # not strictly increasing
+        if variant == 2:
+            t[k + 1:n - k - 1] = x[0] + 1e-9 * np.arange(1, n - 2 * k - 1)   # Schoenberg-Whitney fails
+        if variant == 3:
+            t[k + 1] = 2.0                            # beyond xe
+        to, tg = t.copy(), t.copy()
+        o = O.curfit(-1, x, y, None, x[0], x[-1], k, 0.0, nest, n=n, t=to)
+        c0 = np.full(nest, 7.0)
+        g = F.curfit(-1, x, y, None, x[0], x[-1], k, 0.0, nest, n=n, t=tg, c=c0)
+        assert g["ier"] == o["ier"], variant
+        assert _same(tg[:n], to[:n]), variant
+        if o["ier"] == 10:
+            assert np.all(c0 == 7.0), variant
+        else:
+            _check(o, g, k)
+    for bad in (dict(xb=x[0] + 0.01), dict(xe=x[-1] - 0.01), dict(s=-1.0), dict(s=0.0, nest=m + k)):
+        a = dict(xb=x[0], xe=x[-1], s=1.0, nest=nest)
+        a.update(bad)
+        o = O.curfit(0, x, y, None, a["xb"], a["xe"], k, a["s"], a["nest"])
+        g = F.curfit(0, x, y, None, a["xb"], a["xe"], k, a["s"], a["nest"])
+        assert g["ier"] == o["ier"] == 10, bad
+
+
+def test_curves_too_large_for_shared_memory_take_the_batch_kernels(F):
+    """the warp-per-curve kernel keeps the curve in shared memory (200 KB); beyond that the same call runs on the batch
+    kernels -- same bits"""
+    rng = np.random.default_rng(9)
+    m, k = 3000, 3
+    x = np.sort(rng.uniform(0, 1, m))
+    y = np.sin(9 * x) + 0.1 * rng.standard_normal(m)
+    nest = m + k + 1
+    o = O.curfit(0, x, y, None, x[0], x[-1], k, 30.0, nest)
+    g = F.curfit(0, x, y, None, x[0], x[-1], k, 30.0, nest)
+    _check(o, g, k)
+
+
+def test_batch_entry_point_with_one_curve(F):
+    """fp_curfit_batch_c with nbatch = 1 is the same call pattern"""
+    rng = np.random.default_rng(10)
+    m, k, nest = 200, 3, 204
+    x = np.sort(rng.uniform(0, 1, m))
+    y = np.cos(5 * x) + 0.05 * rng.standard_normal(m)
+    o = O.curfit(0, x, y, None, x[0], x[-1], k, 0.5, nest)
+    for on in (True, False):
+        with single_curve_kernel(F, on):
+            g = F.curfit_batch(0, x[None, :], y[None, :], None, k, 0.5, nest)
+            n = int(o["n"])
+            assert int(g["n"][0]) == n and int(g["ier"][0]) == o["ier"] and g["fp"][0] == o["fp"]
+            assert _same(g["t"][0, :n], o["t"][:n]) and _same(g["c"][0, :n - k - 1], o["c"][:n - k - 1])
