@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             ws[i] = gw[i];
         }
     }
+    if (p.ier[b] != IER_OK) return;   // rejected by the host's data checks (core:1265-1285): nothing is written
     int n = 0;
     if (iopt != 0) {
         n = p.n[b];
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
     __syncwarp();
 
     // scalars: every lane carries the same values (pure scalar arithmetic is simply done 32 times over)
-    const double s = p.s, xb = p.xb, xe = p.xe;
+    const double s = p.s, xb = p.ends_from_x ? xs[0] : p.xb, xe = p.ends_from_x ? xs[m - 1] : p.xe;
     const int nmax = m + K1, nmin = 2 * K1;
     const double acc = mul(kTol, s);
     double fpold = 0.0, fp0 = 0.0, fp = p.fp[b], fpms = DBL_MAX;

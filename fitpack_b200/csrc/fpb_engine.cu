@@ -1344,92 +1344,137 @@ int host_fpchec(const double *x, int m, const double *t, int n, int k)
     return FPB_OK;
 }
 
-// ONE curve from host memory (fp_curfit_c and, through it, the handle API): curfit's data checks (core:1265-1285) on
-// the host, where the data is; one H2D of a packed block, curfit_solo_kernel (one warp, fpb_curfit_solo.cu), one D2H.
-// Returns false when the curve does not fit the kernel's shared memory (the caller then takes the batch path).
-bool fit_solo_host(fpb_engine *eng, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y, const FP_REAL *w,
-                   FP_REAL xb, FP_REAL xe, FP_SIZE k, FP_REAL s, FP_SIZE nest, FP_SIZE *n, FP_REAL *t, FP_REAL *c,
-                   FP_REAL *fp, FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata, int32_t *status)
+// A FEW curves from host memory -- one (fp_curfit_c and, through it, the handle API) up to kSoloMaxBatch
+// (fp_curfit_batch_c) -- on the warp-per-curve kernel (fpb_curfit_solo.cu), one CTA of one warp per curve: where the
+// one-thread-per-curve pipeline would leave the GPU to a handful of threads.  curfit's data checks (core:1265-1285)
+// run on the host, where the data is.  One packed block for a single curve (one H2D, one launch, one D2H); for more,
+// x / y / w go up straight from the caller's arrays.  Returns false when the call is not one for this kernel (too
+// large for its shared memory, shared abscissae, ...): the caller then takes the batch path.
+constexpr long long kSoloMaxBatch = 4096;   // measured: 2048 curves 7.4 ms here, 22 ms on the batch kernels (profiles/r02_solo.md)
+
+bool fit_solo_host(fpb_engine *eng, long long nb, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x, const FP_REAL *y,
+                   const FP_REAL *w, const FP_REAL *xbp, const FP_REAL *xep, FP_SIZE k, FP_REAL s, FP_SIZE nest,
+                   FP_SIZE *n, FP_REAL *t, FP_REAL *c, FP_REAL *fp, FP_FLAG *ier, FP_REAL *fpint, FP_SIZE *nrdata,
+                   int32_t *status)
 {
-    if (!g_solo_on.load() || solo_smem_bytes(m, k, nest) > kSoloSmemMax) return false;
+    if (!g_solo_on.load() || nb < 1 || nb > kSoloMaxBatch || m < 1 || solo_smem_bytes(m, k, nest) > kSoloSmemMax)
+        return false;
     if (iopt == 1 && (!fpint || !nrdata)) return false;
     *status = FPB_STATUS_OK;
     const int k1 = k + 1, nmin = 2 * k1, nmax = m + k1;
-    // ---- curfit's checks on the data, core:1271-1285 ----
-    *ier = FPB_INPUT_ERROR;
-    if (xb > x[0] || xe < x[m - 1]) return true;
-    for (int i = 0; i + 1 < m; ++i)
-        if (x[i] > x[i + 1]) return true;
-    int n_in = 0;
-    if (iopt >= 0) {
-        if (s < 0.0 || (std::fabs(s) < DBL_MIN && nest < m + k1)) return true;
-        if (iopt == 1) {
-            n_in = *n;
-            if (!(n_in >= nmin && n_in <= nest && n_in <= nmax)) n_in = nmin;   // garbage n: a fresh start
-        }
-    } else {
-        n_in = *n;
-        if (n_in < nmin || n_in > nest) return true;
-        for (int i = 0, j = n_in - 1; i < k1; ++i, --j) {   // visible to the caller even if fpchec fails (core:1278-1284)
-            t[i] = xb;
-            t[j] = xe;
-        }
-        const int chk = host_fpchec(x, m, t, n_in, k);
-        if (chk != FPB_OK) {
-            *ier = chk;
-            return true;
-        }
-    }
-    // ---- packed block: x y w | t c fpint fp | nrdata n ier ----
-    const size_t od_t = (size_t)3 * m, od_c = od_t + nest, od_f = od_c + nest, od_fp = od_f + nest, nd = od_fp + 1;
-    const size_t bytes = nd * 8 + ((size_t)nest + 2) * 4 + 8;
+    // ---- packed block, in doubles: x y w | fp n ier | t | c | fpint nrdata ----
+    const size_t pts = (size_t)nb * m, kn = (size_t)nb * nest, half = ((size_t)nb + 1) / 2;
+    const size_t o_fp = 3 * pts, o_n = o_fp + nb, o_ier = o_n + half, o_t = o_ier + half, o_c = o_t + kn,
+                 o_f = o_c + kn, o_nrd = o_f + kn, o_end = o_nrd + (kn + 1) / 2;
     DeviceGuard g(eng->device);
     auto fail = [&](int32_t rc) {
         *status = rc;
-        *ier = rc;
+        for (long long b = 0; b < nb; ++b) ier[b] = rc;
         return true;
     };
     if (!g.ok) return fail(FPB_ERR_CUDA);
-    if (!eng->scratch[0].reserve(bytes) || !reserve_pinned((void **)&eng->h_solo, &eng->h_solo_bytes, bytes))
+    if (!eng->scratch[0].reserve(o_end * 8) || !reserve_pinned((void **)&eng->h_solo, &eng->h_solo_bytes, o_end * 8))
         return fail(FPB_ERR_ALLOC);
     double *hd = eng->h_solo, *dd = eng->scratch[0].as<double>();
-    int *hi = reinterpret_cast<int *>(hd + nd), *di = reinterpret_cast<int *>(dd + nd);
-    std::memcpy(hd, x, (size_t)m * 8);
-    std::memcpy(hd + m, y, (size_t)m * 8);
-    if (w) std::memcpy(hd + 2 * (size_t)m, w, (size_t)m * 8);
-    else std::fill(hd + 2 * (size_t)m, hd + 3 * (size_t)m, 1.0);
-    if (iopt != 0) std::memcpy(hd + od_t, t, (size_t)n_in * 8);
-    if (iopt == 1) {
-        std::memcpy(hd + od_f, fpint, (size_t)n_in * 8);
-        std::memcpy(hi, nrdata, (size_t)n_in * 4);
+    int *hn = reinterpret_cast<int *>(hd + o_n), *hier = reinterpret_cast<int *>(hd + o_ier),
+        *hnrd = reinterpret_cast<int *>(hd + o_nrd);
+    // ---- curfit's checks on the data, core:1271-1285, curve by curve ----
+    long long nbad = 0;
+    for (long long b = 0; b < nb; ++b) {
+        const double *xc = x + (size_t)b * m;
+        const double xb = xbp ? *xbp : xc[0], xe = xep ? *xep : xc[m - 1];
+        bool bad = (xb > xc[0] || xe < xc[m - 1]);
+        for (int i = 0; i + 1 < m && !bad; ++i) bad = xc[i] > xc[i + 1];
+        int n_in = 0;
+        int flag = FPB_OK;
+        if (!bad && iopt >= 0) {
+            bad = s < 0.0 || (std::fabs(s) < DBL_MIN && nest < m + k1);
+            if (iopt == 1) {
+                n_in = n[b];
+                if (!(n_in >= nmin && n_in <= nest && n_in <= nmax)) n_in = nmin;   // garbage n: a fresh start
+            }
+        } else if (!bad) {
+            n_in = n[b];
+            bad = n_in < nmin || n_in > nest;
+            if (!bad) {
+                double *tc = t + (size_t)b * nest;
+                for (int i = 0, j = n_in - 1; i < k1; ++i, --j) {   // visible even if fpchec fails (core:1278-1284)
+                    tc[i] = xb;
+                    tc[j] = xe;
+                }
+                flag = host_fpchec(xc, m, tc, n_in, k);
+            }
+        }
+        if (bad) flag = FPB_INPUT_ERROR;
+        hier[b] = flag;           // a curve that arrives flagged is skipped by the kernel
+        hn[b] = n_in;
+        hd[o_fp + b] = fp[b];
+        if (flag != FPB_OK) ++nbad;
+        if (flag == FPB_OK && iopt != 0) std::memcpy(hd + o_t + (size_t)b * nest, t + (size_t)b * nest, (size_t)n_in * 8);
+        if (flag == FPB_OK && iopt == 1) {
+            std::memcpy(hd + o_f + (size_t)b * nest, fpint + (size_t)b * nest, (size_t)n_in * 8);
+            std::memcpy(hnrd + (size_t)b * nest, nrdata + (size_t)b * nest, (size_t)n_in * 4);
+        }
     }
-    hd[od_fp] = *fp;
-    hi[nest] = n_in;
-    hi[nest + 1] = 0;
+    if (nbad == nb) {   // nothing to fit
+        for (long long b = 0; b < nb; ++b) ier[b] = hier[b];
+        return true;
+    }
     cudaStream_t st = eng->stream;
+    bool ok = true;
+    if (nb == 1) {
+        std::memcpy(hd, x, pts * 8);
+        std::memcpy(hd + pts, y, pts * 8);
+        if (w) std::memcpy(hd + 2 * pts, w, pts * 8);
+        else std::fill(hd + 2 * pts, hd + 3 * pts, 1.0);
+        ok = cuda_ok(cudaMemcpyAsync(dd, hd, (iopt == 1 ? o_end : o_c) * 8, cudaMemcpyHostToDevice, st), "H2D curve");
+    } else {
+        ok = cuda_ok(cudaMemcpyAsync(dd, x, pts * 8, cudaMemcpyHostToDevice, st), "H2D x") &&
+             cuda_ok(cudaMemcpyAsync(dd + pts, y, pts * 8, cudaMemcpyHostToDevice, st), "H2D y");
+        if (w) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(dd + 2 * pts, w, pts * 8, cudaMemcpyHostToDevice, st), "H2D w");
+        } else {
+            std::fill(hd + 2 * pts, hd + 3 * pts, 1.0);
+            ok = ok && cuda_ok(cudaMemcpyAsync(dd + 2 * pts, hd + 2 * pts, pts * 8, cudaMemcpyHostToDevice, st), "H2D w");
+        }
+        ok = ok && cuda_ok(cudaMemcpyAsync(dd + o_fp, hd + o_fp, ((iopt != 0 ? o_c : o_t) - o_fp) * 8,
+                                           cudaMemcpyHostToDevice, st), "H2D state");
+        if (iopt == 1)
+            ok = ok && cuda_ok(cudaMemcpyAsync(dd + o_f, hd + o_f, (o_end - o_f) * 8, cudaMemcpyHostToDevice, st), "H2D state");
+    }
     SoloParams p;
-    p.nbatch = 1; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest;
-    p.xb = xb; p.xe = xe; p.s = s;
-    p.x = dd; p.y = dd + m; p.w = dd + 2 * (size_t)m;
-    p.t = dd + od_t; p.c = dd + od_c; p.fpint = dd + od_f; p.fp = dd + od_fp;
-    p.nrdata = di; p.n = di + nest; p.ier = di + nest + 1;
-    bool ok = cuda_ok(cudaMemcpyAsync(dd, hd, bytes, cudaMemcpyHostToDevice, st), "H2D curve") &&
-              cuda_ok(launch_curfit_solo(p, st), "curfit_solo_kernel") &&
-              cuda_ok(cudaMemcpyAsync(hd + od_t, dd + od_t, bytes - od_t * 8, cudaMemcpyDeviceToHost, st), "D2H fit") &&
-              cuda_ok(cudaStreamSynchronize(st), "sync");
+    p.nbatch = (int)nb; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest;
+    p.xb = xbp ? *xbp : 0.0; p.xe = xep ? *xep : 0.0; p.s = s;
+    p.ends_from_x = (xbp && xep) ? 0 : 1;
+    if (!xbp != !xep) {   // one end given, the other from the data: not a case the batch API produces
+        p.ends_from_x = 0;
+        if (nb != 1) return false;
+        p.xb = xbp ? *xbp : x[0];
+        p.xe = xep ? *xep : x[m - 1];
+    }
+    p.x = dd; p.y = dd + pts; p.w = dd + 2 * pts;
+    p.fp = dd + o_fp; p.n = reinterpret_cast<int *>(dd + o_n); p.ier = reinterpret_cast<int *>(dd + o_ier);
+    p.t = dd + o_t; p.c = dd + o_c; p.fpint = dd + o_f; p.nrdata = reinterpret_cast<int *>(dd + o_nrd);
+    const bool want_state = fpint && nrdata;
+    ok = ok && cuda_ok(launch_curfit_solo(p, st), "curfit_solo_kernel") &&
+         cuda_ok(cudaMemcpyAsync(hd + o_fp, dd + o_fp, ((want_state ? o_end : o_f) - o_fp) * 8, cudaMemcpyDeviceToHost, st),
+                 "D2H fit") &&
+         cuda_ok(cudaStreamSynchronize(st), "sync");
     eng->launches++;
     if (!ok) return fail(FPB_ERR_CUDA);
-    const int n_out = hi[nest], ier_out = hi[nest + 1];
-    *n = n_out;
-    *ier = ier_out;
-    const bool untouched = (ier_out == FPB_INSUFFICIENT_STORAGE && iopt >= 0 && s <= 0.0 && nmax > nest);
-    if (!untouched) {
-        *fp = hd[od_fp];
-        if (n_out >= nmin && n_out <= nest) {
-            std::memcpy(t, hd + od_t, (size_t)n_out * 8);
-            std::memcpy(c, hd + od_c, (size_t)(n_out - k1) * 8);
-            if (fpint) std::memcpy(fpint, hd + od_f, (size_t)n_out * 8);
-            if (nrdata) std::memcpy(nrdata, hi, (size_t)n_out * 4);
+    const bool untouched_all = (iopt >= 0 && s <= 0.0 && nmax > nest);   // ier = 1 before anything was computed
+    for (long long b = 0; b < nb; ++b) {
+        const int ier_out = hier[b], n_out = hn[b];
+        ier[b] = ier_out;
+        if (ier_out == FPB_INPUT_ERROR) continue;            // rejected: n, t, c, fp stay the caller's
+        n[b] = n_out;
+        if (untouched_all || n_out < nmin || n_out > nest) continue;
+        fp[b] = hd[o_fp + b];
+        std::memcpy(t + (size_t)b * nest, hd + o_t + (size_t)b * nest, (size_t)n_out * 8);
+        std::memcpy(c + (size_t)b * nest, hd + o_c + (size_t)b * nest, (size_t)(n_out - k1) * 8);
+        if (want_state) {
+            std::memcpy(fpint + (size_t)b * nest, hd + o_f + (size_t)b * nest, (size_t)n_out * 8);
+            std::memcpy(nrdata + (size_t)b * nest, hnrd + (size_t)b * nest, (size_t)n_out * 4);
         }
     }
     return true;
@@ -1447,11 +1492,17 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     fpb_engine *e0 = default_engine(device);
     if (!e0) return FPB_ERR_CUDA;
     const long long total = b1 - b0;
-    if (total == 1 && !shared_x && m >= 1) {   // a batch of one: the warp-per-curve kernel (latency, not throughput)
+    if (total <= kSoloMaxBatch && !shared_x && iopt != 1) {   // a few curves: the warp-per-curve kernel
         int32_t status = FPB_STATUS_OK;
-        const double xbv = xb ? *xb : x[(size_t)b0 * m], xev = xe ? *xe : x[(size_t)b0 * m + m - 1];
-        if (fit_solo_host(e0, iopt, m, x + (size_t)b0 * m, y + (size_t)b0 * m, w ? w + (size_t)b0 * m : nullptr, xbv, xev,
-                          k, s, nest, n + b0, t + (size_t)b0 * nest, c + (size_t)b0 * nest, fp + b0, ier + b0,
+        if (fit_solo_host(e0, total, iopt, m, x + (size_t)b0 * m, y + (size_t)b0 * m, w ? w + (size_t)b0 * m : nullptr,
+                          xb, xe, k, s, nest, n + b0, t + (size_t)b0 * nest, c + (size_t)b0 * nest, fp + b0, ier + b0,
+                          fpint ? fpint + (size_t)b0 * nest : nullptr, nrdata ? nrdata + (size_t)b0 * nest : nullptr,
+                          &status))
+            return status;
+    } else if (total == 1 && !shared_x) {   // continuation of one curve (fp_curfit_c with iopt = 1)
+        int32_t status = FPB_STATUS_OK;
+        if (fit_solo_host(e0, 1, iopt, m, x + (size_t)b0 * m, y + (size_t)b0 * m, w ? w + (size_t)b0 * m : nullptr,
+                          xb, xe, k, s, nest, n + b0, t + (size_t)b0 * nest, c + (size_t)b0 * nest, fp + b0, ier + b0,
                           fpint ? fpint + (size_t)b0 * nest : nullptr, nrdata ? nrdata + (size_t)b0 * nest : nullptr,
                           &status))
             return status;

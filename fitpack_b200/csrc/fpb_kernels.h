@@ -189,6 +189,7 @@ cudaError_t launch_pack_tc(int nb, int nest, int k, const int *n, const int *ier
 struct SoloParams {
     int nbatch, iopt, m, k, nest;
     double xb, xe, s;
+    int ends_from_x;           // 1: xb = x(1), xe = x(m) of each curve
     const double *x, *y, *w;   // [nbatch][m]
     int *n;                    // [nbatch]        in (iopt != 0) / out
     double *t, *c;             // [nbatch][nest]  in (iopt != 0: t) / out

@@ -70,3 +70,19 @@ for (mm, kk, ss) in ((1000, 3, 10.0), (64, 5, 0.05), (256, 3, 0.0)):
     print("m=%d k=%d s=%g (n=%d ier=%d): warp-per-curve %.3f ms | CPU oracle %.3f ms" % (
         mm, kk, ss, r["n"], r["ier"], bench(lambda: F.curfit(0, x, y, None, 0, 1, kk, ss, nest), 50),
         bench(lambda: O.curfit(0, x, y, None, 0, 1, kk, ss, nest), 50)))
+
+# ---- small batches through fp_curfit_batch_c: warp-per-curve kernel (one CTA per curve) vs the batch kernels ----
+import synthdata  # noqa: E402  (the bench workload: 256-point curves, k = 3, s = 2.56)
+for B in (1, 16, 64, 256, 512, 1024, 2048, 4096, 8192):
+    xs, ys = synthdata.c2_curves(np, 0, B, 256)
+    o = O.curfit_batch(0, xs, ys, None, 3, 2.56, 260)
+    res = {}
+    for on in (1, 0):
+        F.lib().fpb_set_single_curve_kernel(on)
+        g = F.curfit_batch(0, xs, ys, None, 3, 2.56, 260)
+        assert np.array_equal(g["n"], o["n"]) and np.array_equal(g["ier"], o["ier"]) and np.array_equal(g["fp"], o["fp"])
+        assert all(np.array_equal(g["t"][b, :o["n"][b]], o["t"][b, :o["n"][b]]) and
+                   np.array_equal(g["c"][b, :o["n"][b] - 4], o["c"][b, :o["n"][b] - 4]) for b in range(B))
+        res[on] = bench(lambda: F.curfit_batch(0, xs, ys, None, 3, 2.56, 260), 20)
+    F.lib().fpb_set_single_curve_kernel(1)
+    print("fp_curfit_batch_c B=%5d: warp-per-curve %.3f ms | batch kernels %.3f ms | bit-identical to the oracle" % (B, res[1], res[0]))

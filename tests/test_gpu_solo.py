@@ -38,7 +38,8 @@ def test_default_is_the_warp_per_curve_kernel(F):
 
 
 @pytest.mark.parametrize("name", ["test_mncurf_sequence_bit_exact", "test_curfit_golden_vectors_bit_exact",
-                                  "test_curfit_input_errors_leave_outputs_untouched", "test_curve_handle_api"])
+                                  "test_curfit_input_errors_leave_outputs_untouched", "test_curve_handle_api",
+                                  "test_host_batch_api_matches_oracle"])
 def test_flat_abi_tests_also_pass_on_the_batch_kernels(F, name):
     """the tests of test_gpu_parity run on the warp-per-curve kernel by default; here on one thread per curve"""
     with single_curve_kernel(F, False):
@@ -151,3 +152,37 @@ def test_batch_entry_point_with_one_curve(F):
             n = int(o["n"])
             assert int(g["n"][0]) == n and int(g["ier"][0]) == o["ier"] and g["fp"][0] == o["fp"]
             assert _same(g["t"][0, :n], o["t"][:n]) and _same(g["c"][0, :n - k - 1], o["c"][:n - k - 1])
+
+
+@pytest.mark.parametrize("weights", [False, True])
+def test_small_host_batches_run_one_warp_per_curve_and_match_the_oracle(F, weights):
+    """fp_curfit_batch_c with up to a few thousand curves: one CTA of one warp per curve instead of one thread per
+    curve; rejected curves (unsorted x) keep the caller's n / t / c / fp; iopt = -1 with per-curve knots"""
+    rng = np.random.default_rng(77 + weights)
+    B, m, k, nest = 300, 120, 3, 124
+    x = np.sort(rng.uniform(0, 1, (B, m)), axis=1)
+    y = np.sin(2 * np.pi * rng.uniform(0.5, 3, (B, 1)) * x) + 0.05 * rng.standard_normal((B, m))
+    w = rng.uniform(0.5, 2.0, (B, m)) if weights else None
+    x[17, 5], x[17, 6] = x[17, 6], x[17, 5]          # curve 17: not sorted -> ier = 10
+    s = 0.3
+    o = O.curfit_batch(0, x, y, w, k, s, nest)
+    t_in = np.full((B, nest), -3.0)
+    g = F.curfit_batch(0, x, y, w, k, s, nest, t=t_in.copy())
+    assert np.array_equal(g["n"], o["n"]) and np.array_equal(g["ier"], o["ier"]) and g["ier"][17] == 10
+    for b in range(B):
+        if b == 17:
+            assert np.all(g["t"][b] == -3.0) and g["n"][b] == 0
+            continue
+        n = int(o["n"][b])
+        assert g["fp"][b] == o["fp"][b]
+        assert _same(g["t"][b, :n], o["t"][b, :n]) and _same(g["c"][b, :n - k - 1], o["c"][b, :n - k - 1])
+        assert np.all(g["t"][b, n:] == -3.0)          # beyond n the caller's array is left alone
+    # least squares on the knots just found (iopt = -1, per-curve n and t)
+    o2 = O.curfit_batch(-1, x, y, w, k, s, nest, n=o["n"].copy(), t=o["t"].copy())
+    g2 = F.curfit_batch(-1, x, y, w, k, s, nest, n=g["n"].copy(), t=g["t"].copy())
+    assert np.array_equal(g2["ier"], o2["ier"])
+    for b in range(B):
+        if o2["ier"][b] == 10:
+            continue
+        n = int(o2["n"][b])
+        assert g2["fp"][b] == o2["fp"][b] and _same(g2["c"][b, :n - k - 1], o2["c"][b, :n - k - 1])
