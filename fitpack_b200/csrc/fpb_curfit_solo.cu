@@ -18,6 +18,10 @@
 //     CPU against the oracle's sequential sweeps;
 //   * the short serial pieces (fpknot, fpback, the ordered sums) run on lane 0.
 // Sums that the reference forms in point order (fp, fpint) are formed in point order.
+//
+// The same kernel, with ND right-hand sides per band row instead of one, is fppara (core:8822-9177, fp_rotate_row_vec
+// 5742-5771, fp_rotate_shifted_vec 5845-5862) for fp_parcur_c: ND coordinate curves share one knot vector and one
+// triangular factor; parcur's own argument checks and chord-length parameters (core:15238-15262) run in the kernel.
 #include "fpb_common.cuh"
 #include "fpb_kernels.h"
 
@@ -27,37 +31,39 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-template <int K> struct SoloCfg {
+template <int K, int ND> struct SoloCfg {
     static constexpr int K1 = K + 1, K2 = K + 2;
-    // data rows: K1 entries + right-hand side per group.  Row r meets band row j at tick r * ST + j: with K1 groups
-    // (ST = 1) a group is free again exactly when its next row starts; where only fewer fit into the warp (k = 5)
-    // the rows start two ticks apart.
-    static constexpr int LG_D = K1 + 1;
+    // data rows: K1 entries + ND right-hand sides per group.  Row r meets band row j at tick r * ST + j: with K1 groups
+    // (ST = 1) a group is free again exactly when its next row starts; where fewer fit into the warp the rows start
+    // ST ticks apart.
+    static constexpr int LG_D = K1 + ND;
     static constexpr int G_D = (32 / LG_D) < K1 ? (32 / LG_D) : K1;
-    static constexpr int ST_D = G_D >= K1 ? 1 : 2;
-    static_assert(G_D * ST_D >= K1, "a group must be free when its next data row starts");
-    // smoothing rows: K2 entries + right-hand side per group, as many groups as fit; start ticks from a table
-    static constexpr int LG_S = K2 + 1;
+    static constexpr int ST_D = (K1 + G_D - 1) / G_D;
+    static_assert(G_D >= 1 && G_D * ST_D >= K1, "a group must be free when its next data row starts");
+    // smoothing rows: K2 entries + ND right-hand sides per group, as many groups as fit; start ticks from a table
+    static constexpr int LG_S = K2 + ND;
     static constexpr int G_S = 32 / LG_S;
+    static_assert(G_S >= 1, "one smoothing row must fit into the warp");
 };
 
-// fpback core:1808-1838 on lane 0.  mat: rows of BAND band entries followed by the right-hand side (row length BAND + 1)
-template <int BAND>
-__device__ __forceinline__ void back_subst_solo(const double *mat, double *cv, int nk1, int lane)
+// fpback core:1808-1838, lane d solving coordinate d.  mat: rows of BAND band entries followed by the ND right-hand
+// sides (row length BAND + ND); the solution of coordinate d goes to cv + d * ldc.
+template <int BAND, int ND>
+__device__ __forceinline__ void back_subst_solo(const double *mat, double *cv, int ldc, int nk1, int lane)
 {
-    constexpr int LD = BAND + 1;
-    if (lane == 0) {
+    constexpr int LD = BAND + ND;
+    if (lane < ND) {
         double cw[BAND - 1];
 #pragma unroll
         for (int q = 0; q < BAND - 1; ++q) cw[q] = 0.0;
         for (int i = nk1; i >= 1; --i) {
-            double store = mat[(i - 1) * LD + BAND];
+            double store = mat[(i - 1) * LD + BAND + lane];
             const int cnt = min(nk1 - i, BAND - 1);
 #pragma unroll
             for (int q = 1; q <= BAND - 1; ++q)
                 if (q <= cnt) store = sub(store, mul(cw[q - 1], mat[(i - 1) * LD + q]));
             const double ci = store / mat[(i - 1) * LD];
-            cv[i - 1] = ci;
+            cv[lane * ldc + i - 1] = ci;
 #pragma unroll
             for (int q = BAND - 2; q >= 1; --q) cw[q] = cw[q - 1];
             cw[0] = ci;
@@ -66,39 +72,42 @@ __device__ __forceinline__ void back_subst_solo(const double *mat, double *cv, i
     __syncwarp();
 }
 
-template <int K>
+template <int K, int ND, bool PAR>
 __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
 {
-    using Cfg = SoloCfg<K>;
-    constexpr int K1 = Cfg::K1, K2 = Cfg::K2;
+    using Cfg = SoloCfg<K, ND>;
+    constexpr int K1 = Cfg::K1, K2 = Cfg::K2, LDA = K1 + ND, LDG = K2 + ND;
     extern __shared__ double sm[];
     const int lane = threadIdx.x, b = blockIdx.x;
     const int m = p.m, nest = p.nest, iopt = p.iopt;
-    double *xs = sm, *ys = xs + m, *ws = ys + m, *res = ws + m, *qs = res + m;
-    double *ts = qs + (size_t)m * K1, *cc = ts + nest, *fpi = cc + nest;
-    // band matrices with their right-hand sides as one more column: (R | z) rows of K1 + 1, (G | c) rows of K2 + 1
-    double *as = fpi + nest, *gs = as + (size_t)nest * (K1 + 1), *bs = gs + (size_t)nest * (K2 + 1);
-    double *hw = bs + (size_t)nest * K2;   // [m][K1 + 1]: the weighted data rows w * (basis values | y)
-    int *lidx = reinterpret_cast<int *>(hw + (size_t)m * (K1 + 1)), *llag = lidx + m, *nrd = llag + m, *sst = nrd + nest;
+    // xs: abscissae (curfit) / parameters u (parcur); ys: the data, ND values per point
+    double *xs = sm, *ys = xs + m, *ws = ys + (size_t)m * ND, *res = ws + m, *qs = res + (size_t)m * ND;
+    double *ts = qs + (size_t)m * K1, *cc = ts + nest, *fpi = cc + (size_t)nest * ND;
+    // band matrices with their right-hand sides as more columns: (R | z) rows of K1 + ND, (G | c) rows of K2 + ND
+    double *as = fpi + nest, *gs = as + (size_t)nest * LDA, *bs = gs + (size_t)nest * LDG;
+    double *hw = bs + (size_t)nest * K2;   // [m][K1 + ND]: the weighted data rows w * (basis values | data)
+    int *lidx = reinterpret_cast<int *>(hw + (size_t)m * LDA), *llag = lidx + m, *nrd = llag + m, *sst = nrd + nest;
 #define T_(i) ts[(i) - 1]
-#define C_(i) cc[(i) - 1]
+#define CD_(d, i) cc[(d) * nest + (i) - 1]
 #define FPI_(i) fpi[(i) - 1]
 #define NRD_(i) nrd[(i) - 1]
-#define A_(i, j) as[((i) - 1) * (K1 + 1) + ((j) - 1)]
+#define A_(i, j) as[((i) - 1) * LDA + ((j) - 1)]
 #define B_(i, j) bs[((i) - 1) * K2 + ((j) - 1)]
 
+    if (p.ier[b] != IER_OK) return;   // rejected by the host's data checks (core:1265-1285): nothing is written
     {
-        const double *gx = p.x + (size_t)b * m, *gy = p.y + (size_t)b * m, *gw = p.w + (size_t)b * m;
-        for (int i = lane; i < m; i += 32) {
-            xs[i] = gx[i];
-            ys[i] = gy[i];
-            ws[i] = gw[i];
+        const double *gy = p.y + (size_t)b * m * ND, *gw = p.w + (size_t)b * m;
+        for (int i = lane; i < m; i += 32) ws[i] = gw[i];
+        for (int i = lane; i < m * ND; i += 32) ys[i] = gy[i];
+        if (!PAR || !p.chord) {
+            const double *gx = p.x + (size_t)b * m;
+            for (int i = lane; i < m; i += 32) xs[i] = gx[i];
         }
     }
-    if (p.ier[b] != IER_OK) return;   // rejected by the host's data checks (core:1265-1285): nothing is written
     int n = 0;
     if (iopt != 0) {
         n = p.n[b];
+        if (PAR && (n < 2 * K1 || n > nest)) n = (iopt < 0) ? -1 : 2 * K1;   // -1: rejected below; garbage on iopt = 1: fresh start
         for (int i = lane; i < n; i += 32) ts[i] = p.t[(size_t)b * nest + i];
         if (iopt > 0)
             for (int i = lane; i < n; i += 32) {
@@ -108,8 +117,131 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
     }
     __syncwarp();
 
+    double xb_ = 0.0, xe_ = 0.0;
+    if constexpr (!PAR) {
+        xb_ = p.ends_from_x ? xs[0] : p.xb;
+        xe_ = p.ends_from_x ? xs[m - 1] : p.xe;
+    } else {
+        // ---- parcur's own part, core:15238-15262: parameters, then the checks on the data ----
+        int bad = 0;
+        if (p.chord) {
+            // u(i) = u(i-1) + norm2(x(:,i) - x(:,i-1)) (gfortran's scaled norm2), then u / u(m)
+            for (int i = 1 + lane; i < m; i += 32) {
+                double result = 0.0, scale = 1.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const double df = sub(ys[i * ND + d], ys[(i - 1) * ND + d]);
+                    if (df != 0.0) {
+                        const double a = fabs(df);
+                        if (scale < a) {
+                            const double val = scale / a;
+                            result = add(1.0, mul(mul(result, val), val));
+                            scale = a;
+                        } else {
+                            const double val = a / scale;
+                            result = add(result, mul(val, val));
+                        }
+                    }
+                }
+                res[i] = mul(scale, sqrt(result));
+            }
+            __syncwarp();
+            double tot = 0.0;
+            if (lane == 0) {
+                xs[0] = 0.0;
+                for (int i = 1; i < m; ++i) {
+                    tot = add(tot, res[i]);
+                    xs[i] = tot;
+                }
+            }
+            tot = __shfl_sync(FULL, tot, 0);
+            __syncwarp();
+            if (tot <= 0.0) {
+                bad = 1;
+            } else {
+                for (int i = 1 + lane; i < m; i += 32) xs[i] = xs[i] / tot;
+                __syncwarp();
+                if (lane == 0) xs[m - 1] = 1.0;
+                xb_ = 0.0;
+                xe_ = 1.0;
+                __syncwarp();
+            }
+            for (int i = lane; i < m; i += 32) p.u_out[(size_t)b * m + i] = xs[i];
+            if (!bad && lane == 0) {
+                p.ube[2 * (size_t)b] = 0.0;
+                p.ube[2 * (size_t)b + 1] = 1.0;
+            }
+        } else {
+            xb_ = p.ube[2 * (size_t)b];
+            xe_ = p.ube[2 * (size_t)b + 1];
+        }
+        if (!bad) {
+            int mybad = (xb_ > xs[0] || xe_ < xs[m - 1] || ws[0] <= 0.0) ? 1 : 0;
+            for (int i = lane; i + 1 < m; i += 32)
+                if (xs[i] >= xs[i + 1] || ws[i + 1] <= 0.0) mybad = 1;
+            bad = __any_sync(FULL, mybad) ? 1 : 0;
+        }
+        int chk = IER_OK;
+        if (!bad) {
+            if (iopt < 0) {
+                if (n < 0) {
+                    bad = 1;
+                } else {
+                    if (lane < K1) {   // visible to the caller even if fpchec fails, core:15264-15270
+                        ts[lane] = xb_;
+                        ts[n - 1 - lane] = xe_;
+                        p.t[(size_t)b * nest + lane] = xb_;
+                        p.t[(size_t)b * nest + n - 1 - lane] = xe_;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {   // fpchec, core:2507-2570
+                        const int nk1c = n - K1, nk2 = nk1c + 1;
+                        auto X = [&](int i) { return xs[i - 1]; };
+                        bool f = (nk1c < K1 || nk1c > m);
+                        if (!f) {
+                            int j = n;
+                            for (int i = 1; i <= K; ++i) {
+                                if (T_(i) > T_(i + 1) || T_(j) < T_(j - 1)) f = true;
+                                --j;
+                            }
+                            for (int i = K2; i <= nk2; ++i)
+                                if (T_(i) <= T_(i - 1)) f = true;
+                            if (X(1) < T_(K1) || X(m) > T_(nk2)) f = true;
+                            if (X(1) >= T_(K2) || X(m) <= T_(nk1c)) f = true;
+                        }
+                        if (!f) {
+                            int i = 1, l = K2;
+                            const int nk3 = nk1c - 1;
+                            for (int j = 2; j <= nk3 && !f; ++j) {
+                                const double tj = T_(j);
+                                ++l;
+                                const double tl = T_(l);
+                                while (i < m && X(i) <= tj) {
+                                    ++i;
+                                    if (i >= m) {
+                                        f = true;
+                                        break;
+                                    }
+                                }
+                                if (!f && X(i) >= tl) f = true;
+                            }
+                        }
+                        chk = f ? IER_INPUT : IER_OK;
+                    }
+                    chk = __shfl_sync(FULL, chk, 0);
+                }
+            } else if (p.s < 0.0 || (fp_is_zero(p.s) && nest < m + K1)) {
+                bad = 1;
+            }
+        }
+        if (bad || chk != IER_OK) {
+            if (lane == 0) p.ier[b] = IER_INPUT;
+            return;
+        }
+    }
+
     // scalars: every lane carries the same values (pure scalar arithmetic is simply done 32 times over)
-    const double s = p.s, xb = p.ends_from_x ? xs[0] : p.xb, xe = p.ends_from_x ? xs[m - 1] : p.xe;
+    const double s = p.s, xb = xb_, xe = xe_;
     const int nmax = m + K1, nmin = 2 * K1;
     const double acc = mul(kTol, s);
     double fpold = 0.0, fp0 = 0.0, fp = p.fp[b], fpms = DBL_MAX;
@@ -168,7 +300,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             ts[lane] = xb;
             ts[nk1 + lane] = xe;
         }
-        for (int i = lane; i < nk1 * (K1 + 1); i += 32) as[i] = 0.0;
+        for (int i = lane; i < nk1 * LDA; i += 32) as[i] = 0.0;
         __syncwarp();
         // knot interval and B-spline values of every point, one point per lane (core:4876-4885)
         for (int it = lane; it < m; it += 32) {
@@ -187,9 +319,10 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
 #pragma unroll
             for (int j = 0; j < K1; ++j) {
                 qs[it * K1 + j] = h[j];
-                hw[it * (K1 + 1) + j] = mul(wi, h[j]);
+                hw[it * LDA + j] = mul(wi, h[j]);
             }
-            hw[it * (K1 + 1) + K1] = mul(ys[it], wi);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) hw[it * LDA + K1 + d] = mul(ys[it * ND + d], wi);
         }
         __syncwarp();
         // the residual loops' own interval counter (core:4947, 5065) advances at most one knot per point:
@@ -216,7 +349,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
         {
             constexpr int LG = Cfg::LG_D, G = Cfg::G_D, ST = Cfg::ST_D, NEVER = INT_MAX / 2;
             const int grp = lane / LG, sub_ = lane - grp * LG;
-            const bool member = grp < G, isrhs = sub_ == K1;
+            const bool member = grp < G, isrhs = sub_ >= K1;
             const int base = member ? grp * LG : 0;
             int row = member ? grp : NEVER, first = 0, start = NEVER, first_n = 0;
             double hv = 0.0, hv_n = 0.0;
@@ -240,7 +373,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
                 const int i0c = act ? i0 : 0;
                 double *rowp = as + (act ? first + i0 - 1 : 0) * LG;   // band row it meets: (R(j, :) | z(j))
                 const int q = sub_ - i0c;                      // 0: the pivot's lane, > 0: a column to its right
-                const int col = isrhs ? K1 : max(q, 0);
+                const int col = isrhs ? sub_ : max(q, 0);
                 const double wwl = rowp[0], s2 = rowp[col];
                 const double piv = __shfl_sync(FULL, hv, base + i0c);
                 const bool rot = act && !fp_is_zero(piv);
@@ -252,7 +385,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
                 if (upd) rowp[col] = col == 0 ? ww : nb;
                 hv = (upd && col != 0) ? na : hv;
                 const bool fin = act && i0 == K;               // the row is through: its residual, then the next row
-                if (fin && isrhs) res[row] = mul(hv, hv);
+                if (fin && isrhs) res[row * ND + (sub_ - K1)] = mul(hv, hv);
                 if (fin) {
                     row += G;
                     first = first_n;
@@ -263,8 +396,13 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
                 }
                 __syncwarp();
             }
-            fp = 0.0;                                          // summed in row order (core:4894)
-            for (int it = 0; it < m; ++it) fp = add(fp, res[it]);
+            fp = 0.0;                                          // summed in row order (core:4894 / 8972: fp + sum(xi**2))
+            for (int it = 0; it < m; ++it) {
+                double sq = res[it * ND];
+#pragma unroll
+                for (int d = 1; d < ND; ++d) sq = add(sq, res[it * ND + d]);
+                fp = add(fp, sq);
+            }
             __syncwarp();
         }
         if (ier == IER_LSQ) fp0 = fp;
@@ -273,7 +411,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             FPI_(n) = fp0;
             NRD_(n) = nplus;
         }
-        back_subst_solo<K1>(as, cc, nk1, lane);
+        back_subst_solo<K1, ND>(as, cc, nest, nk1, lane);
         if (iopt < 0) {
             done = true;
             break;
@@ -308,11 +446,24 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
         // squared residual of every point (core:4948-4953), then the per-interval split in point order (4954-4966)
         for (int it = lane; it < m; it += 32) {
             const int l0 = llag[it] - K2;
-            double term = 0.0;
+            if constexpr (!PAR) {
+                double term = 0.0;
 #pragma unroll
-            for (int j = 1; j <= K1; ++j) term = add(term, mul(C_(l0 + j), qs[it * K1 + j - 1]));
-            term = mul(ws[it], sub(term, ys[it]));
-            res[it] = mul(term, term);
+                for (int j = 1; j <= K1; ++j) term = add(term, mul(CD_(0, l0 + j), qs[it * K1 + j - 1]));
+                term = mul(ws[it], sub(term, ys[it]));
+                res[it] = mul(term, term);
+            } else {   // core:9030-9041
+                double term = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    double fac = 0.0;
+#pragma unroll
+                    for (int j = 1; j <= K1; ++j) fac = add(fac, mul(CD_(d, l0 + j), qs[it * K1 + j - 1]));
+                    const double store = mul(ws[it], sub(fac, ys[it * ND + d]));
+                    term = add(term, mul(store, store));
+                }
+                res[it] = term;
+            }
         }
         __syncwarp();
         int flag = 0;
@@ -409,7 +560,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
         double p1 = 0.0, f1 = sub(fp0, s), p3 = -1.0, f3 = fpms, p2 = 0.0, f2 = 0.0, pp = 0.0;
         bool check1 = false, check3 = false;
         for (int i = 1; i <= nk1; ++i) pp = add(pp, A_(i, 1));
-        pp = (double)nk1 / pp;
+        pp = PAR ? pp / (double)nk1 : (double)nk1 / pp;   // core:5033 / 9119
         const int n8 = n - nmin;
         // start ticks of the smoothing rows: two ticks behind the row before, and not before the group is free
         // (row r meets band rows r+1 .. nk1, one per tick)
@@ -431,16 +582,16 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             ++it2;
             const double pinv = 1.0 / pp;
             // c := z, g := (a | 0), core:5047-5049
-            for (int i = lane; i < nk1 * (K2 + 1); i += 32) {
-                const int r = i / (K2 + 1), q = i - r * (K2 + 1);
-                gs[i] = q < K1 ? as[r * (K1 + 1) + q] : (q == K2 ? as[r * (K1 + 1) + K1] : 0.0);
+            for (int i = lane; i < nk1 * LDG; i += 32) {
+                const int r = i / LDG, q = i - r * LDG;
+                gs[i] = q < K1 ? as[r * LDA + q] : (q >= K2 ? as[r * LDA + K1 + (q - K2)] : 0.0);
             }
             __syncwarp();
             // ---- smoothing rows b(it,:)/p into (G, c) as a wavefront (core:5052-5057, fp_rotate_shifted 5800-5820) ----
             {
                 constexpr int LG = Cfg::LG_S, G = Cfg::G_S, NEVER = INT_MAX / 2;
                 const int grp = lane / LG, sub_ = lane - grp * LG;
-                const bool member = grp < G, isrhs = sub_ == K2;
+                const bool member = grp < G, isrhs = sub_ >= K2;
                 const int base = member ? grp * LG : 0;
                 const int bcol = isrhs ? 0 : sub_;               // column of b this lane reads
                 // lane sub_ < K2 holds the row's entry of band column `col`; the pivot's lane then takes the column
@@ -471,10 +622,10 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
                     const int dc = col - j;
                     const bool pivlane = !isrhs && sub_ == ps;
                     const bool mine = isrhs || pivlane || (dc >= 1 && dc <= noff);
-                    const int tc = isrhs ? K2 : (mine && !pivlane ? dc : 0);
+                    const int tc = isrhs ? sub_ : (mine && !pivlane ? dc : 0);
                     const double wwl = rowp[0], s2 = rowp[tc];
                     const double piv = __shfl_sync(FULL, hv, base + ps);
-                    const bool rot = act && !fp_is_zero(piv);
+                    const bool rot = act && (PAR || !fp_is_zero(piv));   // the vector variant has no zero-pivot skip
                     const bool upd = rot && mine;
                     double ww = rot ? wwl : 1.0, cs, sn;
                     givens_fast(rot ? piv : 1.0, ww, cs, sn);
@@ -497,15 +648,28 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
                     __syncwarp();
                 }
             }
-            back_subst_solo<K2>(gs, cc, nk1, lane);
+            back_subst_solo<K2, ND>(gs, cc, nest, nk1, lane);
             // fp = sum of squared residuals in point order, core:5061-5069
             for (int it = lane; it < m; it += 32) {
                 const int l0 = llag[it] - K2;
-                double term = 0.0;
+                if constexpr (!PAR) {
+                    double term = 0.0;
 #pragma unroll
-                for (int j = 1; j <= K1; ++j) term = add(term, mul(C_(l0 + j), qs[it * K1 + j - 1]));
-                term = mul(ws[it], sub(term, ys[it]));
-                res[it] = mul(term, term);
+                    for (int j = 1; j <= K1; ++j) term = add(term, mul(CD_(0, l0 + j), qs[it * K1 + j - 1]));
+                    term = mul(ws[it], sub(term, ys[it]));
+                    res[it] = mul(term, term);
+                } else {   // core:9147-9158: term * w**2
+                    double term = 0.0;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        double fac = 0.0;
+#pragma unroll
+                        for (int j = 1; j <= K1; ++j) fac = add(fac, mul(CD_(d, l0 + j), qs[it * K1 + j - 1]));
+                        const double store = sub(fac, ys[it * ND + d]);
+                        term = add(term, mul(store, store));
+                    }
+                    res[it] = mul(term, mul(ws[it], ws[it]));
+                }
             }
             __syncwarp();
             fp = 0.0;
@@ -579,10 +743,12 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             p.fpint[(size_t)b * nest + i] = fpi[i];
             p.nrdata[(size_t)b * nest + i] = nrd[i];
         }
-        for (int i = lane; i < nk1; i += 32) p.c[(size_t)b * nest + i] = cc[i];
+        // curfit: c(1:nk1); parcur: coordinate d at c(d*n + 1 : d*n + nk1) (core:8981-8985)
+        for (int d = 0; d < ND; ++d)
+            for (int i = lane; i < nk1; i += 32) p.c[(size_t)b * p.c_stride + (size_t)d * n + i] = cc[d * nest + i];
     }
 #undef T_
-#undef C_
+#undef CD_
 #undef FPI_
 #undef NRD_
 #undef A_
@@ -591,41 +757,59 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
 
 }  // namespace
 
-size_t solo_smem_bytes(int m, int k, int nest)
+size_t solo_smem_bytes(int m, int k, int nest, int idim)
 {
-    const size_t k1 = k + 1, k2 = k + 2;
-    const size_t doubles = (size_t)m * (4 + k1 + k1 + 1) + (size_t)nest * (3 + (k1 + 1) + (k2 + 1) + k2);
+    const size_t k1 = k + 1, k2 = k + 2, nd = idim;
+    const size_t doubles = (size_t)m * (2 + 2 * nd + k1 + k1 + nd) + (size_t)nest * (2 + nd + (k1 + nd) + (k2 + nd) + k2);
     return doubles * 8 + ((size_t)2 * m + 2 * (size_t)nest) * 4;
 }
 
+bool solo_supports(int k, int idim, int par)
+{
+    if (k < 1 || k > 5) return false;
+    return par ? (idim == 2 || idim == 3) : idim == 1;
+}
+
+namespace {
+template <int K, int ND, bool PAR>
+cudaError_t launch_solo_one(const SoloParams &p, size_t smem, int dev, cudaStream_t st)
+{
+    static size_t opted[64] = {0};   // the attribute is per device
+    if (smem > opted[dev & 63]) {
+        const cudaError_t err = cudaFuncSetAttribute(curfit_solo_kernel<K, ND, PAR>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        opted[dev & 63] = smem;
+    }
+    curfit_solo_kernel<K, ND, PAR><<<p.nbatch, 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int K>
+cudaError_t launch_solo_k(const SoloParams &p, size_t smem, int dev, cudaStream_t st)
+{
+    if (!p.par) return launch_solo_one<K, 1, false>(p, smem, dev, st);
+    if (p.idim == 2) return launch_solo_one<K, 2, true>(p, smem, dev, st);
+    if (p.idim == 3) return launch_solo_one<K, 3, true>(p, smem, dev, st);
+    return cudaErrorInvalidValue;
+}
+}  // namespace
+
 cudaError_t launch_curfit_solo(const SoloParams &p, cudaStream_t st)
 {
-    const size_t smem = solo_smem_bytes(p.m, p.k, p.nest);
-    cudaError_t err = cudaSuccess;
+    if (!solo_supports(p.k, p.idim, p.par)) return cudaErrorInvalidValue;
+    const size_t smem = solo_smem_bytes(p.m, p.k, p.nest, p.idim);
     int dev = 0;
-    if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
-#define FPB_SOLO_CASE(KK)                                                                                          \
-    case KK: {                                                                                                     \
-        static size_t opted[64] = {0};   /* the attribute is per device */                                         \
-        if (smem > opted[dev & 63]) {                                                                              \
-            err = cudaFuncSetAttribute(curfit_solo_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                       (int)smem);                                                                 \
-            if (err != cudaSuccess) return err;                                                                    \
-            opted[dev & 63] = smem;                                                                                \
-        }                                                                                                          \
-        curfit_solo_kernel<KK><<<p.nbatch, 32, smem, st>>>(p);                                                     \
-        break;                                                                                                     \
-    }
+    const cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
     switch (p.k) {
-        FPB_SOLO_CASE(1)
-        FPB_SOLO_CASE(2)
-        FPB_SOLO_CASE(3)
-        FPB_SOLO_CASE(4)
-        FPB_SOLO_CASE(5)
+    case 1: return launch_solo_k<1>(p, smem, dev, st);
+    case 2: return launch_solo_k<2>(p, smem, dev, st);
+    case 3: return launch_solo_k<3>(p, smem, dev, st);
+    case 4: return launch_solo_k<4>(p, smem, dev, st);
+    case 5: return launch_solo_k<5>(p, smem, dev, st);
     default: return cudaErrorInvalidValue;
     }
-#undef FPB_SOLO_CASE
-    return cudaGetLastError();
 }
 
 }  // namespace fpb

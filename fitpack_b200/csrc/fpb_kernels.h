@@ -185,20 +185,27 @@ cudaError_t launch_fill_i32(int *dst, int value, long long count, cudaStream_t s
 cudaError_t launch_pack_tc(int nb, int nest, int k, const int *n, const int *ier, const double *t, const double *c,
                            unsigned long long *cursor, long long *off, double *tp, double *cp, int nsm,
                            cudaStream_t stream);
-// ---- single-curve fit, one warp per curve (fpb_curfit_solo.cu) ----
+// ---- a few curves, one warp per curve (fpb_curfit_solo.cu): curfit (idim = 1, par = 0) or parcur (par = 1) ----
 struct SoloParams {
     int nbatch, iopt, m, k, nest;
+    int idim, par, chord;      // right-hand sides per point; fppara semantics; parcur computes chord-length parameters
     double xb, xe, s;
-    int ends_from_x;           // 1: xb = x(1), xe = x(m) of each curve
-    const double *x, *y, *w;   // [nbatch][m]
+    int ends_from_x;           // curfit: 1: xb = x(1), xe = x(m) of each curve
+    const double *x;           // [nbatch][m]        abscissae (curfit) / parameters u (parcur, unless chord)
+    const double *y;           // [nbatch][m][idim]  data
+    const double *w;           // [nbatch][m]
+    double *u_out;             // parcur with chord: the parameters computed, [nbatch][m]
+    double *ube;               // parcur: [nbatch][2] ub, ue (in; out when chord)
     int *n;                    // [nbatch]        in (iopt != 0) / out
-    double *t, *c;             // [nbatch][nest]  in (iopt != 0: t) / out
+    double *t, *c;             // t [nbatch][nest] in (iopt != 0) / out; c [nbatch][c_stride] out
+    long long c_stride;
     double *fp;                // [nbatch]        in / out (left alone when nothing was computed)
-    int *ier;                  // [nbatch]        out
+    int *ier;                  // [nbatch]        in: != 0 skips the curve; out
     double *fpint;             // [nbatch][nest]  in (iopt = 1) / out
     int *nrdata;               // [nbatch][nest]  in (iopt = 1) / out
 };
-size_t solo_smem_bytes(int m, int k, int nest);
+size_t solo_smem_bytes(int m, int k, int nest, int idim);
+bool solo_supports(int k, int idim, int par);
 constexpr size_t kSoloSmemMax = 200 * 1024;
 cudaError_t launch_curfit_solo(const SoloParams &p, cudaStream_t stream);
 

@@ -450,6 +450,7 @@ void fp_parcur_c(FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u
     if (mx < m * idim || nc < nest * idim) return;
     if (lwrk < m * (k + 1) + nest * (6 + idim + 3 * k)) return;
     // wrk(1:nest) is fpint and iwrk(1:nest) is nrdata (core:15275-15283): the iopt=1 state
+    if (parcur_solo_host(iopt, ipar, idim, m, u, x, w, ub, ue, k, *s, nest, n, t, c, fp, wrk, iwrk, ier)) return;
     FP_FLAG ier1 = FPB_INPUT_ERROR;
     const int32_t rc = fp_parcur_batch_c(1, iopt, ipar, idim, m, u, x, w, ub, ue, k, *s, nest, n, t, c, fp,
                                          &ier1, wrk, iwrk, 1);

@@ -39,7 +39,8 @@ def test_default_is_the_warp_per_curve_kernel(F):
 
 @pytest.mark.parametrize("name", ["test_mncurf_sequence_bit_exact", "test_curfit_golden_vectors_bit_exact",
                                   "test_curfit_input_errors_leave_outputs_untouched", "test_curve_handle_api",
-                                  "test_host_batch_api_matches_oracle"])
+                                  "test_host_batch_api_matches_oracle",
+                                  "test_parcur_golden_cases_flat_abi_bit_exact"])
 def test_flat_abi_tests_also_pass_on_the_batch_kernels(F, name):
     """the tests of test_gpu_parity run on the warp-per-curve kernel by default; here on one thread per curve"""
     with single_curve_kernel(F, False):
@@ -186,3 +187,72 @@ def test_small_host_batches_run_one_warp_per_curve_and_match_the_oracle(F, weigh
             continue
         n = int(o2["n"][b])
         assert g2["fp"][b] == o2["fp"][b] and _same(g2["c"][b, :n - k - 1], o2["c"][b, :n - k - 1])
+
+
+def _same_parcur(o, g, idim, k):
+    assert (g["n"], g["ier"]) == (o["n"], o["ier"])
+    assert _same(g["u"], o["u"]) and g["ub"] == o["ub"] and g["ue"] == o["ue"]
+    if o["ier"] == 10:
+        return
+    n = int(o["n"])
+    assert g["fp"] == o["fp"] and _same(g["t"][:n], o["t"][:n])
+    for d in range(idim):
+        assert _same(g["c"][d * n:d * n + n - k - 1], o["c"][d * n:d * n + n - k - 1])
+
+
+@pytest.mark.parametrize("idim", [2, 3])
+def test_parcur_flat_abi_on_the_warp_per_curve_kernel(F, idim):
+    """fp_parcur_c (idim 2, 3) = the same kernel with idim right-hand sides per band row (fppara core:8822-9177):
+    chord-length and given parameters, iopt 0 -> 1 -> -1, weights, s from interpolation to 'polynomial accepted';
+    n, ier, fp, t, c (in the reference's c(d*n + i) layout), u, ub, ue bit for bit"""
+    rng = np.random.default_rng(500 + idim)
+    for trial in range(80):
+        k = int(rng.integers(1, 6))
+        m = int(rng.integers(2 * k + 2, 260))
+        ph = np.sort(rng.uniform(0, 1, m)) * rng.uniform(1, 6)
+        x = np.stack([np.cos(ph), np.sin(ph), ph * 0.3][:idim], 1) + 0.03 * rng.standard_normal((m, idim))
+        w = rng.uniform(0.5, 2.0, m) if trial % 3 else None
+        s = float(m * 0.001 * rng.choice([0.0, 0.1, 1.0, 10.0, 1000.0]))
+        nest = int(rng.choice([m + k + 1, max(2 * k + 2, m // 2)]))
+        ipar = int(trial % 4 == 1)
+        kw = {}
+        if ipar:
+            u = np.cumsum(rng.uniform(0.1, 1.0, m))
+            kw = dict(u=u, ub=float(u[0]) - (trial % 2) * 0.1, ue=float(u[-1]))
+        o = O.parcur(0, ipar, idim, x, w, k, s, nest, **kw)
+        g = F.parcur(0, ipar, idim, x, w, k, s, nest, **kw)
+        _same_parcur(o, g, idim, k)
+        if o["ier"] > 0 or s == 0.0 or trial % 2:
+            continue
+        s2 = s * 0.4
+        o1 = O.parcur(1, ipar, idim, x, w, k, s2, nest, u=o["u"], ub=o["ub"], ue=o["ue"], n=o["n"], t=o["t"],
+                      wrk=o["wrk"], iwrk=o["iwrk"], c=o["c"])
+        g1 = F.parcur(1, ipar, idim, x, w, k, s2, nest, u=g["u"], ub=g["ub"], ue=g["ue"], n=g["n"], t=g["t"],
+                      wrk=g["wrk"], iwrk=g["iwrk"], c=g["c"])
+        _same_parcur(o1, g1, idim, k)
+        o2 = O.parcur(-1, ipar, idim, x, w, k, s2, nest, u=o1["u"], ub=o1["ub"], ue=o1["ue"], n=o1["n"], t=o1["t"])
+        g2 = F.parcur(-1, ipar, idim, x, w, k, s2, nest, u=g1["u"], ub=g1["ub"], ue=g1["ue"], n=g1["n"], t=g1["t"])
+        _same_parcur(o2, g2, idim, k)
+
+
+def test_parcur_rejected_inputs_on_the_warp_per_curve_kernel(F):
+    """parcur's checks (core:15255-15270) run inside the kernel: ier = 10, n / t / c / fp untouched, the computed
+    parameters and the clamped end knots visible as in the reference"""
+    m, k, idim, nest = 60, 3, 2, 70
+    ph = np.linspace(0, 3, m)
+    x = np.stack([np.cos(ph), np.sin(ph)], 1)
+    u = np.linspace(0, 1, m)
+    ubad = u.copy()
+    ubad[10] = ubad[9]
+    wbad = np.ones(m)
+    wbad[5] = 0.0
+    tbad = np.zeros(nest)
+    tbad[4:8] = [0.2, 0.2, 0.5, 0.7]
+    for a in (dict(ipar=1, u=ubad, ub=0.0, ue=1.0), dict(ipar=0, w=wbad),
+              dict(ipar=1, iopt=-1, u=u, ub=0.0, ue=1.0, n=12, t=tbad), dict(ipar=1, u=u, ub=0.5, ue=1.0)):
+        iopt, ipar, w = a.pop("iopt", 0), a.pop("ipar"), a.pop("w", None)
+        o = O.parcur(iopt, ipar, idim, x, w, k, 0.1, nest, **a)
+        g = F.parcur(iopt, ipar, idim, x, w, k, 0.1, nest, **a)
+        assert o["ier"] == g["ier"] == 10
+        _same_parcur(o, g, idim, k)
+        assert _same(o["t"], g["t"]) and _same(o["c"], g["c"])
