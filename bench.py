@@ -391,6 +391,36 @@ def main():
                     "kernel, 49 % in part 2 (profiles/r02_kernels.md)"}
     roof["secondary"] = []   # the other kernels of the metric, filled in below (driver keeps `roofline`)
 
+    # ---------------------------------------------------------------- one curve per call (the reference's call pattern)
+    if rank == 0 and not args.no_e2e:
+        L1 = fitpack_b200.lib()
+        xs1, ys1 = synth_host(np, 0, 1, M)
+        x1, y1 = np.ascontiguousarray(xs1[0]), np.ascontiguousarray(ys1[0])
+
+        def one_call():
+            return fitpack_b200.curfit(0, x1, y1, None, float(x1[0]), float(x1[-1]), K, S, NEST)
+
+        def lat(fn, reps):
+            fn()
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return 1e3 * (time.perf_counter() - t0) / reps
+        solo_ms = lat(one_call, 100)
+        prev = L1.fpb_set_single_curve_kernel(0)
+        batch1_ms = lat(one_call, 20)
+        L1.fpb_set_single_curve_kernel(prev)
+        roof["single_call"] = {
+            "api": "fp_curfit_c, curve 0 of the bench batch (m = %d, k = %d, s = %g), wall clock per call" % (M, K, S),
+            "warp_per_curve_kernel_ms": solo_ms, "batch_kernels_one_thread_per_curve_ms": batch1_ms,
+            "kernel": "curfit_solo_kernel<3,1,false>: one warp per curve, band-QR sweeps as a wavefront over lane groups; "
+                      "bound by the dependent Givens chain (29 FP64 + 3 MUFU per tick), not by HBM"}
+        if not args.no_cpu:
+            import oracle_lib as O1
+            roof["single_call"]["cpu_port_ms"] = lat(
+                lambda: O1.curfit(0, x1, y1, None, float(x1[0]), float(x1[-1]), K, S, NEST), 50)
+
     # ---------------------------------------------------------------- parity sample on the SAME batch
     parity = None
     if rank == 0 and not args.no_cpu:
