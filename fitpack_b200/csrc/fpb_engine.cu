@@ -1373,9 +1373,13 @@ bool fit_solo_host(fpb_engine *eng, long long nb, FP_SIZE iopt, FP_SIZE m, const
         return true;
     };
     if (!g.ok) return fail(FPB_ERR_CUDA);
-    if (!eng->scratch[0].reserve(o_end * 8) || !reserve_pinned((void **)&eng->h_solo, &eng->h_solo_bytes, o_end * 8))
+    // the pinned mirror of the block starts where the host needs it: a single curve is packed whole; for more, x and y
+    // (and w) go up straight from the caller's arrays
+    const size_t h0 = (nb == 1) ? 0 : (w ? o_fp : 2 * pts);
+    if (!eng->scratch[0].reserve(o_end * 8) ||
+        !reserve_pinned((void **)&eng->h_solo, &eng->h_solo_bytes, (o_end - h0) * 8))
         return fail(FPB_ERR_ALLOC);
-    double *hd = eng->h_solo, *dd = eng->scratch[0].as<double>();
+    double *hd = eng->h_solo - h0, *dd = eng->scratch[0].as<double>();   // hd + offset is valid for offsets >= h0
     int *hn = reinterpret_cast<int *>(hd + o_n), *hier = reinterpret_cast<int *>(hd + o_ier),
         *hnrd = reinterpret_cast<int *>(hd + o_nrd);
     // ---- curfit's checks on the data, core:1271-1285, curve by curve ----
