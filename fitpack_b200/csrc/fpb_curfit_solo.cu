@@ -22,6 +22,8 @@
 // The same kernel, with ND right-hand sides per band row instead of one, is fppara (core:8822-9177, fp_rotate_row_vec
 // 5742-5771, fp_rotate_shifted_vec 5845-5862) for fp_parcur_c: ND coordinate curves share one knot vector and one
 // triangular factor; parcur's own argument checks and chord-length parameters (core:15238-15262) run in the kernel.
+#include <algorithm>
+
 #include "fpb_common.cuh"
 #include "fpb_kernels.h"
 
@@ -80,15 +82,16 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
     extern __shared__ double sm[];
     const int lane = threadIdx.x, b = blockIdx.x;
     const int m = p.m, nest = p.nest, iopt = p.iopt;
+    const int ncap = min(nest, m + K1);   // the knot count never exceeds min(nest, m + k + 1): the shared arrays are that long
     // xs: abscissae (curfit) / parameters u (parcur); ys: the data, ND values per point
     double *xs = sm, *ys = xs + m, *ws = ys + (size_t)m * ND, *res = ws + m, *qs = res + (size_t)m * ND;
-    double *ts = qs + (size_t)m * K1, *cc = ts + nest, *fpi = cc + (size_t)nest * ND;
+    double *ts = qs + (size_t)m * K1, *cc = ts + ncap, *fpi = cc + (size_t)ncap * ND;
     // band matrices with their right-hand sides as more columns: (R | z) rows of K1 + ND, (G | c) rows of K2 + ND
-    double *as = fpi + nest, *gs = as + (size_t)nest * LDA, *bs = gs + (size_t)nest * LDG;
-    double *hw = bs + (size_t)nest * K2;   // [m][K1 + ND]: the weighted data rows w * (basis values | data)
-    int *lidx = reinterpret_cast<int *>(hw + (size_t)m * LDA), *llag = lidx + m, *nrd = llag + m, *sst = nrd + nest;
+    double *as = fpi + ncap, *gs = as + (size_t)ncap * LDA, *bs = gs + (size_t)ncap * LDG;
+    double *hw = bs + (size_t)ncap * K2;   // [m][K1 + ND]: the weighted data rows w * (basis values | data)
+    int *lidx = reinterpret_cast<int *>(hw + (size_t)m * LDA), *llag = lidx + m, *nrd = llag + m, *sst = nrd + ncap;
 #define T_(i) ts[(i) - 1]
-#define CD_(d, i) cc[(d) * nest + (i) - 1]
+#define CD_(d, i) cc[(d) * ncap + (i) - 1]
 #define FPI_(i) fpi[(i) - 1]
 #define NRD_(i) nrd[(i) - 1]
 #define A_(i, j) as[((i) - 1) * LDA + ((j) - 1)]
@@ -107,7 +110,8 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
     int n = 0;
     if (iopt != 0) {
         n = p.n[b];
-        if (PAR && (n < 2 * K1 || n > nest)) n = (iopt < 0) ? -1 : 2 * K1;   // -1: rejected below; garbage on iopt = 1: fresh start
+        // -1: rejected below (nk1 > m fails fpchec, core:2519); garbage on iopt = 1: a fresh start
+        if (PAR && (n < 2 * K1 || n > nest || n > m + K1)) n = (iopt < 0) ? -1 : 2 * K1;
         for (int i = lane; i < n; i += 32) ts[i] = p.t[(size_t)b * nest + i];
         if (iopt > 0)
             for (int i = lane; i < n; i += 32) {
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
             FPI_(n) = fp0;
             NRD_(n) = nplus;
         }
-        back_subst_solo<K1, ND>(as, cc, nest, nk1, lane);
+        back_subst_solo<K1, ND>(as, cc, ncap, nk1, lane);
         if (iopt < 0) {
             done = true;
             break;
@@ -648,7 +652,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
                     __syncwarp();
                 }
             }
-            back_subst_solo<K2, ND>(gs, cc, nest, nk1, lane);
+            back_subst_solo<K2, ND>(gs, cc, ncap, nk1, lane);
             // fp = sum of squared residuals in point order, core:5061-5069
             for (int it = lane; it < m; it += 32) {
                 const int l0 = llag[it] - K2;
@@ -745,7 +749,7 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
         }
         // curfit: c(1:nk1); parcur: coordinate d at c(d*n + 1 : d*n + nk1) (core:8981-8985)
         for (int d = 0; d < ND; ++d)
-            for (int i = lane; i < nk1; i += 32) p.c[(size_t)b * p.c_stride + (size_t)d * n + i] = cc[d * nest + i];
+            for (int i = lane; i < nk1; i += 32) p.c[(size_t)b * p.c_stride + (size_t)d * n + i] = cc[d * ncap + i];
     }
 #undef T_
 #undef CD_
@@ -760,8 +764,9 @@ __global__ void __launch_bounds__(32) curfit_solo_kernel(SoloParams p)
 size_t solo_smem_bytes(int m, int k, int nest, int idim)
 {
     const size_t k1 = k + 1, k2 = k + 2, nd = idim;
-    const size_t doubles = (size_t)m * (2 + 2 * nd + k1 + k1 + nd) + (size_t)nest * (2 + nd + (k1 + nd) + (k2 + nd) + k2);
-    return doubles * 8 + ((size_t)2 * m + 2 * (size_t)nest) * 4;
+    const size_t ncap = (size_t)std::min(nest, m + k + 1);
+    const size_t doubles = (size_t)m * (2 + 2 * nd + k1 + k1 + nd) + ncap * (2 + nd + (k1 + nd) + (k2 + nd) + k2);
+    return doubles * 8 + ((size_t)2 * m + 2 * ncap) * 4;
 }
 
 bool solo_supports(int k, int idim, int par)

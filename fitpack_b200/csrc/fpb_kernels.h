@@ -206,7 +206,7 @@ struct SoloParams {
 };
 size_t solo_smem_bytes(int m, int k, int nest, int idim);
 bool solo_supports(int k, int idim, int par);
-constexpr size_t kSoloSmemMax = 200 * 1024;
+constexpr size_t kSoloSmemMax = 224 * 1024;   // of the 227 KB a CTA may have on sm_100
 cudaError_t launch_curfit_solo(const SoloParams &p, cudaStream_t stream);
 
 cudaError_t launch_fp64_probe(double *scratch, int blocks, int iters, int fused, cudaStream_t stream);

@@ -131,6 +131,13 @@ def test_curves_too_large_for_shared_memory_take_the_batch_kernels(F):
     """the warp-per-curve kernel keeps the curve in shared memory (200 KB); beyond that the same call runs on the batch
     kernels -- same bits"""
     rng = np.random.default_rng(9)
+    # 820 points with the handle API's nest = 1.4 m still fit (the shared arrays are min(nest, m+k+1) long) ...
+    m, k = 820, 3
+    x = np.sort(rng.uniform(0, 1, m))
+    y = np.sin(9 * x) + 0.1 * rng.standard_normal(m)
+    nest = max(102, int(np.ceil(np.float32(1.4) * m)))
+    _check(O.curfit(0, x, y, None, x[0], x[-1], k, 8.0, nest), F.curfit(0, x, y, None, x[0], x[-1], k, 8.0, nest), k)
+    # ... 3000 points do not
     m, k = 3000, 3
     x = np.sort(rng.uniform(0, 1, m))
     y = np.sin(9 * x) + 0.1 * rng.standard_normal(m)
