@@ -56,6 +56,8 @@ SYMBOLS = {
     "fpb_engine_set_curev_mode": (_I32, [_VP, _I32]),
     "fpb_engine_set_bispev_mode": (_I32, [_VP, _I32]),
     "fpb_set_single_curve_kernel": (_I32, [_I32]),
+    "fpb_host_sharers": (_I32, []),
+    "fpb_host_form": (C.c_char_p, [_I64]),
     "fpb_engine_last_kernel_ms": (_F64, [_VP]),
     "fpb_probe_fp64_gops": (_F64, [_VP, _I32]),
     "fpb_selftest_fastmath": (_I32, [_VP, _I64, _I64, _VP]),

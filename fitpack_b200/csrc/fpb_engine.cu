@@ -1106,6 +1106,17 @@ int host_sharers()
     return std::max(env_ranks, std::max(1, g_slices_in_flight.load()));
 }
 
+// Does a large fresh fit of `total` curves per slice take the wavefront form (true) or the chunk-per-engine form?
+// (fit_slice_host adds the conditions on the call itself: iopt = 0, own abscissae, no continuation state, memory.)
+bool wavefront_preferred(long long total)
+{
+    static const char *mode = std::getenv("FPB_HOST_MODE");
+    if (total < 4 * 65536 || total > 0x3fffffff) return false;
+    if (mode && std::strcmp(mode, "workers") == 0) return false;
+    if (mode && std::strcmp(mode, "wave") == 0) return true;
+    return host_sharers() <= 4;   // see host_sharers()
+}
+
 // Wavefront form of the host-pointer batch fit (large fresh fits, iopt = 0): ONE pipeline over the whole slice
 // on one engine.  The inputs stream in as chunks on a copy stream (H2D into two alternating staging sets, tile
 // transpose into the slice-wide point-major arrays); each chunk's curves join the running pipeline at the first
@@ -1516,12 +1527,9 @@ int32_t fit_slice_host(int device, long long b0, long long b1, FP_SIZE iopt, FP_
     // large fresh fits: one pipeline over the slice, chunks joining as they arrive (FPB_HOST_MODE=workers: the
     // chunk-per-engine form below)
     {
-        static const bool force_workers = std::getenv("FPB_HOST_MODE") && std::strcmp(std::getenv("FPB_HOST_MODE"), "workers") == 0;
         const size_t per_curve_w = (size_t)m * 8 * 2 * (w ? 3 : 2) + (size_t)nest * 8 * 4 + 64;   // slice-wide device bytes per curve
-        static const bool force_wave = std::getenv("FPB_HOST_MODE") && std::strcmp(std::getenv("FPB_HOST_MODE"), "wave") == 0;
-        const bool host_bound = !force_wave && host_sharers() > 4;   // see host_sharers()
-        if (!force_workers && !host_bound && iopt == 0 && !shared_x && !fpint && !nrdata && total >= 4 * 65536 &&
-            total <= 0x3fffffff && (size_t)total * per_curve_w <= ((size_t)40 << 30))
+        if (wavefront_preferred(total) && iopt == 0 && !shared_x && !fpint && !nrdata &&
+            (size_t)total * per_curve_w <= ((size_t)40 << 30))
             return fit_slice_wavefront(e0, b0, b1, m, x, y, w, xb, xe, k, s, nest, n, t, c, fp, ier);
     }
     int workers = 4;   // measured (profiles/r02_e2e.md): 2 -> 209 ms, 3 -> 213 ms, 4 -> 184 ms, 6 -> 190 ms per 2^20 curves
@@ -1785,6 +1793,14 @@ int32_t shard_units_over_gpus(long long total, int ngpus, long long align,
 extern "C" {
 
 int32_t fpb_set_single_curve_kernel(int32_t on) { return g_solo_on.exchange(on ? 1 : 0); }
+
+int32_t fpb_host_sharers(void) { return host_sharers(); }
+
+const char *fpb_host_form(int64_t nbatch)
+{
+    if (nbatch <= kSoloMaxBatch && g_solo_on.load()) return "warp-per-curve";
+    return wavefront_preferred(nbatch) ? "wavefront" : "chunks";
+}
 
 
 int32_t fp_curfit_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE m, const FP_REAL *x,

@@ -266,6 +266,15 @@ module fitpack_b200
          import :: c_int32_t
          integer(c_int32_t), value :: on
       end function fpb_set_single_curve_kernel
+      ! ranks / slices assumed to share this host (LOCAL_WORLD_SIZE, ... or FPB_LOCAL_RANKS)
+      integer(c_int32_t) function fpb_host_sharers() bind(C,name="fpb_host_sharers")
+         import :: c_int32_t
+      end function fpb_host_sharers
+      ! form of the host-pointer batch fit for nbatch curves per GPU slice (C string: "warp-per-curve", "wavefront", "chunks")
+      type(c_ptr) function fpb_host_form(nbatch) bind(C,name="fpb_host_form")
+         import :: c_ptr, c_int64_t
+         integer(c_int64_t), value :: nbatch
+      end function fpb_host_form
       integer(c_int32_t) function fpb_engine_set_bispev_mode(eng,mode) bind(C,name="fpb_engine_set_bispev_mode")
          import :: c_ptr, c_int32_t
          type(c_ptr), value :: eng

@@ -172,6 +172,13 @@ int32_t fpb_engine_set_curev_mode(fpb_engine *eng, int32_t mode);
    latency; 0 the batch kernels with one thread per curve.  Same bits either way.  Process-wide; returns the
    previous setting (the environment variable FPB_SOLO=0 sets the initial one). */
 int32_t fpb_set_single_curve_kernel(int32_t on);
+/* How many ranks / slices this process assumes are copying through the same host (LOCAL_WORLD_SIZE,
+   OMPI_COMM_WORLD_LOCAL_SIZE, SLURM_NTASKS_PER_NODE or FPB_LOCAL_RANKS; at least 1), and which form of the
+   host-pointer batch fit a fresh fit (iopt = 0, own abscissae) of `nbatch` curves per GPU slice takes with it:
+   "warp-per-curve" (small batches), "wavefront" (one pipeline the chunks join as they land) or "chunks" (chunk per
+   engine; the choice when more than 4 sharers make the host the bound).  DESIGN.md section 5.  No GPU needed. */
+int32_t fpb_host_sharers(void);
+const char *fpb_host_form(int64_t nbatch);
 /* number of kernels this engine has launched since creation (bench bookkeeping) */
 int64_t fpb_engine_launch_count(const fpb_engine *eng);
 /* same counter for the DEFAULT engine of `device` -- the one the host-pointer entry points
