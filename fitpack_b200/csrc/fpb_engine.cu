@@ -1699,87 +1699,116 @@ template <class F> int32_t shard_over_gpus(long long total, int ngpus, long long
 }  // namespace
 
 namespace fpb {
-bool parcur_solo_host(int32_t iopt, int32_t ipar, int32_t idim, int32_t m, double *u, const double *x, const double *w,
-                      double *ub, double *ue, int32_t k, double s, int32_t nest, int32_t *n, double *t, double *c,
-                      double *fp, double *fpint, int32_t *nrdata, int32_t *ier)
+bool parcur_solo_host(fpb_engine *eng, long long nb, int32_t iopt, int32_t ipar, int32_t idim, int32_t m, double *u,
+                      const double *x, const double *w, double *ub, double *ue, int32_t k, double s, int32_t nest,
+                      int32_t *n, double *t, double *c, double *fp, int32_t *ier, double *fpint, int32_t *nrdata,
+                      int32_t *status)
 {
-    if (!g_solo_on.load() || !w || !fpint || !nrdata || !solo_supports(k, idim, 1) ||
+    if (!g_solo_on.load() || nb < 1 || nb > kSoloMaxBatch || !solo_supports(k, idim, 1) ||
         solo_smem_bytes(m, k, nest, idim) > kSoloSmemMax)
         return false;
-    HostApiLock lk(-1);
-    fpb_engine *eng = default_engine(-1);
-    if (!eng) {
-        *ier = FPB_ERR_CUDA;
+    if (iopt == 1 && (!fpint || !nrdata)) return false;
+    *status = FPB_STATUS_OK;
+    auto fail = [&](int32_t rc) {
+        *status = rc;
+        for (long long b = 0; b < nb; ++b) ier[b] = rc;
         return true;
-    }
+    };
     DeviceGuard g(eng->device);
-    if (!g.ok) {
-        *ier = FPB_ERR_CUDA;
-        return true;
-    }
+    if (!g.ok) return fail(FPB_ERR_CUDA);
     const int k1 = k + 1, nmin = 2 * k1, nmax = m + k1;
-    const bool chord = (ipar == 0 && iopt <= 0);
-    // ---- packed block, in doubles: u | x | w | ub ue fp | n ier | t | c | fpint | nrdata ----
-    const size_t o_x = m, o_w = o_x + (size_t)m * idim, o_be = o_w + m, o_ni = o_be + 3, o_t = o_ni + 1,
-                 o_c = o_t + nest, o_f = o_c + (size_t)nest * idim, o_nrd = o_f + nest, o_end = o_nrd + ((size_t)nest + 1) / 2;
-    if (!eng->scratch[0].reserve(o_end * 8) || !reserve_pinned((void **)&eng->h_solo, &eng->h_solo_bytes, o_end * 8)) {
-        *ier = FPB_ERR_ALLOC;
-        return true;
+    const bool chord = (ipar == 0 && iopt <= 0), want_state = fpint && nrdata;
+    // ---- block, in doubles: u | x | w | ub,ue | fp | n | ier | t | c | fpint | nrdata ----
+    const size_t pts = (size_t)nb * m, kn = (size_t)nb * nest, half = ((size_t)nb + 1) / 2;
+    const size_t o_x = pts, o_w = o_x + pts * idim, o_be = o_w + pts, o_fp = o_be + 2 * (size_t)nb, o_n = o_fp + nb,
+                 o_ier = o_n + half, o_t = o_ier + half, o_c = o_t + kn, o_f = o_c + kn * idim, o_nrd = o_f + kn,
+                 o_end = o_nrd + (kn + 1) / 2;
+    // pinned mirror from where the host needs it: everything for one curve; for more, u / x / w go up from the caller's
+    // arrays (w = NULL: ones from the mirror)
+    const size_t h0 = (nb == 1) ? 0 : (w ? o_be : o_w);
+    if (!eng->scratch[0].reserve(o_end * 8) ||
+        !reserve_pinned((void **)&eng->h_solo, &eng->h_solo_bytes, (o_end - h0) * 8))
+        return fail(FPB_ERR_ALLOC);
+    double *hd = eng->h_solo - h0, *dd = eng->scratch[0].as<double>();   // hd + offset is valid for offsets >= h0
+    int *hn = reinterpret_cast<int *>(hd + o_n), *hier = reinterpret_cast<int *>(hd + o_ier),
+        *hnrd = reinterpret_cast<int *>(hd + o_nrd);
+    for (long long b = 0; b < nb; ++b) {
+        const int n_in = (iopt != 0) ? n[b] : 0;
+        const bool n_ok = n_in >= nmin && n_in <= nest;
+        hd[o_be + 2 * b] = ub[b];
+        hd[o_be + 2 * b + 1] = ue[b];
+        hd[o_fp + b] = fp[b];
+        hn[b] = n_in;
+        hier[b] = 0;
+        if (iopt != 0 && n_ok) std::memcpy(hd + o_t + (size_t)b * nest, t + (size_t)b * nest, (size_t)n_in * 8);
+        if (iopt == 1 && n_ok) {
+            std::memcpy(hd + o_f + (size_t)b * nest, fpint + (size_t)b * nest, (size_t)n_in * 8);
+            std::memcpy(hnrd + (size_t)b * nest, nrdata + (size_t)b * nest, (size_t)n_in * 4);
+        }
     }
-    double *hd = eng->h_solo, *dd = eng->scratch[0].as<double>();
-    int *hni = reinterpret_cast<int *>(hd + o_ni), *hnrd = reinterpret_cast<int *>(hd + o_nrd);
-    const int n_in = (iopt != 0) ? *n : 0;
-    const bool n_ok = n_in >= nmin && n_in <= nest;
-    if (!chord) std::memcpy(hd, u, (size_t)m * 8);
-    std::memcpy(hd + o_x, x, (size_t)m * idim * 8);
-    std::memcpy(hd + o_w, w, (size_t)m * 8);
-    hd[o_be] = *ub;
-    hd[o_be + 1] = *ue;
-    hd[o_be + 2] = *fp;
-    hni[0] = n_in;
-    hni[1] = 0;
-    if (iopt != 0 && n_ok) std::memcpy(hd + o_t, t, (size_t)n_in * 8);
-    if (iopt == 1 && n_ok) {
-        std::memcpy(hd + o_f, fpint, (size_t)n_in * 8);
-        std::memcpy(hnrd, nrdata, (size_t)n_in * 4);
+    cudaStream_t st = eng->stream;
+    bool ok = true;
+    if (nb == 1) {
+        if (!chord) std::memcpy(hd, u, pts * 8);
+        std::memcpy(hd + o_x, x, pts * idim * 8);
+        if (w) std::memcpy(hd + o_w, w, pts * 8);
+        else std::fill(hd + o_w, hd + o_be, 1.0);
+        ok = cuda_ok(cudaMemcpyAsync(dd, hd, (iopt == 1 ? o_end : o_c) * 8, cudaMemcpyHostToDevice, st), "H2D curve");
+    } else {
+        if (!chord) ok = cuda_ok(cudaMemcpyAsync(dd, u, pts * 8, cudaMemcpyHostToDevice, st), "H2D u");
+        ok = ok && cuda_ok(cudaMemcpyAsync(dd + o_x, x, pts * idim * 8, cudaMemcpyHostToDevice, st), "H2D x");
+        if (w) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(dd + o_w, w, pts * 8, cudaMemcpyHostToDevice, st), "H2D w");
+        } else {
+            std::fill(hd + o_w, hd + o_be, 1.0);
+            ok = ok && cuda_ok(cudaMemcpyAsync(dd + o_w, hd + o_w, pts * 8, cudaMemcpyHostToDevice, st), "H2D w");
+        }
+        ok = ok && cuda_ok(cudaMemcpyAsync(dd + o_be, hd + o_be, ((iopt != 0 ? o_c : o_t) - o_be) * 8, cudaMemcpyHostToDevice, st),
+                           "H2D state");
+        if (iopt == 1)
+            ok = ok && cuda_ok(cudaMemcpyAsync(dd + o_f, hd + o_f, (o_end - o_f) * 8, cudaMemcpyHostToDevice, st), "H2D state");
     }
     SoloParams p;
     std::memset(&p, 0, sizeof p);
-    p.nbatch = 1; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest;
+    p.nbatch = (int)nb; p.iopt = iopt; p.m = m; p.k = k; p.nest = nest;
     p.idim = idim; p.par = 1; p.chord = chord ? 1 : 0; p.s = s;
-    p.x = dd; p.u_out = dd; p.y = dd + o_x; p.w = dd + o_w; p.ube = dd + o_be; p.fp = dd + o_be + 2;
-    p.n = reinterpret_cast<int *>(dd + o_ni); p.ier = p.n + 1;
+    p.x = dd; p.u_out = dd; p.y = dd + o_x; p.w = dd + o_w; p.ube = dd + o_be; p.fp = dd + o_fp;
+    p.n = reinterpret_cast<int *>(dd + o_n); p.ier = reinterpret_cast<int *>(dd + o_ier);
     p.t = dd + o_t; p.c = dd + o_c; p.c_stride = (long long)nest * idim;
     p.fpint = dd + o_f; p.nrdata = reinterpret_cast<int *>(dd + o_nrd);
-    cudaStream_t st = eng->stream;
-    const bool ok = cuda_ok(cudaMemcpyAsync(dd, hd, (iopt == 1 ? o_end : o_c) * 8, cudaMemcpyHostToDevice, st), "H2D curve") &&
-                    cuda_ok(launch_curfit_solo(p, st), "curfit_solo_kernel (parcur)") &&
-                    cuda_ok(cudaMemcpyAsync(hd, dd, o_end * 8, cudaMemcpyDeviceToHost, st), "D2H fit") &&
-                    cuda_ok(cudaStreamSynchronize(st), "sync");
+    ok = ok && cuda_ok(launch_curfit_solo(p, st), "curfit_solo_kernel (parcur)");
+    if (chord) ok = ok && cuda_ok(cudaMemcpyAsync(u, dd, pts * 8, cudaMemcpyDeviceToHost, st), "D2H u");
+    ok = ok && cuda_ok(cudaMemcpyAsync(hd + o_be, dd + o_be, ((want_state ? o_end : o_f) - o_be) * 8, cudaMemcpyDeviceToHost, st),
+                       "D2H fit") &&
+         cuda_ok(cudaStreamSynchronize(st), "sync");
     eng->launches++;
-    if (!ok) {
-        *ier = FPB_ERR_CUDA;
-        return true;
+    if (!ok) return fail(FPB_ERR_CUDA);
+    const bool untouched_all = (iopt >= 0 && s <= 0.0 && nmax > nest);   // ier = 1 before anything was computed
+    for (long long b = 0; b < nb; ++b) {
+        const int n_out = hn[b], ier_out = hier[b];
+        ier[b] = ier_out;
+        if (chord) {   // the parameters are computed before the checks (core:15238-15253): visible either way
+            ub[b] = hd[o_be + 2 * b];
+            ue[b] = hd[o_be + 2 * b + 1];
+        }
+        if (ier_out == FPB_INPUT_ERROR) {   // the clamped end knots of a rejected iopt = -1 curve (core:15264-15270)
+            const int n_in = (iopt != 0) ? n[b] : 0;
+            if (iopt < 0 && n_in >= nmin && n_in <= nest && n_in <= nmax)
+                std::memcpy(t + (size_t)b * nest, hd + o_t + (size_t)b * nest, (size_t)n_in * 8);
+            continue;
+        }
+        n[b] = n_out;
+        if (untouched_all || n_out < nmin || n_out > nest) continue;
+        fp[b] = hd[o_fp + b];
+        std::memcpy(t + (size_t)b * nest, hd + o_t + (size_t)b * nest, (size_t)n_out * 8);
+        for (int d = 0; d < idim; ++d)
+            std::memcpy(c + (size_t)b * nest * idim + (size_t)d * n_out, hd + o_c + (size_t)b * nest * idim + (size_t)d * n_out,
+                        (size_t)(n_out - k1) * 8);
+        if (want_state) {
+            std::memcpy(fpint + (size_t)b * nest, hd + o_f + (size_t)b * nest, (size_t)n_out * 8);
+            std::memcpy(nrdata + (size_t)b * nest, hnrd + (size_t)b * nest, (size_t)n_out * 4);
+        }
     }
-    const int n_out = hni[0], ier_out = hni[1];
-    *ier = ier_out;
-    if (chord) {   // the parameters are computed before the checks (core:15238-15253): the caller sees them either way
-        std::memcpy(u, hd, (size_t)m * 8);
-        *ub = hd[o_be];
-        *ue = hd[o_be + 1];
-    }
-    if (ier_out == FPB_INPUT_ERROR) {
-        if (iopt < 0 && n_ok) std::memcpy(t, hd + o_t, (size_t)n_in * 8);   // the clamped end knots (core:15264-15270)
-        return true;
-    }
-    *n = n_out;
-    if ((iopt >= 0 && s <= 0.0 && nmax > nest) || n_out < nmin || n_out > nest) return true;   // ier = 1, nothing computed
-    *fp = hd[o_be + 2];
-    std::memcpy(t, hd + o_t, (size_t)n_out * 8);
-    for (int d = 0; d < idim; ++d)
-        std::memcpy(c + (size_t)d * n_out, hd + o_c + (size_t)d * n_out, (size_t)(n_out - k1) * 8);
-    std::memcpy(fpint, hd + o_f, (size_t)n_out * 8);
-    std::memcpy(nrdata, hnrd, (size_t)n_out * 4);
     return true;
 }
 

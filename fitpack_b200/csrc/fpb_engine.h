@@ -102,12 +102,14 @@ struct FitArrival {
     cudaEvent_t ready;
 };
 int32_t run_fit_pipeline(fpb_engine *eng, FitParams p, const std::vector<FitArrival> *arrivals = nullptr);
-// ONE parametric curve from host memory on the warp-per-curve kernel (fp_parcur_c; fpb_curfit_solo.cu).  Returns
-// false when the call is not one for that kernel (idim other than 2 or 3, too large for its shared memory, switched
-// off): the caller then takes the batch path.  Otherwise *ier is the reference's flag or an FPB_ERR_* code.
-bool parcur_solo_host(int32_t iopt, int32_t ipar, int32_t idim, int32_t m, double *u, const double *x, const double *w,
-                      double *ub, double *ue, int32_t k, double s, int32_t nest, int32_t *n, double *t, double *c,
-                      double *fp, double *fpint, int32_t *nrdata, int32_t *ier);
+// A few parametric curves from host memory on the warp-per-curve kernel (fp_parcur_c, small fp_parcur_batch_c slices;
+// fpb_curfit_solo.cu), on `eng` (the caller holds its HostApiLock).  Returns false when the call is not one for that
+// kernel (idim other than 2 or 3, too large for its shared memory, too many curves, switched off): the caller then
+// takes the batch path.  Otherwise ier[b] is the reference's flag, or *status / ier[] an FPB_ERR_* code.
+bool parcur_solo_host(fpb_engine *eng, long long nb, int32_t iopt, int32_t ipar, int32_t idim, int32_t m, double *u,
+                      const double *x, const double *w, double *ub, double *ue, int32_t k, double s, int32_t nest,
+                      int32_t *n, double *t, double *c, double *fp, int32_t *ier, double *fpint, int32_t *nrdata,
+                      int32_t *status);
 // contiguous slices [b0, b1) of `total` units over the first `ngpus` devices (<= 0: all), one host
 // thread + default engine per device; fn(engine, b0, b1) runs on each (no collective)
 int32_t shard_units_over_gpus(long long total, int ngpus, long long align,

@@ -341,6 +341,15 @@ int32_t fp_parcur_batch_c(FP_SIZE nbatch, FP_SIZE iopt, FP_SIZE ipar, FP_SIZE id
     }
     // contiguous slices of the batch per GPU, one host thread + engine per device (no collective)
     return shard_units_over_gpus(nbatch, ngpus, 128, [&](fpb_engine *eng, long long s0, long long s1) -> int32_t {
+    {   // a few curves (fp_parcur_c: one): the warp-per-curve kernel
+        int32_t status = FPB_STATUS_OK;
+        const size_t md0 = (size_t)m * idim;
+        if (parcur_solo_host(eng, s1 - s0, iopt, ipar, idim, m, u + (size_t)s0 * m, x + (size_t)s0 * md0,
+                             w ? w + (size_t)s0 * m : nullptr, ub + s0, ue + s0, k, s, nest, n + s0, t + (size_t)s0 * nest,
+                             c + (size_t)s0 * nest * idim, fp + s0, ier + s0, fpint ? fpint + (size_t)s0 * nest : nullptr,
+                             nrdata ? nrdata + (size_t)s0 * nest : nullptr, &status))
+            return status;
+    }
     Guard g(eng->device);
     if (!g.ok) return FPB_ERR_CUDA;
     cudaStream_t st = eng->stream;
@@ -450,7 +459,6 @@ void fp_parcur_c(FP_SIZE iopt, FP_SIZE ipar, FP_SIZE idim, FP_SIZE m, FP_REAL *u
     if (mx < m * idim || nc < nest * idim) return;
     if (lwrk < m * (k + 1) + nest * (6 + idim + 3 * k)) return;
     // wrk(1:nest) is fpint and iwrk(1:nest) is nrdata (core:15275-15283): the iopt=1 state
-    if (parcur_solo_host(iopt, ipar, idim, m, u, x, w, ub, ue, k, *s, nest, n, t, c, fp, wrk, iwrk, ier)) return;
     FP_FLAG ier1 = FPB_INPUT_ERROR;
     const int32_t rc = fp_parcur_batch_c(1, iopt, ipar, idim, m, u, x, w, ub, ue, k, *s, nest, n, t, c, fp,
                                          &ier1, wrk, iwrk, 1);

@@ -10,7 +10,7 @@ import pytest
 import oracle_lib as O
 import test_gpu_deviations
 import test_gpu_parity
-from test_gpu_parity import F, _same  # noqa: F401  (fixture)
+from test_gpu_parity import F, eng, _same  # noqa: F401  (fixtures)
 
 pytestmark = pytest.mark.gpu
 
@@ -263,3 +263,44 @@ def test_parcur_rejected_inputs_on_the_warp_per_curve_kernel(F):
         assert o["ier"] == g["ier"] == 10
         _same_parcur(o, g, idim, k)
         assert _same(o["t"], g["t"]) and _same(o["c"], g["c"])
+
+
+@pytest.mark.parametrize("idim,k,weights,ipar", [(2, 3, False, 0), (3, 5, True, 1)])
+def test_parcur_host_batches_also_pass_on_the_batch_kernels(F, eng, idim, k, weights, ipar):
+    """fp_parcur_batch_c slices of up to 4096 curves (idim 2, 3) run one warp per curve by default -- which is what
+    test_gpu_parity.test_parcur_batch_bit_exact_vs_oracle (1500 curves) now exercises; here the same test on the batch
+    kernels, and the rejected-curve test on both"""
+    with single_curve_kernel(F, False):
+        test_gpu_parity.test_parcur_batch_bit_exact_vs_oracle(F, eng, idim, k, weights, ipar)
+    for on in (True, False):
+        with single_curve_kernel(F, on):
+            test_gpu_parity.test_parcur_percur_batches_with_invalid_curves(F)
+            import test_gpu_boundary
+            test_gpu_boundary.test_parcur_batch_rejected_rows_keep_the_callers_n_t_c(F)
+
+
+def test_parcur_small_batch_continuation_and_given_knots(F):
+    """iopt = 1 and iopt = -1 for a small batch of parametric curves through fp_parcur_batch_c"""
+    from refdata import synth_param_curves
+    rng = np.random.default_rng(314)
+    B, m, idim, k = 200, 80, 2, 3
+    th, x = synth_param_curves(rng, B, m, idim)
+    nest, s = m + k + 1, m * 0.0025 * idim
+    o = O.parcur_batch(0, 0, idim, x, None, k, s, nest)
+    g = F.parcur_batch(0, 0, idim, x, None, k, s, nest)
+    assert _same(g["n"], o["n"]) and _same(g["fp"], o["fp"]) and _same(g["u"], o["u"])
+    # least squares on the knots found, per curve (the oracle one curve at a time)
+    g2 = F.parcur_batch(-1, 0, idim, x, None, k, s, nest, u=g["u"], ub=g["ub"], ue=g["ue"], n=g["n"], t=g["t"])
+    g1 = F.parcur_batch(1, 0, idim, x, None, k, s * 0.3, nest, u=g["u"], ub=g["ub"], ue=g["ue"], n=g["n"], t=g["t"],
+                        fpint=g["fpint"], nrdata=g["nrdata"], c=g["c"])
+    for b in range(0, B, 7):
+        ob = O.parcur(0, 0, idim, x[b], None, k, s, nest)
+        o2 = O.parcur(-1, 0, idim, x[b], None, k, s, nest, u=ob["u"], ub=ob["ub"], ue=ob["ue"], n=ob["n"], t=ob["t"])
+        o1 = O.parcur(1, 0, idim, x[b], None, k, s * 0.3, nest, u=ob["u"], ub=ob["ub"], ue=ob["ue"], n=ob["n"], t=ob["t"],
+                      wrk=ob["wrk"], iwrk=ob["iwrk"], c=ob["c"])
+        for gg, oo in ((g2, o2), (g1, o1)):
+            n = int(oo["n"])
+            assert int(gg["n"][b]) == n and int(gg["ier"][b]) == oo["ier"] and gg["fp"][b] == oo["fp"], b
+            assert _same(gg["t"][b, :n], oo["t"][:n])
+            for d in range(idim):
+                assert _same(gg["c"][b, d * n:d * n + n - k - 1], oo["c"][d * n:d * n + n - k - 1])
