@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libfitpack_b200.so")
 
-SOURCES = ["fpb_curfit.cu", "fpb_curfit_d2.cu", "fpb_curfit_d3.cu", "fpb_curfit_d0.cu", "fpb_curfit_solo.cu", "fpb_splev.cu", "fpb_shared.cu", "fpb_util.cu", "fpb_regrid.cu", "fpb_calculus.cu", "fpb_parcur.cu", "fpb_percur.cu",
+SOURCES = ["fpb_curfit.cu", "fpb_curfit_d2.cu", "fpb_curfit_d3.cu", "fpb_curfit_d0.cu", "fpb_curfit_solo.cu", "fpb_splev.cu", "fpb_shared.cu", "fpb_util.cu", "fpb_regrid.cu", "fpb_calculus.cu", "fpb_parcur.cu", "fpb_percur.cu", "fpb_percur_solo.cu",
            "fpb_engine.cu",
            "fpb_curve.cpp"]
 
@@ -73,6 +73,8 @@ def build(force=False, verbose=False):
         deps = [s] + headers
         if src.startswith("fpb_curfit_d"):
             deps.append(os.path.join(CSRC, "fpb_curfit.cu"))
+        if src == "fpb_percur_solo.cu":
+            deps.append(os.path.join(CSRC, "fpb_percur.cu"))
         if force or _stale(o, deps):
             jobs.append((s, o))
 

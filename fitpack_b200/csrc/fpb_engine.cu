@@ -316,6 +316,12 @@ void fitpack_message_c(FP_FLAG ierr, char *msg)
 
 } // extern "C"
 
+namespace {
+// a few curves: the warp-per-curve / curve-per-CTA kernels (1) or the batch kernels (0); fpb_set_single_curve_kernel
+std::atomic<int> g_solo_on{(std::getenv("FPB_SOLO") && std::atoi(std::getenv("FPB_SOLO")) == 0) ? 0 : 1};
+constexpr int kPerSoloMaxBatch = 1024;
+}  // namespace
+
 namespace fpb {
 // The pass pipeline shared by curfit (idim = 1) and parcur: `p` arrives with the caller's arrays,
 // strides and scalars set; this fills in the engine-owned workspace / state and runs the passes.
@@ -420,6 +426,16 @@ int32_t run_fit_pipeline(fpb_engine *eng, FitParams p, const std::vector<FitArri
     // late ones (a list entry with the top bit set has not had its first pass).  Otherwise: pass 1 over the
     // whole batch (identity list), then passes over the shrinking list of curves that still need a finer
     // knot set; the host reads the list length every other pass.
+    // A few periodic curves: the whole of fpperi per curve in ONE launch, the curve's workspace in shared memory
+    // (fpb_percur_solo.cu), instead of ~2R launches of threads working out of global memory with a host read-back
+    // between them.
+    if (p.periodic && nbatch <= kPerSoloMaxBatch && g_solo_on.load() &&
+        percur_solo_smem_bytes(m, k, L.ws_per_lane, L.nestp) <= kSoloSmemMax) {
+        if (!cuda_ok(launch_percur_solo(p, st), "percur_solo_kernel")) return FPB_ERR_CUDA;
+        eng->launches++;
+        end_timing(eng);
+        return FPB_STATUS_OK;
+    }
     const bool staged = arrivals != nullptr && !arrivals->empty() && iopt >= 0 && !p.periodic;
     p.staged = staged ? 1 : 0;
     size_t next_arr = 0;
@@ -1320,9 +1336,6 @@ int32_t fit_slice_wavefront(fpb_engine *eng, long long b0, long long b1, FP_SIZE
 // pieces dealt round-robin to `workers` host threads, each with its own engine (stream, workspace,
 // staging): the copies of one chunk and the sparsely populated tail of its fit overlap the other workers'
 // compute.  FPB_HOST_WORKERS (1..4) / FPB_HOST_CHUNKS override the defaults.
-// batch of one from host memory: warp-per-curve kernel (1) or the batch kernels (0); fpb_set_single_curve_kernel
-std::atomic<int> g_solo_on{(std::getenv("FPB_SOLO") && std::atoi(std::getenv("FPB_SOLO")) == 0) ? 0 : 1};
-
 // fpchec, core:2507-2570 (host form: the flat entry point has the knots and abscissae in host memory)
 int host_fpchec(const double *x, int m, const double *t, int n, int k)
 {

@@ -135,6 +135,9 @@ cudaError_t launch_percur_pass(const FitParams &p, int grid, cudaStream_t st, co
 cudaError_t launch_percur_part2(const FitParams &p, int grid, cudaStream_t st, const int *list,
                                 const int *count);
 int percur_resident_warps(int k, int nsm);
+// a few periodic curves: one CTA per curve, workspace in shared memory, one launch (fpb_percur_solo.cu)
+size_t percur_solo_smem_bytes(int m, int k, int ws_per_lane, int nestp);
+cudaError_t launch_percur_solo(const FitParams &p, cudaStream_t stream);
 // chord-length parameters of parcur (ipar = 0), one thread per curve
 cudaError_t launch_parcur_param(int nbatch, int m, int idim, const double *x, long long x_sb,
                                 long long x_si, long long x_sd, double *u, long long u_sb,

@@ -40,7 +40,8 @@ def test_default_is_the_warp_per_curve_kernel(F):
 @pytest.mark.parametrize("name", ["test_mncurf_sequence_bit_exact", "test_curfit_golden_vectors_bit_exact",
                                   "test_curfit_input_errors_leave_outputs_untouched", "test_curve_handle_api",
                                   "test_host_batch_api_matches_oracle",
-                                  "test_parcur_golden_cases_flat_abi_bit_exact"])
+                                  "test_parcur_golden_cases_flat_abi_bit_exact",
+                                  "test_percur_golden_cases_flat_abi_bit_exact"])
 def test_flat_abi_tests_also_pass_on_the_batch_kernels(F, name):
     """the tests of test_gpu_parity run on the warp-per-curve kernel by default; here on one thread per curve"""
     with single_curve_kernel(F, False):
@@ -304,3 +305,45 @@ def test_parcur_small_batch_continuation_and_given_knots(F):
             assert _same(gg["t"][b, :n], oo["t"][:n])
             for d in range(idim):
                 assert _same(gg["c"][b, d * n:d * n + n - k - 1], oo["c"][d * n:d * n + n - k - 1])
+
+
+def test_percur_on_the_curve_per_cta_kernel(F):
+    """fp_percur_c and fp_percur_batch_c slices of up to 1024 curves: fpperi (core:9668-10192) per curve in one launch,
+    the curve's workspace in shared memory (fpb_percur_solo.cu: the per-curve code of the batch kernels compiled with
+    unit stride).  Random fits with continuations, and a small batch, bit for bit against the oracle."""
+    rng = np.random.default_rng(31)
+    for trial in range(60):
+        k = int(rng.integers(1, 6))
+        m = int(rng.integers(2 * k + 4, 200))
+        x = np.sort(rng.uniform(0, 2 * np.pi, m))
+        x[0], x[-1] = 0.0, 2 * np.pi
+        y = np.sin(x * int(rng.integers(1, 5))) + 0.05 * rng.standard_normal(m)
+        y[-1] = y[0]
+        w = rng.uniform(0.5, 2.0, m) if trial % 3 else None
+        s = float(m * 0.0025 * rng.choice([0.0, 0.1, 1.0, 10.0, 1000.0]))
+        nest = int(rng.choice([m + 2 * k, max(2 * k + 4, m // 2)]))
+        o = O.percur(0, x, y, w, k, s, nest)
+        g = F.percur(0, x, y, w, k, s, nest)
+        _check(o, g, k)
+        if o["ier"] > 0 or s == 0.0 or trial % 2:
+            continue
+        o1 = O.percur(1, x, y, w, k, s * 0.4, nest, n=o["n"], t=o["t"], wrk=o["wrk"], iwrk=o["iwrk"], c=o["c"], fp=o["fp"])
+        g1 = F.percur(1, x, y, w, k, s * 0.4, nest, n=g["n"], t=g["t"], wrk=g["wrk"], iwrk=g["iwrk"], c=g["c"], fp=g["fp"])
+        _check(o1, g1, k)
+    B, m, k, nest = 300, 90, 3, 96
+    th = np.sort(rng.uniform(0, 2 * np.pi, (B, m)), axis=1)
+    th[:, 0], th[:, -1] = 0.0, 2 * np.pi
+    yy = np.sin(2 * th) + 0.1 * rng.standard_normal(th.shape)
+    yy[:, -1] = yy[:, 0]
+    th[5, 10] = th[5, 9]                                  # curve 5: x not increasing -> ier = 10
+    ob = O.percur_batch(0, th, yy, None, k, 0.9, nest)
+    for on in (True, False):
+        with single_curve_kernel(F, on):
+            gb = F.percur_batch(0, th, yy, None, k, 0.9, nest)
+            assert _same(gb["n"], ob["n"]) and _same(gb["ier"], ob["ier"]) and gb["ier"][5] == 10
+            for b in range(B):
+                if b == 5:
+                    continue
+                n = int(ob["n"][b])
+                assert gb["fp"][b] == ob["fp"][b], b
+                assert _same(gb["t"][b, :n], ob["t"][b, :n]) and _same(gb["c"][b, :n - k - 1], ob["c"][b, :n - k - 1]), b
