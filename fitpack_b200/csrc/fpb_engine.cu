@@ -1104,11 +1104,11 @@ int32_t fit_slice_pipelined(fpb_engine *eng, const std::vector<long long> &cuts,
 // How many slices copy through this host at the same time: the ranks the launcher put on this node (torchrun's
 // LOCAL_WORLD_SIZE, Open MPI's and Slurm's equivalents, or FPB_LOCAL_RANKS) or, for one process sharding a call
 // over its GPUs, the number of slices in flight.  Two decisions hang on it.  (1) Helper threads per slice = cores /
-// sharers.  (2) Which host form runs: with more than 4 sharers the host side is the bound (8 GPUs behind one host:
-// 23 GB/s H2D and 9 GB/s D2H per GPU instead of 55 / 50), the copies take longer than the fit, and the wavefront
-// form -- which pays its tail and copy-out after the last byte has landed -- loses to the chunk-per-engine form,
-// whose copy-out overlaps later chunks (298.8 vs 267.7 ms per step of 2^20 curves at 8 GPUs; 168.1 vs 182.5 ms
-// at one GPU).  A rate measured on the copy stream was tried as the signal and flapped between forms (ranks are not
+// sharers.  (2) Which host form runs: with more than 2 sharers the host side starts to be the bound (8 GPUs behind one
+// host: 23 GB/s H2D and 9 GB/s D2H per GPU instead of 55 / 50) and the wavefront form -- which pays its tail, its
+// copy-out and its scatter after the last byte has landed -- loses to the chunk-per-engine form, whose copy-out
+// overlaps later chunks: per step of 2^20 curves 168.1 vs 182.5 ms at one GPU, 188.8 vs 182.9 ms at 4, 298.8 vs
+// 267.7 ms at 8.  A rate measured on the copy stream was tried as the signal and flapped between forms (ranks are not
 // in step during warm-up: 23..54 GB/s on the same box); the launcher's count is deterministic.
 std::atomic<int> g_slices_in_flight{0};
 int host_sharers()
@@ -1130,7 +1130,7 @@ bool wavefront_preferred(long long total)
     if (total < 4 * 65536 || total > 0x3fffffff) return false;
     if (mode && std::strcmp(mode, "workers") == 0) return false;
     if (mode && std::strcmp(mode, "wave") == 0) return true;
-    return host_sharers() <= 4;   // see host_sharers()
+    return host_sharers() <= 2;   // see host_sharers()
 }
 
 // Wavefront form of the host-pointer batch fit (large fresh fits, iopt = 0): ONE pipeline over the whole slice

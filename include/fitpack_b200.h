@@ -176,7 +176,7 @@ int32_t fpb_set_single_curve_kernel(int32_t on);
    OMPI_COMM_WORLD_LOCAL_SIZE, SLURM_NTASKS_PER_NODE or FPB_LOCAL_RANKS; at least 1), and which form of the
    host-pointer batch fit a fresh fit (iopt = 0, own abscissae) of `nbatch` curves per GPU slice takes with it:
    "warp-per-curve" (small batches), "wavefront" (one pipeline the chunks join as they land) or "chunks" (chunk per
-   engine; the choice when more than 4 sharers make the host the bound).  DESIGN.md section 5.  No GPU needed. */
+   engine; the choice when more than 2 sharers make the host the bound).  DESIGN.md section 5.  No GPU needed. */
 int32_t fpb_host_sharers(void);
 const char *fpb_host_form(int64_t nbatch);
 /* number of kernels this engine has launched since creation (bench bookkeeping) */

@@ -2,7 +2,7 @@
 
 Eight ranks copying through one host make the host the bound (23 GB/s per GPU instead of 55): the wavefront form loses
 to the chunk-per-engine form there (298.8 vs 267.7 ms per step, profiles/r02_e2e.md), so the library counts the ranks the
-launcher put on the node and switches above 4."""
+launcher put on the node and switches above 2 (4 GPUs: 188.8 vs 182.9 ms)."""
 import os
 import subprocess
 import sys
@@ -29,7 +29,8 @@ def test_one_rank_takes_the_wavefront_form_for_large_batches():
 def test_eight_ranks_per_node_take_the_chunk_per_engine_form():
     for var in ("LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE", "FPB_LOCAL_RANKS"):
         assert _run({var: "8"}) == ["8", "warp-per-curve", "warp-per-curve", "chunks", "chunks"], var
-    assert _run({"LOCAL_WORLD_SIZE": "4"})[-1] == "wavefront"
+    assert _run({"LOCAL_WORLD_SIZE": "4"})[-1] == "chunks"
+    assert _run({"LOCAL_WORLD_SIZE": "2"})[-1] == "wavefront"
     assert _run({"LOCAL_WORLD_SIZE": "8", "FPB_LOCAL_RANKS": "2"})[0] == "2"        # the explicit knob wins
 
 
