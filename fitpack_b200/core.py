@@ -238,6 +238,20 @@ def splint(t, n, c, k, a, b):
     return float(v), wrk
 
 
+def fourco(t, n, c, alfa):
+    """fourco (reference core:1474-1520) through fp_fourco_c: the integrals of a cubic spline against sin(alfa x) and
+    cos(alfa x) over its support; returns (ress, resc, ier, wrk1, wrk2)."""
+    t, c, alfa = _f64(t), _f64(c), _f64(alfa)
+    m = alfa.size
+    ress, resc = np.zeros(max(m, 1)), np.zeros(max(m, 1))
+    wrk1, wrk2 = np.zeros(max(int(n), 1)), np.zeros(max(int(n), 1))
+    ier_ = C.c_int32(0)
+    lib().fp_fourco_c(_p(t), int(n), _p(c), _p(alfa), m, _p(ress), _p(resc), _p(wrk1), _p(wrk2), C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_fourco_c: %s" % lib().fpb_last_error().decode())
+    return ress[:m], resc[:m], ier_.value, wrk1, wrk2
+
+
 # ------------------------------------------------------------------ parametric curves
 def parcur_lwrk(m, k, nest, idim):
     return m * (k + 1) + nest * (6 + idim + 3 * k)

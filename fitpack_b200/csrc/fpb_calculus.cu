@@ -200,6 +200,188 @@ struct DevSel {
     }
 };
 
+// ---- fourco: Fourier integrals of a cubic spline (core:1474-1520, fpbfou 1947-2123, fpcsin 4636-4686) ----
+// One thread per alfa(i): the integrals of the n-4 cubic B-splines against sin / cos(alfa x) -- divided differences at
+// the boundaries and for |alfa * support| > 1, a series otherwise -- summed with the coefficients in index order.
+// sin / cos are CUDA's double-precision functions (<= 2 ulp; the reference's are libm's): results agree with the
+// reference to rounding level, not bit for bit -- the one routine here with a tolerance instead of identity.
+__device__ void fpcsin_dev(double a, double b, double par, double sia, double coa, double sib, double cob, double &ress,
+                           double &resc)
+{
+    const double eps = 1.0e-10;
+    const double ab = sub(b, a), ab4 = mul(mul(ab, ab), mul(ab, ab)), alfa = mul(ab, par);
+    if (fabs(alfa) <= 1.0) {
+        double fac = 0.25, f1 = fac, f2 = 0.0;
+        int i = 4;
+        for (int j = 1; j <= 5; ++j) {
+            ++i;
+            fac = mul(fac, alfa) / (double)i;
+            f2 = add(f2, fac);
+            if (fabs(fac) <= eps) break;
+            ++i;
+            fac = mul(-fac, alfa) / (double)i;
+            f1 = add(f1, fac);
+            if (fabs(fac) <= eps) break;
+        }
+        ress = mul(ab4, add(mul(coa, f2), mul(sia, f1)));
+        resc = mul(ab4, sub(mul(coa, f1), mul(sia, f2)));
+    } else {
+        const double beta = 1.0 / alfa, b2 = mul(beta, beta), b4 = mul(6.0, mul(b2, b2));
+        const double f1 = mul(mul(3.0, b2), sub(1.0, mul(2.0, b2))), f2 = mul(beta, sub(1.0, mul(6.0, b2)));
+        ress = mul(ab4, add(add(mul(coa, f2), mul(sia, f1)), mul(sib, b4)));
+        resc = mul(ab4, add(sub(mul(coa, f1), mul(sia, f2)), mul(cob, b4)));
+    }
+}
+
+__global__ void fourco_kernel(const double *__restrict__ t, int n, const double *__restrict__ c,
+                              const double *__restrict__ alfa, int m, double *__restrict__ ress,
+                              double *__restrict__ resc, double *__restrict__ wrk1, double *__restrict__ wrk2)
+{
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ia >= m) return;
+    const bool keep = (ia == m - 1);   // the reference leaves the integrals of the LAST alfa in wrk1 / wrk2
+    auto T = [&](int i) { return t[i - 1]; };
+    const double par = alfa[ia];
+    const double eps = 1.0e-08, con1 = 0.5e-01, con2 = 0.12e+03;
+    double co[6], si[6], hs[6], hc[6], rs[4], rc[4];   // 1-based
+    const int nm3 = n - 3, nm7 = n - 7, n4 = n - 4;
+    const double term = fp_is_zero(par) ? 0.0 : 6.0 / par;
+    double sum_s = 0.0, sum_c = 0.0;   // dot_product(c(1:n4), .) in index order
+    auto emit = [&](int j, double vs, double vc) {
+        sum_s = add(sum_s, mul(c[j - 1], vs));
+        sum_c = add(sum_c, mul(c[j - 1], vc));
+        if (keep) {
+            wrk1[j - 1] = vs;
+            wrk2[j - 1] = vc;
+        }
+    };
+    double beta = mul(par, T(4));
+    co[1] = cos(beta);
+    si[1] = sin(beta);
+    for (int j = 1; j <= 3; ++j) {   // left boundary
+        const int jp1 = j + 1, jp4 = j + 4;
+        beta = mul(par, T(jp4));
+        co[jp1] = cos(beta);
+        si[jp1] = sin(beta);
+        fpcsin_dev(T(4), T(jp4), par, si[1], co[1], si[jp1], co[jp1], rs[j], rc[j]);
+        int i = 5 - j;
+        hs[i] = 0.0;
+        hc[i] = 0.0;
+        for (int jj = 1; jj <= j; ++jj) {
+            hs[i + jj] = rs[jj];
+            hc[i + jj] = rc[jj];
+        }
+        for (int jj = 1; jj <= 3; ++jj) {
+            if (i < jj) i = jj;
+            int k = 5, li = jp4;
+            for (int ll = i; ll <= 4; ++ll) {
+                const double fac = sub(T(li), T(li - jj));
+                hs[k] = sub(hs[k], hs[k - 1]) / fac;
+                hc[k] = sub(hc[k], hc[k - 1]) / fac;
+                --k;
+                --li;
+            }
+        }
+        emit(j, sub(hs[5], hs[4]), sub(hc[5], hc[4]));
+    }
+    for (int j = 4; j <= nm7; ++j) {   // interior
+        const int jp4 = j + 4;
+        beta = mul(par, T(jp4));
+        co[5] = cos(beta);
+        si[5] = sin(beta);
+        const double delta = sub(T(jp4), T(j));
+        beta = mul(delta, par);
+        double s2, c2;
+        if (fabs(beta) > 1.0) {
+            for (int i = 1; i <= 5; ++i) {
+                hs[i] = si[i];
+                hc[i] = co[i];
+            }
+            for (int jj = 1; jj <= 3; ++jj) {
+                int k = 5, li = jp4;
+                for (int ll = jj; ll <= 4; ++ll) {
+                    const double fac = mul(par, sub(T(li), T(li - jj)));
+                    hs[k] = sub(hs[k], hs[k - 1]) / fac;
+                    hc[k] = sub(hc[k], hc[k - 1]) / fac;
+                    --k;
+                    --li;
+                }
+            }
+            s2 = mul(sub(hs[5], hs[4]), term);
+            c2 = mul(sub(hc[5], hc[4]), term);
+        } else {
+            for (int i = 1; i <= 4; ++i) {
+                hs[i] = mul(par, sub(T(j + i), T(j)));
+                hc[i] = hs[i];
+            }
+            double f3 = mul(con1, add(add(add(hs[1], hs[2]), hs[3]), hs[4]));
+            double c1 = 0.25, s1 = f3;
+            if (fabs(f3) > eps) {
+                double sign = 1.0, fac = con2;
+                int k = 5, is = 0;
+                for (int ic = 1; ic <= 20; ++ic) {
+                    ++k;
+                    fac = mul(fac, (double)k);
+                    double f1 = 0.0;
+                    f3 = 0.0;
+                    for (int i = 1; i <= 4; ++i) {
+                        f1 = add(f1, hc[i]);
+                        const double f2 = mul(f1, hs[i]);
+                        hc[i] = f2;
+                        f3 = add(f3, f2);
+                    }
+                    f3 = mul(f3, 6.0) / fac;
+                    if (is == 0) {
+                        sign = -sign;
+                        is = 1;
+                        c1 = add(c1, mul(f3, sign));
+                    } else {
+                        is = 0;
+                        s1 = add(s1, mul(f3, sign));
+                    }
+                    if (fabs(f3) <= eps) break;
+                }
+            }
+            s2 = mul(delta, add(mul(co[1], s1), mul(si[1], c1)));
+            c2 = mul(delta, sub(mul(co[1], c1), mul(si[1], s1)));
+        }
+        emit(j, s2, c2);
+        for (int i = 1; i <= 4; ++i) {
+            co[i] = co[i + 1];
+            si[i] = si[i + 1];
+        }
+    }
+    double es[4], ec[4];   // right boundary: computed for j = n-4, n-5, n-6, summed in index order
+    for (int j = 1; j <= 3; ++j) {
+        const int nmj = nm3 - j;
+        int i = 5 - j;
+        fpcsin_dev(T(nm3), T(nmj), par, si[4], co[4], si[i - 1], co[i - 1], rs[j], rc[j]);
+        hc[i] = 0.0;
+        hs[i] = 0.0;
+        for (int jj = 1; jj <= j; ++jj) {
+            hc[i + jj] = rc[jj];
+            hs[i + jj] = rs[jj];
+        }
+        for (int jj = 1; jj <= 3; ++jj) {
+            if (i < jj) i = jj;
+            int k = 5, li = nmj;
+            for (int ll = i; ll <= 4; ++ll) {
+                const double fac = sub(T(li + jj), T(li));
+                hs[k] = sub(hs[k - 1], hs[k]) / fac;
+                hc[k] = sub(hc[k - 1], hc[k]) / fac;
+                --k;
+                ++li;
+            }
+        }
+        es[j] = sub(hs[4], hs[5]);
+        ec[j] = sub(hc[4], hc[5]);
+    }
+    for (int j = 3; j >= 1; --j) emit(nm3 - j, es[j], ec[j]);
+    (void)n4;
+    ress[ia] = sum_s;
+    resc[ia] = sum_c;
+}
+
 // upload knots and coefficients of one spline into the engine's calculus buffers
 bool upload_spline(fpb_engine *eng, const double *t, const double *c, int n, double **dt, double **dc,
                    double **dw)
@@ -344,6 +526,53 @@ FP_REAL fp_splint_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP
     if (wrk)
         for (int i = 0; i < nk1; ++i) wrk[i] = h[i];
     return h[n];
+}
+
+// reference: src/fitpack_core_c.f90:216-223 -> fourco core:1474-1520
+void fp_fourco_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, const FP_REAL *alfa, FP_SIZE m, FP_REAL *ress,
+                 FP_REAL *resc, FP_REAL *wrk1, FP_REAL *wrk2, FP_FLAG *ier)
+{
+    // data checks, core:1489-1505
+    if (n < 10) {
+        *ier = FPB_INSUFFICIENT_KNOTS;
+        return;
+    }
+    *ier = FPB_INPUT_ERROR;
+    for (int j = 0; j < 3; ++j)
+        if (t[j] > t[j + 1]) return;
+    for (int j = n - 3; j < n; ++j)
+        if (t[j] < t[j - 1]) return;
+    for (int j = 3; j < n - 4; ++j)
+        if (t[j] >= t[j + 1]) return;
+    *ier = FPB_OK;
+    if (m < 1) return;
+    HostApiLock api_lock(-1);  // per-device serialisation (fpb_engine.h)
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    DevSel g(eng->device);
+    double *dt, *dc, *dw;
+    DevBuf *B = eng->calc;
+    if (!upload_spline(eng, t, c, n, &dt, &dc, &dw) || !B[2].reserve((size_t)2 * n * 8 + 64) || !B[3].reserve((size_t)m * 8) ||
+        !B[4].reserve((size_t)2 * m * 8)) {
+        *ier = FPB_ERR_ALLOC;
+        return;
+    }
+    dw = B[2].as<double>();
+    double *da = B[3].as<double>(), *dr = B[4].as<double>();
+    bool ok = cuda_ok(cudaMemcpyAsync(da, alfa, (size_t)m * 8, cudaMemcpyHostToDevice, eng->stream), "H2D alfa");
+    if (ok) {
+        fourco_kernel<<<(m + 63) / 64, 64, 0, eng->stream>>>(dt, n, dc, da, m, dr, dr + m, dw, dw + n);
+        eng->launches++;
+    }
+    ok = ok && cuda_ok(cudaMemcpyAsync(ress, dr, (size_t)m * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H ress") &&
+         cuda_ok(cudaMemcpyAsync(resc, dr + m, (size_t)m * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H resc");
+    if (ok && wrk1) ok = cuda_ok(cudaMemcpyAsync(wrk1, dw, (size_t)(n - 4) * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H wrk1");
+    if (ok && wrk2) ok = cuda_ok(cudaMemcpyAsync(wrk2, dw + n, (size_t)(n - 4) * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H wrk2");
+    ok = ok && cuda_ok(cudaStreamSynchronize(eng->stream), "sync");
+    if (!ok) *ier = FPB_ERR_CUDA;
 }
 
 }  // extern "C"

@@ -494,6 +494,22 @@ FP_REAL fitpack_curve_c_integral(fitpack_curve_c *self, FP_REAL from, FP_REAL to
     return fp_splint_c(cv->t.data(), cv->knots, cv->c.data(), cv->order, from, to, wk.data());
 }
 
+// fourier_coefficients, fitpack_curves.f90:650-668 (C handle src/fitpack_curves_c.f90:276-291): fourco on the curve's
+// knots and coefficients with wrk_fou(:,1), wrk_fou(:,2) as workspace; A = sine integrals, B = cosine integrals
+void fitpack_curve_c_fourier(fitpack_curve_c *self, FP_SIZE nparm, const FP_REAL *alpha, FP_REAL *A, FP_REAL *B,
+                             FP_FLAG *ierr)
+{
+    Curve *cv = ensure(self);
+    FP_FLAG ier = FPB_INPUT_ERROR;
+    if (cv) {
+        if (cv->wrk_fou.size() < static_cast<size_t>(cv->nest) * 2) cv->wrk_fou.assign(static_cast<size_t>(cv->nest) * 2, 0.0);
+        if (cv->knots >= 1 && cv->knots <= cv->nest && (nparm <= 0 || (alpha && A && B)))
+            fp_fourco_c(cv->t.data(), cv->knots, cv->c.data(), alpha, nparm, A, B, cv->wrk_fou.data(),
+                        cv->wrk_fou.data() + cv->nest, &ier);
+    }
+    if (ierr) *ierr = ier;
+}
+
 FP_REAL fitpack_curve_c_smoothing(fitpack_curve_c *self)
 {
     Curve *cv = ensure(self);

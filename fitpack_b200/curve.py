@@ -112,6 +112,15 @@ class FitpackCurve:
         """curve%integral(from, to)  (splint)"""
         return lib().fitpack_curve_c_integral(C.addressof(self._h), float(a), float(b))
 
+    def fourier(self, alpha):
+        """curve%fourier_coefficients(alpha, A, B)  (fourco; cubic splines): returns (A, B, ierr)"""
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        a, b = np.zeros(max(alpha.size, 1)), np.zeros(max(alpha.size, 1))
+        ierr = C.c_int32(0)
+        lib().fitpack_curve_c_fourier(C.addressof(self._h), alpha.size, alpha.ctypes.data_as(C.c_void_p),
+                                      a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.addressof(ierr))
+        return a[:alpha.size], b[:alpha.size], ierr.value
+
     # parallel communication (curve%comm_size / comm_pack / comm_expand, fitpack_curves.f90:821-895)
     def comm_size(self):
         return lib().fitpack_curve_c_comm_size(C.addressof(self._h))

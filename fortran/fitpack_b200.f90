@@ -23,7 +23,7 @@ module fitpack_b200
                                             FPB_ERR_ARG = -101, FPB_ERR_ALLOC = -102
 
    public :: fp_curfit_c, fp_splev_c, fp_curfit_batch_c, fp_splev_batch_c
-   public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c
+   public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c, fp_fourco_c
    public :: fp_parcur_c, fp_curev_c, fp_parcur_batch_c, fp_percur_c, fp_percur_batch_c
    public :: fitpack_curve_c_comm_size, fitpack_curve_c_comm_pack, fitpack_curve_c_comm_expand
    public :: fp_curfit_batch_dev_c, fp_curfit_shared_dev_c, fp_splev_batch_dev_c
@@ -184,6 +184,16 @@ module fitpack_b200
          real   (FP_REAL), intent(in)        :: t(n),c(n)
          real   (FP_REAL), intent(inout)     :: wrk(n)
       end function fp_splint_c
+
+      ! Fourier integrals of a cubic spline (same argument list as the reference's fp_fourco_c)
+      subroutine fp_fourco_c(t,n,c,alfa,m,ress,resc,wrk1,wrk2,ier) bind(C,name="fp_fourco_c")
+         import
+         integer(FP_SIZE), intent(in), value :: n,m
+         integer(FP_FLAG), intent(out)       :: ier
+         real   (FP_REAL), intent(in)        :: t(n),c(n),alfa(m)
+         real   (FP_REAL), intent(inout)     :: wrk1(n),wrk2(n)
+         real   (FP_REAL), intent(out)       :: ress(m),resc(m)
+      end subroutine fp_fourco_c
 
       ! (B) batches of independent curves, host arrays.  Fortran arrays x(m,nbatch) are exactly
       ! the "curve-major" [nbatch][m] C layout the library expects.

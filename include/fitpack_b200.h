@@ -61,6 +61,7 @@ typedef bool    FP_BOOL;
 #define FPB_MAXIT                  3
 #define FPB_INVALID_RANGE          6
 #define FPB_INPUT_ERROR           10
+#define FPB_INSUFFICIENT_KNOTS    13   /* fourco: a cubic spline with n >= 10 knots is required */
 
 /* status of the batch/engine calls themselves (not per-curve ier) */
 #define FPB_STATUS_OK      0
@@ -110,6 +111,8 @@ FP_FLAG fitpack_curve_c_interpolating(fitpack_curve_c *self, FP_SIZE *order);
 FP_REAL fitpack_curve_c_eval_one     (fitpack_curve_c *self, FP_REAL x, FP_FLAG *ierr);
 void    fitpack_curve_c_eval_many    (fitpack_curve_c *self, FP_SIZE npts, FP_REAL *x, FP_REAL *y, FP_FLAG *ierr);
 FP_REAL fitpack_curve_c_integral     (fitpack_curve_c *self, FP_REAL from, FP_REAL to);
+void    fitpack_curve_c_fourier      (fitpack_curve_c *self, FP_SIZE nparm, const FP_REAL *alpha, FP_REAL *A, FP_REAL *B,
+                                      FP_FLAG *ierr);
 FP_REAL fitpack_curve_c_derivative   (fitpack_curve_c *self, FP_REAL x, FP_SIZE order, FP_SIZE *ierr);
 FP_FLAG fitpack_curve_c_all_derivatives(fitpack_curve_c *self, FP_REAL x, FP_REAL *ddx);
 FP_REAL fitpack_curve_c_smoothing    (fitpack_curve_c *self);
@@ -292,6 +295,13 @@ void fp_spalde_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k1, FP_R
                  FP_FLAG *ier);
 FP_REAL fp_splint_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP_REAL a, FP_REAL b,
                     FP_REAL *wrk);
+/* fourco (include/fitpack_core_c.h:152-153, src/fitpack_core_c.f90:216-223 -> core:1474-1520): the integrals
+   ress(i) = int s(x) sin(alfa(i) x) dx, resc(i) = int s(x) cos(alfa(i) x) dx over [t(4), t(n-3)] of a CUBIC spline;
+   ier = 13 for n < 10, 10 for invalid knots.  wrk1, wrk2 (length n) return the B-spline integrals of the last alfa.
+   One thread per alfa; sin / cos are CUDA's (<= 2 ulp), so values agree with the reference to ~1e-13 relative, the
+   one routine of this library that is not bit-identical by construction. */
+void fp_fourco_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, const FP_REAL *alfa, FP_SIZE m, FP_REAL *ress,
+                 FP_REAL *resc, FP_REAL *wrk1, FP_REAL *wrk2, FP_FLAG *ier);
 
 /* ---------------------------------------------------------- gridded surfaces -- */
 /*

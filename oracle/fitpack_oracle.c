@@ -1503,6 +1503,186 @@ double orc_splint(const double *t, int32_t n, const double *c, int32_t k, double
  * Layouts follow the reference: x(idim,m) coordinate-fastest, c((d-1)*n + i), z likewise.
  * ===================================================================================== */
 
+/* ------------------------------------------------------------------ fourco: Fourier integrals of a cubic spline */
+/* fpcsin, core:4636-4686 */
+static void fpcsin(double a, double b, double par, double sia, double coa, double sib, double cob, double *ress,
+                   double *resc)
+{
+    const double eps = 1.0e-10;
+    double ab = b - a, ab4 = (ab * ab) * (ab * ab), alfa = ab * par;   /* gfortran: ab**4 = (ab*ab)*(ab*ab) */
+    if (fabs(alfa) <= 1.0) {
+        double fac = 0.25, f1 = fac, f2 = 0.0, ai;
+        int i = 4, j;
+        for (j = 1; j <= 5; ++j) {
+            ++i;
+            ai = (double)i;
+            fac = fac * alfa / ai;
+            f2 = f2 + fac;
+            if (fabs(fac) <= eps) break;
+            ++i;
+            ai = (double)i;
+            fac = -fac * alfa / ai;
+            f1 = f1 + fac;
+            if (fabs(fac) <= eps) break;
+        }
+        *ress = ab4 * (coa * f2 + sia * f1);
+        *resc = ab4 * (coa * f1 - sia * f2);
+    } else {
+        double beta = 1.0 / alfa, b2 = beta * beta, b4 = 6.0 * (b2 * b2);
+        double f1 = 3.0 * b2 * (1.0 - 2.0 * b2), f2 = beta * (1.0 - 6.0 * b2);
+        *ress = ab4 * (coa * f2 + sia * f1 + sib * b4);
+        *resc = ab4 * (coa * f1 - sia * f2 + cob * b4);
+    }
+}
+
+/* fpbfou, core:1947-2123 : ress(j), resc(j) = integral of N_j,4(x) sin / cos(par x), j = 1 .. n-4 */
+static void fpbfou(const double *t, int n, double par, double *ress, double *resc)
+{
+    const double *T = t - 1;
+    double *RS = ress - 1, *RC = resc - 1;
+    const double eps = 1.0e-08, con1 = 0.5e-01, con2 = 0.12e+03;
+    double co[6], si[6], hs[6], hc[6], rs[4], rc[4];   /* 1-based */
+    double ak, beta, c1, c2, delta, fac, f1, f2, f3, sign, s1, s2, term;
+    int i, ic, ipj, is, j, jj, jp1, jp4, k, li, lj, ll, nmj, nm3 = n - 3, nm7 = n - 7;
+    term = (par != 0.0 && !orc_equal(par, 0.0)) ? 6.0 / par : 0.0;   /* merge(six/par, zero, not_equal(par, zero)) */
+    beta = par * T[4];
+    co[1] = cos(beta);
+    si[1] = sin(beta);
+    for (j = 1; j <= 3; ++j) {                       /* left boundary: divided differences */
+        jp1 = j + 1;
+        jp4 = j + 4;
+        beta = par * T[jp4];
+        co[jp1] = cos(beta);
+        si[jp1] = sin(beta);
+        fpcsin(T[4], T[jp4], par, si[1], co[1], si[jp1], co[jp1], &rs[j], &rc[j]);
+        i = 5 - j;
+        hs[i] = 0.0;
+        hc[i] = 0.0;
+        for (jj = 1; jj <= j; ++jj) {
+            ipj = i + jj;
+            hs[ipj] = rs[jj];
+            hc[ipj] = rc[jj];
+        }
+        for (jj = 1; jj <= 3; ++jj) {
+            if (i < jj) i = jj;
+            k = 5;
+            li = jp4;
+            for (ll = i; ll <= 4; ++ll) {
+                lj = li - jj;
+                fac = T[li] - T[lj];
+                hs[k] = (hs[k] - hs[k - 1]) / fac;
+                hc[k] = (hc[k] - hc[k - 1]) / fac;
+                --k;
+                --li;
+            }
+        }
+        RS[j] = hs[5] - hs[4];
+        RC[j] = hc[5] - hc[4];
+    }
+    for (j = 4; j <= nm7; ++j) {                     /* interior */
+        jp4 = j + 4;
+        beta = par * T[jp4];
+        co[5] = cos(beta);
+        si[5] = sin(beta);
+        delta = T[jp4] - T[j];
+        beta = delta * par;
+        if (fabs(beta) > 1.0) {
+            for (i = 1; i <= 5; ++i) { hs[i] = si[i]; hc[i] = co[i]; }
+            for (jj = 1; jj <= 3; ++jj) {
+                k = 5;
+                li = jp4;
+                for (ll = jj; ll <= 4; ++ll) {
+                    lj = li - jj;
+                    fac = par * (T[li] - T[lj]);
+                    hs[k] = (hs[k] - hs[k - 1]) / fac;
+                    hc[k] = (hc[k] - hc[k - 1]) / fac;
+                    --k;
+                    --li;
+                }
+            }
+            s2 = (hs[5] - hs[4]) * term;
+            c2 = (hc[5] - hc[4]) * term;
+        } else {
+            for (i = 1; i <= 4; ++i) { hs[i] = par * (T[j + i] - T[j]); hc[i] = hs[i]; }
+            f3 = con1 * (((hs[1] + hs[2]) + hs[3]) + hs[4]);
+            c1 = 0.25;
+            s1 = f3;
+            if (fabs(f3) > eps) {
+                sign = 1.0;
+                fac = con2;
+                k = 5;
+                is = 0;
+                for (ic = 1; ic <= 20; ++ic) {
+                    ++k;
+                    ak = (double)k;
+                    fac = fac * ak;
+                    f1 = 0.0;
+                    f3 = 0.0;
+                    for (i = 1; i <= 4; ++i) {
+                        f1 = f1 + hc[i];
+                        f2 = f1 * hs[i];
+                        hc[i] = f2;
+                        f3 = f3 + f2;
+                    }
+                    f3 = f3 * 6.0 / fac;
+                    if (is == 0) { sign = -sign; is = 1; c1 = c1 + f3 * sign; }
+                    else { is = 0; s1 = s1 + f3 * sign; }
+                    if (fabs(f3) <= eps) break;
+                }
+            }
+            s2 = delta * (co[1] * s1 + si[1] * c1);
+            c2 = delta * (co[1] * c1 - si[1] * s1);
+        }
+        RS[j] = s2;
+        RC[j] = c2;
+        for (i = 1; i <= 4; ++i) { co[i] = co[i + 1]; si[i] = si[i + 1]; }
+    }
+    for (j = 1; j <= 3; ++j) {                       /* right boundary */
+        nmj = nm3 - j;
+        i = 5 - j;
+        fpcsin(T[nm3], T[nmj], par, si[4], co[4], si[i - 1], co[i - 1], &rs[j], &rc[j]);
+        hc[i] = 0.0;
+        hs[i] = 0.0;
+        for (jj = 1; jj <= j; ++jj) { hc[i + jj] = rc[jj]; hs[i + jj] = rs[jj]; }
+        for (jj = 1; jj <= 3; ++jj) {
+            if (i < jj) i = jj;
+            k = 5;
+            li = nmj;
+            for (ll = i; ll <= 4; ++ll) {
+                lj = li + jj;
+                fac = T[lj] - T[li];
+                hs[k] = (hs[k - 1] - hs[k]) / fac;
+                hc[k] = (hc[k - 1] - hc[k]) / fac;
+                --k;
+                ++li;
+            }
+        }
+        RS[nmj] = hs[4] - hs[5];
+        RC[nmj] = hc[4] - hc[5];
+    }
+}
+
+/* fourco, core:1474-1520 (argument list of fp_fourco_c) */
+void orc_fourco(const double *t, int32_t n, const double *c, const double *alfa, int32_t m, double *ress,
+                double *resc, double *wrk1, double *wrk2, int32_t *ier)
+{
+    int i, j, n4 = n - 4;
+    if (n < 10) { *ier = 13; return; }                 /* FITPACK_INSUFFICIENT_KNOTS */
+    *ier = IER_INPUT;
+    for (j = 0; j < 3; ++j) if (t[j] > t[j + 1]) return;
+    for (j = n - 3; j < n; ++j) if (t[j] < t[j - 1]) return;
+    for (j = 3; j < n4; ++j) if (t[j] >= t[j + 1]) return;   /* t(4:n4) >= t(5:n-3) */
+    *ier = IER_OK;
+    for (i = 0; i < m; ++i) {
+        double s = 0.0, cc = 0.0;
+        fpbfou(t, n, alfa[i], wrk1, wrk2);
+        for (j = 0; j < n4; ++j) s = s + c[j] * wrk1[j];
+        for (j = 0; j < n4; ++j) cc = cc + c[j] * wrk2[j];
+        ress[i] = s;
+        resc[i] = cc;
+    }
+}
+
 /* Fortran NORM2 as gfortran evaluates it (scaled form of libgfortran's norm2_r8 / the
    inline expansion in trans-intrinsic.cc); netlib parcur uses sqrt(sum d**2). */
 static double f_norm2(const double *v, int nd)

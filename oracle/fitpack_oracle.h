@@ -122,6 +122,9 @@ void orc_spalde(const double *t, int32_t n, const double *c, int32_t k1, double 
                 int32_t *ier);
 double orc_splint(const double *t, int32_t n, const double *c, int32_t k, double a, double b,
                   double *wrk);
+/* fourco core:1474-1520 with fpbfou 1947-2123, fpcsin 4636-4686: Fourier integrals of a cubic spline (fp_fourco_c) */
+void orc_fourco(const double *t, int32_t n, const double *c, const double *alfa, int32_t m, double *ress,
+                double *resc, double *wrk1, double *wrk2, int32_t *ier);
 
 /* parcur core:15201-15285 + fppara 8822-9177 (argument list of fp_parcur_c), curev core:1126-1182
    (argument list of fp_curev_c).  x(idim,m) coordinate-fastest; c((d-1)*n + i). */

@@ -292,6 +292,18 @@ def splint(t, n, c, k, a, b):
     return float(v), wrk
 
 
+def fourco(t, n, c, alfa):
+    """orc_fourco (reference core:1474-1520); returns (ress, resc, ier, wrk1, wrk2)"""
+    t, c, alfa = (np.ascontiguousarray(v, dtype=np.float64) for v in (t, c, alfa))
+    m = alfa.size
+    ress, resc, w1, w2 = np.zeros(max(m, 1)), np.zeros(max(m, 1)), np.zeros(max(n, 1)), np.zeros(max(n, 1))
+    ier = C.c_int32(0)
+    L = lib()
+    L.orc_fourco.restype = None
+    L.orc_fourco(_d(t), C.c_int32(n), _d(c), _d(alfa), C.c_int32(m), _d(ress), _d(resc), _d(w1), _d(w2), C.byref(ier))
+    return ress[:m], resc[:m], ier.value, w1, w2
+
+
 # ------------------------------------------------------------------ parametric curves
 def parcur_lwrk(m, k, nest, idim):
     return m * (k + 1) + nest * (6 + idim + 3 * k)

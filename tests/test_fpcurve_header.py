@@ -1,5 +1,5 @@
 """CPU: the reference's header-only C++ wrapper include/fpCurve.hpp compiles and LINKS against
-libfitpack_b200.so for the on-path methods (drop-in check of the handle C-ABI).  Only runs where
+libfitpack_b200.so with EVERY method it has (drop-in check of the whole handle C-ABI, include/fitpack_curves_c.h:45-63).  Only runs where
 the reference tree is mounted (the build container); it is not executed (no GPU here)."""
 import os
 import subprocess
@@ -29,8 +29,14 @@ int main(int argc, char**) {
         c.set_bc(OUTSIDE_EXTRAPOLATE);
         fpCurve d(c);
         d = c;
-        std::printf("%d %g %zu %d %g %g %d\n", ier, v, vv.size(), c.degree(), c.smoothing(), c.mse(),
-                    d.get_bc());
+        // every method of the wrapper: derivatives, integral, Fourier coefficients
+        double d1 = c.ddx(2.5, 1, &e);
+        std::vector<double> dall = c.ddx(2.5, &e);
+        double area = c.integral(0.0, 7.0);
+        std::vector<double> alpha{0.0, 1.0}, A, B;
+        ier = c.fourier(alpha, A, B);
+        std::printf("%d %g %zu %d %g %g %d %g %zu %g %zu\n", ier, v, vv.size(), c.degree(), c.smoothing(), c.mse(),
+                    d.get_bc(), d1, dall.size(), area, A.size() + B.size());
     }
     return FITPACK_SUCCESS_c(0) ? 0 : 1;
 }
