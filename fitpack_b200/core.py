@@ -238,6 +238,30 @@ def splint(t, n, c, k, a, b):
     return float(v), wrk
 
 
+def cualde(idim, t, n, c, k1, u):
+    """cualde (reference core:1062-1101) through fp_cualde_c; returns (d [k1][idim], ier)."""
+    t, c = _f64(t), _f64(c)
+    d = np.zeros(max(k1 * idim, 1))
+    ier_ = C.c_int32(0)
+    lib().fp_cualde_c(int(idim), _p(t), int(n), _p(c), c.size, int(k1), float(u), _p(d), d.size, C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_cualde_c: %s" % lib().fpb_last_error().decode())
+    return d[:k1 * idim].reshape(k1, idim), ier_.value
+
+
+def insert(iopt, t, n, c, k, x, nest):
+    """insert (reference insert_inplace core:15138-15159) through fp_insert_c; returns (t, n, c, ier) -- copies of
+    length nest with the knot x inserted (unchanged when ier = 10)."""
+    tt, cc = np.zeros(nest), np.zeros(nest)
+    tt[:min(nest, len(t))] = np.asarray(t, dtype=np.float64)[:nest]
+    cc[:min(nest, len(c))] = np.asarray(c, dtype=np.float64)[:nest]
+    n_, ier_ = C.c_int32(int(n)), C.c_int32(0)
+    lib().fp_insert_c(int(iopt), _p(tt), C.addressof(n_), _p(cc), int(k), float(x), int(nest), C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_insert_c: %s" % lib().fpb_last_error().decode())
+    return tt, n_.value, cc, ier_.value
+
+
 def fourco(t, n, c, alfa):
     """fourco (reference core:1474-1520) through fp_fourco_c: the integrals of a cubic spline against sin(alfa x) and
     cos(alfa x) over its support; returns (ress, resc, ier, wrk1, wrk2)."""

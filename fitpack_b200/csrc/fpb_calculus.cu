@@ -382,6 +382,61 @@ __global__ void fourco_kernel(const double *__restrict__ t, int n, const double 
     resc[ia] = sum_c;
 }
 
+// insert_inplace -> insert -> fpinst (core:15138-15159, 15064-15120, 7961-8026), in place on the device copies of t and c:
+// the knot x goes in after t(l), the k coefficients it touches become convex combinations, the rest shift by one; a
+// periodic spline (iopt /= 0) gets its wrap-around knots and coefficients repaired.  One thread: O(n) moves.
+__global__ void insert_kernel(int iopt, double *__restrict__ t, int *__restrict__ n_io, double *__restrict__ c, int k,
+                              double x, int nest, int *__restrict__ ier)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    auto T = [&](int i) -> double & { return t[i - 1]; };
+    auto Cc = [&](int i) -> double & { return c[i - 1]; };
+    const int n = *n_io, k1 = k + 1, nk = n - k;
+    *ier = IER_INPUT;
+    if (nest <= n) return;
+    if (x < T(k1) || x > T(nk)) return;
+    const int l = knot_interval(t, x, k1, nk - 1);
+    if (T(l) >= T(l + 1)) return;
+    if (iopt != 0) {
+        const int kk = 2 * k;
+        if (l <= kk && l >= (n - kk)) return;
+    }
+    *ier = IER_OK;
+    const int nk1 = n - k1, ll = l + 1;
+    for (int i = n; i >= ll; --i) T(i + 1) = T(i);
+    T(ll) = x;
+    for (int i = nk1; i >= l; --i) Cc(i + 1) = Cc(i);
+    int i = l;
+    for (int j = 1; j <= k; ++j) {
+        const int m = i + k1;
+        const double fac = sub(x, T(i)) / sub(T(m), T(i));
+        Cc(i) = add(mul(fac, Cc(i)), mul(sub(1.0, fac), Cc(i - 1)));
+        --i;
+    }
+    const int nn = n + 1;
+    if (iopt != 0) {
+        const int nkk = nn - k, nl = nkk - k1;
+        const double per = sub(T(nkk), T(k1));
+        int ii = k1, jj = nkk;
+        if (ll > nl) {
+            for (int m = 1; m <= k; ++m) {
+                Cc(m) = Cc(m + nl);
+                --ii;
+                --jj;
+                T(ii) = sub(T(jj), per);
+            }
+        } else if (ll <= (k1 + k)) {
+            for (int m = 1; m <= k; ++m) {
+                Cc(m + nl) = Cc(m);
+                ++ii;
+                ++jj;
+                T(jj) = add(T(ii), per);
+            }
+        }
+    }
+    *n_io = nn;
+}
+
 // upload knots and coefficients of one spline into the engine's calculus buffers
 bool upload_spline(fpb_engine *eng, const double *t, const double *c, int n, double **dt, double **dc,
                    double **dw)
@@ -573,6 +628,73 @@ void fp_fourco_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, const FP_REAL *a
     if (ok && wrk2) ok = cuda_ok(cudaMemcpyAsync(wrk2, dw + n, (size_t)(n - 4) * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H wrk2");
     ok = ok && cuda_ok(cudaStreamSynchronize(eng->stream), "sync");
     if (!ok) *ier = FPB_ERR_CUDA;
+}
+
+// reference: src/fitpack_core_c.f90:187-194 -> cualde core:1062-1101: all derivatives of a parametric curve at u,
+// d((j-1)*idim + i) = d^(j-1) s_i / du^(j-1) -- fpader per coordinate curve (the spalde kernel), interleaved
+void fp_cualde_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE nc, FP_SIZE k1, FP_REAL u,
+                 FP_REAL *d, FP_SIZE nd, FP_FLAG *ier)
+{
+    *ier = FPB_INPUT_ERROR;
+    if (idim < 1 || k1 < 2 || k1 > 6 || n < 2 * k1) return;
+    if (nd < k1 * idim || nc < n * (idim - 1) + n - k1) return;   // core:1079
+    HostApiLock api_lock(-1);
+    double h[8];
+    for (FP_SIZE i = 0; i < idim; ++i) {
+        FP_FLAG ie = FPB_INPUT_ERROR;
+        fp_spalde_c(t, n, c + (size_t)i * n, k1, u, h, &ie);   // same range / interval checks as cualde (core:1081-1085)
+        if (ie != FPB_OK) {
+            *ier = ie;
+            return;
+        }
+        for (FP_SIZE kk = 0; kk < k1; ++kk) d[(size_t)kk * idim + i] = h[kk];
+    }
+    *ier = FPB_OK;
+}
+
+// reference: src/fitpack_core_c.f90:197-204 -> insert_inplace core:15138-15159
+void fp_insert_c(FP_SIZE iopt, FP_REAL *t, FP_SIZE *n, FP_REAL *c, FP_SIZE k, FP_REAL x, FP_SIZE nest, FP_FLAG *ier)
+{
+    *ier = FPB_INPUT_ERROR;
+    const int n0 = *n;
+    if (k < 1 || k > 5 || n0 < 2 * (k + 1) || nest <= n0) return;   // nest <= n: core:15080
+    HostApiLock api_lock(-1);
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    DevSel g(eng->device);
+    DevBuf *B = eng->calc;
+    const size_t len = (size_t)n0 + 1;
+    if (!B[0].reserve(len * 8) || !B[1].reserve(len * 8) || !B[2].reserve(64)) {
+        *ier = FPB_ERR_ALLOC;
+        return;
+    }
+    double *dt = B[0].as<double>(), *dc = B[1].as<double>();
+    int *dn = B[2].as<int>(), *dier = dn + 1;
+    int hni[2] = {n0, FPB_INPUT_ERROR};
+    bool ok = cuda_ok(cudaMemcpyAsync(dt, t, (size_t)n0 * 8, cudaMemcpyHostToDevice, eng->stream), "H2D t") &&
+              cuda_ok(cudaMemcpyAsync(dc, c, (size_t)n0 * 8, cudaMemcpyHostToDevice, eng->stream), "H2D c") &&
+              cuda_ok(cudaMemcpyAsync(dn, hni, 8, cudaMemcpyHostToDevice, eng->stream), "H2D n");
+    if (ok) {
+        insert_kernel<<<1, 32, 0, eng->stream>>>(iopt, dt, dn, dc, k, x, nest, dier);
+        eng->launches++;
+    }
+    std::vector<double> ht(len), hc(len);
+    ok = ok && cuda_ok(cudaMemcpyAsync(hni, dn, 8, cudaMemcpyDeviceToHost, eng->stream), "D2H n") &&
+         cuda_ok(cudaMemcpyAsync(ht.data(), dt, len * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H t") &&
+         cuda_ok(cudaMemcpyAsync(hc.data(), dc, len * 8, cudaMemcpyDeviceToHost, eng->stream), "D2H c") &&
+         cuda_ok(cudaStreamSynchronize(eng->stream), "sync");
+    if (!ok) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    *ier = hni[1];
+    if (hni[1] != FPB_OK) return;   // t, c, n stay the caller's
+    *n = hni[0];
+    std::memcpy(t, ht.data(), (size_t)hni[0] * 8);
+    std::memcpy(c, hc.data(), (size_t)(hni[0] - k - 1) * 8);
 }
 
 }  // extern "C"

@@ -23,7 +23,7 @@ module fitpack_b200
                                             FPB_ERR_ARG = -101, FPB_ERR_ALLOC = -102
 
    public :: fp_curfit_c, fp_splev_c, fp_curfit_batch_c, fp_splev_batch_c
-   public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c, fp_fourco_c
+   public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c, fp_fourco_c, fp_cualde_c, fp_insert_c
    public :: fp_parcur_c, fp_curev_c, fp_parcur_batch_c, fp_percur_c, fp_percur_batch_c
    public :: fitpack_curve_c_comm_size, fitpack_curve_c_comm_pack, fitpack_curve_c_comm_expand
    public :: fp_curfit_batch_dev_c, fp_curfit_shared_dev_c, fp_splev_batch_dev_c
@@ -194,6 +194,24 @@ module fitpack_b200
          real   (FP_REAL), intent(inout)     :: wrk1(n),wrk2(n)
          real   (FP_REAL), intent(out)       :: ress(m),resc(m)
       end subroutine fp_fourco_c
+
+      ! all derivatives of a parametric curve at u / knot insertion in place (the reference's argument lists)
+      subroutine fp_cualde_c(idim,t,n,c,nc,k1,u,d,nd,ier) bind(C,name="fp_cualde_c")
+         import
+         integer(FP_SIZE), intent(in), value :: idim,n,nc,k1,nd
+         integer(FP_FLAG), intent(out)       :: ier
+         real   (FP_REAL), intent(in), value :: u
+         real   (FP_REAL), intent(in)        :: t(n),c(nc)
+         real   (FP_REAL), intent(out)       :: d(nd)
+      end subroutine fp_cualde_c
+      subroutine fp_insert_c(iopt,t,n,c,k,x,nest,ier) bind(C,name="fp_insert_c")
+         import
+         integer(FP_SIZE), intent(in), value :: iopt,k,nest
+         real   (FP_REAL), intent(inout)     :: t(nest),c(nest)
+         real   (FP_REAL), intent(in), value :: x
+         integer(FP_SIZE), intent(inout)     :: n
+         integer(FP_FLAG), intent(out)       :: ier
+      end subroutine fp_insert_c
 
       ! (B) batches of independent curves, host arrays.  Fortran arrays x(m,nbatch) are exactly
       ! the "curve-major" [nbatch][m] C layout the library expects.

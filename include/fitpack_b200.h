@@ -302,6 +302,13 @@ FP_REAL fp_splint_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE k, FP
    one routine of this library that is not bit-identical by construction. */
 void fp_fourco_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, const FP_REAL *alfa, FP_SIZE m, FP_REAL *ress,
                  FP_REAL *resc, FP_REAL *wrk1, FP_REAL *wrk2, FP_FLAG *ier);
+/* cualde (include/fitpack_core_c.h, src/fitpack_core_c.f90:187-194 -> core:1062-1101): all derivatives of a parametric
+   curve at u, d((j-1)*idim + i) = d^(j-1) s_i / du^(j-1).  insert (src/fitpack_core_c.f90:197-204 -> insert_inplace
+   core:15138-15159, fpinst 7961-8026): the knot x inserted into (t, n, c) in place; iopt /= 0: periodic spline; on
+   ier = 10 nothing changes.  Both bit-identical to the reference's arithmetic. */
+void fp_cualde_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE nc, FP_SIZE k1, FP_REAL u,
+                 FP_REAL *d, FP_SIZE nd, FP_FLAG *ier);
+void fp_insert_c(FP_SIZE iopt, FP_REAL *t, FP_SIZE *n, FP_REAL *c, FP_SIZE k, FP_REAL x, FP_SIZE nest, FP_FLAG *ier);
 
 /* ---------------------------------------------------------- gridded surfaces -- */
 /*

@@ -1414,6 +1414,89 @@ void orc_spalde(const double *t, int32_t n, const double *c, int32_t k1, double 
     fpader(t, c, k1, x, l, d);
 }
 
+/* cualde, core:1062-1101 (argument list of fp_cualde_c): all derivatives of a parametric curve at u;
+   d((j-1)*idim + i) = d^(j-1) s_i / du^(j-1), i = 1..idim, j = 1..k1 */
+void orc_cualde(int32_t idim, const double *t, int32_t n, const double *c, int32_t nc, int32_t k1, double u,
+                double *d, int32_t nd, int32_t *ier)
+{
+    const double *T = t - 1;
+    double h[ORC_MAX_ORDER + 1];
+    int nk1 = n - k1, l, i, kk;
+    (void)nc;
+    *ier = IER_INPUT;
+    if (nd < k1 * idim) return;
+    if (u < T[k1] || u > T[nk1 + 1]) return;
+    l = orc_knot_interval(t, u, k1, nk1);
+    if (T[l] >= T[l + 1]) return;
+    *ier = IER_OK;
+    for (i = 0; i < idim; ++i) {
+        fpader(t, c + (size_t)i * n, k1, u, l, h);
+        for (kk = 0; kk < k1; ++kk) d[kk * idim + i] = h[kk];
+    }
+}
+
+/* insert_inplace -> insert -> fpinst, core:15138-15159, 15064-15120, 7961-8026 (argument list of fp_insert_c):
+   insert the knot x into the spline (t, n, c) of degree k; iopt /= 0: periodic spline.  On error t, c, n stay. */
+void orc_insert(int32_t iopt, double *t, int32_t *n_io, double *c, int32_t k, double x, int32_t nest,
+                int32_t *ier)
+{
+    double *T = t - 1, *Cc = c - 1;
+    int n = *n_io, k1 = k + 1, nk = n - k, nk1, l, ll, i, i1, j, m, mk, nn, nl;
+    double fac, per;
+    *ier = IER_INPUT;
+    if (nest <= n) return;
+    if (x < T[k1] || x > T[nk]) return;
+    nk1 = nk - 1;
+    l = orc_knot_interval(t, x, k1, nk1);
+    if (T[l] >= T[l + 1]) return;
+    if (iopt != 0) {
+        int kk = 2 * k;
+        if (l <= kk && l >= (n - kk)) return;
+    }
+    *ier = IER_OK;
+    /* fpinst: new knots tt = [t(1:l), x, t(l+1:n)] (in place: shift right) */
+    nk1 = n - k1;
+    ll = l + 1;
+    for (i = n; i >= ll; --i) T[i + 1] = T[i];
+    T[ll] = x;
+    /* new coefficients (in place, from the top: cc(i+1) = c(i) for i = nk1 .. l) */
+    for (i = nk1; i >= l; --i) Cc[i + 1] = Cc[i];
+    i = l;
+    for (j = 1; j <= k; ++j) {
+        m = i + k1;
+        fac = (x - T[i]) / (T[m] - T[i]);
+        i1 = i - 1;
+        Cc[i] = fac * Cc[i] + (1.0 - fac) * Cc[i1];     /* c(i), c(i-1): not yet overwritten (i descends) */
+        i = i1;
+    }
+    nn = n + 1;
+    if (iopt != 0) {                                  /* periodic boundary conditions */
+        int nkk = nn - k;
+        nl = nkk - k1;
+        per = T[nkk] - T[k1];
+        i = k1;
+        j = nkk;
+        if (ll > nl) {
+            for (m = 1; m <= k; ++m) {
+                mk = m + nl;
+                Cc[m] = Cc[mk];
+                --i;
+                --j;
+                T[i] = T[j] - per;
+            }
+        } else if (ll <= (k1 + k)) {
+            for (m = 1; m <= k; ++m) {
+                mk = m + nl;
+                Cc[mk] = Cc[m];
+                ++i;
+                ++j;
+                T[j] = T[i] + per;
+            }
+        }
+    }
+    *n_io = nn;
+}
+
 /* fpintb, core:8058-8166 : integrals of the normalized B-splines over [x, y] */
 static void fpintb(const double *t, int n, double *bint, int nk1, double x, double y)
 {

@@ -123,6 +123,11 @@ void orc_spalde(const double *t, int32_t n, const double *c, int32_t k1, double 
 double orc_splint(const double *t, int32_t n, const double *c, int32_t k, double a, double b,
                   double *wrk);
 /* fourco core:1474-1520 with fpbfou 1947-2123, fpcsin 4636-4686: Fourier integrals of a cubic spline (fp_fourco_c) */
+/* cualde core:1062-1101 (fp_cualde_c), insert core:15064-15159 + fpinst 7961-8026 (fp_insert_c, in place) */
+void orc_cualde(int32_t idim, const double *t, int32_t n, const double *c, int32_t nc, int32_t k1, double u,
+                double *d, int32_t nd, int32_t *ier);
+void orc_insert(int32_t iopt, double *t, int32_t *n_io, double *c, int32_t k, double x, int32_t nest,
+                int32_t *ier);
 void orc_fourco(const double *t, int32_t n, const double *c, const double *alfa, int32_t m, double *ress,
                 double *resc, double *wrk1, double *wrk2, int32_t *ier);
 

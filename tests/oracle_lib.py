@@ -292,6 +292,30 @@ def splint(t, n, c, k, a, b):
     return float(v), wrk
 
 
+def cualde(idim, t, n, c, k1, u):
+    """orc_cualde (reference core:1062-1101); returns (d [k1][idim], ier)"""
+    t, c = (np.ascontiguousarray(v, dtype=np.float64) for v in (t, c))
+    d = np.zeros(k1 * idim)
+    ier = C.c_int32(0)
+    L = lib()
+    L.orc_cualde.restype = None
+    L.orc_cualde(C.c_int32(idim), _d(t), C.c_int32(n), _d(c), C.c_int32(c.size), C.c_int32(k1), C.c_double(u), _d(d),
+                 C.c_int32(d.size), C.byref(ier))
+    return d.reshape(k1, idim), ier.value
+
+
+def insert(iopt, t, n, c, k, x, nest):
+    """orc_insert (reference insert_inplace core:15138-15159); returns (t, n, c, ier) -- copies, length nest"""
+    tt, cc = np.zeros(nest), np.zeros(nest)
+    tt[:min(nest, len(t))] = np.asarray(t, dtype=np.float64)[:nest]
+    cc[:min(nest, len(c))] = np.asarray(c, dtype=np.float64)[:nest]
+    n_, ier = C.c_int32(int(n)), C.c_int32(0)
+    L = lib()
+    L.orc_insert.restype = None
+    L.orc_insert(C.c_int32(iopt), _d(tt), C.byref(n_), _d(cc), C.c_int32(k), C.c_double(x), C.c_int32(nest), C.byref(ier))
+    return tt, n_.value, cc, ier.value
+
+
 def fourco(t, n, c, alfa):
     """orc_fourco (reference core:1474-1520); returns (ress, resc, ier, wrk1, wrk2)"""
     t, c, alfa = (np.ascontiguousarray(v, dtype=np.float64) for v in (t, c, alfa))
