@@ -92,6 +92,7 @@ SYMBOLS = {
     "fp_fourco_c": (None, [_VP, _I32, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     "fp_cualde_c": (None, [_I32, _VP, _I32, _VP, _I32, _I32, _F64, _VP, _I32, _VP]),
     "fp_insert_c": (None, [_I32, _VP, _VP, _VP, _I32, _F64, _I32, _VP]),
+    "fp_sproot_c": (None, [_VP, _I32, _VP, _VP, _I32, _VP, _VP]),
     "fitpack_curve_c_fourier": (None, [_VP, _I32, _VP, _VP, _VP, _VP]),
     "fp_parcur_c": (None, [_I32, _I32, _I32, _I32, _VP, _I32, _VP, _VP, _VP, _VP, _I32, _VP, _I32, _VP, _VP,
                            _I32, _VP, _VP, _VP, _I32, _VP, _VP]),

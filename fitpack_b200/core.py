@@ -262,6 +262,17 @@ def insert(iopt, t, n, c, k, x, nest):
     return tt, n_.value, cc, ier_.value
 
 
+def sproot(t, n, c, mest):
+    """sproot (reference core:17962-18109) through fp_sproot_c; returns (zeros[:m], m, ier)."""
+    t, c = _f64(t), _f64(c)
+    z = np.zeros(max(int(mest), 1))
+    m_, ier_ = C.c_int32(0), C.c_int32(0)
+    lib().fp_sproot_c(_p(t), int(n), _p(c), _p(z), int(mest), C.addressof(m_), C.addressof(ier_))
+    if ier_.value <= FPB_ERR_CUDA:
+        raise FitpackB200Error("fp_sproot_c: %s" % lib().fpb_last_error().decode())
+    return z[:min(m_.value, int(mest))].copy(), m_.value, ier_.value
+
+
 def fourco(t, n, c, alfa):
     """fourco (reference core:1474-1520) through fp_fourco_c: the integrals of a cubic spline against sin(alfa x) and
     cos(alfa x) over its support; returns (ress, resc, ier, wrk1, wrk2)."""

@@ -437,6 +437,138 @@ __global__ void insert_kernel(int iopt, double *__restrict__ t, int *__restrict_
     *n_io = nn;
 }
 
+// ---- sproot: the zeros of a cubic spline (core:17962-18109; fpcuro core:5108-5198) ----
+// One thread walks the knot intervals as the reference does (the polynomial of an interval reuses its neighbour's end
+// values), solves each cubic in closed form + one Newton correction, sorts and removes duplicates.  pow / atan2 / cos
+// are CUDA's: zeros agree with the reference to rounding level (tolerance in the tests), not bit for bit.
+__device__ void fpcuro_dev(double a, double b, double c, double d, double *x, int &n)
+{
+    const double ovfl = 1.0e4, tent = 0.1;
+    const double pi3 = atan(1.0) / 0.75, e3 = tent / 0.3;
+    double a1 = fabs(a), b1 = fabs(b), c1 = fabs(c), d1 = fabs(d);
+    if (fmax(fmax(b1, c1), d1) < mul(a1, ovfl)) {
+        b1 = mul(b / a, e3);
+        c1 = c / a;
+        d1 = d / a;
+        const double q = sub(mul(c1, e3), mul(b1, b1));
+        const double r = add(mul(mul(b1, b1), b1), mul(sub(d1, mul(b1, c1)), 0.5));
+        const double disc = add(mul(mul(q, q), q), mul(r, r));
+        if (disc > 0.0) {
+            const double u = sqrt(disc), u1 = add(-r, u), u2 = sub(-r, u);
+            n = 1;
+            x[0] = sub(add(copysign(pow(fabs(u1), e3), u1), copysign(pow(fabs(u2), e3), u2)), b1);
+        } else {
+            const double u = copysign(sqrt(fabs(q)), r);
+            const double p3 = mul(atan2(sqrt(-disc), fabs(r)), e3);
+            const double u2 = add(u, u);
+            n = 3;
+            x[0] = sub(mul(-u2, cos(p3)), b1);
+            x[1] = sub(mul(u2, cos(sub(pi3, p3))), b1);
+            x[2] = sub(mul(u2, cos(add(pi3, p3))), b1);
+        }
+    } else if (fmax(c1, d1) < mul(b1, ovfl)) {
+        const double disc = sub(mul(c, c), mul(mul(4.0, b), d));
+        if (disc < 0.0) {
+            n = 0;
+            return;
+        }
+        n = 2;
+        const double u = sqrt(disc), bb = add(b, b);
+        x[0] = add(-c, u) / bb;
+        x[1] = sub(-c, u) / bb;
+    } else if (d1 < mul(c1, ovfl)) {
+        n = 1;
+        x[0] = -d / c;
+    } else {
+        n = 0;
+        return;
+    }
+    for (int i = 0; i < n; ++i) {
+        const double y = x[i];
+        const double f = add(mul(add(mul(add(mul(a, y), b), y), c), y), d);
+        const double df = add(mul(add(mul(mul(3.0, a), y), mul(2.0, b)), y), c);
+        const double step = (fabs(f) < mul(fabs(df), tent)) ? f / df : 0.0;
+        x[i] = sub(y, step);
+    }
+}
+
+__global__ void sproot_kernel(const double *__restrict__ t, int n, const double *__restrict__ c,
+                              double *__restrict__ zeros, int mest, int *__restrict__ m_out, int *__restrict__ ier)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    auto T = [&](int i) { return t[i - 1]; };
+    auto Cc = [&](int i) { return c[i - 1]; };
+    const int n4 = n - 4;
+    int m = 0;
+    double h1 = sub(T(4), T(3)), h2 = sub(T(5), T(4)), t1 = sub(T(4), T(2)), t2 = sub(T(5), T(3)), t3 = sub(T(6), T(4)),
+           t4 = sub(T(5), T(2)), t5 = sub(T(6), T(3));
+    double c1 = Cc(1), c2 = Cc(2), c3 = Cc(3);
+    double c4 = sub(c2, c1) / t4, c5 = sub(c3, c2) / t5;
+    double d4 = add(mul(h2, c1), mul(t1, c2)) / t4, d5 = add(mul(t3, c2), mul(h1, c3)) / t5;
+    double a0 = add(mul(h2, d4), mul(h1, d5)) / t2;
+    double ah = mul(3.0, add(mul(h2, c4), mul(h1, c5))) / t2;
+    bool z1 = !(ah < 0.0), nz1 = !z1;
+    *ier = IER_OK;
+    for (int l = 4; l <= n4; ++l) {
+        h1 = h2;
+        h2 = sub(T(l + 2), T(l + 1));
+        t1 = t2;
+        t2 = t3;
+        t3 = sub(T(l + 3), T(l + 1));
+        t4 = t5;
+        t5 = sub(T(l + 3), T(l));
+        c1 = c2;
+        c2 = c3;
+        c3 = Cc(l);
+        c4 = c5;
+        c5 = sub(c3, c2) / t5;
+        d4 = add(mul(h2, c1), mul(t1, c2)) / t4;
+        d5 = add(mul(h1, c3), mul(t3, c2)) / t5;
+        const double b0 = add(mul(h2, d4), mul(h1, d5)) / t2;
+        const double bh = mul(3.0, add(mul(h2, c4), mul(h1, c5))) / t2;
+        const double a1 = mul(ah, h1), b1 = mul(bh, h1);
+        const double a2 = sub(sub(mul(3.0, sub(b0, a0)), b1), mul(2.0, a1));
+        const double a3 = add(add(mul(2.0, sub(a0, b0)), b1), a1);
+        const bool z0 = !(a0 < 0.0), nz0 = !z0, z2 = !(a2 < 0.0), nz2 = !z2, z3 = !(b1 < 0.0), nz3 = !z3;
+        const bool z4 = !(add(mul(3.0, a3), a2) < 0.0), nz4 = !z4;
+        if (mul(a0, b0) <= 0.0 || ((z0 && ((nz1 && (z3 || (z2 && nz4))) || (nz2 && z3 && z4))) ||
+                                   (nz0 && ((z1 && (nz3 || (nz2 && z4))) || (z2 && nz3 && nz4))))) {
+            double y[3];
+            int j = 0;
+            fpcuro_dev(a3, a2, a1, a0, y, j);
+            for (int i = 0; i < j; ++i) {
+                if (y[i] < 0.0 || y[i] > 1.0) continue;
+                if (m >= mest) {
+                    *ier = IER_STORAGE;
+                    *m_out = m;
+                    return;
+                }
+                zeros[m++] = add(T(l), mul(h1, y[i]));
+            }
+        }
+        a0 = b0;
+        ah = bh;
+        z1 = z3;
+        nz1 = nz3;
+    }
+    if (m >= 2) {
+        for (int i = 1; i < m; ++i) {   // ascending (the result of fitpack_quicksort is order-unique)
+            const double v = zeros[i];
+            int j = i - 1;
+            for (; j >= 0 && zeros[j] > v; --j) zeros[j + 1] = zeros[j];
+            zeros[j + 1] = v;
+        }
+        const int j = m;
+        m = 1;
+        for (int i = 2; i <= j; ++i) {
+            if (fp_equal(zeros[i - 1], zeros[m - 1])) continue;
+            ++m;
+            zeros[m - 1] = zeros[i - 1];
+        }
+    }
+    *m_out = m;
+}
+
 // upload knots and coefficients of one spline into the engine's calculus buffers
 bool upload_spline(fpb_engine *eng, const double *t, const double *c, int n, double **dt, double **dc,
                    double **dw)
@@ -695,6 +827,52 @@ void fp_insert_c(FP_SIZE iopt, FP_REAL *t, FP_SIZE *n, FP_REAL *c, FP_SIZE k, FP
     *n = hni[0];
     std::memcpy(t, ht.data(), (size_t)hni[0] * 8);
     std::memcpy(c, hc.data(), (size_t)(hni[0] - k - 1) * 8);
+}
+
+// reference: src/fitpack_core_c.f90:226-233 -> sproot core:17962-18109
+void fp_sproot_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_REAL *zeros, FP_SIZE mest, FP_SIZE *m, FP_FLAG *ier)
+{
+    *m = 0;
+    // data checks, core:17990-18006
+    if (n < 8) {
+        *ier = FPB_INSUFFICIENT_KNOTS;
+        return;
+    }
+    *ier = FPB_INPUT_ERROR;
+    for (int i = 0, j = n - 1; i < 3; ++i, --j) {
+        if (t[i] > t[i + 1]) return;
+        if (t[j] < t[j - 1]) return;
+    }
+    for (int i = 3; i < n - 4; ++i)
+        if (t[i] >= t[i + 1]) return;
+    HostApiLock api_lock(-1);
+    fpb_engine *eng = default_engine(-1);
+    if (!eng) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    DevSel g(eng->device);
+    double *dt, *dc, *dw;
+    DevBuf *B = eng->calc;
+    const size_t mz = (size_t)std::max(mest, 1);
+    if (!upload_spline(eng, t, c, n, &dt, &dc, &dw) || !B[3].reserve(mz * 8) || !B[4].reserve(64)) {
+        *ier = FPB_ERR_ALLOC;
+        return;
+    }
+    double *dz = B[3].as<double>();
+    int *dm = B[4].as<int>();
+    sproot_kernel<<<1, 32, 0, eng->stream>>>(dt, n, dc, dz, mest, dm, dm + 1);
+    eng->launches++;
+    int hm[2] = {0, FPB_INPUT_ERROR};
+    if (!cuda_ok(cudaMemcpyAsync(hm, dm, 8, cudaMemcpyDeviceToHost, eng->stream), "D2H m") ||
+        !cuda_ok(cudaStreamSynchronize(eng->stream), "sync")) {
+        *ier = FPB_ERR_CUDA;
+        return;
+    }
+    *m = hm[0];
+    *ier = hm[1];
+    if (hm[0] > 0 && !cuda_ok(cudaMemcpy(zeros, dz, (size_t)std::min(hm[0], mest) * 8, cudaMemcpyDeviceToHost), "D2H zeros"))
+        *ier = FPB_ERR_CUDA;
 }
 
 }  // extern "C"

@@ -23,7 +23,7 @@ module fitpack_b200
                                             FPB_ERR_ARG = -101, FPB_ERR_ALLOC = -102
 
    public :: fp_curfit_c, fp_splev_c, fp_curfit_batch_c, fp_splev_batch_c
-   public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c, fp_fourco_c, fp_cualde_c, fp_insert_c
+   public :: fp_regrid_c, fp_bispev_c, fp_splder_c, fp_spalde_c, fp_splint_c, fp_fourco_c, fp_cualde_c, fp_insert_c, fp_sproot_c
    public :: fp_parcur_c, fp_curev_c, fp_parcur_batch_c, fp_percur_c, fp_percur_batch_c
    public :: fitpack_curve_c_comm_size, fitpack_curve_c_comm_pack, fitpack_curve_c_comm_expand
    public :: fp_curfit_batch_dev_c, fp_curfit_shared_dev_c, fp_splev_batch_dev_c
@@ -212,6 +212,14 @@ module fitpack_b200
          integer(FP_SIZE), intent(inout)     :: n
          integer(FP_FLAG), intent(out)       :: ier
       end subroutine fp_insert_c
+      subroutine fp_sproot_c(t,n,c,zeros,mest,m,ier) bind(C,name="fp_sproot_c")
+         import
+         integer(FP_SIZE), intent(in), value :: n,mest
+         integer(FP_SIZE), intent(out)       :: m
+         integer(FP_FLAG), intent(out)       :: ier
+         real   (FP_REAL), intent(in)        :: t(n),c(n)
+         real   (FP_REAL), intent(out)       :: zeros(mest)
+      end subroutine fp_sproot_c
 
       ! (B) batches of independent curves, host arrays.  Fortran arrays x(m,nbatch) are exactly
       ! the "curve-major" [nbatch][m] C layout the library expects.

@@ -309,6 +309,10 @@ void fp_fourco_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, const FP_REAL *a
 void fp_cualde_c(FP_SIZE idim, const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_SIZE nc, FP_SIZE k1, FP_REAL u,
                  FP_REAL *d, FP_SIZE nd, FP_FLAG *ier);
 void fp_insert_c(FP_SIZE iopt, FP_REAL *t, FP_SIZE *n, FP_REAL *c, FP_SIZE k, FP_REAL x, FP_SIZE nest, FP_FLAG *ier);
+/* sproot (src/fitpack_core_c.f90:226-233 -> core:17962-18109, fpcuro 5108-5198): the zeros of a CUBIC spline in
+   [t(4), t(n-3)], ascending, duplicates removed; m = their number; ier = 13 for n < 8, 10 for invalid knots, 1 when more
+   than mest zeros exist (the first mest found are returned).  pow / atan2 / cos are CUDA's: rounding-level agreement. */
+void fp_sproot_c(const FP_REAL *t, FP_SIZE n, const FP_REAL *c, FP_REAL *zeros, FP_SIZE mest, FP_SIZE *m, FP_FLAG *ier);
 
 /* ---------------------------------------------------------- gridded surfaces -- */
 /*

@@ -1766,6 +1766,156 @@ void orc_fourco(const double *t, int32_t n, const double *c, const double *alfa,
     }
 }
 
+/* ------------------------------------------------------------------ sproot: zeros of a cubic spline */
+/* fpcuro, core:5108-5198 : real zeros of a x^3 + b x^2 + c x + d, one Newton correction each */
+static void fpcuro(double a, double b, double c, double d, double *x, int *n)
+{
+    const double ovfl = 1.0e4, tent = 0.1;
+    const double pi3 = atan(1.0) / 0.75, e3 = tent / 0.3;
+    double a1 = fabs(a), b1 = fabs(b), c1 = fabs(c), d1 = fabs(d), df, disc, f, p3, q, r, step, u, u1, u2, y;
+    double mx = b1;
+    int i;
+    if (c1 > mx) mx = c1;
+    if (d1 > mx) mx = d1;
+    if (mx < a1 * ovfl) {
+        b1 = b / a * e3;
+        c1 = c / a;
+        d1 = d / a;
+        q = c1 * e3 - b1 * b1;
+        r = b1 * b1 * b1 + (d1 - b1 * c1) * 0.5;
+        disc = q * q * q + r * r;
+        if (disc > 0.0) {
+            u = sqrt(disc);
+            u1 = -r + u;
+            u2 = -r - u;
+            *n = 1;
+            x[0] = copysign(pow(fabs(u1), e3), u1) + copysign(pow(fabs(u2), e3), u2) - b1;
+        } else {
+            u = copysign(sqrt(fabs(q)), r);
+            p3 = atan2(sqrt(-disc), fabs(r)) * e3;
+            u2 = u + u;
+            *n = 3;
+            x[0] = -u2 * cos(p3) - b1;
+            x[1] = u2 * cos(pi3 - p3) - b1;
+            x[2] = u2 * cos(pi3 + p3) - b1;
+        }
+    } else if ((c1 > d1 ? c1 : d1) < b1 * ovfl) {
+        disc = c * c - 4.0 * b * d;
+        if (disc < 0.0) { *n = 0; return; }
+        *n = 2;
+        u = sqrt(disc);
+        b1 = b + b;
+        x[0] = (-c + u) / b1;
+        x[1] = (-c - u) / b1;
+    } else if (d1 < c1 * ovfl) {
+        *n = 1;
+        x[0] = -d / c;
+    } else {
+        *n = 0;
+        return;
+    }
+    for (i = 0; i < *n; ++i) {
+        y = x[i];
+        f = ((a * y + b) * y + c) * y + d;
+        df = (3.0 * a * y + 2.0 * b) * y + c;
+        step = (fabs(f) < fabs(df) * tent) ? f / df : 0.0;
+        x[i] = y - step;
+    }
+}
+
+/* sproot, core:17962-18109 (argument list of fp_sproot_c) */
+void orc_sproot(const double *t, int32_t n, const double *c, double *zeros, int32_t mest, int32_t *m_out,
+                int32_t *ier)
+{
+    const double *T = t - 1, *Cc = c - 1;
+    double ah, a0, a1, a2, a3, bh, b0, b1, c1, c2, c3, c4, c5, d4, d5, h1, h2, t1, t2, t3, t4, t5, y[3];
+    int i, j, l, n4 = n - 4, m = 0, z0, z1, z2, z3, z4, nz0, nz1, nz2, nz3, nz4;
+    *m_out = 0;
+    if (n < 8) { *ier = 13; return; }
+    *ier = IER_INPUT;
+    j = n;
+    for (i = 1; i <= 3; ++i) {
+        if (T[i] > T[i + 1]) return;
+        if (T[j] < T[j - 1]) return;
+        --j;
+    }
+    for (i = 4; i <= n4; ++i)
+        if (T[i] >= T[i + 1]) return;
+    *ier = IER_OK;
+    h1 = T[4] - T[3];
+    h2 = T[5] - T[4];
+    t1 = T[4] - T[2];
+    t2 = T[5] - T[3];
+    t3 = T[6] - T[4];
+    t4 = T[5] - T[2];
+    t5 = T[6] - T[3];
+    c1 = Cc[1];
+    c2 = Cc[2];
+    c3 = Cc[3];
+    c4 = (c2 - c1) / t4;
+    c5 = (c3 - c2) / t5;
+    d4 = (h2 * c1 + t1 * c2) / t4;
+    d5 = (t3 * c2 + h1 * c3) / t5;
+    a0 = (h2 * d4 + h1 * d5) / t2;
+    ah = 3.0 * (h2 * c4 + h1 * c5) / t2;
+    z1 = !(ah < 0.0);
+    nz1 = !z1;
+    for (l = 4; l <= n4; ++l) {
+        h1 = h2;
+        h2 = T[l + 2] - T[l + 1];
+        t1 = t2;
+        t2 = t3;
+        t3 = T[l + 3] - T[l + 1];
+        t4 = t5;
+        t5 = T[l + 3] - T[l];
+        c1 = c2;
+        c2 = c3;
+        c3 = Cc[l];
+        c4 = c5;
+        c5 = (c3 - c2) / t5;
+        d4 = (h2 * c1 + t1 * c2) / t4;
+        d5 = (h1 * c3 + t3 * c2) / t5;
+        b0 = (h2 * d4 + h1 * d5) / t2;
+        bh = 3.0 * (h2 * c4 + h1 * c5) / t2;
+        a1 = ah * h1;
+        b1 = bh * h1;
+        a2 = 3.0 * (b0 - a0) - b1 - 2.0 * a1;
+        a3 = 2.0 * (a0 - b0) + b1 + a1;
+        z0 = !(a0 < 0.0); nz0 = !z0;
+        z2 = !(a2 < 0.0); nz2 = !z2;
+        z3 = !(b1 < 0.0); nz3 = !z3;
+        z4 = !(3.0 * a3 + a2 < 0.0); nz4 = !z4;
+        if (a0 * b0 <= 0.0 || ((z0 && ((nz1 && (z3 || (z2 && nz4))) || (nz2 && z3 && z4))) ||
+                               (nz0 && ((z1 && (nz3 || (nz2 && z4))) || (z2 && nz3 && nz4))))) {
+            fpcuro(a3, a2, a1, a0, y, &j);
+            for (i = 0; i < j; ++i) {
+                if (y[i] < 0.0 || y[i] > 1.0) continue;
+                if (m >= mest) { *ier = IER_STORAGE; *m_out = m; return; }
+                zeros[m++] = T[l] + h1 * y[i];
+            }
+        }
+        a0 = b0;
+        ah = bh;
+        z1 = z3;
+        nz1 = nz3;
+    }
+    *m_out = m;
+    if (m < 2) return;
+    for (i = 1; i < m; ++i) {                       /* ascending order (fitpack_quicksort: the result is order-unique) */
+        double v = zeros[i];
+        for (j = i - 1; j >= 0 && zeros[j] > v; --j) zeros[j + 1] = zeros[j];
+        zeros[j + 1] = v;
+    }
+    j = m;
+    m = 1;
+    for (i = 2; i <= j; ++i) {
+        if (orc_equal(zeros[i - 1], zeros[m - 1])) continue;
+        ++m;
+        zeros[m - 1] = zeros[i - 1];
+    }
+    *m_out = m;
+}
+
 /* Fortran NORM2 as gfortran evaluates it (scaled form of libgfortran's norm2_r8 / the
    inline expansion in trans-intrinsic.cc); netlib parcur uses sqrt(sum d**2). */
 static double f_norm2(const double *v, int nd)

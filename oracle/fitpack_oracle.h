@@ -128,6 +128,9 @@ void orc_cualde(int32_t idim, const double *t, int32_t n, const double *c, int32
                 double *d, int32_t nd, int32_t *ier);
 void orc_insert(int32_t iopt, double *t, int32_t *n_io, double *c, int32_t k, double x, int32_t nest,
                 int32_t *ier);
+/* sproot core:17962-18109 with fpcuro 5108-5198 (fp_sproot_c): the zeros of a cubic spline in [t(4), t(n-3)] */
+void orc_sproot(const double *t, int32_t n, const double *c, double *zeros, int32_t mest, int32_t *m_out,
+                int32_t *ier);
 void orc_fourco(const double *t, int32_t n, const double *c, const double *alfa, int32_t m, double *ress,
                 double *resc, double *wrk1, double *wrk2, int32_t *ier);
 

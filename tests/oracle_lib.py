@@ -316,6 +316,17 @@ def insert(iopt, t, n, c, k, x, nest):
     return tt, n_.value, cc, ier.value
 
 
+def sproot(t, n, c, mest):
+    """orc_sproot (reference core:17962-18109); returns (zeros[:m], m, ier)"""
+    t, c = (np.ascontiguousarray(v, dtype=np.float64) for v in (t, c))
+    z = np.zeros(max(mest, 1))
+    m, ier = C.c_int32(0), C.c_int32(0)
+    L = lib()
+    L.orc_sproot.restype = None
+    L.orc_sproot(_d(t), C.c_int32(n), _d(c), _d(z), C.c_int32(mest), C.byref(m), C.byref(ier))
+    return z[:m.value].copy(), m.value, ier.value
+
+
 def fourco(t, n, c, alfa):
     """orc_fourco (reference core:1474-1520); returns (ress, resc, ier, wrk1, wrk2)"""
     t, c, alfa = (np.ascontiguousarray(v, dtype=np.float64) for v in (t, c, alfa))
