@@ -393,6 +393,7 @@ def main():
 
     # ---------------------------------------------------------------- one curve per call (the reference's call pattern)
     if rank == 0 and not args.no_e2e:
+      try:
         L1 = fitpack_b200.lib()
         xs1, ys1 = synth_host(np, 0, 1, M)
         x1, y1 = np.ascontiguousarray(xs1[0]), np.ascontiguousarray(ys1[0])
@@ -420,6 +421,8 @@ def main():
             import oracle_lib as O1
             roof["single_call"]["cpu_port_ms"] = lat(
                 lambda: O1.curfit(0, x1, y1, None, float(x1[0]), float(x1[-1]), K, S, NEST), 50)
+      except Exception as exc:   # a secondary record must not cost the headline line
+        roof["single_call"] = {"error": repr(exc)}
 
     # ---------------------------------------------------------------- parity sample on the SAME batch
     parity = None
