@@ -14,7 +14,13 @@
  *
  * PARITY PIN STATUS: no Fortran compiler in this image => the reference binary
  * cannot be produced; pinned against the reference's own test assertions and
- * scipy's C translation of the same netlib algorithm (tests/golden/).
+ * scipy's C translation of the same netlib algorithm (tests/golden/); the places
+ * where the reference departs from netlib by hand-derived expectations
+ * (tests/deviation_cases.py).  Known-answer tests of the reference itself that
+ * carry numbers are used where they exist: mnfour (exact Fourier integrals,
+ * test/fitpack_tests.f90:1536-1680) for fourco; insert and sproot equal scipy's
+ * netlib routines bit for bit.  oracle/ref_recipe/ builds the reference with
+ * gfortran and regenerates the goldens where a compiler is available.
  */
 #include "fitpack_oracle.h"
 
