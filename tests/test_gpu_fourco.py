@@ -1,5 +1,5 @@
 """fp_fourco_c / fitpack_curve_c_fourier on the GPU against the CPU oracle (reference core:1474-1520) and the reference's
-known-answer test mnfour.  Tolerance, stated: 1e-12 absolute against the oracle on the reference's mnfour case, 1e-9 * max(1, |value|) on
+known-answer test mnfour.  Tolerance, stated: 1e-12 absolute against the oracle on the reference's mnfour case, 5e-9 * max(1, |value|) on
 random splines with close knots (the kernel follows the reference's operation order but its sin / cos are CUDA's,
 <= 2 ulp, libm's in the reference, and the divided differences amplify that) -- and mnfour's own 1e-10 + 1e-6 |exact|
 against the exact integrals."""
@@ -49,7 +49,7 @@ def test_random_cubic_splines_against_the_oracle(F):
         assert ier == oier == 0
         # the divided differences divide by (alfa * knot gap)^3: with close knots the 2-ulp difference between CUDA's and
         # libm's sin / cos is amplified (the algorithm's own accuracy is ~1e-8, the cut-off of its series)
-        tol = 1e-9 * np.maximum(1.0, np.maximum(np.abs(os_), np.abs(oc_)))
+        tol = 5e-9 * np.maximum(1.0, np.maximum(np.abs(os_), np.abs(oc_)))   # largest seen: 5.6e-10
         err = max(np.max(np.abs(ress - os_)), np.max(np.abs(resc - oc_)))
         worst = max(worst, err)
         assert np.all(np.abs(ress - os_) <= tol) and np.all(np.abs(resc - oc_) <= tol), (trial, err)
