@@ -3,6 +3,8 @@ include/fitpack_b200.h declares.  No compute call is made (no GPU here)."""
 import os
 import re
 
+import pytest
+
 import fitpack_b200
 from fitpack_b200 import _lib
 
@@ -67,3 +69,26 @@ def test_product_does_not_reference_the_oracle():
                 if re.search(r"oracle_lib|fitpack_oracle|orc_curfit|orc_splev", txt):
                     bad.append(f)
     assert not bad, bad
+
+
+REF_INC = "/root/reference/include"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INC), reason="reference headers not mounted")
+def test_every_function_of_the_reference_handle_header_is_exported():
+    """include/fitpack_curves_c.h of the reference declares 19 fitpack_curve_c_* functions: all must be exported by
+    libfitpack_b200.so; of the flat layer (include/fitpack_core_c.h) every 1-D curve routine except clocur and the
+    constrained fitters, plus regrid / bispev"""
+    import re
+    import subprocess
+    import fitpack_b200
+    lib = fitpack_b200.ensure_built()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    handle = set(re.findall(r"\b(fitpack_curve_c_[a-z_]+)\s*\(", open(os.path.join(REF_INC, "fitpack_curves_c.h")).read()))
+    assert len(handle) == 19 and not (handle - exported), sorted(handle - exported)
+    flat = set(re.findall(r"\b(fp_[a-z]+_c|FITPACK_SUCCESS_c|fitpack_message_c)\s*\(",
+                          open(os.path.join(REF_INC, "fitpack_core_c.h")).read()))
+    not_provided = {"fp_bispeu_c", "fp_clocur_c", "fp_cocosp_c", "fp_concon_c", "fp_parder_c", "fp_parsur_c",
+                    "fp_pogrid_c", "fp_polar_c", "fp_spgrid_c", "fp_sphere_c", "fp_surfit_c"}   # DESIGN.md section 8
+    assert flat - exported == not_provided, sorted(flat - exported)
